@@ -1,0 +1,180 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) here.
+
+    python oracle/refharness/gen_golden.py            # all cases
+    python oracle/refharness/gen_golden.py mass_td3   # one case
+
+Each file freezes, for a handful of episodes with i.i.d. uniform meta-actions:
+  st_<field>[S, MAXV]   full vehicle state before every policy step and after the last one of
+                        each episode (S = sum over episodes of T_ep + 1), see ref_loader.export_state
+  st_{steps,time,n_veh,n_cav,n_merge}[S]
+  ep_start[n_ep+1]      offsets into the S axis (episode j owns states ep_start[j]..ep_start[j+1]-1)
+  act[T, MAXV] int8     meta-actions applied at step t (-1 padding)
+  row_of_step[T]        index on the S axis of the pre-state of step t (post-state is row+1)
+  obs[T, MAXV, n_s], reward[T], done[T], agents_rewards/regional_rewards/agents_dones[T, MAXV],
+  average_speed/traffic_speed/min_headway/merge_percent[T]       -- MergeEnv.step return values
+  sh_<field>[T, 3, MAXV] per-sub-step shield record (ran, leader, front_adj, rear_adj,
+                        constrain_adj, active, is_lc_safe, safe_acc, safe_steer, nom_acc, nom_steer)
+  qp_{a,c_lead,c_adj,has_adj,lo,hi,u,active}[Q]                  -- every QP the reference posed
+  config (json)
+
+Test infrastructure; the committed fixtures are what travels to the GPU box.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import ref_loader as rl  # noqa: E402
+
+OUT_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "tests", "golden")
+
+# name -> (config overrides, reset seeds, action-rng seed)
+CASES = {
+    # BASELINE configs[0] sibling on the LC env (test-configs_marl-cav-heading-unsafe.ini)
+    "unsafe_td1": (dict(safety_guarantee="none", traffic_density=1, HEADWAY_TIME=1.2), [0, 7, 11], 100),
+    "unsafe_td3": (dict(safety_guarantee="none", traffic_density=3, HEADWAY_TIME=1.2), [3, 4], 101),
+    "unsafe_td2_mixed": (dict(safety_guarantee="none", traffic_density=2, traffic_type="mixed",
+                              mixed_traffic=True), [5, 6, 21], 102),
+    # BASELINE configs[1]: marl_cav-heading-t_headway-cbf-avs_cint.ini
+    "hss_td3": (dict(safety_guarantee="cbf-avs_cint", traffic_density=3), [0, 20], 103),
+    "hss_td3_mixed": (dict(safety_guarantee="cbf-avs_cint", traffic_density=3, traffic_type="mixed",
+                           mixed_traffic=True), [40, 60], 104),
+    # BASELINE configs[2]: marl_cav-heading-t_headway-cbf-cav.ini
+    "mass_td1": (dict(safety_guarantee="cbf-cav", traffic_density=1, mixed_traffic=False), [0, 25, 50], 105),
+    # BASELINE configs[3]: marl_cav-heading-t_headway-cbf-cav-td3-srew.ini
+    "mass_td3_srew": (dict(safety_guarantee="cbf-cav", traffic_density=3, mixed_traffic=False,
+                           agent_reward="srew", HIGH_SPEED_REWARD=4, HEADWAY_COST=1, MERGING_LANE_COST=8),
+                      [0, 75], 106),
+    # BASELINE configs[4] mixed variant: marl_cav-heading-t_headway-cbf-cav-mixed.ini
+    "mass_td3_mixed": (dict(safety_guarantee="cbf-cav", traffic_density=3, mixed_traffic=True,
+                            traffic_type="mixed"), [100, 125], 107),
+    # marl_cav-heading-t_headway-cbf-cav-mixed-mrew.ini
+    "mass_td2_mixed_mrew": (dict(safety_guarantee="cbf-cav", traffic_density=2, mixed_traffic=True,
+                                 traffic_type="mixed", agent_reward="mrew", HIGH_SPEED_REWARD=4,
+                                 HEADWAY_COST=1, MERGING_LANE_COST=8), [150, 175], 108),
+}
+
+SH_I = ("ran", "leader", "front_adj", "rear_adj", "constrain_adj", "active", "is_lc_safe")
+SH_F = ("safe_acc", "safe_steer", "nom_acc", "nom_steer")
+
+
+def run_case(name):
+    overrides, seeds, aseed = CASES[name]
+    env = rl.make_env(**overrides)
+    rl.drain_shield_log()
+    M = rl.MAXV
+    n_s = env.n_s
+    states, ep_start, acts, rows = [], [0], [], []
+    outs = {k: [] for k in ("obs", "reward", "done", "agents_rewards", "regional_rewards", "agents_dones",
+                            "average_speed", "traffic_speed", "min_headway", "merge_percent")}
+    sh = {k: [] for k in SH_I + SH_F}
+    qps = []
+    arng = np.random.RandomState(aseed)
+    for seed in seeds:
+        env.reset(is_training=False, testing_seeds=seed)
+        rl.drain_shield_log()
+        done = False
+        while not done:
+            st = rl.export_state(env)
+            rows.append(len(states))
+            states.append(st)
+            n = int(st["n_cav"])
+            a = arng.randint(0, 5, size=n)
+            obs, reward, done, info = env.step(tuple(int(x) for x in a))
+            o = rl.step_outputs(env, obs, reward, done, info)
+            ap = np.full(M, -1, np.int8)
+            ap[:n] = a
+            acts.append(ap)
+            op = np.zeros((M, n_s))
+            op[:n] = o["obs"]
+            outs["obs"].append(op)
+            for k in ("agents_rewards", "regional_rewards", "agents_dones"):
+                p = np.zeros(M, o[k].dtype)
+                p[:n] = o[k]
+                outs[k].append(p)
+            for k in ("reward", "done", "average_speed", "traffic_speed", "min_headway", "merge_percent"):
+                outs[k].append(o[k])
+            # shield records of this policy step, split by sub-step (order of execution per sub-step:
+            # each CAV at most once, so a repeated vehicle id starts a new sub-step)
+            log = rl.drain_shield_log()
+            rec_i = {k: np.full((3, M), -1 if k in ("leader", "front_adj", "rear_adj") else 0, np.int32)
+                     for k in SH_I}
+            rec_f = {k: np.zeros((3, M)) for k in SH_F}
+            # sub-step index: shield is skipped while len(state_hist) < 2, i.e. sub-steps 0,1 of the episode
+            first_sub = 2 if int(st["steps"]) == 0 else 0
+            sub, seen = first_sub, set()
+            for e in log:
+                if e["veh"] in seen:
+                    sub, seen = sub + 1, set()
+                seen.add(e["veh"])
+                assert sub < 3, (name, seed, sub)
+                v = e["veh"]
+                rec_i["ran"][sub, v] = 1
+                for k in ("leader", "front_adj", "rear_adj", "constrain_adj", "active", "is_lc_safe"):
+                    rec_i[k][sub, v] = int(e[k])
+                for k in SH_F:
+                    rec_f[k][sub, v] = e[k]
+                q = e["qp"]
+                qps.append((q["a"], q["c_lead"], q["c_adj"] if q["c_adj"] is not None else 0.0,
+                            float(q["c_adj"] is not None), q["lo"], q["hi"], q["u"], float(q["active"])))
+            for k in SH_I:
+                sh[k].append(rec_i[k])
+            for k in SH_F:
+                sh[k].append(rec_f[k])
+        states.append(rl.export_state(env))
+        ep_start.append(len(states))
+    data = {}
+    for k in rl.F64_FIELDS + rl.I32_FIELDS:
+        data["st_" + k] = np.stack([s[k] for s in states])
+    for k in ("steps", "time", "n_veh", "n_cav", "n_merge"):
+        data["st_" + k] = np.array([s[k] for s in states], np.int32)
+    data["ep_start"] = np.array(ep_start, np.int32)
+    data["act"] = np.stack(acts)
+    data["row_of_step"] = np.array(rows, np.int32)
+    for k, v in outs.items():
+        data[k] = np.stack(v) if np.ndim(v[0]) else np.array(v)
+    for k in SH_I + SH_F:
+        data["sh_" + k] = np.stack(sh[k])
+    q = np.array(qps, np.float64).reshape(-1, 8)
+    for j, k in enumerate(("a", "c_lead", "c_adj", "has_adj", "lo", "hi", "u", "active")):
+        data["qp_" + k] = q[:, j]
+    cfg = dict(rl.DEFAULT_ENV_CONFIG, **overrides)
+    cfg["n_s"] = n_s
+    cfg["seeds"] = seeds
+    data["config"] = np.array(json.dumps(cfg))
+    os.makedirs(OUT_DIR, exist_ok=True)
+    path = os.path.join(OUT_DIR, name + ".npz")
+    np.savez_compressed(path, **data)
+    T = len(acts)
+    crashed = int(np.sum(data["st_crashed"][np.array(ep_start[1:]) - 1].max(axis=1) > 0))
+    print("%-22s episodes=%d steps=%d qps=%d crashed_eps=%d vetoes=%d active=%d size=%.0fKB" % (
+        name, len(seeds), T, len(qps), crashed,
+        int(np.sum((data["sh_ran"] == 1) & (data["sh_is_lc_safe"] == 0))),
+        int(np.sum(data["sh_active"] > 0)), os.path.getsize(path) / 1024))
+
+
+def check_geometry():
+    """The constants our engines hard-code (SURVEY.md §8 'Fixed scenario constants')."""
+    env = rl.make_env()
+    env.reset()
+    net = env.road.network
+    expect = {("a", "b", 0): (0, 0, 320), ("b", "c", 0): (320, 0, 100), ("b", "c", 1): (320, 4, 100),
+              ("c", "d", 0): (420, 0, 1000), ("j", "k", 0): (0, 10.5, 220), ("k", "b", 0): (220, 7.25, 100)}
+    for l, (sx, sy, ln) in expect.items():
+        lane = net.get_lane(l)
+        assert lane.start[0] == sx and lane.start[1] == sy and lane.length == ln, (l, lane.start, lane.length)
+        assert lane.direction[0] == 1.0 and lane.direction[1] == 0.0 and lane.heading == 0.0
+    kb = net.get_lane(("k", "b", 0))
+    assert kb.amplitude == 3.25 and kb.pulsation == 2 * np.pi / 200 and kb.phase == np.pi / 2
+    ob = env.road.objects[0]
+    assert ob.position[0] == 420.0 and ob.position[1] == 4.0 and len(env.road.objects) == 1
+
+
+if __name__ == "__main__":
+    check_geometry()
+    names = sys.argv[1:] or list(CASES)
+    for nm in names:
+        run_case(nm)
