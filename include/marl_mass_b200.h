@@ -1,0 +1,144 @@
+/* marl_mass_b200.h — C ABI of the B200-native batched merge environment + HSS/MASS CBF shields.
+ *
+ * The reference (hkbharath/MARL-MASS) is pure Python and has no FFI; its boundary for this path is two
+ * Python call surfaces.  Each entry point below names the reference interface it replaces
+ * (paths relative to the reference tree).  The Python host (marl-mass_b200/env.py) binds these with ctypes;
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions: every function returns 0 on success and a negative mm_status on failure, never throws;
+ * mm_last_error() gives the text.  A handle owns all of its device memory.  Kernels are enqueued on the
+ * caller's stream (a cudaStream_t passed as void*; NULL = default stream) with no implicit synchronisation,
+ * except the *_host entry points, which return after the results are in the host buffers.
+ * One host thread per handle.
+ *
+ * Host-side state/diagnostic arrays are env-major, [n_envs][MM_MAXV] per vehicle field, slot = index in the
+ * reference's road.vehicles (CAVs first, which is also controlled_vehicles order and the vehicle id).
+ */
+#ifndef MARL_MASS_B200_H
+#define MARL_MASS_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MM_MAXV 12          /* vehicle slots per env (reference max is 11: td3 = 6 CAV + 5 HDV) */
+#define MM_OBS_ROWS 5       /* KinematicLCObservation vehicles_count (observation.py:132) */
+#define MM_OBS_FEATS 6      /* presence,x,y,vx,vy,heading (observation.py:232) */
+#define MM_NS 30            /* MergeEnvLCMARL.n_s (merge_env_v1.py:413) */
+#define MM_NA 5             /* n_a: LANE_LEFT, IDLE, LANE_RIGHT, FASTER, SLOWER (action.py:141-147) */
+
+typedef enum { MM_OK = 0, MM_ERR_ARG = -1, MM_ERR_CUDA = -2, MM_ERR_STATE = -3 } mm_status;
+
+enum { MM_KIND_NONE = 0, MM_KIND_CAV = 1, MM_KIND_HDV = 2 };
+enum { MM_SHIELD_NONE = 0, MM_SHIELD_HSS = 1, MM_SHIELD_MASS = 2 };
+enum { MM_REW_DEFAULT = 0, MM_REW_SREW = 1, MM_REW_MREW = 2 };
+enum { MM_TRAFFIC_CAV = 0, MM_TRAFFIC_MIXED = 1 };
+enum { MM_NB_NONE = -1, MM_NB_OBSTACLE = -2 };
+/* QP active-set code reported per shield solve */
+enum { MM_ACT_LEAD = 1, MM_ACT_UPPER = 2, MM_ACT_LOWER = 4, MM_ACT_ADJ = 8, MM_ACT_SLACK = 16 };
+
+/* Replaces: env.config[...] keys set by run_mappo.py:145-171 and the class globals CBFType.GAMMA_B / TAU
+ * (run_mappo.py:137-139).  As in the reference, a changed config is picked up by the next reset. */
+typedef struct {
+    int32_t shield;          /* safety_guarantee: none -> NONE; cbf-avs_cint|hss|av|avs -> HSS; cbf-cav|mass -> MASS */
+    int32_t reward_kind;     /* agent_reward: default | srew | mrew */
+    int32_t traffic_density; /* 1..3 (merge_env_v1.py:180-211) */
+    int32_t traffic_type;    /* cav (all vehicles are CAVs) | mixed (HDVs are IDMVehicleHist) */
+    int32_t duration_steps;  /* duration * policy_frequency (100) */
+    int32_t substeps;        /* simulation_frequency // policy_frequency (3) */
+    double dt;               /* 1 / simulation_frequency */
+    double eta;              /* cbf_eta -> CBFType.GAMMA_B */
+    double tau;              /* HEADWAY_TIME -> CBFType.TAU */
+    double collision_reward, high_speed_reward, headway_cost, headway_time, merging_lane_cost;
+} mm_config;
+
+typedef struct mm_env mm_env;
+
+/* Host mirror of the full per-env state, for teacher forcing and checkpointing.
+ * Replaces: nothing in the reference (it never checkpoints env state); fields follow
+ * Vehicle / ControlledVehicle / MDPLCVehicle / IDMVehicleHist attributes. */
+typedef struct {
+    double *x, *y, *heading, *speed, *target_speed, *gvx, *rec1_x, *rec1_vx, *rec2_x, *rec2_vx,
+           *act_steer, *act_acc, *safe_steer, *safe_acc, *timer, *min_headway;     /* [n_envs][MM_MAXV] */
+    int32_t *kind, *lane, *target_lane, *speed_index, *crashed, *hl_action, *hist_len, *fg_set,
+            *is_collaborating, *is_lc_safe, *collaborate_adj;                        /* [n_envs][MM_MAXV] */
+    int32_t *n_veh, *n_cav, *n_merge, *steps, *time;                                 /* [n_envs] */
+} mm_state_host;
+
+/* Device pointers of the step outputs (valid until mm_destroy; contents valid after the step's stream work).
+ * Replaces the return values of MergeEnv.step (merge_env_v1.py:126-166) and AbstractEnv.step's info dict
+ * (abstract.py:489-498). */
+typedef struct {
+    float *obs;               /* [n_envs][MM_MAXV][MM_NS]; rows >= n_agents are zero */
+    float *reward;            /* [n_envs] mean of local rewards (merge_env_v1.py:517-524) */
+    uint8_t *done;            /* [n_envs] _is_terminal (merge_env_v1.py:168-172) */
+    float *agents_rewards;    /* [n_envs][MM_MAXV] info["agents_rewards"] */
+    float *regional_rewards;  /* [n_envs][MM_MAXV] info["regional_rewards"] */
+    uint8_t *agents_dones;    /* [n_envs][MM_MAXV] info["agents_dones"] */
+    float *average_speed;     /* [n_envs] info["average_speed"] */
+    float *traffic_speed;     /* [n_envs] info["traffic_speed"] */
+    float *min_headway;       /* [n_envs] info["min_headway"] */
+    float *merge_percent;     /* [n_envs] info["merge_percent"] at done, else -1 */
+    int32_t *n_agents;        /* [n_envs] len(env.controlled_vehicles) */
+    int8_t *actions;          /* [n_envs][MM_MAXV] device-side action buffer read by mm_step(actions=NULL) */
+} mm_buffers;
+
+/* Host arrays receiving the per-sub-step shield record of the last mm_step, [n_envs][3][MM_MAXV].
+ * Replaces: safe_status/safe_diff/safe_action logged by MDPLCVehicle.log_step (safe_controller.py:187-227). */
+typedef struct {
+    int32_t *ran, *leader, *front_adj, *rear_adj, *constrain_adj, *active, *is_lc_safe;
+    double *safe_acc, *safe_steer, *nom_acc, *nom_steer, *lc_margin;
+} mm_shield_diag_host;
+
+/* Episode statistics accumulated on the device since the last mm_stats(reset=1).
+ * Sums are what ranks all-reduce(SUM); min_headway all-reduces with MIN. */
+typedef struct {
+    double agent_steps, env_steps, episodes, crashed_episodes, reward_sum, speed_sum, merge_percent_sum,
+           shield_solves, shield_active, lane_change_vetoes;
+    double min_headway;
+} mm_stats_t;
+
+/* gym.make(env_id) + config mutation (run_mappo.py:143-171).  record_diag != 0 keeps the per-sub-step shield
+ * record (test / control-profile use; costs extra stores). */
+int mm_create(const mm_config *cfg, int n_envs, int device, int record_diag, mm_env **out);
+int mm_destroy(mm_env *env);
+int mm_set_config(mm_env *env, const mm_config *cfg);
+int mm_num_envs(const mm_env *env);
+
+/* AbstractEnv.reset (abstract.py:176-209) for every env whose mask byte is non-zero (mask == NULL: all).
+ * Spawn follows merge_env_v1.py:180-211,265-364 with a counter-based RNG keyed by (seed, env index, episode
+ * counter): the same law as the reference, not the same MT19937 stream (use mm_set_state for exact scenes).
+ * num_cav > 0 pins the CAV count (reset(num_CAV=...)).  mask is a DEVICE pointer.  Writes the first obs. */
+int mm_reset(mm_env *env, uint64_t seed, const uint8_t *mask_dev, int num_cav, void *stream);
+
+/* MergeEnv.step (merge_env_v1.py:126-166): actions_dev is [n_envs][MM_MAXV] int8 on the device
+ * (NULL: use mm_buffers.actions).  auto_reset != 0 re-spawns finished envs after their outputs are written
+ * (the obs of a finished env is then the first obs of its next episode, as MAPPO.interact does, mappo.py:133-135). */
+int mm_step(mm_env *env, const int8_t *actions_dev, int auto_reset, void *stream);
+
+/* Same step through HOST buffers (pinned or pageable): copies actions in, steps, copies obs/reward/done out,
+ * chunked over internal streams so copies overlap compute.  Any output pointer may be NULL. */
+int mm_step_host(mm_env *env, const int8_t *actions, int auto_reset, float *obs, float *reward, uint8_t *done,
+                 float *regional_rewards, int32_t *n_agents);
+
+int mm_buffers_get(mm_env *env, mm_buffers *out);
+int mm_get_state(mm_env *env, mm_state_host *dst);        /* synchronous */
+int mm_set_state(mm_env *env, const mm_state_host *src);  /* synchronous; also refreshes obs / n_agents */
+int mm_get_shield_diag(mm_env *env, mm_shield_diag_host *dst);   /* requires record_diag */
+int mm_stats(mm_env *env, mm_stats_t *out, int reset);    /* synchronous */
+
+/* The CBF-QP alone (cbf.py:110-161 through cvxopt.solvers.qp): n independent solves on DEVICE arrays;
+ * u and active may alias nothing else.  Used for the solves/s microbenchmark and the QP known-answer tests. */
+int mm_shield_qp(const double *a, const double *c_lead, const double *c_adj, const uint8_t *has_adj,
+                 const double *lo, const double *hi, int64_t n, double *u, uint8_t *active, void *stream);
+
+/* Launch bookkeeping for bench.py ("gpu_launches") */
+int64_t mm_kernel_launches(const mm_env *env);
+const char *mm_last_error(void);
+const char *mm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,371 @@
+// capi.cu — host side of the C ABI declared in include/marl_mass_b200.h.
+// Owns device memory, launches the kernels of merge_step.cu, and implements the host-buffer step
+// (chunked over streams so that PCIe copies overlap compute).  No torch types anywhere.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "mm_internal.h"
+
+using namespace mm;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(mm_status code, const char *what, cudaError_t ce = cudaSuccess) {
+    char buf[512];
+    if (ce != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(ce));
+    else snprintf(buf, sizeof buf, "%s", what);
+    g_last_error = buf;
+    return (int)code;
+}
+
+#define CUDA_OK(expr)                                                        \
+    do {                                                                     \
+        cudaError_t _ce = (expr);                                            \
+        if (_ce != cudaSuccess) return fail(MM_ERR_CUDA, #expr, _ce);        \
+    } while (0)
+
+constexpr int MAX_CHUNKS = 8;
+constexpr int HOST_F64 = 16, HOST_I32 = 11, HOST_ENV = 5;
+
+}  // namespace
+
+struct mm_env {
+    int n_envs = 0, device = 0, record_diag = 0;
+    mm_config cfg{};
+    DevState st{};
+    DevOut out{};
+    int8_t *actions = nullptr;
+    size_t stats_rows = 0;
+    uint64_t seed = 0;
+    int64_t launches = 0;
+    cudaStream_t streams[MAX_CHUNKS]{};
+    int n_streams = 0;
+    std::vector<void *> allocs;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(mm_env *env, T **ptr, size_t count, bool zero = true) {
+    void *p = nullptr;
+    CUDA_OK(cudaMalloc(&p, count * sizeof(T)));
+    if (zero) CUDA_OK(cudaMemset(p, 0, count * sizeof(T)));
+    env->allocs.push_back(p);
+    *ptr = static_cast<T *>(p);
+    return 0;
+}
+
+int validate(const mm_config *c) {
+    if (!c) return fail(MM_ERR_ARG, "config is null");
+    if (c->shield < MM_SHIELD_NONE || c->shield > MM_SHIELD_MASS) return fail(MM_ERR_ARG, "Undefined safety_type");
+    if (c->reward_kind < MM_REW_DEFAULT || c->reward_kind > MM_REW_MREW) return fail(MM_ERR_ARG, "unknown agent_reward");
+    if (c->traffic_density < 1 || c->traffic_density > 3) return fail(MM_ERR_ARG, "traffic_density must be 1, 2 or 3");
+    if (c->traffic_type != MM_TRAFFIC_CAV && c->traffic_type != MM_TRAFFIC_MIXED) return fail(MM_ERR_ARG, "unknown traffic_type");
+    if (c->substeps < 1 || c->substeps > 3) return fail(MM_ERR_ARG, "substeps must be in 1..3");
+    if (c->duration_steps < 1 || c->duration_steps > 255) return fail(MM_ERR_ARG, "duration_steps must be in 1..255");
+    if (!(c->dt > 0)) return fail(MM_ERR_ARG, "dt must be positive");
+    return 0;
+}
+
+StepParams step_params(mm_env *env, const int8_t *actions, int off, int count) {
+    StepParams p{};
+    p.st = env->st;
+    p.out = env->out;
+    p.actions = actions;
+    p.cfg = env->cfg;
+    p.n_envs = env->n_envs;
+    p.env_offset = off;
+    p.env_count = count;
+    p.obs_mask = nullptr;
+    return p;
+}
+
+int reset_stats(mm_env *env) {
+    std::vector<double> h(env->stats_rows * N_STATS, 0.0);
+    for (size_t r = 0; r < env->stats_rows; ++r) h[r * N_STATS + ST_MINHW] = std::numeric_limits<double>::infinity();
+    CUDA_OK(cudaMemcpy(env->out.stats, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// enqueue one policy step (+ optional re-spawn of finished envs) for envs [off, off+count) on `stream`
+void enqueue_step(mm_env *env, const int8_t *actions_dev, int auto_reset, int off, int count, cudaStream_t stream) {
+    StepParams p = step_params(env, actions_dev, off, count);
+    launch_step(p, env->record_diag != 0, stream);
+    env->launches += 1;
+    if (auto_reset) {
+        ResetParams r{};
+        r.st = env->st; r.out = env->out; r.mask = nullptr; r.cfg = env->cfg; r.seed = env->seed;
+        r.n_envs = env->n_envs; r.env_offset = off; r.env_count = count; r.num_cav = 0; r.use_done = 1;
+        launch_reset(r, stream);
+        StepParams o = step_params(env, nullptr, off, count);
+        o.obs_mask = env->out.done;
+        launch_observe(o, stream);
+        env->launches += 2;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *mm_last_error(void) { return g_last_error.c_str(); }
+const char *mm_version(void) { return "marl-mass_b200 0.1 (sm_100a, f64 core)"; }
+
+int mm_create(const mm_config *cfg, int n_envs, int device, int record_diag, mm_env **out) {
+    if (!out) return fail(MM_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (int rc = validate(cfg)) return rc;
+    if (n_envs < 1) return fail(MM_ERR_ARG, "n_envs must be >= 1");
+    CUDA_OK(cudaSetDevice(device));
+    mm_env *env = new mm_env();
+    env->n_envs = n_envs; env->device = device; env->record_diag = record_diag; env->cfg = *cfg;
+    const size_t E = (size_t)n_envs;
+    int rc = 0;
+    rc |= dev_alloc(env, &env->st.f64, (size_t)F_COUNT * MAXV * E);
+    rc |= dev_alloc(env, &env->st.flags, (size_t)MAXV * E);
+    rc |= dev_alloc(env, &env->st.einfo, E);
+    rc |= dev_alloc(env, &env->st.episode, E);
+    rc |= dev_alloc(env, &env->out.obs, E * MAXV * NS);
+    rc |= dev_alloc(env, &env->out.reward, E);
+    rc |= dev_alloc(env, &env->out.agents_rewards, E * MAXV);
+    rc |= dev_alloc(env, &env->out.regional_rewards, E * MAXV);
+    rc |= dev_alloc(env, &env->out.average_speed, E);
+    rc |= dev_alloc(env, &env->out.traffic_speed, E);
+    rc |= dev_alloc(env, &env->out.min_headway, E);
+    rc |= dev_alloc(env, &env->out.merge_percent, E);
+    rc |= dev_alloc(env, &env->out.done, E);
+    rc |= dev_alloc(env, &env->out.agents_dones, E * MAXV);
+    rc |= dev_alloc(env, &env->out.n_agents, E);
+    rc |= dev_alloc(env, &env->actions, E * MAXV);
+    env->stats_rows = (E + 31) / 32;
+    rc |= dev_alloc(env, &env->out.stats, env->stats_rows * N_STATS);
+    if (record_diag) {
+        rc |= dev_alloc(env, &env->out.sh_i, (size_t)7 * E * 3 * MAXV);
+        rc |= dev_alloc(env, &env->out.sh_f, (size_t)5 * E * 3 * MAXV);
+    }
+    if (rc) { mm_destroy(env); return rc; }
+    if ((rc = reset_stats(env))) { mm_destroy(env); return rc; }
+    env->n_streams = MAX_CHUNKS;
+    for (int i = 0; i < env->n_streams; ++i) {
+        cudaError_t ce = cudaStreamCreateWithFlags(&env->streams[i], cudaStreamNonBlocking);
+        if (ce != cudaSuccess) { mm_destroy(env); return fail(MM_ERR_CUDA, "cudaStreamCreate", ce); }
+    }
+    *out = env;
+    return 0;
+}
+
+int mm_destroy(mm_env *env) {
+    if (!env) return 0;
+    cudaSetDevice(env->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < MAX_CHUNKS; ++i)
+        if (env->streams[i]) cudaStreamDestroy(env->streams[i]);
+    for (void *p : env->allocs) cudaFree(p);
+    delete env;
+    return 0;
+}
+
+int mm_set_config(mm_env *env, const mm_config *cfg) {
+    if (!env) return fail(MM_ERR_ARG, "env is null");
+    if (int rc = validate(cfg)) return rc;
+    env->cfg = *cfg;
+    return 0;
+}
+
+int mm_num_envs(const mm_env *env) { return env ? env->n_envs : 0; }
+int64_t mm_kernel_launches(const mm_env *env) { return env ? env->launches : 0; }
+
+int mm_reset(mm_env *env, uint64_t seed, const uint8_t *mask_dev, int num_cav, void *stream) {
+    if (!env) return fail(MM_ERR_ARG, "env is null");
+    if (num_cav < 0 || num_cav > 11) return fail(MM_ERR_ARG, "num_cav must be in 0..11");
+    CUDA_OK(cudaSetDevice(env->device));
+    env->seed = seed;
+    ResetParams r{};
+    r.st = env->st; r.out = env->out; r.mask = mask_dev; r.cfg = env->cfg; r.seed = seed;
+    r.n_envs = env->n_envs; r.env_offset = 0; r.env_count = env->n_envs; r.num_cav = num_cav; r.use_done = 0;
+    launch_reset(r, stream);
+    StepParams o = step_params(env, nullptr, 0, env->n_envs);
+    o.obs_mask = mask_dev;
+    launch_observe(o, stream);
+    env->launches += 2;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int mm_step(mm_env *env, const int8_t *actions_dev, int auto_reset, void *stream) {
+    if (!env) return fail(MM_ERR_ARG, "env is null");
+    CUDA_OK(cudaSetDevice(env->device));
+    enqueue_step(env, actions_dev ? actions_dev : env->actions, auto_reset, 0, env->n_envs, (cudaStream_t)stream);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int mm_step_host(mm_env *env, const int8_t *actions, int auto_reset, float *obs, float *reward, uint8_t *done,
+                 float *regional_rewards, int32_t *n_agents) {
+    if (!env) return fail(MM_ERR_ARG, "env is null");
+    if (!actions) return fail(MM_ERR_ARG, "actions is null");
+    CUDA_OK(cudaSetDevice(env->device));
+    const int E = env->n_envs;
+    // chunk = multiple of 128 envs (block size; also keeps the per-warp statistics rows disjoint)
+    int n_chunks = (E + 16383) / 16384;
+    if (n_chunks > env->n_streams) n_chunks = env->n_streams;
+    if (n_chunks < 1) n_chunks = 1;
+    int chunk = ((E + n_chunks - 1) / n_chunks + 127) / 128 * 128;
+    for (int c = 0; c < n_chunks; ++c) {
+        int off = c * chunk;
+        if (off >= E) break;
+        int count = E - off < chunk ? E - off : chunk;
+        cudaStream_t s = env->streams[c];
+        CUDA_OK(cudaMemcpyAsync(env->actions + (size_t)off * MAXV, actions + (size_t)off * MAXV, (size_t)count * MAXV,
+                                cudaMemcpyHostToDevice, s));
+        enqueue_step(env, env->actions, auto_reset, off, count, s);
+        if (obs)
+            CUDA_OK(cudaMemcpyAsync(obs + (size_t)off * MAXV * NS, env->out.obs + (size_t)off * MAXV * NS,
+                                    (size_t)count * MAXV * NS * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (reward)
+            CUDA_OK(cudaMemcpyAsync(reward + off, env->out.reward + off, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (done)
+            CUDA_OK(cudaMemcpyAsync(done + off, env->out.done + off, (size_t)count, cudaMemcpyDeviceToHost, s));
+        if (regional_rewards)
+            CUDA_OK(cudaMemcpyAsync(regional_rewards + (size_t)off * MAXV, env->out.regional_rewards + (size_t)off * MAXV,
+                                    (size_t)count * MAXV * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (n_agents)
+            CUDA_OK(cudaMemcpyAsync(n_agents + off, env->out.n_agents + off, (size_t)count * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    }
+    for (int c = 0; c < n_chunks; ++c) CUDA_OK(cudaStreamSynchronize(env->streams[c]));
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int mm_buffers_get(mm_env *env, mm_buffers *b) {
+    if (!env || !b) return fail(MM_ERR_ARG, "null argument");
+    b->obs = env->out.obs; b->reward = env->out.reward; b->done = env->out.done;
+    b->agents_rewards = env->out.agents_rewards; b->regional_rewards = env->out.regional_rewards;
+    b->agents_dones = env->out.agents_dones; b->average_speed = env->out.average_speed;
+    b->traffic_speed = env->out.traffic_speed; b->min_headway = env->out.min_headway;
+    b->merge_percent = env->out.merge_percent; b->n_agents = env->out.n_agents; b->actions = env->actions;
+    return 0;
+}
+
+int mm_get_state(mm_env *env, mm_state_host *dst) {
+    if (!env || !dst) return fail(MM_ERR_ARG, "null argument");
+    CUDA_OK(cudaSetDevice(env->device));
+    const size_t E = (size_t)env->n_envs, P = E * MAXV;
+    double *f64 = nullptr; int32_t *i32 = nullptr, *envv = nullptr;
+    CUDA_OK(cudaMalloc(&f64, HOST_F64 * P * sizeof(double)));
+    CUDA_OK(cudaMalloc(&i32, HOST_I32 * P * sizeof(int32_t)));
+    CUDA_OK(cudaMalloc(&envv, HOST_ENV * E * sizeof(int32_t)));
+    CUDA_OK(cudaDeviceSynchronize());
+    launch_unpack_state(env->st, env->n_envs, f64, i32, envv, nullptr);
+    CUDA_OK(cudaDeviceSynchronize());
+    double *fd[HOST_F64] = {dst->x, dst->y, dst->heading, dst->speed, dst->target_speed, dst->gvx, dst->rec1_x, dst->rec1_vx,
+                            dst->rec2_x, dst->rec2_vx, dst->act_steer, dst->act_acc, dst->safe_steer, dst->safe_acc,
+                            dst->timer, dst->min_headway};
+    int32_t *id[HOST_I32] = {dst->kind, dst->lane, dst->target_lane, dst->speed_index, dst->crashed, dst->hl_action,
+                             dst->hist_len, dst->fg_set, dst->is_collaborating, dst->is_lc_safe, dst->collaborate_adj};
+    int32_t *ed[HOST_ENV] = {dst->n_veh, dst->n_cav, dst->n_merge, dst->steps, dst->time};
+    for (int k = 0; k < HOST_F64; ++k)
+        if (fd[k]) CUDA_OK(cudaMemcpy(fd[k], f64 + k * P, P * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < HOST_I32; ++k)
+        if (id[k]) CUDA_OK(cudaMemcpy(id[k], i32 + k * P, P * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < HOST_ENV; ++k)
+        if (ed[k]) CUDA_OK(cudaMemcpy(ed[k], envv + k * E, E * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    cudaFree(f64); cudaFree(i32); cudaFree(envv);
+    return 0;
+}
+
+int mm_set_state(mm_env *env, const mm_state_host *src) {
+    if (!env || !src) return fail(MM_ERR_ARG, "null argument");
+    CUDA_OK(cudaSetDevice(env->device));
+    const size_t E = (size_t)env->n_envs, P = E * MAXV;
+    const double *fd[HOST_F64] = {src->x, src->y, src->heading, src->speed, src->target_speed, src->gvx, src->rec1_x,
+                                  src->rec1_vx, src->rec2_x, src->rec2_vx, src->act_steer, src->act_acc, src->safe_steer,
+                                  src->safe_acc, src->timer, src->min_headway};
+    const int32_t *id[HOST_I32] = {src->kind, src->lane, src->target_lane, src->speed_index, src->crashed, src->hl_action,
+                                   src->hist_len, src->fg_set, src->is_collaborating, src->is_lc_safe, src->collaborate_adj};
+    const int32_t *ed[HOST_ENV] = {src->n_veh, src->n_cav, src->n_merge, src->steps, src->time};
+    for (int k = 0; k < HOST_F64; ++k) if (!fd[k]) return fail(MM_ERR_ARG, "mm_set_state: every f64 field is required");
+    for (int k = 0; k < HOST_I32; ++k) if (!id[k]) return fail(MM_ERR_ARG, "mm_set_state: every i32 field is required");
+    for (int k = 0; k < HOST_ENV; ++k) if (!ed[k]) return fail(MM_ERR_ARG, "mm_set_state: every env field is required");
+    for (size_t e = 0; e < E; ++e) {
+        if (ed[0][e] < 0 || ed[0][e] > 11 || ed[1][e] < 1 || ed[1][e] > ed[0][e])
+            return fail(MM_ERR_STATE, "mm_set_state: need 1 <= n_cav <= n_veh <= 11");
+        for (int i = 0; i < ed[0][e]; ++i) {
+            int kind = id[0][e * MAXV + i];
+            if (kind != (i < ed[1][e] ? MM_KIND_CAV : MM_KIND_HDV))
+                return fail(MM_ERR_STATE, "mm_set_state: slots [0,n_cav) must be CAVs and [n_cav,n_veh) HDVs");
+        }
+    }
+    double *f64 = nullptr; int32_t *i32 = nullptr, *envv = nullptr;
+    CUDA_OK(cudaMalloc(&f64, HOST_F64 * P * sizeof(double)));
+    CUDA_OK(cudaMalloc(&i32, HOST_I32 * P * sizeof(int32_t)));
+    CUDA_OK(cudaMalloc(&envv, HOST_ENV * E * sizeof(int32_t)));
+    for (int k = 0; k < HOST_F64; ++k) CUDA_OK(cudaMemcpy(f64 + k * P, fd[k], P * sizeof(double), cudaMemcpyHostToDevice));
+    for (int k = 0; k < HOST_I32; ++k) CUDA_OK(cudaMemcpy(i32 + k * P, id[k], P * sizeof(int32_t), cudaMemcpyHostToDevice));
+    for (int k = 0; k < HOST_ENV; ++k) CUDA_OK(cudaMemcpy(envv + k * E, ed[k], E * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaDeviceSynchronize());
+    launch_pack_state(env->st, env->n_envs, f64, i32, envv, nullptr);
+    StepParams o = step_params(env, nullptr, 0, env->n_envs);
+    launch_observe(o, nullptr);
+    env->launches += 2;
+    CUDA_OK(cudaDeviceSynchronize());
+    cudaFree(f64); cudaFree(i32); cudaFree(envv);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int mm_get_shield_diag(mm_env *env, mm_shield_diag_host *dst) {
+    if (!env || !dst) return fail(MM_ERR_ARG, "null argument");
+    if (!env->record_diag) return fail(MM_ERR_STATE, "handle was created without record_diag");
+    CUDA_OK(cudaSetDevice(env->device));
+    CUDA_OK(cudaDeviceSynchronize());
+    const size_t P = (size_t)env->n_envs * 3 * MAXV;
+    int32_t *id[7] = {dst->ran, dst->leader, dst->front_adj, dst->rear_adj, dst->constrain_adj, dst->active, dst->is_lc_safe};
+    double *fd[5] = {dst->safe_acc, dst->safe_steer, dst->nom_acc, dst->nom_steer, dst->lc_margin};
+    for (int k = 0; k < 7; ++k)
+        if (id[k]) CUDA_OK(cudaMemcpy(id[k], env->out.sh_i + k * P, P * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 5; ++k)
+        if (fd[k]) CUDA_OK(cudaMemcpy(fd[k], env->out.sh_f + k * P, P * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int mm_stats(mm_env *env, mm_stats_t *out, int reset) {
+    if (!env || !out) return fail(MM_ERR_ARG, "null argument");
+    CUDA_OK(cudaSetDevice(env->device));
+    CUDA_OK(cudaDeviceSynchronize());
+    std::vector<double> h(env->stats_rows * N_STATS);
+    CUDA_OK(cudaMemcpy(h.data(), env->out.stats, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    double acc[N_STATS] = {0};
+    acc[ST_MINHW] = std::numeric_limits<double>::infinity();
+    for (size_t r = 0; r < env->stats_rows; ++r)
+        for (int k = 0; k < N_STATS; ++k) {
+            double v = h[r * N_STATS + k];
+            acc[k] = k == ST_MINHW ? std::fmin(acc[k], v) : acc[k] + v;
+        }
+    out->agent_steps = acc[ST_AGENT_STEPS]; out->env_steps = acc[ST_ENV_STEPS]; out->episodes = acc[ST_EPISODES];
+    out->crashed_episodes = acc[ST_CRASHED]; out->reward_sum = acc[ST_REWARD]; out->speed_sum = acc[ST_SPEED];
+    out->merge_percent_sum = acc[ST_MERGE]; out->shield_solves = acc[ST_SOLVES]; out->shield_active = acc[ST_ACTIVE];
+    out->lane_change_vetoes = acc[ST_VETOES]; out->min_headway = acc[ST_MINHW];
+    if (reset) return reset_stats(env);
+    return 0;
+}
+
+int mm_shield_qp(const double *a, const double *c_lead, const double *c_adj, const uint8_t *has_adj, const double *lo,
+                 const double *hi, int64_t n, double *u, uint8_t *active, void *stream) {
+    if (!a || !c_lead || !c_adj || !has_adj || !lo || !hi || !u || !active) return fail(MM_ERR_ARG, "null argument");
+    if (n < 0) return fail(MM_ERR_ARG, "n must be >= 0");
+    launch_qp(a, c_lead, c_adj, has_adj, lo, hi, n, u, active, stream);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

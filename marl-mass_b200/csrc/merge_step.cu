@@ -1,0 +1,1326 @@
+// merge_step.cu — sm_100a kernels of the batched merge environment and its HSS / MASS CBF shields.
+//
+// One thread advances one environment by one whole policy step (3 physics sub-steps, each = ordered
+// act() pass + ordered step() pass with the shield inside + pairwise collision pass), then builds the
+// KinematicLC observations, local/regional rewards, terminal flags and info scalars.  Within an env the
+// reference semantics are strictly sequential (front-to-back by x: a follower's shield reads its leader's
+// already-updated position, shielded action and pre-step record), so the parallel axis is the env axis.
+//
+// Memory plan per thread: the four fields every neighbour scan touches (x, y, heading, speed) and the packed
+// discrete state live in shared memory as [slot][thread] planes (bank-conflict free for any per-thread slot
+// index); the colder fields stay in HBM/L2 as [field][slot][env] planes and are touched O(1) times per
+// vehicle per sub-step.  Arithmetic is IEEE double, compiled with -fmad=false, so that every threshold
+// decision (lane argmin, neighbour order, crash test, veto, active set) reproduces the float64 reference.
+//
+// Reference map (paths relative to the reference tree):
+//   sub-step driver ............ highway_env/envs/common/abstract.py:512-532, road/road.py:269-292
+//   CAV controllers ............ vehicle/controller.py:90-197, 293-337
+//   HDV IDM + MOBIL ............ vehicle/behavior.py:74-266, road/road.py:352-381
+//   bicycle model, collisions .. vehicle/kinematics.py:122-209, vehicle/safe_controller.py:100-185, utils.py:55-121
+//   lane algebra ............... road/lane.py:61-210, road/road.py:51-109
+//   shields .................... vehicle/safety/decentral_layer.py:15-817, vehicle/safety/cbf.py:110-430
+//   observation / rewards ...... envs/common/observation.py:181-273, envs/merge_env_v1.py:64-178,373-474
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include "mm_internal.h"
+
+namespace mm {
+
+constexpr int BLOCK = 128;
+constexpr double PI = 3.141592653589793;
+constexpr double TWO_PI = 2 * PI;
+
+enum { L_AB0 = 0, L_BC0 = 1, L_BC1 = 2, L_CD0 = 3, L_JK0 = 4, L_KB0 = 5, N_LANES = 6 };
+enum { A_LANE_LEFT = 0, A_IDLE = 1, A_LANE_RIGHT = 2, A_FASTER = 3, A_SLOWER = 4, A_NONE = 7 };
+constexpr int OBST = MAXV;  // entity id of the single obstacle at (420, 4)
+
+__constant__ double c_lane_sx[N_LANES] = {0.0, 320.0, 320.0, 420.0, 0.0, 220.0};
+__constant__ double c_lane_sy[N_LANES] = {0.0, 0.0, 4.0, 0.0, 10.5, 7.25};
+__constant__ double c_lane_len[N_LANES] = {320.0, 100.0, 100.0, 1000.0, 220.0, 100.0};
+
+constexpr double OBST_X = 420.0, OBST_Y = 4.0;
+constexpr double VLEN = 5.0, VWID = 2.0, LWIDTH = 4.0;
+constexpr double SINE_AMP = 3.25;
+constexpr double SINE_PULS = 2 * PI / (2 * 100.0);
+constexpr double SINE_PHASE = PI / 2;
+constexpr double PERCEPTION = 180.0;
+constexpr double KP_A = 1 / 0.6;
+constexpr double KP_HEADING = 1 / 0.2;
+constexpr double KP_LATERAL = 1.0 / 3 * KP_HEADING;
+constexpr double PURSUIT_TAU = 0.5 * 0.2;
+constexpr double MAX_STEER = PI / 3;
+constexpr double ACC_LO = -12.5, ACC_HI = 6.0;
+
+// ------------------------------------------------------------------------------------------------
+// per-thread view of one environment
+// ------------------------------------------------------------------------------------------------
+struct Env {
+    double *sx, *sy, *sh, *sv;  // shared planes, already offset by threadIdx.x; element i at [i * BLOCK]
+    uint32_t *sf;
+    double *g;                  // cold planes, already offset by the env index; element (f, i) at [(f*MAXV+i)*E]
+    size_t E;
+    int n_veh, n_cav;
+};
+
+#define X(i) (ev.sx[(i) * BLOCK])
+#define Y(i) (ev.sy[(i) * BLOCK])
+#define H(i) (ev.sh[(i) * BLOCK])
+#define V(i) (ev.sv[(i) * BLOCK])
+#define FL(i) (ev.sf[(i) * BLOCK])
+#define GF(f, i) (ev.g[(size_t)((f) * MAXV + (i)) * ev.E])
+
+__device__ __forceinline__ int fl_kind(uint32_t f) { return f & FL_KIND_MASK; }
+__device__ __forceinline__ int fl_lane(uint32_t f) { return (f >> FL_LANE_SHIFT) & FL_3BIT; }
+__device__ __forceinline__ int fl_tlane(uint32_t f) { return (f >> FL_TLANE_SHIFT) & FL_3BIT; }
+__device__ __forceinline__ int fl_hl(uint32_t f) { return (f >> FL_HL_SHIFT) & FL_3BIT; }
+__device__ __forceinline__ int fl_hist(uint32_t f) { return (f >> FL_HIST_SHIFT) & 3u; }
+__device__ __forceinline__ uint32_t fl_set(uint32_t f, uint32_t shift, uint32_t mask, uint32_t v) {
+    return (f & ~(mask << shift)) | (v << shift);
+}
+
+// ------------------------------------------------------------------------------------------------
+// scalar helpers (utils.py:16-41)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double not_zero(double x) {
+    if (fabs(x) > 1e-2) return x;
+    return x > 0 ? 1e-2 : -1e-2;
+}
+__device__ __forceinline__ double clipd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+// Python's floored float modulo by a positive modulus
+__device__ __forceinline__ double pymod_pos(double a, double b) {
+    double r = fmod(a, b);
+    if (r < 0) r += b;
+    return r;
+}
+__device__ __forceinline__ double wrap_to_pi(double x) { return pymod_pos(x + PI, TWO_PI) - PI; }
+__device__ __forceinline__ double lmap(double v, double x0, double x1, double y0, double y1) {
+    return y0 + (v - x0) * (y1 - y0) / (x1 - x0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// lane algebra: every lane is x-aligned, so s = x - start.x and r = y - start.y (- sine offset on kb0)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double lane_s(int lane, double px) { return px - c_lane_sx[lane]; }
+__device__ __forceinline__ double lane_r(int lane, double s, double py) {
+    double r = py - c_lane_sy[lane];
+    if (lane == L_KB0) r = r - SINE_AMP * sin(SINE_PULS * s + SINE_PHASE);
+    return r;
+}
+__device__ __forceinline__ double lane_heading_at(int lane, double s) {
+    if (lane == L_KB0) return atan(SINE_AMP * SINE_PULS * cos(SINE_PULS * s + SINE_PHASE));
+    return 0.0;
+}
+__device__ __forceinline__ bool on_lane(int lane, double px, double py, double margin) {
+    double s = lane_s(lane, px);
+    double r = lane_r(lane, s, py);
+    return fabs(r) <= LWIDTH / 2 + margin && -VLEN <= s && s < c_lane_len[lane] + VLEN;
+}
+// L1 distance to a straight lane (lane.py:97-100); only ever needed for bc0 / bc1
+__device__ __forceinline__ double straight_lane_distance(int lane, double px, double py) {
+    double s = lane_s(lane, px);
+    double r = py - c_lane_sy[lane];
+    return fabs(r) + fmax(s - c_lane_len[lane], 0.0) + fmax(0.0 - s, 0.0);
+}
+// road.py:67-109 with route=None (every node has a single successor)
+__device__ __forceinline__ int next_lane(int lane, double px, double py) {
+    if (lane == L_AB0 || lane == L_KB0)
+        return straight_lane_distance(L_BC0, px, py) <= straight_lane_distance(L_BC1, px, py) ? L_BC0 : L_BC1;
+    if (lane == L_JK0) return L_KB0;
+    return L_CD0;
+}
+__device__ __forceinline__ int lane_road(int lane) { return lane == L_BC1 ? L_BC0 : lane; }
+__device__ __forceinline__ int lane_rid(int lane) { return lane == L_BC1 ? 1 : 0; }
+
+// road.py:51-65 + lane.py:102-108: first minimum over [ab0, bc0, bc1, cd0, jk0, kb0].
+// The five straight lanes share heading_at == 0, so one wrap_to_pi serves them; kb0 (last in argmin order)
+// is evaluated only if its heading-free lower bound can still beat the incumbent.
+__device__ __noinline__ int closest_lane(double px, double py, double heading) {
+    double ang0 = fabs(wrap_to_pi(heading - 0.0));
+    int best = 0;
+    double bd = CUDART_INF;
+#pragma unroll
+    for (int l = 0; l < 5; ++l) {
+        double s = lane_s(l, px);
+        double r = py - c_lane_sy[l];
+        double d = fabs(r) + fmax(s - c_lane_len[l], 0.0) + fmax(0.0 - s, 0.0) + 1.0 * ang0;
+        if (d < bd) { bd = d; best = l; }
+    }
+    double s = lane_s(L_KB0, px);
+    double along = fmax(s - c_lane_len[L_KB0], 0.0) + fmax(0.0 - s, 0.0);
+    if (along < bd) {  // |r| >= 0 and angle >= 0, and fp addition is monotone: d >= along
+        double r = lane_r(L_KB0, s, py);
+        double ang = fabs(wrap_to_pi(heading - lane_heading_at(L_KB0, s)));
+        double d = fabs(r) + fmax(s - c_lane_len[L_KB0], 0.0) + fmax(0.0 - s, 0.0) + 1.0 * ang;
+        if (d < bd) best = L_KB0;
+    }
+    return best;
+}
+
+// controller.py:146-187
+__device__ __noinline__ double steering_control(double px, double py, double heading, double speed, int tlane) {
+    double s = lane_s(tlane, px);
+    double r = lane_r(tlane, s, py);
+    double future_heading = lane_heading_at(tlane, s + speed * PURSUIT_TAU);
+    double lat_cmd = -KP_LATERAL * r;
+    double nz = not_zero(speed);
+    double heading_cmd = asin(clipd(lat_cmd / nz, -1.0, 1.0));
+    double heading_ref = future_heading + clipd(heading_cmd, -PI / 4, PI / 4);
+    double rate_cmd = KP_HEADING * wrap_to_pi(heading_ref - heading);
+    double steering = asin(clipd(VLEN / 2 / nz * rate_cmd, -1.0, 1.0));
+    return clipd(steering, -MAX_STEER, MAX_STEER);
+}
+
+__device__ __forceinline__ int speed_to_index(double speed) {
+    double x = (speed - 10.0) / (30.0 - 10.0);
+    return (int)clipd(rint(x * 4), 0.0, 4.0);
+}
+
+// controller.py:136-144
+__device__ __forceinline__ int follow_road(int tlane, double px, double py) {
+    double s = lane_s(tlane, px);
+    if (s > c_lane_len[tlane] - VLEN / 2) return next_lane(tlane, px, py);
+    return tlane;
+}
+
+// MDPLCVehicle.act -> MDPVehicle.act -> ControlledVehicle.act (safe_controller.py:63-66, controller.py:293-311, 90-134)
+__device__ void cav_act(Env &ev, int i, int action) {
+    uint32_t f = FL(i);
+    double px = X(i), py = Y(i), speed = V(i);
+    if (action != A_NONE) f = fl_set(f, FL_HL_SHIFT, FL_3BIT, (uint32_t)action);
+    if (action == A_FASTER || action == A_SLOWER) {
+        int idx = speed_to_index(speed) + (action == A_FASTER ? 1 : -1);
+        idx = min(max(idx, 0), 4);
+        f = fl_set(f, FL_SIDX_SHIFT, FL_3BIT, (uint32_t)idx);
+        GF(F_TSPEED, i) = 10.0 + idx * (30.0 - 10.0) / 4;
+    }
+    int tl = follow_road(fl_tlane(f), px, py);
+    // the only reachable, non-forbidden side lane of the network is bc0 seen from bc1 (LANE_LEFT)
+    if (action == A_LANE_LEFT && tl == L_BC1) {
+        double s = lane_s(L_BC0, px), r = py - c_lane_sy[L_BC0];
+        if (fabs(r) <= 2 * LWIDTH && 0 <= s && s < c_lane_len[L_BC0] + VLEN) tl = L_BC0;
+    }
+    f = fl_set(f, FL_TLANE_SHIFT, FL_3BIT, (uint32_t)tl);
+    FL(i) = f;
+    GF(F_ACT_STEER, i) = steering_control(px, py, H(i), speed, tl);
+    GF(F_ACT_ACC, i) = KP_A * (GF(F_TSPEED, i) - speed);
+}
+
+// ------------------------------------------------------------------------------------------------
+// HDV: IDM + MOBIL (behavior.py)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ent_pos(const Env &ev, int id, double &px, double &py) {
+    if (id == OBST) { px = OBST_X; py = OBST_Y; } else { px = X(id); py = Y(id); }
+}
+
+// road.py:352-381 (candidates: vehicles in list order, then the obstacle)
+__device__ void neighbour_vehicles(const Env &ev, int self, int lane, int &front, int &rear) {
+    double s = lane_s(lane, X(self)), s_front = 0, s_rear = 0;
+    front = -1;
+    rear = -1;
+    for (int j = 0; j <= ev.n_veh; ++j) {
+        int id = j == ev.n_veh ? OBST : j;
+        if (id == self) continue;
+        double px, py;
+        ent_pos(ev, id, px, py);
+        double s_v = lane_s(lane, px);
+        if (!(-VLEN <= s_v && s_v < c_lane_len[lane] + VLEN)) continue;
+        double lat = lane_r(lane, s_v, py);
+        if (!(fabs(lat) <= LWIDTH / 2 + 1)) continue;
+        if (s <= s_v && (front < 0 || s_v <= s_front)) { s_front = s_v; front = id; }
+        if (s_v < s && (rear < 0 || s_v > s_rear)) { s_rear = s_v; rear = id; }
+    }
+}
+
+// behavior.py:141-156
+__device__ double desired_gap(const Env &ev, int ego, int front) {
+    double fvx = 0, fvy = 0;
+    if (front != OBST) {
+        double fs, fc;
+        sincos(H(front), &fs, &fc);
+        fvx = V(front) * fc;
+        fvy = V(front) * fs;
+    }
+    double es, ec, speed = V(ego);
+    sincos(H(ego), &es, &ec);
+    double dv = (speed * ec - fvx) * ec + (speed * es - fvy) * es;
+    return 10.0 + speed * 1.5 + speed * dv / (2 * sqrt(15.0));
+}
+
+// behavior.py:111-139 (ego/front: -1 None, OBST obstacle)
+__device__ double idm_acc(const Env &ev, int ego, int front) {
+    if (ego < 0 || ego == OBST) return 0.0;
+    double acc = 3.0 * (1 - pow(fmax(V(ego), 0.0) / not_zero(GF(F_TSPEED, ego)), 4.0));
+    if (front >= 0) {
+        double fx, fy;
+        ent_pos(ev, front, fx, fy);
+        int el = fl_lane(FL(ego));
+        double d = lane_s(el, fx) - lane_s(el, X(ego));
+        double q = desired_gap(ev, ego, front) / not_zero(d);
+        acc -= 3.0 * (q * q);
+    }
+    return acc;
+}
+
+// behavior.py:186-266 (route None, POLITENESS 0: the follower terms enter the jerk with weight 0.0)
+__device__ int hdv_change_lane(Env &ev, int self, uint32_t f, int tl) {
+    int lane = fl_lane(f);
+    if (lane != tl) {
+        if (lane_road(lane) == lane_road(tl)) {
+            for (int j = 0; j < ev.n_veh; ++j) {
+                uint32_t fj = FL(j);
+                if (j != self && fl_lane(fj) != tl && fl_tlane(fj) == tl) {
+                    double d = lane_s(lane, X(j)) - lane_s(lane, X(self));
+                    if (0 < d && d < desired_gap(ev, self, j)) return lane;
+                }
+            }
+        }
+        return tl;
+    }
+    double timer = GF(F_TIMER, self);
+    if (!(1.0 < timer)) return tl;
+    GF(F_TIMER, self) = 0.0;
+    if (lane != L_BC1) return tl;  // bc0's side lane bc1 is forbidden; nothing else has side lanes
+    {
+        double s = lane_s(L_BC0, X(self)), r = Y(self) - c_lane_sy[L_BC0];
+        if (!(fabs(r) <= 2 * LWIDTH && 0 <= s && s < c_lane_len[L_BC0] + VLEN)) return tl;
+    }
+    int new_prec, new_foll, old_prec, old_foll;
+    neighbour_vehicles(ev, self, L_BC0, new_prec, new_foll);
+    double nf_a = idm_acc(ev, new_foll, new_prec);
+    double nf_pred = idm_acc(ev, new_foll, self);
+    if (nf_pred < -9.0) return tl;
+    neighbour_vehicles(ev, self, lane, old_prec, old_foll);
+    double self_pred = idm_acc(ev, self, new_prec);
+    double self_a = idm_acc(ev, self, old_prec);
+    double of_a = idm_acc(ev, old_foll, self);
+    double of_pred = idm_acc(ev, old_foll, old_prec);
+    double jerk = self_pred - self_a + 0. * (nf_pred - nf_a + of_pred - of_a);
+    if (jerk < 0.1) return tl;
+    return L_BC0;
+}
+
+// behavior.py:74-100
+__device__ __noinline__ void hdv_act(Env &ev, int i) {
+    uint32_t f = FL(i);
+    if (f & FL_CRASHED) return;
+    int front, rear;
+    neighbour_vehicles(ev, i, fl_lane(f), front, rear);
+    int tl = follow_road(fl_tlane(f), X(i), Y(i));
+    tl = hdv_change_lane(ev, i, f, tl);
+    FL(i) = fl_set(f, FL_TLANE_SHIFT, FL_3BIT, (uint32_t)tl);
+    GF(F_ACT_STEER, i) = steering_control(X(i), Y(i), H(i), V(i), tl);
+    GF(F_ACT_ACC, i) = clipd(idm_acc(ev, i, front), -6.0, 6.0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// shields
+// ------------------------------------------------------------------------------------------------
+// Closed-form minimiser of the reference's QP (cbf.py:110-135 with rows cbf.py:288-322 / 374-422):
+//   min 1/2 (u0^2 + u1^2 + 1e18 s^2)  s.t.  a u0 - s <= c_lead, [a u0 - s <= c_adj,]  lo <= u0 <= hi.
+__device__ __forceinline__ double solve_cbf_qp(double a, double c_lead, double c_adj, bool has_adj, double lo,
+                                               double hi, int &active) {
+    double u = 0.0;
+    active = 0;
+    if (u > hi) { u = hi; active = MM_ACT_UPPER; }
+    if (u < lo) { u = lo; active = MM_ACT_LOWER; }
+    if (a > 0.0) {
+        double lim = c_lead / a;
+        int row = MM_ACT_LEAD;
+        if (has_adj) {
+            double la = c_adj / a;
+            if (la < lim) { lim = la; row = MM_ACT_ADJ; }
+        }
+        if (u > lim) {
+            if (lim >= lo) { u = lim; active = row; }
+            else { u = lo; active = row | MM_ACT_LOWER | MM_ACT_SLACK; }
+        }
+    } else if (a < 0.0) {
+        double lim = c_lead / a;
+        int row = MM_ACT_LEAD;
+        if (has_adj) {
+            double la = c_adj / a;
+            if (la > lim) { lim = la; row = MM_ACT_ADJ; }
+        }
+        if (u < lim) {
+            if (lim <= hi) { u = lim; active = row; }
+            else { u = hi; active = row | MM_ACT_UPPER | MM_ACT_SLACK; }
+        }
+    } else {
+        double c = has_adj ? fmin(c_lead, c_adj) : c_lead;
+        if (c < 0.0) active |= MM_ACT_SLACK | MM_ACT_LEAD;
+    }
+    return u;
+}
+
+// decentral_layer.py:23-39
+__device__ __forceinline__ int is_adj_lane(int l1, double px, double py, int l2) {
+    if (lane_road(l1) == lane_road(l2) && abs(lane_rid(l1) - lane_rid(l2)) == 1) return lane_rid(l1) - lane_rid(l2);
+    int nl = next_lane(l1, px, py);
+    if (lane_road(nl) == lane_road(l2) && abs(lane_rid(nl) - lane_rid(l2)) == 1) return lane_rid(nl) - lane_rid(l2);
+    return 0;
+}
+
+// controller.py:257-267; left: dir == "L"
+__device__ __forceinline__ void get_corner(double px, double py, double heading, bool left, double &cx, double &cy) {
+    const double corner_len = sqrt((VWID / 2) * (VWID / 2) + (VLEN / 2) * (VLEN / 2)) + 0.0075;
+    const double corner_alpha = atan(VWID / VLEN);
+    double ang = left ? corner_alpha + heading : -corner_alpha + heading;
+    cx = px + (corner_len * cos(corner_alpha + heading));
+    cy = py - (corner_len * sin(ang)) + 0.01;
+}
+
+struct ShieldRec {
+    int leader, front_adj, rear_adj, constrain_adj, active, is_lc_safe;
+    double lc_margin;
+};
+
+// road.py:257-267: the `count` nearest (by |longitudinal offset in the ego lane|, stable) among vehicles
+// closer than 180 m.  Keeps a sorted top-K in registers.
+template <int K>
+__device__ __forceinline__ int close_vehicles(const Env &ev, int self, int (&ids)[K]) {
+    double keys[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { keys[k] = CUDART_INF; ids[k] = -1; }
+    double ex = X(self), ey = Y(self);
+    int el = fl_lane(FL(self));
+    double es = lane_s(el, ex);
+    int n = 0;
+    for (int j = 0; j < ev.n_veh; ++j) {
+        if (j == self) continue;
+        double ox = X(j), oy = Y(j);
+        double dx = ox - ex, dy = oy - ey;
+        if (!(sqrt(dx * dx + dy * dy) < PERCEPTION)) continue;
+        double key = fabs(lane_s(el, ox) - es);
+        int id = j;
+        ++n;
+        // stable insertion: a later element goes after equal keys; once placed, everything behind shifts
+        bool placed = false;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (placed || key < keys[k]) {
+                double tk = keys[k]; keys[k] = key; key = tk;
+                int ti = ids[k]; ids[k] = id; id = ti;
+                placed = true;
+            }
+        }
+    }
+    return n < K ? n : K;
+}
+
+// safety_layer -> safe_action_hss / safe_action_mass (decentral_layer.py:767-817, 290-518, 521-764) with
+// multi_agent_state (85-257) and CBF_AV / CBF_CAV (cbf.py:197-430).  Returns the shielded (steer, acc).
+__device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, double &out_steer, double &out_acc,
+                                    ShieldRec &rec) {
+    const double dt = cfg.dt, eta = cfg.eta, tau = cfg.tau;
+    const bool mass = cfg.shield == MM_SHIELD_MASS;
+    uint32_t f = FL(self);
+    const int elane = fl_lane(f);
+    const double ex = X(self), ey = Y(self), eh = H(self), espeed = V(self);
+    const double act_acc = GF(F_ACT_ACC, self), act_steer = GF(F_ACT_STEER, self);
+
+    double v_min = espeed + ACC_LO * dt;
+    if (mass) v_min = fmax(0.0, v_min);
+    double v_max = espeed + ACC_HI * dt;
+    double evx_raw = espeed * cos(eh);
+    double evx = evx_raw > 1 ? evx_raw : 1;
+    double es = lane_s(elane, ex);
+
+    double x_ol = ex + PERCEPTION + 1, x_oa = ex + PERCEPTION + 1, x_oar = ex - PERCEPTION - 1;
+    bool has_ol = false, has_oa = false, has_oar = false;
+    double vx_ol = 0, vx_oa = 0, vx_oar = 0, a_ol = 0, a_oa = 0, g_ol = 0, g_oa = 0;
+    bool constrain_adj = false;
+    int id_ol = MM_NB_NONE, id_oa = MM_NB_NONE, id_oar = MM_NB_NONE;
+
+    int nb[5];
+    int n_nb = close_vehicles<5>(ev, self, nb);
+#pragma unroll 1
+    for (int k = 0; k < n_nb; ++k) {
+        int o = nb[k];
+        uint32_t fo = FL(o);
+        int olane = fl_lane(fo);
+        double ox = X(o), oy = Y(o), oh = H(o);
+        bool o_cav = fl_kind(fo) == MM_KIND_CAV;
+        int v_a = is_adj_lane(elane, ex, ey, olane);
+        int a_v = is_adj_lane(olane, ox, oy, elane);
+        double d = lane_s(elane, ox) - es;
+        // is_approaching_same_lane (decentral_layer.py:46-57)
+        bool approaching = false;
+        if (!(d < 0)) {
+            double y_dist = oy - ey;
+            bool hc = y_dist < 0 ? (oh > 0.037) : (oh < -0.037);
+            approaching = fabs(y_dist) <= 3.5 && hc;
+        }
+        if (!approaching && (v_a != 0 || a_v != 0)) {
+            if (!has_oar && d < 0) {  // rear-adjacent: its current state
+                has_oar = true; id_oar = o;
+                x_oar = ox;
+                vx_oar = V(o) * cos(oh);
+            } else if (!has_oa && d >= 0) {  // front-adjacent: its record before its last step
+                has_oa = true; id_oa = o;
+                x_oa = GF(F_REC2X, o);
+                vx_oa = GF(F_REC2VX, o);
+                if (mass) {
+                    a_oa = o_cav ? GF(F_SAFE_ACC, o) : ACC_LO;
+                    g_oa = o_cav ? GF(F_GVX, o) : 1.0;
+                    bool left = (v_a == -1 || a_v == 1);
+                    double cx, cy;
+                    get_corner(ox, oy, oh, left, cx, cy);
+                    constrain_adj = !on_lane(olane, cx, cy, 0.0);
+                }
+            }
+        } else if (!o_cav && elane == L_AB0 && olane == L_KB0 && d >= 0) {
+            // on-ramp HDV: its record is shifted IN PLACE by half a second of ego speed (decentral_layer.py:175-184)
+            double nx = GF(F_REC2X, o) + 0.5 * evx_raw;
+            GF(F_REC2X, o) = nx;
+            has_oa = true; id_oa = o;
+            x_oa = nx;
+            vx_oa = GF(F_REC2VX, o);
+            constrain_adj = true;
+            a_oa = ACC_LO;
+            g_oa = 1.0;
+        } else if (!has_ol && d > 0) {
+            bool same = (elane == olane) || (olane == next_lane(elane, ex, ey));
+            if (same || approaching) {
+                has_ol = true; id_ol = o;
+                x_ol = GF(F_REC2X, o);
+                vx_ol = GF(F_REC2VX, o);
+                if (mass) {
+                    a_ol = o_cav ? GF(F_SAFE_ACC, o) : ACC_LO;
+                    g_ol = o_cav ? GF(F_GVX, o) : 1.0;
+                }
+            }
+        }
+    }
+    // the obstacle can take over either role (decentral_layer.py:213-246)
+    if (!(ex > OBST_X)) {
+        double ady = fabs(OBST_Y - ey);
+        if ((!has_ol || OBST_X <= x_ol) && ady <= 2) {
+            has_ol = true; id_ol = MM_NB_OBSTACLE; x_ol = OBST_X; vx_ol = 0;
+            if (mass) { a_ol = 0; g_ol = 0; }
+        }
+        if ((!has_oa || OBST_X <= x_oa) && 2 < ady && ady <= 4) {
+            has_oa = true; id_oa = MM_NB_OBSTACLE; x_oa = OBST_X; vx_oa = 0;
+            if (mass) { a_oa = 0; g_oa = 0; constrain_adj = false; }
+        }
+    }
+    if (!mass) { g_ol = 1.0; g_oa = 1.0; }
+
+    // safe distances and headway (decentral_layer.py:448-468)
+    double sv_oar = (has_oar ? vx_oar : 0.0) + ACC_HI * dt;
+    sv_oar = sv_oar > 1 ? sv_oar : 1;
+    double buffer = (ACC_HI + 0.1) * dt * tau;
+    double sd_l = evx * tau + VLEN + buffer;
+    double sd_r = sv_oar * tau + VLEN + buffer;
+    GF(F_MINHW, self) = (x_ol - ex - VLEN) / evx;
+
+    // one-step predictions (decentral_layer.py:60-77)
+    double v_ll = fmax(0.0, evx + act_acc * dt);
+    double v_ol = has_ol ? fmax(0.0, vx_ol + (mass ? a_ol : ACC_LO) * dt) : 0.0;
+    double v_oa = has_oa ? fmax(0.0, vx_oa + (mass ? a_oa : ACC_LO) * dt) : 0.0;
+    double v_oar = has_oar ? fmax(0.0, vx_oar + ACC_HI * dt) : 0.0;
+
+    double q_lon = -VLEN - sd_l;
+    double q_lona = -VLEN - sd_l;
+    bool has_adj = mass && constrain_adj;
+    if (has_adj) q_lona = -VLEN - sd_l - 2.0134;
+    double q_lonr = -VLEN - sd_r;
+
+    double ge_dt = GF(F_GVX, self) * dt, gol_dt = g_ol * dt, goa_dt = g_oa * dt, gr_dt = 1 * dt;
+    double dl = -ex + x_ol, da = -ex + x_oa, dr = ex + -x_oar;
+    double c_lead = dl + (eta - 1) * dl + eta * q_lon + (-(ge_dt * v_ll) + gol_dt * v_ol);
+    double c_adj = 0.0;
+    if (has_adj) c_adj = da + (eta - 1) * da + eta * q_lona + (-(ge_dt * v_ll) + goa_dt * v_oa);
+    double hi = v_max - v_ll;
+    double lo = -(-v_min + v_ll);
+    int active;
+    double u = solve_cbf_qp(ge_dt, c_lead, c_adj, has_adj, lo, hi, active);
+    double v_safe = v_ll + u;
+
+    // lane-change veto (cbf.py:324-339)
+    double hls_a = da + q_lona;
+    double hlds_a = da + (-ge_dt * v_safe + goa_dt * v_oa) + q_lona;
+    double hls_r = dr + q_lonr;
+    double hlds_r = dr + (ge_dt * v_safe + -gr_dt * v_oar) + q_lonr;
+    double cond_a = hlds_a + (eta - 1) * hls_a;
+    double cond_r = hlds_r + (eta - 1) * hls_r;
+    bool allowed = (hls_a >= 0 && cond_a >= 0) && (hls_r >= 0 && cond_r >= 0);
+    rec.lc_margin = fmin(fmin(fabs(hls_a), fabs(cond_a)), fmin(fabs(hls_r), fabs(cond_r)));
+
+    double steer = act_steer;
+    bool lc_safe = true;
+    bool veto;
+    if (!mass) {
+        veto = !allowed;
+    } else {
+        double cx, cy;
+        get_corner(ex, ey, eh, true, cx, cy);
+        bool can_abort = on_lane(elane, cx, cy, 0.0);
+        get_corner(ex, ey, eh, false, cx, cy);
+        can_abort = can_abort && on_lane(elane, cx, cy, 0.0);
+        veto = can_abort && !allowed;
+        int hl = fl_hl(f);
+        if (!veto && (hl == A_LANE_RIGHT || hl == A_LANE_LEFT) && espeed < 1.6667) v_safe = v_ll;
+        f = cond_a >= -1e-6 ? (f | FL_CADJ) : (f & ~FL_CADJ);
+    }
+    if (veto) {
+        f = fl_set(f, FL_TLANE_SHIFT, FL_3BIT, (uint32_t)elane);
+        steer = steering_control(ex, ey, eh, espeed, elane);
+        lc_safe = false;
+    }
+    f = constrain_adj ? (f | FL_COLLAB) : (f & ~FL_COLLAB);
+    f = lc_safe ? (f | FL_LCSAFE) : (f & ~FL_LCSAFE);
+    FL(self) = f;
+
+    out_acc = (v_safe - evx) / dt;
+    out_steer = steer;
+    rec.leader = id_ol; rec.front_adj = id_oa; rec.rear_adj = id_oar;
+    rec.constrain_adj = constrain_adj; rec.active = active; rec.is_lc_safe = lc_safe;
+}
+
+// ------------------------------------------------------------------------------------------------
+// integration (kinematics.py:122-152, safe_controller.py:100-185, behavior.py:102-109,504-522)
+// ------------------------------------------------------------------------------------------------
+template <bool DIAG>
+__device__ void vehicle_step(Env &ev, const StepParams &p, int i, int sub, size_t e_glob, double *stat_acc) {
+    uint32_t f = FL(i);
+    const bool cav = fl_kind(f) == MM_KIND_CAV;
+    const double dt = p.cfg.dt;
+    double speed = V(i), heading = H(i);
+    double steer = GF(F_ACT_STEER, i), acc = GF(F_ACT_ACC, i);
+    if (!cav) GF(F_TIMER, i) = GF(F_TIMER, i) + dt;
+    // clip_actions
+    if (f & FL_CRASHED) { steer = 0.0; acc = -1.0 * speed; }
+    if (speed > 40.0) acc = fmin(acc, 1.0 * (40.0 - speed));
+    else if (speed < -40.0) acc = fmax(acc, 1.0 * (40.0 - speed));
+    if (cav) {
+        acc = clipd(acc, ACC_LO, ACC_HI);
+        GF(F_ACT_STEER, i) = steer;
+        GF(F_ACT_ACC, i) = acc;
+        // get_safe_action gate (safe_controller.py:229-239)
+        if (p.cfg.shield != MM_SHIELD_NONE && (f & FL_FG) && fl_hist(f) >= 2) {
+            ShieldRec rec;
+            double nom_steer = steer, nom_acc = acc;
+            shield(ev, p.cfg, i, steer, acc, rec);
+            f = FL(i);
+            stat_acc[ST_SOLVES] += 1;
+            stat_acc[ST_ACTIVE] += rec.active != 0;
+            stat_acc[ST_VETOES] += !rec.is_lc_safe;
+            if (DIAG) {
+                size_t plane = (size_t)p.n_envs * 3 * MAXV;
+                size_t idx = (e_glob * 3 + sub) * MAXV + i;
+                int32_t *si = p.out.sh_i;
+                si[idx] = 1; si[plane + idx] = rec.leader; si[2 * plane + idx] = rec.front_adj;
+                si[3 * plane + idx] = rec.rear_adj; si[4 * plane + idx] = rec.constrain_adj;
+                si[5 * plane + idx] = rec.active; si[6 * plane + idx] = rec.is_lc_safe;
+                double *sf = p.out.sh_f;
+                sf[idx] = acc; sf[plane + idx] = steer; sf[2 * plane + idx] = nom_acc;
+                sf[3 * plane + idx] = nom_steer; sf[4 * plane + idx] = rec.lc_margin;
+            }
+        }
+        GF(F_SAFE_STEER, i) = steer;
+        GF(F_SAFE_ACC, i) = acc;
+    } else {
+        GF(F_ACT_STEER, i) = steer;
+        GF(F_ACT_ACC, i) = acc;
+    }
+    // modified bicycle model
+    double beta = atan(1.0 / 2 * tan(steer));
+    double sn, cs;
+    sincos(heading + beta, &sn, &cs);
+    double nx = X(i) + speed * cs * dt;
+    double ny = Y(i) + speed * sn * dt;
+    double nh = heading + speed * sin(beta) / (VLEN / 2) * dt;
+    double nv = fmax(0.0, speed + acc * dt);
+    if (cav) {
+        GF(F_GVX, i) = cos(nh + beta);
+        f |= FL_FG;
+    }
+    // on_state_update + log_step
+    int lane = closest_lane(nx, ny, nh);
+    f = fl_set(f, FL_LANE_SHIFT, FL_3BIT, (uint32_t)lane);
+    GF(F_REC2X, i) = X(i);
+    GF(F_REC2VX, i) = GF(F_REC1VX, i);
+    GF(F_REC1VX, i) = nv * cos(nh);
+    int hist = fl_hist(f);
+    if (hist < 2) f = fl_set(f, FL_HIST_SHIFT, 3u, (uint32_t)(hist + 1));
+    X(i) = nx; Y(i) = ny; H(i) = nh; V(i) = nv;
+    FL(i) = f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// collisions (road.py:288-292, kinematics.py:175-209, utils.py:55-121)
+// ------------------------------------------------------------------------------------------------
+// does rect1 (centre c1, half sizes lx/wy, angle a1) have one of its 9 sample points inside rect2?
+// NB the reference rotates (p - c2) by +a2, not -a2; reproduced as is.
+__device__ bool has_corner_inside(double c1x, double c1y, double lx, double wy, double a1, double c2x, double c2y,
+                                  double l2, double w2, double a2) {
+    double s1, co1, s2, co2;
+    sincos(a1, &s1, &co1);
+    sincos(a2, &s2, &co2);
+    const double px[9] = {0, -lx, lx, 0, 0, -lx, -lx, lx, lx};
+    const double py[9] = {0, 0, 0, -wy, wy, -wy, wy, -wy, wy};
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        double rx = co1 * px[k] + -s1 * py[k];
+        double ry = s1 * px[k] + co1 * py[k];
+        double dx = (c1x + rx) - c2x, dy = (c1y + ry) - c2y;
+        double ux = co2 * dx + -s2 * dy;
+        double uy = s2 * dx + co2 * dy;
+        if (-l2 / 2 <= ux && ux <= l2 / 2 && -w2 / 2 <= uy && uy <= w2 / 2) return true;
+    }
+    return false;
+}
+
+__device__ __noinline__ bool rects_intersect(double ax, double ay, double ah, double bx, double by, double bh,
+                                             double blen, double bwid) {
+    return has_corner_inside(ax, ay, 0.9 * VLEN / 2, 0.9 * VWID / 2, ah, bx, by, 0.9 * blen, 0.9 * bwid, bh) ||
+           has_corner_inside(bx, by, 0.9 * blen / 2, 0.9 * bwid / 2, bh, ax, ay, 0.9 * VLEN, 0.9 * VWID, ah);
+}
+
+__device__ void collision_pass(Env &ev) {
+    for (int i = 0; i < ev.n_veh; ++i) {
+        double ax = X(i), ay = Y(i);
+        for (int j = 0; j < ev.n_veh; ++j) {
+            if (j == i) continue;
+            if (FL(i) & FL_CRASHED) break;
+            double dx = X(j) - ax, dy = Y(j) - ay;
+            if (sqrt(dx * dx + dy * dy) > VLEN) continue;
+            if (rects_intersect(ax, ay, H(i), X(j), Y(j), H(j), VLEN, VWID)) {
+                double va = V(i), vb = V(j);
+                double m = fabs(va) <= fabs(vb) ? va : vb;
+                V(i) = m; V(j) = m;
+                FL(i) |= FL_CRASHED; FL(j) |= FL_CRASHED;
+            }
+        }
+        if (!(FL(i) & FL_CRASHED)) {
+            double dx = OBST_X - ax, dy = OBST_Y - ay;
+            if (!(sqrt(dx * dx + dy * dy) > VLEN) && rects_intersect(ax, ay, H(i), OBST_X, OBST_Y, 0.0, 2.0, 2.0)) {
+                double va = V(i);
+                V(i) = fabs(va) <= 0 ? va : 0.0;
+                FL(i) |= FL_CRASHED;
+            }
+        }
+    }
+}
+
+// merge_env_v1.py:168-172
+__device__ __forceinline__ bool is_terminal(const Env &ev, int steps, int duration_steps) {
+    bool t = steps >= duration_steps;
+    for (int i = 0; i < ev.n_cav; ++i) t = t || (FL(i) & FL_CRASHED) || X(i) < 0;
+    return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// observation, rewards, info
+// ------------------------------------------------------------------------------------------------
+// observation.py:241-273 + normalize_obs 181-193: ego row absolute, 4 nearest rows relative, no clipping
+__device__ void observe_agent(const Env &ev, int self, float *obs) {
+    double es, ec;
+    sincos(H(self), &es, &ec);
+    double ex = X(self), ey = Y(self), evx = V(self) * ec, evy = V(self) * es;
+    int nb[4];
+    int n_nb = close_vehicles<4>(ev, self, nb);
+    float row[NS];
+    row[0] = 1.0f;
+    row[1] = (float)lmap(ex, -150.0, 150.0, -1, 1);
+    row[2] = (float)lmap(ey, -12, 12, -1, 1);
+    row[3] = (float)lmap(evx, -45.0, 45.0, -1, 1);
+    row[4] = (float)lmap(evy, -45.0, 45.0, -1, 1);
+    row[5] = (float)lmap(H(self), -PI / 2, PI / 2, -1, 1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float *r = row + (k + 1) * MM_OBS_FEATS;
+        if (k < n_nb) {
+            int o = nb[k];
+            double os, oc;
+            sincos(H(o), &os, &oc);
+            r[0] = 1.0f;
+            r[1] = (float)lmap(X(o) - ex, -150.0, 150.0, -1, 1);
+            r[2] = (float)lmap(Y(o) - ey, -12, 12, -1, 1);
+            r[3] = (float)lmap(V(o) * oc - evx, -45.0, 45.0, -1, 1);
+            r[4] = (float)lmap(V(o) * os - evy, -45.0, 45.0, -1, 1);
+            r[5] = (float)lmap(H(o), -PI / 2, PI / 2, -1, 1);
+        } else {
+#pragma unroll
+            for (int q = 0; q < MM_OBS_FEATS; ++q) r[q] = 0.0f;
+        }
+    }
+    float2 *dst = reinterpret_cast<float2 *>(obs);  // 120-byte rows: 8-byte aligned
+#pragma unroll
+    for (int q = 0; q < NS / 2; ++q) dst[q] = make_float2(row[2 * q], row[2 * q + 1]);
+}
+
+// abstract.py:620-635
+__device__ double headway_distance(const Env &ev, int self) {
+    double ex = X(self), hd = 60;
+    int lane = fl_lane(FL(self));
+    int nl = next_lane(lane, ex, Y(self));
+    bool use_next = lane != L_BC1;
+    for (int j = 0; j < ev.n_veh; ++j) {
+        int lj = fl_lane(FL(j));
+        double d = X(j) - ex;
+        if (X(j) > ex && (lj == lane || (use_next && lj == nl)) && d < hd) hd = d;
+    }
+    return hd;
+}
+
+// merge_env_v1.py:64-89 and 439-474
+__device__ double agent_reward(const Env &ev, const mm_config &cfg, int self, double hd) {
+    uint32_t f = FL(self);
+    bool special = cfg.reward_kind != MM_REW_DEFAULT && fl_kind(f) == MM_KIND_CAV;
+    bool mrew = cfg.reward_kind == MM_REW_MREW;
+    double speed = V(self);
+    double r1 = 30.0;
+    if (special && mrew && (f & FL_COLLAB)) r1 = 10.0 + (30.0 - 10.0) / 2;
+    double scaled = lmap(speed, 10.0, r1, 0, 1);
+    double merging = 0.0;
+    if (fl_lane(f) == L_BC1 && (!special || !mrew || (f & FL_LCSAFE))) {
+        double d = X(self) - 420.0;
+        merging = -exp(-(d * d) / (10 * 100.0));
+    }
+    double hc = 0.0;
+    if (speed > 0) {
+        hc = log(hd / (cfg.headway_time * speed));
+        if (special) hc = -1 * hc;
+    }
+    double crashed = (f & FL_CRASHED) ? 1.0 : 0.0;
+    return cfg.collision_reward * (-1 * crashed) + (cfg.high_speed_reward * clipd(scaled, 0.0, 1.0)) +
+           cfg.merging_lane_cost * merging + cfg.headway_cost * (hc < 0 ? hc : 0.0);
+}
+
+// road.py:294-350: visibility groups by query lane, bit l of the mask = lane l is visible
+__device__ __forceinline__ void surrounding(const Env &ev, int self, int qlane, int &front, int &rear) {
+    const uint32_t masks[N_LANES] = {0x03u, 0x0Bu, 0x24u, 0x0Au, 0x30u, 0x34u};
+    uint32_t m = masks[qlane];
+    double s = X(self), s_front = 0, s_rear = 0;
+    front = -1;
+    rear = -1;
+    for (int j = 0; j < ev.n_veh; ++j) {
+        if (j == self || !((m >> fl_lane(FL(j))) & 1u)) continue;
+        double s_v = X(j);
+        if (s <= s_v && (front < 0 || s_v <= s_front)) { s_front = s_v; front = j; }
+        if (s_v < s && (rear < 0 || s_v > s_rear)) { s_rear = s_v; rear = j; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// x-descending stable order packed as 4-bit slot ids (road.py:277,286)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t order_by_x_desc(const Env &ev) {
+    uint64_t ord = 0;
+    for (int i = 0; i < ev.n_veh; ++i) {
+        double xi = X(i);
+        int p = i;
+        while (p > 0 && X((int)((ord >> (4 * (p - 1))) & 15u)) < xi) --p;
+        uint64_t low = ord & ((1ull << (4 * p)) - 1ull);
+        uint64_t high = (ord >> (4 * p)) << (4 * (p + 1));
+        ord = low | ((uint64_t)i << (4 * p)) | high;
+    }
+    return ord;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the policy-step kernel
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_env(Env &ev, const DevState &st, size_t e, size_t E) {
+    for (int i = 0; i < ev.n_veh; ++i) {
+        X(i) = st.f64[((size_t)F_X * MAXV + i) * E + e];
+        Y(i) = st.f64[((size_t)F_Y * MAXV + i) * E + e];
+        H(i) = st.f64[((size_t)F_H * MAXV + i) * E + e];
+        V(i) = st.f64[((size_t)F_V * MAXV + i) * E + e];
+        FL(i) = st.flags[(size_t)i * E + e];
+    }
+}
+__device__ __forceinline__ void store_env(const Env &ev, const DevState &st, size_t e, size_t E) {
+    for (int i = 0; i < ev.n_veh; ++i) {
+        st.f64[((size_t)F_X * MAXV + i) * E + e] = X(i);
+        st.f64[((size_t)F_Y * MAXV + i) * E + e] = Y(i);
+        st.f64[((size_t)F_H * MAXV + i) * E + e] = H(i);
+        st.f64[((size_t)F_V * MAXV + i) * E + e] = V(i);
+        st.flags[(size_t)i * E + e] = FL(i);
+    }
+}
+
+// observation + rewards + info for one env whose hot state is staged in `ev` (abstract.py:469-498,
+// merge_env_v1.py:126-166)
+__device__ void write_outputs(const Env &ev, const StepParams &p, size_t e, int steps, int n_merge, bool with_rewards,
+                              double *stat_acc) {
+    const DevOut &o = p.out;
+    float *obs = o.obs + e * (size_t)(MAXV * NS);
+    for (int i = 0; i < ev.n_cav; ++i) observe_agent(ev, i, obs + i * NS);
+    float2 *z = reinterpret_cast<float2 *>(obs + ev.n_cav * NS);
+    for (int q = 0; q < (MAXV - ev.n_cav) * NS / 2; ++q) z[q] = make_float2(0.f, 0.f);
+    o.n_agents[e] = ev.n_cav;
+    if (!with_rewards) return;
+
+    double local[MAXV];
+    double rsum = 0, ssum = 0, tsum = 0, minhw = CUDART_INF;
+    bool done = is_terminal(ev, steps, p.cfg.duration_steps);
+    bool any_crash = false;
+#pragma unroll 1
+    for (int i = 0; i < ev.n_cav; ++i) {
+        double hd = headway_distance(ev, i);
+        local[i] = agent_reward(ev, p.cfg, i, hd);
+        rsum += local[i];
+        ssum += V(i);
+        // merge_env_v1.py:373-386
+        double ex = X(i);
+        if (fabs(OBST_Y - Y(i)) <= 2 && OBST_X > ex) {
+            double d = OBST_X - ex;
+            if (d < hd) hd = d;
+        }
+        hd = hd - VLEN;
+        double vx = V(i) * cos(H(i));
+        minhw = fmin(minhw, hd / (vx > 1 ? vx : 1));
+        any_crash = any_crash || (FL(i) & FL_CRASHED);
+    }
+    for (int i = 0; i < ev.n_veh; ++i) tsum += V(i);
+    int n_rem = 0;
+#pragma unroll 1
+    for (int i = 0; i < MAXV; ++i) {
+        float lr = 0.f, rr = 0.f;
+        uint8_t ad = 0;
+        if (i < ev.n_cav) {
+            // regional reward (merge_env_v1.py:91-124)
+            int lane = fl_lane(FL(i));
+            int fl_ = -1, rl = -1, fr = -1, rrr = -1;
+            if (lane == L_AB0 || lane == L_BC0 || lane == L_CD0) {
+                surrounding(ev, i, lane, fl_, rl);
+                if (lane == L_BC0) surrounding(ev, i, L_BC1, fr, rrr);
+                else if (lane == L_AB0 && X(i) > 220) surrounding(ev, i, L_KB0, fr, rrr);
+            } else {
+                surrounding(ev, i, lane, fr, rrr);
+                if (lane == L_BC1) surrounding(ev, i, L_BC0, fl_, rl);
+                else if (lane == L_KB0) surrounding(ev, i, L_AB0, fl_, rl);
+            }
+            int cand[5] = {fl_, fr, i, rl, rrr};
+            double sum = 0;
+            int cnt = 0;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                int j = cand[k];
+                if (j >= 0 && j < ev.n_cav) { sum = sum + local[j]; ++cnt; }
+            }
+            lr = (float)local[i];
+            rr = (float)(sum / cnt);
+            ad = ((FL(i) & FL_CRASHED) || steps >= p.cfg.duration_steps || X(i) < 0) ? 1 : 0;
+            if (lane == L_BC1 || lane == L_KB0 || lane == L_JK0) ++n_rem;
+        }
+        o.agents_rewards[e * MAXV + i] = lr;
+        o.regional_rewards[e * MAXV + i] = rr;
+        o.agents_dones[e * MAXV + i] = ad;
+    }
+    double reward = rsum / ev.n_cav;
+    o.reward[e] = (float)reward;
+    o.done[e] = done ? 1 : 0;
+    o.average_speed[e] = (float)(ssum / ev.n_cav);
+    o.traffic_speed[e] = (float)(tsum / ev.n_veh);
+    o.min_headway[e] = (float)minhw;
+    double mp = -1.0;
+    if (done) mp = n_merge > 0 ? (double)(n_merge - n_rem) / n_merge * 100 : 100.0;
+    o.merge_percent[e] = (float)mp;
+
+    stat_acc[ST_AGENT_STEPS] += ev.n_cav;
+    stat_acc[ST_ENV_STEPS] += 1;
+    stat_acc[ST_REWARD] += reward;
+    stat_acc[ST_SPEED] += ssum / ev.n_cav;
+    stat_acc[ST_MINHW] = fmin(stat_acc[ST_MINHW], minhw);
+    if (done) {
+        stat_acc[ST_EPISODES] += 1;
+        stat_acc[ST_CRASHED] += any_crash;
+        stat_acc[ST_MERGE] += mp;
+    }
+}
+
+__device__ __forceinline__ void flush_stats(double *stat_acc, double *stats, size_t first_env_of_warp) {
+    // one row of partial sums per warp of envs: no atomics on the step path; mm_stats() folds the rows
+    const unsigned full = 0xffffffffu;
+    size_t warp_row = first_env_of_warp >> 5;
+#pragma unroll
+    for (int k = 0; k < N_STATS; ++k) {
+        double v = stat_acc[k];
+        for (int off = 16; off > 0; off >>= 1) {
+            double o = __shfl_down_sync(full, v, off);
+            v = (k == ST_MINHW) ? fmin(v, o) : v + o;
+        }
+        if ((threadIdx.x & 31) == 0) {
+            double *dst = stats + warp_row * N_STATS + k;
+            *dst = (k == ST_MINHW) ? fmin(*dst, v) : *dst + v;
+        }
+    }
+}
+
+template <bool DIAG>
+__global__ void __launch_bounds__(BLOCK, 3) step_kernel(const __grid_constant__ StepParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sm = reinterpret_cast<double *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int local = blockIdx.x * BLOCK + tid;
+    const bool valid = local < p.env_count;
+    const size_t E = (size_t)p.n_envs;
+    const size_t e = (size_t)p.env_offset + (valid ? local : 0);
+
+    double stat_acc[N_STATS];
+#pragma unroll
+    for (int k = 0; k < N_STATS; ++k) stat_acc[k] = 0.0;
+    stat_acc[ST_MINHW] = CUDART_INF;
+
+    if (valid) {
+        Env ev;
+        ev.sx = sm + tid;
+        ev.sy = sm + MAXV * BLOCK + tid;
+        ev.sh = sm + 2 * MAXV * BLOCK + tid;
+        ev.sv = sm + 3 * MAXV * BLOCK + tid;
+        ev.sf = reinterpret_cast<uint32_t *>(sm + 4 * MAXV * BLOCK) + tid;
+        ev.g = p.st.f64 + e;
+        ev.E = E;
+        uint32_t ei = p.st.einfo[e];
+        ev.n_veh = (ei >> EI_NVEH_SHIFT) & EI_4BIT;
+        ev.n_cav = (ei >> EI_NCAV_SHIFT) & EI_4BIT;
+        int n_merge = (ei >> EI_NMERGE_SHIFT) & EI_4BIT;
+        int steps = (ei >> EI_STEPS_SHIFT) & EI_STEPS_MASK;
+        int time = (ei >> EI_TIME_SHIFT) & EI_TIME_MASK;
+        load_env(ev, p.st, e, E);
+
+        // 12 action bytes of this env
+        int8_t act[MAXV];
+        {
+            const uint32_t *a32 = reinterpret_cast<const uint32_t *>(p.actions + e * MAXV);
+#pragma unroll
+            for (int w = 0; w < MAXV / 4; ++w) {
+                uint32_t v = a32[w];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) act[w * 4 + b] = (int8_t)((v >> (8 * b)) & 0xff);
+            }
+        }
+        if (DIAG) {
+            size_t plane = (size_t)p.n_envs * 3 * MAXV;
+            for (int k = 0; k < 3 * MAXV; ++k) {
+                size_t idx = e * 3 * MAXV + k;
+                p.out.sh_i[idx] = 0;
+                p.out.sh_i[plane + idx] = MM_NB_NONE; p.out.sh_i[2 * plane + idx] = MM_NB_NONE;
+                p.out.sh_i[3 * plane + idx] = MM_NB_NONE;
+                p.out.sh_i[4 * plane + idx] = 0; p.out.sh_i[5 * plane + idx] = 0; p.out.sh_i[6 * plane + idx] = 0;
+                for (int q = 0; q < 5; ++q) p.out.sh_f[q * plane + idx] = 0.0;
+            }
+        }
+
+        steps = min(steps + 1, (int)EI_STEPS_MASK);  // abstract.py:457
+#pragma unroll 1
+        for (int sub = 0; sub < p.cfg.substeps; ++sub) {  // abstract.py:514-531
+            if (time % p.cfg.substeps == 0) {
+                for (int i = 0; i < ev.n_cav; ++i) {
+                    int a = act[i];
+                    cav_act(ev, i, (a >= 0 && a <= 4) ? a : A_IDLE);
+                }
+            }
+            uint64_t ord = order_by_x_desc(ev);
+#pragma unroll 1
+            for (int q = 0; q < ev.n_veh; ++q) {  // road.act()
+                int i = (int)((ord >> (4 * q)) & 15u);
+                if (fl_kind(FL(i)) == MM_KIND_CAV) cav_act(ev, i, A_NONE);
+                else hdv_act(ev, i);
+            }
+#pragma unroll 1
+            for (int q = 0; q < ev.n_veh; ++q) {  // road.step(dt): same order, positions did not move
+                int i = (int)((ord >> (4 * q)) & 15u);
+                vehicle_step<DIAG>(ev, p, i, sub < 3 ? sub : 2, e, stat_acc);
+            }
+            collision_pass(ev);
+            time = min(time + 1, (int)EI_TIME_MASK);
+            if (is_terminal(ev, steps, p.cfg.duration_steps)) break;
+        }
+
+        write_outputs(ev, p, e, steps, n_merge, true, stat_acc);
+        store_env(ev, p.st, e, E);
+        p.st.einfo[e] = (ei & 0xfffu) | ((uint32_t)steps << EI_STEPS_SHIFT) | ((uint32_t)time << EI_TIME_SHIFT);
+    }
+    flush_stats(stat_acc, p.out.stats, (size_t)p.env_offset + (size_t)(local & ~31));
+}
+
+// observation only (reset() / set_state refresh)
+__global__ void __launch_bounds__(BLOCK) observe_kernel(const __grid_constant__ StepParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sm = reinterpret_cast<double *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int local = blockIdx.x * BLOCK + tid;
+    if (local >= p.env_count) return;
+    const size_t E = (size_t)p.n_envs;
+    const size_t e = (size_t)p.env_offset + local;
+    if (p.obs_mask && !p.obs_mask[e]) return;
+    Env ev;
+    ev.sx = sm + tid;
+    ev.sy = sm + MAXV * BLOCK + tid;
+    ev.sh = sm + 2 * MAXV * BLOCK + tid;
+    ev.sv = sm + 3 * MAXV * BLOCK + tid;
+    ev.sf = reinterpret_cast<uint32_t *>(sm + 4 * MAXV * BLOCK) + tid;
+    ev.g = p.st.f64 + e;
+    ev.E = E;
+    uint32_t ei = p.st.einfo[e];
+    ev.n_veh = (ei >> EI_NVEH_SHIFT) & EI_4BIT;
+    ev.n_cav = (ei >> EI_NCAV_SHIFT) & EI_4BIT;
+    load_env(ev, p.st, e, E);
+    write_outputs(ev, p, e, 0, 0, false, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-side spawn (merge_env_v1.py:180-211, 265-364; abstract.py:176-199) with Philox4x32-10
+// ------------------------------------------------------------------------------------------------
+struct Philox {
+    uint32_t key[2], ctr[4], out[4];
+    int have;
+    __device__ Philox(uint64_t seed, uint64_t stream, uint32_t episode) {
+        key[0] = (uint32_t)seed; key[1] = (uint32_t)(seed >> 32);
+        ctr[0] = 0; ctr[1] = episode; ctr[2] = (uint32_t)stream; ctr[3] = (uint32_t)(stream >> 32);
+        have = 0;
+    }
+    __device__ void round_(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    }
+    __device__ uint32_t next() {
+        if (have == 0) {
+            uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
+            uint32_t k0 = key[0], k1 = key[1];
+#pragma unroll
+            for (int r = 0; r < 10; ++r) {
+                round_(c, k0, k1);
+                k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+            }
+            out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+            ctr[0]++;
+            have = 4;
+        }
+        return out[--have];
+    }
+    __device__ double uniform() {  // [0, 1) with 53 bits
+        uint64_t a = next(), b = next();
+        return (double)(((a << 21) ^ b) & ((1ull << 53) - 1)) * (1.0 / 9007199254740992.0);
+    }
+    __device__ int below(int n) { return (int)(((uint64_t)next() * (uint64_t)n) >> 32); }
+};
+
+__global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ ResetParams p) {
+    const int local = blockIdx.x * BLOCK + threadIdx.x;
+    if (local >= p.env_count) return;
+    const size_t E = (size_t)p.n_envs;
+    const size_t e = (size_t)p.env_offset + local;
+    if (p.use_done) { if (!p.out.done[e]) return; }
+    else if (p.mask && !p.mask[e]) return;
+
+    uint32_t episode = p.st.episode[e];
+    p.st.episode[e] = episode + 1;
+    Philox rng(p.seed, (uint64_t)e, episode);
+
+    // _num_vehicles (merge_env_v1.py:180-211, 476-495)
+    int lo_c, lo_h;
+    switch (p.cfg.traffic_density) {
+        case 1: lo_c = 1; lo_h = 1; break;
+        case 2: lo_c = 2; lo_h = 2; break;
+        default: lo_c = 4; lo_h = 3; break;
+    }
+    int n_cav = p.num_cav > 0 ? p.num_cav : lo_c + rng.below(3);
+    int n_hdv = lo_h + rng.below(3);
+    if (p.cfg.traffic_type == MM_TRAFFIC_CAV) { n_cav += n_hdv; n_hdv = 0; }
+    if (n_cav + n_hdv > 11) n_cav = 11 - n_hdv;
+
+    // spawn slots without replacement: main [10,60,...,260], ramp [5,55,...,255] (merge_env_v1.py:284-319)
+    int main_slots[6] = {0, 1, 2, 3, 4, 5}, ramp_slots[6] = {0, 1, 2, 3, 4, 5};
+    for (int k = 0; k < 5; ++k) {  // Fisher-Yates: a uniformly random order of the six slots of each road
+        int j = k + rng.below(6 - k);
+        int t = main_slots[k]; main_slots[k] = main_slots[j]; main_slots[j] = t;
+        j = k + rng.below(6 - k);
+        t = ramp_slots[k]; ramp_slots[k] = ramp_slots[j]; ramp_slots[j] = t;
+    }
+    int n_s_c = n_cav != 1 ? n_cav / 2 : rng.below(2);
+    int n_m_c = n_cav - n_s_c;
+    int n_s_h = n_hdv != 1 ? n_hdv / 2 : rng.below(2);
+    int n_m_h = n_hdv - n_s_h;
+    if (n_s_c + n_s_h > 6) n_s_h = 6 - n_s_c;
+    if (n_m_c + n_m_h > 6) n_m_h = 6 - n_m_c;
+    int n_veh = n_s_c + n_m_c + n_s_h + n_m_h;
+    n_hdv = n_s_h + n_m_h;
+
+    int mi = 0, ri = 0;
+    for (int i = 0; i < MAXV; ++i) {
+        double *g = p.st.f64 + e;
+        uint32_t f = 0;
+        double x = 0, y = 0, speed = 0, tspeed = 0, timer = 0;
+        if (i < n_veh) {
+            bool cav = i < n_cav;
+            bool on_main = cav ? (i < n_s_c) : (i - n_cav < n_s_h);
+            double noise = rng.uniform() * 8 - 4;
+            speed = rng.uniform() * 2 + 25;
+            if (on_main) { x = 10.0 + 50.0 * main_slots[mi++] + noise; y = 0.0; }
+            else { x = 5.0 + 50.0 * ramp_slots[ri++] + noise; y = 10.5; }
+            int lane = closest_lane(x, y, 0.0);
+            int sidx = 0;
+            if (cav) {
+                sidx = speed_to_index(speed);
+                tspeed = 10.0 + sidx * (30.0 - 10.0) / 4;
+            } else {
+                tspeed = speed;
+                timer = pymod_pos((x + y) * PI, 1.0);  // behavior.py:54
+            }
+            f = (uint32_t)(cav ? MM_KIND_CAV : MM_KIND_HDV) | ((uint32_t)lane << FL_LANE_SHIFT) |
+                ((uint32_t)lane << FL_TLANE_SHIFT) | ((uint32_t)sidx << FL_SIDX_SHIFT) | ((uint32_t)A_NONE << FL_HL_SHIFT);
+        }
+        for (int fld = 0; fld < F_COUNT; ++fld) g[((size_t)fld * MAXV + i) * E] = 0.0;
+        g[((size_t)F_X * MAXV + i) * E] = x;
+        g[((size_t)F_Y * MAXV + i) * E] = y;
+        g[((size_t)F_V * MAXV + i) * E] = speed;
+        g[((size_t)F_TSPEED * MAXV + i) * E] = tspeed;
+        g[((size_t)F_TIMER * MAXV + i) * E] = timer;
+        g[((size_t)F_MINHW * MAXV + i) * E] = 180.0 / 40.0;  // safe_controller.py:56
+        p.st.flags[(size_t)i * E + e] = f;
+    }
+    p.st.einfo[e] = (uint32_t)n_veh | ((uint32_t)n_cav << EI_NCAV_SHIFT) | ((uint32_t)n_m_c << EI_NMERGE_SHIFT);
+}
+
+// ------------------------------------------------------------------------------------------------
+// state (un)packing between the env-major host mirror and the SoA planes
+// ------------------------------------------------------------------------------------------------
+// host mirror field order (mm_state_host): f64: x y heading speed target_speed gvx rec1_x rec1_vx rec2_x rec2_vx
+// act_steer act_acc safe_steer safe_acc timer min_headway; i32: kind lane target_lane speed_index crashed
+// hl_action hist_len fg_set is_collaborating is_lc_safe collaborate_adj; env: n_veh n_cav n_merge steps time
+__constant__ int c_host_f64_to_field[16] = {F_X, F_Y, F_H, F_V, F_TSPEED, F_GVX, -1, F_REC1VX, F_REC2X, F_REC2VX,
+                                            F_ACT_STEER, F_ACT_ACC, F_SAFE_STEER, F_SAFE_ACC, F_TIMER, F_MINHW};
+
+__global__ void pack_state_kernel(DevState st, int n_envs, const double *f64_em, const int32_t *i32_em,
+                                  const int32_t *env_em) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t E = (size_t)n_envs;
+    if (idx >= E * MAXV) return;
+    size_t e = idx / MAXV;
+    int i = (int)(idx % MAXV);
+    for (int k = 0; k < 16; ++k) {
+        int fld = c_host_f64_to_field[k];
+        if (fld >= 0) st.f64[((size_t)fld * MAXV + i) * E + e] = f64_em[(size_t)k * E * MAXV + idx];
+    }
+    const size_t P = E * MAXV;
+    int hl = i32_em[5 * P + idx];
+    int hist = i32_em[6 * P + idx];
+    uint32_t f = ((uint32_t)i32_em[0 * P + idx] & 3u) | (((uint32_t)i32_em[1 * P + idx] & 7u) << FL_LANE_SHIFT) |
+                 (((uint32_t)i32_em[2 * P + idx] & 7u) << FL_TLANE_SHIFT) |
+                 (((uint32_t)max(i32_em[3 * P + idx], 0) & 7u) << FL_SIDX_SHIFT) |
+                 (i32_em[4 * P + idx] ? FL_CRASHED : 0u) | ((uint32_t)((hl >= 0 && hl <= 4) ? hl : A_NONE) << FL_HL_SHIFT) |
+                 ((uint32_t)min(max(hist, 0), 2) << FL_HIST_SHIFT) | (i32_em[7 * P + idx] ? FL_FG : 0u) |
+                 (i32_em[8 * P + idx] ? FL_COLLAB : 0u) | (i32_em[9 * P + idx] ? FL_LCSAFE : 0u) |
+                 (i32_em[10 * P + idx] ? FL_CADJ : 0u);
+    st.flags[(size_t)i * E + e] = f;
+    if (i == 0) {
+        st.einfo[e] = ((uint32_t)env_em[e] & 15u) | (((uint32_t)env_em[E + e] & 15u) << EI_NCAV_SHIFT) |
+                      (((uint32_t)env_em[2 * E + e] & 15u) << EI_NMERGE_SHIFT) |
+                      (((uint32_t)min(env_em[3 * E + e], 255) & EI_STEPS_MASK) << EI_STEPS_SHIFT) |
+                      (((uint32_t)min(env_em[4 * E + e], 4095) & EI_TIME_MASK) << EI_TIME_SHIFT);
+    }
+}
+
+__global__ void unpack_state_kernel(DevState st, int n_envs, double *f64_em, int32_t *i32_em, int32_t *env_em) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t E = (size_t)n_envs;
+    if (idx >= E * MAXV) return;
+    size_t e = idx / MAXV;
+    int i = (int)(idx % MAXV);
+    for (int k = 0; k < 16; ++k) {
+        int fld = c_host_f64_to_field[k];
+        if (fld < 0) fld = F_X;  // rec1_x == x (the record is taken right after the move)
+        f64_em[(size_t)k * E * MAXV + idx] = st.f64[((size_t)fld * MAXV + i) * E + e];
+    }
+    const size_t P = E * MAXV;
+    uint32_t f = st.flags[(size_t)i * E + e];
+    int hl = fl_hl(f);
+    i32_em[0 * P + idx] = fl_kind(f);
+    i32_em[1 * P + idx] = fl_lane(f);
+    i32_em[2 * P + idx] = fl_tlane(f);
+    i32_em[3 * P + idx] = fl_kind(f) == MM_KIND_CAV ? (int)((f >> FL_SIDX_SHIFT) & 7u) : (fl_kind(f) ? -1 : 0);
+    i32_em[4 * P + idx] = (f & FL_CRASHED) ? 1 : 0;
+    i32_em[5 * P + idx] = hl == A_NONE ? -1 : hl;
+    i32_em[6 * P + idx] = fl_hist(f);
+    i32_em[7 * P + idx] = (f & FL_FG) ? 1 : 0;
+    i32_em[8 * P + idx] = (f & FL_COLLAB) ? 1 : 0;
+    i32_em[9 * P + idx] = (f & FL_LCSAFE) ? 1 : 0;
+    i32_em[10 * P + idx] = (f & FL_CADJ) ? 1 : 0;
+    if (i == 0) {
+        uint32_t ei = st.einfo[e];
+        env_em[e] = (ei >> EI_NVEH_SHIFT) & EI_4BIT;
+        env_em[E + e] = (ei >> EI_NCAV_SHIFT) & EI_4BIT;
+        env_em[2 * E + e] = (ei >> EI_NMERGE_SHIFT) & EI_4BIT;
+        env_em[3 * E + e] = (ei >> EI_STEPS_SHIFT) & EI_STEPS_MASK;
+        env_em[4 * E + e] = (ei >> EI_TIME_SHIFT) & EI_TIME_MASK;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone QP kernel (solves/s microbenchmark, known-answer tests)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) qp_kernel(const double *__restrict__ a, const double *__restrict__ c_lead,
+                                                 const double *__restrict__ c_adj, const uint8_t *__restrict__ has_adj,
+                                                 const double *__restrict__ lo, const double *__restrict__ hi, int64_t n,
+                                                 double *__restrict__ u, uint8_t *__restrict__ active) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int act;
+        u[i] = solve_cbf_qp(a[i], c_lead[i], c_adj[i], has_adj[i] != 0, lo[i], hi[i], act);
+        active[i] = (uint8_t)act;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+constexpr size_t STEP_SMEM = (size_t)4 * MAXV * BLOCK * sizeof(double) + (size_t)MAXV * BLOCK * sizeof(uint32_t);
+
+void launch_step(const StepParams &p, bool diag, void *stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM);
+        cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM);
+        cudaFuncSetAttribute(observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM);
+        attr_set = true;
+    }
+    int grid = (p.env_count + BLOCK - 1) / BLOCK;
+    if (grid <= 0) return;
+    if (diag) step_kernel<true><<<grid, BLOCK, STEP_SMEM, (cudaStream_t)stream>>>(p);
+    else step_kernel<false><<<grid, BLOCK, STEP_SMEM, (cudaStream_t)stream>>>(p);
+}
+
+void launch_observe(const StepParams &p, void *stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM);
+        attr_set = true;
+    }
+    int grid = (p.env_count + BLOCK - 1) / BLOCK;
+    if (grid <= 0) return;
+    observe_kernel<<<grid, BLOCK, STEP_SMEM, (cudaStream_t)stream>>>(p);
+}
+
+void launch_reset(const ResetParams &p, void *stream) {
+    int grid = (p.env_count + BLOCK - 1) / BLOCK;
+    if (grid <= 0) return;
+    reset_kernel<<<grid, BLOCK, 0, (cudaStream_t)stream>>>(p);
+}
+
+void launch_pack_state(const DevState &st, int n_envs, const double *f64_em, const int32_t *i32_em,
+                       const int32_t *env_em, void *stream) {
+    size_t n = (size_t)n_envs * MAXV;
+    pack_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(st, n_envs, f64_em, i32_em, env_em);
+}
+
+void launch_unpack_state(const DevState &st, int n_envs, double *f64_em, int32_t *i32_em, int32_t *env_em,
+                         void *stream) {
+    size_t n = (size_t)n_envs * MAXV;
+    unpack_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(st, n_envs, f64_em, i32_em, env_em);
+}
+
+void launch_qp(const double *a, const double *c_lead, const double *c_adj, const uint8_t *has_adj, const double *lo,
+               const double *hi, int64_t n, double *u, uint8_t *active, void *stream) {
+    if (n <= 0) return;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    qp_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, c_lead, c_adj, has_adj, lo, hi, n, u, active);
+}
+
+}  // namespace mm

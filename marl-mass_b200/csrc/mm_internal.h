@@ -1,0 +1,100 @@
+// mm_internal.h — layout shared by the kernels (merge_step.cu) and the host side of the C ABI (capi.cu).
+//
+// HBM layout (structure of arrays, env index fastest so that thread-per-env accesses coalesce):
+//   f64   [F_COUNT][MM_MAXV][E]   vehicle state, one plane per field and slot
+//   flags [MM_MAXV][E] u32        packed discrete vehicle state (bit layout below)
+//   einfo [E] u32                 packed env scalars: n_veh, n_cav, n_merge, steps, time
+//   episode [E] u32               episode counter (RNG stream id for device-side spawn)
+// Outputs are env-major (what the caller consumes): obs [E][MM_MAXV][MM_NS] f32, etc.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+#include "marl_mass_b200.h"
+
+namespace mm {
+
+constexpr int MAXV = MM_MAXV;
+constexpr int NS = MM_NS;
+
+enum F64Field {
+    F_X = 0, F_Y, F_H, F_V,          // position, heading, speed            (staged in shared memory)
+    F_TSPEED,                        // target_speed
+    F_GVX,                           // fg_params["g"]["vx"] of the last integration
+    F_REC1VX,                        // state_hist[-1]["vx"] (x of that record == current x)
+    F_REC2X, F_REC2VX,               // state_hist[-2]["x"], ["vx"]
+    F_ACT_STEER, F_ACT_ACC,          // low-level action of the current sub-step
+    F_SAFE_STEER, F_SAFE_ACC,        // shielded action of the last step()
+    F_TIMER,                         // IDMVehicle.timer
+    F_MINHW,                         // MDPLCVehicle.min_headway
+    F_COUNT
+};
+
+// flags word
+constexpr uint32_t FL_KIND_SHIFT = 0, FL_KIND_MASK = 3u;
+constexpr uint32_t FL_LANE_SHIFT = 2, FL_TLANE_SHIFT = 5, FL_SIDX_SHIFT = 8, FL_3BIT = 7u;
+constexpr uint32_t FL_CRASHED = 1u << 11;
+constexpr uint32_t FL_HL_SHIFT = 12;         // 3 bits, 7 = None
+constexpr uint32_t FL_HIST_SHIFT = 15;       // 2 bits, saturating len(state_hist)
+constexpr uint32_t FL_FG = 1u << 17;
+constexpr uint32_t FL_COLLAB = 1u << 18;     // is_collaborating
+constexpr uint32_t FL_LCSAFE = 1u << 19;     // is_lc_safe
+constexpr uint32_t FL_CADJ = 1u << 20;       // collaborate_adj
+
+// einfo word
+constexpr uint32_t EI_NVEH_SHIFT = 0, EI_NCAV_SHIFT = 4, EI_NMERGE_SHIFT = 8, EI_4BIT = 15u;
+constexpr uint32_t EI_STEPS_SHIFT = 12, EI_STEPS_MASK = 255u;
+constexpr uint32_t EI_TIME_SHIFT = 20, EI_TIME_MASK = 4095u;
+
+struct DevState {
+    double *f64;        // [F_COUNT][MAXV][E]
+    uint32_t *flags;    // [MAXV][E]
+    uint32_t *einfo;    // [E]
+    uint32_t *episode;  // [E]
+};
+
+struct DevOut {
+    float *obs, *reward, *agents_rewards, *regional_rewards, *average_speed, *traffic_speed, *min_headway,
+          *merge_percent;
+    uint8_t *done, *agents_dones;
+    int32_t *n_agents;
+    // per-sub-step shield record [E][3][MAXV] (record_diag only, else null)
+    int32_t *sh_i;      // 7 planes: ran, leader, front_adj, rear_adj, constrain_adj, active, is_lc_safe
+    double *sh_f;       // 5 planes: safe_acc, safe_steer, nom_acc, nom_steer, lc_margin
+    double *stats;      // [N_STATS] accumulators
+};
+
+enum StatSlot { ST_AGENT_STEPS = 0, ST_ENV_STEPS, ST_EPISODES, ST_CRASHED, ST_REWARD, ST_SPEED, ST_MERGE,
+                ST_SOLVES, ST_ACTIVE, ST_VETOES, ST_MINHW, N_STATS };
+
+struct StepParams {
+    DevState st;
+    DevOut out;
+    const int8_t *actions;   // [E][MAXV]
+    mm_config cfg;
+    int n_envs;
+    int env_offset;          // first env of this launch (chunked host path)
+    int env_count;           // envs in this launch
+    const uint8_t *obs_mask; // observe_kernel: refresh only envs whose mask byte is set (null: all)
+};
+
+struct ResetParams {
+    DevState st;
+    DevOut out;
+    const uint8_t *mask;     // [E] or null; when use_done != 0 the done flags are the mask
+    mm_config cfg;
+    uint64_t seed;
+    int n_envs, env_offset, env_count, num_cav, use_done;
+};
+
+// launchers (merge_step.cu)
+void launch_step(const StepParams &p, bool diag, void *stream);
+void launch_reset(const ResetParams &p, void *stream);
+void launch_observe(const StepParams &p, void *stream);
+void launch_pack_state(const DevState &st, int n_envs, const double *f64_em /*[16][E][MAXV]*/,
+                       const int32_t *i32_em /*[11][E][MAXV]*/, const int32_t *env_em /*[5][E]*/, void *stream);
+void launch_unpack_state(const DevState &st, int n_envs, double *f64_em, int32_t *i32_em, int32_t *env_em,
+                         void *stream);
+void launch_qp(const double *a, const double *c_lead, const double *c_adj, const uint8_t *has_adj,
+               const double *lo, const double *hi, int64_t n, double *u, uint8_t *active, void *stream);
+
+}  // namespace mm

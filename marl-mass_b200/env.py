@@ -1,0 +1,385 @@
+"""Host side of the batched merge environment: the reference's gym-style surface over the C ABI.
+
+Two classes:
+
+* `MergeEnvBatched` — E independent merge envs on one GPU, one kernel launch per policy step.
+  `reset()` / `step()` mirror `MergeEnv.reset/step` (highway_env/envs/merge_env_v1.py:126-166,
+  envs/common/abstract.py:176-209, 443-510) with a leading env axis; outputs are zero-copy torch views of the
+  device buffers the handle owns.
+* `MergeEnvLCMARL` — single-env adapter with the exact reference surface MAPPO drives
+  (marl/mappo.py:44,104-135,281-342): `reset(is_training, testing_seeds, num_CAV) -> (obs, mask)`,
+  `step(tuple) -> (obs, reward, done, info)`, `controlled_vehicles`, `config`, `n_s`, `n_a`, `T`, `is_crashed()`.
+
+Config keys are the reference's ENV_CONFIG keys (run_mappo.py:145-171); as there, mutating `env.config[...]`
+takes effect at the next `reset()`.  CBF eta/tau — class globals `CBFType.GAMMA_B/TAU` in the reference
+(run_mappo.py:137-139) — are the keys `cbf_eta` and `HEADWAY_TIME`.
+
+There is no CPU path: every call goes to libmarl_mass_b200.so and raises if it is missing.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from . import spawn as _spawn
+from ._lib import ENV_FIELDS, F64_FIELDS, I32_FIELDS, MAXV, NA, NS, SH_F, SH_I
+
+SHIELD = {"none": 0, "cbf-hss": 1, "cbf-av": 1, "cbf-avs": 1, "cbf-avs_cint": 1, "cbf-mass": 2, "cbf-cav": 2}
+REWARD = {"default": 0, "srew": 1, "mrew": 2}
+TRAFFIC = {"cav": 0, "mixed": 1}
+
+DEFAULT_CONFIG = {
+    # merge_env_v1.py:32-57, 415-437 and abstract.py:106-130, with the values the shipped MASS ini uses
+    "simulation_frequency": 15, "policy_frequency": 5, "duration": 20,
+    "COLLISION_REWARD": 200, "HIGH_SPEED_REWARD": 1, "HEADWAY_COST": 4, "HEADWAY_TIME": 1.2,
+    "MERGING_LANE_COST": 4, "traffic_density": 1, "safety_guarantee": "none", "lateral_control": "steer",
+    "mixed_traffic": None, "traffic_type": "cav", "agent_reward": "default", "cbf_eta": 0.0,
+    "action_masking": False, "seed": 0,
+}
+
+
+def make_mm_config(cfg):
+    """Reference config dict -> mm_config.  Raises ValueError exactly where the reference would
+    (decentral_layer.py:817 unknown safety type; safe_controller.py:174 unsupported lateral control)."""
+    sg = cfg.get("safety_guarantee", "none")
+    if sg in ("priority", "dmc"):
+        raise ValueError("safety_guarantee %r (look-ahead baseline shields) is outside the batched hot path" % sg)
+    if sg not in SHIELD:
+        raise ValueError("Undefined safety_type:{0}".format(sg.split("-")[-1]))
+    if cfg.get("lateral_control", "steer") != "steer":
+        raise AttributeError("Lateral control: {0} is not supported".format(cfg.get("lateral_control")))
+    if cfg.get("action_masking", False):
+        raise ValueError("action_masking=True (MAPPO_GI) is not built yet; the shipped HSS/MASS configs use False")
+    tt = cfg.get("traffic_type", "cav")
+    if tt not in TRAFFIC:
+        raise ValueError("traffic_type %r is not supported on the batched path (cav | mixed)" % (tt,))
+    sim, pol = int(cfg["simulation_frequency"]), int(cfg["policy_frequency"])
+    return _lib.MMConfig(
+        shield=SHIELD[sg], reward_kind=REWARD[cfg.get("agent_reward", "default")],
+        traffic_density=int(cfg["traffic_density"]), traffic_type=TRAFFIC[tt],
+        duration_steps=int(cfg["duration"] * pol), substeps=sim // pol, dt=1 / sim,
+        eta=float(cfg.get("cbf_eta", 0.0)), tau=float(cfg["HEADWAY_TIME"]),
+        collision_reward=float(cfg["COLLISION_REWARD"]), high_speed_reward=float(cfg["HIGH_SPEED_REWARD"]),
+        headway_cost=float(cfg["HEADWAY_COST"]), headway_time=float(cfg["HEADWAY_TIME"]),
+        merging_lane_cost=float(cfg["MERGING_LANE_COST"]))
+
+
+class _DevArray(object):
+    """Minimal __cuda_array_interface__ carrier so torch can view handle-owned device memory."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+        self._owner = owner
+
+
+class MergeEnvBatched(object):
+    n_s = NS
+    n_a = NA
+
+    def __init__(self, n_envs, config=None, device=0, record_diag=False):
+        self.config = dict(DEFAULT_CONFIG)
+        if config:
+            self.config.update(config)
+        self.n_envs = int(n_envs)
+        self.device = int(device)
+        self.record_diag = bool(record_diag)
+        self.T = int(self.config["duration"] * self.config["policy_frequency"])
+        self._L = _lib.lib()
+        self._h = C.c_void_p()
+        _lib.check(self._L.mm_create(C.byref(make_mm_config(self.config)), self.n_envs, self.device,
+                                     int(self.record_diag), C.byref(self._h)))
+        self._views = None
+        self._reset_count = 0
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.mm_destroy(self._h)
+            self._h = C.c_void_p()
+            self._views = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ device views
+    def buffers(self):
+        """dict of torch tensors aliasing the handle's device buffers (valid until close())."""
+        if self._views is None:
+            import torch
+            b = _lib.MMBuffers()
+            _lib.check(self._L.mm_buffers_get(self._h, C.byref(b)))
+            E = self.n_envs
+            spec = {"obs": ((E, MAXV, NS), "<f4"), "reward": ((E,), "<f4"), "done": ((E,), "|u1"),
+                    "agents_rewards": ((E, MAXV), "<f4"), "regional_rewards": ((E, MAXV), "<f4"),
+                    "agents_dones": ((E, MAXV), "|u1"), "average_speed": ((E,), "<f4"),
+                    "traffic_speed": ((E,), "<f4"), "min_headway": ((E,), "<f4"), "merge_percent": ((E,), "<f4"),
+                    "n_agents": ((E,), "<i4"), "actions": ((E, MAXV), "|i1")}
+            dev = "cuda:%d" % self.device
+            self._views = {k: torch.as_tensor(_DevArray(getattr(b, k), shp, ts, self), device=dev)
+                           for k, (shp, ts) in spec.items()}
+        return self._views
+
+    @staticmethod
+    def _stream_ptr(stream):
+        if stream is None:
+            import torch
+            return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        return C.c_void_p(getattr(stream, "cuda_stream", stream))
+
+    # ------------------------------------------------------------------ reference surface, batched
+    def _apply_config(self):
+        self.T = int(self.config["duration"] * self.config["policy_frequency"])
+        _lib.check(self._L.mm_set_config(self._h, C.byref(make_mm_config(self.config))))
+
+    def reset(self, seed=None, mask=None, num_CAV=0, stream=None):
+        """Device-side spawn of every env (or those with mask != 0); returns (obs, action_mask).
+
+        seed=None continues the reference's habit of `self.seed += 1` per reset (abstract.py:183-190)."""
+        self._apply_config()
+        if seed is None:
+            seed = int(self.config.get("seed", 0)) + self._reset_count
+        self._reset_count += 1
+        mptr = C.c_void_p(0)
+        if mask is not None:
+            assert mask.is_cuda and mask.dtype.itemsize == 1 and mask.numel() == self.n_envs
+            mptr = C.c_void_p(mask.data_ptr())
+        _lib.check(self._L.mm_reset(self._h, C.c_uint64(int(seed) & (2 ** 64 - 1)), mptr, int(num_CAV),
+                                    self._stream_ptr(stream)))
+        v = self.buffers()
+        return v["obs"], self.action_mask()
+
+    def reset_from_seeds(self, seeds, num_CAV=0):
+        """Exactly the reference's scenes for `testing_seeds` (host replay of its MT19937 stream)."""
+        self._apply_config()
+        seeds = list(seeds)
+        assert len(seeds) == self.n_envs
+        st = _spawn.spawn_state(seeds, self.config["traffic_density"], self.config.get("traffic_type", "cav"), num_CAV)
+        self.set_state(st)
+        v = self.buffers()
+        return v["obs"], self.action_mask()
+
+    def action_mask(self):
+        """All ones, as the reference returns when action_masking is False (abstract.py:207-209)."""
+        import torch
+        return torch.ones((self.n_envs, MAXV, NA), dtype=torch.int32, device="cuda:%d" % self.device)
+
+    def step(self, actions=None, auto_reset=False, stream=None):
+        """One policy step for every env.  actions: int8 CUDA tensor [E, MAXV] (None: the `actions` view).
+
+        Returns (obs [E,MAXV,30] f32, reward [E] f32, done [E] u8, info) where info holds the device views
+        named as the reference's info keys.  Nothing is synchronised."""
+        aptr = C.c_void_p(0)
+        if actions is not None:
+            assert actions.is_cuda and actions.dtype.itemsize == 1 and actions.is_contiguous()
+            assert actions.numel() == self.n_envs * MAXV
+            aptr = C.c_void_p(actions.data_ptr())
+        _lib.check(self._L.mm_step(self._h, aptr, int(bool(auto_reset)), self._stream_ptr(stream)))
+        v = self.buffers()
+        return v["obs"], v["reward"], v["done"], v
+
+    def step_host(self, actions, auto_reset=False, out=None):
+        """Same step through HOST arrays (numpy or pinned torch tensors): actions [E,MAXV] int8 in,
+        obs/reward/done/regional_rewards/n_agents out.  Returns when the results are in `out`."""
+        a = actions if isinstance(actions, np.ndarray) else actions.numpy()
+        assert a.dtype == np.int8 and a.flags.c_contiguous and a.size == self.n_envs * MAXV
+        if out is None:
+            out = self.alloc_host_out()
+        ptr = {k: (out[k].ctypes.data if isinstance(out[k], np.ndarray) else out[k].data_ptr()) for k in out}
+        _lib.check(self._L.mm_step_host(self._h, C.c_void_p(a.ctypes.data), int(bool(auto_reset)),
+                                        C.c_void_p(ptr.get("obs", 0)), C.c_void_p(ptr.get("reward", 0)),
+                                        C.c_void_p(ptr.get("done", 0)), C.c_void_p(ptr.get("regional_rewards", 0)),
+                                        C.c_void_p(ptr.get("n_agents", 0))))
+        return out
+
+    def alloc_host_out(self, pinned=True):
+        import torch
+        E = self.n_envs
+        mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=pinned).numpy()
+        return {"obs": mk((E, MAXV, NS), torch.float32), "reward": mk((E,), torch.float32),
+                "done": mk((E,), torch.uint8), "regional_rewards": mk((E, MAXV), torch.float32),
+                "n_agents": mk((E,), torch.int32)}
+
+    # ------------------------------------------------------------------ state (teacher forcing / checkpoint)
+    def _host_state_struct(self, st):
+        kw = {}
+        for k in F64_FIELDS:
+            assert st[k].dtype == np.float64 and st[k].flags.c_contiguous and st[k].shape == (self.n_envs, MAXV), k
+            kw[k] = st[k].ctypes.data_as(C.POINTER(C.c_double))
+        for k in I32_FIELDS:
+            assert st[k].dtype == np.int32 and st[k].flags.c_contiguous and st[k].shape == (self.n_envs, MAXV), k
+            kw[k] = st[k].ctypes.data_as(C.POINTER(C.c_int32))
+        for k in ENV_FIELDS:
+            assert st[k].dtype == np.int32 and st[k].flags.c_contiguous and st[k].shape == (self.n_envs,), k
+            kw[k] = st[k].ctypes.data_as(C.POINTER(C.c_int32))
+        return _lib.MMStateHost(**kw)
+
+    def get_state(self):
+        st = _spawn.empty_state(self.n_envs)
+        _lib.check(self._L.mm_get_state(self._h, C.byref(self._host_state_struct(st))))
+        return st
+
+    def set_state(self, st):
+        _lib.check(self._L.mm_set_state(self._h, C.byref(self._host_state_struct(st))))
+
+    def shield_diag(self):
+        E = self.n_envs
+        d = {k: np.zeros((E, 3, MAXV), np.int32) for k in SH_I}
+        d.update({k: np.zeros((E, 3, MAXV), np.float64) for k in SH_F})
+        s = _lib.MMShieldDiagHost(**{k: d[k].ctypes.data_as(C.POINTER(C.c_int32)) for k in SH_I},
+                                  **{k: d[k].ctypes.data_as(C.POINTER(C.c_double)) for k in SH_F})
+        _lib.check(self._L.mm_get_shield_diag(self._h, C.byref(s)))
+        return d
+
+    def stats(self, reset=False):
+        s = _lib.MMStats()
+        _lib.check(self._L.mm_stats(self._h, C.byref(s), int(reset)))
+        return {k: getattr(s, k) for k, _ in _lib.MMStats._fields_}
+
+    def kernel_launches(self):
+        return int(self._L.mm_kernel_launches(self._h))
+
+
+def shield_qp(a, c_lead, c_adj, has_adj, lo, hi, stream=None):
+    """n independent CBF-QP solves on CUDA tensors (f64 inputs, uint8 has_adj).  Returns (u f64, active u8)."""
+    import torch
+    n = a.numel()
+    for t in (a, c_lead, c_adj, lo, hi):
+        assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.numel() == n
+    assert has_adj.is_cuda and has_adj.dtype == torch.uint8 and has_adj.numel() == n
+    u = torch.empty_like(a)
+    active = torch.empty(n, dtype=torch.uint8, device=a.device)
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream if stream is None else stream.cuda_stream)
+    _lib.check(_lib.lib().mm_shield_qp(*[C.c_void_p(t.data_ptr()) for t in (a, c_lead, c_adj, has_adj, lo, hi)],
+                                       C.c_int64(n), C.c_void_p(u.data_ptr()), C.c_void_p(active.data_ptr()), sp))
+    return u, active
+
+
+# --------------------------------------------------------------------------------------------------
+# single-env adapter with the reference surface
+# --------------------------------------------------------------------------------------------------
+class _VehicleView(object):
+    """What MAPPO reads from env.controlled_vehicles[i] (mappo.py:329-346): crashed, position, speed."""
+
+    def __init__(self, env, slot):
+        self._env, self._slot = env, slot
+
+    def _st(self):
+        return self._env._state()
+
+    @property
+    def crashed(self):
+        return bool(self._st()["crashed"][0, self._slot])
+
+    @property
+    def position(self):
+        st = self._st()
+        return np.array([st["x"][0, self._slot], st["y"][0, self._slot]])
+
+    @property
+    def speed(self):
+        return float(self._st()["speed"][0, self._slot])
+
+    @property
+    def heading(self):
+        return float(self._st()["heading"][0, self._slot])
+
+    @property
+    def id(self):
+        return self._slot
+
+
+class MergeEnvLCMARL(object):
+    """Drop-in for gym.make('merge-multi-agent-v1') on the step path (merge_env_v1.py:410-525)."""
+    n_a = NA
+    n_s = NS
+
+    def __init__(self, config=None, device=0):
+        self._b = MergeEnvBatched(1, config, device=device, record_diag=False)
+        self.config = self._b.config
+        self.seed = self.config.get("seed", 0)
+        self.T = self._b.T
+        self.steps = 0
+        self.controlled_vehicles = []
+        self.vehicle_speed, self.vehicle_pos = [], []
+        self._cache = None
+        self.reset()
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def _state(self):
+        if self._cache is None:
+            self._cache = self._b.get_state()
+        return self._cache
+
+    def reset(self, is_training=True, testing_seeds=0, num_CAV=0):
+        seed = self.seed if is_training else testing_seeds
+        self.seed += 1  # abstract.py:190
+        self._b.reset_from_seeds([seed], num_CAV=num_CAV)
+        self.T = self._b.T
+        self._cache = None
+        self.steps = 0
+        self.vehicle_speed, self.vehicle_pos = [], []
+        n = int(self._state()["n_cav"][0])
+        self.controlled_vehicles = [_VehicleView(self, i) for i in range(n)]
+        import torch
+        torch.cuda.synchronize(self._b.device)
+        obs = self._b.buffers()["obs"][0, :n].double().cpu().numpy()
+        return obs, np.array([[1] * self.n_a] * n)
+
+    def step(self, action):
+        import torch
+        n = len(self.controlled_vehicles)
+        a = np.full((1, MAXV), 1, np.int8)
+        a[0, :n] = np.asarray(tuple(action), np.int64)[:n]
+        v = self._b.buffers()
+        v["actions"].copy_(torch.from_numpy(a))
+        self._b.step(None)
+        torch.cuda.synchronize(self._b.device)
+        self._cache = None
+        self.steps += 1
+        st = self._state()
+        obs = v["obs"][0, :n].double().cpu().numpy()
+        reward = float(v["reward"][0])
+        done = bool(v["done"][0])
+        speeds = [float(st["speed"][0, i]) for i in range(n)]
+        self.vehicle_speed.append(speeds)
+        self.vehicle_pos.append([float(st["x"][0, i]) for i in range(n)])
+        info = {
+            "speed": speeds[0], "crashed": bool(st["crashed"][0, 0]), "action": action, "new_action": action,
+            "action_mask": np.array([[1] * self.n_a] * n), "average_speed": float(v["average_speed"][0]),
+            "vehicle_speed": np.array(self.vehicle_speed), "vehicle_position": np.array(self.vehicle_pos),
+            "agents_dones": tuple(bool(x) for x in v["agents_dones"][0, :n].cpu().numpy()),
+            "agents_info": [[float(st["x"][0, i]), float(st["y"][0, i]), speeds[i]] for i in range(n)],
+            "agents_rewards": tuple(float(x) for x in v["agents_rewards"][0, :n].cpu().numpy()),
+            "regional_rewards": tuple(float(x) for x in v["regional_rewards"][0, :n].cpu().numpy()),
+            "traffic_speed": float(v["traffic_speed"][0]), "min_headway": float(v["min_headway"][0]),
+        }
+        if done:
+            info["merge_percent"] = float(v["merge_percent"][0])
+        return obs, reward, done, info
+
+    def is_crashed(self):
+        st = self._state()
+        return bool(st["crashed"][0, :len(self.controlled_vehicles)].any())
+
+    def render(self, mode="human"):
+        return None
+
+    def close(self):
+        self._b.close()
+
+
+_REGISTRY = {"merge-multi-agent-v1": MergeEnvLCMARL}
+
+
+def make(env_id, **kwargs):
+    """gym.make stand-in for the env ids on the hot path (merge_env_v1.py:686-689)."""
+    if env_id not in _REGISTRY:
+        raise KeyError("env id %r is not provided by marl_mass_b200 (available: %s)" % (env_id, sorted(_REGISTRY)))
+    return _REGISTRY[env_id](**kwargs)

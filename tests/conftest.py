@@ -1,0 +1,22 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return os.path.join(ROOT, "tests", "golden")
+
+
+GOLDEN_CASES = ["unsafe_td1", "unsafe_td3", "unsafe_td2_mixed", "hss_td3", "hss_td3_mixed", "mass_td1",
+                "mass_td3_srew", "mass_td3_mixed", "mass_td2_mixed_mrew"]

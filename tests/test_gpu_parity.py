@@ -1,0 +1,314 @@
+"""GPU suite: the CUDA path, called through the C ABI, against (a) the golden vectors frozen from the reference
+and (b) the CPU oracle on seeded scenes.  Discrete outputs bit-exact; continuous state <= 1e-9 relative
+(float64 core; the north-star tolerance is 1e-4), float32 outputs (obs, rewards) <= 2e-6.
+"""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES
+from helpers import (ENV_FIELDS, F64_FIELDS, I32_FIELDS, LC_BOUNDARY_EPS, OUT_F, OUT_I, SH_F, SH_I, compare_states,
+                     load_golden, rel_err, used_mask)
+
+pytestmark = pytest.mark.gpu
+
+STATE_TOL = 1e-9
+F32_TOL = 2e-6
+
+
+@pytest.fixture(scope="module")
+def mm():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import marl_mass_b200 as m
+    m.lib()  # raises if the sm_100a library was not built: there is no fallback to test
+    return m
+
+
+@pytest.fixture(scope="module")
+def orc():
+    import oracle
+    oracle.lib()
+    return oracle
+
+
+def env_config(cfg):
+    keys = ("simulation_frequency", "policy_frequency", "duration", "COLLISION_REWARD", "HIGH_SPEED_REWARD",
+            "HEADWAY_COST", "HEADWAY_TIME", "MERGING_LANE_COST", "traffic_density", "safety_guarantee",
+            "traffic_type", "agent_reward", "cbf_eta")
+    return {k: cfg[k] for k in keys}
+
+
+def full_state(orc, g, rows):
+    return orc.state_from_golden(g, rows)
+
+
+def outputs_to_numpy(v, keys):
+    import torch
+    torch.cuda.synchronize()
+    return {k: v[k].cpu().numpy() for k in keys}
+
+
+def check_outputs(got, want, ncav):
+    m = np.arange(12)[None, :] < ncav[:, None]
+    for k in OUT_I:
+        assert np.array_equal(got[k].astype(np.int32) * (m if got[k].ndim == 2 else 1),
+                              np.asarray(want[k], np.int32)), k
+    for k in OUT_F:
+        assert rel_err(got[k], want[k]).max() <= F32_TOL, (k, rel_err(got[k], want[k]).max())
+
+
+def check_shield(diag, want, lc_margin):
+    ran = want["sh_ran"] == 1
+    assert np.array_equal(diag["ran"], want["sh_ran"])
+    boundary = ran & (lc_margin < LC_BOUNDARY_EPS)
+    for k in SH_I:
+        bad = (diag[k] != want["sh_" + k]) & ran & ~boundary
+        assert not bad.any(), (k, np.argwhere(bad)[:5].tolist())
+    for k in SH_F:
+        assert (rel_err(diag[k], want["sh_" + k]) * (ran & ~boundary)).max() <= STATE_TOL, k
+    return int(boundary.sum())
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_cuda_vs_golden_teacher_forced(mm, orc, name):
+    """Reference pre-state + reference actions -> CUDA step -> reference post-state, outputs, shield record."""
+    g, cfg = load_golden(name)
+    rows = g["row_of_step"]
+    T = len(rows)
+    env = mm.MergeEnvBatched(T, env_config(cfg), record_diag=True)
+    env.set_state(full_state(orc, g, rows))
+    import torch
+    act = torch.from_numpy(np.ascontiguousarray(g["act"])).cuda()
+    _, _, _, v = env.step(act)
+    got = outputs_to_numpy(v, OUT_F + OUT_I)
+    post = env.get_state()
+    compare_states(post, full_state(orc, g, rows + 1), STATE_TOL, name)
+    check_outputs(got, {k: g[k] for k in OUT_F + OUT_I}, g["st_n_cav"][rows])
+    diag = env.shield_diag()
+    nb = check_shield(diag, {k: g[k] for k in g.files if k.startswith("sh_")}, diag["lc_margin"])
+    assert nb <= 0.01 * max(int((g["sh_ran"] == 1).sum()), 1) + 1
+    env.close()
+
+
+@pytest.mark.parametrize("name", ["hss_td3", "mass_td3_mixed", "unsafe_td2_mixed"])
+def test_cuda_free_running_episode(mm, orc, name):
+    """Whole episodes on the GPU alone (state never re-synced) end on the reference's final state."""
+    import torch
+    g, cfg = load_golden(name)
+    ep, rows = g["ep_start"], g["row_of_step"]
+    n_ep = len(ep) - 1
+    env = mm.MergeEnvBatched(n_ep, env_config(cfg))
+    env.set_state(full_state(orc, g, ep[:-1]))
+    lens = [int(((rows >= ep[j]) & (rows < ep[j + 1] - 1)).sum()) for j in range(n_ep)]
+    first_step = [int(np.where(rows == ep[j])[0][0]) for j in range(n_ep)]
+    finals = {}
+    for t in range(max(lens)):
+        a = np.ones((n_ep, 12), np.int8)
+        for j in range(n_ep):
+            if t < lens[j]:
+                a[j] = g["act"][first_step[j] + t]
+        _, _, done, v = env.step(torch.from_numpy(a).cuda())
+        d = done.cpu().numpy()
+        st = env.get_state()
+        for j in range(n_ep):
+            if t < lens[j]:
+                assert int(d[j]) == int(g["done"][first_step[j] + t]), (name, j, t)
+                if t == lens[j] - 1:
+                    finals[j] = {k: st[k][j:j + 1].copy() for k in st}
+    for j in range(n_ep):
+        compare_states(finals[j], full_state(orc, g, [ep[j + 1] - 1]), 1e-6, "%s episode %d" % (name, j))
+    env.close()
+
+
+@pytest.mark.parametrize("shield,traffic,td,reward", [
+    ("cbf-cav", "cav", 3, "default"), ("cbf-cav", "mixed", 3, "srew"), ("cbf-avs_cint", "cav", 3, "default"),
+    ("cbf-avs_cint", "mixed", 2, "mrew"), ("none", "mixed", 1, "default"), ("cbf-cav", "cav", 1, "mrew")])
+def test_cuda_vs_oracle_seeded_rollout(mm, orc, shield, traffic, td, reward):
+    """4096 device-spawned scenes, 40 policy steps of uniform random actions, CUDA and oracle advanced in lock
+    step from the same start; state is re-synced from the oracle only when a discrete mismatch was excluded as
+    a veto-boundary case (never observed so far)."""
+    import torch
+    E, T = 4096, 40
+    cfg = dict(mm.DEFAULT_CONFIG, safety_guarantee=shield, traffic_type=traffic, traffic_density=td,
+               agent_reward=reward, HEADWAY_TIME=0.5, cbf_eta=0.03125, HIGH_SPEED_REWARD=4, HEADWAY_COST=1,
+               MERGING_LANE_COST=8)
+    env = mm.MergeEnvBatched(E, cfg, record_diag=True)
+    env.reset(seed=1234 + td)
+    st = env.get_state()
+    ocfg = orc.make_config(cfg)
+    obs0 = outputs_to_numpy(env.buffers(), ("obs",))["obs"]
+    assert rel_err(obs0, orc.observe(st)).max() <= F32_TOL
+    rng = np.random.RandomState(7)
+    alive = np.ones(E, bool)
+    worst = 0.0
+    for t in range(T):
+        a = rng.randint(0, 5, size=(E, 12)).astype(np.int8)
+        want = orc.step(ocfg, st, a, n_threads=8)
+        _, _, _, v = env.step(torch.from_numpy(a).cuda())
+        got = outputs_to_numpy(v, OUT_F + OUT_I)
+        post = env.get_state()
+        # compare only envs that had not finished before this step (finished envs are not stepped by MAPPO)
+        sel = np.where(alive)[0]
+        sub = lambda d: {k: d[k][sel] for k in d}
+        worst = max(worst, compare_states(sub(post), sub(st), STATE_TOL, "step %d" % t))
+        check_outputs(sub(got), sub({k: want[k] for k in OUT_F + OUT_I}), st["n_cav"][sel])
+        diag = env.shield_diag()
+        check_shield(sub(diag), sub({k: want[k] for k in want if k.startswith("sh_")}), diag["lc_margin"][sel])
+        alive &= want["done"] == 0
+    if shield == "none":
+        assert alive.sum() < E  # unshielded random driving does crash inside the window
+    env.close()
+
+
+def test_diag_off_equals_diag_on(mm):
+    """The benchmarked instantiation (no shield record) computes the same step as the tested one."""
+    import torch
+    cfg = dict(mm.DEFAULT_CONFIG, safety_guarantee="cbf-cav", traffic_density=3, traffic_type="mixed",
+               HEADWAY_TIME=0.5, cbf_eta=0.03125)
+    E = 2048
+    a_env = mm.MergeEnvBatched(E, cfg, record_diag=True)
+    b_env = mm.MergeEnvBatched(E, cfg, record_diag=False)
+    a_env.reset(seed=5)
+    b_env.set_state(a_env.get_state())
+    rng = np.random.RandomState(3)
+    for t in range(12):
+        a = torch.from_numpy(rng.randint(0, 5, size=(E, 12)).astype(np.int8)).cuda()
+        a_env.step(a)
+        b_env.step(a)
+    sa, sb = a_env.get_state(), b_env.get_state()
+    for k in F64_FIELDS + I32_FIELDS + ENV_FIELDS:
+        assert np.array_equal(sa[k], sb[k]), k
+    va, vb = a_env.buffers(), b_env.buffers()
+    torch.cuda.synchronize()
+    for k in ("obs", "reward", "done", "regional_rewards", "min_headway"):
+        assert torch.equal(va[k], vb[k]), k
+    a_env.close()
+    b_env.close()
+
+
+def test_host_buffer_step_equals_device_step(mm):
+    """mm_step_host (chunked over streams, pinned host buffers) == mm_step on device tensors."""
+    import torch
+    cfg = dict(mm.DEFAULT_CONFIG, safety_guarantee="cbf-cav", traffic_density=3, HEADWAY_TIME=0.5, cbf_eta=0.03125)
+    E = 40000  # not a multiple of the chunk size: exercises the ragged last chunk
+    a_env = mm.MergeEnvBatched(E, cfg)
+    b_env = mm.MergeEnvBatched(E, cfg)
+    a_env.reset(seed=11)
+    b_env.set_state(a_env.get_state())
+    rng = np.random.RandomState(5)
+    out = b_env.alloc_host_out()
+    for t in range(5):
+        a = rng.randint(0, 5, size=(E, 12)).astype(np.int8)
+        obs, rew, done, v = a_env.step(torch.from_numpy(a).cuda())
+        b_env.step_host(a, out=out)
+        torch.cuda.synchronize()
+        assert np.array_equal(obs.cpu().numpy(), out["obs"])
+        assert np.array_equal(rew.cpu().numpy(), out["reward"])
+        assert np.array_equal(done.cpu().numpy(), out["done"])
+        assert np.array_equal(v["regional_rewards"].cpu().numpy(), out["regional_rewards"])
+        assert np.array_equal(v["n_agents"].cpu().numpy(), out["n_agents"])
+    a_env.close()
+    b_env.close()
+
+
+def test_qp_kernel_vs_golden_and_oracle(mm, orc):
+    """mm_shield_qp: every QP the reference posed + 1e6 synthetic ones (oracle as the checker)."""
+    import torch
+    qs = []
+    for name in GOLDEN_CASES:
+        g, _ = load_golden(name)
+        if len(g["qp_a"]):
+            qs.append(np.stack([g["qp_" + k] for k in ("a", "c_lead", "c_adj", "has_adj", "lo", "hi", "u", "active")], 1))
+    q = np.concatenate(qs)
+    dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    u, act = mm.shield_qp(dev(q[:, 0]), dev(q[:, 1]), dev(q[:, 2]), dev(q[:, 3].astype(np.uint8)), dev(q[:, 4]), dev(q[:, 5]))
+    assert np.array_equal(u.cpu().numpy(), q[:, 6])
+    assert np.array_equal(act.cpu().numpy(), q[:, 7].astype(np.uint8))
+    rng = np.random.RandomState(0)
+    n = 1 << 20
+    dt = 1 / 15
+    a = dt * np.cos(rng.uniform(-0.3, 0.3, n)) * rng.choice([1.0, 1.0, 1.0, -1.0, 0.0], n)
+    c_lead, c_adj = rng.normal(0.1, 0.2, n), rng.normal(0.1, 0.2, n)
+    has_adj = (rng.rand(n) < 0.3).astype(np.uint8)
+    lo = -12.5 * dt + rng.uniform(-0.5, 0.5, n)
+    hi = lo + rng.uniform(0, 1.5, n)
+    u, act = mm.shield_qp(dev(a), dev(c_lead), dev(c_adj), dev(has_adj), dev(lo), dev(hi))
+    u, act = u.cpu().numpy(), act.cpu().numpy()
+    for i in rng.choice(n, 4000, replace=False):
+        wu, wa = orc.qp(a[i], c_lead[i], c_adj[i], bool(has_adj[i]), lo[i], hi[i])
+        assert u[i] == wu and act[i] == wa, i
+    assert len(np.unique(act)) >= 8
+
+
+def test_device_spawn_law(mm):
+    """reset(): the device-side spawn follows merge_env_v1.py:180-211,265-364 (counts, slots, noise, speeds)."""
+    for td, traffic, cav_rng, hdv_rng in ((1, "cav", (2, 6), (0, 0)), (3, "cav", (7, 11), (0, 0)),
+                                          (3, "mixed", (4, 6), (3, 5)), (2, "mixed", (2, 4), (2, 4))):
+        E = 20000
+        env = mm.MergeEnvBatched(E, dict(mm.DEFAULT_CONFIG, traffic_density=td, traffic_type=traffic))
+        env.reset(seed=td)
+        st = env.get_state()
+        ncav, nhdv = st["n_cav"], st["n_veh"] - st["n_cav"]
+        assert ncav.min() == cav_rng[0] and ncav.max() == cav_rng[1]
+        assert nhdv.min() == hdv_rng[0] and nhdv.max() == hdv_rng[1]
+        m = used_mask(st)
+        assert (st["kind"][m] > 0).all() and (st["kind"][~m] == 0).all()
+        sp = st["speed"][m]
+        assert sp.min() >= 25 and sp.max() < 27 and abs(sp.mean() - 26) < 0.02
+        main = m & (st["y"] == 0.0)
+        ramp = m & (st["y"] == 10.5)
+        assert (main | ramp)[m].all()
+        for sel, base in ((main, 10.0), (ramp, 5.0)):
+            x = st["x"][sel]
+            slot = np.round((x - base) / 50.0)
+            noise = x - base - 50.0 * slot
+            assert slot.min() == 0 and slot.max() == 5 and np.abs(noise).max() <= 4.0
+            assert abs(noise.mean()) < 0.05 and abs(noise.std() - 8 / np.sqrt(12)) < 0.05
+        # no slot is used twice within an env
+        key = np.where(main, np.round((st["x"] - 10.0) / 50.0), np.where(ramp, 10 + np.round((st["x"] - 5.0) / 50.0), -1))
+        for e in range(0, E, 97):
+            k = key[e][m[e]]
+            assert len(np.unique(k)) == len(k)
+        # n_merge = CAVs spawned on the ramp; CAV split follows num_CAV // 2
+        cav = np.arange(12)[None, :] < ncav[:, None]
+        assert np.array_equal((cav & ramp).sum(1), st["n_merge"])
+        assert np.array_equal((cav & main).sum(1)[ncav != 1], (ncav // 2)[ncav != 1])
+        assert (st["target_speed"][cav] == 25.0).all() and (st["speed_index"][cav] == 3).all()
+        assert (st["min_headway"][cav] == 4.5).all() and (st["hist_len"][m] == 0).all()
+        hd = m & ~cav
+        if hd.any():
+            assert np.array_equal(st["target_speed"][hd], st["speed"][hd])
+            assert np.allclose(st["timer"][hd], ((st["x"][hd] + st["y"][hd]) * np.pi) % 1.0, atol=1e-12)
+        env.close()
+
+
+def test_full_size_properties(mm):
+    """BASELINE size (65536 envs, MASS td3): size-independent invariants of a 100-step auto-reset rollout."""
+    import torch
+    E = 65536
+    cfg = dict(mm.DEFAULT_CONFIG, safety_guarantee="cbf-cav", traffic_density=3, HEADWAY_TIME=0.5, cbf_eta=0.03125,
+               agent_reward="srew", HIGH_SPEED_REWARD=4, HEADWAY_COST=1, MERGING_LANE_COST=8)
+    env = mm.MergeEnvBatched(E, cfg)
+    obs, _ = env.reset(seed=99)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    episodes = 0
+    for t in range(101):
+        a = torch.randint(0, 5, (E, 12), generator=gen, device="cuda", dtype=torch.int8)
+        obs, rew, done, v = env.step(a, auto_reset=True)
+        assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+        n = v["n_agents"]
+        assert int(n.min()) >= 7 and int(n.max()) <= 11
+        present = obs[:, :, 0]
+        idx = torch.arange(12, device="cuda")[None, :]
+        assert torch.equal(present > 0, idx < n[:, None])          # ego rows present exactly for live agents
+        assert torch.equal(v["agents_dones"].amax(1) > 0, done > 0)
+        episodes += int(done.sum())
+        if t < 99:
+            assert int(done.sum()) <= E // 20                      # shielded: crashes are rare before the horizon
+    s = env.stats()
+    assert s["episodes"] == episodes and s["env_steps"] == 101 * E
+    assert episodes >= E  # every env hit the 100-step horizon once
+    # steps restarted at 0 for finished envs
+    st = env.get_state()
+    assert st["steps"].max() <= 100 and (st["steps"] <= 1).sum() >= E * 0.9
+    env.close()

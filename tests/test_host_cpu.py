@@ -1,0 +1,136 @@
+"""CPU suite, part 2: host logic and the C-ABI surface (no compute calls: there is no GPU here)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, ROOT
+from helpers import load_golden
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    import marl_mass_b200 as mm
+    from marl_mass_b200 import build
+    build.build()
+    L = mm.lib()
+    header = open(os.path.join(ROOT, "include", "marl_mass_b200.h")).read()
+    declared = set(re.findall(r"\b(mm_[a-z_]+)\s*\(", header))
+    assert {"mm_create", "mm_step", "mm_step_host", "mm_reset", "mm_shield_qp", "mm_get_state"} <= declared
+    for name in declared:
+        assert hasattr(L, name), "declared in include/marl_mass_b200.h but not exported: " + name
+    assert b"sm_100a" in L.mm_version()
+
+
+def test_shared_object_is_sm100a_only():
+    from marl_mass_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from marl_mass_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libmarl_mass_b200.so")
+    with pytest.raises(_lib.MMError, match="no CPU fallback"):
+        _lib.lib()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "marl-mass_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), os.path.join(dirpath, f)
+
+
+def test_config_mapping_and_error_behaviour():
+    import marl_mass_b200 as mm
+    c = mm.make_mm_config(dict(mm.DEFAULT_CONFIG, safety_guarantee="cbf-cav", HEADWAY_TIME=0.5, cbf_eta=0.03125,
+                               traffic_density=3, traffic_type="mixed", agent_reward="srew"))
+    assert (c.shield, c.reward_kind, c.traffic_density, c.traffic_type) == (2, 1, 3, 1)
+    assert c.duration_steps == 100 and c.substeps == 3 and c.dt == 1 / 15 and c.tau == 0.5 and c.eta == 0.03125
+    for sg in ("cbf-avs_cint", "cbf-avs", "cbf-av", "cbf-hss"):
+        assert mm.make_mm_config(dict(mm.DEFAULT_CONFIG, safety_guarantee=sg)).shield == 1
+    with pytest.raises(ValueError, match="Undefined safety_type"):   # decentral_layer.py:817
+        mm.make_mm_config(dict(mm.DEFAULT_CONFIG, safety_guarantee="cbf-foo"))
+    with pytest.raises(AttributeError, match="Lateral control"):     # safe_controller.py:174
+        mm.make_mm_config(dict(mm.DEFAULT_CONFIG, lateral_control="steer_vel"))
+    with pytest.raises(ValueError):
+        mm.make_mm_config(dict(mm.DEFAULT_CONFIG, safety_guarantee="priority"))
+    with pytest.raises(KeyError):
+        mm.make("merge-v1")
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_seed_exact_spawn_matches_reference_reset(name):
+    """Host replay of the reference's MT19937 draw order: reset(testing_seeds=s) builds the same scene."""
+    import marl_mass_b200 as mm
+    from marl_mass_b200 import _lib
+    g, cfg = load_golden(name)
+    st = mm.spawn.spawn_state(cfg["seeds"], cfg["traffic_density"], cfg["traffic_type"])
+    rows = g["ep_start"][:-1]
+    for k in _lib.F64_FIELDS + _lib.I32_FIELDS + _lib.ENV_FIELDS:
+        assert np.array_equal(g["st_" + k][rows], st[k]), k
+
+
+def test_spawn_num_cav_override_and_ranges():
+    import marl_mass_b200 as mm
+    for seed in range(40):
+        v, n_merge = mm.spawn.spawn_scene(seed, 3, "mixed", num_CAV=5)
+        kinds = [k for k, *_ in v]
+        assert kinds.count(1) == 5 and 3 <= kinds.count(2) <= 5 and kinds == sorted(kinds)
+        assert n_merge == 5 - 5 // 2
+        xs = [x for _, x, _, _ in v]
+        assert len(set(np.round(xs, 9))) == len(xs) and all(1 <= x <= 264 for x in xs)
+    with pytest.raises(ValueError):
+        mm.spawn.spawn_scene(0, 1, "hdv")
+
+
+def test_shard_ranges_cover_the_env_axis():
+    from marl_mass_b200 import dist
+    for total, world in ((1 << 20, 8), (65536, 4), (1000, 3), (5, 8)):
+        spans = [dist.shard_range(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [e - b for b, e in spans]
+        assert max(sizes) - min(sizes) <= 1
+    assert len({dist.rank_seed(7, r) for r in range(8)}) == 8
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch.distributed as dist
+from marl_mass_b200 import dist as mmd
+rank = int(os.environ["RANK"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=rank, world_size=2)
+stats = {k: float(rank + 1) for k in mmd.SUM_KEYS}
+stats["min_headway"] = 0.75 - 0.25 * rank
+tot = mmd.all_reduce_stats(stats)
+assert all(tot[k] == 3.0 for k in mmd.SUM_KEYS), tot
+assert tot["min_headway"] == 0.5, tot
+b, e = mmd.shard_range(65536 * 2, rank, 2)
+assert e - b == 65536 and b == rank * 65536
+s = mmd.summarize(tot)
+assert s["crash_rate"] == 1.0 and s["shield_active_frac"] == 1.0
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_stats_all_reduce_world_size_2_gloo(tmp_path):
+    """The only collective on the path: SUM of the counters, MIN of min_headway."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port],
+                              env=dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1"),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and ("ok %d" % r) in o, o

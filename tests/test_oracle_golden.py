@@ -1,0 +1,124 @@
+"""CPU suite, part 1: pin the oracle (oracle/merge_oracle.c) against the golden vectors that
+oracle/refharness/gen_golden.py froze from the UNMODIFIED reference env + shield.
+
+Teacher forcing: every policy step starts from the reference's own pre-step state, gets the
+reference's action tuple, and must reproduce the reference's post-step state, MergeEnv.step outputs and
+per-sub-step shield record.  Discrete outputs bit-exact; continuous within 1e-9 relative (observed: 1e-13).
+"""
+import numpy as np
+import pytest
+
+import oracle as orc
+from conftest import GOLDEN_CASES
+from helpers import (ENV_FIELDS, F64_FIELDS, LC_BOUNDARY_EPS, OUT_F, OUT_I, SH_F, SH_I, compare_states,
+                     load_golden, rel_err)
+
+TOL = 1e-9
+ALL = (orc.F64_FIELDS, orc.I32_FIELDS, orc.ENV_FIELDS)
+
+
+def golden_state(g, rows):
+    return orc.state_from_golden(g, rows)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_teacher_forced_step(name):
+    g, cfg = load_golden(name)
+    rows = g["row_of_step"]
+    st = golden_state(g, rows)
+    out = orc.step(cfg, st, g["act"], n_threads=4)
+    want = golden_state(g, rows + 1)
+    compare_states(st, want, TOL, name)
+    for k in OUT_I:
+        assert np.array_equal(out[k], g[k]), k
+    for k in OUT_F:
+        assert rel_err(out[k], g[k]).max() <= TOL, k
+    ran = g["sh_ran"] == 1
+    assert np.array_equal(out["sh_ran"], g["sh_ran"])
+    boundary = ran & (out["sh_lc_margin"] < LC_BOUNDARY_EPS)
+    for k in SH_I:
+        bad = (out["sh_" + k] != g["sh_" + k]) & ran & ~boundary
+        assert not bad.any(), (k, np.argwhere(bad)[:5].tolist())
+    for k in SH_F:
+        assert (rel_err(out["sh_" + k], g["sh_" + k]) * (ran & ~boundary)).max() <= TOL, k
+    # the excluded boundary set must stay tiny (<= 1% of solves)
+    assert boundary.sum() <= 0.01 * max(ran.sum(), 1) + 1
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_free_running_episodes(name):
+    """From each episode's first state, step the oracle alone with the recorded actions to the end of the
+    episode: it must terminate on the same step and land on the reference's final state."""
+    g, cfg = load_golden(name)
+    ep = g["ep_start"]
+    rows = g["row_of_step"]
+    for j in range(len(ep) - 1):
+        first, last = ep[j], ep[j + 1] - 1
+        steps = np.where((rows >= first) & (rows < last))[0]
+        st = golden_state(g, [first])
+        done = 0
+        for t in steps:
+            assert not done
+            out = orc.step(cfg, st, g["act"][t:t + 1])
+            done = int(out["done"][0])
+            assert done == int(g["done"][t])
+            assert rel_err(out["reward"], g["reward"][t]).max() <= 1e-7
+        assert done == 1
+        compare_states(st, golden_state(g, [last]), 1e-7, "%s episode %d" % (name, j))
+
+
+@pytest.mark.parametrize("name", [c for c in GOLDEN_CASES if not c.startswith("unsafe")])
+def test_qp_known_answers(name):
+    """Every QP the reference posed (G, h as built by cbf.py:288-322/374-422) -> same minimiser and active set."""
+    g, _ = load_golden(name)
+    n = len(g["qp_a"])
+    assert n > 1000
+    for i in range(0, n, 7):
+        u, act = orc.qp(g["qp_a"][i], g["qp_c_lead"][i], g["qp_c_adj"][i], g["qp_has_adj"][i] > 0,
+                        g["qp_lo"][i], g["qp_hi"][i])
+        assert u == g["qp_u"][i] and act == int(g["qp_active"][i])
+
+
+def test_qp_cases_by_hand():
+    # inactive: 0 inside the box and below the barrier limit
+    assert orc.qp(0.0667, 3.0, 0.0, False, -0.8, 0.4) == (0.0, 0)
+    # barrier row active: u = c/a
+    u, act = orc.qp(0.05, -0.01, 0.0, False, -0.8, 0.4)
+    assert u == -0.01 / 0.05 and act == 1
+    # lower bound + slack: the limit is below the box
+    u, act = orc.qp(0.05, -1.0, 0.0, False, -0.8, 0.4)
+    assert u == -0.8 and act == (1 | 4 | 16)
+    # adjacent row tighter than the lead row
+    u, act = orc.qp(0.05, -0.01, -0.02, True, -0.8, 0.4)
+    assert u == -0.02 / 0.05 and act == 8
+    # box entirely below zero
+    u, act = orc.qp(0.05, 3.0, 0.0, False, -0.8, -0.1)
+    assert u == -0.1 and act == 2
+
+
+def test_observe_matches_reset_observation():
+    """reset() returns the observation of the spawned scene: oracle observe on a golden pre-state equals the
+    obs the reference returned for the previous step's post-state."""
+    g, cfg = load_golden("mass_td3_mixed")
+    rows = g["row_of_step"]
+    st = golden_state(g, rows + 1)
+    obs = orc.observe(st)
+    assert rel_err(obs, g["obs"]).max() <= TOL
+
+
+def test_fixture_inventory():
+    """Fixtures cover crashes, vetoes, every QP active-set class that occurs, HDVs and both shields."""
+    seen_active = set()
+    crashed = vetoes = hdv = 0
+    for name in GOLDEN_CASES:
+        g, cfg = load_golden(name)
+        seen_active |= set(np.unique(g["sh_active"][g["sh_ran"] == 1]).tolist())
+        crashed += int(g["st_crashed"].max())
+        vetoes += int(((g["sh_ran"] == 1) & (g["sh_is_lc_safe"] == 0)).sum())
+        hdv += int((g["st_kind"] == 2).sum() > 0)
+        for k in F64_FIELDS:
+            assert np.isfinite(g["st_" + k]).all()
+        for k in ENV_FIELDS:
+            assert (g["st_" + k] >= 0).all()
+    assert {0, 1, 8}.issubset(seen_active), seen_active
+    assert crashed >= 3 and vetoes > 1000 and hdv >= 4
