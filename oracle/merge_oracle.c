@@ -659,7 +659,11 @@ static void shield(const mo_config *cfg, env_t *e, int self, shield_rec *rec) {
     double hlds_r = dr + (ge_dt * v_safe + -gr_dt * v_oar) + q_lonr;
     double cond_a = hlds_a + (eta - 1) * hls_a;
     double cond_r = hlds_r + (eta - 1) * hls_r;
-    int allowed = (hls_a >= 0 && cond_a >= 0) && (hls_r >= 0 && cond_r >= 0);
+    /* Tie rule (DESIGN.md "Veto tie rule"): when the adjacent row is the binding QP constraint (and feasible),
+       cond_a is 0 in exact arithmetic and +-1e-15 rounding noise in float64; it is taken
+       as satisfied, which is also what an interior-point solve (real cvxopt) yields. */
+    int adj_inv_ok = (active == MO_ACT_ADJ) ? 1 : (cond_a >= 0);
+    int allowed = (hls_a >= 0 && adj_inv_ok) && (hls_r >= 0 && cond_r >= 0);
     rec->lc_margin = fmin(fmin(fabs(hls_a), fabs(cond_a)), fmin(fabs(hls_r), fabs(cond_r)));
 
     if (!mass) {
