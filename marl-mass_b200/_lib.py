@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_build", "libmarl_mass_b200.so")
+LIB_PATH = os.environ.get("MM_LIB_PATH") or os.path.join(_HERE, "_build", "libmarl_mass_b200.so")
 
 MAXV = 12
 NS = 30

@@ -129,11 +129,12 @@ int mm_create(const mm_config *cfg, int n_envs, int device, int record_diag, mm_
     mm_env *env = new mm_env();
     env->n_envs = n_envs; env->device = device; env->record_diag = record_diag; env->cfg = *cfg;
     const size_t E = (size_t)n_envs;
+    const size_t E_pad = (E + TILE - 1) / TILE * TILE;   // state is tiled: [n_tiles][field][slot][TILE]
     int rc = 0;
-    rc |= dev_alloc(env, &env->st.f64, (size_t)F_COUNT * MAXV * E);
-    rc |= dev_alloc(env, &env->st.flags, (size_t)MAXV * E);
-    rc |= dev_alloc(env, &env->st.einfo, E);
-    rc |= dev_alloc(env, &env->st.episode, E);
+    rc |= dev_alloc(env, &env->st.f64, (size_t)F_COUNT * MAXV * E_pad);
+    rc |= dev_alloc(env, &env->st.flags, (size_t)MAXV * E_pad);
+    rc |= dev_alloc(env, &env->st.einfo, E_pad);
+    rc |= dev_alloc(env, &env->st.episode, E_pad);
     rc |= dev_alloc(env, &env->out.obs, E * MAXV * NS);
     rc |= dev_alloc(env, &env->out.reward, E);
     rc |= dev_alloc(env, &env->out.agents_rewards, E * MAXV);

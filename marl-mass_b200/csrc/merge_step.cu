@@ -26,7 +26,10 @@
 
 namespace mm {
 
-constexpr int BLOCK = 128;
+constexpr int BLOCK = TILE;
+#ifndef MM_MIN_BLOCKS
+#define MM_MIN_BLOCKS 3   // CTAs per SM the step kernel is compiled for (register budget 65536 / (128 * n))
+#endif
 constexpr double PI = 3.141592653589793;
 constexpr double TWO_PI = 2 * PI;
 
@@ -50,6 +53,11 @@ constexpr double KP_LATERAL = 1.0 / 3 * KP_HEADING;
 constexpr double PURSUIT_TAU = 0.5 * 0.2;
 constexpr double MAX_STEER = PI / 3;
 constexpr double ACC_LO = -12.5, ACC_HI = 6.0;
+// sqrt is correctly rounded and monotone, so the reference's norm tests have exact squared-distance forms:
+//   sqrt(q) < 180  <=>  q < 0x1.fa3ffffffffffp+14   (the smallest double whose sqrt rounds to 180.0)
+//   sqrt(q) > 5    <=>  q > 0x1.9000000000001p+4    (the largest double whose sqrt rounds to 5.0)
+constexpr double PERCEPTION_SQ_LT = 0x1.fa3ffffffffffp+14;
+constexpr double VLEN_SQ_GT = 0x1.9000000000001p+4;
 
 // ------------------------------------------------------------------------------------------------
 // per-thread view of one environment
@@ -57,8 +65,7 @@ constexpr double ACC_LO = -12.5, ACC_HI = 6.0;
 struct Env {
     double *sx, *sy, *sh, *sv;  // shared planes, already offset by threadIdx.x; element i at [i * BLOCK]
     uint32_t *sf;
-    double *g;                  // cold planes, already offset by the env index; element (f, i) at [(f*MAXV+i)*E]
-    size_t E;
+    double *g;                  // this env's column of its tile; element (f, i) at [(f*MAXV+i)*TILE]
     int n_veh, n_cav;
 };
 
@@ -67,7 +74,7 @@ struct Env {
 #define H(i) (ev.sh[(i) * BLOCK])
 #define V(i) (ev.sv[(i) * BLOCK])
 #define FL(i) (ev.sf[(i) * BLOCK])
-#define GF(f, i) (ev.g[(size_t)((f) * MAXV + (i)) * ev.E])
+#define GF(f, i) (ev.g[((f) * MAXV + (i)) * TILE])
 
 __device__ __forceinline__ int fl_kind(uint32_t f) { return f & FL_KIND_MASK; }
 __device__ __forceinline__ int fl_lane(uint32_t f) { return (f >> FL_LANE_SHIFT) & FL_3BIT; }
@@ -77,6 +84,23 @@ __device__ __forceinline__ int fl_hist(uint32_t f) { return (f >> FL_HIST_SHIFT)
 __device__ __forceinline__ uint32_t fl_set(uint32_t f, uint32_t shift, uint32_t mask, uint32_t v) {
     return (f & ~(mask << shift)) | (v << shift);
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// double-precision libm entry points, one copy each.  Inlining them at every call site made the step kernel
+// 233 KB of SASS and instruction-cache misses its top stall (profiles/r1_v1_*); as out-of-line functions
+// the whole kernel is a fraction of that.  Same libdevice code, same bits.
+// ------------------------------------------------------------------------------------------------
+__device__ __noinline__ double m_sin(double x) { return sin(x); }
+__device__ __noinline__ double m_cos(double x) { return cos(x); }
+__device__ __noinline__ double2 m_sincos(double x) { double2 r; sincos(x, &r.x, &r.y); return r; }
+__device__ __noinline__ double m_tan(double x) { return tan(x); }
+__device__ __noinline__ double m_atan(double x) { return atan(x); }
+__device__ __noinline__ double m_asin(double x) { return asin(x); }
+__device__ __noinline__ double m_exp(double x) { return exp(x); }
+__device__ __noinline__ double m_log(double x) { return log(x); }
+__device__ __noinline__ double m_pow(double x, double y) { return pow(x, y); }
+__device__ __noinline__ double m_fmod(double x, double y) { return fmod(x, y); }
 
 // ------------------------------------------------------------------------------------------------
 // scalar helpers (utils.py:16-41)
@@ -88,7 +112,8 @@ __device__ __forceinline__ double not_zero(double x) {
 __device__ __forceinline__ double clipd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 // Python's floored float modulo by a positive modulus
 __device__ __forceinline__ double pymod_pos(double a, double b) {
-    double r = fmod(a, b);
+    if (a >= 0 && a < b) return a;  // fmod(a, b) == a exactly when 0 <= a < b: skip the (iterative) fmod
+    double r = m_fmod(a, b);
     if (r < 0) r += b;
     return r;
 }
@@ -103,11 +128,11 @@ __device__ __forceinline__ double lmap(double v, double x0, double x1, double y0
 __device__ __forceinline__ double lane_s(int lane, double px) { return px - c_lane_sx[lane]; }
 __device__ __forceinline__ double lane_r(int lane, double s, double py) {
     double r = py - c_lane_sy[lane];
-    if (lane == L_KB0) r = r - SINE_AMP * sin(SINE_PULS * s + SINE_PHASE);
+    if (lane == L_KB0) r = r - SINE_AMP * m_sin(SINE_PULS * s + SINE_PHASE);
     return r;
 }
 __device__ __forceinline__ double lane_heading_at(int lane, double s) {
-    if (lane == L_KB0) return atan(SINE_AMP * SINE_PULS * cos(SINE_PULS * s + SINE_PHASE));
+    if (lane == L_KB0) return m_atan(SINE_AMP * SINE_PULS * m_cos(SINE_PULS * s + SINE_PHASE));
     return 0.0;
 }
 __device__ __forceinline__ bool on_lane(int lane, double px, double py, double margin) {
@@ -122,7 +147,7 @@ __device__ __forceinline__ double straight_lane_distance(int lane, double px, do
     return fabs(r) + fmax(s - c_lane_len[lane], 0.0) + fmax(0.0 - s, 0.0);
 }
 // road.py:67-109 with route=None (every node has a single successor)
-__device__ __forceinline__ int next_lane(int lane, double px, double py) {
+__device__ __noinline__ int next_lane(int lane, double px, double py) {
     if (lane == L_AB0 || lane == L_KB0)
         return straight_lane_distance(L_BC0, px, py) <= straight_lane_distance(L_BC1, px, py) ? L_BC0 : L_BC1;
     if (lane == L_JK0) return L_KB0;
@@ -163,10 +188,10 @@ __device__ __noinline__ double steering_control(double px, double py, double hea
     double future_heading = lane_heading_at(tlane, s + speed * PURSUIT_TAU);
     double lat_cmd = -KP_LATERAL * r;
     double nz = not_zero(speed);
-    double heading_cmd = asin(clipd(lat_cmd / nz, -1.0, 1.0));
+    double heading_cmd = m_asin(clipd(lat_cmd / nz, -1.0, 1.0));
     double heading_ref = future_heading + clipd(heading_cmd, -PI / 4, PI / 4);
     double rate_cmd = KP_HEADING * wrap_to_pi(heading_ref - heading);
-    double steering = asin(clipd(VLEN / 2 / nz * rate_cmd, -1.0, 1.0));
+    double steering = m_asin(clipd(VLEN / 2 / nz * rate_cmd, -1.0, 1.0));
     return clipd(steering, -MAX_STEER, MAX_STEER);
 }
 
@@ -183,7 +208,7 @@ __device__ __forceinline__ int follow_road(int tlane, double px, double py) {
 }
 
 // MDPLCVehicle.act -> MDPVehicle.act -> ControlledVehicle.act (safe_controller.py:63-66, controller.py:293-311, 90-134)
-__device__ void cav_act(Env &ev, int i, int action) {
+__device__ __noinline__ void cav_act(Env &ev, int i, int action) {
     uint32_t f = FL(i);
     double px = X(i), py = Y(i), speed = V(i);
     if (action != A_NONE) f = fl_set(f, FL_HL_SHIFT, FL_3BIT, (uint32_t)action);
@@ -213,7 +238,7 @@ __device__ __forceinline__ void ent_pos(const Env &ev, int id, double &px, doubl
 }
 
 // road.py:352-381 (candidates: vehicles in list order, then the obstacle)
-__device__ void neighbour_vehicles(const Env &ev, int self, int lane, int &front, int &rear) {
+__device__ __noinline__ void neighbour_vehicles(const Env &ev, int self, int lane, int &front, int &rear) {
     double s = lane_s(lane, X(self)), s_front = 0, s_rear = 0;
     front = -1;
     rear = -1;
@@ -232,24 +257,24 @@ __device__ void neighbour_vehicles(const Env &ev, int self, int lane, int &front
 }
 
 // behavior.py:141-156
-__device__ double desired_gap(const Env &ev, int ego, int front) {
+__device__ __noinline__ double desired_gap(const Env &ev, int ego, int front) {
     double fvx = 0, fvy = 0;
     if (front != OBST) {
         double fs, fc;
-        sincos(H(front), &fs, &fc);
+        { double2 sc_ = m_sincos(H(front)); fs = sc_.x; fc = sc_.y; }
         fvx = V(front) * fc;
         fvy = V(front) * fs;
     }
     double es, ec, speed = V(ego);
-    sincos(H(ego), &es, &ec);
+    { double2 sc_ = m_sincos(H(ego)); es = sc_.x; ec = sc_.y; }
     double dv = (speed * ec - fvx) * ec + (speed * es - fvy) * es;
     return 10.0 + speed * 1.5 + speed * dv / (2 * sqrt(15.0));
 }
 
 // behavior.py:111-139 (ego/front: -1 None, OBST obstacle)
-__device__ double idm_acc(const Env &ev, int ego, int front) {
+__device__ __noinline__ double idm_acc(const Env &ev, int ego, int front) {
     if (ego < 0 || ego == OBST) return 0.0;
-    double acc = 3.0 * (1 - pow(fmax(V(ego), 0.0) / not_zero(GF(F_TSPEED, ego)), 4.0));
+    double acc = 3.0 * (1 - m_pow(fmax(V(ego), 0.0) / not_zero(GF(F_TSPEED, ego)), 4.0));
     if (front >= 0) {
         double fx, fy;
         ent_pos(ev, front, fx, fy);
@@ -262,7 +287,7 @@ __device__ double idm_acc(const Env &ev, int ego, int front) {
 }
 
 // behavior.py:186-266 (route None, POLITENESS 0: the follower terms enter the jerk with weight 0.0)
-__device__ int hdv_change_lane(Env &ev, int self, uint32_t f, int tl) {
+__device__ __noinline__ int hdv_change_lane(Env &ev, int self, uint32_t f, int tl) {
     int lane = fl_lane(f);
     if (lane != tl) {
         if (lane_road(lane) == lane_road(tl)) {
@@ -353,9 +378,8 @@ __device__ __forceinline__ double solve_cbf_qp(double a, double c_lead, double c
 }
 
 // decentral_layer.py:23-39
-__device__ __forceinline__ int is_adj_lane(int l1, double px, double py, int l2) {
+__device__ __forceinline__ int is_adj_lane(int l1, int nl /* next_lane(l1, position) */, int l2) {
     if (lane_road(l1) == lane_road(l2) && abs(lane_rid(l1) - lane_rid(l2)) == 1) return lane_rid(l1) - lane_rid(l2);
-    int nl = next_lane(l1, px, py);
     if (lane_road(nl) == lane_road(l2) && abs(lane_rid(nl) - lane_rid(l2)) == 1) return lane_rid(nl) - lane_rid(l2);
     return 0;
 }
@@ -363,10 +387,10 @@ __device__ __forceinline__ int is_adj_lane(int l1, double px, double py, int l2)
 // controller.py:257-267; left: dir == "L"
 __device__ __forceinline__ void get_corner(double px, double py, double heading, bool left, double &cx, double &cy) {
     const double corner_len = sqrt((VWID / 2) * (VWID / 2) + (VLEN / 2) * (VLEN / 2)) + 0.0075;
-    const double corner_alpha = atan(VWID / VLEN);
+    const double corner_alpha = m_atan(VWID / VLEN);
     double ang = left ? corner_alpha + heading : -corner_alpha + heading;
-    cx = px + (corner_len * cos(corner_alpha + heading));
-    cy = py - (corner_len * sin(ang)) + 0.01;
+    cx = px + (corner_len * m_cos(corner_alpha + heading));
+    cy = py - (corner_len * m_sin(ang)) + 0.01;
 }
 
 struct ShieldRec {
@@ -389,7 +413,7 @@ __device__ __forceinline__ int close_vehicles(const Env &ev, int self, int (&ids
         if (j == self) continue;
         double ox = X(j), oy = Y(j);
         double dx = ox - ex, dy = oy - ey;
-        if (!(sqrt(dx * dx + dy * dy) < PERCEPTION)) continue;
+        if (!(dx * dx + dy * dy < PERCEPTION_SQ_LT)) continue;  // np.linalg.norm(...) < 180
         double key = fabs(lane_s(el, ox) - es);
         int id = j;
         ++n;
@@ -421,7 +445,7 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
     double v_min = espeed + ACC_LO * dt;
     if (mass) v_min = fmax(0.0, v_min);
     double v_max = espeed + ACC_HI * dt;
-    double evx_raw = espeed * cos(eh);
+    double evx_raw = espeed * m_cos(eh);
     double evx = evx_raw > 1 ? evx_raw : 1;
     double es = lane_s(elane, ex);
 
@@ -433,6 +457,7 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
 
     int nb[5];
     int n_nb = close_vehicles<5>(ev, self, nb);
+    const int e_next = next_lane(elane, ex, ey);
 #pragma unroll 1
     for (int k = 0; k < n_nb; ++k) {
         int o = nb[k];
@@ -440,8 +465,8 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
         int olane = fl_lane(fo);
         double ox = X(o), oy = Y(o), oh = H(o);
         bool o_cav = fl_kind(fo) == MM_KIND_CAV;
-        int v_a = is_adj_lane(elane, ex, ey, olane);
-        int a_v = is_adj_lane(olane, ox, oy, elane);
+        int v_a = is_adj_lane(elane, e_next, olane);
+        int a_v = is_adj_lane(olane, next_lane(olane, ox, oy), elane);
         double d = lane_s(elane, ox) - es;
         // is_approaching_same_lane (decentral_layer.py:46-57)
         bool approaching = false;
@@ -454,7 +479,7 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
             if (!has_oar && d < 0) {  // rear-adjacent: its current state
                 has_oar = true; id_oar = o;
                 x_oar = ox;
-                vx_oar = V(o) * cos(oh);
+                vx_oar = V(o) * m_cos(oh);
             } else if (!has_oa && d >= 0) {  // front-adjacent: its record before its last step
                 has_oa = true; id_oa = o;
                 x_oa = GF(F_REC2X, o);
@@ -479,7 +504,7 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
             a_oa = ACC_LO;
             g_oa = 1.0;
         } else if (!has_ol && d > 0) {
-            bool same = (elane == olane) || (olane == next_lane(elane, ex, ey));
+            bool same = (elane == olane) || (olane == e_next);
             if (same || approaching) {
                 has_ol = true; id_ol = o;
                 x_ol = GF(F_REC2X, o);
@@ -627,15 +652,15 @@ __device__ void vehicle_step(Env &ev, const StepParams &p, int i, int sub, size_
         GF(F_ACT_ACC, i) = acc;
     }
     // modified bicycle model
-    double beta = atan(1.0 / 2 * tan(steer));
+    double beta = m_atan(1.0 / 2 * m_tan(steer));
     double sn, cs;
-    sincos(heading + beta, &sn, &cs);
+    { double2 sc_ = m_sincos(heading + beta); sn = sc_.x; cs = sc_.y; }
     double nx = X(i) + speed * cs * dt;
     double ny = Y(i) + speed * sn * dt;
-    double nh = heading + speed * sin(beta) / (VLEN / 2) * dt;
+    double nh = heading + speed * m_sin(beta) / (VLEN / 2) * dt;
     double nv = fmax(0.0, speed + acc * dt);
     if (cav) {
-        GF(F_GVX, i) = cos(nh + beta);
+        GF(F_GVX, i) = m_cos(nh + beta);
         f |= FL_FG;
     }
     // on_state_update + log_step
@@ -643,7 +668,7 @@ __device__ void vehicle_step(Env &ev, const StepParams &p, int i, int sub, size_
     f = fl_set(f, FL_LANE_SHIFT, FL_3BIT, (uint32_t)lane);
     GF(F_REC2X, i) = X(i);
     GF(F_REC2VX, i) = GF(F_REC1VX, i);
-    GF(F_REC1VX, i) = nv * cos(nh);
+    GF(F_REC1VX, i) = nv * m_cos(nh);
     int hist = fl_hist(f);
     if (hist < 2) f = fl_set(f, FL_HIST_SHIFT, 3u, (uint32_t)(hist + 1));
     X(i) = nx; Y(i) = ny; H(i) = nh; V(i) = nv;
@@ -655,17 +680,21 @@ __device__ void vehicle_step(Env &ev, const StepParams &p, int i, int sub, size_
 // ------------------------------------------------------------------------------------------------
 // does rect1 (centre c1, half sizes lx/wy, angle a1) have one of its 9 sample points inside rect2?
 // NB the reference rotates (p - c2) by +a2, not -a2; reproduced as is.
-__device__ bool has_corner_inside(double c1x, double c1y, double lx, double wy, double a1, double c2x, double c2y,
+__device__ __noinline__ bool has_corner_inside(double c1x, double c1y, double lx, double wy, double a1, double c2x, double c2y,
                                   double l2, double w2, double a2) {
     double s1, co1, s2, co2;
-    sincos(a1, &s1, &co1);
-    sincos(a2, &s2, &co2);
-    const double px[9] = {0, -lx, lx, 0, 0, -lx, -lx, lx, lx};
-    const double py[9] = {0, 0, 0, -wy, wy, -wy, wy, -wy, wy};
-#pragma unroll
+    { double2 sc_ = m_sincos(a1); s1 = sc_.x; co1 = sc_.y; }
+    { double2 sc_ = m_sincos(a2); s2 = sc_.x; co2 = sc_.y; }
+    // sample points in the reference's order: centre, -l, +l, -w, +w, -l-w, -l+w, +l-w, +l+w (utils.py:115-117);
+    // sign of the l / w component of point k packed two bits each (0: zero, 1: plus, 2: minus)
+    const uint32_t lsel = 0x16818u, wsel = 0x19980u;
+#pragma unroll 1
     for (int k = 0; k < 9; ++k) {
-        double rx = co1 * px[k] + -s1 * py[k];
-        double ry = s1 * px[k] + co1 * py[k];
+        uint32_t lc = (lsel >> (2 * k)) & 3u, wc = (wsel >> (2 * k)) & 3u;
+        double pxk = lc == 0 ? 0.0 : (lc == 1 ? lx : -lx);
+        double pyk = wc == 0 ? 0.0 : (wc == 1 ? wy : -wy);
+        double rx = co1 * pxk + -s1 * pyk;
+        double ry = s1 * pxk + co1 * pyk;
         double dx = (c1x + rx) - c2x, dy = (c1y + ry) - c2y;
         double ux = co2 * dx + -s2 * dy;
         double uy = s2 * dx + co2 * dy;
@@ -680,14 +709,14 @@ __device__ __noinline__ bool rects_intersect(double ax, double ay, double ah, do
            has_corner_inside(bx, by, 0.9 * blen / 2, 0.9 * bwid / 2, bh, ax, ay, 0.9 * VLEN, 0.9 * VWID, ah);
 }
 
-__device__ void collision_pass(Env &ev) {
+__device__ __noinline__ void collision_pass(Env &ev) {
     for (int i = 0; i < ev.n_veh; ++i) {
         double ax = X(i), ay = Y(i);
         for (int j = 0; j < ev.n_veh; ++j) {
             if (j == i) continue;
             if (FL(i) & FL_CRASHED) break;
             double dx = X(j) - ax, dy = Y(j) - ay;
-            if (sqrt(dx * dx + dy * dy) > VLEN) continue;
+            if (dx * dx + dy * dy > VLEN_SQ_GT) continue;  // np.linalg.norm(...) > LENGTH
             if (rects_intersect(ax, ay, H(i), X(j), Y(j), H(j), VLEN, VWID)) {
                 double va = V(i), vb = V(j);
                 double m = fabs(va) <= fabs(vb) ? va : vb;
@@ -697,7 +726,7 @@ __device__ void collision_pass(Env &ev) {
         }
         if (!(FL(i) & FL_CRASHED)) {
             double dx = OBST_X - ax, dy = OBST_Y - ay;
-            if (!(sqrt(dx * dx + dy * dy) > VLEN) && rects_intersect(ax, ay, H(i), OBST_X, OBST_Y, 0.0, 2.0, 2.0)) {
+            if (!(dx * dx + dy * dy > VLEN_SQ_GT) && rects_intersect(ax, ay, H(i), OBST_X, OBST_Y, 0.0, 2.0, 2.0)) {
                 double va = V(i);
                 V(i) = fabs(va) <= 0 ? va : 0.0;
                 FL(i) |= FL_CRASHED;
@@ -716,45 +745,35 @@ __device__ __forceinline__ bool is_terminal(const Env &ev, int steps, int durati
 // ------------------------------------------------------------------------------------------------
 // observation, rewards, info
 // ------------------------------------------------------------------------------------------------
-// observation.py:241-273 + normalize_obs 181-193: ego row absolute, 4 nearest rows relative, no clipping
-__device__ void observe_agent(const Env &ev, int self, float *obs) {
-    double es, ec;
-    sincos(H(self), &es, &ec);
-    double ex = X(self), ey = Y(self), evx = V(self) * ec, evy = V(self) * es;
+// observation.py:241-273 + normalize_obs 181-193: ego row absolute, 4 nearest rows relative, no clipping.
+// The rows are float32 outputs, so lmap's divisions by the constant ranges are multiplications by the
+// reciprocals here (a <= 1-ulp float64 difference, invisible after rounding to float32).
+__device__ __noinline__ void observe_agent(const Env &ev, int self, const double *vx, const double *vy, float *obs) {
+    const double KX = 2.0 / 300.0, KY = 2.0 / 24.0, KV = 2.0 / 90.0, KH = 2.0 / PI;
+    double ex = X(self), ey = Y(self), evx = vx[self], evy = vy[self];
     int nb[4];
     int n_nb = close_vehicles<4>(ev, self, nb);
-    float row[NS];
-    row[0] = 1.0f;
-    row[1] = (float)lmap(ex, -150.0, 150.0, -1, 1);
-    row[2] = (float)lmap(ey, -12, 12, -1, 1);
-    row[3] = (float)lmap(evx, -45.0, 45.0, -1, 1);
-    row[4] = (float)lmap(evy, -45.0, 45.0, -1, 1);
-    row[5] = (float)lmap(H(self), -PI / 2, PI / 2, -1, 1);
+    float2 *dst = reinterpret_cast<float2 *>(obs);  // 120-byte rows: 8-byte aligned
+    dst[0] = make_float2(1.0f, (float)((ex + 150.0) * KX - 1.0));
+    dst[1] = make_float2((float)((ey + 12.0) * KY - 1.0), (float)((evx + 45.0) * KV - 1.0));
+    dst[2] = make_float2((float)((evy + 45.0) * KV - 1.0), (float)((H(self) + PI / 2) * KH - 1.0));
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        float *r = row + (k + 1) * MM_OBS_FEATS;
+        float2 a = make_float2(0.f, 0.f), b = a, c = a;
         if (k < n_nb) {
             int o = nb[k];
-            double os, oc;
-            sincos(H(o), &os, &oc);
-            r[0] = 1.0f;
-            r[1] = (float)lmap(X(o) - ex, -150.0, 150.0, -1, 1);
-            r[2] = (float)lmap(Y(o) - ey, -12, 12, -1, 1);
-            r[3] = (float)lmap(V(o) * oc - evx, -45.0, 45.0, -1, 1);
-            r[4] = (float)lmap(V(o) * os - evy, -45.0, 45.0, -1, 1);
-            r[5] = (float)lmap(H(o), -PI / 2, PI / 2, -1, 1);
-        } else {
-#pragma unroll
-            for (int q = 0; q < MM_OBS_FEATS; ++q) r[q] = 0.0f;
+            a = make_float2(1.0f, (float)(((X(o) - ex) + 150.0) * KX - 1.0));
+            b = make_float2((float)(((Y(o) - ey) + 12.0) * KY - 1.0), (float)(((vx[o] - evx) + 45.0) * KV - 1.0));
+            c = make_float2((float)(((vy[o] - evy) + 45.0) * KV - 1.0), (float)((H(o) + PI / 2) * KH - 1.0));
         }
+        dst[3 * (k + 1)] = a;
+        dst[3 * (k + 1) + 1] = b;
+        dst[3 * (k + 1) + 2] = c;
     }
-    float2 *dst = reinterpret_cast<float2 *>(obs);  // 120-byte rows: 8-byte aligned
-#pragma unroll
-    for (int q = 0; q < NS / 2; ++q) dst[q] = make_float2(row[2 * q], row[2 * q + 1]);
 }
 
 // abstract.py:620-635
-__device__ double headway_distance(const Env &ev, int self) {
+__device__ __noinline__ double headway_distance(const Env &ev, int self) {
     double ex = X(self), hd = 60;
     int lane = fl_lane(FL(self));
     int nl = next_lane(lane, ex, Y(self));
@@ -768,7 +787,7 @@ __device__ double headway_distance(const Env &ev, int self) {
 }
 
 // merge_env_v1.py:64-89 and 439-474
-__device__ double agent_reward(const Env &ev, const mm_config &cfg, int self, double hd) {
+__device__ __noinline__ double agent_reward(const Env &ev, const mm_config &cfg, int self, double hd) {
     uint32_t f = FL(self);
     bool special = cfg.reward_kind != MM_REW_DEFAULT && fl_kind(f) == MM_KIND_CAV;
     bool mrew = cfg.reward_kind == MM_REW_MREW;
@@ -779,11 +798,11 @@ __device__ double agent_reward(const Env &ev, const mm_config &cfg, int self, do
     double merging = 0.0;
     if (fl_lane(f) == L_BC1 && (!special || !mrew || (f & FL_LCSAFE))) {
         double d = X(self) - 420.0;
-        merging = -exp(-(d * d) / (10 * 100.0));
+        merging = -m_exp(-(d * d) / (10 * 100.0));
     }
     double hc = 0.0;
     if (speed > 0) {
-        hc = log(hd / (cfg.headway_time * speed));
+        hc = m_log(hd / (cfg.headway_time * speed));
         if (special) hc = -1 * hc;
     }
     double crashed = (f & FL_CRASHED) ? 1.0 : 0.0;
@@ -792,7 +811,7 @@ __device__ double agent_reward(const Env &ev, const mm_config &cfg, int self, do
 }
 
 // road.py:294-350: visibility groups by query lane, bit l of the mask = lane l is visible
-__device__ __forceinline__ void surrounding(const Env &ev, int self, int qlane, int &front, int &rear) {
+__device__ __noinline__ void surrounding(const Env &ev, int self, int qlane, int &front, int &rear) {
     const uint32_t masks[N_LANES] = {0x03u, 0x0Bu, 0x24u, 0x0Au, 0x30u, 0x34u};
     uint32_t m = masks[qlane];
     double s = X(self), s_front = 0, s_rear = 0;
@@ -825,32 +844,40 @@ __device__ __forceinline__ uint64_t order_by_x_desc(const Env &ev) {
 // ------------------------------------------------------------------------------------------------
 // the policy-step kernel
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load_env(Env &ev, const DevState &st, size_t e, size_t E) {
+__device__ __forceinline__ void load_env(Env &ev, const DevState &st, size_t e) {
+    const uint32_t *fl = st.flags + flags_index(e, 0);
     for (int i = 0; i < ev.n_veh; ++i) {
-        X(i) = st.f64[((size_t)F_X * MAXV + i) * E + e];
-        Y(i) = st.f64[((size_t)F_Y * MAXV + i) * E + e];
-        H(i) = st.f64[((size_t)F_H * MAXV + i) * E + e];
-        V(i) = st.f64[((size_t)F_V * MAXV + i) * E + e];
-        FL(i) = st.flags[(size_t)i * E + e];
+        X(i) = GF(F_X, i);
+        Y(i) = GF(F_Y, i);
+        H(i) = GF(F_H, i);
+        V(i) = GF(F_V, i);
+        FL(i) = fl[i * TILE];
     }
 }
-__device__ __forceinline__ void store_env(const Env &ev, const DevState &st, size_t e, size_t E) {
+__device__ __forceinline__ void store_env(const Env &ev, const DevState &st, size_t e) {
+    uint32_t *fl = st.flags + flags_index(e, 0);
     for (int i = 0; i < ev.n_veh; ++i) {
-        st.f64[((size_t)F_X * MAXV + i) * E + e] = X(i);
-        st.f64[((size_t)F_Y * MAXV + i) * E + e] = Y(i);
-        st.f64[((size_t)F_H * MAXV + i) * E + e] = H(i);
-        st.f64[((size_t)F_V * MAXV + i) * E + e] = V(i);
-        st.flags[(size_t)i * E + e] = FL(i);
+        GF(F_X, i) = X(i);
+        GF(F_Y, i) = Y(i);
+        GF(F_H, i) = H(i);
+        GF(F_V, i) = V(i);
+        fl[i * TILE] = FL(i);
     }
 }
 
 // observation + rewards + info for one env whose hot state is staged in `ev` (abstract.py:469-498,
 // merge_env_v1.py:126-166)
-__device__ void write_outputs(const Env &ev, const StepParams &p, size_t e, int steps, int n_merge, bool with_rewards,
+__device__ __noinline__ void write_outputs(const Env &ev, const StepParams &p, size_t e, int steps, int n_merge, bool with_rewards,
                               double *stat_acc) {
     const DevOut &o = p.out;
     float *obs = o.obs + e * (size_t)(MAXV * NS);
-    for (int i = 0; i < ev.n_cav; ++i) observe_agent(ev, i, obs + i * NS);
+    double vx[MAXV], vy[MAXV];   // Vehicle.velocity (kinematics.py:215-217) of every vehicle, once per env
+    for (int i = 0; i < ev.n_veh; ++i) {
+        double2 sc = m_sincos(H(i));
+        vx[i] = V(i) * sc.y;
+        vy[i] = V(i) * sc.x;
+    }
+    for (int i = 0; i < ev.n_cav; ++i) observe_agent(ev, i, vx, vy, obs + i * NS);
     float2 *z = reinterpret_cast<float2 *>(obs + ev.n_cav * NS);
     for (int q = 0; q < (MAXV - ev.n_cav) * NS / 2; ++q) z[q] = make_float2(0.f, 0.f);
     o.n_agents[e] = ev.n_cav;
@@ -873,8 +900,7 @@ __device__ void write_outputs(const Env &ev, const StepParams &p, size_t e, int 
             if (d < hd) hd = d;
         }
         hd = hd - VLEN;
-        double vx = V(i) * cos(H(i));
-        minhw = fmin(minhw, hd / (vx > 1 ? vx : 1));
+        minhw = fmin(minhw, hd / (vx[i] > 1 ? vx[i] : 1));
         any_crash = any_crash || (FL(i) & FL_CRASHED);
     }
     for (int i = 0; i < ev.n_veh; ++i) tsum += V(i);
@@ -954,13 +980,12 @@ __device__ __forceinline__ void flush_stats(double *stat_acc, double *stats, siz
 }
 
 template <bool DIAG>
-__global__ void __launch_bounds__(BLOCK, 3) step_kernel(const __grid_constant__ StepParams p) {
+__global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid_constant__ StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sm = reinterpret_cast<double *>(smem_raw);
     const int tid = threadIdx.x;
     const int local = blockIdx.x * BLOCK + tid;
     const bool valid = local < p.env_count;
-    const size_t E = (size_t)p.n_envs;
     const size_t e = (size_t)p.env_offset + (valid ? local : 0);
 
     double stat_acc[N_STATS];
@@ -975,15 +1000,14 @@ __global__ void __launch_bounds__(BLOCK, 3) step_kernel(const __grid_constant__ 
         ev.sh = sm + 2 * MAXV * BLOCK + tid;
         ev.sv = sm + 3 * MAXV * BLOCK + tid;
         ev.sf = reinterpret_cast<uint32_t *>(sm + 4 * MAXV * BLOCK) + tid;
-        ev.g = p.st.f64 + e;
-        ev.E = E;
+        ev.g = p.st.f64 + f64_index(e, 0, 0);
         uint32_t ei = p.st.einfo[e];
         ev.n_veh = (ei >> EI_NVEH_SHIFT) & EI_4BIT;
         ev.n_cav = (ei >> EI_NCAV_SHIFT) & EI_4BIT;
         int n_merge = (ei >> EI_NMERGE_SHIFT) & EI_4BIT;
         int steps = (ei >> EI_STEPS_SHIFT) & EI_STEPS_MASK;
         int time = (ei >> EI_TIME_SHIFT) & EI_TIME_MASK;
-        load_env(ev, p.st, e, E);
+        load_env(ev, p.st, e);
 
         // 12 action bytes of this env
         int8_t act[MAXV];
@@ -1035,7 +1059,7 @@ __global__ void __launch_bounds__(BLOCK, 3) step_kernel(const __grid_constant__ 
         }
 
         write_outputs(ev, p, e, steps, n_merge, true, stat_acc);
-        store_env(ev, p.st, e, E);
+        store_env(ev, p.st, e);
         p.st.einfo[e] = (ei & 0xfffu) | ((uint32_t)steps << EI_STEPS_SHIFT) | ((uint32_t)time << EI_TIME_SHIFT);
     }
     flush_stats(stat_acc, p.out.stats, (size_t)p.env_offset + (size_t)(local & ~31));
@@ -1048,7 +1072,6 @@ __global__ void __launch_bounds__(BLOCK) observe_kernel(const __grid_constant__ 
     const int tid = threadIdx.x;
     const int local = blockIdx.x * BLOCK + tid;
     if (local >= p.env_count) return;
-    const size_t E = (size_t)p.n_envs;
     const size_t e = (size_t)p.env_offset + local;
     if (p.obs_mask && !p.obs_mask[e]) return;
     Env ev;
@@ -1057,12 +1080,11 @@ __global__ void __launch_bounds__(BLOCK) observe_kernel(const __grid_constant__ 
     ev.sh = sm + 2 * MAXV * BLOCK + tid;
     ev.sv = sm + 3 * MAXV * BLOCK + tid;
     ev.sf = reinterpret_cast<uint32_t *>(sm + 4 * MAXV * BLOCK) + tid;
-    ev.g = p.st.f64 + e;
-    ev.E = E;
+    ev.g = p.st.f64 + f64_index(e, 0, 0);
     uint32_t ei = p.st.einfo[e];
     ev.n_veh = (ei >> EI_NVEH_SHIFT) & EI_4BIT;
     ev.n_cav = (ei >> EI_NCAV_SHIFT) & EI_4BIT;
-    load_env(ev, p.st, e, E);
+    load_env(ev, p.st, e);
     write_outputs(ev, p, e, 0, 0, false, nullptr);
 }
 
@@ -1108,7 +1130,6 @@ struct Philox {
 __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ ResetParams p) {
     const int local = blockIdx.x * BLOCK + threadIdx.x;
     if (local >= p.env_count) return;
-    const size_t E = (size_t)p.n_envs;
     const size_t e = (size_t)p.env_offset + local;
     if (p.use_done) { if (!p.out.done[e]) return; }
     else if (p.mask && !p.mask[e]) return;
@@ -1147,8 +1168,8 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ Re
     n_hdv = n_s_h + n_m_h;
 
     int mi = 0, ri = 0;
+    double *g = p.st.f64 + f64_index(e, 0, 0);
     for (int i = 0; i < MAXV; ++i) {
-        double *g = p.st.f64 + e;
         uint32_t f = 0;
         double x = 0, y = 0, speed = 0, tspeed = 0, timer = 0;
         if (i < n_veh) {
@@ -1170,14 +1191,14 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ Re
             f = (uint32_t)(cav ? MM_KIND_CAV : MM_KIND_HDV) | ((uint32_t)lane << FL_LANE_SHIFT) |
                 ((uint32_t)lane << FL_TLANE_SHIFT) | ((uint32_t)sidx << FL_SIDX_SHIFT) | ((uint32_t)A_NONE << FL_HL_SHIFT);
         }
-        for (int fld = 0; fld < F_COUNT; ++fld) g[((size_t)fld * MAXV + i) * E] = 0.0;
-        g[((size_t)F_X * MAXV + i) * E] = x;
-        g[((size_t)F_Y * MAXV + i) * E] = y;
-        g[((size_t)F_V * MAXV + i) * E] = speed;
-        g[((size_t)F_TSPEED * MAXV + i) * E] = tspeed;
-        g[((size_t)F_TIMER * MAXV + i) * E] = timer;
-        g[((size_t)F_MINHW * MAXV + i) * E] = 180.0 / 40.0;  // safe_controller.py:56
-        p.st.flags[(size_t)i * E + e] = f;
+        for (int fld = 0; fld < F_COUNT; ++fld) g[(fld * MAXV + i) * TILE] = 0.0;
+        g[(F_X * MAXV + i) * TILE] = x;
+        g[(F_Y * MAXV + i) * TILE] = y;
+        g[(F_V * MAXV + i) * TILE] = speed;
+        g[(F_TSPEED * MAXV + i) * TILE] = tspeed;
+        g[(F_TIMER * MAXV + i) * TILE] = timer;
+        g[(F_MINHW * MAXV + i) * TILE] = 180.0 / 40.0;  // safe_controller.py:56
+        p.st.flags[flags_index(e, i)] = f;
     }
     p.st.einfo[e] = (uint32_t)n_veh | ((uint32_t)n_cav << EI_NCAV_SHIFT) | ((uint32_t)n_m_c << EI_NMERGE_SHIFT);
 }
@@ -1200,7 +1221,7 @@ __global__ void pack_state_kernel(DevState st, int n_envs, const double *f64_em,
     int i = (int)(idx % MAXV);
     for (int k = 0; k < 16; ++k) {
         int fld = c_host_f64_to_field[k];
-        if (fld >= 0) st.f64[((size_t)fld * MAXV + i) * E + e] = f64_em[(size_t)k * E * MAXV + idx];
+        if (fld >= 0) st.f64[f64_index(e, fld, i)] = f64_em[(size_t)k * E * MAXV + idx];
     }
     const size_t P = E * MAXV;
     int hl = i32_em[5 * P + idx];
@@ -1212,7 +1233,7 @@ __global__ void pack_state_kernel(DevState st, int n_envs, const double *f64_em,
                  ((uint32_t)min(max(hist, 0), 2) << FL_HIST_SHIFT) | (i32_em[7 * P + idx] ? FL_FG : 0u) |
                  (i32_em[8 * P + idx] ? FL_COLLAB : 0u) | (i32_em[9 * P + idx] ? FL_LCSAFE : 0u) |
                  (i32_em[10 * P + idx] ? FL_CADJ : 0u);
-    st.flags[(size_t)i * E + e] = f;
+    st.flags[flags_index(e, i)] = f;
     if (i == 0) {
         st.einfo[e] = ((uint32_t)env_em[e] & 15u) | (((uint32_t)env_em[E + e] & 15u) << EI_NCAV_SHIFT) |
                       (((uint32_t)env_em[2 * E + e] & 15u) << EI_NMERGE_SHIFT) |
@@ -1230,10 +1251,10 @@ __global__ void unpack_state_kernel(DevState st, int n_envs, double *f64_em, int
     for (int k = 0; k < 16; ++k) {
         int fld = c_host_f64_to_field[k];
         if (fld < 0) fld = F_X;  // rec1_x == x (the record is taken right after the move)
-        f64_em[(size_t)k * E * MAXV + idx] = st.f64[((size_t)fld * MAXV + i) * E + e];
+        f64_em[(size_t)k * E * MAXV + idx] = st.f64[f64_index(e, fld, i)];
     }
     const size_t P = E * MAXV;
-    uint32_t f = st.flags[(size_t)i * E + e];
+    uint32_t f = st.flags[flags_index(e, i)];
     int hl = fl_hl(f);
     i32_em[0 * P + idx] = fl_kind(f);
     i32_em[1 * P + idx] = fl_lane(f);

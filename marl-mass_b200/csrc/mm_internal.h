@@ -1,10 +1,14 @@
 // mm_internal.h — layout shared by the kernels (merge_step.cu) and the host side of the C ABI (capi.cu).
 //
-// HBM layout (structure of arrays, env index fastest so that thread-per-env accesses coalesce):
-//   f64   [F_COUNT][MM_MAXV][E]   vehicle state, one plane per field and slot
-//   flags [MM_MAXV][E] u32        packed discrete vehicle state (bit layout below)
-//   einfo [E] u32                 packed env scalars: n_veh, n_cav, n_merge, steps, time
-//   episode [E] u32               episode counter (RNG stream id for device-side spawn)
+// HBM layout: array of tiles of structure-of-arrays.  A tile is TILE = 128 consecutive envs (= one CTA);
+// inside a tile every (field, slot) is a contiguous run of 128 values, so a warp's access is one or two
+// fully used 128-byte lines, and the whole state of a CTA is one contiguous ~190 KB span (one TLB entry —
+// a plain [field][slot][E] layout put the 180 planes of an env 8 MB apart at E = 2^20 and thrashed the
+// 128-entry TLB: 80 ms/step instead of 22, profiles/r1_v1_*).
+//   f64   [n_tiles][F_COUNT][MM_MAXV][TILE]   vehicle state
+//   flags [n_tiles][MM_MAXV][TILE] u32        packed discrete vehicle state (bit layout below)
+//   einfo [E_pad] u32                         packed env scalars: n_veh, n_cav, n_merge, steps, time
+//   episode [E_pad] u32                       episode counter (RNG stream id for device-side spawn)
 // Outputs are env-major (what the caller consumes): obs [E][MM_MAXV][MM_NS] f32, etc.
 #pragma once
 #include <stdint.h>
@@ -15,6 +19,7 @@ namespace mm {
 
 constexpr int MAXV = MM_MAXV;
 constexpr int NS = MM_NS;
+constexpr int TILE = 128;   // envs per tile == threads per CTA of the step kernel
 
 enum F64Field {
     F_X = 0, F_Y, F_H, F_V,          // position, heading, speed            (staged in shared memory)
@@ -46,10 +51,10 @@ constexpr uint32_t EI_STEPS_SHIFT = 12, EI_STEPS_MASK = 255u;
 constexpr uint32_t EI_TIME_SHIFT = 20, EI_TIME_MASK = 4095u;
 
 struct DevState {
-    double *f64;        // [F_COUNT][MAXV][E]
-    uint32_t *flags;    // [MAXV][E]
-    uint32_t *einfo;    // [E]
-    uint32_t *episode;  // [E]
+    double *f64;        // [n_tiles][F_COUNT][MAXV][TILE]
+    uint32_t *flags;    // [n_tiles][MAXV][TILE]
+    uint32_t *einfo;    // [E_pad]
+    uint32_t *episode;  // [E_pad]
 };
 
 struct DevOut {
@@ -96,5 +101,13 @@ void launch_unpack_state(const DevState &st, int n_envs, double *f64_em, int32_t
                          void *stream);
 void launch_qp(const double *a, const double *c_lead, const double *c_adj, const uint8_t *has_adj,
                const double *lo, const double *hi, int64_t n, double *u, uint8_t *active, void *stream);
+
+// element (field f, slot i) of env e
+__host__ __device__ inline size_t f64_index(size_t e, int f, int i) {
+    return (((e / TILE) * F_COUNT + (size_t)f) * MAXV + (size_t)i) * TILE + (e % TILE);
+}
+__host__ __device__ inline size_t flags_index(size_t e, int i) {
+    return ((e / TILE) * MAXV + (size_t)i) * TILE + (e % TILE);
+}
 
 }  // namespace mm
