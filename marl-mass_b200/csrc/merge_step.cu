@@ -140,16 +140,15 @@ __device__ __forceinline__ bool on_lane(int lane, double px, double py, double m
     double r = lane_r(lane, s, py);
     return fabs(r) <= LWIDTH / 2 + margin && -VLEN <= s && s < c_lane_len[lane] + VLEN;
 }
-// L1 distance to a straight lane (lane.py:97-100); only ever needed for bc0 / bc1
-__device__ __forceinline__ double straight_lane_distance(int lane, double px, double py) {
-    double s = lane_s(lane, px);
-    double r = py - c_lane_sy[lane];
-    return fabs(r) + fmax(s - c_lane_len[lane], 0.0) + fmax(0.0 - s, 0.0);
-}
-// road.py:67-109 with route=None (every node has a single successor)
-__device__ __noinline__ int next_lane(int lane, double px, double py) {
-    if (lane == L_AB0 || lane == L_KB0)
-        return straight_lane_distance(L_BC0, px, py) <= straight_lane_distance(L_BC1, px, py) ? L_BC0 : L_BC1;
+// road.py:67-109 with route=None (every node has a single successor).  From ab0 / kb0 the next road has two
+// lanes and the closer one (lane.py:97-100 distance, first minimum) is taken; bc0 and bc1 share start.x and
+// length, so the two distances differ only in |r|.
+__device__ __forceinline__ int next_lane(int lane, double px, double py) {
+    if (lane == L_AB0 || lane == L_KB0) {
+        double s = px - 320.0;
+        double over = fmax(s - 100.0, 0.0), under = fmax(0.0 - s, 0.0);
+        return fabs(py - 0.0) + over + under <= fabs(py - 4.0) + over + under ? L_BC0 : L_BC1;
+    }
     if (lane == L_JK0) return L_KB0;
     return L_CD0;
 }
@@ -417,6 +416,7 @@ __device__ __forceinline__ int close_vehicles(const Env &ev, int self, int (&ids
         double key = fabs(lane_s(el, ox) - es);
         int id = j;
         ++n;
+        if (!(key < keys[K - 1])) continue;  // not among the K nearest so far (ties go to the earlier vehicle)
         // stable insertion: a later element goes after equal keys; once placed, everything behind shifts
         bool placed = false;
 #pragma unroll
@@ -445,7 +445,9 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
     double v_min = espeed + ACC_LO * dt;
     if (mass) v_min = fmax(0.0, v_min);
     double v_max = espeed + ACC_HI * dt;
-    double evx_raw = espeed * m_cos(eh);
+    // to_dict()["vx"] = speed * cos(heading): for a vehicle that has not crashed this is bit-for-bit the value its
+    // last log_step recorded (same operands), so the record is reused instead of a cosine
+    double evx_raw = (f & FL_CRASHED) ? espeed * m_cos(eh) : GF(F_REC1VX, self);
     double evx = evx_raw > 1 ? evx_raw : 1;
     double es = lane_s(elane, ex);
 
@@ -479,7 +481,7 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
             if (!has_oar && d < 0) {  // rear-adjacent: its current state
                 has_oar = true; id_oar = o;
                 x_oar = ox;
-                vx_oar = V(o) * m_cos(oh);
+                vx_oar = (fo & FL_CRASHED) ? V(o) * m_cos(oh) : GF(F_REC1VX, o);
             } else if (!has_oa && d >= 0) {  // front-adjacent: its record before its last step
                 has_oa = true; id_oa = o;
                 x_oa = GF(F_REC2X, o);
@@ -580,12 +582,18 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
     if (!mass) {
         veto = !allowed;
     } else {
-        double cx, cy;
-        get_corner(ex, ey, eh, true, cx, cy);
-        bool can_abort = on_lane(elane, cx, cy, 0.0);
-        get_corner(ex, ey, eh, false, cx, cy);
-        can_abort = can_abort && on_lane(elane, cx, cy, 0.0);
-        veto = can_abort && !allowed;
+        // can_abort_lc (decentral_layer.py:728-736) only matters when the lane change is not allowed
+        veto = false;
+        if (!allowed) {
+            double cx, cy;
+            get_corner(ex, ey, eh, true, cx, cy);
+            bool can_abort = on_lane(elane, cx, cy, 0.0);
+            if (can_abort) {
+                get_corner(ex, ey, eh, false, cx, cy);
+                can_abort = on_lane(elane, cx, cy, 0.0);
+            }
+            veto = can_abort;
+        }
         int hl = fl_hl(f);
         if (!veto && (hl == A_LANE_RIGHT || hl == A_LANE_LEFT) && espeed < 1.6667) v_safe = v_ll;
         f = cond_a >= -1e-6 ? (f | FL_CADJ) : (f & ~FL_CADJ);
@@ -709,6 +717,27 @@ __device__ __noinline__ bool rects_intersect(double ax, double ay, double ah, do
            has_corner_inside(bx, by, 0.9 * blen / 2, 0.9 * bwid / 2, bh, ax, ay, 0.9 * VLEN, 0.9 * VWID, ah);
 }
 
+// Conservative pre-test for has_corner_inside(rect1 -> rect2): with u = R(a2)(c1 + R(a1)q - c2) and q ranging over
+// rect1's sample points (|qx| <= lx1, |qy| <= wy1), |sin a| <= |a| and |cos a| >= 1 - a^2/2 give lower bounds on
+// |ux| and |uy|; if either bound clears the half size of rect2 by more than 1e-6 m no sample point can pass the
+// inside test (the reference's own rounding error there is ~1e-15), so the exact 9-point test is skipped.
+// Side-by-side vehicles on bc0/bc1 and queues behind the obstacle are the common case this removes.
+__device__ __forceinline__ bool may_have_corner_inside(double adx, double ady, double lx1, double wy1, double a1,
+                                                       double l2, double w2, double a2) {
+    double aa1 = fabs(a1), aa2 = fabs(a2);
+    double c2min = fmax(0.0, 1.0 - 0.5 * aa2 * aa2), s2max = fmin(1.0, aa2), s1max = fmin(1.0, aa1);
+    double reach = lx1 + wy1;
+    double uy_min = c2min * fmax(0.0, ady - (s1max * lx1 + wy1)) - s2max * (adx + reach);
+    if (uy_min > 0.5 * w2 + 1e-6) return false;
+    double ux_min = c2min * fmax(0.0, adx - (lx1 + s1max * wy1)) - s2max * (ady + reach);
+    if (ux_min > 0.5 * l2 + 1e-6) return false;
+    return true;
+}
+__device__ __forceinline__ bool may_intersect(double adx, double ady, double ah, double bh, double blen, double bwid) {
+    return may_have_corner_inside(adx, ady, 0.9 * VLEN / 2, 0.9 * VWID / 2, ah, 0.9 * blen, 0.9 * bwid, bh) ||
+           may_have_corner_inside(adx, ady, 0.9 * blen / 2, 0.9 * bwid / 2, bh, 0.9 * VLEN, 0.9 * VWID, ah);
+}
+
 __device__ __noinline__ void collision_pass(Env &ev) {
     for (int i = 0; i < ev.n_veh; ++i) {
         double ax = X(i), ay = Y(i);
@@ -717,6 +746,7 @@ __device__ __noinline__ void collision_pass(Env &ev) {
             if (FL(i) & FL_CRASHED) break;
             double dx = X(j) - ax, dy = Y(j) - ay;
             if (dx * dx + dy * dy > VLEN_SQ_GT) continue;  // np.linalg.norm(...) > LENGTH
+            if (!may_intersect(fabs(dx), fabs(dy), H(i), H(j), VLEN, VWID)) continue;
             if (rects_intersect(ax, ay, H(i), X(j), Y(j), H(j), VLEN, VWID)) {
                 double va = V(i), vb = V(j);
                 double m = fabs(va) <= fabs(vb) ? va : vb;
@@ -726,7 +756,8 @@ __device__ __noinline__ void collision_pass(Env &ev) {
         }
         if (!(FL(i) & FL_CRASHED)) {
             double dx = OBST_X - ax, dy = OBST_Y - ay;
-            if (!(dx * dx + dy * dy > VLEN_SQ_GT) && rects_intersect(ax, ay, H(i), OBST_X, OBST_Y, 0.0, 2.0, 2.0)) {
+            if (!(dx * dx + dy * dy > VLEN_SQ_GT) && may_intersect(fabs(dx), fabs(dy), H(i), 0.0, 2.0, 2.0) &&
+                rects_intersect(ax, ay, H(i), OBST_X, OBST_Y, 0.0, 2.0, 2.0)) {
                 double va = V(i);
                 V(i) = fabs(va) <= 0 ? va : 0.0;
                 FL(i) |= FL_CRASHED;
@@ -810,18 +841,29 @@ __device__ __noinline__ double agent_reward(const Env &ev, const mm_config &cfg,
            cfg.merging_lane_cost * merging + cfg.headway_cost * (hc < 0 ? hc : 0.0);
 }
 
-// road.py:294-350: visibility groups by query lane, bit l of the mask = lane l is visible
-__device__ __noinline__ void surrounding(const Env &ev, int self, int qlane, int &front, int &rear) {
-    const uint32_t masks[N_LANES] = {0x03u, 0x0Bu, 0x24u, 0x0Au, 0x30u, 0x34u};
-    uint32_t m = masks[qlane];
-    double s = X(self), s_front = 0, s_rear = 0;
-    front = -1;
-    rear = -1;
+// road.py:294-350: nearest vehicle ahead / behind by world x among the lanes visible from a query lane
+// (bit l of a mask = lane l is visible).  Two queries share one pass over the vehicles.
+__device__ __forceinline__ uint32_t visible_lanes(int qlane) {
+    // ab0:{ab0,bc0} bc0:{ab0,bc0,cd0} bc1:{kb0,bc1} cd0:{bc0,cd0} jk0:{jk0,kb0} kb0:{jk0,kb0,bc1}
+    return (0x34300A240B03ull >> (8 * qlane)) & 0xffu;
+}
+__device__ __noinline__ void surrounding2(const Env &ev, int self, uint32_t m1, uint32_t m2, int &f1, int &r1, int &f2,
+                                          int &r2) {
+    double s = X(self), sf1 = 0, sr1 = 0, sf2 = 0, sr2 = 0;
+    f1 = r1 = f2 = r2 = -1;
     for (int j = 0; j < ev.n_veh; ++j) {
-        if (j == self || !((m >> fl_lane(FL(j))) & 1u)) continue;
+        if (j == self) continue;
+        uint32_t bit = 1u << fl_lane(FL(j));
         double s_v = X(j);
-        if (s <= s_v && (front < 0 || s_v <= s_front)) { s_front = s_v; front = j; }
-        if (s_v < s && (rear < 0 || s_v > s_rear)) { s_rear = s_v; rear = j; }
+        bool ahead = s <= s_v, behind = s_v < s;
+        if (m1 & bit) {
+            if (ahead && (f1 < 0 || s_v <= sf1)) { sf1 = s_v; f1 = j; }
+            if (behind && (r1 < 0 || s_v > sr1)) { sr1 = s_v; r1 = j; }
+        }
+        if (m2 & bit) {
+            if (ahead && (f2 < 0 || s_v <= sf2)) { sf2 = s_v; f2 = j; }
+            if (behind && (r2 < 0 || s_v > sr2)) { sr2 = s_v; r2 = j; }
+        }
     }
 }
 
@@ -910,18 +952,17 @@ __device__ __noinline__ void write_outputs(const Env &ev, const StepParams &p, s
         float lr = 0.f, rr = 0.f;
         uint8_t ad = 0;
         if (i < ev.n_cav) {
-            // regional reward (merge_env_v1.py:91-124)
+            // regional reward (merge_env_v1.py:91-124): own-lane group plus, where one exists, the group across
             int lane = fl_lane(FL(i));
-            int fl_ = -1, rl = -1, fr = -1, rrr = -1;
-            if (lane == L_AB0 || lane == L_BC0 || lane == L_CD0) {
-                surrounding(ev, i, lane, fl_, rl);
-                if (lane == L_BC0) surrounding(ev, i, L_BC1, fr, rrr);
-                else if (lane == L_AB0 && X(i) > 220) surrounding(ev, i, L_KB0, fr, rrr);
-            } else {
-                surrounding(ev, i, lane, fr, rrr);
-                if (lane == L_BC1) surrounding(ev, i, L_BC0, fl_, rl);
-                else if (lane == L_KB0) surrounding(ev, i, L_AB0, fl_, rl);
-            }
+            bool on_main = lane == L_AB0 || lane == L_BC0 || lane == L_CD0;
+            int across = -1;
+            if (lane == L_BC0) across = L_BC1;
+            else if (lane == L_AB0 && X(i) > 220) across = L_KB0;
+            else if (lane == L_BC1) across = L_BC0;
+            else if (lane == L_KB0) across = L_AB0;
+            int fo, ro, fa, ra;
+            surrounding2(ev, i, visible_lanes(lane), across >= 0 ? visible_lanes(across) : 0u, fo, ro, fa, ra);
+            int fl_ = on_main ? fo : fa, rl = on_main ? ro : ra, fr = on_main ? fa : fo, rrr = on_main ? ra : ro;
             int cand[5] = {fl_, fr, i, rl, rrr};
             double sum = 0;
             int cnt = 0;
@@ -979,6 +1020,14 @@ __device__ __forceinline__ void flush_stats(double *stat_acc, double *stats, siz
     }
 }
 
+// MM_PHASE_SYNC: CTA-wide barriers that keep the four warps of a CTA in the same phase of the step, so that they
+// share instruction-cache lines (the kernel is ~130 KB of SASS; instruction fetch was a top stall without them).
+//   0: none   1: one barrier per sub-step   2: additionally one per vehicle rank inside the act / step passes
+#ifndef MM_PHASE_SYNC
+#define MM_PHASE_SYNC 2
+#endif
+#define PHASE_BARRIER(level) do { if (MM_PHASE_SYNC >= (level)) __syncthreads(); } while (0)
+
 template <bool DIAG>
 __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid_constant__ StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -993,33 +1042,27 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
     for (int k = 0; k < N_STATS; ++k) stat_acc[k] = 0.0;
     stat_acc[ST_MINHW] = CUDART_INF;
 
+    Env ev;
+    ev.sx = sm + tid;
+    ev.sy = sm + MAXV * BLOCK + tid;
+    ev.sh = sm + 2 * MAXV * BLOCK + tid;
+    ev.sv = sm + 3 * MAXV * BLOCK + tid;
+    ev.sf = reinterpret_cast<uint32_t *>(sm + 4 * MAXV * BLOCK) + tid;
+    ev.g = p.st.f64 + f64_index(e, 0, 0);
+    ev.n_veh = 0;
+    ev.n_cav = 0;
+    uint32_t ei = 0, act_lo = 0, act_mid = 0, act_hi = 0;
+    int n_merge = 0, steps = 0, time = 0;
     if (valid) {
-        Env ev;
-        ev.sx = sm + tid;
-        ev.sy = sm + MAXV * BLOCK + tid;
-        ev.sh = sm + 2 * MAXV * BLOCK + tid;
-        ev.sv = sm + 3 * MAXV * BLOCK + tid;
-        ev.sf = reinterpret_cast<uint32_t *>(sm + 4 * MAXV * BLOCK) + tid;
-        ev.g = p.st.f64 + f64_index(e, 0, 0);
-        uint32_t ei = p.st.einfo[e];
+        ei = p.st.einfo[e];
         ev.n_veh = (ei >> EI_NVEH_SHIFT) & EI_4BIT;
         ev.n_cav = (ei >> EI_NCAV_SHIFT) & EI_4BIT;
-        int n_merge = (ei >> EI_NMERGE_SHIFT) & EI_4BIT;
-        int steps = (ei >> EI_STEPS_SHIFT) & EI_STEPS_MASK;
-        int time = (ei >> EI_TIME_SHIFT) & EI_TIME_MASK;
+        n_merge = (ei >> EI_NMERGE_SHIFT) & EI_4BIT;
+        steps = (ei >> EI_STEPS_SHIFT) & EI_STEPS_MASK;
+        time = (ei >> EI_TIME_SHIFT) & EI_TIME_MASK;
         load_env(ev, p.st, e);
-
-        // 12 action bytes of this env
-        int8_t act[MAXV];
-        {
-            const uint32_t *a32 = reinterpret_cast<const uint32_t *>(p.actions + e * MAXV);
-#pragma unroll
-            for (int w = 0; w < MAXV / 4; ++w) {
-                uint32_t v = a32[w];
-#pragma unroll
-                for (int b = 0; b < 4; ++b) act[w * 4 + b] = (int8_t)((v >> (8 * b)) & 0xff);
-            }
-        }
+        const uint32_t *a32 = reinterpret_cast<const uint32_t *>(p.actions + e * MAXV);  // 12 action bytes
+        act_lo = a32[0]; act_mid = a32[1]; act_hi = a32[2];
         if (DIAG) {
             size_t plane = (size_t)p.n_envs * 3 * MAXV;
             for (int k = 0; k < 3 * MAXV; ++k) {
@@ -1031,33 +1074,51 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
                 for (int q = 0; q < 5; ++q) p.out.sh_f[q * plane + idx] = 0.0;
             }
         }
-
         steps = min(steps + 1, (int)EI_STEPS_MASK);  // abstract.py:457
+    }
+    bool running = valid;
+    const int n_rank = MM_PHASE_SYNC >= 2 ? MAXV - 1 : 0;  // uniform trip count when ranks are barrier-separated
 #pragma unroll 1
-        for (int sub = 0; sub < p.cfg.substeps; ++sub) {  // abstract.py:514-531
+    for (int sub = 0; sub < p.cfg.substeps; ++sub) {  // abstract.py:514-531
+        PHASE_BARRIER(1);
+        uint64_t ord = 0;
+        if (running) {
             if (time % p.cfg.substeps == 0) {
                 for (int i = 0; i < ev.n_cav; ++i) {
-                    int a = act[i];
+                    uint32_t w = i < 4 ? act_lo : (i < 8 ? act_mid : act_hi);
+                    int a = (int)(int8_t)((w >> (8 * (i & 3))) & 0xffu);
                     cav_act(ev, i, (a >= 0 && a <= 4) ? a : A_IDLE);
                 }
             }
-            uint64_t ord = order_by_x_desc(ev);
+            ord = order_by_x_desc(ev);
+        }
+        const int n_live = running ? ev.n_veh : 0;
 #pragma unroll 1
-            for (int q = 0; q < ev.n_veh; ++q) {  // road.act()
+        for (int q = 0; q < (MM_PHASE_SYNC >= 2 ? n_rank : n_live); ++q) {  // road.act()
+            PHASE_BARRIER(2);
+            if (q < n_live) {
                 int i = (int)((ord >> (4 * q)) & 15u);
                 if (fl_kind(FL(i)) == MM_KIND_CAV) cav_act(ev, i, A_NONE);
                 else hdv_act(ev, i);
             }
+        }
 #pragma unroll 1
-            for (int q = 0; q < ev.n_veh; ++q) {  // road.step(dt): same order, positions did not move
+        for (int q = 0; q < (MM_PHASE_SYNC >= 2 ? n_rank : n_live); ++q) {  // road.step(dt): same order
+            PHASE_BARRIER(2);
+            if (q < n_live) {
                 int i = (int)((ord >> (4 * q)) & 15u);
                 vehicle_step<DIAG>(ev, p, i, sub < 3 ? sub : 2, e, stat_acc);
             }
+        }
+        PHASE_BARRIER(2);
+        if (running) {
             collision_pass(ev);
             time = min(time + 1, (int)EI_TIME_MASK);
-            if (is_terminal(ev, steps, p.cfg.duration_steps)) break;
+            if (is_terminal(ev, steps, p.cfg.duration_steps)) running = false;  // abstract.py:530
         }
-
+    }
+    PHASE_BARRIER(1);
+    if (valid) {
         write_outputs(ev, p, e, steps, n_merge, true, stat_acc);
         store_env(ev, p.st, e);
         p.st.einfo[e] = (ei & 0xfffu) | ((uint32_t)steps << EI_STEPS_SHIFT) | ((uint32_t)time << EI_TIME_SHIFT);
