@@ -328,7 +328,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": E * mm.MAXV,
                 "d2h_bytes_per_step": E * (mm.MAXV * mm.NS * 4 + 4 + 1 + mm.MAXV * 4 + 4), "steps": K2,
-                "api": "mm_step_host (pinned host buffers, %d-stream chunked copy/compute overlap)" % 8},
+                "api": "mm_step_host (pinned host buffers, 64Ki-env chunks round-robin on 4 streams: copies overlap compute)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "kernel": "step_kernel<false>", "kernel_ms": kms,

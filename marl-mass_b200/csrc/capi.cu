@@ -216,16 +216,22 @@ int mm_step_host(mm_env *env, const int8_t *actions, int auto_reset, float *obs,
     if (!actions) return fail(MM_ERR_ARG, "actions is null");
     CUDA_OK(cudaSetDevice(env->device));
     const int E = env->n_envs;
-    // chunk = multiple of 128 envs (block size; also keeps the per-warp statistics rows disjoint)
-    int n_chunks = (E + 16383) / 16384;
-    if (n_chunks > env->n_streams) n_chunks = env->n_streams;
+    // Chunks of ~64 Ki envs (a multiple of the 128-env tile, which also keeps the per-warp statistics rows
+    // disjoint) issued round-robin on 4 streams: chunk k's device-to-host copies run while chunks k+1.. compute.
+    static const int chunk_target = [] {
+        const char *s = getenv("MM_HOST_CHUNK");
+        int v = s ? atoi(s) : 0;
+        return v > 0 ? v : 65536;
+    }();
+    const int n_str = 4;
+    int n_chunks = (E + chunk_target - 1) / chunk_target;
     if (n_chunks < 1) n_chunks = 1;
-    int chunk = ((E + n_chunks - 1) / n_chunks + 127) / 128 * 128;
+    int chunk = ((E + n_chunks - 1) / n_chunks + TILE - 1) / TILE * TILE;
     for (int c = 0; c < n_chunks; ++c) {
         int off = c * chunk;
         if (off >= E) break;
         int count = E - off < chunk ? E - off : chunk;
-        cudaStream_t s = env->streams[c];
+        cudaStream_t s = env->streams[c % n_str];
         CUDA_OK(cudaMemcpyAsync(env->actions + (size_t)off * MAXV, actions + (size_t)off * MAXV, (size_t)count * MAXV,
                                 cudaMemcpyHostToDevice, s));
         enqueue_step(env, env->actions, auto_reset, off, count, s);
@@ -242,7 +248,7 @@ int mm_step_host(mm_env *env, const int8_t *actions, int auto_reset, float *obs,
         if (n_agents)
             CUDA_OK(cudaMemcpyAsync(n_agents + off, env->out.n_agents + off, (size_t)count * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     }
-    for (int c = 0; c < n_chunks; ++c) CUDA_OK(cudaStreamSynchronize(env->streams[c]));
+    for (int c = 0; c < n_str; ++c) CUDA_OK(cudaStreamSynchronize(env->streams[c]));
     CUDA_OK(cudaGetLastError());
     return 0;
 }

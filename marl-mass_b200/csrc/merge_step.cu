@@ -207,7 +207,7 @@ __device__ __forceinline__ int follow_road(int tlane, double px, double py) {
 }
 
 // MDPLCVehicle.act -> MDPVehicle.act -> ControlledVehicle.act (safe_controller.py:63-66, controller.py:293-311, 90-134)
-__device__ __noinline__ void cav_act(Env &ev, int i, int action) {
+__device__ __noinline__ void cav_act(Env &ev, int i, int action, double &steer, double &acc) {
     uint32_t f = FL(i);
     double px = X(i), py = Y(i), speed = V(i);
     if (action != A_NONE) f = fl_set(f, FL_HL_SHIFT, FL_3BIT, (uint32_t)action);
@@ -225,8 +225,8 @@ __device__ __noinline__ void cav_act(Env &ev, int i, int action) {
     }
     f = fl_set(f, FL_TLANE_SHIFT, FL_3BIT, (uint32_t)tl);
     FL(i) = f;
-    GF(F_ACT_STEER, i) = steering_control(px, py, H(i), speed, tl);
-    GF(F_ACT_ACC, i) = KP_A * (GF(F_TSPEED, i) - speed);
+    steer = steering_control(px, py, H(i), speed, tl);
+    acc = KP_A * (GF(F_TSPEED, i) - speed);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -259,13 +259,10 @@ __device__ __noinline__ void neighbour_vehicles(const Env &ev, int self, int lan
 __device__ __noinline__ double desired_gap(const Env &ev, int ego, int front) {
     double fvx = 0, fvy = 0;
     if (front != OBST) {
-        double fs, fc;
-        { double2 sc_ = m_sincos(H(front)); fs = sc_.x; fc = sc_.y; }
-        fvx = V(front) * fc;
-        fvy = V(front) * fs;
+        fvx = V(front) * GF(F_COSH, front);
+        fvy = V(front) * GF(F_SINH, front);
     }
-    double es, ec, speed = V(ego);
-    { double2 sc_ = m_sincos(H(ego)); es = sc_.x; ec = sc_.y; }
+    double ec = GF(F_COSH, ego), es = GF(F_SINH, ego), speed = V(ego);
     double dv = (speed * ec - fvx) * ec + (speed * es - fvy) * es;
     return 10.0 + speed * 1.5 + speed * dv / (2 * sqrt(15.0));
 }
@@ -383,13 +380,15 @@ __device__ __forceinline__ int is_adj_lane(int l1, int nl /* next_lane(l1, posit
     return 0;
 }
 
-// controller.py:257-267; left: dir == "L"
-__device__ __forceinline__ void get_corner(double px, double py, double heading, bool left, double &cx, double &cy) {
-    const double corner_len = sqrt((VWID / 2) * (VWID / 2) + (VLEN / 2) * (VLEN / 2)) + 0.0075;
-    const double corner_alpha = m_atan(VWID / VLEN);
-    double ang = left ? corner_alpha + heading : -corner_alpha + heading;
-    cx = px + (corner_len * m_cos(corner_alpha + heading));
-    cy = py - (corner_len * m_sin(ang)) + 0.01;
+// controller.py:257-267; left: dir == "L".  cos/sin(+-alpha + heading) by angle addition from the cached cos/sin of
+// the heading (alpha = atan(WIDTH / LENGTH) = atan(0.4): cos = 5/sqrt(29), sin = 2/sqrt(29)).
+__device__ __forceinline__ void get_corner(double px, double py, double ch, double sh, bool left, double &cx, double &cy) {
+    const double corner_len = 2.700082417423684;   // sqrt(1^2 + 2.5^2) + 0.0075
+    const double ca = 0.9284766908852593, sa = 0.3713906763541037;
+    double sin_pa = sa * ch + ca * sh;             // sin(alpha + heading)
+    double sin_ma = ca * sh - sa * ch;             // sin(-alpha + heading)
+    cx = px + (corner_len * (ca * ch - sa * sh));
+    cy = py - (corner_len * (left ? sin_pa : sin_ma)) + 0.01;
 }
 
 struct ShieldRec {
@@ -447,7 +446,7 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
     double v_max = espeed + ACC_HI * dt;
     // to_dict()["vx"] = speed * cos(heading): for a vehicle that has not crashed this is bit-for-bit the value its
     // last log_step recorded (same operands), so the record is reused instead of a cosine
-    double evx_raw = (f & FL_CRASHED) ? espeed * m_cos(eh) : GF(F_REC1VX, self);
+    double evx_raw = (f & FL_CRASHED) ? espeed * GF(F_COSH, self) : GF(F_REC1VX, self);
     double evx = evx_raw > 1 ? evx_raw : 1;
     double es = lane_s(elane, ex);
 
@@ -481,7 +480,7 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
             if (!has_oar && d < 0) {  // rear-adjacent: its current state
                 has_oar = true; id_oar = o;
                 x_oar = ox;
-                vx_oar = (fo & FL_CRASHED) ? V(o) * m_cos(oh) : GF(F_REC1VX, o);
+                vx_oar = (fo & FL_CRASHED) ? V(o) * GF(F_COSH, o) : GF(F_REC1VX, o);
             } else if (!has_oa && d >= 0) {  // front-adjacent: its record before its last step
                 has_oa = true; id_oa = o;
                 x_oa = GF(F_REC2X, o);
@@ -491,7 +490,7 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
                     g_oa = o_cav ? GF(F_GVX, o) : 1.0;
                     bool left = (v_a == -1 || a_v == 1);
                     double cx, cy;
-                    get_corner(ox, oy, oh, left, cx, cy);
+                    get_corner(ox, oy, GF(F_COSH, o), GF(F_SINH, o), left, cx, cy);
                     constrain_adj = !on_lane(olane, cx, cy, 0.0);
                 }
             }
@@ -586,10 +585,11 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
         veto = false;
         if (!allowed) {
             double cx, cy;
-            get_corner(ex, ey, eh, true, cx, cy);
+            const double ech = GF(F_COSH, self), esh = GF(F_SINH, self);
+            get_corner(ex, ey, ech, esh, true, cx, cy);
             bool can_abort = on_lane(elane, cx, cy, 0.0);
             if (can_abort) {
-                get_corner(ex, ey, eh, false, cx, cy);
+                get_corner(ex, ey, ech, esh, false, cx, cy);
                 can_abort = on_lane(elane, cx, cy, 0.0);
             }
             veto = can_abort;
@@ -616,22 +616,28 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
 // ------------------------------------------------------------------------------------------------
 // integration (kinematics.py:122-152, safe_controller.py:100-185, behavior.py:102-109,504-522)
 // ------------------------------------------------------------------------------------------------
+// `steer`, `acc`: the low-level action act() produced for this sub-step.
+// Trigonometry: with t = tan(delta)/2 the slip angle beta = atan(t) has cos = 1/sqrt(1+t^2), sin = t/sqrt(1+t^2),
+// and cos/sin(heading + beta) follow by angle addition from the cached cos/sin(heading); one sincos of the new
+// heading refreshes the cache and gives g.vx = cos(heading' + beta) and the logged vx.  That is 2 libm calls per
+// move instead of 6 (tan, atan, sincos, sin, cos, cos), each result within a few ulp of the reference's chain.
 template <bool DIAG>
-__device__ void vehicle_step(Env &ev, const StepParams &p, int i, int sub, size_t e_glob, double *stat_acc) {
+__device__ void vehicle_step(Env &ev, const StepParams &p, int i, int sub, size_t e_glob, double *stat_acc, double steer,
+                             double acc) {
     uint32_t f = FL(i);
     const bool cav = fl_kind(f) == MM_KIND_CAV;
     const double dt = p.cfg.dt;
-    double speed = V(i), heading = H(i);
-    double steer = GF(F_ACT_STEER, i), acc = GF(F_ACT_ACC, i);
+    const double speed = V(i), heading = H(i);
+    const double ch = GF(F_COSH, i), sh = GF(F_SINH, i), rec1vx = GF(F_REC1VX, i);   // issued early: L2 latency
     if (!cav) GF(F_TIMER, i) = GF(F_TIMER, i) + dt;
     // clip_actions
     if (f & FL_CRASHED) { steer = 0.0; acc = -1.0 * speed; }
     if (speed > 40.0) acc = fmin(acc, 1.0 * (40.0 - speed));
     else if (speed < -40.0) acc = fmax(acc, 1.0 * (40.0 - speed));
+    if (cav) acc = clipd(acc, ACC_LO, ACC_HI);
+    GF(F_ACT_STEER, i) = steer;
+    GF(F_ACT_ACC, i) = acc;
     if (cav) {
-        acc = clipd(acc, ACC_LO, ACC_HI);
-        GF(F_ACT_STEER, i) = steer;
-        GF(F_ACT_ACC, i) = acc;
         // get_safe_action gate (safe_controller.py:229-239)
         if (p.cfg.shield != MM_SHIELD_NONE && (f & FL_FG) && fl_hist(f) >= 2) {
             ShieldRec rec;
@@ -655,28 +661,28 @@ __device__ void vehicle_step(Env &ev, const StepParams &p, int i, int sub, size_
         }
         GF(F_SAFE_STEER, i) = steer;
         GF(F_SAFE_ACC, i) = acc;
-    } else {
-        GF(F_ACT_STEER, i) = steer;
-        GF(F_ACT_ACC, i) = acc;
     }
-    // modified bicycle model
-    double beta = m_atan(1.0 / 2 * m_tan(steer));
-    double sn, cs;
-    { double2 sc_ = m_sincos(heading + beta); sn = sc_.x; cs = sc_.y; }
-    double nx = X(i) + speed * cs * dt;
-    double ny = Y(i) + speed * sn * dt;
-    double nh = heading + speed * m_sin(beta) / (VLEN / 2) * dt;
+    // modified bicycle model (kinematics.py:133-140, safe_controller.py:151-172)
+    double t = 1.0 / 2 * m_tan(steer);
+    double cb = 1.0 / sqrt(1.0 + t * t), sb = t * cb;           // cos / sin of the slip angle
+    double c_hb = ch * cb - sh * sb, s_hb = sh * cb + ch * sb;  // cos / sin (heading + beta)
+    double nx = X(i) + speed * c_hb * dt;
+    double ny = Y(i) + speed * s_hb * dt;
+    double nh = heading + speed * sb / (VLEN / 2) * dt;
     double nv = fmax(0.0, speed + acc * dt);
+    double2 scn = m_sincos(nh);
     if (cav) {
-        GF(F_GVX, i) = m_cos(nh + beta);
+        GF(F_GVX, i) = scn.y * cb - scn.x * sb;                 // cos(heading' + beta)
         f |= FL_FG;
     }
     // on_state_update + log_step
     int lane = closest_lane(nx, ny, nh);
     f = fl_set(f, FL_LANE_SHIFT, FL_3BIT, (uint32_t)lane);
     GF(F_REC2X, i) = X(i);
-    GF(F_REC2VX, i) = GF(F_REC1VX, i);
-    GF(F_REC1VX, i) = nv * m_cos(nh);
+    GF(F_REC2VX, i) = rec1vx;
+    GF(F_REC1VX, i) = nv * scn.y;
+    GF(F_COSH, i) = scn.y;
+    GF(F_SINH, i) = scn.x;
     int hist = fl_hist(f);
     if (hist < 2) f = fl_set(f, FL_HIST_SHIFT, 3u, (uint32_t)(hist + 1));
     X(i) = nx; Y(i) = ny; H(i) = nh; V(i) = nv;
@@ -686,13 +692,10 @@ __device__ void vehicle_step(Env &ev, const StepParams &p, int i, int sub, size_
 // ------------------------------------------------------------------------------------------------
 // collisions (road.py:288-292, kinematics.py:175-209, utils.py:55-121)
 // ------------------------------------------------------------------------------------------------
-// does rect1 (centre c1, half sizes lx/wy, angle a1) have one of its 9 sample points inside rect2?
+// does rect1 (centre c1, half sizes lx/wy, heading cos/sin co1/s1) have one of its 9 sample points inside rect2?
 // NB the reference rotates (p - c2) by +a2, not -a2; reproduced as is.
-__device__ __noinline__ bool has_corner_inside(double c1x, double c1y, double lx, double wy, double a1, double c2x, double c2y,
-                                  double l2, double w2, double a2) {
-    double s1, co1, s2, co2;
-    { double2 sc_ = m_sincos(a1); s1 = sc_.x; co1 = sc_.y; }
-    { double2 sc_ = m_sincos(a2); s2 = sc_.x; co2 = sc_.y; }
+__device__ __noinline__ bool has_corner_inside(double c1x, double c1y, double lx, double wy, double co1, double s1,
+                                               double c2x, double c2y, double l2, double w2, double co2, double s2) {
     // sample points in the reference's order: centre, -l, +l, -w, +w, -l-w, -l+w, +l-w, +l+w (utils.py:115-117);
     // sign of the l / w component of point k packed two bits each (0: zero, 1: plus, 2: minus)
     const uint32_t lsel = 0x16818u, wsel = 0x19980u;
@@ -711,31 +714,32 @@ __device__ __noinline__ bool has_corner_inside(double c1x, double c1y, double lx
     return false;
 }
 
-__device__ __noinline__ bool rects_intersect(double ax, double ay, double ah, double bx, double by, double bh,
-                                             double blen, double bwid) {
-    return has_corner_inside(ax, ay, 0.9 * VLEN / 2, 0.9 * VWID / 2, ah, bx, by, 0.9 * blen, 0.9 * bwid, bh) ||
-           has_corner_inside(bx, by, 0.9 * blen / 2, 0.9 * bwid / 2, bh, ax, ay, 0.9 * VLEN, 0.9 * VWID, ah);
+__device__ __noinline__ bool rects_intersect(double ax, double ay, double aco, double asn, double bx, double by,
+                                             double bco, double bsn, double blen, double bwid) {
+    return has_corner_inside(ax, ay, 0.9 * VLEN / 2, 0.9 * VWID / 2, aco, asn, bx, by, 0.9 * blen, 0.9 * bwid, bco, bsn) ||
+           has_corner_inside(bx, by, 0.9 * blen / 2, 0.9 * bwid / 2, bco, bsn, ax, ay, 0.9 * VLEN, 0.9 * VWID, aco, asn);
 }
 
 // Conservative pre-test for has_corner_inside(rect1 -> rect2): with u = R(a2)(c1 + R(a1)q - c2) and q ranging over
-// rect1's sample points (|qx| <= lx1, |qy| <= wy1), |sin a| <= |a| and |cos a| >= 1 - a^2/2 give lower bounds on
-// |ux| and |uy|; if either bound clears the half size of rect2 by more than 1e-6 m no sample point can pass the
-// inside test (the reference's own rounding error there is ~1e-15), so the exact 9-point test is skipped.
-// Side-by-side vehicles on bc0/bc1 and queues behind the obstacle are the common case this removes.
-__device__ __forceinline__ bool may_have_corner_inside(double adx, double ady, double lx1, double wy1, double a1,
-                                                       double l2, double w2, double a2) {
-    double aa1 = fabs(a1), aa2 = fabs(a2);
-    double c2min = fmax(0.0, 1.0 - 0.5 * aa2 * aa2), s2max = fmin(1.0, aa2), s1max = fmin(1.0, aa1);
+// rect1's sample points (|qx| <= lx1, |qy| <= wy1), |ux| >= |cos a2| |dx| - |sin a2| |dy| and the analogous bound for
+// uy hold with |dx| >= |Dx| - (lx1 + |sin a1| wy1), |dy| <= |Dy| + lx1 + wy1, ...; if either bound clears the half
+// size of rect2 by more than 1e-6 m no sample point can pass the inside test (the reference's own rounding error
+// there is ~1e-15), so the exact 9-point test is skipped.  Side-by-side vehicles on bc0/bc1 and queues behind
+// the obstacle are the common case this removes.
+__device__ __forceinline__ bool may_have_corner_inside(double adx, double ady, double lx1, double wy1, double as1,
+                                                       double l2, double w2, double ac2, double as2) {
     double reach = lx1 + wy1;
-    double uy_min = c2min * fmax(0.0, ady - (s1max * lx1 + wy1)) - s2max * (adx + reach);
+    double uy_min = ac2 * fmax(0.0, ady - (as1 * lx1 + wy1)) - as2 * (adx + reach);
     if (uy_min > 0.5 * w2 + 1e-6) return false;
-    double ux_min = c2min * fmax(0.0, adx - (lx1 + s1max * wy1)) - s2max * (ady + reach);
+    double ux_min = ac2 * fmax(0.0, adx - (lx1 + as1 * wy1)) - as2 * (ady + reach);
     if (ux_min > 0.5 * l2 + 1e-6) return false;
     return true;
 }
-__device__ __forceinline__ bool may_intersect(double adx, double ady, double ah, double bh, double blen, double bwid) {
-    return may_have_corner_inside(adx, ady, 0.9 * VLEN / 2, 0.9 * VWID / 2, ah, 0.9 * blen, 0.9 * bwid, bh) ||
-           may_have_corner_inside(adx, ady, 0.9 * blen / 2, 0.9 * bwid / 2, bh, 0.9 * VLEN, 0.9 * VWID, ah);
+__device__ __forceinline__ bool may_intersect(double adx, double ady, double aco, double asn, double bco, double bsn,
+                                              double blen, double bwid) {
+    aco = fabs(aco); asn = fabs(asn); bco = fabs(bco); bsn = fabs(bsn);
+    return may_have_corner_inside(adx, ady, 0.9 * VLEN / 2, 0.9 * VWID / 2, asn, 0.9 * blen, 0.9 * bwid, bco, bsn) ||
+           may_have_corner_inside(adx, ady, 0.9 * blen / 2, 0.9 * bwid / 2, bsn, 0.9 * VLEN, 0.9 * VWID, aco, asn);
 }
 
 __device__ __noinline__ void collision_pass(Env &ev) {
@@ -746,8 +750,9 @@ __device__ __noinline__ void collision_pass(Env &ev) {
             if (FL(i) & FL_CRASHED) break;
             double dx = X(j) - ax, dy = Y(j) - ay;
             if (dx * dx + dy * dy > VLEN_SQ_GT) continue;  // np.linalg.norm(...) > LENGTH
-            if (!may_intersect(fabs(dx), fabs(dy), H(i), H(j), VLEN, VWID)) continue;
-            if (rects_intersect(ax, ay, H(i), X(j), Y(j), H(j), VLEN, VWID)) {
+            double aco = GF(F_COSH, i), asn = GF(F_SINH, i), bco = GF(F_COSH, j), bsn = GF(F_SINH, j);
+            if (!may_intersect(fabs(dx), fabs(dy), aco, asn, bco, bsn, VLEN, VWID)) continue;
+            if (rects_intersect(ax, ay, aco, asn, X(j), Y(j), bco, bsn, VLEN, VWID)) {
                 double va = V(i), vb = V(j);
                 double m = fabs(va) <= fabs(vb) ? va : vb;
                 V(i) = m; V(j) = m;
@@ -756,11 +761,14 @@ __device__ __noinline__ void collision_pass(Env &ev) {
         }
         if (!(FL(i) & FL_CRASHED)) {
             double dx = OBST_X - ax, dy = OBST_Y - ay;
-            if (!(dx * dx + dy * dy > VLEN_SQ_GT) && may_intersect(fabs(dx), fabs(dy), H(i), 0.0, 2.0, 2.0) &&
-                rects_intersect(ax, ay, H(i), OBST_X, OBST_Y, 0.0, 2.0, 2.0)) {
-                double va = V(i);
-                V(i) = fabs(va) <= 0 ? va : 0.0;
-                FL(i) |= FL_CRASHED;
+            if (!(dx * dx + dy * dy > VLEN_SQ_GT)) {
+                double aco = GF(F_COSH, i), asn = GF(F_SINH, i);
+                if (may_intersect(fabs(dx), fabs(dy), aco, asn, 1.0, 0.0, 2.0, 2.0) &&
+                    rects_intersect(ax, ay, aco, asn, OBST_X, OBST_Y, 1.0, 0.0, 2.0, 2.0)) {
+                    double va = V(i);
+                    V(i) = fabs(va) <= 0 ? va : 0.0;
+                    FL(i) |= FL_CRASHED;
+                }
             }
         }
     }
@@ -915,9 +923,8 @@ __device__ __noinline__ void write_outputs(const Env &ev, const StepParams &p, s
     float *obs = o.obs + e * (size_t)(MAXV * NS);
     double vx[MAXV], vy[MAXV];   // Vehicle.velocity (kinematics.py:215-217) of every vehicle, once per env
     for (int i = 0; i < ev.n_veh; ++i) {
-        double2 sc = m_sincos(H(i));
-        vx[i] = V(i) * sc.y;
-        vy[i] = V(i) * sc.x;
+        vx[i] = V(i) * GF(F_COSH, i);
+        vy[i] = V(i) * GF(F_SINH, i);
     }
     for (int i = 0; i < ev.n_cav; ++i) observe_agent(ev, i, vx, vy, obs + i * NS);
     float2 *z = reinterpret_cast<float2 *>(obs + ev.n_cav * NS);
@@ -1028,6 +1035,12 @@ __device__ __forceinline__ void flush_stats(double *stat_acc, double *stats, siz
 #endif
 #define PHASE_BARRIER(level) do { if (MM_PHASE_SYNC >= (level)) __syncthreads(); } while (0)
 
+__device__ __forceinline__ int meta_action(uint32_t lo, uint32_t mid, uint32_t hi, int i) {
+    uint32_t w = i < 4 ? lo : (i < 8 ? mid : hi);
+    int a = (int)(int8_t)((w >> (8 * (i & 3))) & 0xffu);
+    return (a >= 0 && a <= 4) ? a : A_IDLE;
+}
+
 template <bool DIAG>
 __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid_constant__ StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1077,29 +1090,42 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
         steps = min(steps + 1, (int)EI_STEPS_MASK);  // abstract.py:457
     }
     bool running = valid;
+    // All-CAV envs: a CAV's act() reads and writes only its own state (controller.py:90-134), so it can run right
+    // before that vehicle's step() instead of in a separate pass; the result is identical and the action never
+    // leaves registers.  With HDVs present the two ordered passes are kept (MOBIL reads the others' target lanes).
+    // The choice is made per CTA so that the barriers below stay uniform.
+    const bool merged = __syncthreads_and(!valid || ev.n_cav == ev.n_veh) != 0;
     const int n_rank = MM_PHASE_SYNC >= 2 ? MAXV - 1 : 0;  // uniform trip count when ranks are barrier-separated
 #pragma unroll 1
     for (int sub = 0; sub < p.cfg.substeps; ++sub) {  // abstract.py:514-531
         PHASE_BARRIER(1);
         uint64_t ord = 0;
+        const bool apply_meta = running && (time % p.cfg.substeps == 0);   // abstract.py:516-519
         if (running) {
-            if (time % p.cfg.substeps == 0) {
+            if (apply_meta && !merged) {
                 for (int i = 0; i < ev.n_cav; ++i) {
-                    uint32_t w = i < 4 ? act_lo : (i < 8 ? act_mid : act_hi);
-                    int a = (int)(int8_t)((w >> (8 * (i & 3))) & 0xffu);
-                    cav_act(ev, i, (a >= 0 && a <= 4) ? a : A_IDLE);
+                    double st_, ac_;
+                    cav_act(ev, i, meta_action(act_lo, act_mid, act_hi, i), st_, ac_);
                 }
             }
             ord = order_by_x_desc(ev);
         }
         const int n_live = running ? ev.n_veh : 0;
+        if (!merged) {
 #pragma unroll 1
-        for (int q = 0; q < (MM_PHASE_SYNC >= 2 ? n_rank : n_live); ++q) {  // road.act()
-            PHASE_BARRIER(2);
-            if (q < n_live) {
-                int i = (int)((ord >> (4 * q)) & 15u);
-                if (fl_kind(FL(i)) == MM_KIND_CAV) cav_act(ev, i, A_NONE);
-                else hdv_act(ev, i);
+            for (int q = 0; q < (MM_PHASE_SYNC >= 2 ? n_rank : n_live); ++q) {  // road.act()
+                PHASE_BARRIER(2);
+                if (q < n_live) {
+                    int i = (int)((ord >> (4 * q)) & 15u);
+                    if (fl_kind(FL(i)) == MM_KIND_CAV) {
+                        double st_, ac_;
+                        cav_act(ev, i, A_NONE, st_, ac_);
+                        GF(F_ACT_STEER, i) = st_;
+                        GF(F_ACT_ACC, i) = ac_;
+                    } else {
+                        hdv_act(ev, i);
+                    }
+                }
             }
         }
 #pragma unroll 1
@@ -1107,7 +1133,15 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
             PHASE_BARRIER(2);
             if (q < n_live) {
                 int i = (int)((ord >> (4 * q)) & 15u);
-                vehicle_step<DIAG>(ev, p, i, sub < 3 ? sub : 2, e, stat_acc);
+                double st_, ac_;
+                if (merged) {
+                    // sub-step 0 calls act(meta) and then act(None); the second call recomputes the same controls
+                    cav_act(ev, i, apply_meta ? meta_action(act_lo, act_mid, act_hi, i) : A_NONE, st_, ac_);
+                } else {
+                    st_ = GF(F_ACT_STEER, i);
+                    ac_ = GF(F_ACT_ACC, i);
+                }
+                vehicle_step<DIAG>(ev, p, i, sub < 3 ? sub : 2, e, stat_acc, st_, ac_);
             }
         }
         PHASE_BARRIER(2);
@@ -1259,6 +1293,7 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ Re
         g[(F_TSPEED * MAXV + i) * TILE] = tspeed;
         g[(F_TIMER * MAXV + i) * TILE] = timer;
         g[(F_MINHW * MAXV + i) * TILE] = 180.0 / 40.0;  // safe_controller.py:56
+        g[(F_COSH * MAXV + i) * TILE] = 1.0;            // heading 0
         p.st.flags[flags_index(e, i)] = f;
     }
     p.st.einfo[e] = (uint32_t)n_veh | ((uint32_t)n_cav << EI_NCAV_SHIFT) | ((uint32_t)n_m_c << EI_NMERGE_SHIFT);
@@ -1283,6 +1318,11 @@ __global__ void pack_state_kernel(DevState st, int n_envs, const double *f64_em,
     for (int k = 0; k < 16; ++k) {
         int fld = c_host_f64_to_field[k];
         if (fld >= 0) st.f64[f64_index(e, fld, i)] = f64_em[(size_t)k * E * MAXV + idx];
+    }
+    {
+        double2 sc = m_sincos(f64_em[(size_t)2 * E * MAXV + idx]);   // host field 2 = heading
+        st.f64[f64_index(e, F_COSH, i)] = sc.y;
+        st.f64[f64_index(e, F_SINH, i)] = sc.x;
     }
     const size_t P = E * MAXV;
     int hl = i32_em[5 * P + idx];

@@ -5,7 +5,7 @@
 // fully used 128-byte lines, and the whole state of a CTA is one contiguous ~190 KB span (one TLB entry —
 // a plain [field][slot][E] layout put the 180 planes of an env 8 MB apart at E = 2^20 and thrashed the
 // 128-entry TLB: 80 ms/step instead of 22, profiles/r1_v1_*).
-//   f64   [n_tiles][F_COUNT][MM_MAXV][TILE]   vehicle state
+//   f64   [n_tiles][F_COUNT][MM_MAXV][TILE]   vehicle state (15 reference fields + cached cos/sin of the heading)
 //   flags [n_tiles][MM_MAXV][TILE] u32        packed discrete vehicle state (bit layout below)
 //   einfo [E_pad] u32                         packed env scalars: n_veh, n_cav, n_merge, steps, time
 //   episode [E_pad] u32                       episode counter (RNG stream id for device-side spawn)
@@ -31,6 +31,7 @@ enum F64Field {
     F_SAFE_STEER, F_SAFE_ACC,        // shielded action of the last step()
     F_TIMER,                         // IDMVehicle.timer
     F_MINHW,                         // MDPLCVehicle.min_headway
+    F_COSH, F_SINH,                  // cos / sin of the current heading (derived; refreshed by every move)
     F_COUNT
 };
 
