@@ -200,6 +200,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer pass (default min(steps, 20))")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--policy", action="store_true",
+                    help="BASELINE configs[3]: sample the actions from the MAPPO actor (30-128-128-5) on the device "
+                         "inside the timed region instead of reading pre-drawn uniform actions")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.envs:
@@ -255,10 +258,22 @@ def main():
     sampler = ClockSampler(dev)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    policy = None
+    if args.policy:
+        from marl_mass_b200.rollout import BatchedMAPPORollout
+        torch.manual_seed(rank)
+        policy = BatchedMAPPORollout(env, roll_out_n_steps=1)
+        vbuf = env.buffers()
+        for t in range(3):
+            env.step(policy._act(vbuf["obs"], vbuf["n_agents"])[0], auto_reset=True)
     barrier()
     ev0.record()
-    for t in range(K):
-        env.step(pool[t % 8], auto_reset=True)
+    if policy is None:
+        for t in range(K):
+            env.step(pool[t % 8], auto_reset=True)
+    else:
+        for t in range(K):
+            env.step(policy._act(vbuf["obs"], vbuf["n_agents"])[0], auto_reset=True)
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
@@ -281,6 +296,28 @@ def main():
         env.reset(seed=mmd.rank_seed(2, rank), mask=v["done"])
     torch.cuda.synchronize()
     clocks = sampler.stop()
+
+    # CBF-QP alone (the metric's "CBF-QP solves/s"): 2^26 synthetic solves, ~10 % of rows active
+    nq = 1 << 26
+    g2 = torch.Generator(device="cuda").manual_seed(7)
+    dtq = 1.0 / 15
+    qa = dtq * torch.cos(torch.rand(nq, generator=g2, device="cuda", dtype=torch.float64) * 0.6 - 0.3)
+    qcl = torch.randn(nq, generator=g2, device="cuda", dtype=torch.float64) * 3 + 2
+    qca = torch.randn(nq, generator=g2, device="cuda", dtype=torch.float64) * 3 + 2
+    qha = (torch.rand(nq, generator=g2, device="cuda") < 0.3).to(torch.uint8)
+    qlo = torch.full((nq,), -12.5 * dtq, device="cuda", dtype=torch.float64) + 1e-3 * torch.rand(nq, generator=g2, device="cuda", dtype=torch.float64)
+    qhi = qlo + 18.5 * dtq
+    for _ in range(3):
+        mm.shield_qp(qa, qcl, qca, qha, qlo, qhi)
+    qe0, qe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    qe0.record()
+    for _ in range(10):
+        qu, qact = mm.shield_qp(qa, qcl, qca, qha, qlo, qhi)
+    qe1.record()
+    torch.cuda.synchronize()
+    qp_ms = qe0.elapsed_time(qe1) / 10
+    qp_active = float((qact != 0).float().mean())
+    del qa, qcl, qca, qha, qlo, qhi, qu, qact
 
     # e2e pass: host buffers through mm_step_host
     K2 = args.e2e_steps or min(K, 20)
@@ -336,6 +373,11 @@ def main():
                      "note": "issue/latency-bound f64 kernel (SURVEY.md 8d): HBM fraction is reported as asked; "
                              "see profiles/ for pipe utilisation"},
     }
+    line["qp_microbench"] = {"solves_per_s": nq / (qp_ms * 1e-3), "n": nq, "ms": qp_ms, "active_frac": qp_active,
+                             "bytes_per_solve": 50, "achieved_GBps": nq * 50 / (qp_ms * 1e-3) / 1e9,
+                             "hbm_frac": nq * 50 / (qp_ms * 1e-3) / 1e9 / peak, "dtype": "f64"}
+    if args.policy:
+        line["config"]["actions"] = "sampled on device from the MAPPO actor 30-128-128-5 (torch, fp32) inside the timed region"
     if rank == 0 and world == 1 and not args.skip_cpu:
         v_cpu, cores, n_steps, e_cpu, _ = cpu_port_throughput(wl["cfg"], args.cpu_seconds, min(E, 16384))
         line["cpu_baseline"] = {"value": v_cpu, "unit": "agent-steps/s", "cores": cores, "kind": "port",

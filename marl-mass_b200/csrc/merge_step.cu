@@ -373,11 +373,14 @@ __device__ __forceinline__ double solve_cbf_qp(double a, double c_lead, double c
     return u;
 }
 
-// decentral_layer.py:23-39
-__device__ __forceinline__ int is_adj_lane(int l1, int nl /* next_lane(l1, position) */, int l2) {
-    if (lane_road(l1) == lane_road(l2) && abs(lane_rid(l1) - lane_rid(l2)) == 1) return lane_rid(l1) - lane_rid(l2);
-    if (lane_road(nl) == lane_road(l2) && abs(lane_rid(nl) - lane_rid(l2)) == 1) return lane_rid(nl) - lane_rid(l2);
-    return 0;
+// decentral_layer.py:23-39.  Only the b->c road has two lanes, so adjacency can only arise through lane l1 itself
+// when it is bc0/bc1, else through its next lane nl = next_lane(l1, position); the result is
+// (index of that lane on the road) - (index of l2) when both are bc lanes and differ, else 0.
+__device__ __forceinline__ int is_adj_lane(int l1, int nl, int l2) {
+    bool l1_bc = (l1 == L_BC0) | (l1 == L_BC1);
+    int eff = l1_bc ? l1 : nl;
+    bool eff_bc = (eff == L_BC0) | (eff == L_BC1), l2_bc = (l2 == L_BC0) | (l2 == L_BC1);
+    return (eff_bc & l2_bc & (eff != l2)) ? (eff == L_BC1 ? 1 : -1) : 0;
 }
 
 // controller.py:257-267; left: dir == "L".  cos/sin(+-alpha + heading) by angle addition from the cached cos/sin of
@@ -416,15 +419,14 @@ __device__ __forceinline__ int close_vehicles(const Env &ev, int self, int (&ids
         int id = j;
         ++n;
         if (!(key < keys[K - 1])) continue;  // not among the K nearest so far (ties go to the earlier vehicle)
-        // stable insertion: a later element goes after equal keys; once placed, everything behind shifts
-        bool placed = false;
+        // replace the current K-th and bubble it forward; strict '<' keeps equal keys in list order (stable sort)
+        keys[K - 1] = key;
+        ids[K - 1] = id;
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            if (placed || key < keys[k]) {
-                double tk = keys[k]; keys[k] = key; key = tk;
-                int ti = ids[k]; ids[k] = id; id = ti;
-                placed = true;
-            }
+        for (int k = K - 1; k > 0; --k) {
+            if (!(keys[k] < keys[k - 1])) break;
+            double tk = keys[k]; keys[k] = keys[k - 1]; keys[k - 1] = tk;
+            int ti = ids[k]; ids[k] = ids[k - 1]; ids[k - 1] = ti;
         }
     }
     return n < K ? n : K;
@@ -748,6 +750,10 @@ __device__ __noinline__ void collision_pass(Env &ev) {
         for (int j = 0; j < ev.n_veh; ++j) {
             if (j == i) continue;
             if (FL(i) & FL_CRASHED) break;
+            // The pair {j < i} already had its turn as (j, i) unless j was crashed by then (check_collision returns
+            // early for a crashed caller); an uncrashed j means that test ran and was negative, and the geometry
+            // has not changed since, so only crashed lower-index partners need the test from this side.
+            if (j < i && !(FL(j) & FL_CRASHED)) continue;
             double dx = X(j) - ax, dy = Y(j) - ay;
             if (dx * dx + dy * dy > VLEN_SQ_GT) continue;  // np.linalg.norm(...) > LENGTH
             double aco = GF(F_COSH, i), asn = GF(F_SINH, i), bco = GF(F_COSH, j), bsn = GF(F_SINH, j);

@@ -1,0 +1,161 @@
+"""Batched MAPPO rollout on top of `MergeEnvBatched` (BASELINE configs[3]).
+
+The reference's `MAPPO.interact` (marl/mappo.py:102-158) steps ONE env, one agent at a time through a shared
+actor; here the same data flow runs for E envs x up to 11 agents per step with no host synchronisation:
+
+    obs [E,12,30] --actor--> log-probs --multinomial--> actions [E,12] int8 --env.step(auto_reset)--> ...
+
+Kept from the reference: the networks (marl/single_agent/Model_common.py:5-40: actor 30-128-128-5 log-softmax,
+critic on (state, one-hot action)), reward selection `regionalR | global_R` (mappo.py:122-125), reward scaling,
+the discounted return (`_discount_reward`, mappo.py:364-370, final value 0 at episode end, critic bootstrap
+otherwise) and the PPO-clip / critic losses of `MAPPO.train` (mappo.py:161-206) — batched over every live
+(env, agent, t) sample instead of looped per agent.  The learner itself stays out of scope for the hot-path work;
+this module is the caller that lets BASELINE configs[3] (policy + env on device) be measured.
+"""
+import torch
+from torch import nn
+
+from ._lib import MAXV, NA, NS
+
+
+class ActorNetwork(nn.Module):
+    """marl/single_agent/Model_common.py:5-23 with output_act = log_softmax."""
+
+    def __init__(self, state_dim=NS, hidden_size=128, output_size=NA):
+        super().__init__()
+        self.fc1 = nn.Linear(state_dim, hidden_size)
+        self.fc2 = nn.Linear(hidden_size, hidden_size)
+        self.fc3 = nn.Linear(hidden_size, output_size)
+
+    def forward(self, state):
+        out = torch.relu(self.fc1(state))
+        out = torch.relu(self.fc2(out))
+        return torch.log_softmax(self.fc3(out), dim=-1)
+
+
+class CriticNetwork(nn.Module):
+    """marl/single_agent/Model_common.py:26-41."""
+
+    def __init__(self, state_dim=NS, action_dim=NA, hidden_size=128):
+        super().__init__()
+        self.fc1 = nn.Linear(state_dim, hidden_size)
+        self.fc2 = nn.Linear(hidden_size + action_dim, hidden_size)
+        self.fc3 = nn.Linear(hidden_size, 1)
+
+    def forward(self, state, action_one_hot):
+        out = torch.relu(self.fc1(state))
+        out = torch.relu(self.fc2(torch.cat([out, action_one_hot], -1)))
+        return self.fc3(out)
+
+
+def discounted_returns(rewards, dones, final_value, gamma):
+    """R_t = r_t + gamma * R_{t+1}, restarted after a terminal step (mappo.py:364-370 run per episode).
+
+    rewards [T, ...], dones [T, ...] (1 where step t ended its episode), final_value [...] = bootstrap for the
+    step after the last one (ignored where the last step was terminal)."""
+    out = torch.empty_like(rewards)
+    running = final_value
+    for t in range(rewards.shape[0] - 1, -1, -1):
+        running = rewards[t] + gamma * running * (1.0 - dones[t])
+        out[t] = running
+    return out
+
+
+class BatchedMAPPORollout(object):
+    def __init__(self, env, actor=None, critic=None, roll_out_n_steps=100, reward_gamma=0.99, reward_scale=20.0,
+                 reward_type="regionalR", clip_param=0.2, actor_lr=5e-4, critic_lr=5e-4, max_grad_norm=5.0):
+        self.env = env
+        dev = torch.device("cuda", env.device)
+        self.actor = (actor or ActorNetwork()).to(dev)
+        self.critic = (critic or CriticNetwork()).to(dev)
+        self.actor_target = ActorNetwork().to(dev)
+        self.critic_target = CriticNetwork().to(dev)
+        self.actor_target.load_state_dict(self.actor.state_dict())
+        self.critic_target.load_state_dict(self.critic.state_dict())
+        self.T = int(roll_out_n_steps)
+        self.gamma, self.reward_scale, self.reward_type = float(reward_gamma), float(reward_scale), reward_type
+        self.clip_param, self.max_grad_norm = clip_param, max_grad_norm
+        self.actor_opt = torch.optim.RMSprop(self.actor.parameters(), lr=actor_lr)   # mappo.py:88-90
+        self.critic_opt = torch.optim.RMSprop(self.critic.parameters(), lr=critic_lr)
+        self.dev = dev
+        self.obs = None
+        E = env.n_envs
+        self._slot = torch.arange(MAXV, device=dev)[None, :]
+        self.buf = None
+        self.E = E
+
+    @torch.no_grad()
+    def _act(self, obs, n_agents):
+        logp = self.actor(obs.view(-1, NS))                               # [E*12, 5]
+        a = torch.multinomial(logp.exp(), 1).view(self.E, MAXV)           # exploration_action, mappo.py:225-230
+        live = self._slot < n_agents[:, None]
+        return torch.where(live, a, torch.ones_like(a)).to(torch.int8), live
+
+    @torch.no_grad()
+    def collect(self):
+        """One rollout of T policy steps for every env; returns the batch dict (device tensors)."""
+        env, E, T = self.env, self.E, self.T
+        v = env.buffers()
+        if self.obs is None:
+            self.obs, _ = env.reset()
+        S = torch.empty((T, E, MAXV, NS), device=self.dev)
+        A = torch.empty((T, E, MAXV), dtype=torch.int64, device=self.dev)
+        R = torch.empty((T, E, MAXV), device=self.dev)
+        D = torch.empty((T, E), device=self.dev)
+        L = torch.empty((T, E, MAXV), dtype=torch.bool, device=self.dev)
+        for t in range(T):
+            n_agents = v["n_agents"].clone()
+            S[t].copy_(self.obs)
+            a, live = self._act(self.obs, n_agents)
+            self.obs, reward, done, info = env.step(a, auto_reset=True)
+            A[t], L[t] = a.long(), live
+            if self.reward_type == "regionalR":
+                R[t].copy_(info["regional_rewards"])
+            else:
+                R[t].copy_(reward[:, None].expand(E, MAXV))
+            D[t].copy_(done)
+        if self.reward_scale > 0:
+            R /= self.reward_scale
+        # bootstrap where the last step did not end the episode (mappo.py:148-150)
+        a_fin, _ = self._act(self.obs, v["n_agents"])
+        onehot = torch.nn.functional.one_hot(a_fin.long(), NA).float()
+        final_value = self.critic(self.obs.view(-1, NS), onehot.view(-1, NA)).view(E, MAXV)
+        returns = discounted_returns(R, D[:, :, None].expand(T, E, MAXV), final_value, self.gamma)
+        self.buf = dict(states=S, actions=A, returns=returns, live=L, dones=D, rewards=R)
+        return self.buf
+
+    def update(self, minibatch=1 << 18, epochs=1):
+        """PPO-clip actor update and critic regression on the last rollout (mappo.py:161-206), all agents at once."""
+        b = self.buf
+        live = b["live"].reshape(-1)
+        idx = live.nonzero(as_tuple=False).squeeze(1)
+        S = b["states"].reshape(-1, NS)
+        A = torch.nn.functional.one_hot(b["actions"].reshape(-1), NA).float()
+        G = b["returns"].reshape(-1, 1)
+        stats = {}
+        for _ in range(epochs):
+            perm = idx[torch.randperm(idx.numel(), device=self.dev)]
+            for k in range(0, perm.numel(), minibatch):
+                j = perm[k:k + minibatch]
+                s, a, g = S[j], A[j], G[j]
+                with torch.no_grad():
+                    adv = g - self.critic_target(s, a)
+                    old_logp = (self.actor_target(s) * a).sum(1)
+                logp = (self.actor(s) * a).sum(1)
+                ratio = torch.exp(logp - old_logp)
+                surr = torch.min(ratio * adv.squeeze(1),
+                                 torch.clamp(ratio, 1 - self.clip_param, 1 + self.clip_param) * adv.squeeze(1))
+                actor_loss = -surr.mean()
+                self.actor_opt.zero_grad(set_to_none=True)
+                actor_loss.backward()
+                nn.utils.clip_grad_norm_(self.actor.parameters(), self.max_grad_norm)
+                self.actor_opt.step()
+                critic_loss = nn.functional.mse_loss(self.critic(s, a), g)
+                self.critic_opt.zero_grad(set_to_none=True)
+                critic_loss.backward()
+                nn.utils.clip_grad_norm_(self.critic.parameters(), self.max_grad_norm)
+                self.critic_opt.step()
+                stats = {"actor_loss": float(actor_loss), "critic_loss": float(critic_loss), "samples": int(idx.numel())}
+        self.actor_target.load_state_dict(self.actor.state_dict())     # TARGET_TAU = 1.0 in every shipped ini
+        self.critic_target.load_state_dict(self.critic.state_dict())
+        return stats

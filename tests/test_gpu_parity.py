@@ -312,3 +312,34 @@ def test_full_size_properties(mm):
     st = env.get_state()
     assert st["steps"].max() <= 100 and (st["steps"] <= 1).sum() >= E * 0.9
     env.close()
+
+
+def test_batched_mappo_rollout(mm):
+    """BASELINE configs[3] data flow on a small batch: policy + env on device, returns, one PPO update."""
+    import torch
+    from marl_mass_b200.rollout import BatchedMAPPORollout
+    torch.manual_seed(0)
+    E, T = 2048, 25
+    cfg = dict(mm.DEFAULT_CONFIG, safety_guarantee="cbf-cav", traffic_density=3, HEADWAY_TIME=0.5, cbf_eta=0.03125,
+               agent_reward="srew", HIGH_SPEED_REWARD=4, HEADWAY_COST=1, MERGING_LANE_COST=8)
+    env = mm.MergeEnvBatched(E, cfg)
+    ro = BatchedMAPPORollout(env, roll_out_n_steps=T)
+    env.reset(seed=3)
+    env.stats(reset=True)
+    ro.obs = env.buffers()["obs"]
+    b = ro.collect()
+    assert b["states"].shape == (T, E, 12, 30) and b["returns"].shape == (T, E, 12)
+    assert torch.isfinite(b["returns"]).all()
+    s = env.stats()
+    assert int(b["live"].sum()) == int(s["agent_steps"])          # every live (env, agent, t) sample is one agent-step
+    assert set(torch.unique(b["actions"]).tolist()) <= {0, 1, 2, 3, 4}
+    # terminal steps cut the return: R_t == r_t there
+    term = b["dones"] > 0
+    if term.any():
+        t_idx, e_idx = term.nonzero(as_tuple=True)
+        assert torch.allclose(b["returns"][t_idx, e_idx], b["rewards"][t_idx, e_idx])
+    before = [p.detach().clone() for p in ro.actor.parameters()]
+    st = ro.update(minibatch=1 << 16)
+    assert st["samples"] == int(b["live"].sum()) and np.isfinite(st["actor_loss"]) and np.isfinite(st["critic_loss"])
+    assert any(not torch.equal(a, p) for a, p in zip(before, ro.actor.parameters()))
+    env.close()

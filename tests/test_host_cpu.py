@@ -134,3 +134,33 @@ def test_stats_all_reduce_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and ("ok %d" % r) in o, o
+
+
+def test_discounted_returns_match_reference_formula():
+    """rollout.discounted_returns == MAPPO._discount_reward (marl/mappo.py:364-370) run per episode segment."""
+    import torch
+    from marl_mass_b200.rollout import discounted_returns, ActorNetwork, CriticNetwork
+    rng = np.random.RandomState(0)
+    T, N, gamma = 37, 5, 0.99
+    r = rng.randn(T, N)
+    d = (rng.rand(T, N) < 0.1).astype(np.float64)
+    fv = rng.randn(N)
+    got = discounted_returns(torch.from_numpy(r), torch.from_numpy(d), torch.from_numpy(fv), gamma).numpy()
+    for n in range(N):
+        start = 0
+        ends = list(np.where(d[:, n] > 0)[0]) + ([T - 1] if d[T - 1, n] == 0 else [])
+        for end in ends:
+            seg = r[start:end + 1, n]
+            running = 0.0 if d[end, n] > 0 else fv[n]
+            want = np.zeros_like(seg)
+            for t in reversed(range(len(seg))):        # the reference loop
+                running = running * gamma + seg[t]
+                want[t] = running
+            assert np.allclose(got[start:end + 1, n], want, rtol=0, atol=1e-12)
+            start = end + 1
+    a, c = ActorNetwork(), CriticNetwork()
+    x = torch.randn(7, 30)
+    lp = a(x)
+    assert lp.shape == (7, 5) and torch.allclose(lp.exp().sum(1), torch.ones(7), atol=1e-6)
+    assert c(x, torch.nn.functional.one_hot(torch.arange(7) % 5, 5).float()).shape == (7, 1)
+    assert sum(p.numel() for p in a.parameters()) == 30 * 128 + 128 + 128 * 128 + 128 + 128 * 5 + 5
