@@ -62,20 +62,27 @@ constexpr double VLEN_SQ_GT = 0x1.9000000000001p+4;
 // ------------------------------------------------------------------------------------------------
 // per-thread view of one environment
 // ------------------------------------------------------------------------------------------------
+// The staged planes are addressed through the dynamic shared-memory symbol itself so that every function, inlined
+// or not, knows the address space (LDS/STS instead of generic LD/ST) and the per-thread view is a single index.
+extern __shared__ __align__(16) double sm_planes[];   // [4][MAXV][BLOCK] f64 (x, y, heading, speed) + [MAXV][BLOCK] u32
 struct Env {
-    double *sx, *sy, *sh, *sv;  // shared planes, already offset by threadIdx.x; element i at [i * BLOCK]
-    uint32_t *sf;
+    int tid;                    // threadIdx.x: column of this env inside the CTA's planes
     double *g;                  // this env's column of its tile; element (f, i) at [(f*MAXV+i)*TILE]
     int n_veh, n_cav;
 };
 
-#define X(i) (ev.sx[(i) * BLOCK])
-#define Y(i) (ev.sy[(i) * BLOCK])
-#define H(i) (ev.sh[(i) * BLOCK])
-#define V(i) (ev.sv[(i) * BLOCK])
-#define FL(i) (ev.sf[(i) * BLOCK])
-#define GF(f, i) (ev.g[((f) * MAXV + (i)) * TILE])
+#define X(i) (sm_planes[(0 * MAXV + (i)) * BLOCK + ev.tid])
+#define Y(i) (sm_planes[(1 * MAXV + (i)) * BLOCK + ev.tid])
+#define H(i) (sm_planes[(2 * MAXV + (i)) * BLOCK + ev.tid])
+#define V(i) (sm_planes[(3 * MAXV + (i)) * BLOCK + ev.tid])
+#define FL(i) (reinterpret_cast<uint32_t *>(sm_planes + 4 * MAXV * BLOCK)[(i) * BLOCK + ev.tid])
+#define GF(f, i) (*tile_ptr(ev.g, (f), (i)))
 
+__device__ __forceinline__ double *tile_ptr(double *col, int f, int i) {
+    double *q = col + ((f) * MAXV + (i)) * TILE;
+    __builtin_assume(__isGlobal(q));   // lets out-of-line functions emit LDG/STG instead of generic accesses
+    return q;
+}
 __device__ __forceinline__ int fl_kind(uint32_t f) { return f & FL_KIND_MASK; }
 __device__ __forceinline__ int fl_lane(uint32_t f) { return (f >> FL_LANE_SHIFT) & FL_3BIT; }
 __device__ __forceinline__ int fl_tlane(uint32_t f) { return (f >> FL_TLANE_SHIFT) & FL_3BIT; }
@@ -1049,8 +1056,6 @@ __device__ __forceinline__ int meta_action(uint32_t lo, uint32_t mid, uint32_t h
 
 template <bool DIAG>
 __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid_constant__ StepParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *sm = reinterpret_cast<double *>(smem_raw);
     const int tid = threadIdx.x;
     const int local = blockIdx.x * BLOCK + tid;
     const bool valid = local < p.env_count;
@@ -1062,11 +1067,7 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
     stat_acc[ST_MINHW] = CUDART_INF;
 
     Env ev;
-    ev.sx = sm + tid;
-    ev.sy = sm + MAXV * BLOCK + tid;
-    ev.sh = sm + 2 * MAXV * BLOCK + tid;
-    ev.sv = sm + 3 * MAXV * BLOCK + tid;
-    ev.sf = reinterpret_cast<uint32_t *>(sm + 4 * MAXV * BLOCK) + tid;
+    ev.tid = tid;
     ev.g = p.st.f64 + f64_index(e, 0, 0);
     ev.n_veh = 0;
     ev.n_cav = 0;
@@ -1168,19 +1169,13 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
 
 // observation only (reset() / set_state refresh)
 __global__ void __launch_bounds__(BLOCK) observe_kernel(const __grid_constant__ StepParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *sm = reinterpret_cast<double *>(smem_raw);
     const int tid = threadIdx.x;
     const int local = blockIdx.x * BLOCK + tid;
     if (local >= p.env_count) return;
     const size_t e = (size_t)p.env_offset + local;
     if (p.obs_mask && !p.obs_mask[e]) return;
     Env ev;
-    ev.sx = sm + tid;
-    ev.sy = sm + MAXV * BLOCK + tid;
-    ev.sh = sm + 2 * MAXV * BLOCK + tid;
-    ev.sv = sm + 3 * MAXV * BLOCK + tid;
-    ev.sf = reinterpret_cast<uint32_t *>(sm + 4 * MAXV * BLOCK) + tid;
+    ev.tid = tid;
     ev.g = p.st.f64 + f64_index(e, 0, 0);
     uint32_t ei = p.st.einfo[e];
     ev.n_veh = (ei >> EI_NVEH_SHIFT) & EI_4BIT;
