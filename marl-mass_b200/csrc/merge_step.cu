@@ -22,6 +22,7 @@
 //   observation / rewards ...... envs/common/observation.py:181-273, envs/merge_env_v1.py:64-178,373-474
 #include <cuda_runtime.h>
 #include <math_constants.h>
+#include <cstdlib>
 #include "mm_internal.h"
 
 namespace mm {
@@ -65,19 +66,20 @@ constexpr double VLEN_SQ_GT = 0x1.9000000000001p+4;
 // The staged planes are addressed through the dynamic shared-memory symbol itself so that every function, inlined
 // or not, knows the address space (LDS/STS instead of generic LD/ST) and the per-thread view is a single index.
 constexpr int TOPK_MAX = 5;                                       // close_vehicles_to(count=5) in the shield
-constexpr int SCRATCH_OFF = 4 * MAXV * BLOCK + MAXV * BLOCK / 2;  // doubles: 4 f64 planes + the u32 flags plane
-extern __shared__ __align__(16) double sm_planes[];   // [4][MAXV][BLOCK] f64 (x, y, heading, speed) + [MAXV][BLOCK] u32
+constexpr int SMV = 11;                                           // staged slots: an env never has more than 11 vehicles
+constexpr int SCRATCH_OFF = 4 * SMV * BLOCK + (SMV + 1) * BLOCK / 2;  // doubles: 4 f64 planes + the u32 flags plane
+extern __shared__ __align__(16) double sm_planes[];   // [4][SMV][BLOCK] f64 (x, y, heading, speed) + [SMV+1][BLOCK] u32 + top-K scratch
 struct Env {
     int tid;                    // threadIdx.x: column of this env inside the CTA's planes
     double *g;                  // this env's column of its tile; element (f, i) at [(f*MAXV+i)*TILE]
     int n_veh, n_cav;
 };
 
-#define X(i) (sm_planes[(0 * MAXV + (i)) * BLOCK + ev.tid])
-#define Y(i) (sm_planes[(1 * MAXV + (i)) * BLOCK + ev.tid])
-#define H(i) (sm_planes[(2 * MAXV + (i)) * BLOCK + ev.tid])
-#define V(i) (sm_planes[(3 * MAXV + (i)) * BLOCK + ev.tid])
-#define FL(i) (reinterpret_cast<uint32_t *>(sm_planes + 4 * MAXV * BLOCK)[(i) * BLOCK + ev.tid])
+#define X(i) (sm_planes[(0 * SMV + (i)) * BLOCK + ev.tid])
+#define Y(i) (sm_planes[(1 * SMV + (i)) * BLOCK + ev.tid])
+#define H(i) (sm_planes[(2 * SMV + (i)) * BLOCK + ev.tid])
+#define V(i) (sm_planes[(3 * SMV + (i)) * BLOCK + ev.tid])
+#define FL(i) (reinterpret_cast<uint32_t *>(sm_planes + 4 * SMV * BLOCK)[(i) * BLOCK + ev.tid])
 #define GF(f, i) (*tile_ptr(ev.g, (f), (i)))
 
 __device__ __forceinline__ double *tile_ptr(double *col, int f, int i) {
@@ -1418,8 +1420,14 @@ void launch_step(const StepParams &p, bool diag, void *stream) {
     }
     int grid = (p.env_count + BLOCK - 1) / BLOCK;
     if (grid <= 0) return;
-    if (diag) step_kernel<true><<<grid, BLOCK, STEP_SMEM, (cudaStream_t)stream>>>(p);
-    else step_kernel<false><<<grid, BLOCK, STEP_SMEM, (cudaStream_t)stream>>>(p);
+    // MM_EXTRA_SMEM (bytes): occupancy experiment knob - pads the CTA's shared memory to lower the CTAs/SM
+    static const size_t extra = [] { const char *e = getenv("MM_EXTRA_SMEM"); return e ? (size_t)atol(e) : (size_t)0; }();
+    if (extra) {
+        cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(STEP_SMEM + extra));
+        cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(STEP_SMEM + extra));
+    }
+    if (diag) step_kernel<true><<<grid, BLOCK, STEP_SMEM + extra, (cudaStream_t)stream>>>(p);
+    else step_kernel<false><<<grid, BLOCK, STEP_SMEM + extra, (cudaStream_t)stream>>>(p);
 }
 
 void launch_observe(const StepParams &p, void *stream) {
