@@ -354,6 +354,14 @@ def main():
     bytes_per_launch = E * (veh_per_env * BYTES_PER_VEHICLE + mean_agents * BYTES_PER_AGENT + BYTES_PER_ENV)
     peak, peak_src = load_peaks()
     achieved = bytes_per_launch / (kms * 1e-3) / 1e9
+    # DRAM traffic of the step kernel from the committed ncu capture (profiles/r1_traffic.json), scaled per env
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if tj.get("workload") == args.workload:
+            traffic = tj["dram_bytes"] * (E / float(tj["envs"]))
+    except Exception:
+        traffic = None
 
     line = {
         "metric": "shielded agent-steps/s", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": K,
@@ -373,7 +381,7 @@ def main():
                 "api": "mm_step_host (pinned host buffers, 64Ki-env chunks round-robin on 4 streams: copies overlap compute)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "step_kernel<false>", "kernel_ms": kms,
+                     "traffic": traffic, "kernel": "step_kernel<false>", "kernel_ms": kms,
                      "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src,
                      "note": "issue/latency-bound f64 kernel (SURVEY.md 8d): HBM fraction is reported as asked; "
                              "see profiles/ for pipe utilisation"},

@@ -818,9 +818,10 @@ __device__ __noinline__ void observe_agent(const Env &ev, int self, const double
     uint32_t nb_ids;
     int n_nb = close_vehicles<4>(ev, self, nb_ids);
     float2 *dst = reinterpret_cast<float2 *>(obs);  // 120-byte rows: 8-byte aligned
-    dst[0] = make_float2(1.0f, (float)((ex + 150.0) * KX - 1.0));
-    dst[1] = make_float2((float)((ey + 12.0) * KY - 1.0), (float)((evx + 45.0) * KV - 1.0));
-    dst[2] = make_float2((float)((evy + 45.0) * KV - 1.0), (float)((H(self) + PI / 2) * KH - 1.0));
+    // streaming stores (st.global.cs): outputs are written once and must not evict the L2-resident state tiles
+    __stcs(dst + 0, make_float2(1.0f, (float)((ex + 150.0) * KX - 1.0)));
+    __stcs(dst + 1, make_float2((float)((ey + 12.0) * KY - 1.0), (float)((evx + 45.0) * KV - 1.0)));
+    __stcs(dst + 2, make_float2((float)((evy + 45.0) * KV - 1.0), (float)((H(self) + PI / 2) * KH - 1.0)));
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         float2 a = make_float2(0.f, 0.f), b = a, c = a;
@@ -830,9 +831,9 @@ __device__ __noinline__ void observe_agent(const Env &ev, int self, const double
             b = make_float2((float)(((Y(o) - ey) + 12.0) * KY - 1.0), (float)(((vx[o] - evx) + 45.0) * KV - 1.0));
             c = make_float2((float)(((vy[o] - evy) + 45.0) * KV - 1.0), (float)((H(o) + PI / 2) * KH - 1.0));
         }
-        dst[3 * (k + 1)] = a;
-        dst[3 * (k + 1) + 1] = b;
-        dst[3 * (k + 1) + 2] = c;
+        __stcs(dst + 3 * (k + 1), a);
+        __stcs(dst + 3 * (k + 1) + 1, b);
+        __stcs(dst + 3 * (k + 1) + 2, c);
     }
 }
 
@@ -953,7 +954,10 @@ __device__ __noinline__ void write_outputs(const Env &ev, const StepParams &p, s
     }
     for (int i = 0; i < ev.n_cav; ++i) observe_agent(ev, i, vx, vy, obs + i * NS);
     float2 *z = reinterpret_cast<float2 *>(obs + ev.n_cav * NS);
-    for (int q = 0; q < (MAXV - ev.n_cav) * NS / 2; ++q) z[q] = make_float2(0.f, 0.f);
+    // rows of absent agents are zeroed when the scene is (re)built and n_cav is fixed for the episode, so the
+    // per-step path does not rewrite them
+    if (!with_rewards)
+        for (int q = 0; q < (MAXV - ev.n_cav) * NS / 2; ++q) __stcs(z + q, make_float2(0.f, 0.f));
     o.n_agents[e] = ev.n_cav;
     if (!with_rewards) return;
 
