@@ -155,7 +155,8 @@ class BatchedMAPPORollout(object):
                 critic_loss.backward()
                 nn.utils.clip_grad_norm_(self.critic.parameters(), self.max_grad_norm)
                 self.critic_opt.step()
-                stats = {"actor_loss": float(actor_loss), "critic_loss": float(critic_loss), "samples": int(idx.numel())}
+                stats = {"actor_loss": float(actor_loss.detach()), "critic_loss": float(critic_loss.detach()),
+                         "samples": int(idx.numel())}
         self.actor_target.load_state_dict(self.actor.state_dict())     # TARGET_TAU = 1.0 in every shipped ini
         self.critic_target.load_state_dict(self.critic.state_dict())
         return stats
