@@ -82,6 +82,8 @@ typedef struct {
     float *merge_percent;     /* [n_envs] info["merge_percent"] at done, else -1 */
     int32_t *n_agents;        /* [n_envs] len(env.controlled_vehicles) */
     int8_t *actions;          /* [n_envs][MM_MAXV] device-side action buffer read by mm_step(actions=NULL) */
+    uint8_t *action_mask;     /* [n_envs][MM_MAXV] bit a = meta-action a available (_get_available_actions,
+                                 abstract.py:219-240), per agent; info["action_mask"] when action_masking is on */
 } mm_buffers;
 
 /* Host arrays receiving the per-sub-step shield record of the last mm_step, [n_envs][3][MM_MAXV].

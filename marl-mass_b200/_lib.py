@@ -44,7 +44,7 @@ class MMBuffers(C.Structure):
     _fields_ = [("obs", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p), ("agents_rewards", C.c_void_p),
                 ("regional_rewards", C.c_void_p), ("agents_dones", C.c_void_p), ("average_speed", C.c_void_p),
                 ("traffic_speed", C.c_void_p), ("min_headway", C.c_void_p), ("merge_percent", C.c_void_p),
-                ("n_agents", C.c_void_p), ("actions", C.c_void_p)]
+                ("n_agents", C.c_void_p), ("actions", C.c_void_p), ("action_mask", C.c_void_p)]
 
 
 class MMShieldDiagHost(C.Structure):

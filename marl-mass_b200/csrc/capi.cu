@@ -146,6 +146,7 @@ int mm_create(const mm_config *cfg, int n_envs, int device, int record_diag, mm_
     rc |= dev_alloc(env, &env->out.done, E);
     rc |= dev_alloc(env, &env->out.agents_dones, E * MAXV);
     rc |= dev_alloc(env, &env->out.n_agents, E);
+    rc |= dev_alloc(env, &env->out.action_mask, E * MAXV);
     rc |= dev_alloc(env, &env->actions, E * MAXV);
     env->stats_rows = (E + 31) / 32;
     rc |= dev_alloc(env, &env->out.stats, env->stats_rows * N_STATS);
@@ -259,7 +260,7 @@ int mm_buffers_get(mm_env *env, mm_buffers *b) {
     b->agents_rewards = env->out.agents_rewards; b->regional_rewards = env->out.regional_rewards;
     b->agents_dones = env->out.agents_dones; b->average_speed = env->out.average_speed;
     b->traffic_speed = env->out.traffic_speed; b->min_headway = env->out.min_headway;
-    b->merge_percent = env->out.merge_percent; b->n_agents = env->out.n_agents; b->actions = env->actions;
+    b->merge_percent = env->out.merge_percent; b->n_agents = env->out.n_agents; b->actions = env->actions; b->action_mask = env->out.action_mask;
     return 0;
 }
 

@@ -959,6 +959,23 @@ __device__ __noinline__ void write_outputs(const Env &ev, const StepParams &p, s
     if (!with_rewards)
         for (int q = 0; q < (MAXV - ev.n_cav) * NS / 2; ++q) __stcs(z + q, make_float2(0.f, 0.f));
     o.n_agents[e] = ev.n_cav;
+    // _get_available_actions (abstract.py:219-240): IDLE always; LANE_LEFT only from bc1 when bc0 is reachable (the
+    // one non-forbidden side lane of the network); FASTER / SLOWER by the speed index
+    for (int i = 0; i < MAXV; ++i) {
+        uint32_t bits = 0;
+        if (i < ev.n_cav) {
+            uint32_t f = FL(i);
+            bits = 1u << A_IDLE;
+            if (fl_lane(f) == L_BC1) {
+                double s = lane_s(L_BC0, X(i)), r = Y(i) - c_lane_sy[L_BC0];
+                if (fabs(r) <= 2 * LWIDTH && 0 <= s && s < c_lane_len[L_BC0] + VLEN) bits |= 1u << A_LANE_LEFT;
+            }
+            int sidx = (int)((f >> FL_SIDX_SHIFT) & FL_3BIT);
+            if (sidx < 4) bits |= 1u << A_FASTER;
+            if (sidx > 0) bits |= 1u << A_SLOWER;
+        }
+        o.action_mask[e * MAXV + i] = (uint8_t)bits;
+    }
     if (!with_rewards) return;
 
     double local[MAXV];
@@ -1062,6 +1079,9 @@ __device__ __forceinline__ void flush_stats(double *stat_acc, double *stats, siz
 #ifndef MM_PHASE_SYNC
 #define MM_PHASE_SYNC 2
 #endif
+#ifndef MM_SORT_LANES
+#define MM_SORT_LANES 0   // measured: < 1 % (profiles/README.md); kept as an experiment knob
+#endif
 #define PHASE_BARRIER(level) do { if (MM_PHASE_SYNC >= (level)) __syncthreads(); } while (0)
 
 __device__ __forceinline__ int meta_action(uint32_t lo, uint32_t mid, uint32_t hi, int i) {
@@ -1073,7 +1093,36 @@ __device__ __forceinline__ int meta_action(uint32_t lo, uint32_t mid, uint32_t h
 template <bool DIAG>
 __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid_constant__ StepParams p) {
     const int tid = threadIdx.x;
+#if MM_SORT_LANES
+    // Lane <-> env assignment inside the CTA is free: give each warp envs with (nearly) the same vehicle count, so
+    // that the per-rank loops do not idle lanes (counts are 7..11 at hard density).  Stable counting sort of the
+    // CTA's 128 envs by n_veh with warp ballots; deterministic.
+    __shared__ int s_wcnt[BLOCK / 32][16];
+    __shared__ unsigned char s_perm[BLOCK];
+    {
+        const int l0 = blockIdx.x * BLOCK + tid;
+        int key = 15;
+        if (l0 < p.env_count) key = (int)((p.st.einfo[(size_t)p.env_offset + l0] >> EI_NVEH_SHIFT) & EI_4BIT);
+        const int warp = tid >> 5, lane = tid & 31;
+        int rank_in_warp = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            unsigned m = __ballot_sync(0xffffffffu, key == k);
+            if (lane == 0) s_wcnt[warp][k] = __popc(m);
+            if (key == k) rank_in_warp = __popc(m & ((1u << lane) - 1u));
+        }
+        __syncthreads();
+        int pos = rank_in_warp;
+        for (int k = 0; k < 16; ++k)
+            for (int w = 0; w < BLOCK / 32; ++w)
+                if (k < key || (k == key && w < warp)) pos += s_wcnt[w][k];
+        s_perm[pos] = (unsigned char)tid;
+        __syncthreads();
+    }
+    const int local = blockIdx.x * BLOCK + (int)s_perm[tid];
+#else
     const int local = blockIdx.x * BLOCK + tid;
+#endif
     const bool valid = local < p.env_count;
     const size_t e = (size_t)p.env_offset + (valid ? local : 0);
 
@@ -1180,7 +1229,7 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
         store_env(ev, p.st, e);
         p.st.einfo[e] = (ei & 0xfffu) | ((uint32_t)steps << EI_STEPS_SHIFT) | ((uint32_t)time << EI_TIME_SHIFT);
     }
-    flush_stats(stat_acc, p.out.stats, (size_t)p.env_offset + (size_t)(local & ~31));
+    flush_stats(stat_acc, p.out.stats, (size_t)p.env_offset + (size_t)((blockIdx.x * BLOCK + tid) & ~31));
 }
 
 // observation only (reset() / set_state refresh)

@@ -61,7 +61,7 @@ struct DevState {
 struct DevOut {
     float *obs, *reward, *agents_rewards, *regional_rewards, *average_speed, *traffic_speed, *min_headway,
           *merge_percent;
-    uint8_t *done, *agents_dones;
+    uint8_t *done, *agents_dones, *action_mask;
     int32_t *n_agents;
     // per-sub-step shield record [E][3][MAXV] (record_diag only, else null)
     int32_t *sh_i;      // 7 planes: ran, leader, front_adj, rear_adj, constrain_adj, active, is_lc_safe

@@ -48,8 +48,6 @@ def make_mm_config(cfg):
         raise ValueError("Undefined safety_type:{0}".format(sg.split("-")[-1]))
     if cfg.get("lateral_control", "steer") != "steer":
         raise AttributeError("Lateral control: {0} is not supported".format(cfg.get("lateral_control")))
-    if cfg.get("action_masking", False):
-        raise ValueError("action_masking=True (MAPPO_GI) is not built yet; the shipped HSS/MASS configs use False")
     tt = cfg.get("traffic_type", "cav")
     if tt not in TRAFFIC:
         raise ValueError("traffic_type %r is not supported on the batched path (cav | mixed)" % (tt,))
@@ -117,7 +115,7 @@ class MergeEnvBatched(object):
                     "agents_rewards": ((E, MAXV), "<f4"), "regional_rewards": ((E, MAXV), "<f4"),
                     "agents_dones": ((E, MAXV), "|u1"), "average_speed": ((E,), "<f4"),
                     "traffic_speed": ((E,), "<f4"), "min_headway": ((E,), "<f4"), "merge_percent": ((E,), "<f4"),
-                    "n_agents": ((E,), "<i4"), "actions": ((E, MAXV), "|i1")}
+                    "n_agents": ((E,), "<i4"), "actions": ((E, MAXV), "|i1"), "action_mask": ((E, MAXV), "|u1")}
             dev = "cuda:%d" % self.device
             self._views = {k: torch.as_tensor(_DevArray(getattr(b, k), shp, ts, self), device=dev)
                            for k, (shp, ts) in spec.items()}
@@ -163,9 +161,16 @@ class MergeEnvBatched(object):
         return v["obs"], self.action_mask()
 
     def action_mask(self):
-        """All ones, as the reference returns when action_masking is False (abstract.py:207-209)."""
+        """[E, MAXV, 5] int32.  action_masking False: all ones, as the reference returns (abstract.py:207-209).
+        True: `_get_available_actions` per agent (abstract.py:219-240), unpacked from the kernel's bitmask.
+        (The reference builds its mask as `[[0] * n_a] * n`, so its rows alias one list and every agent ends up
+        with the union over agents; `MergeEnvLCMARL` reproduces that, this batched view is per agent.)"""
         import torch
-        return torch.ones((self.n_envs, MAXV, NA), dtype=torch.int32, device="cuda:%d" % self.device)
+        dev = "cuda:%d" % self.device
+        if not self.config.get("action_masking", False):
+            return torch.ones((self.n_envs, MAXV, NA), dtype=torch.int32, device=dev)
+        bits = self.buffers()["action_mask"].to(torch.int32)
+        return (bits[:, :, None] >> torch.arange(NA, device=dev, dtype=torch.int32)[None, None, :]) & 1
 
     def step(self, actions=None, auto_reset=False, stream=None):
         """One policy step for every env.  actions: int8 CUDA tensor [E, MAXV] (None: the `actions` view).
@@ -330,7 +335,7 @@ class MergeEnvLCMARL(object):
         import torch
         torch.cuda.synchronize(self._b.device)
         obs = self._b.buffers()["obs"][0, :n].double().cpu().numpy()
-        return obs, np.array([[1] * self.n_a] * n)
+        return obs, self._mask(n)
 
     def step(self, action):
         import torch
@@ -352,7 +357,7 @@ class MergeEnvLCMARL(object):
         self.vehicle_pos.append([float(st["x"][0, i]) for i in range(n)])
         info = {
             "speed": speeds[0], "crashed": bool(st["crashed"][0, 0]), "action": action, "new_action": action,
-            "action_mask": np.array([[1] * self.n_a] * n), "average_speed": float(v["average_speed"][0]),
+            "action_mask": self._mask(n), "average_speed": float(v["average_speed"][0]),
             "vehicle_speed": np.array(self.vehicle_speed), "vehicle_position": np.array(self.vehicle_pos),
             "agents_dones": tuple(bool(x) for x in v["agents_dones"][0, :n].cpu().numpy()),
             "agents_info": [[float(st["x"][0, i]), float(st["y"][0, i]), speeds[i]] for i in range(n)],
@@ -363,6 +368,15 @@ class MergeEnvLCMARL(object):
         if done:
             info["merge_percent"] = float(v["merge_percent"][0])
         return obs, reward, done, info
+
+    def _mask(self, n):
+        """action mask as the reference returns it (abstract.py:201-209, 474-481): all ones without masking; with
+        masking the reference's rows alias ONE list (`[[0] * n_a] * n`), i.e. the union over the agents."""
+        if not self.config.get("action_masking", False):
+            return np.array([[1] * self.n_a] * n)
+        bits = self._b.buffers()["action_mask"][0, :n].cpu().numpy()
+        union = int(np.bitwise_or.reduce(bits)) if n else 0
+        return np.array([[(union >> a) & 1 for a in range(self.n_a)]] * n)
 
     def is_crashed(self):
         st = self._state()

@@ -13,6 +13,7 @@ Each file freezes, for a handful of episodes with i.i.d. uniform meta-actions:
   row_of_step[T]        index on the S axis of the pre-state of step t (post-state is row+1)
   obs[T, MAXV, n_s], reward[T], done[T], agents_rewards/regional_rewards/agents_dones[T, MAXV],
   average_speed/traffic_speed/min_headway/merge_percent[T]       -- MergeEnv.step return values
+  avail_bits[T, MAXV]   per-agent _get_available_actions bitmask on the post-step state
   sh_<field>[T, 3, MAXV] per-sub-step shield record (ran, leader, front_adj, rear_adj,
                         constrain_adj, active, is_lc_safe, safe_acc, safe_steer, nom_acc, nom_steer)
   qp_{a,c_lead,c_adj,has_adj,lo,hi,u,active}[Q]                  -- every QP the reference posed
@@ -69,7 +70,7 @@ def run_case(name):
     n_s = env.n_s
     states, ep_start, acts, rows = [], [0], [], []
     outs = {k: [] for k in ("obs", "reward", "done", "agents_rewards", "regional_rewards", "agents_dones",
-                            "average_speed", "traffic_speed", "min_headway", "merge_percent")}
+                            "average_speed", "traffic_speed", "min_headway", "merge_percent", "avail_bits")}
     sh = {k: [] for k in SH_I + SH_F}
     qps = []
     arng = np.random.RandomState(aseed)
@@ -97,6 +98,12 @@ def run_case(name):
                 outs[k].append(p)
             for k in ("reward", "done", "average_speed", "traffic_speed", "min_headway", "merge_percent"):
                 outs[k].append(o[k])
+            # per-agent _get_available_actions (abstract.py:219-240) on the post-step state, as a bitmask
+            ab = np.zeros(M, np.int32)
+            for i, cv in enumerate(env.controlled_vehicles):
+                for act_id in env._get_available_actions(cv, env):
+                    ab[i] |= 1 << int(act_id)
+            outs["avail_bits"].append(ab)
             # shield records of this policy step, split by sub-step (order of execution per sub-step:
             # each CAV at most once, so a repeated vehicle id starts a new sub-step)
             log = rl.drain_shield_log()

@@ -81,6 +81,8 @@ def test_cuda_vs_golden_teacher_forced(mm, orc, name):
     act = torch.from_numpy(np.ascontiguousarray(g["act"])).cuda()
     _, _, _, v = env.step(act)
     got = outputs_to_numpy(v, OUT_F + OUT_I)
+    # per-agent action availability (abstract.py:219-240) against the reference's own _get_available_actions
+    assert np.array_equal(v["action_mask"].cpu().numpy().astype(np.int32), g["avail_bits"])
     post = env.get_state()
     compare_states(post, full_state(orc, g, rows + 1), STATE_TOL, name)
     check_outputs(got, {k: g[k] for k in OUT_F + OUT_I}, g["st_n_cav"][rows])
@@ -432,3 +434,32 @@ def test_masked_reset_stats_and_errors(mm, orc):
     plain.close()
     with pytest.raises(mm.MMError):
         mm.MergeEnvBatched(0, cfg)
+
+
+def test_action_masking_surface(mm):
+    """action_masking=True: batched view = per-agent bits; the single-env adapter reproduces the reference's
+    aliased-rows mask (`[[0] * n_a] * n`, abstract.py:475-479), i.e. the union over agents in every row."""
+    import torch
+    g, cfg = load_golden("mass_td3_srew")
+    c = dict(env_config(cfg), action_masking=True)
+    env = mm.make("merge-multi-agent-v1", config=c)
+    obs, mask = env.reset(is_training=False, testing_seeds=cfg["seeds"][0])
+    n = len(env.controlled_vehicles)
+    assert mask.shape == (n, 5) and (mask == mask[0]).all() and mask[0, 1] == 1
+    rows = g["row_of_step"]
+    for t in range(30):
+        obs, r, d, info = env.step(tuple(int(x) for x in g["act"][t, :n]))
+        bits = g["avail_bits"][t, :n]
+        union = int(np.bitwise_or.reduce(bits))
+        want = np.array([[(union >> a) & 1 for a in range(5)]] * n)
+        assert np.array_equal(info["action_mask"], want)
+    env.close()
+    b = mm.MergeEnvBatched(64, dict(c, traffic_density=3))
+    _, m = b.reset(seed=0)
+    assert m.shape == (64, 12, 5) and m.dtype == torch.int32
+    n_ag = b.buffers()["n_agents"]
+    live = torch.arange(12, device="cuda")[None, :] < n_ag[:, None]
+    assert bool((m[..., 1] == live.int()).all())          # IDLE exactly for live agents
+    assert bool((m[..., 2] == 0).all())                   # LANE_RIGHT is never available on this network
+    assert bool((m[live][:, 3] == 1).all() and (m[live][:, 4] == 1).all())   # spawn speed index is 3
+    b.close()
