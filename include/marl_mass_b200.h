@@ -51,6 +51,8 @@ typedef struct {
     double eta;              /* cbf_eta -> CBFType.GAMMA_B */
     double tau;              /* HEADWAY_TIME -> CBFType.TAU */
     double collision_reward, high_speed_reward, headway_cost, headway_time, merging_lane_cost;
+    int32_t env_v0;          /* 1: env id merge-multi-agent-v0 (MergeEnvMARL, merge_env_v1.py:389-408): MDPVehicle CAVs
+                                (no [-12.5, 6] acceleration clip, never shielded); obs columns 0..4 of each row */
 } mm_config;
 
 typedef struct mm_env mm_env;

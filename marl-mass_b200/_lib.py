@@ -33,7 +33,7 @@ class MMConfig(C.Structure):
                 ("traffic_type", C.c_int32), ("duration_steps", C.c_int32), ("substeps", C.c_int32),
                 ("dt", C.c_double), ("eta", C.c_double), ("tau", C.c_double),
                 ("collision_reward", C.c_double), ("high_speed_reward", C.c_double), ("headway_cost", C.c_double),
-                ("headway_time", C.c_double), ("merging_lane_cost", C.c_double)]
+                ("headway_time", C.c_double), ("merging_lane_cost", C.c_double), ("env_v0", C.c_int32)]
 
 
 class MMStateHost(C.Structure):

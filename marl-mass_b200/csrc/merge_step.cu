@@ -655,12 +655,12 @@ __device__ void vehicle_step(Env &ev, const StepParams &p, int i, int sub, size_
     if (f & FL_CRASHED) { steer = 0.0; acc = -1.0 * speed; }
     if (speed > 40.0) acc = fmin(acc, 1.0 * (40.0 - speed));
     else if (speed < -40.0) acc = fmax(acc, 1.0 * (40.0 - speed));
-    if (cav) acc = clipd(acc, ACC_LO, ACC_HI);
+    if (cav && !p.cfg.env_v0) acc = clipd(acc, ACC_LO, ACC_HI);   // MDPLCVehicle.clip_actions; MDPVehicle (v0) has none
     GF(F_ACT_STEER, i) = steer;
     GF(F_ACT_ACC, i) = acc;
     if (cav) {
         // get_safe_action gate (safe_controller.py:229-239)
-        if (p.cfg.shield != MM_SHIELD_NONE && (f & FL_FG) && fl_hist(f) >= 2) {
+        if (p.cfg.shield != MM_SHIELD_NONE && !p.cfg.env_v0 && (f & FL_FG) && fl_hist(f) >= 2) {
             ShieldRec rec;
             double nom_steer = steer, nom_acc = acc;
             shield(ev, p.cfg, i, steer, acc, rec);

@@ -34,26 +34,45 @@ DEFAULT_CONFIG = {
     "COLLISION_REWARD": 200, "HIGH_SPEED_REWARD": 1, "HEADWAY_COST": 4, "HEADWAY_TIME": 1.2,
     "MERGING_LANE_COST": 4, "traffic_density": 1, "safety_guarantee": "none", "lateral_control": "steer",
     "mixed_traffic": None, "traffic_type": "cav", "agent_reward": "default", "cbf_eta": 0.0,
-    "action_masking": False, "seed": 0,
+    "action_masking": False, "seed": 0, "env_name": "merge-multi-agent-v1",
 }
+ENV_IDS = ("merge-multi-agent-v1", "merge-multi-agent-v0")
+
+
+def traffic_type_of(cfg):
+    """cav | mixed as the env class resolves it (merge_env_v1.py:206-209 for v0, 476-495 for v1)."""
+    if cfg.get("env_name", "merge-multi-agent-v1") == "merge-multi-agent-v0":
+        return "cav" if cfg.get("mixed_traffic", True) is False else "mixed"
+    return cfg.get("traffic_type", "cav")
 
 
 def make_mm_config(cfg):
     """Reference config dict -> mm_config.  Raises ValueError exactly where the reference would
     (decentral_layer.py:817 unknown safety type; safe_controller.py:174 unsupported lateral control)."""
+    env_name = cfg.get("env_name", "merge-multi-agent-v1")
+    if env_name not in ENV_IDS:
+        raise KeyError("env id %r is not provided by marl_mass_b200 (available: %s)" % (env_name, list(ENV_IDS)))
+    v0 = env_name == "merge-multi-agent-v0"
     sg = cfg.get("safety_guarantee", "none")
     if sg in ("priority", "dmc"):
         raise ValueError("safety_guarantee %r (look-ahead baseline shields) is outside the batched hot path" % sg)
     if sg not in SHIELD:
         raise ValueError("Undefined safety_type:{0}".format(sg.split("-")[-1]))
-    if cfg.get("lateral_control", "steer") != "steer":
+    if cfg.get("lateral_control", "steer") != "steer" and not v0:
         raise AttributeError("Lateral control: {0} is not supported".format(cfg.get("lateral_control")))
-    tt = cfg.get("traffic_type", "cav")
+    if v0:
+        # MergeEnvMARL (merge_env_v1.py:389-408): MDPVehicle ignores safety_guarantee / lateral_control /
+        # agent_reward / traffic_type; vehicle counts follow `mixed_traffic` alone (merge_env_v1.py:206-209)
+        tt = "cav" if cfg.get("mixed_traffic", True) is False else "mixed"
+        sg, rk = "none", "default"
+    else:
+        tt = cfg.get("traffic_type", "cav")
+        rk = cfg.get("agent_reward", "default")
     if tt not in TRAFFIC:
         raise ValueError("traffic_type %r is not supported on the batched path (cav | mixed)" % (tt,))
     sim, pol = int(cfg["simulation_frequency"]), int(cfg["policy_frequency"])
     return _lib.MMConfig(
-        shield=SHIELD[sg], reward_kind=REWARD[cfg.get("agent_reward", "default")],
+        shield=SHIELD[sg], reward_kind=REWARD[rk], env_v0=int(v0),
         traffic_density=int(cfg["traffic_density"]), traffic_type=TRAFFIC[tt],
         duration_steps=int(cfg["duration"] * pol), substeps=sim // pol, dt=1 / sim,
         eta=float(cfg.get("cbf_eta", 0.0)), tau=float(cfg["HEADWAY_TIME"]),
@@ -83,6 +102,8 @@ class MergeEnvBatched(object):
         self.device = int(device)
         self.record_diag = bool(record_diag)
         self.T = int(self.config["duration"] * self.config["policy_frequency"])
+        self.v0 = self.config.get("env_name", "merge-multi-agent-v1") == "merge-multi-agent-v0"
+        self.n_s = 25 if self.v0 else NS   # Kinematics 5x5 (v0) vs KinematicLC 5x6 (v1)
         self._L = _lib.lib()
         self._h = C.c_void_p()
         _lib.check(self._L.mm_create(C.byref(make_mm_config(self.config)), self.n_envs, self.device,
@@ -155,7 +176,7 @@ class MergeEnvBatched(object):
         self._apply_config()
         seeds = list(seeds)
         assert len(seeds) == self.n_envs
-        st = _spawn.spawn_state(seeds, self.config["traffic_density"], self.config.get("traffic_type", "cav"), num_CAV)
+        st = _spawn.spawn_state(seeds, self.config["traffic_density"], traffic_type_of(self.config), num_CAV)
         self.set_state(st)
         v = self.buffers()
         return v["obs"], self.action_mask()
@@ -171,6 +192,14 @@ class MergeEnvBatched(object):
             return torch.ones((self.n_envs, MAXV, NA), dtype=torch.int32, device=dev)
         bits = self.buffers()["action_mask"].to(torch.int32)
         return (bits[:, :, None] >> torch.arange(NA, device=dev, dtype=torch.int32)[None, None, :]) & 1
+
+    def obs_view(self, obs=None):
+        """The observation as the env id defines it: [E, MAXV, 30] for v1; for v0 (Kinematics, no heading column)
+        columns 0..4 of each of the 5 rows, [E, MAXV, 25] (a copy)."""
+        obs = self.buffers()["obs"] if obs is None else obs
+        if not self.v0:
+            return obs
+        return obs.view(self.n_envs, MAXV, 5, 6)[..., :5].reshape(self.n_envs, MAXV, 25)
 
     def step(self, actions=None, auto_reset=False, stream=None):
         """One policy step for every env.  actions: int8 CUDA tensor [E, MAXV] (None: the `actions` view).
@@ -302,8 +331,12 @@ class MergeEnvLCMARL(object):
     n_a = NA
     n_s = NS
 
+    ENV_NAME = "merge-multi-agent-v1"
+
     def __init__(self, config=None, device=0):
+        config = dict(config or {}, env_name=self.ENV_NAME)
         self._b = MergeEnvBatched(1, config, device=device, record_diag=False)
+        self.n_s = self._b.n_s
         self.config = self._b.config
         self.seed = self.config.get("seed", 0)
         self.T = self._b.T
@@ -334,7 +367,7 @@ class MergeEnvLCMARL(object):
         self.controlled_vehicles = [_VehicleView(self, i) for i in range(n)]
         import torch
         torch.cuda.synchronize(self._b.device)
-        obs = self._b.buffers()["obs"][0, :n].double().cpu().numpy()
+        obs = self._b.obs_view()[0, :n].double().cpu().numpy()
         return obs, self._mask(n)
 
     def step(self, action):
@@ -349,7 +382,7 @@ class MergeEnvLCMARL(object):
         self._cache = None
         self.steps += 1
         st = self._state()
-        obs = v["obs"][0, :n].double().cpu().numpy()
+        obs = self._b.obs_view()[0, :n].double().cpu().numpy()
         reward = float(v["reward"][0])
         done = bool(v["done"][0])
         speeds = [float(st["speed"][0, i]) for i in range(n)]
@@ -389,7 +422,14 @@ class MergeEnvLCMARL(object):
         self._b.close()
 
 
-_REGISTRY = {"merge-multi-agent-v1": MergeEnvLCMARL}
+class MergeEnvMARL(MergeEnvLCMARL):
+    """Drop-in for gym.make('merge-multi-agent-v0') (merge_env_v1.py:389-408): un-shielded MDPVehicle CAVs,
+    IDMVehicle HDVs unless mixed_traffic is False, Kinematics 5x5 observation (n_s = 25)."""
+    ENV_NAME = "merge-multi-agent-v0"
+    n_s = 25
+
+
+_REGISTRY = {"merge-multi-agent-v1": MergeEnvLCMARL, "merge-multi-agent-v0": MergeEnvMARL}
 
 
 def make(env_id, **kwargs):

@@ -722,8 +722,8 @@ static void order_by_x_desc(const env_t *e, int *ord) {
 static void cav_step(const mo_config *cfg, env_t *e, int self, shield_rec *rec) {
     veh_t *v = &e->v[self];
     clip_actions(v);
-    v->act_acc = clipd(v->act_acc, -12.5, 6.0); /* safe_controller.py:100-104 */
-    if (cfg->shield == MO_SHIELD_NONE || !v->fg_set || v->hist_len < 2) { /* safe_controller.py:229-239 */
+    if (!cfg->env_v0) v->act_acc = clipd(v->act_acc, -12.5, 6.0); /* safe_controller.py:100-104; MDPVehicle (v0) steps with kinematics.py:122-141 */
+    if (cfg->env_v0 || cfg->shield == MO_SHIELD_NONE || !v->fg_set || v->hist_len < 2) { /* safe_controller.py:229-239 */
         v->safe_acc = v->act_acc;
         v->safe_steer = v->act_steer;
     } else {

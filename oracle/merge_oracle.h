@@ -39,6 +39,7 @@ typedef struct {
     double eta;              /* CBFType.GAMMA_B (cbf_eta) */
     double tau;              /* CBFType.TAU */
     double collision_reward, high_speed_reward, headway_cost, headway_time, merging_lane_cost;
+    int32_t env_v0;          /* 1: merge-multi-agent-v0 (MDPVehicle: no [-12.5, 6] acceleration clip, never shielded) */
 } mo_config;
 
 typedef struct {

@@ -35,7 +35,8 @@ class MoConfig(C.Structure):
     _fields_ = [("shield", C.c_int32), ("reward_kind", C.c_int32), ("duration_steps", C.c_int32),
                 ("substeps", C.c_int32), ("dt", C.c_double), ("eta", C.c_double), ("tau", C.c_double),
                 ("collision_reward", C.c_double), ("high_speed_reward", C.c_double),
-                ("headway_cost", C.c_double), ("headway_time", C.c_double), ("merging_lane_cost", C.c_double)]
+                ("headway_cost", C.c_double), ("headway_time", C.c_double), ("merging_lane_cost", C.c_double),
+                ("env_v0", C.c_int32)]
 
 
 class MoState(C.Structure):
@@ -76,8 +77,11 @@ def lib():
 def make_config(cfg):
     """cfg: dict with the reference's ENV_CONFIG keys (run_mappo.py:142-171)."""
     sim, pol = int(cfg.get("simulation_frequency", 15)), int(cfg.get("policy_frequency", 5))
+    v0 = cfg.get("env_name", "merge-multi-agent-v1") == "merge-multi-agent-v0"
     return MoConfig(
-        shield=SHIELD[cfg.get("safety_guarantee", "none")], reward_kind=REWARD[cfg.get("agent_reward", "default")],
+        env_v0=int(v0),
+        shield=0 if v0 else SHIELD[cfg.get("safety_guarantee", "none")],
+        reward_kind=0 if v0 else REWARD[cfg.get("agent_reward", "default")],
         duration_steps=int(cfg.get("duration", 20) * pol), substeps=sim // pol, dt=1 / sim,
         eta=float(cfg.get("cbf_eta", 0.0)), tau=float(cfg.get("HEADWAY_TIME", 1.2)),
         collision_reward=float(cfg.get("COLLISION_REWARD", 200)),
@@ -159,5 +163,6 @@ def state_from_golden(g, rows):
         st[k] = np.ascontiguousarray(g["st_" + k][rows], np.int32)
     for k in ENV_FIELDS:
         st[k] = np.ascontiguousarray(g["st_" + k][rows], np.int32)
-    # the kernels know two kinds only: shielded-capable CAV (MDPLCVehicle) and HDV (IDMVehicleHist)
+    # the engines know two kinds: CAV (MDPLCVehicle, or MDPVehicle in the v0 env) and HDV (IDMVehicle[Hist])
+    st["kind"] = np.where(st["kind"] == 3, 1, np.where(st["kind"] == 4, 2, st["kind"])).astype(np.int32)
     return st

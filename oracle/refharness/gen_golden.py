@@ -56,6 +56,11 @@ CASES = {
     "mass_td2_mixed_mrew": (dict(safety_guarantee="cbf-cav", traffic_density=2, mixed_traffic=True,
                                  traffic_type="mixed", agent_reward="mrew", HIGH_SPEED_REWARD=4,
                                  HEADWAY_COST=1, MERGING_LANE_COST=8), [150, 175], 108),
+    # BASELINE configs[0]: test-configs_marl-cav-unsafe.ini (env merge-multi-agent-v0: MDPVehicle, 5x5 observation)
+    "v0_unsafe_td1": (dict(env_name="merge-multi-agent-v0", safety_guarantee="none", traffic_density=1,
+                           HEADWAY_TIME=1.2, mixed_traffic=False), [0, 9, 13], 109),
+    "v0_unsafe_td2_mixed": (dict(env_name="merge-multi-agent-v0", safety_guarantee="none", traffic_density=2,
+                                 HEADWAY_TIME=1.2, mixed_traffic=True), [2, 8], 110),
 }
 
 SH_I = ("ran", "leader", "front_adj", "rear_adj", "constrain_adj", "active", "is_lc_safe")

@@ -20,3 +20,4 @@ def golden_dir():
 
 GOLDEN_CASES = ["unsafe_td1", "unsafe_td3", "unsafe_td2_mixed", "hss_td3", "hss_td3_mixed", "mass_td1",
                 "mass_td3_srew", "mass_td3_mixed", "mass_td2_mixed_mrew"]
+V0_CASES = ["v0_unsafe_td1", "v0_unsafe_td2_mixed"]

@@ -53,16 +53,27 @@ def used_mask(st):
     return np.arange(st["x"].shape[1])[None, :] < n
 
 
-def compare_states(got, want, tol, what=""):
+# the v0 env's vehicles (MDPVehicle / IDMVehicle) have no history, shield or flag attributes to compare
+V0_F64 = ("x", "y", "heading", "speed", "target_speed", "act_steer", "act_acc", "timer")
+V0_I32 = ("kind", "lane", "target_lane", "speed_index", "crashed")
+
+
+def obs25(obs):
+    """Kinematics (v0) view of a KinematicLC observation: drop the heading column of each of the 5 rows."""
+    obs = np.asarray(obs)
+    return obs.reshape(obs.shape[:-1] + (5, 6))[..., :5].reshape(obs.shape[:-1] + (25,))
+
+
+def compare_states(got, want, tol, what="", v0=False):
     """Discrete fields exact, continuous within tol (relative, floor 1); only live slots are compared."""
     m = used_mask(want)
     for k in ENV_FIELDS:
         assert np.array_equal(got[k], want[k]), "%s env field %s differs" % (what, k)
-    for k in I32_FIELDS:
+    for k in (V0_I32 if v0 else I32_FIELDS):
         bad = np.argwhere((got[k] != want[k]) & m)
         assert len(bad) == 0, "%s discrete field %s differs at %s" % (what, k, bad[:5].tolist())
     worst = 0.0
-    for k in F64_FIELDS:
+    for k in (V0_F64 if v0 else F64_FIELDS):
         if k == "rec1_x":
             continue
         err = rel_err(got[k], want[k]) * m

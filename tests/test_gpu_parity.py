@@ -5,9 +5,9 @@ and (b) the CPU oracle on seeded scenes.  Discrete outputs bit-exact; continuous
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_CASES
+from conftest import GOLDEN_CASES, V0_CASES
 from helpers import (ENV_FIELDS, F64_FIELDS, I32_FIELDS, LC_BOUNDARY_EPS, OUT_F, OUT_I, SH_F, SH_I, compare_states,
-                     load_golden, rel_err, used_mask)
+                     load_golden, obs25, rel_err, used_mask)
 
 pytestmark = pytest.mark.gpu
 
@@ -34,7 +34,7 @@ def orc():
 def env_config(cfg):
     keys = ("simulation_frequency", "policy_frequency", "duration", "COLLISION_REWARD", "HIGH_SPEED_REWARD",
             "HEADWAY_COST", "HEADWAY_TIME", "MERGING_LANE_COST", "traffic_density", "safety_guarantee",
-            "traffic_type", "agent_reward", "cbf_eta")
+            "traffic_type", "agent_reward", "cbf_eta", "env_name", "mixed_traffic")
     return {k: cfg[k] for k in keys}
 
 
@@ -463,3 +463,37 @@ def test_action_masking_surface(mm):
     assert bool((m[..., 2] == 0).all())                   # LANE_RIGHT is never available on this network
     assert bool((m[live][:, 3] == 1).all() and (m[live][:, 4] == 1).all())   # spawn speed index is 3
     b.close()
+
+
+@pytest.mark.parametrize("name", V0_CASES)
+def test_v0_env_cuda_vs_golden_and_adapter(mm, orc, name):
+    """BASELINE configs[0]: env merge-multi-agent-v0 (no shield, MDPVehicle, 5x5 observation) teacher-forced against
+    the reference, then whole episodes through make('merge-multi-agent-v0')."""
+    import torch
+    g, cfg = load_golden(name)
+    rows = g["row_of_step"]
+    env = mm.MergeEnvBatched(len(rows), env_config(cfg))
+    assert env.n_s == 25
+    env.set_state(full_state(orc, g, rows))
+    _, _, _, v = env.step(torch.from_numpy(np.ascontiguousarray(g["act"])).cuda())
+    got = outputs_to_numpy(v, OUT_F + OUT_I)
+    got["obs"] = obs25(got["obs"])
+    assert np.array_equal(env.obs_view().cpu().numpy(), got["obs"])
+    compare_states(env.get_state(), full_state(orc, g, rows + 1), STATE_TOL, name, v0=True)
+    check_outputs(got, {k: g[k] for k in OUT_F + OUT_I}, g["st_n_cav"][rows])
+    assert np.array_equal(v["action_mask"].cpu().numpy().astype(np.int32), g["avail_bits"])
+    env.close()
+    single = mm.make("merge-multi-agent-v0", config=env_config(cfg))
+    ep = g["ep_start"]
+    for j, seed in enumerate(cfg["seeds"]):
+        obs, mask = single.reset(is_training=False, testing_seeds=seed)
+        n = int(g["st_n_cav"][ep[j]])
+        assert obs.shape == (n, 25) and single.n_s == 25
+        done = False
+        for t in np.where((rows >= ep[j]) & (rows < ep[j + 1] - 1))[0]:
+            obs, reward, done, info = single.step(tuple(int(x) for x in g["act"][t, :n]))
+            assert rel_err(obs, g["obs"][t, :n]).max() <= 1e-5
+            assert abs(reward - g["reward"][t]) <= 1e-5 * max(1, abs(g["reward"][t]))
+            assert done == bool(g["done"][t])
+        assert done
+    single.close()

@@ -8,7 +8,7 @@ import sys
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_CASES, ROOT
+from conftest import GOLDEN_CASES, ROOT, V0_CASES
 from helpers import load_golden
 
 
@@ -76,6 +76,18 @@ def test_seed_exact_spawn_matches_reference_reset(name):
     rows = g["ep_start"][:-1]
     for k in _lib.F64_FIELDS + _lib.I32_FIELDS + _lib.ENV_FIELDS:
         assert np.array_equal(g["st_" + k][rows], st[k]), k
+
+
+@pytest.mark.parametrize("name", V0_CASES)
+def test_seed_exact_spawn_v0_env(name):
+    import marl_mass_b200 as mm
+    from marl_mass_b200.env import traffic_type_of
+    g, cfg = load_golden(name)
+    st = mm.spawn.spawn_state(cfg["seeds"], cfg["traffic_density"], traffic_type_of(cfg))
+    rows = g["ep_start"][:-1]
+    for k in ("x", "y", "speed", "target_speed", "timer", "lane", "target_lane", "n_veh", "n_cav", "n_merge"):
+        assert np.array_equal(g["st_" + k][rows], st[k]), k
+    assert np.array_equal(np.where(g["st_kind"][rows] == 3, 1, np.where(g["st_kind"][rows] == 4, 2, 0)), st["kind"])
 
 
 def test_spawn_num_cav_override_and_ranges():

@@ -9,9 +9,9 @@ import numpy as np
 import pytest
 
 import oracle as orc
-from conftest import GOLDEN_CASES
+from conftest import GOLDEN_CASES, V0_CASES
 from helpers import (ENV_FIELDS, F64_FIELDS, LC_BOUNDARY_EPS, OUT_F, OUT_I, SH_F, SH_I, compare_states,
-                     load_golden, rel_err)
+                     load_golden, obs25, rel_err)
 
 TOL = 1e-9
 ALL = (orc.F64_FIELDS, orc.I32_FIELDS, orc.ENV_FIELDS)
@@ -122,3 +122,29 @@ def test_fixture_inventory():
             assert (g["st_" + k] >= 0).all()
     assert {0, 1, 8}.issubset(seen_active), seen_active
     assert crashed >= 3 and vetoes > 1000 and hdv >= 4
+
+
+@pytest.mark.parametrize("name", V0_CASES)
+def test_v0_env_teacher_forced_and_free_running(name):
+    """BASELINE configs[0] (test-configs_marl-cav-unsafe.ini, env merge-multi-agent-v0): MDPVehicle CAVs without the
+    [-12.5, 6] acceleration clip, plain IDMVehicle HDVs, 5x5 Kinematics observation."""
+    g, cfg = load_golden(name)
+    assert cfg["n_s"] == 25
+    rows = g["row_of_step"]
+    st = golden_state(g, rows)
+    out = orc.step(cfg, st, g["act"], n_threads=4)
+    compare_states(st, golden_state(g, rows + 1), TOL, name, v0=True)
+    for k in OUT_I:
+        assert np.array_equal(out[k], g[k]), k
+    for k in OUT_F:
+        got = obs25(out[k]) if k == "obs" else out[k]
+        assert rel_err(got, g[k]).max() <= TOL, k
+    assert not out["sh_ran"].any()
+    ep = g["ep_start"]
+    for j in range(len(ep) - 1):
+        steps = np.where((rows >= ep[j]) & (rows < ep[j + 1] - 1))[0]
+        s1 = golden_state(g, [ep[j]])
+        for t in steps:
+            o = orc.step(cfg, s1, g["act"][t:t + 1])
+            assert int(o["done"][0]) == int(g["done"][t])
+        compare_states(s1, golden_state(g, [ep[j + 1] - 1]), 1e-7, "%s episode %d" % (name, j), v0=True)
