@@ -53,6 +53,9 @@ typedef struct {
     double collision_reward, high_speed_reward, headway_cost, headway_time, merging_lane_cost;
     int32_t env_v0;          /* 1: env id merge-multi-agent-v0 (MergeEnvMARL, merge_env_v1.py:389-408): MDPVehicle CAVs
                                 (no [-12.5, 6] acceleration clip, never shielded); obs columns 0..4 of each row */
+    int32_t steer_vel;       /* 1: lateral_control = steer_vel (safe_controller.py:84-98,124-150): steering angle is a
+                                state driven by a steering-velocity command; neighbour CAV headings are observed
+                                relative to the ego */
 } mm_config;
 
 typedef struct mm_env mm_env;
@@ -62,7 +65,8 @@ typedef struct mm_env mm_env;
  * Vehicle / ControlledVehicle / MDPLCVehicle / IDMVehicleHist attributes. */
 typedef struct {
     double *x, *y, *heading, *speed, *target_speed, *gvx, *rec1_x, *rec1_vx, *rec2_x, *rec2_vx,
-           *act_steer, *act_acc, *safe_steer, *safe_acc, *timer, *min_headway;     /* [n_envs][MM_MAXV] */
+           *act_steer, *act_acc, *safe_steer, *safe_acc, *timer, *min_headway,
+           *steering_angle;                                                        /* [n_envs][MM_MAXV] */
     int32_t *kind, *lane, *target_lane, *speed_index, *crashed, *hl_action, *hist_len, *fg_set,
             *is_collaborating, *is_lc_safe, *collaborate_adj;                        /* [n_envs][MM_MAXV] */
     int32_t *n_veh, *n_cav, *n_merge, *steps, *time;                                 /* [n_envs] */

@@ -14,7 +14,7 @@ NS = 30
 NA = 5
 
 F64_FIELDS = ("x", "y", "heading", "speed", "target_speed", "gvx", "rec1_x", "rec1_vx", "rec2_x", "rec2_vx",
-              "act_steer", "act_acc", "safe_steer", "safe_acc", "timer", "min_headway")
+              "act_steer", "act_acc", "safe_steer", "safe_acc", "timer", "min_headway", "steering_angle")
 I32_FIELDS = ("kind", "lane", "target_lane", "speed_index", "crashed", "hl_action", "hist_len", "fg_set",
               "is_collaborating", "is_lc_safe", "collaborate_adj")
 ENV_FIELDS = ("n_veh", "n_cav", "n_merge", "steps", "time")
@@ -33,7 +33,8 @@ class MMConfig(C.Structure):
                 ("traffic_type", C.c_int32), ("duration_steps", C.c_int32), ("substeps", C.c_int32),
                 ("dt", C.c_double), ("eta", C.c_double), ("tau", C.c_double),
                 ("collision_reward", C.c_double), ("high_speed_reward", C.c_double), ("headway_cost", C.c_double),
-                ("headway_time", C.c_double), ("merging_lane_cost", C.c_double), ("env_v0", C.c_int32)]
+                ("headway_time", C.c_double), ("merging_lane_cost", C.c_double), ("env_v0", C.c_int32),
+                ("steer_vel", C.c_int32)]
 
 
 class MMStateHost(C.Structure):

@@ -34,7 +34,7 @@ int fail(mm_status code, const char *what, cudaError_t ce = cudaSuccess) {
     } while (0)
 
 constexpr int MAX_CHUNKS = 8;
-constexpr int HOST_F64 = 16, HOST_I32 = 11, HOST_ENV = 5;
+constexpr int HOST_F64 = 17, HOST_I32 = 11, HOST_ENV = 5;
 
 }  // namespace
 
@@ -277,7 +277,7 @@ int mm_get_state(mm_env *env, mm_state_host *dst) {
     CUDA_OK(cudaDeviceSynchronize());
     double *fd[HOST_F64] = {dst->x, dst->y, dst->heading, dst->speed, dst->target_speed, dst->gvx, dst->rec1_x, dst->rec1_vx,
                             dst->rec2_x, dst->rec2_vx, dst->act_steer, dst->act_acc, dst->safe_steer, dst->safe_acc,
-                            dst->timer, dst->min_headway};
+                            dst->timer, dst->min_headway, dst->steering_angle};
     int32_t *id[HOST_I32] = {dst->kind, dst->lane, dst->target_lane, dst->speed_index, dst->crashed, dst->hl_action,
                              dst->hist_len, dst->fg_set, dst->is_collaborating, dst->is_lc_safe, dst->collaborate_adj};
     int32_t *ed[HOST_ENV] = {dst->n_veh, dst->n_cav, dst->n_merge, dst->steps, dst->time};
@@ -297,7 +297,7 @@ int mm_set_state(mm_env *env, const mm_state_host *src) {
     const size_t E = (size_t)env->n_envs, P = E * MAXV;
     const double *fd[HOST_F64] = {src->x, src->y, src->heading, src->speed, src->target_speed, src->gvx, src->rec1_x,
                                   src->rec1_vx, src->rec2_x, src->rec2_vx, src->act_steer, src->act_acc, src->safe_steer,
-                                  src->safe_acc, src->timer, src->min_headway};
+                                  src->safe_acc, src->timer, src->min_headway, src->steering_angle};
     const int32_t *id[HOST_I32] = {src->kind, src->lane, src->target_lane, src->speed_index, src->crashed, src->hl_action,
                                    src->hist_len, src->fg_set, src->is_collaborating, src->is_lc_safe, src->collaborate_adj};
     const int32_t *ed[HOST_ENV] = {src->n_veh, src->n_cav, src->n_merge, src->steps, src->time};

@@ -218,7 +218,7 @@ __device__ __forceinline__ int follow_road(int tlane, double px, double py) {
 }
 
 // MDPLCVehicle.act -> MDPVehicle.act -> ControlledVehicle.act (safe_controller.py:63-66, controller.py:293-311, 90-134)
-__device__ __noinline__ void cav_act(Env &ev, int i, int action, double &steer, double &acc) {
+__device__ __noinline__ void cav_act(Env &ev, int i, int action, bool steer_vel, double &steer, double &acc) {
     uint32_t f = FL(i);
     double px = X(i), py = Y(i), speed = V(i);
     if (action != A_NONE) f = fl_set(f, FL_HL_SHIFT, FL_3BIT, (uint32_t)action);
@@ -237,6 +237,9 @@ __device__ __noinline__ void cav_act(Env &ev, int i, int action, double &steer, 
     f = fl_set(f, FL_TLANE_SHIFT, FL_3BIT, (uint32_t)tl);
     FL(i) = f;
     steer = steering_control(px, py, H(i), speed, tl);
+    // MDPLCVehicle.steering_control in steer_vel mode: a steering velocity towards 1/8 of the reference angle
+    // (safe_controller.py:93-96), clipped like any steering command in ControlledVehicle.act (controller.py:131-133)
+    if (steer_vel) steer = clipd(20 * (steer * 0.125 - GF(F_STEERANG, i)), -MAX_STEER, MAX_STEER);
     acc = KP_A * (GF(F_TSPEED, i) - speed);
 }
 
@@ -622,6 +625,7 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
     if (veto) {
         f = fl_set(f, FL_TLANE_SHIFT, FL_3BIT, (uint32_t)elane);
         steer = steering_control(ex, ey, eh, espeed, elane);
+        if (cfg.steer_vel) steer = 20 * (steer * 0.125 - GF(F_STEERANG, self));   // not clipped on this path
         lc_safe = false;
     }
     f = constrain_adj ? (f | FL_COLLAB) : (f & ~FL_COLLAB);
@@ -684,12 +688,20 @@ __device__ void vehicle_step(Env &ev, const StepParams &p, int i, int sub, size_
         GF(F_SAFE_ACC, i) = acc;
     }
     // modified bicycle model (kinematics.py:133-140, safe_controller.py:151-172)
-    double t = 1.0 / 2 * m_tan(steer);
+    // steer_vel (safe_controller.py:124-150): the wheel angle is a state, the command is its rate, and the heading
+    // increment is not multiplied by dt (as written in the reference)
+    const bool sv = cav && p.cfg.steer_vel && !p.cfg.env_v0;
+    double wheel = steer;
+    if (sv) {
+        wheel = GF(F_STEERANG, i);
+        GF(F_STEERANG, i) = wheel + steer * dt;
+    }
+    double t = 1.0 / 2 * m_tan(wheel);
     double cb = 1.0 / sqrt(1.0 + t * t), sb = t * cb;           // cos / sin of the slip angle
     double c_hb = ch * cb - sh * sb, s_hb = sh * cb + ch * sb;  // cos / sin (heading + beta)
     double nx = X(i) + speed * c_hb * dt;
     double ny = Y(i) + speed * s_hb * dt;
-    double nh = heading + speed * sb / (VLEN / 2) * dt;
+    double nh = sv ? heading + speed * sb / (VLEN / 2) : heading + speed * sb / (VLEN / 2) * dt;
     double nv = fmax(0.0, speed + acc * dt);
     double2 scn = m_sincos(nh);
     if (cav) {
@@ -812,7 +824,8 @@ __device__ __forceinline__ bool is_terminal(const Env &ev, int steps, int durati
 // observation.py:241-273 + normalize_obs 181-193: ego row absolute, 4 nearest rows relative, no clipping.
 // The rows are float32 outputs, so lmap's divisions by the constant ranges are multiplications by the
 // reciprocals here (a <= 1-ulp float64 difference, invisible after rounding to float32).
-__device__ __noinline__ void observe_agent(const Env &ev, int self, const double *vx, const double *vy, float *obs) {
+__device__ __noinline__ void observe_agent(const Env &ev, int self, bool steer_vel, const double *vx, const double *vy,
+                                           float *obs) {
     const double KX = 2.0 / 300.0, KY = 2.0 / 24.0, KV = 2.0 / 90.0, KH = 2.0 / PI;
     double ex = X(self), ey = Y(self), evx = vx[self], evy = vy[self];
     uint32_t nb_ids;
@@ -829,7 +842,9 @@ __device__ __noinline__ void observe_agent(const Env &ev, int self, const double
             int o = (int)((nb_ids >> (4 * k)) & 15u);
             a = make_float2(1.0f, (float)(((X(o) - ex) + 150.0) * KX - 1.0));
             b = make_float2((float)(((Y(o) - ey) + 12.0) * KY - 1.0), (float)(((vx[o] - evx) + 45.0) * KV - 1.0));
-            c = make_float2((float)(((vy[o] - evy) + 45.0) * KV - 1.0), (float)((H(o) + PI / 2) * KH - 1.0));
+            double oh = H(o);
+            if (steer_vel && o < ev.n_cav) oh = oh - H(self);   // MDPLCVehicle.to_dict(origin) (safe_controller.py:75-81)
+            c = make_float2((float)(((vy[o] - evy) + 45.0) * KV - 1.0), (float)((oh + PI / 2) * KH - 1.0));
         }
         __stcs(dst + 3 * (k + 1), a);
         __stcs(dst + 3 * (k + 1) + 1, b);
@@ -952,7 +967,8 @@ __device__ __noinline__ void write_outputs(const Env &ev, const StepParams &p, s
         vx[i] = V(i) * GF(F_COSH, i);
         vy[i] = V(i) * GF(F_SINH, i);
     }
-    for (int i = 0; i < ev.n_cav; ++i) observe_agent(ev, i, vx, vy, obs + i * NS);
+    const bool sv = p.cfg.steer_vel && !p.cfg.env_v0;
+    for (int i = 0; i < ev.n_cav; ++i) observe_agent(ev, i, sv, vx, vy, obs + i * NS);
     float2 *z = reinterpret_cast<float2 *>(obs + ev.n_cav * NS);
     // rows of absent agents are zeroed when the scene is (re)built and n_cav is fixed for the episode, so the
     // per-step path does not rewrite them
@@ -1162,6 +1178,7 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
         steps = min(steps + 1, (int)EI_STEPS_MASK);  // abstract.py:457
     }
     bool running = valid;
+    const bool sv = p.cfg.steer_vel && !p.cfg.env_v0;
     // All-CAV envs: a CAV's act() reads and writes only its own state (controller.py:90-134), so it can run right
     // before that vehicle's step() instead of in a separate pass; the result is identical and the action never
     // leaves registers.  With HDVs present the two ordered passes are kept (MOBIL reads the others' target lanes).
@@ -1177,7 +1194,7 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
             if (apply_meta && !merged) {
                 for (int i = 0; i < ev.n_cav; ++i) {
                     double st_, ac_;
-                    cav_act(ev, i, meta_action(act_lo, act_mid, act_hi, i), st_, ac_);
+                    cav_act(ev, i, meta_action(act_lo, act_mid, act_hi, i), sv, st_, ac_);
                 }
             }
             ord = order_by_x_desc(ev);
@@ -1191,7 +1208,7 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
                     int i = (int)((ord >> (4 * q)) & 15u);
                     if (fl_kind(FL(i)) == MM_KIND_CAV) {
                         double st_, ac_;
-                        cav_act(ev, i, A_NONE, st_, ac_);
+                        cav_act(ev, i, A_NONE, sv, st_, ac_);
                         GF(F_ACT_STEER, i) = st_;
                         GF(F_ACT_ACC, i) = ac_;
                     } else {
@@ -1208,7 +1225,7 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
                 double st_, ac_;
                 if (merged) {
                     // sub-step 0 calls act(meta) and then act(None); the second call recomputes the same controls
-                    cav_act(ev, i, apply_meta ? meta_action(act_lo, act_mid, act_hi, i) : A_NONE, st_, ac_);
+                    cav_act(ev, i, apply_meta ? meta_action(act_lo, act_mid, act_hi, i) : A_NONE, sv, st_, ac_);
                 } else {
                     st_ = GF(F_ACT_STEER, i);
                     ac_ = GF(F_ACT_ACC, i);
@@ -1369,10 +1386,10 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ Re
 // state (un)packing between the env-major host mirror and the SoA planes
 // ------------------------------------------------------------------------------------------------
 // host mirror field order (mm_state_host): f64: x y heading speed target_speed gvx rec1_x rec1_vx rec2_x rec2_vx
-// act_steer act_acc safe_steer safe_acc timer min_headway; i32: kind lane target_lane speed_index crashed
+// act_steer act_acc safe_steer safe_acc timer min_headway steering_angle; i32: kind lane target_lane speed_index crashed
 // hl_action hist_len fg_set is_collaborating is_lc_safe collaborate_adj; env: n_veh n_cav n_merge steps time
-__constant__ int c_host_f64_to_field[16] = {F_X, F_Y, F_H, F_V, F_TSPEED, F_GVX, -1, F_REC1VX, F_REC2X, F_REC2VX,
-                                            F_ACT_STEER, F_ACT_ACC, F_SAFE_STEER, F_SAFE_ACC, F_TIMER, F_MINHW};
+__constant__ int c_host_f64_to_field[17] = {F_X, F_Y, F_H, F_V, F_TSPEED, F_GVX, -1, F_REC1VX, F_REC2X, F_REC2VX,
+                                            F_ACT_STEER, F_ACT_ACC, F_SAFE_STEER, F_SAFE_ACC, F_TIMER, F_MINHW, F_STEERANG};
 
 __global__ void pack_state_kernel(DevState st, int n_envs, const double *f64_em, const int32_t *i32_em,
                                   const int32_t *env_em) {
@@ -1381,7 +1398,7 @@ __global__ void pack_state_kernel(DevState st, int n_envs, const double *f64_em,
     if (idx >= E * MAXV) return;
     size_t e = idx / MAXV;
     int i = (int)(idx % MAXV);
-    for (int k = 0; k < 16; ++k) {
+    for (int k = 0; k < 17; ++k) {
         int fld = c_host_f64_to_field[k];
         if (fld >= 0) st.f64[f64_index(e, fld, i)] = f64_em[(size_t)k * E * MAXV + idx];
     }
@@ -1415,7 +1432,7 @@ __global__ void unpack_state_kernel(DevState st, int n_envs, double *f64_em, int
     if (idx >= E * MAXV) return;
     size_t e = idx / MAXV;
     int i = (int)(idx % MAXV);
-    for (int k = 0; k < 16; ++k) {
+    for (int k = 0; k < 17; ++k) {
         int fld = c_host_f64_to_field[k];
         if (fld < 0) fld = F_X;  // rec1_x == x (the record is taken right after the move)
         f64_em[(size_t)k * E * MAXV + idx] = st.f64[f64_index(e, fld, i)];

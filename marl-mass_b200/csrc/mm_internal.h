@@ -32,6 +32,7 @@ enum F64Field {
     F_TIMER,                         // IDMVehicle.timer
     F_MINHW,                         // MDPLCVehicle.min_headway
     F_COSH, F_SINH,                  // cos / sin of the current heading (derived; refreshed by every move)
+    F_STEERANG,                      // MDPLCVehicle.steering_angle (lateral_control = steer_vel only)
     F_COUNT
 };
 
@@ -96,7 +97,7 @@ struct ResetParams {
 void launch_step(const StepParams &p, bool diag, void *stream);
 void launch_reset(const ResetParams &p, void *stream);
 void launch_observe(const StepParams &p, void *stream);
-void launch_pack_state(const DevState &st, int n_envs, const double *f64_em /*[16][E][MAXV]*/,
+void launch_pack_state(const DevState &st, int n_envs, const double *f64_em /*[17][E][MAXV]*/,
                        const int32_t *i32_em /*[11][E][MAXV]*/, const int32_t *env_em /*[5][E]*/, void *stream);
 void launch_unpack_state(const DevState &st, int n_envs, double *f64_em, int32_t *i32_em, int32_t *env_em,
                          void *stream);

@@ -36,7 +36,7 @@ DEFAULT_CONFIG = {
     "mixed_traffic": None, "traffic_type": "cav", "agent_reward": "default", "cbf_eta": 0.0,
     "action_masking": False, "seed": 0, "env_name": "merge-multi-agent-v1",
 }
-ENV_IDS = ("merge-multi-agent-v1", "merge-multi-agent-v0")
+ENV_IDS = ("merge-multi-agent-v1", "merge-multi-agent-v0", "merge-multi-agent-v05")
 
 
 def traffic_type_of(cfg):
@@ -58,8 +58,9 @@ def make_mm_config(cfg):
         raise ValueError("safety_guarantee %r (look-ahead baseline shields) is outside the batched hot path" % sg)
     if sg not in SHIELD:
         raise ValueError("Undefined safety_type:{0}".format(sg.split("-")[-1]))
-    if cfg.get("lateral_control", "steer") != "steer" and not v0:
-        raise AttributeError("Lateral control: {0} is not supported".format(cfg.get("lateral_control")))
+    lat = cfg.get("lateral_control", "steer")
+    if lat not in ("steer", "steer_vel") and not v0:
+        raise AttributeError("Lateral control: {0} is not supported".format(lat))   # safe_controller.py:173-176
     if v0:
         # MergeEnvMARL (merge_env_v1.py:389-408): MDPVehicle ignores safety_guarantee / lateral_control /
         # agent_reward / traffic_type; vehicle counts follow `mixed_traffic` alone (merge_env_v1.py:206-209)
@@ -72,7 +73,7 @@ def make_mm_config(cfg):
         raise ValueError("traffic_type %r is not supported on the batched path (cav | mixed)" % (tt,))
     sim, pol = int(cfg["simulation_frequency"]), int(cfg["policy_frequency"])
     return _lib.MMConfig(
-        shield=SHIELD[sg], reward_kind=REWARD[rk], env_v0=int(v0),
+        shield=SHIELD[sg], reward_kind=REWARD[rk], env_v0=int(v0), steer_vel=int(lat == "steer_vel" and not v0),
         traffic_density=int(cfg["traffic_density"]), traffic_type=TRAFFIC[tt],
         duration_steps=int(cfg["duration"] * pol), substeps=sim // pol, dt=1 / sim,
         eta=float(cfg.get("cbf_eta", 0.0)), tau=float(cfg["HEADWAY_TIME"]),
@@ -103,7 +104,8 @@ class MergeEnvBatched(object):
         self.record_diag = bool(record_diag)
         self.T = int(self.config["duration"] * self.config["policy_frequency"])
         self.v0 = self.config.get("env_name", "merge-multi-agent-v1") == "merge-multi-agent-v0"
-        self.n_s = 25 if self.v0 else NS   # Kinematics 5x5 (v0) vs KinematicLC 5x6 (v1)
+        # Kinematics 5x5 (v0, v05: merge_env_v1.py:389-408, 527-550) vs KinematicLC 5x6 (v1)
+        self.n_s = NS if self.config.get("env_name", "merge-multi-agent-v1") == "merge-multi-agent-v1" else 25
         self._L = _lib.lib()
         self._h = C.c_void_p()
         _lib.check(self._L.mm_create(C.byref(make_mm_config(self.config)), self.n_envs, self.device,
@@ -195,9 +197,9 @@ class MergeEnvBatched(object):
 
     def obs_view(self, obs=None):
         """The observation as the env id defines it: [E, MAXV, 30] for v1; for v0 (Kinematics, no heading column)
-        columns 0..4 of each of the 5 rows, [E, MAXV, 25] (a copy)."""
+        columns 0..4 of each of the 5 rows, [E, MAXV, 25] (a copy); same for v05."""
         obs = self.buffers()["obs"] if obs is None else obs
-        if not self.v0:
+        if self.n_s == NS:
             return obs
         return obs.view(self.n_envs, MAXV, 5, 6)[..., :5].reshape(self.n_envs, MAXV, 25)
 
@@ -429,7 +431,15 @@ class MergeEnvMARL(MergeEnvLCMARL):
     n_s = 25
 
 
-_REGISTRY = {"merge-multi-agent-v1": MergeEnvLCMARL, "merge-multi-agent-v0": MergeEnvMARL}
+class MergeEnvMARLSteerVel(MergeEnvLCMARL):
+    """Drop-in for gym.make('merge-multi-agent-v05') (merge_env_v1.py:527-550): MDPLCVehicle dynamics (shields and
+    lateral_control apply) with the 5x5 Kinematics observation."""
+    ENV_NAME = "merge-multi-agent-v05"
+    n_s = 25
+
+
+_REGISTRY = {"merge-multi-agent-v1": MergeEnvLCMARL, "merge-multi-agent-v0": MergeEnvMARL,
+             "merge-multi-agent-v05": MergeEnvMARLSteerVel}
 
 
 def make(env_id, **kwargs):

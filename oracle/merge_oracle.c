@@ -34,7 +34,7 @@ static const int LANE_FORBIDDEN[N_LANES] = {0, 0, 1, 0, 1, 1};
 
 typedef struct {
     double x, y, heading, speed, target_speed, gvx, rec1_x, rec1_vx, rec2_x, rec2_vx;
-    double act_steer, act_acc, safe_steer, safe_acc, timer, min_headway;
+    double act_steer, act_acc, safe_steer, safe_acc, timer, min_headway, steering_angle;
     int kind, lane, target_lane, speed_index, crashed, hl_action, hist_len, fg_set;
     int is_collaborating, is_lc_safe, collaborate_adj;
 } veh_t;
@@ -198,6 +198,16 @@ static double steering_control(const veh_t *v, int target_lane) {
     return clipd(steering, -MAX_STEERING_ANGLE, MAX_STEERING_ANGLE);
 }
 
+/* safe_controller.py:84-98: MDPLCVehicle.steering_control — a steering VELOCITY in steer_vel mode */
+static double lc_steering_control(const veh_t *v, int target_lane, int steer_vel) {
+    double steering_ref = steering_control(v, target_lane);
+    if (steer_vel) {
+        steering_ref = steering_ref * 0.125;            /* STEER_TARGET_RF */
+        return 20 * (steering_ref - v->steering_angle); /* KP_STEER */
+    }
+    return steering_ref;
+}
+
 /* controller.py:136-144 */
 static void follow_road(veh_t *v) {
     if (lane_after_end(v->target_lane, v->x, v->y)) v->target_lane = next_lane(v->target_lane, v->x, v->y);
@@ -210,7 +220,7 @@ static int speed_to_index(double speed) {
 }
 
 /* controller.py:90-134 called with a meta action (or -1 for None), after MDPVehicle.act (293-311) */
-static void cav_act(veh_t *v, int action) {
+static void cav_act(veh_t *v, int action, int steer_vel) {
     if (action == A_FASTER || action == A_SLOWER) {
         int idx = speed_to_index(v->speed) + (action == A_FASTER ? 1 : -1);
         idx = idx < 0 ? 0 : (idx > 4 ? 4 : idx);
@@ -226,7 +236,7 @@ static void cav_act(veh_t *v, int action) {
             if (lane_is_reachable_from(L_BC0, v->x, v->y)) v->target_lane = L_BC0;
         }
     }
-    double steering = steering_control(v, v->target_lane);
+    double steering = lc_steering_control(v, v->target_lane, steer_vel);
     double acc = KP_A * (v->target_speed - v->speed);
     v->act_steer = clipd(steering, -MAX_STEERING_ANGLE, MAX_STEERING_ANGLE);
     v->act_acc = acc;
@@ -669,7 +679,7 @@ static void shield(const mo_config *cfg, env_t *e, int self, shield_rec *rec) {
     if (!mass) {
         if (!allowed) {
             v->target_lane = v->lane;
-            steer = steering_control(v, v->target_lane);
+            steer = lc_steering_control(v, v->target_lane, cfg->steer_vel);
             v->is_lc_safe = 0;
         }
     } else {
@@ -681,7 +691,7 @@ static void shield(const mo_config *cfg, env_t *e, int self, shield_rec *rec) {
         can_abort = can_abort && lane_on_lane(v->lane, cx, cy, 0);
         if (can_abort && !allowed) {
             v->target_lane = v->lane;
-            steer = steering_control(v, v->target_lane);
+            steer = lc_steering_control(v, v->target_lane, cfg->steer_vel);
             v->is_lc_safe = 0;
         } else if ((v->hl_action == A_LANE_RIGHT || v->hl_action == A_LANE_LEFT) && v->speed < 1.6667) {
             v_safe = v_ll;
@@ -730,7 +740,22 @@ static void cav_step(const mo_config *cfg, env_t *e, int self, shield_rec *rec) 
         shield(cfg, e, self, rec);
     }
     double beta;
-    integrate(v, v->safe_steer, v->safe_acc, cfg->dt, &beta);
+    if (cfg->steer_vel && !cfg->env_v0) {
+        /* safe_controller.py:124-150: the steering angle is a state driven by the steering velocity; note that
+           the heading increment is NOT multiplied by dt (as written in the reference) */
+        beta = atan(1.0 / 2 * tan(v->steering_angle));
+        double vx = v->speed * cos(v->heading + beta);
+        double vy = v->speed * sin(v->heading + beta);
+        v->x += vx * cfg->dt;
+        v->y += vy * cfg->dt;
+        double d_heading = v->speed * sin(beta) / (VEH_LENGTH / 2);
+        v->heading += d_heading;
+        v->speed += v->safe_acc * cfg->dt;
+        v->steering_angle += v->safe_steer * cfg->dt;
+        v->speed = fmax(0, v->speed);
+    } else {
+        integrate(v, v->safe_steer, v->safe_acc, cfg->dt, &beta);
+    }
     v->gvx = cos(v->heading + beta);
     v->fg_set = 1;
     v->lane = closest_lane_index(v->x, v->y, v->heading);
@@ -770,7 +795,7 @@ static int is_terminal(const mo_config *cfg, const env_t *e) {
 /* ---------------------------------------------------------------- observation / reward */
 
 /* observation.py:241-273 + 181-193, absolute=False, normalize=True, clip=False, "steer" mode */
-static void observe_agent(const env_t *e, int self, double *obs /* [MO_NS] */) {
+static void observe_agent(const env_t *e, int self, int steer_vel, double *obs /* [MO_NS] */) {
     const veh_t *a = &e->v[self];
     memset(obs, 0, sizeof(double) * MO_NS);
     double evx = a->speed * cos(a->heading), evy = a->speed * sin(a->heading);
@@ -788,6 +813,7 @@ static void observe_agent(const env_t *e, int self, double *obs /* [MO_NS] */) {
         r[3] = o->speed * cos(o->heading) - evx;
         r[4] = o->speed * sin(o->heading) - evy;
         r[5] = o->heading;
+        if (steer_vel && o->kind == MO_KIND_CAV) r[5] = o->heading - a->heading; /* safe_controller.py:75-81 */
     }
     for (int k = 0; k < n_rows; ++k) {
         double *o = obs + k * MO_OBS_FEATS;
@@ -917,7 +943,7 @@ static void load_env(const mo_state *s, int ei, env_t *e) {
         v->rec1_x = s->rec1_x[k]; v->rec1_vx = s->rec1_vx[k]; v->rec2_x = s->rec2_x[k]; v->rec2_vx = s->rec2_vx[k];
         v->act_steer = s->act_steer[k]; v->act_acc = s->act_acc[k];
         v->safe_steer = s->safe_steer[k]; v->safe_acc = s->safe_acc[k];
-        v->timer = s->timer[k]; v->min_headway = s->min_headway[k];
+        v->timer = s->timer[k]; v->min_headway = s->min_headway[k]; v->steering_angle = s->steering_angle[k];
         v->kind = s->kind[k]; v->lane = s->lane[k]; v->target_lane = s->target_lane[k];
         v->speed_index = s->speed_index[k]; v->crashed = s->crashed[k]; v->hl_action = s->hl_action[k];
         v->hist_len = s->hist_len[k]; v->fg_set = s->fg_set[k];
@@ -937,7 +963,7 @@ static void store_env(const mo_state *s, int ei, const env_t *e) {
         s->rec1_x[k] = v->rec1_x; s->rec1_vx[k] = v->rec1_vx; s->rec2_x[k] = v->rec2_x; s->rec2_vx[k] = v->rec2_vx;
         s->act_steer[k] = v->act_steer; s->act_acc[k] = v->act_acc;
         s->safe_steer[k] = v->safe_steer; s->safe_acc[k] = v->safe_acc;
-        s->timer[k] = v->timer; s->min_headway[k] = v->min_headway;
+        s->timer[k] = v->timer; s->min_headway[k] = v->min_headway; s->steering_angle[k] = v->steering_angle;
         s->kind[k] = v->kind; s->lane[k] = v->lane; s->target_lane[k] = v->target_lane;
         s->speed_index[k] = v->speed_index; s->crashed[k] = v->crashed; s->hl_action[k] = v->hl_action;
         s->hist_len[k] = v->hist_len; s->fg_set[k] = v->fg_set;
@@ -962,14 +988,14 @@ static void step_env(const mo_config *cfg, env_t *e, const int8_t *act, const mo
             /* action.py:226-231 -> safe_controller.py:63-66 -> controller.py:293-311 */
             for (int i = 0; i < e->n_cav; ++i) {
                 e->v[i].hl_action = act[i];
-                cav_act(&e->v[i], act[i]);
+                cav_act(&e->v[i], act[i], cfg->steer_vel && !cfg->env_v0);
             }
         }
         int ord[MAXV];
         order_by_x_desc(e, ord);
         for (int p = 0; p < e->n_veh; ++p) { /* road.py:269-278 */
             int i = ord[p];
-            if (e->v[i].kind == MO_KIND_CAV) cav_act(&e->v[i], -1);
+            if (e->v[i].kind == MO_KIND_CAV) cav_act(&e->v[i], -1, cfg->steer_vel && !cfg->env_v0);
             else hdv_act(e, i);
         }
         order_by_x_desc(e, ord); /* positions are unchanged by act(): same order (road.py:286) */
@@ -990,7 +1016,7 @@ static void step_env(const mo_config *cfg, env_t *e, const int8_t *act, const mo
     memset(local, 0, sizeof(local));
     double rsum = 0, ssum = 0, tsum = 0;
     for (int i = 0; i < e->n_cav; ++i) {
-        observe_agent(e, i, obs + i * MO_NS);
+        observe_agent(e, i, cfg->steer_vel && !cfg->env_v0, obs + i * MO_NS);
         local[i] = agent_reward(cfg, e, i);
         rsum += local[i];
         ssum += e->v[i].speed;
@@ -1067,12 +1093,12 @@ void mo_step(const mo_config *cfg, const mo_state *st, const int8_t *actions, co
     for (int t = 1; t < n_threads; ++t) pthread_join(tids[t], NULL);
 }
 
-void mo_observe(const mo_state *st, double *obs, int n_env) {
+void mo_observe(const mo_state *st, double *obs, int n_env, int steer_vel) {
     for (int ei = 0; ei < n_env; ++ei) {
         env_t e;
         load_env(st, ei, &e);
         double *o = obs + (size_t)ei * MAXV * MO_NS;
         memset(o, 0, sizeof(double) * MAXV * MO_NS);
-        for (int i = 0; i < e.n_cav; ++i) observe_agent(&e, i, o + i * MO_NS);
+        for (int i = 0; i < e.n_cav; ++i) observe_agent(&e, i, steer_vel, o + i * MO_NS);
     }
 }

@@ -40,11 +40,12 @@ typedef struct {
     double tau;              /* CBFType.TAU */
     double collision_reward, high_speed_reward, headway_cost, headway_time, merging_lane_cost;
     int32_t env_v0;          /* 1: merge-multi-agent-v0 (MDPVehicle: no [-12.5, 6] acceleration clip, never shielded) */
+    int32_t steer_vel;       /* 1: lateral_control = steer_vel (safe_controller.py:84-98, 124-150) */
 } mo_config;
 
 typedef struct {
     double *x, *y, *heading, *speed, *target_speed, *gvx, *rec1_x, *rec1_vx, *rec2_x, *rec2_vx,
-           *act_steer, *act_acc, *safe_steer, *safe_acc, *timer, *min_headway;
+           *act_steer, *act_acc, *safe_steer, *safe_acc, *timer, *min_headway, *steering_angle;
     int32_t *kind, *lane, *target_lane, *speed_index, *crashed, *hl_action, *hist_len, *fg_set,
             *is_collaborating, *is_lc_safe, *collaborate_adj;
     int32_t *n_veh, *n_cav, *n_merge, *steps, *time;   /* [n_env] */
@@ -67,7 +68,7 @@ void mo_step(const mo_config *cfg, const mo_state *st, const int8_t *actions, co
              int n_env, int n_threads);
 
 /* Observation only (reset() returns it): obs [n_env][MO_MAXV][MO_NS]. */
-void mo_observe(const mo_state *st, double *obs, int n_env);
+void mo_observe(const mo_state *st, double *obs, int n_env, int steer_vel);
 
 /* The QP alone: closed-form minimiser; returns u, writes the active-set code. */
 double mo_qp(double a, double c_lead, double c_adj, int has_adj, double lo, double hi, int32_t *active);

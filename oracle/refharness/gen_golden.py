@@ -61,6 +61,16 @@ CASES = {
                            HEADWAY_TIME=1.2, mixed_traffic=False), [0, 9, 13], 109),
     "v0_unsafe_td2_mixed": (dict(env_name="merge-multi-agent-v0", safety_guarantee="none", traffic_density=2,
                                  HEADWAY_TIME=1.2, mixed_traffic=True), [2, 8], 110),
+    # lateral_control = steer_vel (configs_marl-cav-heading-unsafe-steer_vel.ini, marl_cav_heading-t_headway-cbf-av-steer_vel.ini,
+    # configs_marl-cav-t_headway-unsafe-steer_vel.ini on env merge-multi-agent-v05)
+    "steervel_unsafe_td2": (dict(safety_guarantee="none", traffic_density=2, HEADWAY_TIME=1.2,
+                                 lateral_control="steer_vel"), [1, 2], 111),
+    "steervel_hss_td3_mixed": (dict(safety_guarantee="cbf-av", traffic_density=3, traffic_type="mixed",
+                                    mixed_traffic=True, lateral_control="steer_vel"), [3, 5], 112),
+    "steervel_mass_td2": (dict(safety_guarantee="cbf-cav", traffic_density=2, mixed_traffic=False,
+                               lateral_control="steer_vel"), [4, 6], 113),
+    "v05_steervel_unsafe_td1": (dict(env_name="merge-multi-agent-v05", safety_guarantee="none", traffic_density=1,
+                                     HEADWAY_TIME=1.2, lateral_control="steer_vel"), [7, 8], 114),
 }
 
 SH_I = ("ran", "leader", "front_adj", "rear_adj", "constrain_adj", "active", "is_lc_safe")

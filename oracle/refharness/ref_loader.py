@@ -166,7 +166,7 @@ def make_env(**overrides):
 # --------------------------------------------------------------------------------------
 MAXV = 12
 F64_FIELDS = ("x", "y", "heading", "speed", "target_speed", "gvx", "rec1_x", "rec1_vx", "rec2_x", "rec2_vx",
-              "act_steer", "act_acc", "safe_steer", "safe_acc", "timer", "min_headway")
+              "act_steer", "act_acc", "safe_steer", "safe_acc", "timer", "min_headway", "steering_angle")
 I32_FIELDS = ("kind", "lane", "target_lane", "speed_index", "crashed", "hl_action", "hist_len", "fg_set",
               "is_collaborating", "is_lc_safe", "collaborate_adj")
 
@@ -220,6 +220,7 @@ def export_state(env):
             out["is_lc_safe"][i] = int(v.is_lc_safe)
             out["collaborate_adj"][i] = int(bool(v.collaborate_adj))
             out["min_headway"][i] = v.min_headway
+            out["steering_angle"][i] = v.steering_angle
     out["n_veh"] = np.int32(len(vs))
     out["n_cav"] = np.int32(len(env.controlled_vehicles))
     out["n_merge"] = np.int32(env.n_merge)

@@ -7,7 +7,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 F64_FIELDS = ("x", "y", "heading", "speed", "target_speed", "gvx", "rec1_x", "rec1_vx", "rec2_x", "rec2_vx",
-              "act_steer", "act_acc", "safe_steer", "safe_acc", "timer", "min_headway")
+              "act_steer", "act_acc", "safe_steer", "safe_acc", "timer", "min_headway", "steering_angle")
 I32_FIELDS = ("kind", "lane", "target_lane", "speed_index", "crashed", "hl_action", "hist_len", "fg_set",
               "is_collaborating", "is_lc_safe")   # collaborate_adj is dead state
 ENV_FIELDS = ("n_veh", "n_cav", "n_merge", "steps", "time")

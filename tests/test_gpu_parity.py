@@ -34,7 +34,7 @@ def orc():
 def env_config(cfg):
     keys = ("simulation_frequency", "policy_frequency", "duration", "COLLISION_REWARD", "HIGH_SPEED_REWARD",
             "HEADWAY_COST", "HEADWAY_TIME", "MERGING_LANE_COST", "traffic_density", "safety_guarantee",
-            "traffic_type", "agent_reward", "cbf_eta", "env_name", "mixed_traffic")
+            "traffic_type", "agent_reward", "cbf_eta", "env_name", "mixed_traffic", "lateral_control")
     return {k: cfg[k] for k in keys}
 
 
@@ -81,6 +81,8 @@ def test_cuda_vs_golden_teacher_forced(mm, orc, name):
     act = torch.from_numpy(np.ascontiguousarray(g["act"])).cuda()
     _, _, _, v = env.step(act)
     got = outputs_to_numpy(v, OUT_F + OUT_I)
+    if cfg["n_s"] == 25:
+        got["obs"] = obs25(got["obs"])
     # per-agent action availability (abstract.py:219-240) against the reference's own _get_available_actions
     assert np.array_equal(v["action_mask"].cpu().numpy().astype(np.int32), g["avail_bits"])
     post = env.get_state()
@@ -92,7 +94,7 @@ def test_cuda_vs_golden_teacher_forced(mm, orc, name):
     env.close()
 
 
-@pytest.mark.parametrize("name", ["hss_td3", "mass_td3_mixed", "unsafe_td2_mixed"])
+@pytest.mark.parametrize("name", ["hss_td3", "mass_td3_mixed", "unsafe_td2_mixed", "steervel_hss_td3_mixed"])
 def test_cuda_free_running_episode(mm, orc, name):
     """Whole episodes on the GPU alone (state never re-synced) end on the reference's final state."""
     import torch
@@ -124,14 +126,17 @@ def test_cuda_free_running_episode(mm, orc, name):
 
 @pytest.mark.parametrize("shield,traffic,td,reward", [
     ("cbf-cav", "cav", 3, "default"), ("cbf-cav", "mixed", 3, "srew"), ("cbf-avs_cint", "cav", 3, "default"),
-    ("cbf-avs_cint", "mixed", 2, "mrew"), ("none", "mixed", 1, "default"), ("cbf-cav", "cav", 1, "mrew")])
+    ("cbf-avs_cint", "mixed", 2, "mrew"), ("none", "mixed", 1, "default"), ("cbf-cav", "cav", 1, "mrew"),
+    ("cbf-cav+steer_vel", "mixed", 3, "default")])
 def test_cuda_vs_oracle_seeded_rollout(mm, orc, shield, traffic, td, reward):
     """4096 device-spawned scenes, 40 policy steps of uniform random actions, CUDA and oracle advanced in lock
     step from the same start; state is re-synced from the oracle only when a discrete mismatch was excluded as
     a veto-boundary case (never observed so far)."""
     import torch
     E, T = 4096, 40
-    cfg = dict(mm.DEFAULT_CONFIG, safety_guarantee=shield, traffic_type=traffic, traffic_density=td,
+    lateral = "steer_vel" if shield.endswith("+steer_vel") else "steer"
+    shield = shield.split("+")[0]
+    cfg = dict(mm.DEFAULT_CONFIG, safety_guarantee=shield, lateral_control=lateral, traffic_type=traffic, traffic_density=td,
                agent_reward=reward, HEADWAY_TIME=0.5, cbf_eta=0.03125, HIGH_SPEED_REWARD=4, HEADWAY_COST=1,
                MERGING_LANE_COST=8)
     env = mm.MergeEnvBatched(E, cfg, record_diag=True)
@@ -139,7 +144,7 @@ def test_cuda_vs_oracle_seeded_rollout(mm, orc, shield, traffic, td, reward):
     st = env.get_state()
     ocfg = orc.make_config(cfg)
     obs0 = outputs_to_numpy(env.buffers(), ("obs",))["obs"]
-    assert rel_err(obs0, orc.observe(st)).max() <= F32_TOL
+    assert rel_err(obs0, orc.observe(st, steer_vel=(lateral == "steer_vel"))).max() <= F32_TOL
     rng = np.random.RandomState(7)
     alive = np.ones(E, bool)
     worst = 0.0
@@ -347,18 +352,18 @@ def test_batched_mappo_rollout(mm):
     env.close()
 
 
-@pytest.mark.parametrize("name", ["mass_td1", "hss_td3_mixed", "unsafe_td1"])
+@pytest.mark.parametrize("name", ["mass_td1", "hss_td3_mixed", "unsafe_td1", "steervel_mass_td2", "v05_steervel_unsafe_td1"])
 def test_single_env_adapter_replays_reference_episodes(mm, name):
     """Drop-in surface: make(...).reset(is_training=False, testing_seeds=s) / step(tuple) reproduce what the
     reference returned for the same seeds and actions, for whole episodes (obs, reward, done, info)."""
     g, cfg = load_golden(name)
     ep, rows = g["ep_start"], g["row_of_step"]
-    env = mm.make("merge-multi-agent-v1", config=env_config(cfg))
-    assert env.n_s == 30 and env.n_a == 5 and env.T == 100
+    env = mm.make(cfg["env_name"], config=env_config(cfg))
+    assert env.n_s == cfg["n_s"] and env.n_a == 5 and env.T == 100
     for j, seed in enumerate(cfg["seeds"]):
         obs, mask = env.reset(is_training=False, testing_seeds=seed)
         n = int(g["st_n_cav"][ep[j]])
-        assert obs.shape == (n, 30) and mask.shape == (n, 5) and mask.all()
+        assert obs.shape == (n, cfg["n_s"]) and mask.shape == (n, 5) and mask.all()
         assert len(env.controlled_vehicles) == n
         steps = np.where((rows >= ep[j]) & (rows < ep[j + 1] - 1))[0]
         # reset observation == the reference's first observation (oracle-free: golden obs of step 0 is post-step,

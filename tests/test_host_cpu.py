@@ -58,8 +58,9 @@ def test_config_mapping_and_error_behaviour():
         assert mm.make_mm_config(dict(mm.DEFAULT_CONFIG, safety_guarantee=sg)).shield == 1
     with pytest.raises(ValueError, match="Undefined safety_type"):   # decentral_layer.py:817
         mm.make_mm_config(dict(mm.DEFAULT_CONFIG, safety_guarantee="cbf-foo"))
-    with pytest.raises(AttributeError, match="Lateral control"):     # safe_controller.py:174
-        mm.make_mm_config(dict(mm.DEFAULT_CONFIG, lateral_control="steer_vel"))
+    with pytest.raises(AttributeError, match="Lateral control"):     # safe_controller.py:173-176
+        mm.make_mm_config(dict(mm.DEFAULT_CONFIG, lateral_control="torque"))
+    assert mm.make_mm_config(dict(mm.DEFAULT_CONFIG, lateral_control="steer_vel")).steer_vel == 1
     with pytest.raises(ValueError):
         mm.make_mm_config(dict(mm.DEFAULT_CONFIG, safety_guarantee="priority"))
     with pytest.raises(KeyError):
@@ -74,6 +75,7 @@ def test_seed_exact_spawn_matches_reference_reset(name):
     g, cfg = load_golden(name)
     st = mm.spawn.spawn_state(cfg["seeds"], cfg["traffic_density"], cfg["traffic_type"])
     rows = g["ep_start"][:-1]
+    assert "steering_angle" in _lib.F64_FIELDS
     for k in _lib.F64_FIELDS + _lib.I32_FIELDS + _lib.ENV_FIELDS:
         assert np.array_equal(g["st_" + k][rows], st[k]), k
 

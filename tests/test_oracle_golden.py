@@ -32,7 +32,8 @@ def test_teacher_forced_step(name):
     for k in OUT_I:
         assert np.array_equal(out[k], g[k]), k
     for k in OUT_F:
-        assert rel_err(out[k], g[k]).max() <= TOL, k
+        got = obs25(out[k]) if (k == "obs" and cfg["n_s"] == 25) else out[k]
+        assert rel_err(got, g[k]).max() <= TOL, k
     ran = g["sh_ran"] == 1
     assert np.array_equal(out["sh_ran"], g["sh_ran"])
     boundary = ran & (out["sh_lc_margin"] < LC_BOUNDARY_EPS)
@@ -67,7 +68,7 @@ def test_free_running_episodes(name):
         compare_states(st, golden_state(g, [last]), 1e-7, "%s episode %d" % (name, j))
 
 
-@pytest.mark.parametrize("name", [c for c in GOLDEN_CASES if not c.startswith("unsafe")])
+@pytest.mark.parametrize("name", [c for c in GOLDEN_CASES if "unsafe" not in c])
 def test_qp_known_answers(name):
     """Every QP the reference posed (G, h as built by cbf.py:288-322/374-422) -> same minimiser and active set."""
     g, _ = load_golden(name)
