@@ -178,3 +178,37 @@ def test_discounted_returns_match_reference_formula():
     assert lp.shape == (7, 5) and torch.allclose(lp.exp().sum(1), torch.ones(7), atol=1e-6)
     assert c(x, torch.nn.functional.one_hot(torch.arange(7) % 5, 5).float()).shape == (7, 1)
     assert sum(p.numel() for p in a.parameters()) == 30 * 128 + 128 + 128 * 128 + 128 + 128 * 5 + 5
+
+
+def test_shipped_ini_files_map_onto_the_batched_path():
+    """Every shipped marl/configs/*.ini except the look-ahead baseline shields (priority / dmc) and the all-HDV
+    evaluation env resolves to an mm_config.  Needs the reference tree (present in the build container only)."""
+    import configparser
+    import glob
+    import marl_mass_b200 as mm
+    cfg_dir = "/root/reference/marl/configs"
+    if not os.path.isdir(cfg_dir):
+        pytest.skip("reference tree not present")
+    ok, rejected = [], {}
+    for f in sorted(glob.glob(os.path.join(cfg_dir, "*.ini"))):
+        c = configparser.ConfigParser()
+        c.read(f)
+        e = c["ENV_CONFIG"]
+        cfg = dict(mm.DEFAULT_CONFIG, env_name=e.get("env_name", "merge-multi-agent-v0"),      # run_mappo.py:142
+                   safety_guarantee=e.get("safety_guarantee"), lateral_control=e.get("lateral_control", "steer"),
+                   mixed_traffic=c.getboolean("ENV_CONFIG", "mixed_traffic", fallback=None),
+                   traffic_type=e.get("traffic_type", "cav"), agent_reward=e.get("agent_reward", "default"),
+                   traffic_density=int(e["traffic_density"]), HEADWAY_TIME=float(e["HEADWAY_TIME"]),
+                   cbf_eta=float(e.get("cbf_eta", 0)),
+                   action_masking=c.getboolean("MODEL_CONFIG", "action_masking", fallback=False))
+        try:
+            mm.make_mm_config(cfg)
+            ok.append(os.path.basename(f))
+        except (ValueError, KeyError, AttributeError) as ex:
+            rejected[os.path.basename(f)] = str(ex)
+    assert len(ok) == 28 and len(rejected) == 9
+    assert all(("priority" in m) or ("dmc" in m) or ("hdv-v1" in m) for m in rejected.values())
+    for must in ("marl_cav-heading-t_headway-cbf-cav.ini", "marl_cav-heading-t_headway-cbf-avs_cint.ini",
+                 "marl_cav-heading-t_headway-cbf-cav-td3-srew.ini", "marl_cav-heading-t_headway-cbf-cav-mixed.ini",
+                 "test-configs_marl-cav-unsafe.ini", "marl_cav_heading-t_headway-cbf-av-steer_vel.ini"):
+        assert must in ok
