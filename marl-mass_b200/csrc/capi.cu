@@ -227,7 +227,7 @@ int mm_step_host(mm_env *env, const int8_t *actions, int auto_reset, float *obs,
     const int n_str = 4;
     int n_chunks = (E + chunk_target - 1) / chunk_target;
     if (n_chunks < 1) n_chunks = 1;
-    int chunk = ((E + n_chunks - 1) / n_chunks + TILE - 1) / TILE * TILE;
+    int chunk = ((E + n_chunks - 1) / n_chunks + 767) / 768 * 768;   // multiple of every supported tile size (32..384)
     for (int c = 0; c < n_chunks; ++c) {
         int off = c * chunk;
         if (off >= E) break;

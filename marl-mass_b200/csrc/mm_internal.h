@@ -19,7 +19,10 @@ namespace mm {
 
 constexpr int MAXV = MM_MAXV;
 constexpr int NS = MM_NS;
-constexpr int TILE = 128;   // envs per tile == threads per CTA of the step kernel
+#ifndef MM_TILE
+#define MM_TILE 128
+#endif
+constexpr int TILE = MM_TILE;   // envs per tile == threads per CTA of the step kernel
 
 enum F64Field {
     F_X = 0, F_Y, F_H, F_V,          // position, heading, speed            (staged in shared memory)
