@@ -28,6 +28,17 @@
 namespace mm {
 
 constexpr int BLOCK = TILE;
+// build-time experiment knobs (profiles/README.md)
+#ifndef MM_INL_A
+#define MM_INL_A __forceinline__   // closest_lane: one hot call site
+#endif
+#ifndef MM_INL_B
+#define MM_INL_B __forceinline__   // cav_act: measured -2 % inlined (profiles/README.md)
+#endif
+#ifndef MM_UNROLL_SCAN
+#define MM_UNROLL_SCAN 1
+#endif
+constexpr int UNROLL_SCAN = MM_UNROLL_SCAN;
 #ifndef MM_MIN_BLOCKS
 #define MM_MIN_BLOCKS 3   // CTAs per SM the step kernel is compiled for (register budget 65536 / (128 * n))
 #endif
@@ -169,7 +180,7 @@ __device__ __forceinline__ int lane_rid(int lane) { return lane == L_BC1 ? 1 : 0
 // road.py:51-65 + lane.py:102-108: first minimum over [ab0, bc0, bc1, cd0, jk0, kb0].
 // The five straight lanes share heading_at == 0, so one wrap_to_pi serves them; kb0 (last in argmin order)
 // is evaluated only if its heading-free lower bound can still beat the incumbent.
-__device__ __noinline__ int closest_lane(double px, double py, double heading) {
+__device__ MM_INL_A int closest_lane(double px, double py, double heading) {
     double ang0 = fabs(wrap_to_pi(heading - 0.0));
     int best = 0;
     double bd = CUDART_INF;
@@ -218,7 +229,7 @@ __device__ __forceinline__ int follow_road(int tlane, double px, double py) {
 }
 
 // MDPLCVehicle.act -> MDPVehicle.act -> ControlledVehicle.act (safe_controller.py:63-66, controller.py:293-311, 90-134)
-__device__ __noinline__ void cav_act(Env &ev, int i, int action, bool steer_vel, double &steer, double &acc) {
+__device__ MM_INL_B void cav_act(Env &ev, int i, int action, bool steer_vel, double &steer, double &acc) {
     uint32_t f = FL(i);
     double px = X(i), py = Y(i), speed = V(i);
     if (action != A_NONE) f = fl_set(f, FL_HL_SHIFT, FL_3BIT, (uint32_t)action);
@@ -428,6 +439,7 @@ __device__ __forceinline__ int close_vehicles(const Env &ev, int self, uint32_t 
     int n = 0;
     uint32_t ids = 0;
     double kth = CUDART_INF;  // current K-th smallest key
+#pragma unroll UNROLL_SCAN
     for (int j = 0; j < ev.n_veh; ++j) {
         if (j == self) continue;
         double ox = X(j), oy = Y(j);
@@ -778,6 +790,7 @@ __device__ __forceinline__ bool may_intersect(double adx, double ady, double aco
 __device__ __noinline__ void collision_pass(Env &ev) {
     for (int i = 0; i < ev.n_veh; ++i) {
         double ax = X(i), ay = Y(i);
+#pragma unroll UNROLL_SCAN
         for (int j = 0; j < ev.n_veh; ++j) {
             if (j == i) continue;
             if (FL(i) & FL_CRASHED) break;
