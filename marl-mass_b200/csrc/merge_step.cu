@@ -635,8 +635,12 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
         f = cond_a >= -1e-6 ? (f | FL_CADJ) : (f & ~FL_CADJ);
     }
     if (veto) {
+        // Re-steering towards the own lane is the nominal command itself when no lane change was under way (same
+        // lane, same state -> same expression); only a vehicle that was actually changing lanes pays for a second
+        // steering law.  (A crashed vehicle's nominal steering was zeroed by clip_actions, so it always recomputes.)
+        bool same_cmd = fl_tlane(f) == elane && !(f & FL_CRASHED) && !cfg.steer_vel;
         f = fl_set(f, FL_TLANE_SHIFT, FL_3BIT, (uint32_t)elane);
-        steer = steering_control(ex, ey, eh, espeed, elane);
+        steer = same_cmd ? act_steer : steering_control(ex, ey, eh, espeed, elane);
         if (cfg.steer_vel) steer = 20 * (steer * 0.125 - GF(F_STEERANG, self));   // not clipped on this path
         lc_safe = false;
     }
