@@ -193,7 +193,10 @@ __device__ MM_INL_A int closest_lane(double px, double py, double heading) {
     }
     double s = lane_s(L_KB0, px);
     double along = fmax(s - c_lane_len[L_KB0], 0.0) + fmax(0.0 - s, 0.0);
-    if (along < bd) {  // |r| >= 0 and angle >= 0, and fp addition is monotone: d >= along
+    // |r| >= 0 and angle >= 0 and fp addition is monotone, so d >= along; moreover |r| >= |y - 7.25| - 3.25 (the
+    // sine offset is at most the amplitude), which rules kb0 out for main-road vehicles driving alongside the ramp
+    // without evaluating the sine lane (1e-9 m of slack against the ~1e-15 rounding of the exact expression)
+    if (along < bd && along + (fabs(py - c_lane_sy[L_KB0]) - SINE_AMP) - 1e-9 < bd) {
         double r = lane_r(L_KB0, s, py);
         double ang = fabs(wrap_to_pi(heading - lane_heading_at(L_KB0, s)));
         double d = fabs(r) + fmax(s - c_lane_len[L_KB0], 0.0) + fmax(0.0 - s, 0.0) + 1.0 * ang;
