@@ -43,5 +43,21 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(name, defines, verbose=False):
+    """Experiment build: _build/variants/lib_<name>.so with extra -D knobs (select it with MM_LIB_PATH)."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    out_dir = os.path.join(OUT_DIR, "variants")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, "lib_%s.so" % name)
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-I", os.path.join(HERE, "..", "include"), "-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:   # python build.py --variant NAME [KNOB=VALUE ...]
+        k = sys.argv.index("--variant")
+        print(build_variant(sys.argv[k + 1], [a for a in sys.argv[k + 2:] if "=" in a], verbose="-v" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

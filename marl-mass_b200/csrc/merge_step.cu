@@ -77,7 +77,11 @@ constexpr double VLEN_SQ_GT = 0x1.9000000000001p+4;
 // The staged planes are addressed through the dynamic shared-memory symbol itself so that every function, inlined
 // or not, knows the address space (LDS/STS instead of generic LD/ST) and the per-thread view is a single index.
 constexpr int TOPK_MAX = 5;                                       // close_vehicles_to(count=5) in the shield
-constexpr int SMV = 11;                                           // staged slots: an env never has more than 11 vehicles
+#ifndef MM_TMA
+#define MM_TMA 1   // 1: hot planes move between HBM and shared memory as cp.async.bulk transactions; 0: per-thread loads
+#endif
+// staged slots: with bulk copies the same [slot][env] shape as the HBM tile; else 11 (an env never has more vehicles)
+constexpr int SMV = MM_TMA ? MAXV : 11;
 constexpr int SCRATCH_OFF = 4 * SMV * BLOCK + (SMV + 1) * BLOCK / 2;  // doubles: 4 f64 planes + the u32 flags plane
 extern __shared__ __align__(16) double sm_planes[];   // [4][SMV][BLOCK] f64 (x, y, heading, speed) + [SMV+1][BLOCK] u32 + top-K scratch
 struct Env {
@@ -955,6 +959,56 @@ __device__ __forceinline__ uint64_t order_by_x_desc(const Env &ev) {
 // ------------------------------------------------------------------------------------------------
 // the policy-step kernel
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// TMA bulk copies (cp.async.bulk, 1-D): the hot planes of a tile - x, y, heading, speed = the first four fields,
+// 48 KB contiguous, and the 6 KB flags plane - move between HBM and shared memory as two bulk transactions issued
+// by one thread, completion signalled on an mbarrier (load) / a bulk async-group (store).
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t HOT_F64_BYTES = 4u * MAXV * TILE * sizeof(double);
+constexpr uint32_t HOT_FLAG_BYTES = (uint32_t)MAXV * TILE * sizeof(uint32_t);
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tile_bulk_load(const DevState &st, size_t tile, uint64_t *mbar) {
+    // called by every thread of the CTA; thread 0 arms the barrier and issues the two copies
+    const uint32_t bar = smem_u32(mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double *g64 = st.f64 + tile * (size_t)F_COUNT * MAXV * TILE;
+        const uint32_t *gfl = st.flags + tile * (size_t)MAXV * TILE;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(HOT_F64_BYTES + HOT_FLAG_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(sm_planes)), "l"(g64), "r"(HOT_F64_BYTES), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(sm_planes + 4 * SMV * BLOCK)), "l"(gfl), "r"(HOT_FLAG_BYTES), "r"(bar) : "memory");
+    }
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar) : "memory");
+    }
+}
+
+__device__ __forceinline__ void tile_bulk_store(const DevState &st, size_t tile) {
+    // every thread: make its shared-memory writes visible to the async proxy, then one thread issues the copies
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double *g64 = st.f64 + tile * (size_t)F_COUNT * MAXV * TILE;
+        uint32_t *gfl = st.flags + tile * (size_t)MAXV * TILE;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     ::"l"(g64), "r"(smem_u32(sm_planes)), "r"(HOT_F64_BYTES) : "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     ::"l"(gfl), "r"(smem_u32(sm_planes + 4 * SMV * BLOCK)), "r"(HOT_FLAG_BYTES) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory may be released after this
+    }
+}
+
 __device__ __forceinline__ void load_env(Env &ev, const DevState &st, size_t e) {
     const uint32_t *fl = st.flags + flags_index(e, 0);
     for (int i = 0; i < ev.n_veh; ++i) {
@@ -1174,6 +1228,9 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
     ev.n_cav = 0;
     uint32_t ei = 0, act_lo = 0, act_mid = 0, act_hi = 0;
     int n_merge = 0, steps = 0, time = 0;
+    __shared__ uint64_t s_mbar;
+    const size_t tile = ((size_t)p.env_offset + (size_t)blockIdx.x * BLOCK) / TILE;   // launches are tile-aligned
+    if (MM_TMA) tile_bulk_load(p.st, tile, &s_mbar);
     if (valid) {
         ei = p.st.einfo[e];
         ev.n_veh = (ei >> EI_NVEH_SHIFT) & EI_4BIT;
@@ -1181,7 +1238,7 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
         n_merge = (ei >> EI_NMERGE_SHIFT) & EI_4BIT;
         steps = (ei >> EI_STEPS_SHIFT) & EI_STEPS_MASK;
         time = (ei >> EI_TIME_SHIFT) & EI_TIME_MASK;
-        load_env(ev, p.st, e);
+        if (!MM_TMA) load_env(ev, p.st, e);
         const uint32_t *a32 = reinterpret_cast<const uint32_t *>(p.actions + e * MAXV);  // 12 action bytes
         act_lo = a32[0]; act_mid = a32[1]; act_hi = a32[2];
         if (DIAG) {
@@ -1263,9 +1320,10 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
     PHASE_BARRIER(1);
     if (valid) {
         write_outputs(ev, p, e, steps, n_merge, true, stat_acc);
-        store_env(ev, p.st, e);
+        if (!MM_TMA) store_env(ev, p.st, e);
         p.st.einfo[e] = (ei & 0xfffu) | ((uint32_t)steps << EI_STEPS_SHIFT) | ((uint32_t)time << EI_TIME_SHIFT);
     }
+    if (MM_TMA) tile_bulk_store(p.st, tile);
     flush_stats(stat_acc, p.out.stats, (size_t)p.env_offset + (size_t)((blockIdx.x * BLOCK + tid) & ~31));
 }
 

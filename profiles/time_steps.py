@@ -17,4 +17,5 @@ for t in range(130):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(); env.step(acts[t % 4], auto_reset=True); b.record(); torch.cuda.synchronize()
     times.append(a.elapsed_time(b))
-print(name, E, "ms/step at t=0,1,2,5,10,20,40,60,80,99,100,110,129:", [round(times[i], 3) for i in (0, 1, 2, 5, 10, 20, 40, 60, 80, 99, 100, 110, 129)])
+import numpy as _np
+print(name, E, "steady(100..129) mean %.3f" % _np.mean(times[100:130]), "ms/step at t=0,1,2,5,10,20,40,60,80,99,100,110,129:", [round(times[i], 3) for i in (0, 1, 2, 5, 10, 20, 40, 60, 80, 99, 100, 110, 129)])
