@@ -201,8 +201,10 @@ __device__ MM_INL_A int closest_lane(double px, double py, double heading) {
     // sine offset is at most the amplitude), which rules kb0 out for main-road vehicles driving alongside the ramp
     // without evaluating the sine lane (1e-9 m of slack against the ~1e-15 rounding of the exact expression)
     if (along < bd && along + (fabs(py - c_lane_sy[L_KB0]) - SINE_AMP) - 1e-9 < bd) {
-        double r = lane_r(L_KB0, s, py);
-        double ang = fabs(wrap_to_pi(heading - lane_heading_at(L_KB0, s)));
+        // lane_r and lane_heading_at of the sine lane at the same s: one sincos serves both
+        double2 sc = m_sincos(SINE_PULS * s + SINE_PHASE);
+        double r = (py - c_lane_sy[L_KB0]) - SINE_AMP * sc.x;
+        double ang = fabs(wrap_to_pi(heading - m_atan(SINE_AMP * SINE_PULS * sc.y)));
         double d = fabs(r) + fmax(s - c_lane_len[L_KB0], 0.0) + fmax(0.0 - s, 0.0) + 1.0 * ang;
         if (d < bd) best = L_KB0;
     }
@@ -258,7 +260,9 @@ __device__ MM_INL_B void cav_act(Env &ev, int i, int action, bool steer_vel, dou
     // MDPLCVehicle.steering_control in steer_vel mode: a steering velocity towards 1/8 of the reference angle
     // (safe_controller.py:93-96), clipped like any steering command in ControlledVehicle.act (controller.py:131-133)
     if (steer_vel) steer = clipd(20 * (steer * 0.125 - GF(F_STEERANG, i)), -MAX_STEER, MAX_STEER);
-    acc = KP_A * (GF(F_TSPEED, i) - speed);
+    // a CAV's target_speed is always index_to_speed(speed_index) (controller.py:281-283, 302-307): same double as the
+    // stored field, without the L2 round trip
+    acc = KP_A * ((10.0 + (int)((f >> FL_SIDX_SHIFT) & FL_3BIT) * (30.0 - 10.0) / 4) - speed);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -405,16 +409,6 @@ __device__ __forceinline__ double solve_cbf_qp(double a, double c_lead, double c
     return u;
 }
 
-// decentral_layer.py:23-39.  Only the b->c road has two lanes, so adjacency can only arise through lane l1 itself
-// when it is bc0/bc1, else through its next lane nl = next_lane(l1, position); the result is
-// (index of that lane on the road) - (index of l2) when both are bc lanes and differ, else 0.
-__device__ __forceinline__ int is_adj_lane(int l1, int nl, int l2) {
-    bool l1_bc = (l1 == L_BC0) | (l1 == L_BC1);
-    int eff = l1_bc ? l1 : nl;
-    bool eff_bc = (eff == L_BC0) | (eff == L_BC1), l2_bc = (l2 == L_BC0) | (l2 == L_BC1);
-    return (eff_bc & l2_bc & (eff != l2)) ? (eff == L_BC1 ? 1 : -1) : 0;
-}
-
 // controller.py:257-267; left: dir == "L".  cos/sin(+-alpha + heading) by angle addition from the cached cos/sin of
 // the heading (alpha = atan(WIDTH / LENGTH) = atan(0.4): cos = 5/sqrt(29), sin = 2/sqrt(29)).
 __device__ __forceinline__ void get_corner(double px, double py, double ch, double sh, bool left, double &cx, double &cy) {
@@ -475,21 +469,23 @@ __device__ __forceinline__ int close_vehicles(const Env &ev, int self, uint32_t 
 
 // safety_layer -> safe_action_hss / safe_action_mass (decentral_layer.py:767-817, 290-518, 521-764) with
 // multi_agent_state (85-257) and CBF_AV / CBF_CAV (cbf.py:197-430).  Returns the shielded (steer, acc).
-__device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, double &out_steer, double &out_acc,
-                                    ShieldRec &rec) {
+// `act_steer`, `act_acc`: the clipped nominal action; `rec1vx`, `ge`: the ego's last logged vx and fg g.vx (the caller
+// has them in registers already).  WITH_MARGIN: also report the veto margin (diagnostic builds only).
+template <bool WITH_MARGIN>
+__device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, double act_steer, double act_acc, double rec1vx,
+                                    double ge, double &out_steer, double &out_acc, ShieldRec &rec) {
     const double dt = cfg.dt, eta = cfg.eta, tau = cfg.tau;
     const bool mass = cfg.shield == MM_SHIELD_MASS;
     uint32_t f = FL(self);
     const int elane = fl_lane(f);
     const double ex = X(self), ey = Y(self), eh = H(self), espeed = V(self);
-    const double act_acc = GF(F_ACT_ACC, self), act_steer = GF(F_ACT_STEER, self);
 
     double v_min = espeed + ACC_LO * dt;
     if (mass) v_min = fmax(0.0, v_min);
     double v_max = espeed + ACC_HI * dt;
     // to_dict()["vx"] = speed * cos(heading): for a vehicle that has not crashed this is bit-for-bit the value its
     // last log_step recorded (same operands), so the record is reused instead of a cosine
-    double evx_raw = (f & FL_CRASHED) ? espeed * GF(F_COSH, self) : GF(F_REC1VX, self);
+    double evx_raw = (f & FL_CRASHED) ? espeed * GF(F_COSH, self) : rec1vx;
     double evx = evx_raw > 1 ? evx_raw : 1;
     double es = lane_s(elane, ex);
 
@@ -502,20 +498,37 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
     uint32_t nb_ids;
     int n_nb = close_vehicles<5>(ev, self, nb_ids);
     const int e_next = next_lane(elane, ex, ey);
+    // is_adj_lane(ego, other) (decentral_layer.py:23-39) can only be non-zero through the two-lane b->c road: the ego
+    // side is its own lane when that is bc0/bc1, else its next lane
+    const bool elane_bc = (elane == L_BC0) | (elane == L_BC1);
+    const int e_eff = elane_bc ? elane : e_next;
+    const bool e_eff_bc = (e_eff == L_BC0) | (e_eff == L_BC1);
+    const bool all_cav = ev.n_cav == ev.n_veh;
 #pragma unroll 1
     for (int k = 0; k < n_nb; ++k) {
         int o = (int)((nb_ids >> (4 * k)) & 15u);
+        double ox = X(o);
+        double d = lane_s(elane, ox) - es;
+        // A vehicle behind can only become the rear-adjacent one, a CAV ahead only front-adjacent or leader: skip
+        // the classification when those roles are taken (HDVs ahead always run it: the on-ramp branch has side effects)
+        if (d < 0 ? has_oar : (all_cav && has_oa && has_ol)) continue;
         uint32_t fo = FL(o);
         int olane = fl_lane(fo);
-        double ox = X(o), oy = Y(o), oh = H(o);
+        double oy = Y(o);
         bool o_cav = fl_kind(fo) == MM_KIND_CAV;
-        int v_a = is_adj_lane(elane, e_next, olane);
-        int a_v = is_adj_lane(olane, next_lane(olane, ox, oy), elane);
-        double d = lane_s(elane, ox) - es;
+        const bool olane_bc = (olane == L_BC0) | (olane == L_BC1);
+        int v_a = (e_eff_bc & olane_bc & (e_eff != olane)) ? (e_eff == L_BC1 ? 1 : -1) : 0;
+        int a_v = 0;
+        if (elane_bc) {   // the other side: its lane if bc0/bc1, else its next lane (only ab0 / kb0 lead into b->c)
+            int o_eff = olane;
+            if (olane == L_AB0 || olane == L_KB0) o_eff = next_lane(olane, ox, oy);
+            bool o_eff_bc = (o_eff == L_BC0) | (o_eff == L_BC1);
+            a_v = (o_eff_bc & (o_eff != elane)) ? (o_eff == L_BC1 ? 1 : -1) : 0;
+        }
         // is_approaching_same_lane (decentral_layer.py:46-57)
         bool approaching = false;
         if (!(d < 0)) {
-            double y_dist = oy - ey;
+            double y_dist = oy - ey, oh = H(o);
             bool hc = y_dist < 0 ? (oh > 0.037) : (oh < -0.037);
             approaching = fabs(y_dist) <= 3.5 && hc;
         }
@@ -594,7 +607,7 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
     if (has_adj) q_lona = -VLEN - sd_l - 2.0134;
     double q_lonr = -VLEN - sd_r;
 
-    double ge_dt = GF(F_GVX, self) * dt, gol_dt = g_ol * dt, goa_dt = g_oa * dt, gr_dt = 1 * dt;
+    double ge_dt = ge * dt, gol_dt = g_ol * dt, goa_dt = g_oa * dt, gr_dt = 1 * dt;
     double dl = -ex + x_ol, da = -ex + x_oa, dr = ex + -x_oar;
     double c_lead = dl + (eta - 1) * dl + eta * q_lon + (-(ge_dt * v_ll) + gol_dt * v_ol);
     double c_adj = 0.0;
@@ -616,7 +629,7 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
     // arithmetic and rounding noise in float64; it counts as satisfied (as an interior-point solve would give).
     bool adj_inv_ok = (active == MM_ACT_ADJ) ? true : (cond_a >= 0);
     bool allowed = (hls_a >= 0 && adj_inv_ok) && (hls_r >= 0 && cond_r >= 0);
-    rec.lc_margin = fmin(fmin(fabs(hls_a), fabs(cond_a)), fmin(fabs(hls_r), fabs(cond_r)));
+    if (WITH_MARGIN) rec.lc_margin = fmin(fmin(fabs(hls_a), fabs(cond_a)), fmin(fabs(hls_r), fabs(cond_r)));
 
     double steer = act_steer;
     bool lc_safe = true;
@@ -670,13 +683,16 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
 // heading refreshes the cache and gives g.vx = cos(heading' + beta) and the logged vx.  That is 2 libm calls per
 // move instead of 6 (tan, atan, sincos, sin, cos, cos), each result within a few ulp of the reference's chain.
 template <bool DIAG>
-__device__ void vehicle_step(Env &ev, const StepParams &p, int i, int sub, size_t e_glob, double *stat_acc, double steer,
-                             double acc) {
+__device__ void vehicle_step(Env &ev, const StepParams &p, int i, int sub, size_t e_glob, uint32_t &shield_counts,
+                             double steer, double acc) {
     uint32_t f = FL(i);
     const bool cav = fl_kind(f) == MM_KIND_CAV;
     const double dt = p.cfg.dt;
     const double speed = V(i), heading = H(i);
     const double ch = GF(F_COSH, i), sh = GF(F_SINH, i), rec1vx = GF(F_REC1VX, i);   // issued early: L2 latency
+    const bool shielded = cav && p.cfg.shield != MM_SHIELD_NONE && !p.cfg.env_v0 && (f & FL_FG) && fl_hist(f) >= 2;
+    double ge = 0.0;
+    if (shielded) ge = GF(F_GVX, i);
     if (!cav) GF(F_TIMER, i) = GF(F_TIMER, i) + dt;
     // clip_actions
     if (f & FL_CRASHED) { steer = 0.0; acc = -1.0 * speed; }
@@ -687,14 +703,13 @@ __device__ void vehicle_step(Env &ev, const StepParams &p, int i, int sub, size_
     GF(F_ACT_ACC, i) = acc;
     if (cav) {
         // get_safe_action gate (safe_controller.py:229-239)
-        if (p.cfg.shield != MM_SHIELD_NONE && !p.cfg.env_v0 && (f & FL_FG) && fl_hist(f) >= 2) {
+        if (shielded) {
             ShieldRec rec;
             double nom_steer = steer, nom_acc = acc;
-            shield(ev, p.cfg, i, steer, acc, rec);
+            shield<DIAG>(ev, p.cfg, i, nom_steer, nom_acc, rec1vx, ge, steer, acc, rec);
             f = FL(i);
-            stat_acc[ST_SOLVES] += 1;
-            stat_acc[ST_ACTIVE] += rec.active != 0;
-            stat_acc[ST_VETOES] += !rec.is_lc_safe;
+            // solves / active / vetoes of this policy step: three 10-bit counters in one register (<= 33 each)
+            shield_counts += 1u | ((uint32_t)(rec.active != 0) << 10) | ((uint32_t)(!rec.is_lc_safe) << 20);
             if (DIAG) {
                 size_t plane = (size_t)p.n_envs * 3 * MAXV;
                 size_t idx = (e_glob * 3 + sub) * MAXV + i;
@@ -1255,6 +1270,7 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
         steps = min(steps + 1, (int)EI_STEPS_MASK);  // abstract.py:457
     }
     bool running = valid;
+    uint32_t shield_counts = 0;
     const bool sv = p.cfg.steer_vel && !p.cfg.env_v0;
     // All-CAV envs: a CAV's act() reads and writes only its own state (controller.py:90-134), so it can run right
     // before that vehicle's step() instead of in a separate pass; the result is identical and the action never
@@ -1307,7 +1323,7 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
                     st_ = GF(F_ACT_STEER, i);
                     ac_ = GF(F_ACT_ACC, i);
                 }
-                vehicle_step<DIAG>(ev, p, i, sub < 3 ? sub : 2, e, stat_acc, st_, ac_);
+                vehicle_step<DIAG>(ev, p, i, sub < 3 ? sub : 2, e, shield_counts, st_, ac_);
             }
         }
         PHASE_BARRIER(2);
@@ -1318,6 +1334,9 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
         }
     }
     PHASE_BARRIER(1);
+    stat_acc[ST_SOLVES] = (double)(shield_counts & 1023u);
+    stat_acc[ST_ACTIVE] = (double)((shield_counts >> 10) & 1023u);
+    stat_acc[ST_VETOES] = (double)((shield_counts >> 20) & 1023u);
     if (valid) {
         write_outputs(ev, p, e, steps, n_merge, true, stat_acc);
         if (!MM_TMA) store_env(ev, p.st, e);
