@@ -76,19 +76,21 @@ constexpr double VLEN_SQ_GT = 0x1.9000000000001p+4;
 // ------------------------------------------------------------------------------------------------
 // The staged planes are addressed through the dynamic shared-memory symbol itself so that every function, inlined
 // or not, knows the address space (LDS/STS instead of generic LD/ST) and the per-thread view is a single index.
-constexpr int TOPK_MAX = 5;                                       // close_vehicles_to(count=5) in the shield
 #ifndef MM_TMA
 #define MM_TMA 1   // 1: hot planes move between HBM and shared memory as cp.async.bulk transactions; 0: per-thread loads
 #endif
 // staged slots: with bulk copies the same [slot][env] shape as the HBM tile; else 11 (an env never has more vehicles)
 constexpr int SMV = MM_TMA ? MAXV : 11;
-constexpr int SCRATCH_OFF = 4 * SMV * BLOCK + (SMV + 1) * BLOCK / 2;  // doubles: 4 f64 planes + the u32 flags plane
-extern __shared__ __align__(16) double sm_planes[];   // [4][SMV][BLOCK] f64 (x, y, heading, speed) + [SMV+1][BLOCK] u32 + top-K scratch
+constexpr int PLANES_F64 = 4 * SMV * BLOCK + (SMV + 1) * BLOCK / 2;   // doubles: 4 f64 planes + the u32 flags plane
+extern __shared__ __align__(16) double sm_planes[];   // [4][SMV][BLOCK] f64 (x, y, heading, speed) + [SMV+1][BLOCK] u32
 struct Env {
     int tid;                    // threadIdx.x: column of this env inside the CTA's planes
     double *g;                  // this env's column of its tile; element (f, i) at [(f*MAXV+i)*TILE]
     int n_veh, n_cav;
+    uint64_t live;              // slot ids by current x, descending, 4 bits each (kept sorted after every move)
+    uint64_t pos;               // inverse: nibble i = position of slot i in `live`
 };
+__device__ __forceinline__ int nib(uint64_t w, int k) { return (int)((w >> (4 * k)) & 15ull); }
 
 #define X(i) (sm_planes[(0 * SMV + (i)) * BLOCK + ev.tid])
 #define Y(i) (sm_planes[(1 * SMV + (i)) * BLOCK + ev.tid])
@@ -426,45 +428,92 @@ struct ShieldRec {
 };
 
 // road.py:257-267: the `count` nearest (by |longitudinal offset in the ego lane|, stable) among vehicles
-// closer than 180 m.  The sorted keys live in a per-thread column of a small shared-memory scratch plane (dynamic
-// indexing is free there; a register-resident insertion network was 15-27 % of all issued instructions), the ids
-// in one packed register, 4 bits each, nearest first.  Returns the count (<= K) and the packed ids.
-#define TOPK(k) (sm_planes[SCRATCH_OFF + (k) * BLOCK + ev.tid])
+// closer than 180 m, as packed ids (4 bits each, nearest first) and their number (<= K).
+//
+// Every lane is x-aligned, so the key |lane_s(el, ox) - es| never decreases along either side of the ego in the
+// x-sorted order `ev.live` (floating-point subtraction is monotone): the K nearest come out of a two-sided walk from
+// the ego's position, a merge by key, instead of a scan of all vehicles with a top-K insertion.  sorted() is stable,
+// i.e. equal keys are ordered by slot id; two equal keys next to each other in the merge (or at the K-th boundary)
+// are the only case the walk cannot order, and it then defers to the scan below.
 template <int K>
-__device__ __forceinline__ int close_vehicles(const Env &ev, int self, uint32_t &packed_ids) {
-#pragma unroll
-    for (int k = 0; k < K; ++k) TOPK(k) = CUDART_INF;
-    double ex = X(self), ey = Y(self);
-    int el = fl_lane(FL(self));
-    double es = lane_s(el, ex);
-    int n = 0;
+__device__ __noinline__ int close_vehicles_scan(const Env &ev, int self, uint32_t &packed_ids) {
+    const double ex = X(self), ey = Y(self);
+    const int el = fl_lane(FL(self));
+    const double es = lane_s(el, ex);
+    double last_key = -1.0;
+    int last_id = -1, n = 0;
     uint32_t ids = 0;
-    double kth = CUDART_INF;  // current K-th smallest key
-#pragma unroll UNROLL_SCAN
-    for (int j = 0; j < ev.n_veh; ++j) {
-        if (j == self) continue;
-        double ox = X(j), oy = Y(j);
-        double dx = ox - ex, dy = oy - ey;
-        if (!(dx * dx + dy * dy < PERCEPTION_SQ_LT)) continue;  // np.linalg.norm(...) < 180
-        double key = fabs(lane_s(el, ox) - es);
-        ++n;
-        if (!(key < kth)) continue;  // not among the K nearest so far (ties go to the earlier vehicle)
-        // shift larger keys back; strict '<' keeps equal keys in list order (sorted() is stable)
-        int k = K - 1;
-        while (k > 0) {
-            double prev = TOPK(k - 1);
-            if (!(key < prev)) break;
-            TOPK(k) = prev;
-            --k;
+    for (int k = 0; k < K; ++k) {   // k-th smallest (key, slot id) by selection: rare path, no scratch memory
+        double best_key = CUDART_INF;
+        int best = -1;
+        for (int j = 0; j < ev.n_veh; ++j) {
+            if (j == self) continue;
+            double ox = X(j), dx = ox - ex, dy = Y(j) - ey;
+            if (!(dx * dx + dy * dy < PERCEPTION_SQ_LT)) continue;  // np.linalg.norm(...) < 180
+            double key = fabs(lane_s(el, ox) - es);
+            if (key < last_key || (key == last_key && j <= last_id)) continue;  // already emitted
+            if (key < best_key) { best_key = key; best = j; }
         }
-        TOPK(k) = key;
-        uint32_t low = ids & ((1u << (4 * k)) - 1u);
-        uint32_t high = (ids >> (4 * k)) << (4 * (k + 1));
-        ids = (low | ((uint32_t)j << (4 * k)) | high) & ((1u << (4 * K)) - 1u);
-        kth = TOPK(K - 1);
+        if (best < 0) break;
+        ids |= (uint32_t)best << (4 * k);
+        last_key = best_key; last_id = best;
+        ++n;
     }
     packed_ids = ids;
-    return n < K ? n : K;
+    return n;
+}
+
+template <int K>
+__device__ __forceinline__ int close_vehicles(const Env &ev, int self, uint32_t &packed_ids) {
+    const double ex = X(self), ey = Y(self);
+    const int el = fl_lane(FL(self));
+    const double es = lane_s(el, ex);
+    const uint64_t live = ev.live;
+    const int n_veh = ev.n_veh;
+    // cursor of each side: next position to look at (front: towards larger x); -1 / n_veh = exhausted
+    int pf = nib(ev.pos, self) - 1, pr = pf + 2;
+    double kf = CUDART_INF, kr = CUDART_INF;
+    int idf = 0, idr = 0;
+    // next vehicle of one side inside the perception radius: its key and id (key = inf when the side is exhausted)
+    auto advance = [&](int pc, const int dir, double &key, int &id) -> int {
+        key = CUDART_INF;
+        while (pc >= 0 && pc < n_veh) {
+            int j = nib(live, pc);
+            pc += dir;
+            double ox = X(j), dx = ox - ex, dy = Y(j) - ey, dx2 = dx * dx;
+            if (!(dx2 < PERCEPTION_SQ_LT)) return -1;                // farther ones on this side fail as well
+            if (!(dx2 + dy * dy < PERCEPTION_SQ_LT)) continue;       // np.linalg.norm(...) < 180
+            key = fabs(lane_s(el, ox) - es);
+            id = j;
+            break;
+        }
+        return pc;
+    };
+    pf = advance(pf, -1, kf, idf);
+    pr = advance(pr, +1, kr, idr);
+    int n = 0;
+    uint32_t ids = 0;
+    double last = -1.0;
+    bool tie = false;
+#pragma unroll 1
+    for (int k = 0; k < K; ++k) {
+        const bool front = kf <= kr;
+        const double key = front ? kf : kr;
+        if (key == CUDART_INF) break;   // both sides exhausted
+        tie |= key == last;
+        last = key;
+        ids |= (uint32_t)(front ? idf : idr) << (4 * k);
+        ++n;
+        // refill the side that was consumed; one copy of the loop serves both sides (lanes stay converged)
+        double nk;
+        int nid = 0;
+        int pc = advance(front ? pf : pr, front ? -1 : +1, nk, nid);
+        if (front) { pf = pc; kf = nk; idf = nid; } else { pr = pc; kr = nk; idr = nid; }
+    }
+    tie |= n == K && fmin(kf, kr) == last;
+    if (tie) return close_vehicles_scan<K>(ev, self, packed_ids);
+    packed_ids = ids;
+    return n;
 }
 
 // safety_layer -> safe_action_hss / safe_action_mass (decentral_layer.py:767-817, 290-518, 521-764) with
@@ -489,11 +538,13 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
     double evx = evx_raw > 1 ? evx_raw : 1;
     double es = lane_s(elane, ex);
 
-    double x_ol = ex + PERCEPTION + 1, x_oa = ex + PERCEPTION + 1, x_oar = ex - PERCEPTION - 1;
-    bool has_ol = false, has_oa = false, has_oar = false;
-    double vx_ol = 0, vx_oa = 0, vx_oar = 0, a_ol = 0, a_oa = 0, g_ol = 0, g_oa = 0;
-    bool constrain_adj = false;
+    // multi_agent_state (decentral_layer.py:85-257) in two passes: the walk over the <= 5 nearest vehicles only decides
+    // WHO is the rear-adjacent / front-adjacent / leading vehicle (shared-memory reads and integer logic); the records
+    // of those three are then fetched together, all lanes converged, with one exposed L2 latency instead of one per role
+    // and per loop iteration.  Nothing the fetch reads changes in between.
     int id_ol = MM_NB_NONE, id_oa = MM_NB_NONE, id_oar = MM_NB_NONE;
+    bool oa_left = false, oa_onramp = false;
+    double x_onramp = 0, vx_onramp = 0;
 
     uint32_t nb_ids;
     int n_nb = close_vehicles<5>(ev, self, nb_ids);
@@ -511,11 +562,10 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
         double d = lane_s(elane, ox) - es;
         // A vehicle behind can only become the rear-adjacent one, a CAV ahead only front-adjacent or leader: skip
         // the classification when those roles are taken (HDVs ahead always run it: the on-ramp branch has side effects)
-        if (d < 0 ? has_oar : (all_cav && has_oa && has_ol)) continue;
+        if (d < 0 ? id_oar != MM_NB_NONE : (all_cav && id_oa != MM_NB_NONE && id_ol != MM_NB_NONE)) continue;
         uint32_t fo = FL(o);
         int olane = fl_lane(fo);
         double oy = Y(o);
-        bool o_cav = fl_kind(fo) == MM_KIND_CAV;
         const bool olane_bc = (olane == L_BC0) | (olane == L_BC1);
         int v_a = (e_eff_bc & olane_bc & (e_eff != olane)) ? (e_eff == L_BC1 ? 1 : -1) : 0;
         int a_v = 0;
@@ -533,46 +583,72 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
             approaching = fabs(y_dist) <= 3.5 && hc;
         }
         if (!approaching && (v_a != 0 || a_v != 0)) {
-            if (!has_oar && d < 0) {  // rear-adjacent: its current state
-                has_oar = true; id_oar = o;
-                x_oar = ox;
-                vx_oar = (fo & FL_CRASHED) ? V(o) * GF(F_COSH, o) : GF(F_REC1VX, o);
-            } else if (!has_oa && d >= 0) {  // front-adjacent: its record before its last step
-                has_oa = true; id_oa = o;
-                x_oa = GF(F_REC2X, o);
-                vx_oa = GF(F_REC2VX, o);
-                if (mass) {
-                    a_oa = o_cav ? GF(F_SAFE_ACC, o) : ACC_LO;
-                    g_oa = o_cav ? GF(F_GVX, o) : 1.0;
-                    bool left = (v_a == -1 || a_v == 1);
-                    double cx, cy;
-                    get_corner(ox, oy, GF(F_COSH, o), GF(F_SINH, o), left, cx, cy);
-                    constrain_adj = !on_lane(olane, cx, cy, 0.0);
-                }
+            if (id_oar == MM_NB_NONE && d < 0) {
+                id_oar = o;                                   // rear-adjacent
+            } else if (id_oa == MM_NB_NONE && d >= 0) {
+                id_oa = o;                                    // front-adjacent
+                oa_left = (v_a == -1 || a_v == 1);
             }
-        } else if (!o_cav && elane == L_AB0 && olane == L_KB0 && d >= 0) {
-            // on-ramp HDV: its record is shifted IN PLACE by half a second of ego speed (decentral_layer.py:175-184)
-            double nx = GF(F_REC2X, o) + 0.5 * evx_raw;
-            GF(F_REC2X, o) = nx;
-            has_oa = true; id_oa = o;
-            x_oa = nx;
-            vx_oa = GF(F_REC2VX, o);
+        } else if (fl_kind(fo) != MM_KIND_CAV && elane == L_AB0 && olane == L_KB0 && d >= 0) {
+            // on-ramp HDV: its record is shifted IN PLACE by half a second of ego speed (decentral_layer.py:175-184);
+            // it takes the front-adjacent role whoever held it
+            x_onramp = GF(F_REC2X, o) + 0.5 * evx_raw;
+            GF(F_REC2X, o) = x_onramp;
+            vx_onramp = GF(F_REC2VX, o);
+            id_oa = o;
+            oa_onramp = true;
+        } else if (id_ol == MM_NB_NONE && d > 0) {
+            if ((elane == olane) || (olane == e_next) || approaching) id_ol = o;   // leader
+        }
+    }
+    const bool has_ol0 = id_ol != MM_NB_NONE, has_oa0 = id_oa != MM_NB_NONE, has_oar0 = id_oar != MM_NB_NONE;
+    double x_ol = ex + PERCEPTION + 1, x_oa = ex + PERCEPTION + 1, x_oar = ex - PERCEPTION - 1;
+    double vx_ol = 0, vx_oa = 0, vx_oar = 0, a_ol = 0, a_oa = 0, g_ol = 0, g_oa = 0;
+    bool constrain_adj = false;
+    {
+        // the three fetches, issued back to back (an absent role reads the ego's own column and is discarded)
+        const int jl = has_ol0 ? id_ol : self, ja = has_oa0 ? id_oa : self, jr = has_oar0 ? id_oar : self;
+        const double l_x = GF(F_REC2X, jl), l_vx = GF(F_REC2VX, jl);            // leader: record before its last step
+        const double a_x = GF(F_REC2X, ja), a_vx = GF(F_REC2VX, ja);            // front-adjacent: same
+        const double r_vx = GF(F_REC1VX, jr);                                    // rear-adjacent: current state
+        double l_a = 0, l_g = 0, a_a = 0, a_g = 0, a_ch = 0, a_sh = 0;
+        if (mass) {
+            l_a = GF(F_SAFE_ACC, jl); l_g = GF(F_GVX, jl);
+            a_a = GF(F_SAFE_ACC, ja); a_g = GF(F_GVX, ja);
+            a_ch = GF(F_COSH, ja); a_sh = GF(F_SINH, ja);
+        }
+        if (has_oar0) {
+            uint32_t fo = FL(jr);
+            x_oar = X(jr);
+            vx_oar = (fo & FL_CRASHED) ? V(jr) * GF(F_COSH, jr) : r_vx;
+        }
+        if (has_ol0) {
+            x_ol = l_x; vx_ol = l_vx;
+            if (mass) {
+                bool o_cav = fl_kind(FL(jl)) == MM_KIND_CAV;
+                a_ol = o_cav ? l_a : ACC_LO;
+                g_ol = o_cav ? l_g : 1.0;
+            }
+        }
+        if (oa_onramp) {
+            x_oa = x_onramp; vx_oa = vx_onramp;
             constrain_adj = true;
             a_oa = ACC_LO;
             g_oa = 1.0;
-        } else if (!has_ol && d > 0) {
-            bool same = (elane == olane) || (olane == e_next);
-            if (same || approaching) {
-                has_ol = true; id_ol = o;
-                x_ol = GF(F_REC2X, o);
-                vx_ol = GF(F_REC2VX, o);
-                if (mass) {
-                    a_ol = o_cav ? GF(F_SAFE_ACC, o) : ACC_LO;
-                    g_ol = o_cav ? GF(F_GVX, o) : 1.0;
-                }
+        } else if (has_oa0) {
+            x_oa = a_x; vx_oa = a_vx;
+            if (mass) {
+                uint32_t fo = FL(ja);
+                bool o_cav = fl_kind(fo) == MM_KIND_CAV;
+                a_oa = o_cav ? a_a : ACC_LO;
+                g_oa = o_cav ? a_g : 1.0;
+                double cx, cy;
+                get_corner(X(ja), Y(ja), a_ch, a_sh, oa_left, cx, cy);
+                constrain_adj = !on_lane(fl_lane(fo), cx, cy, 0.0);
             }
         }
     }
+    bool has_ol = has_ol0, has_oa = has_oa0, has_oar = has_oar0;
     // the obstacle can take over either role (decentral_layer.py:213-246)
     if (!(ex > OBST_X)) {
         double ady = fabs(OBST_Y - ey);
@@ -675,6 +751,37 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
 }
 
 // ------------------------------------------------------------------------------------------------
+// x-sorted order (ev.live / ev.pos)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t invert_order(uint64_t ord, int n) {
+    uint64_t pos = 0;
+    for (int p = 0; p < n; ++p) pos |= (uint64_t)p << (4 * nib(ord, p));
+    return pos;
+}
+// Slot i has just moved to x = nx: restore the descending order by neighbouring swaps (a vehicle advances by at most
+// 2.7 m per sub-step, so this is almost always zero swaps) and keep the inverse in step.
+__device__ __forceinline__ void reorder_after_move(Env &ev, int i, double nx) {
+    uint64_t live = ev.live, pos = ev.pos;
+    int p = nib(pos, i);
+    while (p > 0) {
+        int a = nib(live, p - 1);
+        if (!(X(a) < nx)) break;
+        live = (live & ~(0xffull << (4 * (p - 1)))) | ((uint64_t)i << (4 * (p - 1))) | ((uint64_t)a << (4 * p));
+        pos = (pos & ~(15ull << (4 * a))) | ((uint64_t)p << (4 * a));
+        --p;
+    }
+    while (p < ev.n_veh - 1) {
+        int b = nib(live, p + 1);
+        if (!(X(b) > nx)) break;
+        live = (live & ~(0xffull << (4 * p))) | ((uint64_t)b << (4 * p)) | ((uint64_t)i << (4 * (p + 1)));
+        pos = (pos & ~(15ull << (4 * b))) | ((uint64_t)p << (4 * b));
+        ++p;
+    }
+    ev.live = live;
+    ev.pos = (pos & ~(15ull << (4 * i))) | ((uint64_t)p << (4 * i));
+}
+
+// ------------------------------------------------------------------------------------------------
 // integration (kinematics.py:122-152, safe_controller.py:100-185, behavior.py:102-109,504-522)
 // ------------------------------------------------------------------------------------------------
 // `steer`, `acc`: the low-level action act() produced for this sub-step.
@@ -758,6 +865,7 @@ __device__ void vehicle_step(Env &ev, const StepParams &p, int i, int sub, size_
     if (hist < 2) f = fl_set(f, FL_HIST_SHIFT, 3u, (uint32_t)(hist + 1));
     X(i) = nx; Y(i) = ny; H(i) = nh; V(i) = nv;
     FL(i) = f;
+    reorder_after_move(ev, i, nx);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -811,6 +919,29 @@ __device__ __forceinline__ bool may_intersect(double adx, double ady, double aco
     aco = fabs(aco); asn = fabs(asn); bco = fabs(bco); bsn = fabs(bsn);
     return may_have_corner_inside(adx, ady, 0.9 * VLEN / 2, 0.9 * VWID / 2, asn, 0.9 * blen, 0.9 * bwid, bco, bsn) ||
            may_have_corner_inside(adx, ady, 0.9 * blen / 2, 0.9 * bwid / 2, bsn, 0.9 * VLEN, 0.9 * VWID, aco, asn);
+}
+
+// No pair closer than LENGTH (centre to centre), no vehicle that close to the obstacle: the pass below would not change
+// anything.  In the x-sorted order a vehicle's partners within LENGTH are its immediate successors.
+__device__ __forceinline__ bool any_close_pair(const Env &ev) {
+    const uint64_t live = ev.live;
+    bool any = false;
+    for (int p = 0; p < ev.n_veh; ++p) {
+        const int a = nib(live, p);
+        const double ax = X(a), ay = Y(a);
+        {
+            double dx = OBST_X - ax, dy = OBST_Y - ay;
+            any |= !(dx * dx + dy * dy > VLEN_SQ_GT);
+        }
+        for (int q = p + 1; q < ev.n_veh; ++q) {
+            const int b = nib(live, q);
+            double dx = X(b) - ax, dx2 = dx * dx;
+            if (dx2 > VLEN_SQ_GT) break;             // x only grows apart from here on
+            double dy = Y(b) - ay;
+            any |= !(dx2 + dy * dy > VLEN_SQ_GT);
+        }
+    }
+    return any;
 }
 
 __device__ __noinline__ void collision_pass(Env &ev) {
@@ -891,18 +1022,23 @@ __device__ __noinline__ void observe_agent(const Env &ev, int self, bool steer_v
     }
 }
 
-// abstract.py:620-635
+// abstract.py:620-635: the smallest x-gap to a vehicle strictly ahead in the same lane or (unless on bc1) in the next
+// lane, default 60.  Walking ahead in the x-sorted order the first match is the minimum, and nothing 60 m ahead matters.
 __device__ __noinline__ double headway_distance(const Env &ev, int self) {
-    double ex = X(self), hd = 60;
-    int lane = fl_lane(FL(self));
-    int nl = next_lane(lane, ex, Y(self));
-    bool use_next = lane != L_BC1;
-    for (int j = 0; j < ev.n_veh; ++j) {
-        int lj = fl_lane(FL(j));
-        double d = X(j) - ex;
-        if (X(j) > ex && (lj == lane || (use_next && lj == nl)) && d < hd) hd = d;
+    const double ex = X(self);
+    const int lane = fl_lane(FL(self));
+    const int nl = next_lane(lane, ex, Y(self));
+    const bool use_next = lane != L_BC1;
+    const uint64_t live = ev.live;
+    for (int p = nib(ev.pos, self) - 1; p >= 0; --p) {
+        const int j = nib(live, p);
+        const double xj = X(j), d = xj - ex;
+        if (!(xj > ex)) continue;          // same x: not ahead
+        if (!(d < 60)) break;
+        const int lj = fl_lane(FL(j));
+        if (lj == lane || (use_next && lj == nl)) return d;
     }
-    return hd;
+    return 60;
 }
 
 // merge_env_v1.py:64-89 and 439-474
@@ -935,8 +1071,8 @@ __device__ __forceinline__ uint32_t visible_lanes(int qlane) {
     // ab0:{ab0,bc0} bc0:{ab0,bc0,cd0} bc1:{kb0,bc1} cd0:{bc0,cd0} jk0:{jk0,kb0} kb0:{jk0,kb0,bc1}
     return (0x34300A240B03ull >> (8 * qlane)) & 0xffu;
 }
-__device__ __noinline__ void surrounding2(const Env &ev, int self, uint32_t m1, uint32_t m2, int &f1, int &r1, int &f2,
-                                          int &r2) {
+__device__ __noinline__ void surrounding2_scan(const Env &ev, int self, uint32_t m1, uint32_t m2, int &f1, int &r1, int &f2,
+                                               int &r2) {
     double s = X(self), sf1 = 0, sr1 = 0, sf2 = 0, sr2 = 0;
     f1 = r1 = f2 = r2 = -1;
     for (int j = 0; j < ev.n_veh; ++j) {
@@ -953,6 +1089,43 @@ __device__ __noinline__ void surrounding2(const Env &ev, int self, uint32_t m1, 
             if (behind && (r2 < 0 || s_v > sr2)) { sr2 = s_v; r2 = j; }
         }
     }
+}
+
+// The same through the x-sorted order: the nearest visible vehicle ahead / behind is the first one met walking away from
+// the ego.  Equal x values (with the ego or between two candidates) are where the reference's tie rules bite (ahead
+// includes equality and prefers the later slot, behind prefers the earlier): any equality on the way defers to the scan.
+__device__ __forceinline__ void surrounding2(const Env &ev, int self, uint32_t m1, uint32_t m2, int &f1, int &r1, int &f2,
+                                             int &r2) {
+    const uint64_t live = ev.live;
+    const int ps = nib(ev.pos, self);
+    const bool need2 = m2 != 0;
+    f1 = r1 = f2 = r2 = -1;
+    bool tie = false;
+    double prev = X(self);
+    int p = ps - 1;
+    for (; p >= 0 && (f1 < 0 || (need2 && f2 < 0)); --p) {
+        const int j = nib(live, p);
+        const double xj = X(j);
+        tie |= xj == prev;
+        prev = xj;
+        const uint32_t bit = 1u << fl_lane(FL(j));
+        if (f1 < 0 && (m1 & bit)) f1 = j;
+        if (f2 < 0 && (m2 & bit)) f2 = j;
+    }
+    if (p >= 0) tie |= X(nib(live, p)) == prev;
+    prev = X(self);
+    p = ps + 1;
+    for (; p < ev.n_veh && (r1 < 0 || (need2 && r2 < 0)); ++p) {
+        const int j = nib(live, p);
+        const double xj = X(j);
+        tie |= xj == prev;
+        prev = xj;
+        const uint32_t bit = 1u << fl_lane(FL(j));
+        if (r1 < 0 && (m1 & bit)) r1 = j;
+        if (r2 < 0 && (m2 & bit)) r2 = j;
+    }
+    if (p < ev.n_veh) tie |= X(nib(live, p)) == prev;
+    if (tie) surrounding2_scan(ev, self, m1, m2, f1, r1, f2, r2);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1241,6 +1414,8 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
     ev.g = p.st.f64 + f64_index(e, 0, 0);
     ev.n_veh = 0;
     ev.n_cav = 0;
+    ev.live = 0;
+    ev.pos = 0;
     uint32_t ei = 0, act_lo = 0, act_mid = 0, act_hi = 0;
     int n_merge = 0, steps = 0, time = 0;
     __shared__ uint64_t s_mbar;
@@ -1291,6 +1466,8 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
                 }
             }
             ord = order_by_x_desc(ev);
+            ev.live = ord;
+            ev.pos = invert_order(ord, ev.n_veh);
         }
         const int n_live = running ? ev.n_veh : 0;
         if (!merged) {
@@ -1328,7 +1505,7 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
         }
         PHASE_BARRIER(2);
         if (running) {
-            collision_pass(ev);
+            if (any_close_pair(ev)) collision_pass(ev);
             time = min(time + 1, (int)EI_TIME_MASK);
             if (is_terminal(ev, steps, p.cfg.duration_steps)) running = false;  // abstract.py:530
         }
@@ -1360,6 +1537,8 @@ __global__ void __launch_bounds__(BLOCK) observe_kernel(const __grid_constant__ 
     ev.n_veh = (ei >> EI_NVEH_SHIFT) & EI_4BIT;
     ev.n_cav = (ei >> EI_NCAV_SHIFT) & EI_4BIT;
     load_env(ev, p.st, e);
+    ev.live = order_by_x_desc(ev);
+    ev.pos = invert_order(ev.live, ev.n_veh);
     write_outputs(ev, p, e, 0, 0, false, nullptr);
 }
 
@@ -1575,7 +1754,7 @@ __global__ void __launch_bounds__(256) qp_kernel(const double *__restrict__ a, c
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-constexpr size_t STEP_SMEM = (size_t)SCRATCH_OFF * sizeof(double) + (size_t)TOPK_MAX * BLOCK * sizeof(double);
+constexpr size_t STEP_SMEM = (size_t)PLANES_F64 * sizeof(double);
 
 void launch_step(const StepParams &p, bool diag, void *stream) {
     static bool attr_set = false;
