@@ -35,10 +35,6 @@ constexpr int BLOCK = TILE;
 #ifndef MM_INL_B
 #define MM_INL_B __forceinline__   // cav_act: measured -2 % inlined (profiles/README.md)
 #endif
-#ifndef MM_UNROLL_SCAN
-#define MM_UNROLL_SCAN 1
-#endif
-constexpr int UNROLL_SCAN = MM_UNROLL_SCAN;
 #ifndef MM_MIN_BLOCKS
 #define MM_MIN_BLOCKS 3   // CTAs per SM the step kernel is compiled for (register budget 65536 / (128 * n))
 #endif
@@ -79,10 +75,11 @@ constexpr double VLEN_SQ_GT = 0x1.9000000000001p+4;
 #ifndef MM_TMA
 #define MM_TMA 1   // 1: hot planes move between HBM and shared memory as cp.async.bulk transactions; 0: per-thread loads
 #endif
-// staged slots: with bulk copies the same [slot][env] shape as the HBM tile; else 11 (an env never has more vehicles)
-constexpr int SMV = MM_TMA ? MAXV : 11;
-constexpr int PLANES_F64 = 4 * SMV * BLOCK + (SMV + 1) * BLOCK / 2;   // doubles: 4 f64 planes + the u32 flags plane
-extern __shared__ __align__(16) double sm_planes[];   // [4][SMV][BLOCK] f64 (x, y, heading, speed) + [SMV+1][BLOCK] u32
+// Staged slots: an env never has more than 11 vehicles.  6 f64 planes x 11 slots + the flags = 72 KB per CTA, three
+// CTAs per SM.
+constexpr int SMV = 11;
+constexpr int PLANES_F64 = N_HOT * SMV * BLOCK + (SMV + 1) * BLOCK / 2;   // doubles: hot f64 planes + the u32 flags plane
+extern __shared__ __align__(16) double sm_planes[];   // [N_HOT][SMV][BLOCK] f64 + [SMV+1][BLOCK] u32
 struct Env {
     int tid;                    // threadIdx.x: column of this env inside the CTA's planes
     double *g;                  // this env's column of its tile; element (f, i) at [(f*MAXV+i)*TILE]
@@ -92,11 +89,14 @@ struct Env {
 };
 __device__ __forceinline__ int nib(uint64_t w, int k) { return (int)((w >> (4 * k)) & 15ull); }
 
-#define X(i) (sm_planes[(0 * SMV + (i)) * BLOCK + ev.tid])
-#define Y(i) (sm_planes[(1 * SMV + (i)) * BLOCK + ev.tid])
-#define H(i) (sm_planes[(2 * SMV + (i)) * BLOCK + ev.tid])
-#define V(i) (sm_planes[(3 * SMV + (i)) * BLOCK + ev.tid])
-#define FL(i) (reinterpret_cast<uint32_t *>(sm_planes + 4 * SMV * BLOCK)[(i) * BLOCK + ev.tid])
+#define SMF(f, i) (sm_planes[((f) * SMV + (i)) * BLOCK + ev.tid])
+#define X(i) SMF(F_X, i)
+#define Y(i) SMF(F_Y, i)
+#define H(i) SMF(F_H, i)
+#define V(i) SMF(F_V, i)
+#define CH(i) SMF(F_COSH, i)
+#define SH(i) SMF(F_SINH, i)
+#define FL(i) (reinterpret_cast<uint32_t *>(sm_planes + N_HOT * SMV * BLOCK)[(i) * BLOCK + ev.tid])
 #define GF(f, i) (*tile_ptr(ev.g, (f), (i)))
 
 __device__ __forceinline__ double *tile_ptr(double *col, int f, int i) {
@@ -297,10 +297,10 @@ __device__ __noinline__ void neighbour_vehicles(const Env &ev, int self, int lan
 __device__ __noinline__ double desired_gap(const Env &ev, int ego, int front) {
     double fvx = 0, fvy = 0;
     if (front != OBST) {
-        fvx = V(front) * GF(F_COSH, front);
-        fvy = V(front) * GF(F_SINH, front);
+        fvx = V(front) * CH(front);
+        fvy = V(front) * SH(front);
     }
-    double ec = GF(F_COSH, ego), es = GF(F_SINH, ego), speed = V(ego);
+    double ec = CH(ego), es = SH(ego), speed = V(ego);
     double dv = (speed * ec - fvx) * ec + (speed * es - fvy) * es;
     return 10.0 + speed * 1.5 + speed * dv / (2 * sqrt(15.0));
 }
@@ -534,7 +534,7 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
     double v_max = espeed + ACC_HI * dt;
     // to_dict()["vx"] = speed * cos(heading): for a vehicle that has not crashed this is bit-for-bit the value its
     // last log_step recorded (same operands), so the record is reused instead of a cosine
-    double evx_raw = (f & FL_CRASHED) ? espeed * GF(F_COSH, self) : rec1vx;
+    double evx_raw = (f & FL_CRASHED) ? espeed * CH(self) : rec1vx;
     double evx = evx_raw > 1 ? evx_raw : 1;
     double es = lane_s(elane, ex);
 
@@ -615,12 +615,12 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
         if (mass) {
             l_a = GF(F_SAFE_ACC, jl); l_g = GF(F_GVX, jl);
             a_a = GF(F_SAFE_ACC, ja); a_g = GF(F_GVX, ja);
-            a_ch = GF(F_COSH, ja); a_sh = GF(F_SINH, ja);
+            a_ch = CH(ja); a_sh = SH(ja);
         }
         if (has_oar0) {
             uint32_t fo = FL(jr);
             x_oar = X(jr);
-            vx_oar = (fo & FL_CRASHED) ? V(jr) * GF(F_COSH, jr) : r_vx;
+            vx_oar = (fo & FL_CRASHED) ? V(jr) * CH(jr) : r_vx;
         }
         if (has_ol0) {
             x_ol = l_x; vx_ol = l_vx;
@@ -717,7 +717,7 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
         veto = false;
         if (!allowed) {
             double cx, cy;
-            const double ech = GF(F_COSH, self), esh = GF(F_SINH, self);
+            const double ech = CH(self), esh = SH(self);
             get_corner(ex, ey, ech, esh, true, cx, cy);
             bool can_abort = on_lane(elane, cx, cy, 0.0);
             if (can_abort) {
@@ -791,15 +791,13 @@ __device__ __forceinline__ void reorder_after_move(Env &ev, int i, double nx) {
 // move instead of 6 (tan, atan, sincos, sin, cos, cos), each result within a few ulp of the reference's chain.
 template <bool DIAG>
 __device__ void vehicle_step(Env &ev, const StepParams &p, int i, int sub, size_t e_glob, uint32_t &shield_counts,
-                             double steer, double acc) {
+                             double steer, double acc, const double rec1vx, const double ge) {
     uint32_t f = FL(i);
     const bool cav = fl_kind(f) == MM_KIND_CAV;
     const double dt = p.cfg.dt;
     const double speed = V(i), heading = H(i);
-    const double ch = GF(F_COSH, i), sh = GF(F_SINH, i), rec1vx = GF(F_REC1VX, i);   // issued early: L2 latency
+    const double ch = CH(i), sh = SH(i);
     const bool shielded = cav && p.cfg.shield != MM_SHIELD_NONE && !p.cfg.env_v0 && (f & FL_FG) && fl_hist(f) >= 2;
-    double ge = 0.0;
-    if (shielded) ge = GF(F_GVX, i);
     if (!cav) GF(F_TIMER, i) = GF(F_TIMER, i) + dt;
     // clip_actions
     if (f & FL_CRASHED) { steer = 0.0; acc = -1.0 * speed; }
@@ -859,8 +857,8 @@ __device__ void vehicle_step(Env &ev, const StepParams &p, int i, int sub, size_
     GF(F_REC2X, i) = X(i);
     GF(F_REC2VX, i) = rec1vx;
     GF(F_REC1VX, i) = nv * scn.y;
-    GF(F_COSH, i) = scn.y;
-    GF(F_SINH, i) = scn.x;
+    CH(i) = scn.y;
+    SH(i) = scn.x;
     int hist = fl_hist(f);
     if (hist < 2) f = fl_set(f, FL_HIST_SHIFT, 3u, (uint32_t)(hist + 1));
     X(i) = nx; Y(i) = ny; H(i) = nh; V(i) = nv;
@@ -921,34 +919,37 @@ __device__ __forceinline__ bool may_intersect(double adx, double ady, double aco
            may_have_corner_inside(adx, ady, 0.9 * blen / 2, 0.9 * bwid / 2, bsn, 0.9 * VLEN, 0.9 * VWID, aco, asn);
 }
 
-// No pair closer than LENGTH (centre to centre), no vehicle that close to the obstacle: the pass below would not change
-// anything.  In the x-sorted order a vehicle's partners within LENGTH are its immediate successors.
-__device__ __forceinline__ bool any_close_pair(const Env &ev) {
+// Vehicles with a partner (or the obstacle) within LENGTH, centre to centre, as a bit mask over the slots: the pass below
+// cannot change anything for the others.  In the x-sorted order a vehicle's partners within LENGTH are its immediate
+// successors.
+__device__ __forceinline__ uint32_t close_pair_mask(const Env &ev) {
     const uint64_t live = ev.live;
-    bool any = false;
+    uint32_t mask = 0;
     for (int p = 0; p < ev.n_veh; ++p) {
         const int a = nib(live, p);
         const double ax = X(a), ay = Y(a);
         {
             double dx = OBST_X - ax, dy = OBST_Y - ay;
-            any |= !(dx * dx + dy * dy > VLEN_SQ_GT);
+            if (!(dx * dx + dy * dy > VLEN_SQ_GT)) mask |= 1u << a;
         }
         for (int q = p + 1; q < ev.n_veh; ++q) {
             const int b = nib(live, q);
             double dx = X(b) - ax, dx2 = dx * dx;
             if (dx2 > VLEN_SQ_GT) break;             // x only grows apart from here on
             double dy = Y(b) - ay;
-            any |= !(dx2 + dy * dy > VLEN_SQ_GT);
+            if (!(dx2 + dy * dy > VLEN_SQ_GT)) mask |= (1u << a) | (1u << b);
         }
     }
-    return any;
+    return mask;
 }
 
-__device__ __noinline__ void collision_pass(Env &ev) {
-    for (int i = 0; i < ev.n_veh; ++i) {
+// road.py:288-292 restricted to the vehicles of `mask` (slot order is the reference's list order)
+__device__ __noinline__ void collision_pass(Env &ev, uint32_t mask) {
+    for (uint32_t mi = mask; mi; mi &= mi - 1) {
+        const int i = __ffs(mi) - 1;
         double ax = X(i), ay = Y(i);
-#pragma unroll UNROLL_SCAN
-        for (int j = 0; j < ev.n_veh; ++j) {
+        for (uint32_t mj = mask; mj; mj &= mj - 1) {
+            const int j = __ffs(mj) - 1;
             if (j == i) continue;
             if (FL(i) & FL_CRASHED) break;
             // The pair {j < i} already had its turn as (j, i) unless j was crashed by then (check_collision returns
@@ -957,7 +958,7 @@ __device__ __noinline__ void collision_pass(Env &ev) {
             if (j < i && !(FL(j) & FL_CRASHED)) continue;
             double dx = X(j) - ax, dy = Y(j) - ay;
             if (dx * dx + dy * dy > VLEN_SQ_GT) continue;  // np.linalg.norm(...) > LENGTH
-            double aco = GF(F_COSH, i), asn = GF(F_SINH, i), bco = GF(F_COSH, j), bsn = GF(F_SINH, j);
+            double aco = CH(i), asn = SH(i), bco = CH(j), bsn = SH(j);
             if (!may_intersect(fabs(dx), fabs(dy), aco, asn, bco, bsn, VLEN, VWID)) continue;
             if (rects_intersect(ax, ay, aco, asn, X(j), Y(j), bco, bsn, VLEN, VWID)) {
                 double va = V(i), vb = V(j);
@@ -969,7 +970,7 @@ __device__ __noinline__ void collision_pass(Env &ev) {
         if (!(FL(i) & FL_CRASHED)) {
             double dx = OBST_X - ax, dy = OBST_Y - ay;
             if (!(dx * dx + dy * dy > VLEN_SQ_GT)) {
-                double aco = GF(F_COSH, i), asn = GF(F_SINH, i);
+                double aco = CH(i), asn = SH(i);
                 if (may_intersect(fabs(dx), fabs(dy), aco, asn, 1.0, 0.0, 2.0, 2.0) &&
                     rects_intersect(ax, ay, aco, asn, OBST_X, OBST_Y, 1.0, 0.0, 2.0, 2.0)) {
                     double va = V(i);
@@ -994,10 +995,10 @@ __device__ __forceinline__ bool is_terminal(const Env &ev, int steps, int durati
 // observation.py:241-273 + normalize_obs 181-193: ego row absolute, 4 nearest rows relative, no clipping.
 // The rows are float32 outputs, so lmap's divisions by the constant ranges are multiplications by the
 // reciprocals here (a <= 1-ulp float64 difference, invisible after rounding to float32).
-__device__ __noinline__ void observe_agent(const Env &ev, int self, bool steer_vel, const double *vx, const double *vy,
-                                           float *obs) {
+__device__ __noinline__ void observe_agent(const Env &ev, int self, bool steer_vel, float *obs) {
     const double KX = 2.0 / 300.0, KY = 2.0 / 24.0, KV = 2.0 / 90.0, KH = 2.0 / PI;
-    double ex = X(self), ey = Y(self), evx = vx[self], evy = vy[self];
+    // Vehicle.velocity (kinematics.py:215-217) = speed * [cos, sin](heading)
+    double ex = X(self), ey = Y(self), evx = V(self) * CH(self), evy = V(self) * SH(self);
     uint32_t nb_ids;
     int n_nb = close_vehicles<4>(ev, self, nb_ids);
     float2 *dst = reinterpret_cast<float2 *>(obs);  // 120-byte rows: 8-byte aligned
@@ -1011,10 +1012,11 @@ __device__ __noinline__ void observe_agent(const Env &ev, int self, bool steer_v
         if (k < n_nb) {
             int o = (int)((nb_ids >> (4 * k)) & 15u);
             a = make_float2(1.0f, (float)(((X(o) - ex) + 150.0) * KX - 1.0));
-            b = make_float2((float)(((Y(o) - ey) + 12.0) * KY - 1.0), (float)(((vx[o] - evx) + 45.0) * KV - 1.0));
+            const double ov = V(o);
+            b = make_float2((float)(((Y(o) - ey) + 12.0) * KY - 1.0), (float)(((ov * CH(o) - evx) + 45.0) * KV - 1.0));
             double oh = H(o);
             if (steer_vel && o < ev.n_cav) oh = oh - H(self);   // MDPLCVehicle.to_dict(origin) (safe_controller.py:75-81)
-            c = make_float2((float)(((vy[o] - evy) + 45.0) * KV - 1.0), (float)((oh + PI / 2) * KH - 1.0));
+            c = make_float2((float)(((ov * SH(o) - evy) + 45.0) * KV - 1.0), (float)((oh + PI / 2) * KH - 1.0));
         }
         __stcs(dst + 3 * (k + 1), a);
         __stcs(dst + 3 * (k + 1) + 1, b);
@@ -1152,13 +1154,13 @@ __device__ __forceinline__ uint64_t order_by_x_desc(const Env &ev) {
 // 48 KB contiguous, and the 6 KB flags plane - move between HBM and shared memory as two bulk transactions issued
 // by one thread, completion signalled on an mbarrier (load) / a bulk async-group (store).
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t HOT_F64_BYTES = 4u * MAXV * TILE * sizeof(double);
+constexpr uint32_t HOT_FIELD_BYTES = (uint32_t)SMV * TILE * sizeof(double);       // 11 of the 12 slots of one field
 constexpr uint32_t HOT_FLAG_BYTES = (uint32_t)MAXV * TILE * sizeof(uint32_t);
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void tile_bulk_load(const DevState &st, size_t tile, uint64_t *mbar) {
-    // called by every thread of the CTA; thread 0 arms the barrier and issues the two copies
+    // called by every thread of the CTA; thread 0 arms the barrier and issues the copies
     const uint32_t bar = smem_u32(mbar);
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
@@ -1168,11 +1170,13 @@ __device__ __forceinline__ void tile_bulk_load(const DevState &st, size_t tile, 
     if (threadIdx.x == 0) {
         const double *g64 = st.f64 + tile * (size_t)F_COUNT * MAXV * TILE;
         const uint32_t *gfl = st.flags + tile * (size_t)MAXV * TILE;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(HOT_F64_BYTES + HOT_FLAG_BYTES) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(N_HOT * HOT_FIELD_BYTES + HOT_FLAG_BYTES) : "memory");
+#pragma unroll
+        for (int f = 0; f < N_HOT; ++f)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(sm_planes + f * SMV * BLOCK)), "l"(g64 + (size_t)f * MAXV * TILE), "r"(HOT_FIELD_BYTES), "r"(bar) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(sm_planes)), "l"(g64), "r"(HOT_F64_BYTES), "r"(bar) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(sm_planes + 4 * SMV * BLOCK)), "l"(gfl), "r"(HOT_FLAG_BYTES), "r"(bar) : "memory");
+                     ::"r"(smem_u32(sm_planes + N_HOT * SMV * BLOCK)), "l"(gfl), "r"(HOT_FLAG_BYTES), "r"(bar) : "memory");
     }
     uint32_t done = 0;
     while (!done) {
@@ -1188,10 +1192,12 @@ __device__ __forceinline__ void tile_bulk_store(const DevState &st, size_t tile)
     if (threadIdx.x == 0) {
         double *g64 = st.f64 + tile * (size_t)F_COUNT * MAXV * TILE;
         uint32_t *gfl = st.flags + tile * (size_t)MAXV * TILE;
+#pragma unroll
+        for (int f = 0; f < N_HOT; ++f)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         ::"l"(g64 + (size_t)f * MAXV * TILE), "r"(smem_u32(sm_planes + f * SMV * BLOCK)), "r"(HOT_FIELD_BYTES) : "memory");
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                     ::"l"(g64), "r"(smem_u32(sm_planes)), "r"(HOT_F64_BYTES) : "memory");
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                     ::"l"(gfl), "r"(smem_u32(sm_planes + 4 * SMV * BLOCK)), "r"(HOT_FLAG_BYTES) : "memory");
+                     ::"l"(gfl), "r"(smem_u32(sm_planes + N_HOT * SMV * BLOCK)), "r"(HOT_FLAG_BYTES) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory may be released after this
     }
@@ -1200,20 +1206,16 @@ __device__ __forceinline__ void tile_bulk_store(const DevState &st, size_t tile)
 __device__ __forceinline__ void load_env(Env &ev, const DevState &st, size_t e) {
     const uint32_t *fl = st.flags + flags_index(e, 0);
     for (int i = 0; i < ev.n_veh; ++i) {
-        X(i) = GF(F_X, i);
-        Y(i) = GF(F_Y, i);
-        H(i) = GF(F_H, i);
-        V(i) = GF(F_V, i);
+#pragma unroll
+        for (int f = 0; f < N_HOT; ++f) SMF(f, i) = GF(f, i);
         FL(i) = fl[i * TILE];
     }
 }
 __device__ __forceinline__ void store_env(const Env &ev, const DevState &st, size_t e) {
     uint32_t *fl = st.flags + flags_index(e, 0);
     for (int i = 0; i < ev.n_veh; ++i) {
-        GF(F_X, i) = X(i);
-        GF(F_Y, i) = Y(i);
-        GF(F_H, i) = H(i);
-        GF(F_V, i) = V(i);
+#pragma unroll
+        for (int f = 0; f < N_HOT; ++f) GF(f, i) = SMF(f, i);
         fl[i * TILE] = FL(i);
     }
 }
@@ -1224,13 +1226,8 @@ __device__ __noinline__ void write_outputs(const Env &ev, const StepParams &p, s
                               double *stat_acc) {
     const DevOut &o = p.out;
     float *obs = o.obs + e * (size_t)(MAXV * NS);
-    double vx[MAXV], vy[MAXV];   // Vehicle.velocity (kinematics.py:215-217) of every vehicle, once per env
-    for (int i = 0; i < ev.n_veh; ++i) {
-        vx[i] = V(i) * GF(F_COSH, i);
-        vy[i] = V(i) * GF(F_SINH, i);
-    }
     const bool sv = p.cfg.steer_vel && !p.cfg.env_v0;
-    for (int i = 0; i < ev.n_cav; ++i) observe_agent(ev, i, sv, vx, vy, obs + i * NS);
+    for (int i = 0; i < ev.n_cav; ++i) observe_agent(ev, i, sv, obs + i * NS);
     float2 *z = reinterpret_cast<float2 *>(obs + ev.n_cav * NS);
     // rows of absent agents are zeroed when the scene is (re)built and n_cav is fixed for the episode, so the
     // per-step path does not rewrite them
@@ -1273,7 +1270,8 @@ __device__ __noinline__ void write_outputs(const Env &ev, const StepParams &p, s
             if (d < hd) hd = d;
         }
         hd = hd - VLEN;
-        minhw = fmin(minhw, hd / (vx[i] > 1 ? vx[i] : 1));
+        const double vxi = V(i) * CH(i);
+        minhw = fmin(minhw, hd / (vxi > 1 ? vxi : 1));
         any_crash = any_crash || (FL(i) & FL_CRASHED);
     }
     for (int i = 0; i < ev.n_veh; ++i) tsum += V(i);
@@ -1465,9 +1463,22 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
                     cav_act(ev, i, meta_action(act_lo, act_mid, act_hi, i), sv, st_, ac_);
                 }
             }
-            ord = order_by_x_desc(ev);
-            ev.live = ord;
-            ev.pos = invert_order(ord, ev.n_veh);
+            // road.py:277,286: stable sort by x, descending.  After the first sub-step the live order of the previous
+            // one is that order unless two vehicles share an x (stability then decides by slot id: sort again).
+            bool resort = sub == 0;
+            if (!resort) {
+                double prev = X(nib(ev.live, 0));
+                for (int q = 1; q < ev.n_veh; ++q) {
+                    double xq = X(nib(ev.live, q));
+                    resort |= xq == prev;
+                    prev = xq;
+                }
+            }
+            if (resort) {
+                ev.live = order_by_x_desc(ev);
+                ev.pos = invert_order(ev.live, ev.n_veh);
+            }
+            ord = ev.live;
         }
         const int n_live = running ? ev.n_veh : 0;
         if (!merged) {
@@ -1492,6 +1503,9 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
             PHASE_BARRIER(2);
             if (q < n_live) {
                 int i = (int)((ord >> (4 * q)) & 15u);
+                // the two cold fields of the ego the step needs, requested before the steering law so that their L2
+                // round trip overlaps it
+                const double rec1vx = GF(F_REC1VX, i), ge = GF(F_GVX, i);
                 double st_, ac_;
                 if (merged) {
                     // sub-step 0 calls act(meta) and then act(None); the second call recomputes the same controls
@@ -1500,12 +1514,12 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
                     st_ = GF(F_ACT_STEER, i);
                     ac_ = GF(F_ACT_ACC, i);
                 }
-                vehicle_step<DIAG>(ev, p, i, sub < 3 ? sub : 2, e, shield_counts, st_, ac_);
+                vehicle_step<DIAG>(ev, p, i, sub < 3 ? sub : 2, e, shield_counts, st_, ac_, rec1vx, ge);
             }
         }
         PHASE_BARRIER(2);
         if (running) {
-            if (any_close_pair(ev)) collision_pass(ev);
+            if (uint32_t close = close_pair_mask(ev)) collision_pass(ev, close);
             time = min(time + 1, (int)EI_TIME_MASK);
             if (is_terminal(ev, steps, p.cfg.duration_steps)) running = false;  // abstract.py:530
         }

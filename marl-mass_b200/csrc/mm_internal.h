@@ -26,6 +26,7 @@ constexpr int TILE = MM_TILE;   // envs per tile == threads per CTA of the step 
 
 enum F64Field {
     F_X = 0, F_Y, F_H, F_V,          // position, heading, speed            (staged in shared memory)
+    F_COSH, F_SINH,                  // cos / sin of the heading (derived; refreshed by every move; staged as well)
     F_TSPEED,                        // target_speed
     F_GVX,                           // fg_params["g"]["vx"] of the last integration
     F_REC1VX,                        // state_hist[-1]["vx"] (x of that record == current x)
@@ -34,10 +35,10 @@ enum F64Field {
     F_SAFE_STEER, F_SAFE_ACC,        // shielded action of the last step()
     F_TIMER,                         // IDMVehicle.timer
     F_MINHW,                         // MDPLCVehicle.min_headway
-    F_COSH, F_SINH,                  // cos / sin of the current heading (derived; refreshed by every move)
     F_STEERANG,                      // MDPLCVehicle.steering_angle (lateral_control = steer_vel only)
     F_COUNT
 };
+constexpr int N_HOT = 6;             // fields F_X .. F_SINH live in shared memory during a step
 
 // flags word
 constexpr uint32_t FL_KIND_SHIFT = 0, FL_KIND_MASK = 3u;
