@@ -393,7 +393,8 @@ def main():
                              "ms_mean": float(np.mean(qp_runs)), "bytes_per_solve": 50, "achieved_GBps": nq * 50 / (qp_ms * 1e-3) / 1e9,
                              "hbm_frac": nq * 50 / (qp_ms * 1e-3) / 1e9 / peak, "dtype": "f64"}
     if args.policy:
-        line["config"]["actions"] = "sampled on device from the MAPPO actor 30-128-128-5 (torch, fp32) inside the timed region"
+        line["config"]["actions"] = ("sampled on device from the MAPPO actor 30-128-128-5 inside the timed region "
+                                     "(mm_actor_sample: fused TF32 forward + inverse-CDF draw, one launch per step)")
     if rank == 0 and world == 1 and not args.skip_cpu:
         v_cpu, cores, n_steps, e_cpu, _ = cpu_port_throughput(wl["cfg"], args.cpu_seconds, min(E, 16384))
         line["cpu_baseline"] = {"value": v_cpu, "unit": "agent-steps/s", "cores": cores, "kind": "port",

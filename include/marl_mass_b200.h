@@ -141,6 +141,27 @@ int mm_stats(mm_env *env, mm_stats_t *out, int reset);    /* synchronous */
 int mm_shield_qp(const double *a, const double *c_lead, const double *c_adj, const uint8_t *has_adj,
                  const double *lo, const double *hi, int64_t n, double *u, uint8_t *active, void *stream);
 
+/* Caller side of the path (BASELINE configs[3]: policy + env on the device).
+ *
+ * mm_actor_sample: the shared MAPPO actor (marl/single_agent/Model_common.py:5-23: Linear 30-128, ReLU, Linear 128-128,
+ * ReLU, Linear 128-5, log-softmax) evaluated on n_rows observation rows [n_rows][30] f32 and, fused with it, the
+ * exploration draw of marl/mappo.py:209-228 (np.random.choice(p = softmax): inverse CDF of one uniform per row;
+ * here Philox4x32-10 keyed by (seed, step, row)).  Weights are torch.nn.Linear parameters as they lie in memory
+ * (weight [out][in], bias [out]), TF32 tensor-core math with fp32 accumulation.  n_agents (nullable) [n_rows / 12]:
+ * rows whose slot index (row % 12) is >= n_agents[row / 12] get action 1 (IDLE).  logp_all [n_rows][5] and
+ * logp_sel [n_rows] are optional outputs (log-probabilities of all actions / of the drawn one).  All pointers are
+ * DEVICE pointers; enqueued on `stream`, no synchronisation. */
+int mm_actor_sample(const float *obs, const int32_t *n_agents, int64_t n_rows, const float *w1, const float *b1,
+                    const float *w2, const float *b2, const float *w3, const float *b3, uint64_t seed, uint64_t step,
+                    int8_t *actions, float *logp_all, float *logp_sel, void *stream);
+
+/* mm_discounted_returns: MAPPO._discount_reward (marl/mappo.py:364-370) for every (env, agent) column of a rollout at
+ * once: out[t][c] = rewards[t][c] + gamma * out[t+1][c], restarted after a step with dones[t][c / cols_per_env] != 0,
+ * seeded after the last step with final_value[c] (nullable: 0).  rewards / out [T][n_cols] f32, dones
+ * [T][n_cols / cols_per_env] u8, DEVICE pointers. */
+int mm_discounted_returns(const float *rewards, const uint8_t *dones, const float *final_value, float gamma, int T,
+                          int64_t n_cols, int cols_per_env, float *out, void *stream);
+
 /* Launch bookkeeping for bench.py ("gpu_launches") */
 int64_t mm_kernel_launches(const mm_env *env);
 const char *mm_last_error(void);

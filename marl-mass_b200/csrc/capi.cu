@@ -376,4 +376,25 @@ int mm_shield_qp(const double *a, const double *c_lead, const double *c_adj, con
     return 0;
 }
 
+int mm_actor_sample(const float *obs, const int32_t *n_agents, int64_t n_rows, const float *w1, const float *b1,
+                    const float *w2, const float *b2, const float *w3, const float *b3, uint64_t seed, uint64_t step,
+                    int8_t *actions, float *logp_all, float *logp_sel, void *stream) {
+    if (!obs || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !actions) return fail(MM_ERR_ARG, "null argument");
+    if (n_rows < 0) return fail(MM_ERR_ARG, "n_rows must be >= 0");
+    if (n_agents && n_rows % MAXV != 0) return fail(MM_ERR_ARG, "n_rows must be a multiple of MM_MAXV when n_agents is given");
+    if (launch_actor_sample(obs, n_agents, n_rows, w1, b1, w2, b2, w3, b3, seed, step, actions, logp_all, logp_sel, stream))
+        return fail(MM_ERR_CUDA, cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
+
+int mm_discounted_returns(const float *rewards, const uint8_t *dones, const float *final_value, float gamma, int T,
+                          int64_t n_cols, int cols_per_env, float *out, void *stream) {
+    if (!rewards || !dones || !out) return fail(MM_ERR_ARG, "null argument");
+    if (T < 0 || n_cols < 0 || cols_per_env <= 0 || n_cols % cols_per_env != 0)
+        return fail(MM_ERR_ARG, "bad rollout shape");
+    if (launch_discounted_returns(rewards, dones, final_value, gamma, T, n_cols, cols_per_env, out, stream))
+        return fail(MM_ERR_CUDA, cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
+
 }  // extern "C"

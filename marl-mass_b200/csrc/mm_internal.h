@@ -108,6 +108,13 @@ void launch_unpack_state(const DevState &st, int n_envs, double *f64_em, int32_t
 void launch_qp(const double *a, const double *c_lead, const double *c_adj, const uint8_t *has_adj,
                const double *lo, const double *hi, int64_t n, double *u, uint8_t *active, void *stream);
 
+// caller-side kernels (actor_sample.cu)
+int launch_actor_sample(const float *obs, const int32_t *n_agents, int64_t n_rows, const float *w1, const float *b1,
+                        const float *w2, const float *b2, const float *w3, const float *b3, uint64_t seed, uint64_t step,
+                        int8_t *actions, float *logp_all, float *logp_sel, void *stream);
+int launch_discounted_returns(const float *rewards, const uint8_t *dones, const float *final_value, float gamma, int T,
+                              int64_t n_cols, int cols_per_env, float *out, void *stream);
+
 // element (field f, slot i) of env e
 __host__ __device__ inline size_t f64_index(size_t e, int f, int i) {
     return (((e / TILE) * F_COUNT + (size_t)f) * MAXV + (size_t)i) * TILE + (e % TILE);

@@ -12,9 +12,12 @@ otherwise) and the PPO-clip / critic losses of `MAPPO.train` (mappo.py:161-206) 
 (env, agent, t) sample instead of looped per agent.  The learner itself stays out of scope for the hot-path work;
 this module is the caller that lets BASELINE configs[3] (policy + env on device) be measured.
 """
+import ctypes as C
+
 import torch
 from torch import nn
 
+from . import _lib
 from ._lib import MAXV, NA, NS
 
 
@@ -48,22 +51,57 @@ class CriticNetwork(nn.Module):
         return self.fc3(out)
 
 
-def discounted_returns(rewards, dones, final_value, gamma):
-    """R_t = r_t + gamma * R_{t+1}, restarted after a terminal step (mappo.py:364-370 run per episode).
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
 
-    rewards [T, ...], dones [T, ...] (1 where step t ended its episode), final_value [...] = bootstrap for the
-    step after the last one (ignored where the last step was terminal)."""
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def discounted_returns(rewards, dones, final_value, gamma):
+    """R_t = r_t + gamma * R_{t+1}, restarted after a terminal step (mappo.py:364-370 run per episode), one CUDA
+    kernel for the whole rollout (mm_discounted_returns).
+
+    rewards [T, E, A] f32 cuda, dones [T, E] (non-zero where step t ended the episode of env e), final_value [E, A]
+    = bootstrap for the step after the last one (ignored where the last step was terminal) or None."""
+    T, E, A = rewards.shape
+    rewards = rewards.contiguous().float()
+    d8 = (dones != 0).to(torch.uint8).contiguous()
+    assert rewards.is_cuda and d8.shape == (T, E)
+    fv = None if final_value is None else final_value.contiguous().float()
     out = torch.empty_like(rewards)
-    running = final_value
-    for t in range(rewards.shape[0] - 1, -1, -1):
-        running = rewards[t] + gamma * running * (1.0 - dones[t])
-        out[t] = running
+    _lib.check(_lib.lib().mm_discounted_returns(_ptr(rewards), _ptr(d8), _ptr(fv), C.c_float(gamma), T, C.c_int64(E * A),
+                                                A, _ptr(out), _stream()))
     return out
+
+
+def actor_sample(actor, obs, n_agents=None, seed=0, step=0, want_logp=False):
+    """Fused actor forward + exploration draw (mm_actor_sample): obs [..., 30] f32 cuda -> actions int8 [...].
+
+    `actor` is an ActorNetwork (or any module with fc1/fc2/fc3 Linear layers 30-128-128-5); its parameters are read
+    in place.  n_agents [E] int32 marks the live rows when obs is the env's [E, 12, 30] buffer.  With want_logp the
+    log-probabilities of all five actions are returned too ([..., 5] f32)."""
+    rows = obs.numel() // NS
+    obs = obs.contiguous()
+    assert obs.is_cuda and obs.dtype == torch.float32
+    w = [actor.fc1.weight, actor.fc1.bias, actor.fc2.weight, actor.fc2.bias, actor.fc3.weight, actor.fc3.bias]
+    assert tuple(w[0].shape) == (128, NS) and tuple(w[2].shape) == (128, 128) and tuple(w[4].shape) == (NA, 128)
+    w = [t.detach().contiguous().float() for t in w]
+    actions = torch.empty(obs.shape[:-1], dtype=torch.int8, device=obs.device)
+    logp = torch.empty(obs.shape[:-1] + (NA,), dtype=torch.float32, device=obs.device) if want_logp else None
+    if n_agents is not None:
+        assert n_agents.dtype == torch.int32 and n_agents.is_cuda and n_agents.numel() * MAXV == rows
+    _lib.check(_lib.lib().mm_actor_sample(_ptr(obs), _ptr(n_agents), C.c_int64(rows), *[_ptr(t) for t in w],
+                                          C.c_uint64(seed), C.c_uint64(step), _ptr(actions), _ptr(logp), _ptr(None),
+                                          _stream()))
+    return (actions, logp) if want_logp else actions
 
 
 class BatchedMAPPORollout(object):
     def __init__(self, env, actor=None, critic=None, roll_out_n_steps=100, reward_gamma=0.99, reward_scale=20.0,
-                 reward_type="regionalR", clip_param=0.2, actor_lr=5e-4, critic_lr=5e-4, max_grad_norm=5.0):
+                 reward_type="regionalR", clip_param=0.2, actor_lr=5e-4, critic_lr=5e-4, max_grad_norm=5.0, seed=0,
+                 fused=True):
         self.env = env
         dev = torch.device("cuda", env.device)
         self.actor = (actor or ActorNetwork()).to(dev)
@@ -83,13 +121,26 @@ class BatchedMAPPORollout(object):
         self._slot = torch.arange(MAXV, device=dev)[None, :]
         self.buf = None
         self.E = E
+        self.seed, self._draws = int(seed), 0
+        self.fused = bool(fused)
 
     @torch.no_grad()
-    def _act(self, obs, n_agents):
+    def act_fused(self, obs, n_agents):
+        """The draw of `act_torch` through the fused CUDA kernel (TF32 actor + inverse-CDF sampling, one launch)."""
+        self._draws += 1
+        a = actor_sample(self.actor, obs, n_agents, seed=self.seed, step=self._draws)
+        return a, self._slot < n_agents[:, None]
+
+    @torch.no_grad()
+    def act_torch(self, obs, n_agents):
+        """Plain torch fp32 actor + torch.multinomial: the numerics reference of `act_fused`."""
         logp = self.actor(obs.view(-1, NS))                               # [E*12, 5]
         a = torch.multinomial(logp.exp(), 1).view(self.E, MAXV)           # exploration_action, mappo.py:225-230
         live = self._slot < n_agents[:, None]
         return torch.where(live, a, torch.ones_like(a)).to(torch.int8), live
+
+    def _act(self, obs, n_agents):
+        return self.act_fused(obs, n_agents) if self.fused else self.act_torch(obs, n_agents)
 
     @torch.no_grad()
     def collect(self):
@@ -120,7 +171,7 @@ class BatchedMAPPORollout(object):
         a_fin, _ = self._act(self.obs, v["n_agents"])
         onehot = torch.nn.functional.one_hot(a_fin.long(), NA).float()
         final_value = self.critic(self.obs.view(-1, NS), onehot.view(-1, NA)).view(E, MAXV)
-        returns = discounted_returns(R, D[:, :, None].expand(T, E, MAXV), final_value, self.gamma)
+        returns = discounted_returns(R, D, final_value, self.gamma)
         self.buf = dict(states=S, actions=A, returns=returns, live=L, dones=D, rewards=R)
         return self.buf
 

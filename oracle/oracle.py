@@ -166,3 +166,31 @@ def state_from_golden(g, rows):
     # the engines know two kinds: CAV (MDPLCVehicle, or MDPVehicle in the v0 env) and HDV (IDMVehicle[Hist])
     st["kind"] = np.where(st["kind"] == 3, 1, np.where(st["kind"] == 4, 2, st["kind"])).astype(np.int32)
     return st
+
+
+# --------------------------------------------------------------------------------------------------
+# caller-side restatements: numpy float64, pinned against tests/golden/mappo_caller.npz
+# --------------------------------------------------------------------------------------------------
+def mappo_discount(rewards, dones, final_value, gamma, cols_per_env=1):
+    """marl/mappo.py:364-370 (`running_add = running_add * gamma + r[t]`) for columns [T, n], with the episode
+    boundary handling of MAPPO.interact (102-158): a rollout segment that ended its episode starts from 0."""
+    rewards = np.asarray(rewards, dtype=np.float64)
+    T, n = rewards.shape
+    out = np.zeros_like(rewards)
+    run = np.zeros(n) if final_value is None else np.asarray(final_value, dtype=np.float64).copy()
+    for t in range(T - 1, -1, -1):
+        d = np.repeat(np.asarray(dones[t]) != 0, cols_per_env)
+        run = np.where(d, 0.0, run)
+        run = run * gamma + rewards[t]
+        out[t] = run
+    return out
+
+
+def actor_log_probs(w, obs):
+    """marl/single_agent/Model_common.py:5-23 with output_act = log_softmax: w = dict(fc1_weight, fc1_bias, ...)."""
+    x = np.asarray(obs, dtype=np.float64)
+    h = np.maximum(x @ w["fc1_weight"].T.astype(np.float64) + w["fc1_bias"], 0.0)
+    h = np.maximum(h @ w["fc2_weight"].T.astype(np.float64) + w["fc2_bias"], 0.0)
+    z = h @ w["fc3_weight"].T.astype(np.float64) + w["fc3_bias"]
+    z = z - z.max(axis=1, keepdims=True)
+    return z - np.log(np.exp(z).sum(axis=1, keepdims=True))

@@ -1,0 +1,41 @@
+"""Where the policy-in-the-loop step goes (BASELINE configs[3]): python profiles/time_policy.py [envs]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import marl_mass_b200 as mm
+from bench import WORKLOADS
+from marl_mass_b200.rollout import BatchedMAPPORollout
+
+E = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+cfg = dict(mm.DEFAULT_CONFIG, **WORKLOADS["mass_td3_srew"]["cfg"])
+env = mm.MergeEnvBatched(E, cfg)
+env.reset(seed=1)
+pol = BatchedMAPPORollout(env, roll_out_n_steps=1)
+v = env.buffers()
+
+
+def timed(fn, n=20):
+    for _ in range(3):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); a.record()
+    for _ in range(n):
+        fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+
+
+acts, _ = pol._act(v["obs"], v["n_agents"])
+obs = v["obs"]
+with torch.no_grad():
+    logp = pol.actor(obs.view(-1, mm.NS))
+    print("actor forward      %.3f ms" % timed(lambda: pol.actor(obs.view(-1, mm.NS))))
+    print("exp + multinomial  %.3f ms" % timed(lambda: torch.multinomial(logp.exp(), 1)))
+print("act_torch (all)    %.3f ms" % timed(lambda: pol.act_torch(v["obs"], v["n_agents"])))
+print("env.step           %.3f ms" % timed(lambda: env.step(acts, auto_reset=True)))
+print("act + step         %.3f ms" % timed(lambda: env.step(pol._act(v["obs"], v["n_agents"])[0], auto_reset=True)))
+print("act_fused          %.3f ms" % timed(lambda: pol.act_fused(v["obs"], v["n_agents"])))
+print("act_fused + step   %.3f ms" % timed(lambda: env.step(pol.act_fused(v["obs"], v["n_agents"])[0], auto_reset=True)))
+lp = mm.rollout.actor_sample(pol.actor, obs, v["n_agents"], seed=1, step=1, want_logp=True)[1]
+print("max |logp_fused - logp_torch| = %.3e" % float((lp.view(-1, 5) - logp).abs().max()))

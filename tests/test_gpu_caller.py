@@ -1,0 +1,164 @@
+"""GPU suite, caller side: the fused actor + exploration-draw kernel and the discounted-return
+kernel, through the C ABI, against the reference vectors (tests/golden/mappo_caller.npz), the numpy restatements in
+oracle/ and a plain torch fp32 evaluation of the same network.
+
+Tolerances: the actor runs on TF32 tensor cores (10-bit mantissa, fp32 accumulate): log-probabilities within 2e-2
+absolute of the fp32 network on O(1) inputs (observed ~3e-3); returns are fp32 sums: 1e-5 relative.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+LOGP_TOL = 2e-2
+
+
+@pytest.fixture(scope="module")
+def mm():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import marl_mass_b200 as m
+    m.lib()
+    return m
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "mappo_caller.npz"))
+
+
+def make_actor(g, torch, rollout):
+    actor = rollout.ActorNetwork().cuda()
+    sd = {k[2:].replace("_", ".", 1): torch.from_numpy(g[k]) for k in g.files if k.startswith("w_")}
+    actor.load_state_dict(sd)
+    return actor
+
+
+def test_actor_log_probs_match_the_reference_network(mm, golden):
+    import torch
+    from marl_mass_b200 import rollout
+    actor = make_actor(golden, torch, rollout)
+    obs = torch.from_numpy(golden["obs"]).cuda()
+    acts, logp = rollout.actor_sample(actor, obs, None, seed=3, step=1, want_logp=True)
+    torch.cuda.synchronize()
+    logp = logp.cpu().numpy()
+    assert np.abs(logp - golden["logp"]).max() < LOGP_TOL           # reference ActorNetwork output (fp32, CPU)
+    assert np.abs(np.exp(logp).sum(1) - 1).max() < 1e-5
+    a = acts.cpu().numpy()
+    assert a.shape == (obs.shape[0],) and a.min() >= 0 and a.max() <= 4
+
+
+def test_actor_matches_torch_fp32_on_env_observations_and_masks_absent_agents(mm):
+    import torch
+    import oracle
+    from marl_mass_b200 import rollout
+    E = 2048
+    env = mm.MergeEnvBatched(E, dict(mm.DEFAULT_CONFIG, safety_guarantee="cbf-cav", traffic_density=3,
+                                     HEADWAY_TIME=0.5, cbf_eta=0.03125), device=0)
+    obs, _ = env.reset(seed=5)
+    v = env.buffers()
+    torch.manual_seed(0)
+    actor = rollout.ActorNetwork().cuda()
+    for p in actor.parameters():                    # larger weights than the default init: a sharper policy
+        p.data.mul_(3.0)
+    acts, logp = rollout.actor_sample(actor, obs, v["n_agents"], seed=9, step=4, want_logp=True)
+    with torch.no_grad():
+        want = actor(obs.view(-1, mm.NS)).view(E, mm.MAXV, mm.NA)
+    torch.cuda.synchronize()
+    assert float((logp - want).abs().max()) < LOGP_TOL
+    # numpy float64 restatement of the reference network
+    w = {k.replace(".", "_"): t.detach().cpu().numpy() for k, t in actor.state_dict().items()}
+    ref = oracle.actor_log_probs(w, obs.view(-1, mm.NS).cpu().numpy()).reshape(E, mm.MAXV, mm.NA)
+    assert np.abs(logp.cpu().numpy() - ref).max() < LOGP_TOL
+    live = (torch.arange(mm.MAXV, device="cuda")[None, :] < v["n_agents"][:, None])
+    assert bool((acts[~live] == 1).all())           # absent agents idle
+    assert bool(((acts >= 0) & (acts <= 4)).all())
+    # same (seed, step) -> same draw; another step -> another draw
+    again = rollout.actor_sample(actor, obs, v["n_agents"], seed=9, step=4)
+    other = rollout.actor_sample(actor, obs, v["n_agents"], seed=9, step=5)
+    assert bool((again == acts).all()) and float((other != acts)[live].float().mean()) > 0.2
+    env.close()
+
+
+def test_exploration_draw_follows_the_softmax(mm):
+    """np.random.choice(p = softmax) (mappo.py:223-228): empirical action frequencies of many draws from a few fixed
+    observation rows against the kernel's own probabilities."""
+    import torch
+    from marl_mass_b200 import rollout
+    torch.manual_seed(1)
+    actor = rollout.ActorNetwork().cuda()
+    for p in actor.parameters():
+        p.data.mul_(4.0)
+    base = torch.rand(8, mm.NS, device="cuda") * 2 - 1
+    reps = 1 << 16
+    obs = base[:, None, :].expand(8, reps, mm.NS).contiguous()          # row r of `base` repeated `reps` times
+    freq = torch.zeros(8, mm.NA, device="cuda")
+    n_draws = 4
+    for step in range(n_draws):
+        a, logp = rollout.actor_sample(actor, obs, None, seed=21, step=step, want_logp=True)
+        freq += torch.nn.functional.one_hot(a.long(), mm.NA).float().sum(1)
+    p = logp[:, 0, :].exp()
+    freq /= reps * n_draws
+    # binomial standard error at n = 262144 is <= 1e-3; 6 sigma
+    assert float((freq - p).abs().max()) < 6e-3, (freq, p)
+    assert float(p.max()) > 0.4                                          # the test policy is not uniform
+
+
+def test_discounted_returns_match_reference_vectors_and_restatement(mm, golden):
+    import torch
+    import oracle
+    from marl_mass_b200 import rollout
+    g = golden
+    gamma = float(g["gamma"])
+    # the reference's own outputs: one column per call of MAPPO._discount_reward, shorter columns end in a "done" pad
+    for k, T in enumerate(g["lengths"]):
+        r = torch.from_numpy(g["rewards"][:T, k].astype(np.float32)).cuda().view(T, 1, 1)
+        d = torch.zeros(T, 1, device="cuda")
+        fv = torch.tensor([[float(g["finals"][k])]], device="cuda")
+        got = rollout.discounted_returns(r, d, fv, gamma).view(T).cpu().numpy()
+        want = g["returns"][:T, k]
+        assert np.abs(got - want).max() <= 1e-5 * max(1.0, np.abs(want).max())
+    # a full rollout with episode boundaries against the float64 restatement
+    rng = np.random.RandomState(3)
+    T, E, A = 100, 777, 12
+    r = rng.uniform(-3, 1, size=(T, E, A)).astype(np.float32)
+    d = (rng.uniform(size=(T, E)) < 0.02)
+    fv = rng.uniform(-2, 2, size=(E, A)).astype(np.float32)
+    got = rollout.discounted_returns(torch.from_numpy(r).cuda(), torch.from_numpy(d).cuda(), torch.from_numpy(fv).cuda(),
+                                     gamma).cpu().numpy()
+    want = oracle.mappo_discount(r.reshape(T, E * A), d, fv.reshape(-1), gamma, cols_per_env=A).reshape(T, E, A)
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+    got0 = rollout.discounted_returns(torch.from_numpy(r).cuda(), torch.from_numpy(d).cuda(), None, gamma).cpu().numpy()
+    want0 = oracle.mappo_discount(r.reshape(T, E * A), d, None, gamma, cols_per_env=A).reshape(T, E, A)
+    assert np.abs(got0 - want0).max() <= 1e-5 * np.abs(want0).max()
+
+
+def test_rollout_collect_and_update_run_on_the_fused_path(mm):
+    """BatchedMAPPORollout end to end (fused actor draw, env step, CUDA returns, PPO update): shapes, masks, finite
+    losses, and the fused and torch draws agree in distribution."""
+    import torch
+    from marl_mass_b200 import rollout
+    E = 1024
+    env = mm.MergeEnvBatched(E, dict(mm.DEFAULT_CONFIG, safety_guarantee="cbf-cav", traffic_density=3, HEADWAY_TIME=0.5,
+                                     cbf_eta=0.03125, agent_reward="srew", HIGH_SPEED_REWARD=4, HEADWAY_COST=1,
+                                     MERGING_LANE_COST=8), device=0)
+    torch.manual_seed(0)
+    pol = rollout.BatchedMAPPORollout(env, roll_out_n_steps=12, seed=4)
+    l0 = env.kernel_launches()
+    buf = pol.collect()
+    assert buf["states"].shape == (12, E, mm.MAXV, mm.NS) and buf["returns"].shape == (12, E, mm.MAXV)
+    assert bool(torch.isfinite(buf["returns"]).all())
+    assert env.kernel_launches() > l0
+    stats = pol.update(minibatch=1 << 15)
+    assert np.isfinite(stats["actor_loss"]) and np.isfinite(stats["critic_loss"]) and stats["samples"] > 12 * E * 6
+    v = env.buffers()
+    fa, live = pol.act_fused(v["obs"], v["n_agents"])
+    ta, _ = pol.act_torch(v["obs"], v["n_agents"])
+    hf = torch.bincount(fa[live].long(), minlength=5).float() / live.sum()
+    ht = torch.bincount(ta[live].long(), minlength=5).float() / live.sum()
+    assert float((hf - ht).abs().max()) < 0.03
+    env.close()

@@ -151,15 +151,17 @@ def test_stats_all_reduce_world_size_2_gloo(tmp_path):
 
 
 def test_discounted_returns_match_reference_formula():
-    """rollout.discounted_returns == MAPPO._discount_reward (marl/mappo.py:364-370) run per episode segment."""
+    """The episode-segment semantics of the rollout's returns (oracle.mappo_discount, the checker of the CUDA kernel in
+    tests/test_gpu_caller.py) == MAPPO._discount_reward (marl/mappo.py:364-370) run per episode segment."""
     import torch
-    from marl_mass_b200.rollout import discounted_returns, ActorNetwork, CriticNetwork
+    import oracle
+    from marl_mass_b200.rollout import ActorNetwork, CriticNetwork
     rng = np.random.RandomState(0)
     T, N, gamma = 37, 5, 0.99
     r = rng.randn(T, N)
     d = (rng.rand(T, N) < 0.1).astype(np.float64)
     fv = rng.randn(N)
-    got = discounted_returns(torch.from_numpy(r), torch.from_numpy(d), torch.from_numpy(fv), gamma).numpy()
+    got = oracle.mappo_discount(r, d, fv, gamma)
     for n in range(N):
         start = 0
         ends = list(np.where(d[:, n] > 0)[0]) + ([T - 1] if d[T - 1, n] == 0 else [])

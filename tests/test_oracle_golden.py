@@ -149,3 +149,24 @@ def test_v0_env_teacher_forced_and_free_running(name):
             o = orc.step(cfg, s1, g["act"][t:t + 1])
             assert int(o["done"][0]) == int(g["done"][t])
         compare_states(s1, golden_state(g, [ep[j + 1] - 1]), 1e-7, "%s episode %d" % (name, j), v0=True)
+
+
+def test_caller_side_restatements_match_the_reference_vectors():
+    """oracle.mappo_discount / oracle.actor_log_probs against MAPPO._discount_reward and ActorNetwork outputs frozen
+    from the reference (oracle/refharness/gen_golden_mappo.py)."""
+    import os
+    import oracle
+    from conftest import ROOT
+    g = np.load(os.path.join(ROOT, "tests", "golden", "mappo_caller.npz"))
+    for k, T in enumerate(g["lengths"]):
+        got = oracle.mappo_discount(g["rewards"][:T, k:k + 1], np.zeros((T, 1)), g["finals"][k:k + 1], float(g["gamma"]))
+        assert np.abs(got[:, 0] - g["returns"][:T, k]).max() < 1e-12
+    w = {k[2:]: g[k] for k in g.files if k.startswith("w_")}
+    assert np.abs(oracle.actor_log_probs(w, g["obs"]) - g["logp"]).max() < 5e-6   # reference runs the net in fp32
+    # an episode boundary inside the segment restarts the sum (MAPPO.interact pushes one segment per episode)
+    r = np.arange(6, dtype=np.float64).reshape(6, 1)
+    d = np.array([0, 0, 1, 0, 0, 0]).reshape(6, 1)
+    got = oracle.mappo_discount(r, d, np.array([10.0]), 0.5)
+    a = oracle.mappo_discount(r[:3], np.zeros((3, 1)), np.array([0.0]), 0.5)
+    b = oracle.mappo_discount(r[3:], np.zeros((3, 1)), np.array([10.0]), 0.5)
+    assert np.allclose(got[:, 0], np.concatenate([a[:, 0], b[:, 0]]))
