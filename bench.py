@@ -339,16 +339,31 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e_stats = env.stats(reset=True)
+    del host_out
+    # the same with the observations packed as the reference returns them (live agents' rows only): mm_step_host_ragged
+    rag_out = env.alloc_host_out(pinned=True, ragged=True)
+    env.step_host_ragged(host_act[0], auto_reset=True, out=rag_out)
+    env.stats(reset=True)
+    barrier()
+    t0 = time.perf_counter()
+    for t in range(K2):
+        env.step_host_ragged(host_act[t % 4], auto_reset=True, out=rag_out)
+    torch.cuda.synchronize()
+    rag_s = time.perf_counter() - t0
+    rag_stats = env.stats(reset=True)
+    rag_rows = float(rag_out["n_agents"].sum())
 
     # fold over ranks: time = max, work = sum
     tot = mmd.all_reduce_stats(stats)
     e2e_tot = mmd.all_reduce_stats(e2e_stats)
+    rag_tot = mmd.all_reduce_stats(rag_stats)
     if world > 1:
-        tmax = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device="cuda")
+        tmax = torch.tensor([ms_total, e2e_s, rag_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ms_total, e2e_s = float(tmax[0]), float(tmax[1])
+        ms_total, e2e_s, rag_s = float(tmax[0]), float(tmax[1]), float(tmax[2])
     value = tot["agent_steps"] / (ms_total * 1e-3)
-    e2e_value = e2e_tot["agent_steps"] / e2e_s
+    dense_value = e2e_tot["agent_steps"] / e2e_s
+    e2e_value = rag_tot["agent_steps"] / rag_s
 
     mean_agents = stats["agent_steps"] / max(stats["env_steps"], 1.0)
     mean_hdv = 0.0 if cfg["traffic_type"] == "cav" else {1: 2.0, 2: 3.0, 3: 4.0}[int(cfg["traffic_density"])]
@@ -380,8 +395,11 @@ def main():
                    "crashed_episode_frac": tot["crashed_episodes"] / max(tot["episodes"], 1.0)},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": E * mm.MAXV,
-                "d2h_bytes_per_step": E * (mm.MAXV * mm.NS * 4 + 4 + 1 + mm.MAXV * 4 + 4), "steps": K2,
-                "api": "mm_step_host (pinned host buffers, 64Ki-env chunks round-robin on 4 streams: copies overlap compute)"},
+                "d2h_bytes_per_step": int(rag_rows * mm.NS * 4 + E * (8 + 4 + 1 + mm.MAXV * 4 + 4)), "steps": K2,
+                "api": "mm_step_host_ragged (pinned host buffers, 64Ki-env chunks round-robin on 4 streams; observation "
+                       "rows of the live agents only, as the reference returns them: packed on the device, exact-size copies)",
+                "dense": {"value": dense_value, "d2h_bytes_per_step": E * (mm.MAXV * mm.NS * 4 + 4 + 1 + mm.MAXV * 4 + 4),
+                          "api": "mm_step_host (dense obs [E,12,30] by cudaMemcpyAsync)"}},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "step_kernel<false>", "kernel_ms": kms,

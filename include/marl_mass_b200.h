@@ -130,6 +130,15 @@ int mm_step(mm_env *env, const int8_t *actions_dev, int auto_reset, void *stream
 int mm_step_host(mm_env *env, const int8_t *actions, int auto_reset, float *obs, float *reward, uint8_t *done,
                  float *regional_rewards, int32_t *n_agents);
 
+/* mm_step_host with the observations as the reference returns them (obs ndarray [A, n_s] per env,
+ * merge_env_v1.py:126-166): only the rows of the agents that exist.  Env e's rows are
+ * obs_rows[row_offset[e] * 30 .. (row_offset[e] + n_agents[e]) * 30); offsets are absolute, increasing, and dense inside
+ * every 64 Ki-env chunk (chunk c starts at row chunk_first_env * MM_MAXV; row_offset[n_envs] = n_envs * MM_MAXV).
+ * obs_rows has room for n_envs * MM_MAXV rows of 30 f32 (pinned memory for full PCIe speed); only the packed rows are
+ * transferred: a quarter fewer bytes at hard density.  row_offset [n_envs + 1] int64 host; the other outputs as in
+ * mm_step_host (nullable). */
+int mm_step_host_ragged(mm_env *env, const int8_t *actions, int auto_reset, float *obs_rows, int64_t *row_offset,
+                        float *reward, uint8_t *done, float *regional_rewards, int32_t *n_agents);
 int mm_buffers_get(mm_env *env, mm_buffers *out);
 int mm_get_state(mm_env *env, mm_state_host *dst);        /* synchronous */
 int mm_set_state(mm_env *env, const mm_state_host *src);  /* synchronous; also refreshes obs / n_agents */

@@ -65,6 +65,7 @@ class MMError(RuntimeError):
 _lib = None
 
 EXPORTS = ("mm_create", "mm_destroy", "mm_set_config", "mm_num_envs", "mm_reset", "mm_step", "mm_step_host",
+           "mm_step_host_ragged",
            "mm_buffers_get", "mm_get_state", "mm_set_state", "mm_get_shield_diag", "mm_stats", "mm_shield_qp",
            "mm_actor_sample", "mm_discounted_returns", "mm_kernel_launches", "mm_last_error", "mm_version")
 
@@ -86,6 +87,7 @@ def lib():
     L.mm_reset.argtypes = [h, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p]
     L.mm_step.argtypes = [h, C.c_void_p, C.c_int, C.c_void_p]
     L.mm_step_host.argtypes = [h, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mm_step_host_ragged.argtypes = [h, C.c_void_p, C.c_int] + [C.c_void_p] * 6
     L.mm_buffers_get.argtypes = [h, C.POINTER(MMBuffers)]
     L.mm_get_state.argtypes = [h, C.POINTER(MMStateHost)]
     L.mm_set_state.argtypes = [h, C.POINTER(MMStateHost)]

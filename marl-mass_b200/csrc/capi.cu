@@ -34,6 +34,7 @@ int fail(mm_status code, const char *what, cudaError_t ce = cudaSuccess) {
     } while (0)
 
 constexpr int MAX_CHUNKS = 8;
+constexpr int MAX_HOST_CHUNKS = 64;   // chunks of one mm_step_host_ragged call
 constexpr int HOST_F64 = 17, HOST_I32 = 11, HOST_ENV = 5;
 
 }  // namespace
@@ -44,6 +45,11 @@ struct mm_env {
     DevState st{};
     DevOut out{};
     int8_t *actions = nullptr;
+    // mm_step_host_ragged, allocated on first use: first packed row of every env, packed-row staging, per-chunk counts
+    int64_t *row_offset = nullptr;
+    float *rows_stage = nullptr;
+    int64_t *chunk_rows_dev = nullptr, *chunk_rows_host = nullptr;
+    cudaEvent_t chunk_done[MAX_HOST_CHUNKS]{};
     size_t stats_rows = 0;
     uint64_t seed = 0;
     int64_t launches = 0;
@@ -171,6 +177,9 @@ int mm_destroy(mm_env *env) {
     cudaDeviceSynchronize();
     for (int i = 0; i < MAX_CHUNKS; ++i)
         if (env->streams[i]) cudaStreamDestroy(env->streams[i]);
+    for (int i = 0; i < MAX_HOST_CHUNKS; ++i)
+        if (env->chunk_done[i]) cudaEventDestroy(env->chunk_done[i]);
+    if (env->chunk_rows_host) cudaFreeHost(env->chunk_rows_host);
     for (void *p : env->allocs) cudaFree(p);
     delete env;
     return 0;
@@ -250,6 +259,92 @@ int mm_step_host(mm_env *env, const int8_t *actions, int auto_reset, float *obs,
             CUDA_OK(cudaMemcpyAsync(n_agents + off, env->out.n_agents + off, (size_t)count * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     }
     for (int c = 0; c < n_str; ++c) CUDA_OK(cudaStreamSynchronize(env->streams[c]));
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int mm_step_host_ragged(mm_env *env, const int8_t *actions, int auto_reset, float *obs_rows, int64_t *row_offset,
+                        float *reward, uint8_t *done, float *regional_rewards, int32_t *n_agents) {
+    if (!env) return fail(MM_ERR_ARG, "env is null");
+    if (!actions || !obs_rows || !row_offset) return fail(MM_ERR_ARG, "actions, obs_rows and row_offset are required");
+    CUDA_OK(cudaSetDevice(env->device));
+    const int E = env->n_envs;
+    if (!env->row_offset) {   // first use: staging for the packed rows, offsets, per-chunk counts, events
+        void *p = nullptr;
+        CUDA_OK(cudaMalloc(&p, ((size_t)E + 1) * sizeof(int64_t)));
+        env->allocs.push_back(p);
+        env->row_offset = static_cast<int64_t *>(p);
+        CUDA_OK(cudaMalloc(&p, (size_t)E * MAXV * NS * sizeof(float)));
+        env->allocs.push_back(p);
+        env->rows_stage = static_cast<float *>(p);
+        CUDA_OK(cudaMalloc(&p, MAX_HOST_CHUNKS * sizeof(int64_t)));
+        env->allocs.push_back(p);
+        env->chunk_rows_dev = static_cast<int64_t *>(p);
+        CUDA_OK(cudaHostAlloc(&p, MAX_HOST_CHUNKS * sizeof(int64_t), cudaHostAllocDefault));
+        env->chunk_rows_host = static_cast<int64_t *>(p);
+        for (int c = 0; c < MAX_HOST_CHUNKS; ++c) CUDA_OK(cudaEventCreateWithFlags(&env->chunk_done[c], cudaEventDisableTiming));
+    }
+    static const int chunk_target = [] {
+        const char *s = getenv("MM_HOST_CHUNK");
+        int v = s ? atoi(s) : 0;
+        return v > 0 ? v : 65536;
+    }();
+    const int n_str = 4;
+    int n_chunks = (E + chunk_target - 1) / chunk_target;
+    if (n_chunks < 1) n_chunks = 1;
+    if (n_chunks > MAX_HOST_CHUNKS) n_chunks = MAX_HOST_CHUNKS;
+    int chunk = ((E + n_chunks - 1) / n_chunks + 767) / 768 * 768;
+    // Software pipeline over the chunks, n_str deep: a chunk's compute + packing is enqueued on its stream; when its row
+    // count has arrived (one event wait on the host) its packed rows follow on the same stream - exactly that many
+    // bytes - and only then the stream's next chunk.  The copies of chunk c overlap the compute of chunks c+1..c+3.
+    auto enqueue_compute = [&](int c) -> int {
+        const int off = c * chunk;
+        const int count = E - off < chunk ? E - off : chunk;
+        cudaStream_t s = env->streams[c % n_str];
+        CUDA_OK(cudaMemcpyAsync(env->actions + (size_t)off * MAXV, actions + (size_t)off * MAXV, (size_t)count * MAXV,
+                                cudaMemcpyHostToDevice, s));
+        enqueue_step(env, env->actions, auto_reset, off, count, s);
+        // chunk c packs its rows from row off * MAXV on: offsets are absolute and increasing, dense inside a chunk
+        launch_ragged_pack(env->out.obs + (size_t)off * MAXV * NS, env->out.n_agents + off, count, (int64_t)off * MAXV,
+                           env->row_offset + off, env->chunk_rows_dev + c, env->rows_stage, s);
+        env->launches += 2;
+        CUDA_OK(cudaMemcpyAsync(env->chunk_rows_host + c, env->chunk_rows_dev + c, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        CUDA_OK(cudaEventRecord(env->chunk_done[c], s));
+        return 0;
+    };
+    auto enqueue_copies = [&](int c) -> int {
+        const int off = c * chunk;
+        const int count = E - off < chunk ? E - off : chunk;
+        cudaStream_t s = env->streams[c % n_str];
+        CUDA_OK(cudaEventSynchronize(env->chunk_done[c]));
+        const int64_t rows = env->chunk_rows_host[c];
+        const size_t first = (size_t)off * MAXV * NS;
+        if (rows > 0)
+            CUDA_OK(cudaMemcpyAsync(obs_rows + first, env->rows_stage + first, (size_t)rows * NS * sizeof(float),
+                                    cudaMemcpyDeviceToHost, s));
+        CUDA_OK(cudaMemcpyAsync(row_offset + off, env->row_offset + off, (size_t)count * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        if (reward)
+            CUDA_OK(cudaMemcpyAsync(reward + off, env->out.reward + off, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (done)
+            CUDA_OK(cudaMemcpyAsync(done + off, env->out.done + off, (size_t)count, cudaMemcpyDeviceToHost, s));
+        if (regional_rewards)
+            CUDA_OK(cudaMemcpyAsync(regional_rewards + (size_t)off * MAXV, env->out.regional_rewards + (size_t)off * MAXV,
+                                    (size_t)count * MAXV * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (n_agents)
+            CUDA_OK(cudaMemcpyAsync(n_agents + off, env->out.n_agents + off, (size_t)count * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        return 0;
+    };
+    int used = 0;
+    while (used < n_chunks && used * chunk < E) ++used;
+    for (int c = 0; c < used && c < n_str; ++c)
+        if (int rc = enqueue_compute(c)) return rc;
+    for (int c = 0; c < used; ++c) {
+        if (int rc = enqueue_copies(c)) return rc;
+        if (c + n_str < used)
+            if (int rc = enqueue_compute(c + n_str)) return rc;
+    }
+    for (int c = 0; c < n_str; ++c) CUDA_OK(cudaStreamSynchronize(env->streams[c]));
+    row_offset[E] = (int64_t)E * MAXV;
     CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -108,6 +108,11 @@ void launch_unpack_state(const DevState &st, int n_envs, double *f64_em, int32_t
 void launch_qp(const double *a, const double *c_lead, const double *c_adj, const uint8_t *has_adj,
                const double *lo, const double *hi, int64_t n, double *u, uint8_t *active, void *stream);
 
+// obs / n_agents / row_offset_dev are passed already offset to the chunk; rows_stage is the base of the device staging
+// buffer [E * MAXV][NS] (row offsets are absolute); chunk_rows_dev receives the chunk's packed row count
+void launch_ragged_pack(const float *obs, const int32_t *n_agents, int count, int64_t base_row, int64_t *row_offset_dev,
+                        int64_t *chunk_rows_dev, float *rows_stage, void *stream);
+
 // caller-side kernels (actor_sample.cu)
 int launch_actor_sample(const float *obs, const int32_t *n_agents, int64_t n_rows, const float *w1, const float *b1,
                         const float *w2, const float *b2, const float *w3, const float *b3, uint64_t seed, uint64_t step,

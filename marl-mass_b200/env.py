@@ -231,13 +231,33 @@ class MergeEnvBatched(object):
                                         C.c_void_p(ptr.get("n_agents", 0))))
         return out
 
-    def alloc_host_out(self, pinned=True):
+    def step_host_ragged(self, actions, auto_reset=False, out=None):
+        """`step_host` with the observations packed the way the reference returns them (an [A, n_s] array per env):
+        out["obs_rows"][out["row_offset"][e] : out["row_offset"][e] + out["n_agents"][e]] are env e's rows.  `out` comes
+        from `alloc_host_out(ragged=True)`."""
+        a = actions if isinstance(actions, np.ndarray) else actions.numpy()
+        assert a.dtype == np.int8 and a.flags.c_contiguous and a.size == self.n_envs * MAXV
+        if out is None:
+            out = self.alloc_host_out(ragged=True)
+        ptr = {k: (out[k].ctypes.data if isinstance(out[k], np.ndarray) else out[k].data_ptr()) for k in out}
+        _lib.check(self._L.mm_step_host_ragged(self._h, C.c_void_p(a.ctypes.data), int(bool(auto_reset)),
+                                               C.c_void_p(ptr["obs_rows"]), C.c_void_p(ptr["row_offset"]),
+                                               C.c_void_p(ptr.get("reward", 0)), C.c_void_p(ptr.get("done", 0)),
+                                               C.c_void_p(ptr.get("regional_rewards", 0)), C.c_void_p(ptr.get("n_agents", 0))))
+        return out
+
+    def alloc_host_out(self, pinned=True, ragged=False):
         import torch
         E = self.n_envs
         mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=pinned).numpy()
-        return {"obs": mk((E, MAXV, NS), torch.float32), "reward": mk((E,), torch.float32),
-                "done": mk((E,), torch.uint8), "regional_rewards": mk((E, MAXV), torch.float32),
-                "n_agents": mk((E,), torch.int32)}
+        out = {"reward": mk((E,), torch.float32), "done": mk((E,), torch.uint8),
+               "regional_rewards": mk((E, MAXV), torch.float32), "n_agents": mk((E,), torch.int32)}
+        if ragged:
+            out["obs_rows"] = mk((E * MAXV, NS), torch.float32)
+            out["row_offset"] = mk((E + 1,), torch.int64)
+        else:
+            out["obs"] = mk((E, MAXV, NS), torch.float32)
+        return out
 
     # ------------------------------------------------------------------ state (teacher forcing / checkpoint)
     def _host_state_struct(self, st):

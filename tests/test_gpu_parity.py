@@ -218,6 +218,40 @@ def test_host_buffer_step_equals_device_step(mm):
     b_env.close()
 
 
+def test_ragged_host_step_equals_device_step(mm):
+    """mm_step_host_ragged: the live rows of every env, packed, == the dense device obs,
+    over chunk boundaries (3 chunks at MM_HOST_CHUNK's default) with a short last chunk."""
+    import torch
+    cfg = dict(mm.DEFAULT_CONFIG, safety_guarantee="cbf-cav", traffic_density=3, HEADWAY_TIME=0.5, cbf_eta=0.03125)
+    E = 140001
+    a_env = mm.MergeEnvBatched(E, cfg)
+    b_env = mm.MergeEnvBatched(E, cfg)
+    a_env.reset(seed=12)
+    b_env.set_state(a_env.get_state())
+    rng = np.random.RandomState(6)
+    out = b_env.alloc_host_out(ragged=True)
+    for t in range(4):
+        a = rng.randint(0, 5, size=(E, 12)).astype(np.int8)
+        obs, rew, done, v = a_env.step(torch.from_numpy(a).cuda())
+        out["obs_rows"][:] = np.nan
+        b_env.step_host_ragged(a, out=out)
+        torch.cuda.synchronize()
+        n = v["n_agents"].cpu().numpy()
+        assert np.array_equal(n, out["n_agents"])
+        off = out["row_offset"]
+        assert off[0] == 0 and off[E] == E * 12 and np.all(np.diff(off[:E]) >= n[:-1])
+        dense = obs.cpu().numpy()
+        live = np.arange(12)[None, :] < n[:, None]
+        rows = (off[:E, None] + np.arange(12)[None, :])[live]
+        assert np.array_equal(out["obs_rows"][rows], dense[live])
+        assert np.isnan(out["obs_rows"]).all(axis=1).sum() == E * 12 - int(n.sum())   # nothing else was written
+        assert np.array_equal(rew.cpu().numpy(), out["reward"])
+        assert np.array_equal(done.cpu().numpy(), out["done"])
+        assert np.array_equal(v["regional_rewards"].cpu().numpy(), out["regional_rewards"])
+    a_env.close()
+    b_env.close()
+
+
 def test_qp_kernel_vs_golden_and_oracle(mm, orc):
     """mm_shield_qp: every QP the reference posed + 1e6 synthetic ones (oracle as the checker)."""
     import torch
