@@ -274,8 +274,8 @@ __device__ __forceinline__ void ent_pos(const Env &ev, int id, double &px, doubl
     if (id == OBST) { px = OBST_X; py = OBST_Y; } else { px = X(id); py = Y(id); }
 }
 
-// road.py:352-381 (candidates: vehicles in list order, then the obstacle)
-__device__ __noinline__ void neighbour_vehicles(const Env &ev, int self, int lane, int &front, int &rear) {
+// road.py:352-381 (candidates: vehicles in list order, then the obstacle): the exhaustive scan, kept for the tie cases
+__device__ __noinline__ void neighbour_vehicles_scan(const Env &ev, int self, int lane, int &front, int &rear) {
     double s = lane_s(lane, X(self)), s_front = 0, s_rear = 0;
     front = -1;
     rear = -1;
@@ -290,6 +290,50 @@ __device__ __noinline__ void neighbour_vehicles(const Env &ev, int self, int lan
         if (!(fabs(lat) <= LWIDTH / 2 + 1)) continue;
         if (s <= s_v && (front < 0 || s_v <= s_front)) { s_front = s_v; front = id; }
         if (s_v < s && (rear < 0 || s_v > s_rear)) { s_rear = s_v; rear = id; }
+    }
+}
+
+// The same through the x-sorted order: lane_s is monotone in x, so the front vehicle is the first one ahead of the ego
+// that lies on the lane (margin 1 m), the rear vehicle the first one behind.  The obstacle at (420, 4) is on bc1 only
+// (s = 100, r = 0; every other lane fails on_lane), where it competes by its s like a vehicle and, being last in the
+// candidate list, wins ties for the front place.  Equal longitudinal positions between vehicles are where list order
+// decides: any such equality on the way defers to the scan.
+__device__ __noinline__ void neighbour_vehicles(const Env &ev, int self, int lane, int &front, int &rear) {
+    const uint64_t live = ev.live;
+    const int ps = nib(ev.pos, self);
+    const double s = lane_s(lane, X(self)), hi = c_lane_len[lane] + VLEN;
+    front = -1;
+    rear = -1;
+    bool tie = false;
+    double s_front = 0, s_rear = 0, prev = s;
+    for (int p = ps - 1; p >= 0; --p) {               // ahead: s_v grows
+        const int j = nib(live, p);
+        const double s_v = lane_s(lane, X(j));
+        tie |= s_v == prev;
+        prev = s_v;
+        if (front >= 0) break;                        // one look past the hit, for the tie test only
+        if (!(s_v < hi)) break;
+        if (!(-VLEN <= s_v)) continue;
+        if (!(fabs(lane_r(lane, s_v, Y(j))) <= LWIDTH / 2 + 1)) continue;
+        s_front = s_v; front = j;
+    }
+    prev = s;
+    for (int p = ps + 1; p < ev.n_veh; ++p) {         // behind: s_v shrinks
+        const int j = nib(live, p);
+        const double s_v = lane_s(lane, X(j));
+        tie |= s_v == prev;
+        prev = s_v;
+        if (rear >= 0) break;
+        if (!(-VLEN <= s_v)) break;
+        if (!(s_v < hi)) continue;
+        if (!(fabs(lane_r(lane, s_v, Y(j))) <= LWIDTH / 2 + 1)) continue;
+        s_rear = s_v; rear = j;
+    }
+    if (tie) { neighbour_vehicles_scan(ev, self, lane, front, rear); return; }
+    if (lane == L_BC1) {
+        const double s_o = OBST_X - 320.0;            // lane_s(bc1, 420)
+        if (s <= s_o && (front < 0 || s_o <= s_front)) front = OBST;
+        if (s_o < s && (rear < 0 || s_o > s_rear)) rear = OBST;
     }
 }
 
