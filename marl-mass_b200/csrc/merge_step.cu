@@ -1396,6 +1396,7 @@ __device__ __forceinline__ void flush_stats(double *stat_acc, double *stats, siz
 // MM_PHASE_SYNC: CTA-wide barriers that keep the four warps of a CTA in the same phase of the step, so that they
 // share instruction-cache lines (the kernel is ~130 KB of SASS; instruction fetch was a top stall without them).
 //   0: none   1: one barrier per sub-step   2: additionally one per vehicle rank inside the act / step passes
+//   3: additionally one between a rank's control law and its shield + move (experiment)
 #ifndef MM_PHASE_SYNC
 #define MM_PHASE_SYNC 2
 #endif
@@ -1545,12 +1546,14 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
 #pragma unroll 1
         for (int q = 0; q < (MM_PHASE_SYNC >= 2 ? n_rank : n_live); ++q) {  // road.step(dt): same order
             PHASE_BARRIER(2);
+            int i = 0;
+            double rec1vx = 0, ge = 0, st_ = 0, ac_ = 0;
             if (q < n_live) {
-                int i = (int)((ord >> (4 * q)) & 15u);
+                i = (int)((ord >> (4 * q)) & 15u);
                 // the two cold fields of the ego the step needs, requested before the steering law so that their L2
                 // round trip overlaps it
-                const double rec1vx = GF(F_REC1VX, i), ge = GF(F_GVX, i);
-                double st_, ac_;
+                rec1vx = GF(F_REC1VX, i);
+                ge = GF(F_GVX, i);
                 if (merged) {
                     // sub-step 0 calls act(meta) and then act(None); the second call recomputes the same controls
                     cav_act(ev, i, apply_meta ? meta_action(act_lo, act_mid, act_hi, i) : A_NONE, sv, st_, ac_);
@@ -1558,8 +1561,9 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
                     st_ = GF(F_ACT_STEER, i);
                     ac_ = GF(F_ACT_ACC, i);
                 }
-                vehicle_step<DIAG>(ev, p, i, sub < 3 ? sub : 2, e, shield_counts, st_, ac_, rec1vx, ge);
             }
+            PHASE_BARRIER(3);
+            if (q < n_live) vehicle_step<DIAG>(ev, p, i, sub < 3 ? sub : 2, e, shield_counts, st_, ac_, rec1vx, ge);
         }
         PHASE_BARRIER(2);
         if (running) {

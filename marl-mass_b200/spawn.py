@@ -124,10 +124,12 @@ def fill_scene(st, e, vehicles, n_merge):
 
 
 def spawn_state(seeds, traffic_density=1, traffic_type="cav", num_CAV=0):
-    """Env-major state dict holding the reference's scene for each seed."""
+    """Env-major state dict holding the reference's scene for each seed (num_CAV: one value or one per seed)."""
     seeds = list(seeds)
+    n_cav = list(num_CAV) if hasattr(num_CAV, "__len__") else [num_CAV] * len(seeds)
+    assert len(n_cav) == len(seeds)
     st = empty_state(len(seeds))
     for e, s in enumerate(seeds):
-        vehicles, n_merge = spawn_scene(s, traffic_density, traffic_type, num_CAV)
+        vehicles, n_merge = spawn_scene(s, traffic_density, traffic_type, int(n_cav[e]))
         fill_scene(st, e, vehicles, n_merge)
     return st

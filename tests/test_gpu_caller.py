@@ -162,3 +162,42 @@ def test_rollout_collect_and_update_run_on_the_fused_path(mm):
     ht = torch.bincount(ta[live].long(), minlength=5).float() / live.sum()
     assert float((hf - ht).abs().max()) < 0.03
     env.close()
+
+
+def test_batched_evaluation_equals_the_sequential_protocol(mm):
+    """evaluation.evaluation (every evaluation episode as one env of a batch) == MAPPO.evaluation's loop
+    (marl/mappo.py:255-361) driven through the single-env adapter, episode by episode, with the same action table."""
+    import torch
+    from marl_mass_b200 import evaluation as ev
+    cfg = dict(safety_guarantee="cbf-cav", traffic_density=2, HEADWAY_TIME=0.5, cbf_eta=0.03125, traffic_type="mixed")
+    seeds = [0, 25, 50, 75, 100, 125, 150]
+    table = np.random.RandomState(0).randint(0, 5, size=(len(seeds), 100, 12))
+    step = {"t": 0}
+
+    def action_fn(obs, n_agents):
+        a = torch.from_numpy(table[:, step["t"], :]).cuda()
+        step["t"] += 1
+        return a
+
+    rewards, (vs, vp), info = ev.evaluation(action_fn, cfg, seeds, is_train=True)
+    env = mm.make("merge-multi-agent-v1")
+    env.config.update(cfg)
+    min_hw = float("inf")
+    for i, s in enumerate(seeds):
+        obs, _ = env.reset(is_training=False, testing_seeds=s, num_CAV=ev.eval_num_cav(i, 2))
+        n = len(env.controlled_vehicles)
+        done, t, rs, sp, tsp = False, 0, [], 0.0, 0.0
+        while not done:
+            obs, r, done, inf = env.step(tuple(int(x) for x in table[i, t, :n]))
+            t += 1
+            rs.append(r)
+            sp += inf["average_speed"]
+            tsp += inf["traffic_speed"]
+            min_hw = min(min_hw, inf["min_headway"])
+        assert info["steps"][i] == t and np.allclose(rewards[i], rs, rtol=0, atol=0)
+        assert abs(info["avg_speeds"][i] - sp / t) < 1e-5 and abs(info["traffic_speeds"][i] - tsp / t) < 1e-5
+        assert info["crash_count"][i] == env.is_crashed()
+        assert abs(info["merge_percents"][i] - inf["merge_percent"]) < 1e-6
+        assert vs[i].shape == (t, n) and np.allclose(vs[i], inf["vehicle_speed"]) and np.allclose(vp[i], inf["vehicle_position"])
+    assert abs(info["min_headway"] - min_hw) < 1e-6
+    env.close()
