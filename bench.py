@@ -186,10 +186,33 @@ def run_reference_arm(args, wl):
         "e2e": {"value": v, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Keep stdout to the ONE JSON line: everything any library prints to fd 1 from here on (NCCL's version banner,
+    torchrun notices, ...) goes to stderr; `emit` writes the line to the real stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=60)
@@ -220,7 +243,8 @@ def main():
     rank, world, local_rank = mmd.rank_world()
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("MM_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        if "MM_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["MM_NCCL_DEBUG"]
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = local_rank if world > 1 else 0
@@ -418,7 +442,7 @@ def main():
         line["cpu_baseline"] = {"value": v_cpu, "unit": "agent-steps/s", "cores": cores, "kind": "port",
                                 "sample": "%d envs x %d policy steps (~%.0f s of CPU work)" % (e_cpu, n_steps, args.cpu_seconds)}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     env.close()
     if world > 1:
         dist.destroy_process_group()
