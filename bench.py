@@ -249,6 +249,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = local_rank if world > 1 else 0
     torch.cuda.set_device(dev)
+    numa_cores = mmd.bind_to_gpu(dev) if world > 1 else 0   # host buffers on the GPU's own NUMA node
     E = wl["envs"]
     cfg = dict(mm.DEFAULT_CONFIG, **wl["cfg"])
     env = mm.MergeEnvBatched(E, cfg, device=dev, record_diag=False)
@@ -422,6 +423,7 @@ def main():
                 "d2h_bytes_per_step": int(rag_rows * mm.NS * 4 + E * (8 + 4 + 1 + mm.MAXV * 4 + 4)), "steps": K2,
                 "api": "mm_step_host_ragged (pinned host buffers, 64Ki-env chunks round-robin on 4 streams; observation "
                        "rows of the live agents only, as the reference returns them: packed on the device, exact-size copies)",
+                "host_cores_bound": numa_cores,
                 "dense": {"value": dense_value, "d2h_bytes_per_step": E * (mm.MAXV * mm.NS * 4 + 4 + 1 + mm.MAXV * 4 + 4),
                           "api": "mm_step_host (dense obs [E,12,30] by cudaMemcpyAsync)"}},
         "gpu_launches": int(launches),

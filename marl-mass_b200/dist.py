@@ -26,6 +26,31 @@ def rank_seed(seed, rank):
     return (int(seed) * 0x9E3779B97F4A7C15 + int(rank) * 0xD1B54A32D192ED03) & (2 ** 64 - 1)
 
 
+def bind_to_gpu(device_index):
+    """Pin the calling process to the CPU cores nearest to its GPU (NVML's ideal affinity), so that the pinned host
+    buffers of the host path are first-touched on that GPU's NUMA node and eight ranks do not push their
+    device-to-host traffic across the socket interconnect.  Returns the number of cores, or 0 if NVML is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        idx = device_index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if device_index < len(ids) and ids[device_index].isdigit():
+                idx = int(ids[device_index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        n_words = (os.cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cores = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        allowed = cores & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return len(allowed)
+    except Exception:
+        return 0
+
+
 def all_reduce_stats(stats, device=None):
     """Fold per-rank stats dicts (MergeEnvBatched.stats()) into job totals; no-op without a process group."""
     import torch
