@@ -57,7 +57,8 @@ def check_outputs(got, want, ncav):
         assert rel_err(got[k], want[k]).max() <= F32_TOL, (k, rel_err(got[k], want[k]).max())
 
 
-def check_shield(diag, want, lc_margin):
+def check_shield(diag, want, lc_margin, tol=None):
+    tol = STATE_TOL if tol is None else tol
     ran = want["sh_ran"] == 1
     assert np.array_equal(diag["ran"], want["sh_ran"])
     boundary = ran & (lc_margin < LC_BOUNDARY_EPS)
@@ -65,7 +66,7 @@ def check_shield(diag, want, lc_margin):
         bad = (diag[k] != want["sh_" + k]) & ran & ~boundary
         assert not bad.any(), (k, np.argwhere(bad)[:5].tolist())
     for k in SH_F:
-        assert (rel_err(diag[k], want["sh_" + k]) * (ran & ~boundary)).max() <= STATE_TOL, k
+        assert (rel_err(diag[k], want["sh_" + k]) * (ran & ~boundary)).max() <= tol, k
     return int(boundary.sum())
 
 
@@ -132,8 +133,23 @@ def test_cuda_vs_oracle_seeded_rollout(mm, orc, shield, traffic, td, reward):
     """4096 device-spawned scenes, 40 policy steps of uniform random actions, CUDA and oracle advanced in lock
     step from the same start; state is re-synced from the oracle only when a discrete mismatch was excluded as
     a veto-boundary case (never observed so far)."""
+    lockstep_rollout(mm, orc, shield, traffic, td, reward, 4096, 40, STATE_TOL)
+
+
+@pytest.mark.parametrize("shield,traffic,td,reward", [
+    ("cbf-cav", "cav", 3, "default"), ("cbf-cav", "mixed", 3, "srew"), ("cbf-avs_cint", "mixed", 2, "default")])
+def test_cuda_vs_oracle_whole_episodes(mm, orc, shield, traffic, td, reward):
+    """The same lock-step comparison over the WHOLE 100-step episode (queues behind the obstacle, everybody on cd0, the
+    one-sub-step last policy step, terminal outputs): the late-episode states are where the x-sorted neighbour walks,
+    the close-pair collision mask and the lane-change veto path do most of their work.  Neither side is re-synced, so
+    the libm-level differences between the two float64 implementations compound over 300 sub-steps: continuous state
+    within 1e-6 (as for the free-running golden episodes), every discrete field, output and shield record still exact.
+    Envs drop out of the comparison when one of their vehicles comes (nearly) to a halt - see lockstep_rollout."""
+    lockstep_rollout(mm, orc, shield, traffic, td, reward, 2048, 100, 1e-6)
+
+
+def lockstep_rollout(mm, orc, shield, traffic, td, reward, E, T, state_tol):
     import torch
-    E, T = 4096, 40
     lateral = "steer_vel" if shield.endswith("+steer_vel") else "steer"
     shield = shield.split("+")[0]
     cfg = dict(mm.DEFAULT_CONFIG, safety_guarantee=shield, lateral_control=lateral, traffic_type=traffic, traffic_density=td,
@@ -147,6 +163,8 @@ def test_cuda_vs_oracle_seeded_rollout(mm, orc, shield, traffic, td, reward):
     assert rel_err(obs0, orc.observe(st, steer_vel=(lateral == "steer_vel"))).max() <= F32_TOL
     rng = np.random.RandomState(7)
     alive = np.ones(E, bool)
+    clean = np.ones(E, bool)
+    n_compared = 0
     worst = 0.0
     for t in range(T):
         a = rng.randint(0, 5, size=(E, 12)).astype(np.int8)
@@ -154,14 +172,26 @@ def test_cuda_vs_oracle_seeded_rollout(mm, orc, shield, traffic, td, reward):
         _, _, _, v = env.step(torch.from_numpy(a).cuda())
         got = outputs_to_numpy(v, OUT_F + OUT_I)
         post = env.get_state()
-        # compare only envs that had not finished before this step (finished envs are not stepped by MAPPO)
-        sel = np.where(alive)[0]
-        sub = lambda d: {k: d[k][sel] for k in d}
-        worst = max(worst, compare_states(sub(post), sub(st), STATE_TOL, "step %d" % t))
-        check_outputs(sub(got), sub({k: want[k] for k in OUT_F + OUT_I}), st["n_cav"][sel])
         diag = env.shield_diag()
-        check_shield(sub(diag), sub({k: want[k] for k in want if k.startswith("sh_")}), diag["lc_margin"][sel])
+        # compare only envs that had not finished before this step (finished envs are not stepped by MAPPO) and, in the
+        # whole-episode runs, that are still well conditioned (see below)
+        sel = np.where(alive & clean)[0]
+        sub = lambda d: {k: d[k][sel] for k in d}
+        worst = max(worst, compare_states(sub(post), sub(st), state_tol, "step %d" % t))
+        check_outputs(sub(got), sub({k: want[k] for k in OUT_F + OUT_I}), st["n_cav"][sel])
+        check_shield(sub(diag), sub({k: want[k] for k in want if k.startswith("sh_")}), diag["lc_margin"][sel], state_tol)
         alive &= want["done"] == 0
+        if state_tol > STATE_TOL:
+            # Free-running whole episodes: the steering law of a (nearly) stopped vehicle divides by not_zero(speed) =
+            # +-0.01 twice, i.e. amplifies a 1e-16 difference in its lateral offset by ~1e5 and can flip the sign of the
+            # command; harmless while it stands, but when it creeps forward again the two float64 implementations
+            # leave on (physically meaningless) different headings.  An env is compared up to the step on which one
+            # of its vehicles first drops below 3 m/s (it can then come to a halt within the next policy step);
+            # per-step parity of the slow states is what the teacher-forced golden tests pin.
+            clean &= ~((st["speed"] < 3.0) & used_mask(st)).any(axis=1)
+            n_compared += len(sel)
+    if state_tol > STATE_TOL:
+        assert n_compared > 0.4 * E * T, n_compared     # a large part of the env-steps of the episode was compared
     if shield == "none":
         assert alive.sum() < E  # unshielded random driving does crash inside the window
     env.close()
