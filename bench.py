@@ -36,6 +36,11 @@ WORKLOADS = {
     "mass_td3": dict(cfg=dict(MASS, traffic_density=3, traffic_type="cav"), envs=1 << 20,
                      desc="MASS cbf-cav hard-density merge (BASELINE configs[4]: marl_cav-heading-t_headway-cbf-cav, "
                           "traffic_density=3, all-CAV 7-11 agents/env)"),
+    # opt-in device-spawn variant: vehicle counts drawn per 128-env tile (include/marl_mass_b200.h couple_counts);
+    # NOT the default workload - reported separately (profiles/README.md)
+    "mass_td3_coupled": dict(cfg=dict(MASS, traffic_density=3, traffic_type="cav", couple_vehicle_counts=True), envs=1 << 20,
+                             desc="MASS cbf-cav hard density, all-CAV, vehicle counts coupled per 128-env tile (opt-in spawn "
+                                  "variant: every env keeps the reference's law, envs of a tile share n_CAV)"),
     "mass_td3_mixed": dict(cfg=dict(MASS, traffic_density=3, traffic_type="mixed"), envs=1 << 20,
                            desc="MASS cbf-cav-mixed hard density (4-6 CAV + 3-5 IDM/MOBIL HDV per env)"),
     "mass_td3_srew": dict(cfg=dict(MASS, traffic_density=3, traffic_type="cav", agent_reward="srew",

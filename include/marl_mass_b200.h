@@ -56,6 +56,10 @@ typedef struct {
     int32_t steer_vel;       /* 1: lateral_control = steer_vel (safe_controller.py:84-98,124-150): steering angle is a
                                 state driven by a steering-velocity command; neighbour CAV headings are observed
                                 relative to the ego */
+    int32_t couple_counts;   /* device spawn only (no reference counterpart; default 0).  1: the vehicle COUNTS of an
+                                episode (merge_env_v1.py:180-211) are drawn once per 128-env tile instead of once per
+                                env; every env still follows the reference's law, but the envs of a tile share
+                                (n_CAV, n_HDV), which lets a CTA skip the vehicle ranks none of its envs has */
 } mm_config;
 
 typedef struct mm_env mm_env;

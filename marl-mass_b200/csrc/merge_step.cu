@@ -1411,7 +1411,10 @@ __device__ __forceinline__ int meta_action(uint32_t lo, uint32_t mid, uint32_t h
     return (a >= 0 && a <= 4) ? a : A_IDLE;
 }
 
-template <bool DIAG>
+// DYN_RANKS: the rank loops run to the largest vehicle count of the CTA's envs instead of MAXV - 1.  Only worth a
+// second instantiation when the envs of a tile share their counts (mm_config.couple_counts); with independent counts
+// some env of 128 almost always has 11 vehicles, and the constant trip count compiles to the faster loop.
+template <bool DIAG, bool DYN_RANKS>
 __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid_constant__ StepParams p) {
     const int tid = threadIdx.x;
 #if MM_SORT_LANES
@@ -1495,7 +1498,10 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
     // leaves registers.  With HDVs present the two ordered passes are kept (MOBIL reads the others' target lanes).
     // The choice is made per CTA so that the barriers below stay uniform.
     const bool merged = __syncthreads_and(!valid || ev.n_cav == ev.n_veh) != 0;
-    const int n_rank = MM_PHASE_SYNC >= 2 ? MAXV - 1 : 0;  // uniform trip count when ranks are barrier-separated
+    // uniform trip count when ranks are barrier-separated: the largest vehicle count of the CTA's envs
+    int n_rank = MM_PHASE_SYNC >= 2 ? MAXV - 1 : 0;
+    if (DYN_RANKS && MM_PHASE_SYNC >= 2)
+        while (n_rank > 0 && !__syncthreads_or(ev.n_veh >= n_rank)) --n_rank;
 #pragma unroll 1
     for (int sub = 0; sub < p.cfg.substeps; ++sub) {  // abstract.py:514-531
         PHASE_BARRIER(1);
@@ -1661,8 +1667,18 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ Re
         case 2: lo_c = 2; lo_h = 2; break;
         default: lo_c = 4; lo_h = 3; break;
     }
-    int n_cav = p.num_cav > 0 ? p.num_cav : lo_c + rng.below(3);
-    int n_hdv = lo_h + rng.below(3);
+    // couple_counts: the two count draws come from a stream keyed by the TILE (and the env's episode number), so the
+    // envs of a tile that re-spawn together share (n_CAV, n_HDV); the env's own stream still makes the two draws, so
+    // everything after them is the same whichever way the counts were drawn
+    int d_cav = p.num_cav > 0 ? 0 : rng.below(3);
+    int d_hdv = rng.below(3);
+    if (p.cfg.couple_counts) {
+        Philox tile_rng(p.seed ^ 0x7469'6c65'636e'7473ull, (uint64_t)(e / TILE), episode);
+        d_cav = tile_rng.below(3);
+        d_hdv = tile_rng.below(3);
+    }
+    int n_cav = p.num_cav > 0 ? p.num_cav : lo_c + d_cav;
+    int n_hdv = lo_h + d_hdv;
     if (p.cfg.traffic_type == MM_TRAFFIC_CAV) { n_cav += n_hdv; n_hdv = 0; }
     if (n_cav + n_hdv > 11) n_cav = 11 - n_hdv;
 
@@ -1883,8 +1899,9 @@ constexpr size_t STEP_SMEM = (size_t)PLANES_F64 * sizeof(double);
 void launch_step(const StepParams &p, bool diag, void *stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM);
-        cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM);
+        cudaFuncSetAttribute(step_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM);
+        cudaFuncSetAttribute(step_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM);
+        cudaFuncSetAttribute(step_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM);
         cudaFuncSetAttribute(observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM);
         attr_set = true;
     }
@@ -1893,11 +1910,12 @@ void launch_step(const StepParams &p, bool diag, void *stream) {
     // MM_EXTRA_SMEM (bytes): occupancy experiment knob - pads the CTA's shared memory to lower the CTAs/SM
     static const size_t extra = [] { const char *e = getenv("MM_EXTRA_SMEM"); return e ? (size_t)atol(e) : (size_t)0; }();
     if (extra) {
-        cudaFuncSetAttribute(step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(STEP_SMEM + extra));
-        cudaFuncSetAttribute(step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(STEP_SMEM + extra));
+        cudaFuncSetAttribute(step_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(STEP_SMEM + extra));
+        cudaFuncSetAttribute(step_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(STEP_SMEM + extra));
     }
-    if (diag) step_kernel<true><<<grid, BLOCK, STEP_SMEM + extra, (cudaStream_t)stream>>>(p);
-    else step_kernel<false><<<grid, BLOCK, STEP_SMEM + extra, (cudaStream_t)stream>>>(p);
+    if (diag) step_kernel<true, false><<<grid, BLOCK, STEP_SMEM + extra, (cudaStream_t)stream>>>(p);
+    else if (p.cfg.couple_counts) step_kernel<false, true><<<grid, BLOCK, STEP_SMEM, (cudaStream_t)stream>>>(p);
+    else step_kernel<false, false><<<grid, BLOCK, STEP_SMEM + extra, (cudaStream_t)stream>>>(p);
 }
 
 void launch_observe(const StepParams &p, void *stream) {

@@ -79,7 +79,8 @@ def make_mm_config(cfg):
         eta=float(cfg.get("cbf_eta", 0.0)), tau=float(cfg["HEADWAY_TIME"]),
         collision_reward=float(cfg["COLLISION_REWARD"]), high_speed_reward=float(cfg["HIGH_SPEED_REWARD"]),
         headway_cost=float(cfg["HEADWAY_COST"]), headway_time=float(cfg["HEADWAY_TIME"]),
-        merging_lane_cost=float(cfg["MERGING_LANE_COST"]))
+        merging_lane_cost=float(cfg["MERGING_LANE_COST"]),
+        couple_counts=int(bool(cfg.get("couple_vehicle_counts", False))))
 
 
 class _DevArray(object):

@@ -353,6 +353,35 @@ def test_device_spawn_law(mm):
         env.close()
 
 
+def test_coupled_vehicle_counts_keep_the_law_and_share_counts_per_tile(mm):
+    """couple_vehicle_counts (opt-in device spawn): the envs of a 128-env tile share (n_CAV, n_HDV); the counts are
+    still uniform over the reference's ranges across tiles, everything else is drawn per env; the step path is the
+    same kernel (parity is covered by the other tests: set_state does not care how a scene was drawn)."""
+    import torch
+    E = 128 * 600
+    cfg = dict(mm.DEFAULT_CONFIG, safety_guarantee="cbf-cav", traffic_density=3, traffic_type="mixed", HEADWAY_TIME=0.5,
+               cbf_eta=0.03125, couple_vehicle_counts=True)
+    env = mm.MergeEnvBatched(E, cfg)
+    env.reset(seed=3)
+    st = env.get_state()
+    n_cav, n_veh = st["n_cav"].reshape(600, 128), st["n_veh"].reshape(600, 128)
+    assert (n_cav == n_cav[:, :1]).all() and (n_veh == n_veh[:, :1]).all()
+    assert set(np.unique(n_cav)) == {4, 5, 6} and set(np.unique(n_veh - n_cav)) == {3, 4, 5}
+    for k in (4, 5, 6):
+        assert abs((n_cav[:, 0] == k).mean() - 1 / 3) < 0.08
+    x = st["x"].reshape(600, 128, 12)
+    assert np.unique(np.round(x[:, :, 0], 6)).size > 0.9 * E          # positions are per env
+    # a few steps with auto-reset run fine and the next episode draws new shared counts
+    a = torch.ones((E, 12), dtype=torch.int8, device="cuda")
+    for _ in range(101):
+        env.step(a, auto_reset=True)
+    st2 = env.get_state()
+    n2 = st2["n_cav"].reshape(600, 128)
+    same_tile = (n2 == n2[:, :1]).all(axis=1)
+    assert same_tile.mean() > 0.95 and (n2[:, 0] != n_cav[:, 0]).mean() > 0.4
+    env.close()
+
+
 def test_full_size_properties(mm):
     """BASELINE size (65536 envs, MASS td3): size-independent invariants of a 100-step auto-reset rollout."""
     import torch
