@@ -214,3 +214,22 @@ def test_shipped_ini_files_map_onto_the_batched_path():
                  "marl_cav-heading-t_headway-cbf-cav-td3-srew.ini", "marl_cav-heading-t_headway-cbf-cav-mixed.ini",
                  "test-configs_marl-cav-unsafe.ini", "marl_cav_heading-t_headway-cbf-av-steer_vel.ini"):
         assert must in ok
+
+
+def test_training_driver_reads_the_reference_ini_layout():
+    """train.load_ini: the sections / keys / fallbacks of run_mappo.py:113-171, on the shipped example and (when the
+    reference tree is present) on the reference's own MASS td3 srew ini - both must give the same configuration."""
+    from marl_mass_b200 import train
+    import marl_mass_b200 as mm
+    env_cfg, kw, tr = train.load_ini(os.path.join(ROOT, "examples", "mass_td3_srew.ini"))
+    assert env_cfg["safety_guarantee"] == "cbf-cav" and env_cfg["traffic_density"] == 3 and env_cfg["mixed_traffic"] is False
+    assert env_cfg["agent_reward"] == "srew" and env_cfg["cbf_eta"] == 0.03125 and env_cfg["HEADWAY_TIME"] == 0.5
+    assert kw == {"roll_out_n_steps": 100, "reward_gamma": 0.99, "max_grad_norm": 5.0, "reward_type": "regionalR",
+                  "reward_scale": 20.0, "actor_lr": 5e-4, "critic_lr": 5e-4}
+    assert len(tr["test_seeds"].split(",")) == 20 and tr["eval_episodes"] == 20
+    c = mm.make_mm_config(dict(mm.DEFAULT_CONFIG, **env_cfg))
+    assert (c.shield, c.reward_kind, c.traffic_type) == (2, 1, 0)
+    ref = "/root/reference/marl/configs/marl_cav-heading-t_headway-cbf-cav-td3-srew.ini"
+    if os.path.exists(ref):
+        env_ref, kw_ref, tr_ref = train.load_ini(ref)
+        assert env_ref == env_cfg and kw_ref == kw and tr_ref["test_seeds"] == tr["test_seeds"]
