@@ -175,8 +175,37 @@ class BatchedMAPPORollout(object):
         self.buf = dict(states=S, actions=A, returns=returns, live=L, dones=D, rewards=R)
         return self.buf
 
+    # ---- data parallelism over env shards: one process per GPU, each with its own envs; the only
+    # traffic is the gradient all-reduce of the two small networks (~42 k parameters each) per minibatch
+    def _world(self):
+        import torch.distributed as dist
+        return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+    def sync_parameters(self, src=0):
+        """Broadcast rank `src`'s networks (call once after construction under torchrun)."""
+        import torch.distributed as dist
+        if self._world() > 1:
+            for m in (self.actor, self.critic, self.actor_target, self.critic_target):
+                for t in list(m.parameters()) + list(m.buffers()):
+                    dist.broadcast(t.data, src)
+
+    def _allreduce_grads(self, params):
+        import torch.distributed as dist
+        w = self._world()
+        if w == 1:
+            return
+        params = [q for q in params if q.grad is not None]
+        flat = torch.cat([q.grad.reshape(-1) for q in params])
+        dist.all_reduce(flat)
+        flat /= w
+        o = 0
+        for q in params:
+            q.grad.copy_(flat[o:o + q.numel()].view_as(q.grad))
+            o += q.numel()
+
     def update(self, minibatch=1 << 18, epochs=1):
-        """PPO-clip actor update and critic regression on the last rollout (mappo.py:161-206), all agents at once."""
+        """PPO-clip actor update and critic regression on the last rollout (mappo.py:161-206), all agents at once.
+        Under torch.distributed every rank runs the same number of minibatches and the gradients are averaged."""
         b = self.buf
         live = b["live"].reshape(-1)
         idx = live.nonzero(as_tuple=False).squeeze(1)
@@ -184,10 +213,14 @@ class BatchedMAPPORollout(object):
         A = torch.nn.functional.one_hot(b["actions"].reshape(-1), NA).float()
         G = b["returns"].reshape(-1, 1)
         stats = {}
+        n_max = torch.tensor([idx.numel()], device=self.dev)
+        if self._world() > 1:
+            import torch.distributed as dist
+            dist.all_reduce(n_max, op=dist.ReduceOp.MAX)
+        n_mb = max(1, -(-int(n_max) // int(minibatch)))       # same count on every rank
         for _ in range(epochs):
             perm = idx[torch.randperm(idx.numel(), device=self.dev)]
-            for k in range(0, perm.numel(), minibatch):
-                j = perm[k:k + minibatch]
+            for j in torch.tensor_split(perm, n_mb):
                 s, a, g = S[j], A[j], G[j]
                 with torch.no_grad():
                     adv = g - self.critic_target(s, a)
@@ -199,11 +232,13 @@ class BatchedMAPPORollout(object):
                 actor_loss = -surr.mean()
                 self.actor_opt.zero_grad(set_to_none=True)
                 actor_loss.backward()
+                self._allreduce_grads(list(self.actor.parameters()))
                 nn.utils.clip_grad_norm_(self.actor.parameters(), self.max_grad_norm)
                 self.actor_opt.step()
                 critic_loss = nn.functional.mse_loss(self.critic(s, a), g)
                 self.critic_opt.zero_grad(set_to_none=True)
                 critic_loss.backward()
+                self._allreduce_grads(list(self.critic.parameters()))
                 nn.utils.clip_grad_norm_(self.critic.parameters(), self.max_grad_norm)
                 self.critic_opt.step()
                 stats = {"actor_loss": float(actor_loss.detach()), "critic_loss": float(critic_loss.detach()),

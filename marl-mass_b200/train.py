@@ -52,11 +52,22 @@ def train(config, n_envs=4096, iterations=30, device=0, eval_interval=10, miniba
     from . import evaluation as ev
     from .env import DEFAULT_CONFIG, MergeEnvBatched
     from .rollout import BatchedMAPPORollout, actor_sample
+    import torch.distributed as dist
+    from . import dist as mmd
     env_cfg, rollout_kw, tr = load_ini(config) if isinstance(config, str) else config
+    rank, world, local_rank = mmd.rank_world()
+    if world > 1:                 # torchrun: one process per GPU, n_envs envs each, gradients averaged
+        device = local_rank
+        torch.cuda.set_device(device)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", device))
     torch.manual_seed(tr["torch_seed"])
     env = MergeEnvBatched(n_envs, dict(DEFAULT_CONFIG, **env_cfg), device=device)
-    env.reset(seed=env_cfg["seed"])
-    pol = BatchedMAPPORollout(env, seed=tr["torch_seed"], **rollout_kw)
+    env.reset(seed=mmd.rank_seed(env_cfg["seed"], rank) if world > 1 else env_cfg["seed"])
+    pol = BatchedMAPPORollout(env, seed=tr["torch_seed"] + 104729 * rank, **rollout_kw)
+    pol.sync_parameters()
+    if rank != 0:
+        log = lambda *_: None
     draws = {"n": 0}
 
     def act(obs, n_agents):      # MAPPO.action (mappo.py:231-236): a draw from the softmax, also at evaluation time
@@ -73,19 +84,28 @@ def train(config, n_envs=4096, iterations=30, device=0, eval_interval=10, miniba
         up = pol.update(minibatch=minibatch)
         torch.cuda.synchronize(device)
         t2 = time.perf_counter()
-        s = env.stats()
-        rec = {"iteration": it, "agent_steps": s["agent_steps"], "collect_s": t1 - t0, "update_s": t2 - t1,
+        s = mmd.all_reduce_stats(env.stats())
+        rec = {"iteration": it, "n_gpus": world, "agent_steps": s["agent_steps"], "collect_s": t1 - t0, "update_s": t2 - t1,
                "agent_steps_per_s": s["agent_steps"] / (t1 - t0), "mean_step_reward": s["reward_sum"] / max(s["env_steps"], 1),
                "crashed_episode_frac": s["crashed_episodes"] / max(s["episodes"], 1),
                "average_speed": s["speed_sum"] / max(s["env_steps"], 1), **up}
-        if eval_interval and (it % eval_interval == 0 or it == iterations - 1):
+        if rank == 0 and eval_interval and (it % eval_interval == 0 or it == iterations - 1):
             rewards, _, info = ev.evaluation(act, env_cfg, tr["test_seeds"], eval_episodes=tr["eval_episodes"], device=device)
             rec.update({"eval_reward": float(np.mean([np.sum(r) for r in rewards])),       # run_mappo.py:303-306
                         "eval_avg_speed": float(np.mean(info["avg_speeds"])), "eval_crashes": int(np.sum(info["crash_count"])),
                         "eval_min_headway": info["min_headway"], "eval_merge_percent": float(np.mean(info["merge_percents"]))})
+        if world > 1 and it == iterations - 1:      # the replicas must still hold identical networks
+            flat = torch.cat([q.detach().reshape(-1) for q in list(pol.actor.parameters()) + list(pol.critic.parameters())])
+            hi, lo = flat.clone(), flat.clone()
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            rec["replica_param_max_diff"] = float((hi - lo).abs().max())
         history.append(rec)
         log(json.dumps(rec))
     env.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     return history
 
 
