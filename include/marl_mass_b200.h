@@ -160,13 +160,19 @@ int mm_shield_qp(const double *a, const double *c_lead, const double *c_adj, con
  * ReLU, Linear 128-5, log-softmax) evaluated on n_rows observation rows [n_rows][30] f32 and, fused with it, the
  * exploration draw of marl/mappo.py:209-228 (np.random.choice(p = softmax): inverse CDF of one uniform per row;
  * here Philox4x32-10 keyed by (seed, step, row)).  Weights are torch.nn.Linear parameters as they lie in memory
- * (weight [out][in], bias [out]), TF32 tensor-core math with fp32 accumulation.  n_agents (nullable) [n_rows / 12]:
+ * (weight [out][in], bias [out]), TF32 tensor-core math with fp32 accumulation: the two 128-wide layers run as
+ * tcgen05.mma kind::tf32 with the accumulators in TMEM (one persistent CTA per SM, 128 rows per tile), the 128 -> 5
+ * output layer, the log-softmax and the draw in the thread that owns the row.  n_agents (nullable) [n_rows / 12]:
  * rows whose slot index (row % 12) is >= n_agents[row / 12] get action 1 (IDLE).  logp_all [n_rows][5] and
  * logp_sel [n_rows] are optional outputs (log-probabilities of all actions / of the drawn one).  All pointers are
  * DEVICE pointers; enqueued on `stream`, no synchronisation. */
 int mm_actor_sample(const float *obs, const int32_t *n_agents, int64_t n_rows, const float *w1, const float *b1,
                     const float *w2, const float *b2, const float *w3, const float *b3, uint64_t seed, uint64_t step,
                     int8_t *actions, float *logp_all, float *logp_sel, void *stream);
+
+/* Implementation switch of mm_actor_sample (process-wide): 0 = tcgen05 (default), 1 = the warp-level mma.sync kernel
+ * kept as an independent cross-check. */
+int mm_set_actor_impl(int impl);
 
 /* mm_discounted_returns: MAPPO._discount_reward (marl/mappo.py:364-370) for every (env, agent) column of a rollout at
  * once: out[t][c] = rewards[t][c] + gamma * out[t+1][c], restarted after a step with dones[t][c / cols_per_env] != 0,

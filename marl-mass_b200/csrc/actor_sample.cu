@@ -8,14 +8,19 @@
 // activations (2 x 400 MB) go through HBM four times.  Here a warp carries 16 rows through all three layers in
 // registers and only the observations (120 B / row) and the actions (1 B / row) touch HBM.
 //
-// Mapping: mma.sync.m16n8k8 TF32 (fp32 accumulate) per warp.  The accumulator fragment of layer L (thread holds rows
-// g, g+8 and columns 2t, 2t+1 of each 8-wide tile) is reused directly as the A fragment of layer L+1 (rows g, g+8,
-// columns t, t+4) by permuting the K index of that layer: A column t <-> hidden unit 8kk+2t, A column t+4 <-> 8kk+2t+1,
-// and the weights are laid out in shared memory in fragment order with the same permutation, so no shuffle or
-// shared-memory round trip separates the layers.  This op is ~33 GFLOP per step; legacy warp-level MMA is far from the
-// tcgen05 peak but already makes the op a small fraction of the env step, so the simpler pipeline was kept.
+// Two implementations, same arithmetic (TF32 operands, fp32 accumulation):
+//   * actor_sample_tcgen05_kernel (default): the two 128-wide layers as tcgen05.mma kind::tf32 with the accumulators in
+//     TMEM, 128 rows per tile, epilogues in the thread that owns the row - see the section further down;
+//   * actor_sample_kernel (mm_set_actor_impl(1)): mma.sync.m16n8k8 per warp, kept as the independent cross-check.  The
+//     accumulator fragment of layer L (thread holds rows g, g+8 and columns 2t, 2t+1 of each 8-wide tile) is reused
+//     directly as the A fragment of layer L+1 (rows g, g+8, columns t, t+4) by permuting the K index of that layer:
+//     A column t <-> hidden unit 8kk+2t, A column t+4 <-> 8kk+2t+1, and the weights are laid out in shared memory in
+//     fragment order with the same permutation, so no shuffle or shared-memory round trip separates the layers.
+// Measured at 786 432 rows: torch layers 1.89 ms, mma.sync 0.20 ms, tcgen05 0.17 ms (profiles/README.md); this op is
+// ~33 GFLOP per step, so both are bound by their epilogues and staging, not by the tensor pipe.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdlib>
 #include "mm_internal.h"
 
 namespace mm {
@@ -211,6 +216,257 @@ actor_sample_kernel(const float *__restrict__ obs, const int32_t *__restrict__ n
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// tcgen05 version: the two 128-wide layers on the 5th-generation tensor cores
+// ------------------------------------------------------------------------------------------------
+// One persistent CTA per SM, 512 threads, 128 observation rows per tile (= the 128 TMEM lanes).
+//   layer 1   D1[128x128] = A1[128x32]  * W1^T   4 x tcgen05.mma kind::tf32 (M128 N128 K8), accumulator in TMEM cols 0..127
+//   epilogue  TMEM -> registers (tcgen05.ld 32x32b), + bias, ReLU, TF32 rounding -> A2 in shared memory
+//   layer 2   D2[128x128] = A2[128x128] * W2^T  16 x tcgen05.mma, accumulator in TMEM cols 128..255
+//   epilogue  TMEM -> registers, + bias, ReLU, and the 128 -> 5 output layer as FMAs in the thread that owns the row
+//             (too narrow for an MMA tile), log-softmax, inverse-CDF draw, one action byte per row
+// Operands are K-major, no swizzle: 16-byte rows of 4 TF32 values, core matrices of 8 rows; with the layout
+// [k-chunk][row] (float4) a warp's 32 rows of one chunk are 512 contiguous bytes (conflict-free staging), the stride
+// between 8-row groups is SBO = 128 B and between the two 16-byte k-chunks of one MMA LBO = 2048 B.
+// Warps w, w+4, w+8, w+12 share TMEM lane quarter w%4 (hardware rule) and split the 128 columns four ways; the next
+// tile's observations are requested right after a tile's first MMA is issued, so their latency hides behind the epilogues.
+constexpr int T5_THREADS = 512;
+constexpr int T5_CSPLIT = T5_THREADS / 128;                  // column groups (of 128 / T5_CSPLIT columns) per row
+constexpr int T5_COLS = 128 / T5_CSPLIT;
+constexpr int T5_ROWS = 128;
+constexpr uint32_t T5_CHUNK_BYTES = T5_ROWS * 16;            // one k-chunk (4 values) of all 128 rows
+// shared memory (bytes)
+constexpr uint32_t T5_A1 = 0;                                // [8 chunks][128] float4
+constexpr uint32_t T5_W1 = T5_A1 + 8 * T5_CHUNK_BYTES;       // [8 chunks][128] float4
+constexpr uint32_t T5_A2 = T5_W1 + 8 * T5_CHUNK_BYTES;       // [32 chunks][128] float4
+constexpr uint32_t T5_W2 = T5_A2 + 32 * T5_CHUNK_BYTES;      // [32 chunks][128] float4
+constexpr uint32_t T5_W3 = T5_W2 + 32 * T5_CHUNK_BYTES;      // [128 hidden][8] f32 (5 used)
+constexpr uint32_t T5_B1 = T5_W3 + AC_HID * 8 * 4;
+constexpr uint32_t T5_B2 = T5_B1 + AC_HID * 4;
+constexpr uint32_t T5_B3 = T5_B2 + AC_HID * 4;
+constexpr uint32_t T5_PART = T5_B3 + 8 * 4;                  // [column groups 1..][128 rows][8] f32 partial logits
+constexpr uint32_t T5_BAR = T5_PART + (T5_CSPLIT - 1) * T5_ROWS * 8 * 4;   // 2 mbarriers + the TMEM base address
+constexpr uint32_t T5_SMEM = T5_BAR + 32;
+
+__device__ __forceinline__ uint32_t t5_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t t5_desc(uint32_t smem_addr) {
+    // K-major, SWIZZLE_NONE: start address, LBO (between the two k-chunks of an MMA), SBO (between 8-row groups), version 1
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(T5_CHUNK_BYTES >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) |
+           (1ull << 46);
+}
+// kind::tf32, F32 accumulate, M = 128, N = 128, A and B K-major (cute/arch/mma_sm100_desc.hpp InstrDescriptor)
+constexpr uint32_t T5_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void t5_mma(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                 ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(T5_IDESC), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void t5_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void t5_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void t5_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, "
+                 "%23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                   "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                   "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(T5_THREADS, 1)
+actor_sample_tcgen05_kernel(const float *__restrict__ obs, const int32_t *__restrict__ n_agents, int64_t n_rows,
+                            const float *__restrict__ w1, const float *__restrict__ b1, const float *__restrict__ w2,
+                            const float *__restrict__ b2, const float *__restrict__ w3, const float *__restrict__ b3,
+                            uint64_t seed, uint64_t step, int8_t *__restrict__ actions, float *__restrict__ logp_all,
+                            float *__restrict__ logp_sel) {
+    extern __shared__ __align__(128) uint8_t t5_sm[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float4 *a1 = reinterpret_cast<float4 *>(t5_sm + T5_A1), *w1f = reinterpret_cast<float4 *>(t5_sm + T5_W1);
+    float4 *a2 = reinterpret_cast<float4 *>(t5_sm + T5_A2), *w2f = reinterpret_cast<float4 *>(t5_sm + T5_W2);
+    float *w3s = reinterpret_cast<float *>(t5_sm + T5_W3), *b1s = reinterpret_cast<float *>(t5_sm + T5_B1);
+    float *b2s = reinterpret_cast<float *>(t5_sm + T5_B2), *b3s = reinterpret_cast<float *>(t5_sm + T5_B3);
+    float *part = reinterpret_cast<float *>(t5_sm + T5_PART);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(t5_sm + T5_BAR);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t5_sm + T5_BAR + 16);
+    const uint32_t bar1 = t5_smem(bars), bar2 = t5_smem(bars + 1);
+
+    // ---- one-time setup: weights in operand layout (TF32-rounded), barriers, TMEM ----
+    auto tf = [](float x) { return __uint_as_float(to_tf32(x)); };
+    for (int idx = tid; idx < 8 * T5_ROWS; idx += T5_THREADS) {          // W1: [out n][in k], k padded 30 -> 32
+        const int c = idx / T5_ROWS, n = idx % T5_ROWS, k = 4 * c;
+        float4 v;
+        v.x = tf(k + 0 < AC_IN ? w1[n * AC_IN + k + 0] : 0.f); v.y = tf(k + 1 < AC_IN ? w1[n * AC_IN + k + 1] : 0.f);
+        v.z = tf(k + 2 < AC_IN ? w1[n * AC_IN + k + 2] : 0.f); v.w = tf(k + 3 < AC_IN ? w1[n * AC_IN + k + 3] : 0.f);
+        w1f[idx] = v;
+    }
+    for (int idx = tid; idx < 32 * T5_ROWS; idx += T5_THREADS) {
+        const int c = idx / T5_ROWS, n = idx % T5_ROWS;
+        const float4 v = *reinterpret_cast<const float4 *>(w2 + n * AC_HID + 4 * c);
+        w2f[idx] = make_float4(tf(v.x), tf(v.y), tf(v.z), tf(v.w));
+    }
+    for (int idx = tid; idx < AC_HID * 8; idx += T5_THREADS) {
+        const int h = idx >> 3, k = idx & 7;
+        w3s[idx] = k < AC_OUT ? w3[k * AC_HID + h] : 0.f;
+    }
+    for (int idx = tid; idx < AC_HID; idx += T5_THREADS) { b1s[idx] = b1[idx]; b2s[idx] = b2[idx]; }
+    if (tid < 8) b3s[tid] = tid < AC_OUT ? b3[tid] : 0.f;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar2));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(t5_smem(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t a1_addr = t5_smem(a1), w1_addr = t5_smem(w1f), a2_addr = t5_smem(a2), w2_addr = t5_smem(w2f);
+
+    const int row_in_tile = 32 * (warp & 3) + lane;        // TMEM lane = row of the tile this thread reads
+    const int cgrp = warp >> 2;                            // which T5_COLS of the 128 columns
+    const int col0 = T5_COLS * cgrp;
+    static_assert(T5_COLS == 32, "one tcgen05.ld.32x32b.x32 per thread and epilogue");
+    const uint32_t t_lane = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+    const int64_t n_tiles = (n_rows + T5_ROWS - 1) / T5_ROWS;
+    // observation staging: thread t handles row t % 128, k-chunks 2 * (t / 128) and + 1
+    const int st_r = tid & (T5_ROWS - 1), st_c0 = 2 * (tid >> 7);
+    float4 pre[2];
+    auto fetch = [&](int64_t tile) {
+        const int64_t row = tile * T5_ROWS + st_r;
+        const float2 *src = reinterpret_cast<const float2 *>(obs + row * AC_IN);   // rows are 120 B: 8-byte aligned
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int c = st_c0 + q;
+            float2 lo = make_float2(0.f, 0.f), hi = lo;
+            if (tile < n_tiles && row < n_rows) {
+                lo = __ldg(src + 2 * c);
+                if (4 * c + 2 < AC_IN) hi = __ldg(src + 2 * c + 1);
+            }
+            pre[q] = make_float4(lo.x, lo.y, hi.x, hi.y);
+        }
+    };
+    fetch(blockIdx.x);
+    uint32_t parity = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, parity ^= 1) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+            a1[(st_c0 + q) * T5_ROWS + st_r] = make_float4(tf(pre[q].x), tf(pre[q].y), tf(pre[q].z), tf(pre[q].w));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                t5_mma(tmem, t5_desc(a1_addr + j * 2 * T5_CHUNK_BYTES), t5_desc(w1_addr + j * 2 * T5_CHUNK_BYTES), j > 0);
+            t5_commit(bar1);
+        }
+        fetch(tile + gridDim.x);                           // next tile's rows: in flight during this tile's epilogues
+        t5_wait(bar1, parity);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- epilogue 1: h1 = relu(D1 + b1) -> A2 (this thread: its row, 32 columns) ----
+        {
+            uint32_t v[32];
+            t5_ld32(t_lane + (uint32_t)col0, v);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float4 o;
+                o.x = tf(fmaxf(__uint_as_float(v[4 * q + 0]) + b1s[col0 + 4 * q + 0], 0.f));
+                o.y = tf(fmaxf(__uint_as_float(v[4 * q + 1]) + b1s[col0 + 4 * q + 1], 0.f));
+                o.z = tf(fmaxf(__uint_as_float(v[4 * q + 2]) + b1s[col0 + 4 * q + 2], 0.f));
+                o.w = tf(fmaxf(__uint_as_float(v[4 * q + 3]) + b1s[col0 + 4 * q + 3], 0.f));
+                a2[(col0 / 4 + q) * T5_ROWS + row_in_tile] = o;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                t5_mma(tmem + 128, t5_desc(a2_addr + j * 2 * T5_CHUNK_BYTES), t5_desc(w2_addr + j * 2 * T5_CHUNK_BYTES), j > 0);
+            t5_commit(bar2);
+        }
+        t5_wait(bar2, parity);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- epilogue 2: h2 = relu(D2 + b2), output layer as FMAs over this thread's 32 hidden units ----
+        float lg[AC_OUT] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        {
+            uint32_t v[32];
+            t5_ld32(t_lane + 128u + (uint32_t)col0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float h = fmaxf(__uint_as_float(v[j]) + b2s[col0 + j], 0.f);
+                const float4 wa = *reinterpret_cast<const float4 *>(w3s + (col0 + j) * 8);
+                const float wb = w3s[(col0 + j) * 8 + 4];
+                lg[0] = fmaf(h, wa.x, lg[0]); lg[1] = fmaf(h, wa.y, lg[1]); lg[2] = fmaf(h, wa.z, lg[2]);
+                lg[3] = fmaf(h, wa.w, lg[3]); lg[4] = fmaf(h, wb, lg[4]);
+            }
+        }
+        if (cgrp > 0) {
+#pragma unroll
+            for (int k = 0; k < AC_OUT; ++k) part[((cgrp - 1) * T5_ROWS + row_in_tile) * 8 + k] = lg[k];
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        const int64_t row = tile * T5_ROWS + row_in_tile;
+        if (cgrp == 0 && row < n_rows) {
+            float l[AC_OUT];
+#pragma unroll
+            for (int k = 0; k < AC_OUT; ++k) {
+                float acc = lg[k];
+#pragma unroll
+                for (int g2 = 0; g2 < T5_CSPLIT - 1; ++g2) acc += part[(g2 * T5_ROWS + row_in_tile) * 8 + k];
+                l[k] = acc + b3s[k];
+            }
+            float m = l[0];
+#pragma unroll
+            for (int k = 1; k < AC_OUT; ++k) m = fmaxf(m, l[k]);
+            float e[AC_OUT], S = 0.f;
+#pragma unroll
+            for (int k = 0; k < AC_OUT; ++k) { e[k] = __expf(l[k] - m); S += e[k]; }
+            const float logS = __logf(S);
+            const float u = (float)(philox_row(seed, step, (uint64_t)row) >> 8) * (1.0f / 16777216.0f);
+            const float target = u * S;
+            int a = AC_OUT - 1;
+            float c = 0.f;
+            bool found = false;
+#pragma unroll
+            for (int k = 0; k < AC_OUT; ++k) {
+                c += e[k];
+                if (!found && target < c) { a = k; found = true; }
+            }
+            bool live = true;
+            if (n_agents) live = (int)(row % MAXV) < n_agents[row / MAXV];
+            actions[row] = (int8_t)(live ? a : 1);
+            if (logp_sel) logp_sel[row] = l[a] - m - logS;
+            if (logp_all) {
+#pragma unroll
+                for (int k = 0; k < AC_OUT; ++k) logp_all[row * AC_OUT + k] = l[k] - m - logS;
+            }
+        }
+        __syncthreads();   // `part` is reused by the next tile
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+}
+
 // R_t = r_t + gamma * R_{t+1}, restarted after a terminal step: MAPPO._discount_reward (marl/mappo.py:364-370) for every
 // (env, agent) column of a rollout at once.  rewards / out [T][n_cols], dones [T][n_cols / cols_per_env] (1 where step t
 // ended the episode of that env), final_value [n_cols] (critic bootstrap; ignored where the last step was terminal).
@@ -240,6 +496,9 @@ int launch_discounted_returns(const float *rewards, const uint8_t *dones, const 
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
+int g_actor_impl = -1;   // -1: not chosen yet; 0: tcgen05; 1: mma.sync
+void set_actor_impl(int impl) { g_actor_impl = impl ? 1 : 0; }
+
 int launch_actor_sample(const float *obs, const int32_t *n_agents, int64_t n_rows, const float *w1, const float *b1,
                         const float *w2, const float *b2, const float *w3, const float *b3, uint64_t seed, uint64_t step,
                         int8_t *actions, float *logp_all, float *logp_sel, void *stream) {
@@ -253,6 +512,21 @@ int launch_actor_sample(const float *obs, const int32_t *n_agents, int64_t n_row
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // g_actor_impl (mm_set_actor_impl; initial value from MM_ACTOR_IMPL=mma): 1 selects the warp-level mma.sync kernel
+    // above, kept as the independent cross-check of the tcgen05 one
+    if (g_actor_impl < 0) { const char *e = getenv("MM_ACTOR_IMPL"); g_actor_impl = (e && e[0] == 'm') ? 1 : 0; }
+    if (g_actor_impl == 0) {
+        static bool t5_attr = false;
+        if (!t5_attr) {
+            if (cudaFuncSetAttribute(actor_sample_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T5_SMEM) != cudaSuccess)
+                return 1;
+            t5_attr = true;
+        }
+        int64_t t5_tiles = (n_rows + T5_ROWS - 1) / T5_ROWS, t5_ctas = t5_tiles < sms ? t5_tiles : sms;
+        actor_sample_tcgen05_kernel<<<(unsigned)t5_ctas, T5_THREADS, T5_SMEM, (cudaStream_t)stream>>>(
+            obs, n_agents, n_rows, w1, b1, w2, b2, w3, b3, seed, step, actions, logp_all, logp_sel);
+        return cudaGetLastError() == cudaSuccess ? 0 : 1;
+    }
     int64_t tiles = (n_rows + 15) / 16, ctas = (tiles + AC_THREADS / 32 - 1) / (AC_THREADS / 32);
     if (ctas > sms) ctas = sms;   // persistent: one CTA per SM, warps stride over the 16-row tiles
     actor_sample_kernel<<<(unsigned)ctas, AC_THREADS, smem, (cudaStream_t)stream>>>(obs, n_agents, n_rows, w1, b1, w2, b2, w3,

@@ -482,6 +482,12 @@ int mm_actor_sample(const float *obs, const int32_t *n_agents, int64_t n_rows, c
     return 0;
 }
 
+int mm_set_actor_impl(int impl) {
+    if (impl != 0 && impl != 1) return fail(MM_ERR_ARG, "impl must be 0 (tcgen05) or 1 (mma.sync)");
+    set_actor_impl(impl);
+    return 0;
+}
+
 int mm_discounted_returns(const float *rewards, const uint8_t *dones, const float *final_value, float gamma, int T,
                           int64_t n_cols, int cols_per_env, float *out, void *stream) {
     if (!rewards || !dones || !out) return fail(MM_ERR_ARG, "null argument");

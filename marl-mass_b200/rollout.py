@@ -76,6 +76,11 @@ def discounted_returns(rewards, dones, final_value, gamma):
     return out
 
 
+def set_actor_impl(name):
+    """'tcgen05' (default) or 'mma' (the warp-level mma.sync kernel, kept as a cross-check)."""
+    _lib.check(_lib.lib().mm_set_actor_impl({"tcgen05": 0, "mma": 1}[name]))
+
+
 def actor_sample(actor, obs, n_agents=None, seed=0, step=0, want_logp=False):
     """Fused actor forward + exploration draw (mm_actor_sample): obs [..., 30] f32 cuda -> actions int8 [...].
 

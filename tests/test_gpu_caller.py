@@ -84,6 +84,31 @@ def test_actor_matches_torch_fp32_on_env_observations_and_masks_absent_agents(mm
     env.close()
 
 
+def test_tcgen05_and_mma_sync_actor_kernels_agree(mm):
+    """The tcgen05 kernel (TMEM accumulators, row-per-thread epilogue) against the independent mma.sync kernel (register
+    fragments): same TF32 inputs for the two hidden layers, different accumulation order, and the output layer in fp32
+    FMAs (tcgen05 kernel) vs a TF32 MMA (mma.sync kernel) -> log-probabilities within 1e-2 (observed 3.5e-3 with 3x
+    the default weight scale); the same uniform per row -> the same action except where the draw falls within that
+    distance of a CDF step."""
+    import torch
+    from marl_mass_b200 import rollout
+    torch.manual_seed(3)
+    actor = rollout.ActorNetwork().cuda()
+    for p in actor.parameters():
+        p.data.mul_(3.0)
+    obs = (torch.rand(100003, mm.NS, device="cuda") * 2.4 - 1.2).contiguous()      # not a multiple of the 128-row tile
+    try:
+        rollout.set_actor_impl("mma")
+        a_m, lp_m = rollout.actor_sample(actor, obs, None, seed=5, step=2, want_logp=True)
+        rollout.set_actor_impl("tcgen05")
+        a_t, lp_t = rollout.actor_sample(actor, obs, None, seed=5, step=2, want_logp=True)
+        torch.cuda.synchronize()
+    finally:
+        rollout.set_actor_impl("tcgen05")
+    assert float((lp_m - lp_t).abs().max()) < 1e-2
+    assert float((a_m != a_t).float().mean()) < 5e-3
+
+
 def test_exploration_draw_follows_the_softmax(mm):
     """np.random.choice(p = softmax) (mappo.py:223-228): empirical action frequencies of many draws from a few fixed
     observation rows against the kernel's own probabilities."""
