@@ -1,0 +1,64 @@
+"""Parity soak beyond the test suite: whole-episode CUDA-vs-oracle lock step on fresh seeds and all shield / traffic /
+reward / lateral-control variants.  python profiles/soak_parity.py [n_rounds]   (needs the GPU box; oracle = checker)"""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import numpy as np
+import torch
+import marl_mass_b200 as mm
+import oracle as orc
+from helpers import F64_FIELDS, I32_FIELDS, ENV_FIELDS, OUT_I, rel_err, used_mask, LC_BOUNDARY_EPS, SH_I
+
+CASES = [("cbf-cav", "cav", 3, "default", "steer"), ("cbf-cav", "mixed", 3, "srew", "steer"), ("cbf-avs_cint", "cav", 3, "default", "steer"),
+         ("cbf-avs_cint", "mixed", 2, "mrew", "steer"), ("none", "mixed", 1, "default", "steer"), ("cbf-cav", "cav", 1, "mrew", "steer"),
+         ("cbf-cav", "mixed", 3, "default", "steer_vel"), ("cbf-cav", "cav", 2, "srew", "steer"), ("cbf-avs_cint", "mixed", 3, "default", "steer_vel")]
+rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+E, T = 4096, 100
+total_env_steps, boundary = 0, 0
+t0 = time.time()
+for rnd in range(rounds):
+    for ci, (shield, traffic, td, reward, lateral) in enumerate(CASES):
+        cfg = dict(mm.DEFAULT_CONFIG, safety_guarantee=shield, lateral_control=lateral, traffic_type=traffic, traffic_density=td,
+                   agent_reward=reward, HEADWAY_TIME=0.5, cbf_eta=0.03125, HIGH_SPEED_REWARD=4, HEADWAY_COST=1, MERGING_LANE_COST=8)
+        env = mm.MergeEnvBatched(E, cfg, record_diag=True)
+        env.reset(seed=900000 + 1000 * rnd + ci)
+        st = env.get_state()
+        ocfg = orc.make_config(cfg)
+        rng = np.random.RandomState(100 * rnd + ci)
+        alive, clean = np.ones(E, bool), np.ones(E, bool)
+        for t in range(T):
+            a = rng.randint(0, 5, size=(E, 12)).astype(np.int8)
+            want = orc.step(ocfg, st, a, n_threads=16)
+            _, _, _, v = env.step(torch.from_numpy(a).cuda())
+            post = env.get_state()
+            diag = env.shield_diag()
+            sel = alive & clean
+            m = used_mask(st) & sel[:, None]
+            for k in ENV_FIELDS:
+                assert np.array_equal(post[k][sel], st[k][sel]), (shield, traffic, td, t, k)
+            for k in I32_FIELDS:
+                bad = np.argwhere((post[k] != st[k]) & m)
+                assert len(bad) == 0, (shield, traffic, td, reward, lateral, "step", t, k, bad[:4].tolist())
+            for k in F64_FIELDS:
+                if k == "rec1_x":
+                    continue
+                err = (rel_err(post[k], st[k]) * m).max()
+                assert err < 1e-6, (shield, traffic, td, t, k, err)
+            for k in OUT_I:
+                g = v[k].cpu().numpy()
+                assert np.array_equal(g[sel].astype(np.int32) if g.ndim == 1 else (g[sel] * (np.arange(12)[None, :] < st["n_cav"][sel][:, None])).astype(np.int32),
+                                      np.asarray(want[k], np.int32)[sel]), (shield, traffic, td, t, k)
+            ran = (want["sh_ran"] == 1) & sel[:, None, None]
+            bnd = ran & (diag["lc_margin"] < LC_BOUNDARY_EPS)
+            boundary += int(bnd.sum())
+            for k in SH_I:
+                bad = (diag[k] != want["sh_" + k]) & ran & ~bnd
+                assert not bad.any(), (shield, traffic, td, t, "shield", k, np.argwhere(bad)[:4].tolist())
+            total_env_steps += int(sel.sum())
+            alive &= want["done"] == 0
+            clean &= ~((st["speed"] < 3.0) & used_mask(st)).any(axis=1)
+        env.close()
+        print("round %d %-13s %-6s td%d %-8s %-9s ok  (%.0f s, %d env-steps compared so far, %d veto-boundary solves)" % (
+            rnd, shield, traffic, td, reward, lateral, time.time() - t0, total_env_steps, boundary), flush=True)
+print("SOAK OK", total_env_steps, "env-steps")
