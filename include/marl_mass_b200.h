@@ -181,6 +181,12 @@ int mm_set_actor_impl(int impl);
 int mm_discounted_returns(const float *rewards, const uint8_t *dones, const float *final_value, float gamma, int T,
                           int64_t n_cols, int cols_per_env, float *out, void *stream);
 
+/* The step kernel exists in two builds: 3 CTAs per SM (6 staged fields, 168 registers; the faster one per unit of
+ * work) and 4 CTAs per SM (4 staged fields, 128 registers).  0 (default): automatic - the second build is used for
+ * small grids whose wave structure favours it (e.g. 65 536 envs = 512 CTAs on 148 SMs: one wave instead of a full and
+ * an almost empty one, -27 % step time); 3 / 4: force one (process-wide; tests). */
+int mm_set_step_variant(int variant);
+
 /* Launch bookkeeping for bench.py ("gpu_launches") */
 int64_t mm_kernel_launches(const mm_env *env);
 const char *mm_last_error(void);

@@ -67,7 +67,7 @@ _lib = None
 EXPORTS = ("mm_create", "mm_destroy", "mm_set_config", "mm_num_envs", "mm_reset", "mm_step", "mm_step_host",
            "mm_step_host_ragged",
            "mm_buffers_get", "mm_get_state", "mm_set_state", "mm_get_shield_diag", "mm_stats", "mm_shield_qp",
-           "mm_actor_sample", "mm_set_actor_impl", "mm_discounted_returns", "mm_kernel_launches", "mm_last_error", "mm_version")
+           "mm_actor_sample", "mm_set_actor_impl", "mm_set_step_variant", "mm_discounted_returns", "mm_kernel_launches", "mm_last_error", "mm_version")
 
 
 def lib():
@@ -97,6 +97,7 @@ def lib():
     L.mm_actor_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 6 + [C.c_uint64, C.c_uint64] + \
                                  [C.c_void_p] * 4
     L.mm_set_actor_impl.argtypes = [C.c_int]
+    L.mm_set_step_variant.argtypes = [C.c_int]
     L.mm_discounted_returns.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int64, C.c_int,
                                         C.c_void_p, C.c_void_p]
     L.mm_kernel_launches.argtypes = [h]

@@ -488,6 +488,12 @@ int mm_set_actor_impl(int impl) {
     return 0;
 }
 
+int mm_set_step_variant(int variant) {
+    if (variant != 0 && variant != 3 && variant != 4) return fail(MM_ERR_ARG, "variant must be 0 (automatic), 3 or 4");
+    set_step_variant(variant);
+    return 0;
+}
+
 int mm_discounted_returns(const float *rewards, const uint8_t *dones, const float *final_value, float gamma, int T,
                           int64_t n_cols, int cols_per_env, float *out, void *stream) {
     if (!rewards || !dones || !out) return fail(MM_ERR_ARG, "null argument");

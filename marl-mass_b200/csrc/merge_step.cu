@@ -25,8 +25,25 @@
 #include <cstdlib>
 #include "mm_internal.h"
 
-namespace mm {
+// MM_VARIANT4 (merge_step_occ4.cu includes this file with it defined): the step kernel built for FOUR CTAs per SM -
+// x, y, heading, speed staged (cos / sin of the heading stay in the L2-resident tile), 128 registers - in its own
+// namespace.  A grid that fits one wave of 4 CTAs / SM but not one of 3 (e.g. 65 536 envs = 512 CTAs on 148 SMs)
+// otherwise runs a second, almost empty wave: 2 x the CTA latency instead of 1.3 x.
+#ifdef MM_VARIANT4
+#define MM_NS mm4
+#define MM_NHOT 4
+#ifndef MM_MIN_BLOCKS
+#define MM_MIN_BLOCKS 4
+#endif
+namespace mm4 { using namespace mm; }
+#else
+#define MM_NS mm
+#define MM_NHOT 6
+#endif
 
+namespace MM_NS {
+
+constexpr int N_HOT = MM_NHOT;       // fields F_X .. staged in shared memory during a step (6: including cos / sin heading)
 constexpr int BLOCK = TILE;
 // build-time experiment knobs (profiles/README.md)
 #ifndef MM_INL_A
@@ -94,8 +111,13 @@ __device__ __forceinline__ int nib(uint64_t w, int k) { return (int)((w >> (4 * 
 #define Y(i) SMF(F_Y, i)
 #define H(i) SMF(F_H, i)
 #define V(i) SMF(F_V, i)
+#if MM_NHOT >= 6
 #define CH(i) SMF(F_COSH, i)
 #define SH(i) SMF(F_SINH, i)
+#else
+#define CH(i) GF(F_COSH, i)
+#define SH(i) GF(F_SINH, i)
+#endif
 #define FL(i) (reinterpret_cast<uint32_t *>(sm_planes + N_HOT * SMV * BLOCK)[(i) * BLOCK + ev.tid])
 #define GF(f, i) (*tile_ptr(ev.g, (f), (i)))
 
@@ -1896,7 +1918,7 @@ __global__ void __launch_bounds__(256) qp_kernel(const double *__restrict__ a, c
 // ------------------------------------------------------------------------------------------------
 constexpr size_t STEP_SMEM = (size_t)PLANES_F64 * sizeof(double);
 
-void launch_step(const StepParams &p, bool diag, void *stream) {
+void launch_step_impl(const StepParams &p, bool diag, void *stream) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(step_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM);
@@ -1917,6 +1939,35 @@ void launch_step(const StepParams &p, bool diag, void *stream) {
     else if (p.cfg.couple_counts) step_kernel<false, true><<<grid, BLOCK, STEP_SMEM, (cudaStream_t)stream>>>(p);
     else step_kernel<false, false><<<grid, BLOCK, STEP_SMEM + extra, (cudaStream_t)stream>>>(p);
 }
+
+#ifndef MM_VARIANT4
+static int g_step_variant = 0;
+void set_step_variant(int v) { g_step_variant = (v == 3 || v == 4) ? v : 0; }
+
+// Picks the build of the step kernel: 4 CTAs / SM when the wave structure of the grid favours it (e.g. 512 CTAs on 148
+// SMs: one wave instead of a full and an almost empty one), else the default 3 CTAs / SM build.
+void launch_step(const StepParams &p, bool diag, void *stream) {
+    const int grid = (p.env_count + BLOCK - 1) / BLOCK;
+    static const int sms = [] {
+        int dev = 0, n = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        return n;
+    }();
+    // CTA latency (arbitrary units) with c CTAs resident per SM, measured (profiles/README.md, occupancy sweep and
+    // time_variants.py): the grid costs its full waves plus one partial wave at the occupancy of the remainder
+    auto estimate = [&](int per_sm, const double *lat) {
+        const int slots = per_sm * sms, full = grid / slots, rem = grid - full * slots;
+        return full * lat[per_sm] + lat[(rem + sms - 1) / sms];
+    };
+    static const double lat3[4] = {0.0, 9.55, 11.42, 12.27}, lat4[5] = {0.0, 10.5, 12.6, 13.5, 16.2};
+    const bool small_grid = grid <= 12 * sms;     // on large grids the two builds are within a few per cent: keep the default
+    const bool four = g_step_variant == 4 || (g_step_variant == 0 && !diag && !p.cfg.couple_counts && small_grid &&
+                                              estimate(4, lat4) < 0.97 * estimate(3, lat3));
+    if (four) launch_step_occ4(p, diag, stream);
+    else launch_step_impl(p, diag, stream);
+}
+#endif
 
 void launch_observe(const StepParams &p, void *stream) {
     static bool attr_set = false;
@@ -1955,4 +2006,10 @@ void launch_qp(const double *a, const double *c_lead, const double *c_adj, const
     qp_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, c_lead, c_adj, has_adj, lo, hi, n, u, active);
 }
 
+}  // namespace MM_NS
+
+#ifdef MM_VARIANT4
+namespace mm {
+void launch_step_occ4(const StepParams &p, bool diag, void *stream) { mm4::launch_step_impl(p, diag, stream); }
 }  // namespace mm
+#endif

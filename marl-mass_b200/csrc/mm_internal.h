@@ -38,7 +38,6 @@ enum F64Field {
     F_STEERANG,                      // MDPLCVehicle.steering_angle (lateral_control = steer_vel only)
     F_COUNT
 };
-constexpr int N_HOT = 6;             // fields F_X .. F_SINH live in shared memory during a step
 
 // flags word
 constexpr uint32_t FL_KIND_SHIFT = 0, FL_KIND_MASK = 3u;
@@ -99,6 +98,9 @@ struct ResetParams {
 
 // launchers (merge_step.cu)
 void launch_step(const StepParams &p, bool diag, void *stream);
+// the same kernel compiled for 4 CTAs per SM (merge_step_occ4.cu): picked when that makes the grid a single wave
+void launch_step_occ4(const StepParams &p, bool diag, void *stream);
+void set_step_variant(int v);   // 0: automatic, 3 / 4: force the 3- or 4-CTAs-per-SM build
 void launch_reset(const ResetParams &p, void *stream);
 void launch_observe(const StepParams &p, void *stream);
 void launch_pack_state(const DevState &st, int n_envs, const double *f64_em /*[17][E][MAXV]*/,

@@ -300,6 +300,11 @@ class MergeEnvBatched(object):
         return int(self._L.mm_kernel_launches(self._h))
 
 
+def set_step_variant(variant=0):
+    """0: automatic choice between the 3- and the 4-CTAs-per-SM build of the step kernel; 3 / 4: force one."""
+    _lib.check(_lib.lib().mm_set_step_variant(int(variant)))
+
+
 def shield_qp(a, c_lead, c_adj, has_adj, lo, hi, stream=None):
     """n independent CBF-QP solves on CUDA tensors (f64 inputs, uint8 has_adj).  Returns (u f64, active u8)."""
     import torch

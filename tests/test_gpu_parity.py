@@ -148,6 +148,17 @@ def test_cuda_vs_oracle_whole_episodes(mm, orc, shield, traffic, td, reward):
     lockstep_rollout(mm, orc, shield, traffic, td, reward, 2048, 100, 1e-6)
 
 
+@pytest.mark.parametrize("shield,traffic,td,reward", [("cbf-cav", "cav", 3, "default"), ("cbf-avs_cint", "mixed", 3, "srew")])
+def test_four_ctas_per_sm_build_of_the_step_kernel(mm, orc, shield, traffic, td, reward):
+    """The 4-CTAs-per-SM build (4 staged fields, 128 registers; chosen automatically for grids that then fit one wave)
+    computes the same step: the strict lock-step comparison with that build forced."""
+    try:
+        mm.set_step_variant(4)
+        lockstep_rollout(mm, orc, shield, traffic, td, reward, 4096, 40, STATE_TOL)
+    finally:
+        mm.set_step_variant(0)
+
+
 def lockstep_rollout(mm, orc, shield, traffic, td, reward, E, T, state_tol):
     import torch
     lateral = "steer_vel" if shield.endswith("+steer_vel") else "steer"
