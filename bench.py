@@ -433,7 +433,7 @@ def main():
                           "api": "mm_step_host (dense obs [E,12,30] by cudaMemcpyAsync)"}},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "step_kernel<false>", "kernel_ms": kms,
+                     "traffic": traffic, "kernel": "step_kernel<false, false>", "kernel_ms": kms,
                      "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src,
                      "note": "issue/latency-bound f64 kernel (SURVEY.md 8d): HBM fraction is reported as asked; "
                              "see profiles/ for pipe utilisation"},
