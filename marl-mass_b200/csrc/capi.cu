@@ -102,6 +102,22 @@ int reset_stats(mm_env *env) {
     return 0;
 }
 
+// Envs per chunk of the host paths: 64 Ki for large batches; a mid-size batch is still cut in 4 chunks (>= 16 Ki envs),
+// one per stream, so that its device-to-host copies overlap the compute of the following chunks instead of trailing a
+// single launch (8 smaller chunks were measured too: the extra launches and copies cost more than the overlap gains).
+int host_chunk_target(int n_envs) {
+    static const int forced = [] {
+        const char *s = getenv("MM_HOST_CHUNK");
+        int v = s ? atoi(s) : 0;
+        return v > 0 ? v : 0;
+    }();
+    if (forced) return forced;
+    int t = (n_envs + 3) / 4;     // one chunk per stream
+    if (t < 16384) t = 16384;
+    if (t > 65536) t = 65536;
+    return t;
+}
+
 // enqueue one policy step (+ optional re-spawn of finished envs) for envs [off, off+count) on `stream`
 void enqueue_step(mm_env *env, const int8_t *actions_dev, int auto_reset, int off, int count, cudaStream_t stream) {
     StepParams p = step_params(env, actions_dev, off, count);
@@ -228,11 +244,7 @@ int mm_step_host(mm_env *env, const int8_t *actions, int auto_reset, float *obs,
     const int E = env->n_envs;
     // Chunks of ~64 Ki envs (a multiple of the 128-env tile, which also keeps the per-warp statistics rows
     // disjoint) issued round-robin on 4 streams: chunk k's device-to-host copies run while chunks k+1.. compute.
-    static const int chunk_target = [] {
-        const char *s = getenv("MM_HOST_CHUNK");
-        int v = s ? atoi(s) : 0;
-        return v > 0 ? v : 65536;
-    }();
+    const int chunk_target = host_chunk_target(E);
     const int n_str = 4;
     int n_chunks = (E + chunk_target - 1) / chunk_target;
     if (n_chunks < 1) n_chunks = 1;
@@ -284,11 +296,7 @@ int mm_step_host_ragged(mm_env *env, const int8_t *actions, int auto_reset, floa
         env->chunk_rows_host = static_cast<int64_t *>(p);
         for (int c = 0; c < MAX_HOST_CHUNKS; ++c) CUDA_OK(cudaEventCreateWithFlags(&env->chunk_done[c], cudaEventDisableTiming));
     }
-    static const int chunk_target = [] {
-        const char *s = getenv("MM_HOST_CHUNK");
-        int v = s ? atoi(s) : 0;
-        return v > 0 ? v : 65536;
-    }();
+    const int chunk_target = host_chunk_target(E);
     const int n_str = 4;
     int n_chunks = (E + chunk_target - 1) / chunk_target;
     if (n_chunks < 1) n_chunks = 1;
