@@ -163,12 +163,14 @@ int mm_shield_qp(const double *a, const double *c_lead, const double *c_adj, con
  * (weight [out][in], bias [out]), TF32 tensor-core math with fp32 accumulation: the two 128-wide layers run as
  * tcgen05.mma kind::tf32 with the accumulators in TMEM (one persistent CTA per SM, 128 rows per tile), the 128 -> 5
  * output layer, the log-softmax and the draw in the thread that owns the row.  n_agents (nullable) [n_rows / 12]:
- * rows whose slot index (row % 12) is >= n_agents[row / 12] get action 1 (IDLE).  logp_all [n_rows][5] and
+ * rows whose slot index (row % 12) is >= n_agents[row / 12] get action 1 (IDLE).  action_mask (nullable) [n_rows] u8,
+ * bit k = action k available (the env's action_mask buffer): the invalid-action masking of the MAPPO_GI actor
+ * (marl/single_agent/Model_gi.py:63-66, logits of unavailable actions = -1e8 before the log-softmax).  logp_all [n_rows][5] and
  * logp_sel [n_rows] are optional outputs (log-probabilities of all actions / of the drawn one).  All pointers are
  * DEVICE pointers; enqueued on `stream`, no synchronisation. */
 int mm_actor_sample(const float *obs, const int32_t *n_agents, int64_t n_rows, const float *w1, const float *b1,
                     const float *w2, const float *b2, const float *w3, const float *b3, uint64_t seed, uint64_t step,
-                    int8_t *actions, float *logp_all, float *logp_sel, void *stream);
+                    const uint8_t *action_mask, int8_t *actions, float *logp_all, float *logp_sel, void *stream);
 
 /* Implementation switch of mm_actor_sample (process-wide): 0 = tcgen05 (default), 1 = the warp-level mma.sync kernel
  * kept as an independent cross-check. */

@@ -95,7 +95,7 @@ def lib():
     L.mm_stats.argtypes = [h, C.POINTER(MMStats), C.c_int]
     L.mm_shield_qp.argtypes = [C.c_void_p] * 6 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mm_actor_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 6 + [C.c_uint64, C.c_uint64] + \
-                                 [C.c_void_p] * 4
+                                 [C.c_void_p] * 5
     L.mm_set_actor_impl.argtypes = [C.c_int]
     L.mm_set_step_variant.argtypes = [C.c_int]
     L.mm_discounted_returns.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int64, C.c_int,

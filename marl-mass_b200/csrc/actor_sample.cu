@@ -65,12 +65,22 @@ __device__ __forceinline__ uint32_t philox_row(uint64_t seed, uint64_t step, uin
     return c0;
 }
 
+// Invalid-action masking of the MAPPO_GI actor (marl/single_agent/Model_gi.py:63-66: logits[action_mask == 0] = -1e8
+// before the log-softmax): bit k of mask_bits[row] set = action k available (the env kernel's action_mask buffer).
+__device__ __forceinline__ void apply_action_mask(float (&l)[AC_OUT], const uint8_t *mask_bits, int64_t row) {
+    if (!mask_bits) return;
+    const uint32_t bits = mask_bits[row];
+#pragma unroll
+    for (int k = 0; k < AC_OUT; ++k)
+        if (!((bits >> k) & 1u)) l[k] = -1e8f;
+}
+
 __global__ void __launch_bounds__(AC_THREADS, 1)
 actor_sample_kernel(const float *__restrict__ obs, const int32_t *__restrict__ n_agents, int64_t n_rows,
                     const float *__restrict__ w1, const float *__restrict__ b1, const float *__restrict__ w2,
                     const float *__restrict__ b2, const float *__restrict__ w3, const float *__restrict__ b3,
-                    uint64_t seed, uint64_t step, int8_t *__restrict__ actions, float *__restrict__ logp_all,
-                    float *__restrict__ logp_sel) {
+                    uint64_t seed, uint64_t step, const uint8_t *__restrict__ mask_bits, int8_t *__restrict__ actions,
+                    float *__restrict__ logp_all, float *__restrict__ logp_sel) {
     extern __shared__ __align__(16) uint32_t ac_sm[];
     float *sm_f = reinterpret_cast<float *>(ac_sm);
     const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -185,6 +195,7 @@ actor_sample_kernel(const float *__restrict__ obs, const int32_t *__restrict__ n
                 float l[AC_OUT];
 #pragma unroll
                 for (int k = 0; k < AC_OUT; ++k) l[k] = t == 0 ? l_lo[k] : l_hi[k];
+                apply_action_mask(l, mask_bits, row);
                 float m = l[0];
 #pragma unroll
                 for (int k = 1; k < AC_OUT; ++k) m = fmaxf(m, l[k]);
@@ -287,8 +298,8 @@ __global__ void __launch_bounds__(T5_THREADS, 1)
 actor_sample_tcgen05_kernel(const float *__restrict__ obs, const int32_t *__restrict__ n_agents, int64_t n_rows,
                             const float *__restrict__ w1, const float *__restrict__ b1, const float *__restrict__ w2,
                             const float *__restrict__ b2, const float *__restrict__ w3, const float *__restrict__ b3,
-                            uint64_t seed, uint64_t step, int8_t *__restrict__ actions, float *__restrict__ logp_all,
-                            float *__restrict__ logp_sel) {
+                            uint64_t seed, uint64_t step, const uint8_t *__restrict__ mask_bits,
+                            int8_t *__restrict__ actions, float *__restrict__ logp_all, float *__restrict__ logp_sel) {
     extern __shared__ __align__(128) uint8_t t5_sm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float4 *a1 = reinterpret_cast<float4 *>(t5_sm + T5_A1), *w1f = reinterpret_cast<float4 *>(t5_sm + T5_W1);
@@ -434,6 +445,7 @@ actor_sample_tcgen05_kernel(const float *__restrict__ obs, const int32_t *__rest
                 for (int g2 = 0; g2 < T5_CSPLIT - 1; ++g2) acc += part[(g2 * T5_ROWS + row_in_tile) * 8 + k];
                 l[k] = acc + b3s[k];
             }
+            apply_action_mask(l, mask_bits, row);
             float m = l[0];
 #pragma unroll
             for (int k = 1; k < AC_OUT; ++k) m = fmaxf(m, l[k]);
@@ -501,7 +513,7 @@ void set_actor_impl(int impl) { g_actor_impl = impl ? 1 : 0; }
 
 int launch_actor_sample(const float *obs, const int32_t *n_agents, int64_t n_rows, const float *w1, const float *b1,
                         const float *w2, const float *b2, const float *w3, const float *b3, uint64_t seed, uint64_t step,
-                        int8_t *actions, float *logp_all, float *logp_sel, void *stream) {
+                        const uint8_t *mask_bits, int8_t *actions, float *logp_all, float *logp_sel, void *stream) {
     if (n_rows <= 0) return 0;
     static bool attr_set = false;
     const int smem = AC_SMEM_WORDS * (int)sizeof(uint32_t);
@@ -524,13 +536,13 @@ int launch_actor_sample(const float *obs, const int32_t *n_agents, int64_t n_row
         }
         int64_t t5_tiles = (n_rows + T5_ROWS - 1) / T5_ROWS, t5_ctas = t5_tiles < sms ? t5_tiles : sms;
         actor_sample_tcgen05_kernel<<<(unsigned)t5_ctas, T5_THREADS, T5_SMEM, (cudaStream_t)stream>>>(
-            obs, n_agents, n_rows, w1, b1, w2, b2, w3, b3, seed, step, actions, logp_all, logp_sel);
+            obs, n_agents, n_rows, w1, b1, w2, b2, w3, b3, seed, step, mask_bits, actions, logp_all, logp_sel);
         return cudaGetLastError() == cudaSuccess ? 0 : 1;
     }
     int64_t tiles = (n_rows + 15) / 16, ctas = (tiles + AC_THREADS / 32 - 1) / (AC_THREADS / 32);
     if (ctas > sms) ctas = sms;   // persistent: one CTA per SM, warps stride over the 16-row tiles
     actor_sample_kernel<<<(unsigned)ctas, AC_THREADS, smem, (cudaStream_t)stream>>>(obs, n_agents, n_rows, w1, b1, w2, b2, w3,
-                                                                                     b3, seed, step, actions, logp_all, logp_sel);
+                                                                                     b3, seed, step, mask_bits, actions, logp_all, logp_sel);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 

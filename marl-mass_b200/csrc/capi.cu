@@ -481,11 +481,12 @@ int mm_shield_qp(const double *a, const double *c_lead, const double *c_adj, con
 
 int mm_actor_sample(const float *obs, const int32_t *n_agents, int64_t n_rows, const float *w1, const float *b1,
                     const float *w2, const float *b2, const float *w3, const float *b3, uint64_t seed, uint64_t step,
-                    int8_t *actions, float *logp_all, float *logp_sel, void *stream) {
+                    const uint8_t *action_mask, int8_t *actions, float *logp_all, float *logp_sel, void *stream) {
     if (!obs || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !actions) return fail(MM_ERR_ARG, "null argument");
     if (n_rows < 0) return fail(MM_ERR_ARG, "n_rows must be >= 0");
     if (n_agents && n_rows % MAXV != 0) return fail(MM_ERR_ARG, "n_rows must be a multiple of MM_MAXV when n_agents is given");
-    if (launch_actor_sample(obs, n_agents, n_rows, w1, b1, w2, b2, w3, b3, seed, step, actions, logp_all, logp_sel, stream))
+    if (launch_actor_sample(obs, n_agents, n_rows, w1, b1, w2, b2, w3, b3, seed, step, action_mask, actions, logp_all, logp_sel,
+                            stream))
         return fail(MM_ERR_CUDA, cudaGetErrorString(cudaGetLastError()));
     return 0;
 }

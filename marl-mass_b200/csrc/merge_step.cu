@@ -30,18 +30,18 @@
 // namespace.  A grid that fits one wave of 4 CTAs / SM but not one of 3 (e.g. 65 536 envs = 512 CTAs on 148 SMs)
 // otherwise runs a second, almost empty wave: 2 x the CTA latency instead of 1.3 x.
 #ifdef MM_VARIANT4
-#define MM_NS mm4
+#define MM_KNS mm4
 #define MM_NHOT 4
 #ifndef MM_MIN_BLOCKS
 #define MM_MIN_BLOCKS 4
 #endif
 namespace mm4 { using namespace mm; }
 #else
-#define MM_NS mm
+#define MM_KNS mm
 #define MM_NHOT 6
 #endif
 
-namespace MM_NS {
+namespace MM_KNS {
 
 constexpr int N_HOT = MM_NHOT;       // fields F_X .. staged in shared memory during a step (6: including cos / sin heading)
 constexpr int BLOCK = TILE;
@@ -2006,7 +2006,7 @@ void launch_qp(const double *a, const double *c_lead, const double *c_adj, const
     qp_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, c_lead, c_adj, has_adj, lo, hi, n, u, active);
 }
 
-}  // namespace MM_NS
+}  // namespace MM_KNS
 
 #ifdef MM_VARIANT4
 namespace mm {

@@ -118,7 +118,7 @@ void launch_ragged_pack(const float *obs, const int32_t *n_agents, int count, in
 // caller-side kernels (actor_sample.cu)
 int launch_actor_sample(const float *obs, const int32_t *n_agents, int64_t n_rows, const float *w1, const float *b1,
                         const float *w2, const float *b2, const float *w3, const float *b3, uint64_t seed, uint64_t step,
-                        int8_t *actions, float *logp_all, float *logp_sel, void *stream);
+                        const uint8_t *mask_bits, int8_t *actions, float *logp_all, float *logp_sel, void *stream);
 void set_actor_impl(int impl);
 int launch_discounted_returns(const float *rewards, const uint8_t *dones, const float *final_value, float gamma, int T,
                               int64_t n_cols, int cols_per_env, float *out, void *stream);

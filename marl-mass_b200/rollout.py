@@ -81,12 +81,13 @@ def set_actor_impl(name):
     _lib.check(_lib.lib().mm_set_actor_impl({"tcgen05": 0, "mma": 1}[name]))
 
 
-def actor_sample(actor, obs, n_agents=None, seed=0, step=0, want_logp=False):
+def actor_sample(actor, obs, n_agents=None, seed=0, step=0, want_logp=False, action_mask=None):
     """Fused actor forward + exploration draw (mm_actor_sample): obs [..., 30] f32 cuda -> actions int8 [...].
 
     `actor` is an ActorNetwork (or any module with fc1/fc2/fc3 Linear layers 30-128-128-5); its parameters are read
     in place.  n_agents [E] int32 marks the live rows when obs is the env's [E, 12, 30] buffer.  With want_logp the
-    log-probabilities of all five actions are returned too ([..., 5] f32)."""
+    log-probabilities of all five actions are returned too ([..., 5] f32).  action_mask: uint8 bit masks, one per row
+    (`env.buffers()["action_mask"]`, bit k = action k available) for the MAPPO_GI actor's invalid-action masking."""
     rows = obs.numel() // NS
     obs = obs.contiguous()
     assert obs.is_cuda and obs.dtype == torch.float32
@@ -97,9 +98,12 @@ def actor_sample(actor, obs, n_agents=None, seed=0, step=0, want_logp=False):
     logp = torch.empty(obs.shape[:-1] + (NA,), dtype=torch.float32, device=obs.device) if want_logp else None
     if n_agents is not None:
         assert n_agents.dtype == torch.int32 and n_agents.is_cuda and n_agents.numel() * MAXV == rows
+    if action_mask is not None:
+        assert action_mask.dtype == torch.uint8 and action_mask.is_cuda and action_mask.numel() == rows
+        action_mask = action_mask.contiguous()
     _lib.check(_lib.lib().mm_actor_sample(_ptr(obs), _ptr(n_agents), C.c_int64(rows), *[_ptr(t) for t in w],
-                                          C.c_uint64(seed), C.c_uint64(step), _ptr(actions), _ptr(logp), _ptr(None),
-                                          _stream()))
+                                          C.c_uint64(seed), C.c_uint64(step), _ptr(action_mask), _ptr(actions), _ptr(logp),
+                                          _ptr(None), _stream()))
     return (actions, logp) if want_logp else actions
 
 

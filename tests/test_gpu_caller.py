@@ -109,6 +109,41 @@ def test_tcgen05_and_mma_sync_actor_kernels_agree(mm):
     assert float((a_m != a_t).float().mean()) < 5e-3
 
 
+def test_invalid_action_masking_of_the_gi_actor(mm):
+    """Model_gi.ActorNetwork (marl/single_agent/Model_gi.py:63-66): logits[action_mask == 0] = -1e8, then log-softmax.
+    The env's own action masks (action_masking = True) go straight into the kernel; masked actions are never drawn."""
+    import torch
+    from marl_mass_b200 import rollout
+    E = 4096
+    env = mm.MergeEnvBatched(E, dict(mm.DEFAULT_CONFIG, safety_guarantee="cbf-cav", traffic_density=3, HEADWAY_TIME=0.5,
+                                     cbf_eta=0.03125, action_masking=True), device=0)
+    obs, mask = env.reset(seed=8)                      # mask [E, 12, 5] int32 (unpacked)
+    a0 = torch.randint(0, 5, (E, 12), device="cuda", dtype=torch.int8)
+    for _ in range(30):                                # into the merge zone: lane changes become available for some
+        obs, _, _, _ = env.step(a0, auto_reset=True)
+    v = env.buffers()
+    bits = v["action_mask"]
+    mask = env.action_mask()
+    torch.manual_seed(2)
+    actor = rollout.ActorNetwork().cuda()
+    for impl in ("tcgen05", "mma"):
+        rollout.set_actor_impl(impl)
+        acts, logp = rollout.actor_sample(actor, obs, v["n_agents"], seed=3, step=1, want_logp=True, action_mask=bits)
+        with torch.no_grad():
+            logits = actor.fc3(torch.relu(actor.fc2(torch.relu(actor.fc1(obs.view(-1, mm.NS)))))).view(E, mm.MAXV, mm.NA)
+            logits = torch.where(mask == 0, torch.full_like(logits, -1e8), logits)
+            want = torch.log_softmax(logits + 1e-8, dim=-1)
+        live = torch.arange(mm.MAXV, device="cuda")[None, :] < v["n_agents"][:, None]
+        avail = mask[live] != 0
+        assert float((logp[live] - want[live]).abs()[avail].max()) < LOGP_TOL
+        assert bool((logp[live][~avail] < -1e7).all())
+        chosen = torch.gather(mask[live], 1, acts[live].long()[:, None])
+        assert bool((chosen == 1).all())               # only available actions are drawn
+        assert 0.0 < float((mask[live] == 0).float().mean()) < 0.9
+    rollout.set_actor_impl("tcgen05")
+    env.close()
+
+
 def test_exploration_draw_follows_the_softmax(mm):
     """np.random.choice(p = softmax) (mappo.py:223-228): empirical action frequencies of many draws from a few fixed
     observation rows against the kernel's own probabilities."""
