@@ -282,6 +282,28 @@ class MergeEnvBatched(object):
     def set_state(self, st):
         _lib.check(self._L.mm_set_state(self._h, C.byref(self._host_state_struct(st))))
 
+    def save(self, path):
+        """Checkpoint: the full env-major state (every vehicle field, env counters) plus the config, as one .npz.
+        (The reference cannot checkpoint an env; a batched rollout of hours needs it.)  The device-side spawn streams
+        (per-env episode counters) are not part of it: after `load`, auto-reset draws new scenes from fresh streams."""
+        import json
+        st = self.get_state()
+        np.savez_compressed(path, __config__=np.frombuffer(json.dumps(self.config).encode(), dtype=np.uint8),
+                            __reset_count__=np.int64(self._reset_count), **st)
+
+    def load(self, path):
+        """Resume from `save`: same number of envs; the config stored with the state takes effect."""
+        import json
+        z = np.load(path)
+        st = {k: np.ascontiguousarray(z[k]) for k in z.files if not k.startswith("__")}
+        assert st["n_veh"].shape[0] == self.n_envs, "checkpoint holds %d envs, this handle %d" % (st["n_veh"].shape[0], self.n_envs)
+        self.config.update(json.loads(bytes(z["__config__"]).decode()))
+        self._reset_count = int(z["__reset_count__"])
+        self._apply_config()
+        self.set_state(st)
+        v = self.buffers()
+        return v["obs"], self.action_mask()
+
     def shield_diag(self):
         E = self.n_envs
         d = {k: np.zeros((E, 3, MAXV), np.int32) for k in SH_I}

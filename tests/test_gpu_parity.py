@@ -293,6 +293,34 @@ def test_ragged_host_step_equals_device_step(mm):
     b_env.close()
 
 
+def test_checkpoint_resume_continues_bit_identically(mm, tmp_path):
+    """save() / load(): a rollout resumed from a checkpoint in a fresh handle continues exactly like the original."""
+    import torch
+    cfg = dict(mm.DEFAULT_CONFIG, safety_guarantee="cbf-cav", traffic_density=3, traffic_type="mixed", HEADWAY_TIME=0.5,
+               cbf_eta=0.03125, agent_reward="mrew")
+    E = 3000
+    a_env = mm.MergeEnvBatched(E, cfg)
+    a_env.reset(seed=21)
+    rng = np.random.RandomState(2)
+    acts = [torch.from_numpy(rng.randint(0, 5, size=(E, 12)).astype(np.int8)).cuda() for _ in range(30)]
+    for t in range(15):
+        a_env.step(acts[t])
+    path = str(tmp_path / "ckpt.npz")
+    a_env.save(path)
+    b_env = mm.MergeEnvBatched(E, dict(mm.DEFAULT_CONFIG))      # default config: load() must bring the stored one
+    obs_b, _ = b_env.load(path)
+    assert torch.equal(obs_b, a_env.buffers()["obs"])
+    for t in range(15, 30):
+        oa, ra, da, _ = a_env.step(acts[t])
+        ob, rb, db, _ = b_env.step(acts[t])
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db)
+    sa, sb = a_env.get_state(), b_env.get_state()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
+    a_env.close()
+    b_env.close()
+
+
 def test_qp_kernel_vs_golden_and_oracle(mm, orc):
     """mm_shield_qp: every QP the reference posed + 1e6 synthetic ones (oracle as the checker)."""
     import torch
