@@ -1961,7 +1961,7 @@ void launch_step(const StepParams &p, bool diag, void *stream) {
         return full * lat[per_sm] + lat[(rem + sms - 1) / sms];
     };
     static const double lat3[4] = {0.0, 9.55, 11.42, 12.27}, lat4[5] = {0.0, 10.5, 12.6, 13.5, 16.2};
-    const bool small_grid = grid <= 12 * sms;     // on large grids the two builds are within a few per cent: keep the default
+    const bool small_grid = grid <= 8 * sms;      // measured: still ahead at 1024 CTAs, behind at 1536 (time_variants.py)
     const bool four = g_step_variant == 4 || (g_step_variant == 0 && !diag && !p.cfg.couple_counts && small_grid &&
                                               estimate(4, lat4) < 0.97 * estimate(3, lat3));
     if (four) launch_step_occ4(p, diag, stream);
