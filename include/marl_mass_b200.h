@@ -100,7 +100,10 @@ typedef struct {
  * Replaces: safe_status/safe_diff/safe_action logged by MDPLCVehicle.log_step (safe_controller.py:187-227). */
 typedef struct {
     int32_t *ran, *leader, *front_adj, *rear_adj, *constrain_adj, *active, *is_lc_safe;
-    double *safe_acc, *safe_steer, *nom_acc, *nom_steer, *lc_margin;
+    /* control profile (safe_controller.py:187-227 log_step), every vehicle that moved in the sub-step: */
+    int32_t *moved, *hl_action /* -1 none */, *lane;
+    double *safe_acc, *safe_steer, *nom_acc, *nom_steer, *lc_margin;   /* applied and nominal action (all vehicles) */
+    double *x, *y, *heading, *speed, *min_headway;                     /* state after the sub-step's move */
 } mm_shield_diag_host;
 
 /* Episode statistics accumulated on the device since the last mm_stats(reset=1).

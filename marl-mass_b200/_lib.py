@@ -18,8 +18,8 @@ F64_FIELDS = ("x", "y", "heading", "speed", "target_speed", "gvx", "rec1_x", "re
 I32_FIELDS = ("kind", "lane", "target_lane", "speed_index", "crashed", "hl_action", "hist_len", "fg_set",
               "is_collaborating", "is_lc_safe", "collaborate_adj")
 ENV_FIELDS = ("n_veh", "n_cav", "n_merge", "steps", "time")
-SH_I = ("ran", "leader", "front_adj", "rear_adj", "constrain_adj", "active", "is_lc_safe")
-SH_F = ("safe_acc", "safe_steer", "nom_acc", "nom_steer", "lc_margin")
+SH_I = ("ran", "leader", "front_adj", "rear_adj", "constrain_adj", "active", "is_lc_safe", "moved", "hl_action", "lane")
+SH_F = ("safe_acc", "safe_steer", "nom_acc", "nom_steer", "lc_margin", "x", "y", "heading", "speed", "min_headway")
 
 _PD = C.POINTER(C.c_double)
 _PF = C.POINTER(C.c_float)

@@ -173,8 +173,8 @@ int mm_create(const mm_config *cfg, int n_envs, int device, int record_diag, mm_
     env->stats_rows = (E + 31) / 32;
     rc |= dev_alloc(env, &env->out.stats, env->stats_rows * N_STATS);
     if (record_diag) {
-        rc |= dev_alloc(env, &env->out.sh_i, (size_t)7 * E * 3 * MAXV);
-        rc |= dev_alloc(env, &env->out.sh_f, (size_t)5 * E * 3 * MAXV);
+        rc |= dev_alloc(env, &env->out.sh_i, (size_t)10 * E * 3 * MAXV);
+        rc |= dev_alloc(env, &env->out.sh_f, (size_t)10 * E * 3 * MAXV);
     }
     if (rc) { mm_destroy(env); return rc; }
     if ((rc = reset_stats(env))) { mm_destroy(env); return rc; }
@@ -440,11 +440,13 @@ int mm_get_shield_diag(mm_env *env, mm_shield_diag_host *dst) {
     CUDA_OK(cudaSetDevice(env->device));
     CUDA_OK(cudaDeviceSynchronize());
     const size_t P = (size_t)env->n_envs * 3 * MAXV;
-    int32_t *id[7] = {dst->ran, dst->leader, dst->front_adj, dst->rear_adj, dst->constrain_adj, dst->active, dst->is_lc_safe};
-    double *fd[5] = {dst->safe_acc, dst->safe_steer, dst->nom_acc, dst->nom_steer, dst->lc_margin};
-    for (int k = 0; k < 7; ++k)
+    int32_t *id[10] = {dst->ran, dst->leader, dst->front_adj, dst->rear_adj, dst->constrain_adj, dst->active, dst->is_lc_safe,
+                       dst->moved, dst->hl_action, dst->lane};
+    double *fd[10] = {dst->safe_acc, dst->safe_steer, dst->nom_acc, dst->nom_steer, dst->lc_margin,
+                      dst->x, dst->y, dst->heading, dst->speed, dst->min_headway};
+    for (int k = 0; k < 10; ++k)
         if (id[k]) CUDA_OK(cudaMemcpy(id[k], env->out.sh_i + k * P, P * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    for (int k = 0; k < 5; ++k)
+    for (int k = 0; k < 10; ++k)
         if (fd[k]) CUDA_OK(cudaMemcpy(fd[k], env->out.sh_f + k * P, P * sizeof(double), cudaMemcpyDeviceToHost));
     return 0;
 }

@@ -930,6 +930,20 @@ __device__ void vehicle_step(Env &ev, const StepParams &p, int i, int sub, size_
     X(i) = nx; Y(i) = ny; H(i) = nh; V(i) = nv;
     FL(i) = f;
     reorder_after_move(ev, i, nx);
+    if (DIAG) {
+        // control profile of this sub-step (safe_controller.py:187-227 log_step: the state after the move, the action
+        // that produced it, the high-level action in force), for every vehicle, shielded or not
+        const size_t plane = (size_t)p.n_envs * 3 * MAXV, idx = (e_glob * 3 + sub) * MAXV + i;
+        int32_t *si = p.out.sh_i;
+        double *sf = p.out.sh_f;
+        const int hl = fl_hl(f);
+        si[7 * plane + idx] = 1; si[8 * plane + idx] = hl == A_NONE ? -1 : hl; si[9 * plane + idx] = lane;
+        if (!si[idx]) {   // the shield did not run: the applied action is the (clipped) nominal one
+            sf[idx] = acc; sf[plane + idx] = steer; sf[2 * plane + idx] = acc; sf[3 * plane + idx] = steer;
+        }
+        sf[5 * plane + idx] = nx; sf[6 * plane + idx] = ny; sf[7 * plane + idx] = nh; sf[8 * plane + idx] = nv;
+        sf[9 * plane + idx] = GF(F_MINHW, i);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1507,7 +1521,8 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
                 p.out.sh_i[plane + idx] = MM_NB_NONE; p.out.sh_i[2 * plane + idx] = MM_NB_NONE;
                 p.out.sh_i[3 * plane + idx] = MM_NB_NONE;
                 p.out.sh_i[4 * plane + idx] = 0; p.out.sh_i[5 * plane + idx] = 0; p.out.sh_i[6 * plane + idx] = 0;
-                for (int q = 0; q < 5; ++q) p.out.sh_f[q * plane + idx] = 0.0;
+                p.out.sh_i[7 * plane + idx] = 0; p.out.sh_i[8 * plane + idx] = -1; p.out.sh_i[9 * plane + idx] = 0;
+                for (int q = 0; q < 10; ++q) p.out.sh_f[q * plane + idx] = 0.0;
             }
         }
         steps = min(steps + 1, (int)EI_STEPS_MASK);  // abstract.py:457

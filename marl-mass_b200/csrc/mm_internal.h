@@ -68,8 +68,8 @@ struct DevOut {
     uint8_t *done, *agents_dones, *action_mask;
     int32_t *n_agents;
     // per-sub-step shield record [E][3][MAXV] (record_diag only, else null)
-    int32_t *sh_i;      // 7 planes: ran, leader, front_adj, rear_adj, constrain_adj, active, is_lc_safe
-    double *sh_f;       // 5 planes: safe_acc, safe_steer, nom_acc, nom_steer, lc_margin
+    int32_t *sh_i;      // 10 planes: ran, leader, front_adj, rear_adj, constrain_adj, active, is_lc_safe, moved, hl_action, lane
+    double *sh_f;       // 10 planes: safe_acc, safe_steer, nom_acc, nom_steer, lc_margin, x, y, heading, speed, min_headway
     double *stats;      // [N_STATS] accumulators
 };
 

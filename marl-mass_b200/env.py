@@ -350,6 +350,7 @@ class _VehicleView(object):
 
     def __init__(self, env, slot):
         self._env, self._slot = env, slot
+        self.state_hist, self.action_hist, self.t_step = [], [], 0.0
 
     def _st(self):
         return self._env._state()
@@ -376,6 +377,14 @@ class _VehicleView(object):
         return self._slot
 
 
+class _RoadView(object):
+    """env.road as mappo.py:425-435 / control_eval_mappo.py read it: `.vehicles`, each with `.id`, `.state_hist`,
+    `.action_hist` (the per-sub-step control profile of safe_controller.py:187-227, when store_profile is on)."""
+
+    def __init__(self):
+        self.vehicles = []
+
+
 class MergeEnvLCMARL(object):
     """Drop-in for gym.make('merge-multi-agent-v1') on the step path (merge_env_v1.py:410-525)."""
     n_a = NA
@@ -385,7 +394,11 @@ class MergeEnvLCMARL(object):
 
     def __init__(self, config=None, device=0):
         config = dict(config or {}, env_name=self.ENV_NAME)
-        self._b = MergeEnvBatched(1, config, device=device, record_diag=False)
+        # store_profile (MDPLCVehicle(store_profile=...), safe_controller.py:31,187-189): keep every vehicle's per-sub-step
+        # state / action records in env.road.vehicles[i].state_hist / .action_hist (needs the kernel's diagnostic record)
+        self.store_profile = bool(config.pop("store_profile", False))
+        self.road = _RoadView()
+        self._b = MergeEnvBatched(1, config, device=device, record_diag=self.store_profile)
         self.n_s = self._b.n_s
         self.config = self._b.config
         self.seed = self.config.get("seed", 0)
@@ -414,7 +427,8 @@ class MergeEnvLCMARL(object):
         self.steps = 0
         self.vehicle_speed, self.vehicle_pos = [], []
         n = int(self._state()["n_cav"][0])
-        self.controlled_vehicles = [_VehicleView(self, i) for i in range(n)]
+        self.road.vehicles = [_VehicleView(self, i) for i in range(int(self._state()["n_veh"][0]))]
+        self.controlled_vehicles = self.road.vehicles[:n]
         import torch
         torch.cuda.synchronize(self._b.device)
         obs = self._b.obs_view()[0, :n].double().cpu().numpy()
@@ -431,6 +445,8 @@ class MergeEnvLCMARL(object):
         torch.cuda.synchronize(self._b.device)
         self._cache = None
         self.steps += 1
+        if self.store_profile:
+            self._log_profiles()
         st = self._state()
         obs = self._b.obs_view()[0, :n].double().cpu().numpy()
         reward = float(v["reward"][0])
@@ -451,6 +467,36 @@ class MergeEnvLCMARL(object):
         if done:
             info["merge_percent"] = float(v["merge_percent"][0])
         return obs, reward, done, info
+
+    def _log_profiles(self):
+        """log_step (safe_controller.py:187-227) for every vehicle and sub-step of the policy step just taken."""
+        d = self._b.shield_diag()
+        dt = 1.0 / self.config["simulation_frequency"]
+        steer_vel = self.config.get("lateral_control", "steer") == "steer_vel"
+        for sub in range(3):
+            for v in self.road.vehicles:
+                i = v._slot
+                if not d["moved"][0, sub, i]:
+                    continue
+                v.t_step += dt
+                h, sp = float(d["heading"][0, sub, i]), float(d["speed"][0, sub, i])
+                rec = {"presence": 1, "x": float(d["x"][0, sub, i]), "y": float(d["y"][0, sub, i]),
+                       "vx": sp * np.cos(h), "vy": sp * np.sin(h), "heading": h, "cos_h": np.cos(h), "sin_h": np.sin(h),
+                       "speed": sp, "t_step": v.t_step, "headway": float(d["min_headway"][0, sub, i])}
+                if not steer_vel:
+                    rec["steering_angle"] = float(d["nom_steer"][0, sub, i])
+                ran = bool(d["ran"][0, sub, i])
+                if ran:
+                    rec["safe_status"] = {"active_set": int(d["active"][0, sub, i]), "is_lc_safe": bool(d["is_lc_safe"][0, sub, i])}
+                v.state_hist.append(rec)
+                hl = int(d["hl_action"][0, sub, i])
+                act = {"acceleration": float(d["safe_acc"][0, sub, i]), "steering": float(d["safe_steer"][0, sub, i]),
+                       "ull_acceleration": float(d["nom_acc"][0, sub, i]), "ull_steering": float(d["nom_steer"][0, sub, i]),
+                       "lc_action": hl if hl >= 0 else None, "t_step": v.t_step}
+                if ran:
+                    act["safe_diff"] = {"acceleration": act["acceleration"] - act["ull_acceleration"],
+                                        "steering": act["steering"] - act["ull_steering"]}
+                v.action_hist.append(act)
 
     def _mask(self, n):
         """action mask as the reference returns it (abstract.py:201-209, 474-481): all ones without masking; with

@@ -522,6 +522,47 @@ def test_single_env_adapter_replays_reference_episodes(mm, name):
     env.close()
 
 
+def test_control_profiles_of_the_adapter(mm):
+    """store_profile: env.road.vehicles[i].state_hist / action_hist (safe_controller.py:187-227) after a replayed
+    reference episode - one record per vehicle and sub-step, the last record of a policy step equal to the golden
+    post-step state, the shielded action equal to the golden shield record."""
+    g, cfg = load_golden("mass_td3_mixed")
+    ep, rows = g["ep_start"], g["row_of_step"]
+    env = mm.make(cfg["env_name"], config=dict(env_config(cfg), store_profile=True))
+    seed = cfg["seeds"][0]
+    env.reset(is_training=False, testing_seeds=seed)
+    n_veh = int(g["st_n_veh"][ep[0]])
+    assert len(env.road.vehicles) == n_veh and [v.id for v in env.road.vehicles] == list(range(n_veh))
+    steps = np.where((rows >= ep[0]) & (rows < ep[1] - 1))[0]
+    n = len(env.controlled_vehicles)
+    subs_total = 0
+    for t in steps:
+        env.step(tuple(int(x) for x in g["act"][t, :n]))
+        post = rows[t] + 1
+        n_sub = int(g["st_time"][post] - g["st_time"][rows[t]])          # 3, or fewer on a terminal step
+        subs_total += n_sub
+        for i, v in enumerate(env.road.vehicles):
+            assert len(v.state_hist) == subs_total and len(v.action_hist) == subs_total
+            last = v.state_hist[-1]
+            # (free-running replay of a whole episode: the tolerance of the other adapter tests, not the teacher-forced one)
+            assert abs(last["x"] - g["st_x"][post, i]) <= 1e-5 * max(1, abs(g["st_x"][post, i]))
+            assert abs(last["y"] - g["st_y"][post, i]) <= 1e-5 and abs(last["heading"] - g["st_heading"][post, i]) <= 1e-5
+            # the record is taken before the collision pass: a crash in this sub-step changes the speed afterwards
+            if not g["st_crashed"][post, i]:
+                assert abs(last["speed"] - g["st_speed"][post, i]) <= 1e-5 * max(1, g["st_speed"][post, i])
+            assert abs(last["t_step"] - subs_total / 15) < 1e-9
+            for sub in range(n_sub):
+                a = v.action_hist[subs_total - n_sub + sub]
+                if g["sh_ran"][t, sub, i]:
+                    assert abs(a["acceleration"] - g["sh_safe_acc"][t, sub, i]) <= 1e-4 * max(1, abs(g["sh_safe_acc"][t, sub, i]))
+                    assert abs(a["ull_acceleration"] - g["sh_nom_acc"][t, sub, i]) <= 1e-4 * max(1, abs(g["sh_nom_acc"][t, sub, i]))
+                    assert "safe_diff" in a
+                else:
+                    assert a["acceleration"] == a["ull_acceleration"] and "safe_diff" not in a
+    assert subs_total == int(g["st_time"][ep[1] - 1])
+    env.close()
+
+
 def test_masked_reset_stats_and_errors(mm, orc):
     import torch
     cfg = dict(mm.DEFAULT_CONFIG, safety_guarantee="cbf-avs_cint", traffic_density=2, traffic_type="mixed",
