@@ -419,6 +419,8 @@ def main():
                    "actions": "i.i.d. uniform{0..4}, resident in HBM", "auto_reset": True,
                    "episode_phases": "staggered uniformly over the 100-step episode, per 128-env tile (untimed prologue)",
                    "l2": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (E * 3.0e-6),
+                   "step_kernel_build": "automatic (3 CTAs/SM; 4 CTAs/SM for grids of 3..8 CTAs per SM whose wave "
+                                        "structure favours it, include/marl_mass_b200.h mm_set_step_variant)",
                    "shield_solves_per_s": tot["shield_solves"] / (ms_total * 1e-3),
                    "shield_active_frac": tot["shield_active"] / max(tot["shield_solves"], 1.0),
                    "lane_change_veto_frac": tot["lane_change_vetoes"] / max(tot["shield_solves"], 1.0),
