@@ -14,10 +14,12 @@ CASES = [("cbf-cav", "cav", 3, "default", "steer"), ("cbf-cav", "mixed", 3, "sre
          ("cbf-avs_cint", "mixed", 2, "mrew", "steer"), ("none", "mixed", 1, "default", "steer"), ("cbf-cav", "cav", 1, "mrew", "steer"),
          ("cbf-cav", "mixed", 3, "default", "steer_vel"), ("cbf-cav", "cav", 2, "srew", "steer"), ("cbf-avs_cint", "mixed", 3, "default", "steer_vel")]
 rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+first_round = int(sys.argv[2]) if len(sys.argv) > 2 else 0      # seeds depend on the round index
 E, T = 4096, 100
 total_env_steps, boundary = 0, 0
 t0 = time.time()
-for rnd in range(rounds):
+for rnd in range(first_round, first_round + rounds):
+    mm.set_step_variant(4 if rnd % 2 else 3)                    # odd rounds: the 4-CTAs-per-SM build of the step kernel
     for ci, (shield, traffic, td, reward, lateral) in enumerate(CASES):
         cfg = dict(mm.DEFAULT_CONFIG, safety_guarantee=shield, lateral_control=lateral, traffic_type=traffic, traffic_density=td,
                    agent_reward=reward, HEADWAY_TIME=0.5, cbf_eta=0.03125, HIGH_SPEED_REWARD=4, HEADWAY_COST=1, MERGING_LANE_COST=8)
