@@ -75,7 +75,7 @@ int validate(const mm_config *c) {
     if (c->shield < MM_SHIELD_NONE || c->shield > MM_SHIELD_MASS) return fail(MM_ERR_ARG, "Undefined safety_type");
     if (c->reward_kind < MM_REW_DEFAULT || c->reward_kind > MM_REW_MREW) return fail(MM_ERR_ARG, "unknown agent_reward");
     if (c->traffic_density < 1 || c->traffic_density > 3) return fail(MM_ERR_ARG, "traffic_density must be 1, 2 or 3");
-    if (c->traffic_type != MM_TRAFFIC_CAV && c->traffic_type != MM_TRAFFIC_MIXED) return fail(MM_ERR_ARG, "unknown traffic_type");
+    if (c->traffic_type < MM_TRAFFIC_CAV || c->traffic_type > MM_TRAFFIC_AV) return fail(MM_ERR_ARG, "unknown traffic_type");
     if (c->substeps < 1 || c->substeps > 3) return fail(MM_ERR_ARG, "substeps must be in 1..3");
     if (c->duration_steps < 1 || c->duration_steps > 255) return fail(MM_ERR_ARG, "duration_steps must be in 1..255");
     if (!(c->dt > 0)) return fail(MM_ERR_ARG, "dt must be positive");

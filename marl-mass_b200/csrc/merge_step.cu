@@ -1717,6 +1717,7 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ Re
     int n_cav = p.num_cav > 0 ? p.num_cav : lo_c + d_cav;
     int n_hdv = lo_h + d_hdv;
     if (p.cfg.traffic_type == MM_TRAFFIC_CAV) { n_cav += n_hdv; n_hdv = 0; }
+    else if (p.cfg.traffic_type == MM_TRAFFIC_AV) { n_hdv = n_cav + n_hdv - 1; n_cav = 1; }   // merge_env_v1.py:485-489
     if (n_cav + n_hdv > 11) n_cav = 11 - n_hdv;
 
     // spawn slots without replacement: main [10,60,...,260], ramp [5,55,...,255] (merge_env_v1.py:284-319)

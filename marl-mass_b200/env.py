@@ -26,7 +26,7 @@ from ._lib import ENV_FIELDS, F64_FIELDS, I32_FIELDS, MAXV, NA, NS, SH_F, SH_I
 
 SHIELD = {"none": 0, "cbf-hss": 1, "cbf-av": 1, "cbf-avs": 1, "cbf-avs_cint": 1, "cbf-mass": 2, "cbf-cav": 2}
 REWARD = {"default": 0, "srew": 1, "mrew": 2}
-TRAFFIC = {"cav": 0, "mixed": 1}
+TRAFFIC = {"cav": 0, "mixed": 1, "av": 2}
 
 DEFAULT_CONFIG = {
     # merge_env_v1.py:32-57, 415-437 and abstract.py:106-130, with the values the shipped MASS ini uses
@@ -70,7 +70,7 @@ def make_mm_config(cfg):
         tt = cfg.get("traffic_type", "cav")
         rk = cfg.get("agent_reward", "default")
     if tt not in TRAFFIC:
-        raise ValueError("traffic_type %r is not supported on the batched path (cav | mixed)" % (tt,))
+        raise ValueError("traffic_type %r is not supported on the batched path (cav | mixed | av)" % (tt,))
     sim, pol = int(cfg["simulation_frequency"]), int(cfg["policy_frequency"])
     return _lib.MMConfig(
         shield=SHIELD[sg], reward_kind=REWARD[rk], env_v0=int(v0), steer_vel=int(lat == "steer_vel" and not v0),

@@ -71,6 +71,9 @@ CASES = {
                                lateral_control="steer_vel"), [4, 6], 113),
     "v05_steervel_unsafe_td1": (dict(env_name="merge-multi-agent-v05", safety_guarantee="none", traffic_density=1,
                                      HEADWAY_TIME=1.2, lateral_control="steer_vel"), [7, 8], 114),
+    # traffic_type = av (merge_env_v1.py:485-489): one shielded CAV among IDM / MOBIL vehicles
+    "mass_td3_av": (dict(safety_guarantee="cbf-cav", traffic_density=3, traffic_type="av", mixed_traffic=True),
+                    [30, 31, 32, 33, 34], 115),
 }
 
 SH_I = ("ran", "leader", "front_adj", "rear_adj", "constrain_adj", "active", "is_lc_safe")

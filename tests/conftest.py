@@ -21,5 +21,7 @@ def golden_dir():
 GOLDEN_CASES = ["unsafe_td1", "unsafe_td3", "unsafe_td2_mixed", "hss_td3", "hss_td3_mixed", "mass_td1",
                 "mass_td3_srew", "mass_td3_mixed", "mass_td2_mixed_mrew",
                 # lateral_control = steer_vel, and the 5x5-observation env id merge-multi-agent-v05
-                "steervel_unsafe_td2", "steervel_hss_td3_mixed", "steervel_mass_td2", "v05_steervel_unsafe_td1"]
+                "steervel_unsafe_td2", "steervel_hss_td3_mixed", "steervel_mass_td2", "v05_steervel_unsafe_td1",
+                # traffic_type = av: one shielded CAV among HDVs
+                "mass_td3_av"]
 V0_CASES = ["v0_unsafe_td1", "v0_unsafe_td2_mixed"]
