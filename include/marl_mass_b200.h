@@ -33,7 +33,8 @@ typedef enum { MM_OK = 0, MM_ERR_ARG = -1, MM_ERR_CUDA = -2, MM_ERR_STATE = -3 }
 enum { MM_KIND_NONE = 0, MM_KIND_CAV = 1, MM_KIND_HDV = 2 };
 enum { MM_SHIELD_NONE = 0, MM_SHIELD_HSS = 1, MM_SHIELD_MASS = 2 };
 enum { MM_REW_DEFAULT = 0, MM_REW_SREW = 1, MM_REW_MREW = 2 };
-enum { MM_TRAFFIC_CAV = 0, MM_TRAFFIC_MIXED = 1, MM_TRAFFIC_AV = 2 /* one CAV, the rest HDVs (merge_env_v1.py:485-489) */ };
+enum { MM_TRAFFIC_CAV = 0, MM_TRAFFIC_MIXED = 1, MM_TRAFFIC_AV = 2 /* one CAV, the rest HDVs (merge_env_v1.py:485-489) */,
+       MM_TRAFFIC_HDV = 3 /* HDVs only (490-494); with env_hdv */ };
 enum { MM_NB_NONE = -1, MM_NB_OBSTACLE = -2 };
 /* QP active-set code reported per shield solve */
 enum { MM_ACT_LEAD = 1, MM_ACT_UPPER = 2, MM_ACT_LOWER = 4, MM_ACT_ADJ = 8, MM_ACT_SLACK = 16 };
@@ -60,6 +61,9 @@ typedef struct {
                                 episode (merge_env_v1.py:180-211) are drawn once per 128-env tile instead of once per
                                 env; every env still follows the reference's law, but the envs of a tile share
                                 (n_CAV, n_HDV), which lets a CTA skip the vehicle ranks none of its envs has */
+    int32_t env_hdv;         /* 1: env id merge-multi-agent-hdv-v1 (MergeEnvLCHDV, merge_env_v1.py:552-674; traffic_type
+                                hdv): no controlled vehicles - every vehicle is observed and rewarded (its row in obs /
+                                agents_rewards), any crash ends the episode, no regional rewards / per-agent dones */
 } mm_config;
 
 typedef struct mm_env mm_env;

@@ -34,7 +34,7 @@ class MMConfig(C.Structure):
                 ("dt", C.c_double), ("eta", C.c_double), ("tau", C.c_double),
                 ("collision_reward", C.c_double), ("high_speed_reward", C.c_double), ("headway_cost", C.c_double),
                 ("headway_time", C.c_double), ("merging_lane_cost", C.c_double), ("env_v0", C.c_int32),
-                ("steer_vel", C.c_int32), ("couple_counts", C.c_int32)]
+                ("steer_vel", C.c_int32), ("couple_counts", C.c_int32), ("env_hdv", C.c_int32)]
 
 
 class MMStateHost(C.Structure):

@@ -75,7 +75,9 @@ int validate(const mm_config *c) {
     if (c->shield < MM_SHIELD_NONE || c->shield > MM_SHIELD_MASS) return fail(MM_ERR_ARG, "Undefined safety_type");
     if (c->reward_kind < MM_REW_DEFAULT || c->reward_kind > MM_REW_MREW) return fail(MM_ERR_ARG, "unknown agent_reward");
     if (c->traffic_density < 1 || c->traffic_density > 3) return fail(MM_ERR_ARG, "traffic_density must be 1, 2 or 3");
-    if (c->traffic_type < MM_TRAFFIC_CAV || c->traffic_type > MM_TRAFFIC_AV) return fail(MM_ERR_ARG, "unknown traffic_type");
+    if (c->traffic_type < MM_TRAFFIC_CAV || c->traffic_type > MM_TRAFFIC_HDV) return fail(MM_ERR_ARG, "unknown traffic_type");
+    if ((c->traffic_type == MM_TRAFFIC_HDV) != (c->env_hdv != 0))
+        return fail(MM_ERR_ARG, "traffic_type hdv and the env id merge-multi-agent-hdv-v1 go together");
     if (c->substeps < 1 || c->substeps > 3) return fail(MM_ERR_ARG, "substeps must be in 1..3");
     if (c->duration_steps < 1 || c->duration_steps > 255) return fail(MM_ERR_ARG, "duration_steps must be in 1..255");
     if (!(c->dt > 0)) return fail(MM_ERR_ARG, "dt must be positive");
@@ -408,8 +410,9 @@ int mm_set_state(mm_env *env, const mm_state_host *src) {
     for (int k = 0; k < HOST_I32; ++k) if (!id[k]) return fail(MM_ERR_ARG, "mm_set_state: every i32 field is required");
     for (int k = 0; k < HOST_ENV; ++k) if (!ed[k]) return fail(MM_ERR_ARG, "mm_set_state: every env field is required");
     for (size_t e = 0; e < E; ++e) {
-        if (ed[0][e] < 0 || ed[0][e] > 11 || ed[1][e] < 1 || ed[1][e] > ed[0][e])
-            return fail(MM_ERR_STATE, "mm_set_state: need 1 <= n_cav <= n_veh <= 11");
+        const int min_cav = env->cfg.env_hdv ? 0 : 1;      // the all-HDV env has no controlled vehicle
+        if (ed[0][e] < 1 || ed[0][e] > 11 || ed[1][e] < min_cav || ed[1][e] > ed[0][e])
+            return fail(MM_ERR_STATE, "mm_set_state: need 1 <= n_cav <= n_veh <= 11 (n_cav = 0 only in the all-HDV env)");
         for (int i = 0; i < ed[0][e]; ++i) {
             int kind = id[0][e * MAXV + i];
             if (kind != (i < ed[1][e] ? MM_KIND_CAV : MM_KIND_HDV))

@@ -1062,10 +1062,15 @@ __device__ __noinline__ void collision_pass(Env &ev, uint32_t mask) {
     }
 }
 
-// merge_env_v1.py:168-172
-__device__ __forceinline__ bool is_terminal(const Env &ev, int steps, int duration_steps) {
-    bool t = steps >= duration_steps;
-    for (int i = 0; i < ev.n_cav; ++i) t = t || (FL(i) & FL_CRASHED) || X(i) < 0;
+// vehicles that are observed / rewarded: the controlled ones, or all of them in MergeEnvLCHDV (observation.py:430-442,
+// merge_env_v1.py:518-524)
+__device__ __forceinline__ int n_observed(const Env &ev, const mm_config &cfg) { return cfg.env_hdv ? ev.n_veh : ev.n_cav; }
+
+// merge_env_v1.py:168-172; MergeEnvLCHDV 670-673: any vehicle crashed, no x < 0 clause
+__device__ __forceinline__ bool is_terminal(const Env &ev, int steps, const mm_config &cfg) {
+    bool t = steps >= cfg.duration_steps;
+    const int n = n_observed(ev, cfg);
+    for (int i = 0; i < n; ++i) t = t || (FL(i) & FL_CRASHED) || (!cfg.env_hdv && X(i) < 0);
     return t;
 }
 
@@ -1307,13 +1312,14 @@ __device__ __noinline__ void write_outputs(const Env &ev, const StepParams &p, s
     const DevOut &o = p.out;
     float *obs = o.obs + e * (size_t)(MAXV * NS);
     const bool sv = p.cfg.steer_vel && !p.cfg.env_v0;
-    for (int i = 0; i < ev.n_cav; ++i) observe_agent(ev, i, sv, obs + i * NS);
-    float2 *z = reinterpret_cast<float2 *>(obs + ev.n_cav * NS);
+    const int n_obs = n_observed(ev, p.cfg);      // the controlled vehicles; every vehicle in the all-HDV env
+    for (int i = 0; i < n_obs; ++i) observe_agent(ev, i, sv, obs + i * NS);
+    float2 *z = reinterpret_cast<float2 *>(obs + n_obs * NS);
     // rows of absent agents are zeroed when the scene is (re)built and n_cav is fixed for the episode, so the
     // per-step path does not rewrite them
     if (!with_rewards)
-        for (int q = 0; q < (MAXV - ev.n_cav) * NS / 2; ++q) __stcs(z + q, make_float2(0.f, 0.f));
-    o.n_agents[e] = ev.n_cav;
+        for (int q = 0; q < (MAXV - n_obs) * NS / 2; ++q) __stcs(z + q, make_float2(0.f, 0.f));
+    o.n_agents[e] = n_obs;
     // _get_available_actions (abstract.py:219-240): IDLE always; LANE_LEFT only from bc1 when bc0 is reachable (the
     // one non-forbidden side lane of the network); FASTER / SLOWER by the speed index
     for (int i = 0; i < MAXV; ++i) {
@@ -1335,10 +1341,10 @@ __device__ __noinline__ void write_outputs(const Env &ev, const StepParams &p, s
 
     double local[MAXV];
     double rsum = 0, ssum = 0, tsum = 0, minhw = CUDART_INF;
-    bool done = is_terminal(ev, steps, p.cfg.duration_steps);
+    bool done = is_terminal(ev, steps, p.cfg);
     bool any_crash = false;
 #pragma unroll 1
-    for (int i = 0; i < ev.n_cav; ++i) {
+    for (int i = 0; i < n_obs; ++i) {
         double hd = headway_distance(ev, i);
         local[i] = agent_reward(ev, p.cfg, i, hd);
         rsum += local[i];
@@ -1360,7 +1366,13 @@ __device__ __noinline__ void write_outputs(const Env &ev, const StepParams &p, s
     for (int i = 0; i < MAXV; ++i) {
         float lr = 0.f, rr = 0.f;
         uint8_t ad = 0;
-        if (i < ev.n_cav) {
+        if (i < n_obs && p.cfg.env_hdv) {
+            // MergeEnvLCHDV.step (merge_env_v1.py:603-665): no regional rewards / per-agent dones; the per-vehicle
+            // reward terms are kept for inspection
+            lr = (float)local[i];
+            const int lane = fl_lane(FL(i));
+            if (lane == L_BC1 || lane == L_KB0 || lane == L_JK0) ++n_rem;
+        } else if (i < n_obs) {
             // regional reward (merge_env_v1.py:91-124): own-lane group plus, where one exists, the group across
             int lane = fl_lane(FL(i));
             bool on_main = lane == L_AB0 || lane == L_BC0 || lane == L_CD0;
@@ -1389,20 +1401,20 @@ __device__ __noinline__ void write_outputs(const Env &ev, const StepParams &p, s
         o.regional_rewards[e * MAXV + i] = rr;
         o.agents_dones[e * MAXV + i] = ad;
     }
-    double reward = rsum / ev.n_cav;
+    double reward = rsum / n_obs;
     o.reward[e] = (float)reward;
     o.done[e] = done ? 1 : 0;
-    o.average_speed[e] = (float)(ssum / ev.n_cav);
+    o.average_speed[e] = (float)(ssum / n_obs);
     o.traffic_speed[e] = (float)(tsum / ev.n_veh);
     o.min_headway[e] = (float)minhw;
     double mp = -1.0;
     if (done) mp = n_merge > 0 ? (double)(n_merge - n_rem) / n_merge * 100 : 100.0;
     o.merge_percent[e] = (float)mp;
 
-    stat_acc[ST_AGENT_STEPS] += ev.n_cav;
+    stat_acc[ST_AGENT_STEPS] += n_obs;
     stat_acc[ST_ENV_STEPS] += 1;
     stat_acc[ST_REWARD] += reward;
-    stat_acc[ST_SPEED] += ssum / ev.n_cav;
+    stat_acc[ST_SPEED] += ssum / n_obs;
     stat_acc[ST_MINHW] = fmin(stat_acc[ST_MINHW], minhw);
     if (done) {
         stat_acc[ST_EPISODES] += 1;
@@ -1612,7 +1624,7 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
         if (running) {
             if (uint32_t close = close_pair_mask(ev)) collision_pass(ev, close);
             time = min(time + 1, (int)EI_TIME_MASK);
-            if (is_terminal(ev, steps, p.cfg.duration_steps)) running = false;  // abstract.py:530
+            if (is_terminal(ev, steps, p.cfg)) running = false;  // abstract.py:530
         }
     }
     PHASE_BARRIER(1);
@@ -1718,6 +1730,7 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ Re
     int n_hdv = lo_h + d_hdv;
     if (p.cfg.traffic_type == MM_TRAFFIC_CAV) { n_cav += n_hdv; n_hdv = 0; }
     else if (p.cfg.traffic_type == MM_TRAFFIC_AV) { n_hdv = n_cav + n_hdv - 1; n_cav = 1; }   // merge_env_v1.py:485-489
+    else if (p.cfg.traffic_type == MM_TRAFFIC_HDV) { n_hdv = n_cav + n_hdv; n_cav = 0; }      // merge_env_v1.py:490-494
     if (n_cav + n_hdv > 11) n_cav = 11 - n_hdv;
 
     // spawn slots without replacement: main [10,60,...,260], ramp [5,55,...,255] (merge_env_v1.py:284-319)

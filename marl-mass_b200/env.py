@@ -26,7 +26,7 @@ from ._lib import ENV_FIELDS, F64_FIELDS, I32_FIELDS, MAXV, NA, NS, SH_F, SH_I
 
 SHIELD = {"none": 0, "cbf-hss": 1, "cbf-av": 1, "cbf-avs": 1, "cbf-avs_cint": 1, "cbf-mass": 2, "cbf-cav": 2}
 REWARD = {"default": 0, "srew": 1, "mrew": 2}
-TRAFFIC = {"cav": 0, "mixed": 1, "av": 2}
+TRAFFIC = {"cav": 0, "mixed": 1, "av": 2, "hdv": 3}
 
 DEFAULT_CONFIG = {
     # merge_env_v1.py:32-57, 415-437 and abstract.py:106-130, with the values the shipped MASS ini uses
@@ -36,7 +36,7 @@ DEFAULT_CONFIG = {
     "mixed_traffic": None, "traffic_type": "cav", "agent_reward": "default", "cbf_eta": 0.0,
     "action_masking": False, "seed": 0, "env_name": "merge-multi-agent-v1",
 }
-ENV_IDS = ("merge-multi-agent-v1", "merge-multi-agent-v0", "merge-multi-agent-v05")
+ENV_IDS = ("merge-multi-agent-v1", "merge-multi-agent-v0", "merge-multi-agent-v05", "merge-multi-agent-hdv-v1")
 
 
 def traffic_type_of(cfg):
@@ -70,7 +70,12 @@ def make_mm_config(cfg):
         tt = cfg.get("traffic_type", "cav")
         rk = cfg.get("agent_reward", "default")
     if tt not in TRAFFIC:
-        raise ValueError("traffic_type %r is not supported on the batched path (cav | mixed | av)" % (tt,))
+        raise ValueError("traffic_type %r is not supported (cav | mixed | av | hdv)" % (tt,))
+    hdv_env = env_name == "merge-multi-agent-hdv-v1"
+    if hdv_env != (tt == "hdv"):
+        # MergeEnvLCHDV is the all-HDV evaluation env (merge_env_v1.py:552-674, test-idm-td3.ini); the other env classes
+        # divide by the number of controlled vehicles
+        raise ValueError("traffic_type 'hdv' and env id merge-multi-agent-hdv-v1 go together (got %r with %r)" % (tt, env_name))
     sim, pol = int(cfg["simulation_frequency"]), int(cfg["policy_frequency"])
     return _lib.MMConfig(
         shield=SHIELD[sg], reward_kind=REWARD[rk], env_v0=int(v0), steer_vel=int(lat == "steer_vel" and not v0),
@@ -80,7 +85,7 @@ def make_mm_config(cfg):
         collision_reward=float(cfg["COLLISION_REWARD"]), high_speed_reward=float(cfg["HIGH_SPEED_REWARD"]),
         headway_cost=float(cfg["HEADWAY_COST"]), headway_time=float(cfg["HEADWAY_TIME"]),
         merging_lane_cost=float(cfg["MERGING_LANE_COST"]),
-        couple_counts=int(bool(cfg.get("couple_vehicle_counts", False))))
+        couple_counts=int(bool(cfg.get("couple_vehicle_counts", False))), env_hdv=int(hdv_env))
 
 
 class _DevArray(object):
@@ -106,7 +111,8 @@ class MergeEnvBatched(object):
         self.T = int(self.config["duration"] * self.config["policy_frequency"])
         self.v0 = self.config.get("env_name", "merge-multi-agent-v1") == "merge-multi-agent-v0"
         # Kinematics 5x5 (v0, v05: merge_env_v1.py:389-408, 527-550) vs KinematicLC 5x6 (v1)
-        self.n_s = NS if self.config.get("env_name", "merge-multi-agent-v1") == "merge-multi-agent-v1" else 25
+        # KinematicLC 5x6 for the LC envs (v1, hdv-v1), Kinematics 5x5 for v0 / v05
+        self.n_s = NS if self.config.get("env_name", "merge-multi-agent-v1") in ("merge-multi-agent-v1", "merge-multi-agent-hdv-v1") else 25
         self._L = _lib.lib()
         self._h = C.c_void_p()
         _lib.check(self._L.mm_create(C.byref(make_mm_config(self.config)), self.n_envs, self.device,
@@ -532,8 +538,53 @@ class MergeEnvMARLSteerVel(MergeEnvLCMARL):
     n_s = 25
 
 
+class MergeEnvLCHDV(MergeEnvLCMARL):
+    """Drop-in for gym.make('merge-multi-agent-hdv-v1') (merge_env_v1.py:552-674; eval_idm.py, test-idm-td3.ini): IDM /
+    MOBIL vehicles only.  Nobody is controlled: `step(action)` ignores its argument, the observation has one row per
+    vehicle, the reward is the mean of the per-vehicle reward over all vehicles, any crash ends the episode."""
+    ENV_NAME = "merge-multi-agent-hdv-v1"
+
+    def __init__(self, config=None, device=0):
+        super().__init__(dict({"traffic_type": "hdv"}, **(config or {})), device=device)
+
+    @property
+    def vehicle(self):
+        return self.road.vehicles[0] if self.road.vehicles else None
+
+    def reset(self, is_training=True, testing_seeds=0, num_CAV=0):
+        super().reset(is_training, testing_seeds, num_CAV)
+        n = len(self.road.vehicles)
+        return self._b.obs_view()[0, :n].double().cpu().numpy(), np.array([[1] * self.n_a] * n)
+
+    def step(self, action=()):
+        import torch
+        v = self._b.buffers()
+        self._b.step(None)
+        torch.cuda.synchronize(self._b.device)
+        self._cache = None
+        self.steps += 1
+        if self.store_profile:
+            self._log_profiles()
+        st = self._state()
+        n = len(self.road.vehicles)
+        obs = self._b.obs_view()[0, :n].double().cpu().numpy()
+        self.vehicle_speed.append([float(x) for x in st["speed"][0, :n]])
+        self.vehicle_pos.append([float(x) for x in st["x"][0, :n]])
+        done = bool(v["done"][0])
+        info = {"speed": float(st["speed"][0, 0]), "crashed": bool(st["crashed"][0, 0]),
+                "average_speed": float(v["average_speed"][0]), "traffic_speed": float(v["traffic_speed"][0]),
+                "min_headway": float(v["min_headway"][0])}
+        if done:
+            info["merge_percent"] = float(v["merge_percent"][0])
+        return obs, float(v["reward"][0]), done, info
+
+    def is_crashed(self):
+        st = self._state()
+        return bool(st["crashed"][0, :len(self.road.vehicles)].any())
+
+
 _REGISTRY = {"merge-multi-agent-v1": MergeEnvLCMARL, "merge-multi-agent-v0": MergeEnvMARL,
-             "merge-multi-agent-v05": MergeEnvMARLSteerVel}
+             "merge-multi-agent-v05": MergeEnvMARLSteerVel, "merge-multi-agent-hdv-v1": MergeEnvLCHDV}
 
 
 def make(env_id, **kwargs):

@@ -54,8 +54,10 @@ def num_vehicles(rs, traffic_density, traffic_type, num_CAV=0):
         num_CAV, num_HDV = num_CAV + num_HDV, 0
     elif traffic_type == "av":          # merge_env_v1.py:485-489: one CAV, everybody else human-driven
         num_CAV, num_HDV = 1, num_CAV + num_HDV - 1
+    elif traffic_type == "hdv":         # merge_env_v1.py:490-494: nobody is controlled
+        num_CAV, num_HDV = 0, num_CAV + num_HDV
     elif traffic_type != "mixed":
-        raise ValueError("traffic_type %r is not supported on the batched path (cav | mixed | av)" % (traffic_type,))
+        raise ValueError("traffic_type %r is not supported (cav | mixed | av | hdv)" % (traffic_type,))
     return int(num_CAV), int(num_HDV)
 
 

@@ -782,11 +782,16 @@ static void hdv_step(const mo_config *cfg, env_t *e, int self) {
     if (v->hist_len < 2) v->hist_len++;
 }
 
-/* merge_env_v1.py:168-172 */
+/* vehicles that are observed / rewarded: the controlled ones, or all of them in MergeEnvLCHDV (observation.py:430-442,
+ * merge_env_v1.py:518-524) */
+static int n_out(const mo_config *cfg, const env_t *e) { return cfg->env_hdv ? e->n_veh : e->n_cav; }
+
+/* merge_env_v1.py:168-172; MergeEnvLCHDV: 670-673 (any vehicle crashed, no x < 0 clause) */
 static int is_terminal(const mo_config *cfg, const env_t *e) {
-    for (int i = 0; i < e->n_cav; ++i)
+    for (int i = 0; i < n_out(cfg, e); ++i)
         if (e->v[i].crashed) return 1;
     if (e->steps >= cfg->duration_steps) return 1;
+    if (cfg->env_hdv) return 0;
     for (int i = 0; i < e->n_cav; ++i)
         if (e->v[i].x < 0) return 1;
     return 0;
@@ -913,9 +918,9 @@ static double regional_reward(const env_t *e, int self, const double *local) {
 }
 
 /* merge_env_v1.py:373-386 */
-static double min_time_headway(const env_t *e) {
+static double min_time_headway(const mo_config *cfg, const env_t *e) {   /* hdv env: 587-601, over every vehicle */
     double mh = INFINITY;
-    for (int i = 0; i < e->n_cav; ++i) {
+    for (int i = 0; i < n_out(cfg, e); ++i) {
         const veh_t *a = &e->v[i];
         double hd = headway_distance(e, i);
         if (fabs(OBST_Y - a->y) <= 2 && OBST_X > a->x) {
@@ -1015,7 +1020,8 @@ static void step_env(const mo_config *cfg, env_t *e, const int8_t *act, const mo
     double local[MAXV];
     memset(local, 0, sizeof(local));
     double rsum = 0, ssum = 0, tsum = 0;
-    for (int i = 0; i < e->n_cav; ++i) {
+    const int no = n_out(cfg, e);
+    for (int i = 0; i < no; ++i) {
         observe_agent(e, i, cfg->steer_vel && !cfg->env_v0, obs + i * MO_NS);
         local[i] = agent_reward(cfg, e, i);
         rsum += local[i];
@@ -1023,25 +1029,26 @@ static void step_env(const mo_config *cfg, env_t *e, const int8_t *act, const mo
     }
     for (int i = 0; i < e->n_veh; ++i) tsum += e->v[i].speed;
     int done = is_terminal(cfg, e);
-    out->reward[ei] = rsum / e->n_cav;
+    out->reward[ei] = rsum / no;
     out->done[ei] = done;
-    out->average_speed[ei] = ssum / e->n_cav;
+    out->average_speed[ei] = ssum / no;
     out->traffic_speed[ei] = tsum / e->n_veh;
-    out->min_headway[ei] = min_time_headway(e);
+    out->min_headway[ei] = min_time_headway(cfg, e);
     for (int i = 0; i < MAXV; ++i) {
         int k = ei * MAXV + i;
         out->agents_rewards[k] = 0; out->regional_rewards[k] = 0; out->agents_dones[k] = 0;
     }
-    for (int i = 0; i < e->n_cav; ++i) {
+    for (int i = 0; i < no; ++i) {
         int k = ei * MAXV + i;
         out->agents_rewards[k] = local[i];
+        if (cfg->env_hdv) continue;     /* MergeEnvLCHDV.step returns neither regional rewards nor per-agent dones */
         out->regional_rewards[k] = regional_reward(e, i, local);
         out->agents_dones[k] = e->v[i].crashed || e->steps >= cfg->duration_steps || e->v[i].x < 0;
     }
     double mp = -1.0;
     if (done) {
         int n_rem = 0;
-        for (int i = 0; i < e->n_cav; ++i)
+        for (int i = 0; i < no; ++i)
             if (e->v[i].lane == L_BC1 || e->v[i].lane == L_KB0 || e->v[i].lane == L_JK0) n_rem++;
         mp = e->n_merge > 0 ? (double)(e->n_merge - n_rem) / e->n_merge * 100 : 100.0;
     }
@@ -1093,12 +1100,12 @@ void mo_step(const mo_config *cfg, const mo_state *st, const int8_t *actions, co
     for (int t = 1; t < n_threads; ++t) pthread_join(tids[t], NULL);
 }
 
-void mo_observe(const mo_state *st, double *obs, int n_env, int steer_vel) {
+void mo_observe(const mo_state *st, double *obs, int n_env, int steer_vel, int env_hdv) {
     for (int ei = 0; ei < n_env; ++ei) {
         env_t e;
         load_env(st, ei, &e);
         double *o = obs + (size_t)ei * MAXV * MO_NS;
         memset(o, 0, sizeof(double) * MAXV * MO_NS);
-        for (int i = 0; i < e.n_cav; ++i) observe_agent(&e, i, steer_vel, o + i * MO_NS);
+        for (int i = 0; i < (env_hdv ? e.n_veh : e.n_cav); ++i) observe_agent(&e, i, steer_vel, o + i * MO_NS);
     }
 }

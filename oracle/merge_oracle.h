@@ -41,6 +41,8 @@ typedef struct {
     double collision_reward, high_speed_reward, headway_cost, headway_time, merging_lane_cost;
     int32_t env_v0;          /* 1: merge-multi-agent-v0 (MDPVehicle: no [-12.5, 6] acceleration clip, never shielded) */
     int32_t steer_vel;       /* 1: lateral_control = steer_vel (safe_controller.py:84-98, 124-150) */
+    int32_t env_hdv;         /* 1: merge-multi-agent-hdv-v1 (MergeEnvLCHDV, merge_env_v1.py:552-674): no controlled vehicles;
+                                every vehicle is observed and rewarded, any crash ends the episode */
 } mo_config;
 
 typedef struct {
@@ -68,7 +70,7 @@ void mo_step(const mo_config *cfg, const mo_state *st, const int8_t *actions, co
              int n_env, int n_threads);
 
 /* Observation only (reset() returns it): obs [n_env][MO_MAXV][MO_NS]. */
-void mo_observe(const mo_state *st, double *obs, int n_env, int steer_vel);
+void mo_observe(const mo_state *st, double *obs, int n_env, int steer_vel, int env_hdv);
 
 /* The QP alone: closed-form minimiser; returns u, writes the active-set code. */
 double mo_qp(double a, double c_lead, double c_adj, int has_adj, double lo, double hi, int32_t *active);

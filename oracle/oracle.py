@@ -36,7 +36,7 @@ class MoConfig(C.Structure):
                 ("substeps", C.c_int32), ("dt", C.c_double), ("eta", C.c_double), ("tau", C.c_double),
                 ("collision_reward", C.c_double), ("high_speed_reward", C.c_double),
                 ("headway_cost", C.c_double), ("headway_time", C.c_double), ("merging_lane_cost", C.c_double),
-                ("env_v0", C.c_int32), ("steer_vel", C.c_int32)]
+                ("env_v0", C.c_int32), ("steer_vel", C.c_int32), ("env_hdv", C.c_int32)]
 
 
 class MoState(C.Structure):
@@ -67,7 +67,7 @@ def lib():
         _lib.mo_step.argtypes = [C.POINTER(MoConfig), C.POINTER(MoState), C.POINTER(C.c_int8),
                                  C.POINTER(MoOut), C.c_int, C.c_int]
         _lib.mo_step.restype = None
-        _lib.mo_observe.argtypes = [C.POINTER(MoState), _PD, C.c_int, C.c_int]
+        _lib.mo_observe.argtypes = [C.POINTER(MoState), _PD, C.c_int, C.c_int, C.c_int]
         _lib.mo_observe.restype = None
         _lib.mo_qp.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, _PI]
         _lib.mo_qp.restype = C.c_double
@@ -79,7 +79,7 @@ def make_config(cfg):
     sim, pol = int(cfg.get("simulation_frequency", 15)), int(cfg.get("policy_frequency", 5))
     v0 = cfg.get("env_name", "merge-multi-agent-v1") == "merge-multi-agent-v0"
     return MoConfig(
-        env_v0=int(v0), steer_vel=int(cfg.get("lateral_control", "steer") == "steer_vel" and not v0),
+        env_hdv=int(cfg.get("env_name") == "merge-multi-agent-hdv-v1"), env_v0=int(v0), steer_vel=int(cfg.get("lateral_control", "steer") == "steer_vel" and not v0),
         shield=0 if v0 else SHIELD[cfg.get("safety_guarantee", "none")],
         reward_kind=0 if v0 else REWARD[cfg.get("agent_reward", "default")],
         duration_steps=int(cfg.get("duration", 20) * pol), substeps=sim // pol, dt=1 / sim,
@@ -139,11 +139,11 @@ def step(cfg, st, actions, out=None, n_threads=1):
     return out
 
 
-def observe(st, steer_vel=False):
+def observe(st, steer_vel=False, env_hdv=False):
     n_env = st["n_veh"].shape[0]
     obs = np.zeros((n_env, MAXV, NS))
     cs = _c_state(st)
-    lib().mo_observe(C.byref(cs), obs.ctypes.data_as(_PD), n_env, int(steer_vel))
+    lib().mo_observe(C.byref(cs), obs.ctypes.data_as(_PD), n_env, int(steer_vel), int(env_hdv))
     return obs
 
 

@@ -72,6 +72,9 @@ CASES = {
     "v05_steervel_unsafe_td1": (dict(env_name="merge-multi-agent-v05", safety_guarantee="none", traffic_density=1,
                                      HEADWAY_TIME=1.2, lateral_control="steer_vel"), [7, 8], 114),
     # traffic_type = av (merge_env_v1.py:485-489): one shielded CAV among IDM / MOBIL vehicles
+    # test-idm-td3.ini: env merge-multi-agent-hdv-v1 (MergeEnvLCHDV), traffic_type = hdv: IDM / MOBIL vehicles only
+    "hdv_td3": (dict(env_name="merge-multi-agent-hdv-v1", safety_guarantee="cbf-cav", traffic_density=3,
+                     traffic_type="hdv", mixed_traffic=True), [11, 12, 13], 116),
     "mass_td3_av": (dict(safety_guarantee="cbf-cav", traffic_density=3, traffic_type="av", mixed_traffic=True),
                     [30, 31, 32, 33, 34], 115),
 }
@@ -82,6 +85,7 @@ SH_F = ("safe_acc", "safe_steer", "nom_acc", "nom_steer")
 
 def run_case(name):
     overrides, seeds, aseed = CASES[name]
+    hdv_env = overrides.get("env_name") == "merge-multi-agent-hdv-v1"
     env = rl.make_env(**overrides)
     rl.drain_shield_log()
     M = rl.MAXV
@@ -103,7 +107,12 @@ def run_case(name):
             n = int(st["n_cav"])
             a = arng.randint(0, 5, size=n)
             obs, reward, done, info = env.step(tuple(int(x) for x in a))
-            o = rl.step_outputs(env, obs, reward, done, info)
+            if hdv_env:     # every vehicle is observed and rewarded, nobody is controlled
+                o = rl.step_outputs_hdv(env, obs, reward, done, info)
+                n = int(st["n_veh"])
+                a = np.full(n, -1)
+            else:
+                o = rl.step_outputs(env, obs, reward, done, info)
             ap = np.full(M, -1, np.int8)
             ap[:n] = a
             acts.append(ap)

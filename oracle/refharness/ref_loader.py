@@ -232,6 +232,23 @@ def export_state(env):
     return out
 
 
+def step_outputs_hdv(env, obs, reward, done, info):
+    """MergeEnvLCHDV.step (merge_env_v1.py:603-665): one observation row per vehicle, the reward is the mean of
+    `_agent_reward` over ALL vehicles (`_reward`, 518-524); the per-vehicle terms are recomputed here with the
+    reference's own `_agent_reward` so that they can be pinned too.  No regional rewards / per-agent dones."""
+    n = len(env.road.vehicles)
+    local = np.array([env._agent_reward(None, v) for v in env.road.vehicles], np.float64)
+    assert abs(local.mean() - reward) < 1e-12
+    return dict(
+        obs=np.asarray(obs, np.float64).reshape(n, -1),
+        reward=np.float64(reward), done=np.int32(bool(done)),
+        agents_rewards=local, regional_rewards=np.zeros(n), agents_dones=np.zeros(n, np.int32),
+        average_speed=np.float64(info["average_speed"]), traffic_speed=np.float64(info["traffic_speed"]),
+        min_headway=np.float64(info["min_headway"]), merge_percent=np.float64(info.get("merge_percent", -1.0)),
+        action_mask=np.zeros((n, 5), np.int32),
+    )
+
+
 def step_outputs(env, obs, reward, done, info):
     """Flatten what MergeEnv.step returns (merge_env_v1.py:126-166) into arrays."""
     n = len(env.controlled_vehicles)

@@ -25,3 +25,5 @@ GOLDEN_CASES = ["unsafe_td1", "unsafe_td3", "unsafe_td2_mixed", "hss_td3", "hss_
                 # traffic_type = av: one shielded CAV among HDVs
                 "mass_td3_av"]
 V0_CASES = ["v0_unsafe_td1", "v0_unsafe_td2_mixed"]
+# env merge-multi-agent-hdv-v1 (MergeEnvLCHDV, traffic_type = hdv): every vehicle observed, nobody controlled
+HDV_CASES = ["hdv_td3"]

@@ -563,6 +563,48 @@ def test_control_profiles_of_the_adapter(mm):
     env.close()
 
 
+def test_hdv_env_cuda_vs_golden_and_adapter(mm, orc):
+    """merge-multi-agent-hdv-v1 (MergeEnvLCHDV, traffic_type = hdv): teacher-forced CUDA step vs the reference's states
+    and outputs (one observation row / reward term per vehicle), then whole episodes through make(...)."""
+    import torch
+    g, cfg = load_golden("hdv_td3")
+    rows = g["row_of_step"]
+    T = len(rows)
+    env = mm.MergeEnvBatched(T, env_config(cfg), record_diag=True)
+    st = full_state(orc, g, rows)
+    env.set_state(st)
+    nv = st["n_veh"]
+    m = np.arange(12)[None, :] < nv[:, None]
+    v = env.buffers()
+    assert np.array_equal(v["n_agents"].cpu().numpy(), nv)                       # every vehicle is "observed"
+    obs, rew, done, v = env.step(torch.from_numpy(np.ascontiguousarray(g["act"])).cuda())
+    torch.cuda.synchronize()
+    compare_states(env.get_state(), full_state(orc, g, rows + 1), STATE_TOL, "hdv teacher-forced")
+    assert np.array_equal(done.cpu().numpy(), g["done"])
+    assert rel_err(obs.cpu().numpy(), g["obs"]).max() <= F32_TOL and (obs.cpu().numpy()[~m] == 0).all()
+    for k in ("reward", "average_speed", "traffic_speed", "min_headway", "merge_percent", "agents_rewards"):
+        assert rel_err(v[k].cpu().numpy(), g[k]).max() <= F32_TOL, k
+    assert (v["regional_rewards"] == 0).all() and (v["agents_dones"] == 0).all()
+    assert (env.shield_diag()["ran"] == 0).all()
+    env.close()
+    # adapter: whole episodes
+    single = mm.make("merge-multi-agent-hdv-v1", config=env_config(cfg))
+    ep = g["ep_start"]
+    for j, seed in enumerate(cfg["seeds"]):
+        obs, mask = single.reset(is_training=False, testing_seeds=seed)
+        n = int(g["st_n_veh"][ep[j]])
+        assert obs.shape == (n, 30) and len(single.controlled_vehicles) == 0 and len(single.road.vehicles) == n
+        steps = np.where((rows >= ep[j]) & (rows < ep[j + 1] - 1))[0]
+        for t in steps:
+            obs, reward, done, info = single.step(())
+            assert rel_err(obs, g["obs"][t, :n]).max() <= 1e-5
+            assert abs(reward - g["reward"][t]) <= 1e-5 and done == bool(g["done"][t])
+            assert abs(info["average_speed"] - g["average_speed"][t]) <= 1e-4
+            assert abs(info["min_headway"] - g["min_headway"][t]) <= 1e-4 * max(1, abs(g["min_headway"][t]))
+        assert done and info["merge_percent"] == 100.0 and not single.is_crashed()
+    single.close()
+
+
 def test_masked_reset_stats_and_errors(mm, orc):
     import torch
     cfg = dict(mm.DEFAULT_CONFIG, safety_guarantee="cbf-avs_cint", traffic_density=2, traffic_type="mixed",

@@ -102,7 +102,22 @@ def test_spawn_num_cav_override_and_ranges():
         xs = [x for _, x, _, _ in v]
         assert len(set(np.round(xs, 9))) == len(xs) and all(1 <= x <= 264 for x in xs)
     with pytest.raises(ValueError):
-        mm.spawn.spawn_scene(0, 1, "hdv")
+        mm.spawn.spawn_scene(0, 1, "trucks")
+
+
+def test_seed_exact_spawn_and_config_of_the_hdv_env():
+    import marl_mass_b200 as mm
+    g, cfg = load_golden("hdv_td3")
+    st = mm.spawn.spawn_state(cfg["seeds"], cfg["traffic_density"], cfg["traffic_type"])
+    rows = g["ep_start"][:-1]
+    for k in ("x", "y", "speed", "target_speed", "timer", "kind", "lane", "target_lane", "n_veh", "n_cav", "n_merge"):
+        assert np.array_equal(g["st_" + k][rows], st[k]), k
+    assert (st["n_cav"] == 0).all() and (st["n_merge"] == 0).all() and (st["kind"][st["x"] != 0] == 2).all()
+    c = mm.make_mm_config(dict(mm.DEFAULT_CONFIG, env_name="merge-multi-agent-hdv-v1", traffic_type="hdv", traffic_density=3))
+    assert c.env_hdv == 1 and c.traffic_type == 3
+    for bad in (dict(env_name="merge-multi-agent-hdv-v1", traffic_type="mixed"), dict(env_name="merge-multi-agent-v1", traffic_type="hdv")):
+        with pytest.raises(ValueError, match="go together"):
+            mm.make_mm_config(dict(mm.DEFAULT_CONFIG, **bad))
 
 
 def test_shard_ranges_cover_the_env_axis():
@@ -183,8 +198,8 @@ def test_discounted_returns_match_reference_formula():
 
 
 def test_shipped_ini_files_map_onto_the_batched_path():
-    """Every shipped marl/configs/*.ini except the look-ahead baseline shields (priority / dmc) and the all-HDV
-    evaluation env resolves to an mm_config.  Needs the reference tree (present in the build container only)."""
+    """Every shipped marl/configs/*.ini except the look-ahead baseline shields (priority / dmc) resolves to an
+    mm_config.  Needs the reference tree (present in the build container only)."""
     import configparser
     import glob
     import marl_mass_b200 as mm
@@ -208,8 +223,9 @@ def test_shipped_ini_files_map_onto_the_batched_path():
             ok.append(os.path.basename(f))
         except (ValueError, KeyError, AttributeError) as ex:
             rejected[os.path.basename(f)] = str(ex)
-    assert len(ok) == 28 and len(rejected) == 9
-    assert all(("priority" in m) or ("dmc" in m) or ("hdv-v1" in m) for m in rejected.values())
+    assert len(ok) == 29 and len(rejected) == 8
+    assert all(("priority" in m) or ("dmc" in m) for m in rejected.values())
+    assert "test-idm-td3.ini" in ok
     for must in ("marl_cav-heading-t_headway-cbf-cav.ini", "marl_cav-heading-t_headway-cbf-avs_cint.ini",
                  "marl_cav-heading-t_headway-cbf-cav-td3-srew.ini", "marl_cav-heading-t_headway-cbf-cav-mixed.ini",
                  "test-configs_marl-cav-unsafe.ini", "marl_cav_heading-t_headway-cbf-av-steer_vel.ini"):

@@ -170,3 +170,31 @@ def test_caller_side_restatements_match_the_reference_vectors():
     a = oracle.mappo_discount(r[:3], np.zeros((3, 1)), np.array([0.0]), 0.5)
     b = oracle.mappo_discount(r[3:], np.zeros((3, 1)), np.array([10.0]), 0.5)
     assert np.allclose(got[:, 0], np.concatenate([a[:, 0], b[:, 0]]))
+
+
+def test_hdv_env_teacher_forced_and_free_running():
+    """MergeEnvLCHDV (merge-multi-agent-hdv-v1, test-idm-td3.ini): IDM / MOBIL only; one observation row and one reward
+    term per vehicle, reward = their mean, done on any crash or at the horizon, min headway over every vehicle."""
+    g, cfg = load_golden("hdv_td3")
+    rows = g["row_of_step"]
+    st = golden_state(g, rows)
+    out = orc.step(cfg, st, g["act"], n_threads=4)
+    want = golden_state(g, rows + 1)
+    compare_states(st, want, TOL, "hdv teacher-forced")
+    nv = want["n_veh"]
+    m = np.arange(12)[None, :] < nv[:, None]
+    assert np.array_equal(out["done"], g["done"]) and (out["agents_dones"] == 0).all() and (out["regional_rewards"] == 0).all()
+    assert rel_err(out["obs"], g["obs"]).max() <= TOL and (out["obs"][~m] == 0).all()
+    for k in ("reward", "average_speed", "traffic_speed", "min_headway", "merge_percent"):
+        assert rel_err(out[k], g[k]).max() <= TOL, k
+    assert rel_err(out["agents_rewards"], g["agents_rewards"]).max() <= TOL
+    assert np.array_equal(out["average_speed"], out["traffic_speed"]) and (out["sh_ran"] == 0).all()
+    assert rel_err(orc.observe(golden_state(g, g["ep_start"][:-1]), env_hdv=True)[:, :, 0].sum(1), nv[g["ep_start"][:-1]].astype(float)).max() == 0
+    # free running: whole episodes from the reference's reset states
+    ep = g["ep_start"]
+    st = golden_state(g, ep[:-1])
+    first = np.searchsorted(rows, ep[:-1])
+    for t in range(100):
+        out = orc.step(cfg, st, g["act"][first + np.minimum(t, 99)], n_threads=2)
+    assert out["done"].all() and (st["steps"] == 100).all()
+    compare_states(st, golden_state(g, ep[1:] - 1), 1e-6, "hdv free-running")
