@@ -261,3 +261,29 @@ def test_batched_evaluation_equals_the_sequential_protocol(mm):
         assert vs[i].shape == (t, n) and np.allclose(vs[i], inf["vehicle_speed"]) and np.allclose(vp[i], inf["vehicle_position"])
     assert abs(info["min_headway"] - min_hw) < 1e-6
     env.close()
+
+
+def test_batched_evaluation_of_the_idm_baseline(mm):
+    """eval_idm.py's protocol (the all-IDM env merge-multi-agent-hdv-v1 on the evaluation seeds) through the same batched
+    `evaluation.evaluation`: equals the sequential loop over the adapter."""
+    import torch
+    from marl_mass_b200 import evaluation as ev
+    cfg = dict(env_name="merge-multi-agent-hdv-v1", traffic_type="hdv", safety_guarantee="cbf-cav", traffic_density=3,
+               HEADWAY_TIME=0.5, cbf_eta=0.03125)
+    seeds = [132, 730, 103, 874, 343]
+    idle = lambda obs, n_agents: torch.ones((obs.shape[0], 12), dtype=torch.int8, device="cuda")
+    rewards, (vs, vp), info = ev.evaluation(idle, cfg, seeds, is_train=False)
+    env = mm.make("merge-multi-agent-hdv-v1", config=cfg)
+    for i, s in enumerate(seeds):
+        obs, _ = env.reset(is_training=False, testing_seeds=s)
+        n = len(env.road.vehicles)
+        done, t, rs, sp = False, 0, [], 0.0
+        while not done:
+            obs, r, done, inf = env.step(())
+            t += 1
+            rs.append(r)
+            sp += inf["average_speed"]
+        assert info["steps"][i] == t and np.allclose(rewards[i], rs, rtol=0, atol=0)
+        assert abs(info["avg_speeds"][i] - sp / t) < 1e-5 and info["merge_percents"][i] == inf["merge_percent"] == 100.0
+        assert info["crash_count"][i] == env.is_crashed() and vs[i].shape == (t, n)
+    env.close()
