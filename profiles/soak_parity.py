@@ -12,7 +12,8 @@ from helpers import F64_FIELDS, I32_FIELDS, ENV_FIELDS, OUT_I, rel_err, used_mas
 
 CASES = [("cbf-cav", "cav", 3, "default", "steer"), ("cbf-cav", "mixed", 3, "srew", "steer"), ("cbf-avs_cint", "cav", 3, "default", "steer"),
          ("cbf-avs_cint", "mixed", 2, "mrew", "steer"), ("none", "mixed", 1, "default", "steer"), ("cbf-cav", "cav", 1, "mrew", "steer"),
-         ("cbf-cav", "mixed", 3, "default", "steer_vel"), ("cbf-cav", "cav", 2, "srew", "steer"), ("cbf-avs_cint", "mixed", 3, "default", "steer_vel")]
+         ("cbf-cav", "mixed", 3, "default", "steer_vel"), ("cbf-cav", "cav", 2, "srew", "steer"), ("cbf-avs_cint", "mixed", 3, "default", "steer_vel"),
+         ("cbf-cav", "av", 3, "default", "steer"), ("cbf-avs_cint", "av", 2, "srew", "steer")]
 rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 first_round = int(sys.argv[2]) if len(sys.argv) > 2 else 0      # seeds depend on the round index
 E, T = 4096, 100
