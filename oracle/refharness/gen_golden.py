@@ -77,6 +77,13 @@ CASES = {
                      traffic_type="hdv", mixed_traffic=True), [11, 12, 13], 116),
     "mass_td3_av": (dict(safety_guarantee="cbf-cav", traffic_density=3, traffic_type="av", mixed_traffic=True),
                     [30, 31, 32, 33, 34], 115),
+    # exact ties: before every policy step all x positions and speeds are snapped to integers, so that vehicles of
+    # different lanes share x / s, |ds| keys of the closest-vehicle sorts are equal on both sides of an ego, and equal
+    # speeds keep the ties alive through the sub-steps.  Pins the reference's tie rules (stable sorts, "<=" scans).
+    # Every step is its own one-step "episode" (pre-state, post-state) because the snap breaks the chain.
+    "ties_mass_td3": (dict(safety_guarantee="cbf-cav", traffic_density=3, mixed_traffic=False), [40, 41], 116, "snap"),
+    "ties_hss_td3_mixed": (dict(safety_guarantee="cbf-avs_cint", traffic_density=3, traffic_type="mixed",
+                                mixed_traffic=True), [42, 43], 117, "snap"),
 }
 
 SH_I = ("ran", "leader", "front_adj", "rear_adj", "constrain_adj", "active", "is_lc_safe")
@@ -84,7 +91,8 @@ SH_F = ("safe_acc", "safe_steer", "nom_acc", "nom_steer")
 
 
 def run_case(name):
-    overrides, seeds, aseed = CASES[name]
+    overrides, seeds, aseed = CASES[name][:3]
+    snap = len(CASES[name]) > 3 and CASES[name][3] == "snap"
     hdv_env = overrides.get("env_name") == "merge-multi-agent-hdv-v1"
     env = rl.make_env(**overrides)
     rl.drain_shield_log()
@@ -101,6 +109,10 @@ def run_case(name):
         rl.drain_shield_log()
         done = False
         while not done:
+            if snap:
+                for veh in env.road.vehicles:
+                    veh.position[0] = float(np.round(veh.position[0]))
+                    veh.speed = float(np.round(veh.speed))
             st = rl.export_state(env)
             rows.append(len(states))
             states.append(st)
@@ -158,8 +170,12 @@ def run_case(name):
                 sh[k].append(rec_i[k])
             for k in SH_F:
                 sh[k].append(rec_f[k])
-        states.append(rl.export_state(env))
-        ep_start.append(len(states))
+            if snap:
+                states.append(rl.export_state(env))
+                ep_start.append(len(states))
+        if not snap:
+            states.append(rl.export_state(env))
+            ep_start.append(len(states))
     data = {}
     for k in rl.F64_FIELDS + rl.I32_FIELDS:
         data["st_" + k] = np.stack([s[k] for s in states])

@@ -27,3 +27,6 @@ GOLDEN_CASES = ["unsafe_td1", "unsafe_td3", "unsafe_td2_mixed", "hss_td3", "hss_
 V0_CASES = ["v0_unsafe_td1", "v0_unsafe_td2_mixed"]
 # env merge-multi-agent-hdv-v1 (MergeEnvLCHDV, traffic_type = hdv): every vehicle observed, nobody controlled
 HDV_CASES = ["hdv_td3"]
+# x positions and speeds snapped to integers before every policy step: exact ties in x, s and the |ds| sort keys
+# (the reference's stable-sort / "<=" tie rules); every step is its own (pre-state, post-state) pair
+TIE_CASES = ["ties_mass_td3", "ties_hss_td3_mixed"]

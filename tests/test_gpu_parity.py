@@ -5,7 +5,7 @@ and (b) the CPU oracle on seeded scenes.  Discrete outputs bit-exact; continuous
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_CASES, V0_CASES
+from conftest import GOLDEN_CASES, TIE_CASES, V0_CASES
 from helpers import (ENV_FIELDS, F64_FIELDS, I32_FIELDS, LC_BOUNDARY_EPS, OUT_F, OUT_I, SH_F, SH_I, compare_states,
                      load_golden, obs25, rel_err, used_mask)
 
@@ -70,9 +70,11 @@ def check_shield(diag, want, lc_margin, tol=None):
     return int(boundary.sum())
 
 
-@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("name", GOLDEN_CASES + TIE_CASES)
 def test_cuda_vs_golden_teacher_forced(mm, orc, name):
-    """Reference pre-state + reference actions -> CUDA step -> reference post-state, outputs, shield record."""
+    """Reference pre-state + reference actions -> CUDA step -> reference post-state, outputs, shield record.
+    The TIE_CASES hold exact ties in x / s / |ds| (positions and speeds snapped to integers): the x-ordered walks
+    must detect them and reproduce the reference's stable-sort and "<=" tie rules through their exhaustive scans."""
     g, cfg = load_golden(name)
     rows = g["row_of_step"]
     T = len(rows)

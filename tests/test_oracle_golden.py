@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle as orc
-from conftest import GOLDEN_CASES, V0_CASES
+from conftest import GOLDEN_CASES, TIE_CASES, V0_CASES
 from helpers import (ENV_FIELDS, F64_FIELDS, LC_BOUNDARY_EPS, OUT_F, OUT_I, SH_F, SH_I, compare_states,
                      load_golden, obs25, rel_err)
 
@@ -21,7 +21,7 @@ def golden_state(g, rows):
     return orc.state_from_golden(g, rows)
 
 
-@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("name", GOLDEN_CASES + TIE_CASES)
 def test_teacher_forced_step(name):
     g, cfg = load_golden(name)
     rows = g["row_of_step"]
@@ -123,6 +123,18 @@ def test_fixture_inventory():
             assert (g["st_" + k] >= 0).all()
     assert {0, 1, 8}.issubset(seen_active), seen_active
     assert crashed >= 3 and vetoes > 1000 and hdv >= 4
+    # the tie fixtures really hold ties: vehicles sharing x, and egos with two others at the same |dx|
+    for name in TIE_CASES:
+        g, _ = load_golden(name)
+        rows = g["row_of_step"]
+        same_x = same_key = 0
+        for r in rows:
+            xs = g["st_x"][r, :g["st_n_veh"][r]]
+            same_x += len(xs) - len(np.unique(xs))
+            for i in range(len(xs)):
+                d = np.delete(np.abs(xs - xs[i]), i)
+                same_key += len(d) - len(np.unique(d))
+        assert same_x >= 5 and same_key >= 100, (name, same_x, same_key)
 
 
 @pytest.mark.parametrize("name", V0_CASES)
