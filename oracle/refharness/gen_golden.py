@@ -113,6 +113,10 @@ def run_case(name):
                 for veh in env.road.vehicles:
                     veh.position[0] = float(np.round(veh.position[0]))
                     veh.speed = float(np.round(veh.speed))
+                    # the newest history record IS the current state (log_step after every move,
+                    # safe_controller.py:187-205, behavior.py:509-519): keep that invariant
+                    if getattr(veh, "state_hist", None):
+                        veh.state_hist[-1].update(veh.to_dict())
             st = rl.export_state(env)
             rows.append(len(states))
             states.append(st)

@@ -161,6 +161,63 @@ def test_four_ctas_per_sm_build_of_the_step_kernel(mm, orc, shield, traffic, td,
         mm.set_step_variant(0)
 
 
+@pytest.mark.parametrize("shield,traffic,td", [("cbf-cav", "cav", 3), ("cbf-avs_cint", "mixed", 3), ("cbf-cav", "mixed", 2),
+                                               ("none", "cav", 3)])
+def test_cuda_vs_oracle_scenes_with_exact_ties(mm, orc, shield, traffic, td):
+    """Tie handling at scale: before every policy step the x positions and speeds of 4096 scenes are snapped to
+    integers (as in the TIE_CASES fixtures, where the oracle's tie rules are pinned on the reference), so vehicles share
+    x / s and the closest-vehicle keys tie on both sides of an ego in most envs.  The x-ordered walks of the kernel must
+    fall back to their exhaustive scans exactly there; CUDA and oracle are stepped from the same snapped state."""
+    tie_rollout(mm, orc, shield, traffic, td)
+
+
+def test_exact_ties_with_the_four_cta_build(mm, orc):
+    try:
+        mm.set_step_variant(4)
+        tie_rollout(mm, orc, "cbf-cav", "mixed", 3)
+    finally:
+        mm.set_step_variant(0)
+
+
+def tie_rollout(mm, orc, shield, traffic, td):
+    import torch
+    E, T = 4096, 30
+    cfg = dict(mm.DEFAULT_CONFIG, safety_guarantee=shield, traffic_type=traffic, traffic_density=td, HEADWAY_TIME=0.5,
+               cbf_eta=0.03125)
+    env = mm.MergeEnvBatched(E, cfg, record_diag=True)
+    env.reset(seed=4321 + td)
+    st = env.get_state()
+    ocfg = orc.make_config(cfg)
+    rng = np.random.RandomState(11)
+    alive = np.ones(E, bool)
+    same_x = 0
+    for t in range(T):
+        um = used_mask(st)
+        st["x"] = np.where(um, np.round(st["x"]), st["x"])
+        st["speed"] = np.where(um, np.round(st["speed"]), st["speed"])
+        # the newest history record is the current state (log_step after every move): keep that invariant
+        h1 = um & (st["hist_len"] >= 1)
+        st["rec1_x"] = np.where(h1, st["x"], st["rec1_x"])
+        st["rec1_vx"] = np.where(h1, st["speed"] * np.cos(st["heading"]), st["rec1_vx"])
+        xs = np.where(um, st["x"], np.arange(12)[None, :] * 1e-3 - 1e6)      # unused slots: distinct dummies
+        same_x += int((np.diff(np.sort(xs, axis=1), axis=1) == 0).sum())
+        env.set_state(st)
+        a = rng.randint(0, 5, size=(E, 12)).astype(np.int8)
+        want = orc.step(ocfg, st, a, n_threads=8)
+        _, _, _, v = env.step(torch.from_numpy(a).cuda())
+        got = outputs_to_numpy(v, OUT_F + OUT_I)
+        post = env.get_state()
+        diag = env.shield_diag()
+        sel = np.where(alive)[0]
+        sub = lambda d: {k: d[k][sel] for k in d}
+        compare_states(sub(post), sub(st), STATE_TOL, "tie step %d" % t)
+        check_outputs(sub(got), sub({k: want[k] for k in OUT_F + OUT_I}), st["n_cav"][sel])
+        check_shield(sub(diag), sub({k: want[k] for k in want if k.startswith("sh_")}), diag["lc_margin"][sel])
+        alive &= want["done"] == 0
+    assert same_x > E      # on average more than one shared x per scene over the run
+    env.close()
+
+
 def lockstep_rollout(mm, orc, shield, traffic, td, reward, E, T, state_tol):
     import torch
     lateral = "steer_vel" if shield.endswith("+steer_vel") else "steer"
