@@ -70,7 +70,10 @@ typedef struct mm_env mm_env;
 
 /* Host mirror of the full per-env state, for teacher forcing and checkpointing.
  * Replaces: nothing in the reference (it never checkpoints env state); fields follow
- * Vehicle / ControlledVehicle / MDPLCVehicle / IDMVehicleHist attributes. */
+ * Vehicle / ControlledVehicle / MDPLCVehicle / IDMVehicleHist attributes.
+ * rec1_* / rec2_* are state_hist[-1] / state_hist[-2] (x and vx of the record).  The reference logs a record right
+ * after every move (safe_controller.py:187-205, behavior.py:509-519), so between policy steps rec1_x == x always:
+ * mm_set_state does not store rec1_x (it is not read back from the caller's buffer), mm_get_state returns x for it. */
 typedef struct {
     double *x, *y, *heading, *speed, *target_speed, *gvx, *rec1_x, *rec1_vx, *rec2_x, *rec2_vx,
            *act_steer, *act_acc, *safe_steer, *safe_acc, *timer, *min_headway,

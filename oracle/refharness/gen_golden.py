@@ -84,6 +84,10 @@ CASES = {
     "ties_mass_td3": (dict(safety_guarantee="cbf-cav", traffic_density=3, mixed_traffic=False), [40, 41], 116, "snap"),
     "ties_hss_td3_mixed": (dict(safety_guarantee="cbf-avs_cint", traffic_density=3, traffic_type="mixed",
                                 mixed_traffic=True), [42, 43], 117, "snap"),
+    # the same plus y snapped to a 0.5 m grid: vehicles exactly half-way between bc0 and bc1 during a lane change (the
+    # closest-lane argmin ties and list order decides), lateral offsets exactly on the on_lane / is_lc margins
+    "ties_y_mass_td3_mixed": (dict(safety_guarantee="cbf-cav", traffic_density=3, traffic_type="mixed",
+                                   mixed_traffic=True), [44, 45, 46], 118, "snapy"),
 }
 
 SH_I = ("ran", "leader", "front_adj", "rear_adj", "constrain_adj", "active", "is_lc_safe")
@@ -92,7 +96,8 @@ SH_F = ("safe_acc", "safe_steer", "nom_acc", "nom_steer")
 
 def run_case(name):
     overrides, seeds, aseed = CASES[name][:3]
-    snap = len(CASES[name]) > 3 and CASES[name][3] == "snap"
+    snap = len(CASES[name]) > 3 and CASES[name][3] in ("snap", "snapy")
+    snap_y = len(CASES[name]) > 3 and CASES[name][3] == "snapy"
     hdv_env = overrides.get("env_name") == "merge-multi-agent-hdv-v1"
     env = rl.make_env(**overrides)
     rl.drain_shield_log()
@@ -113,6 +118,8 @@ def run_case(name):
                 for veh in env.road.vehicles:
                     veh.position[0] = float(np.round(veh.position[0]))
                     veh.speed = float(np.round(veh.speed))
+                    if snap_y:
+                        veh.position[1] = float(np.round(veh.position[1] * 2) / 2)
                     # the newest history record IS the current state (log_step after every move,
                     # safe_controller.py:187-205, behavior.py:509-519): keep that invariant
                     if getattr(veh, "state_hist", None):

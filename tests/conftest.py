@@ -29,4 +29,5 @@ V0_CASES = ["v0_unsafe_td1", "v0_unsafe_td2_mixed"]
 HDV_CASES = ["hdv_td3"]
 # x positions and speeds snapped to integers before every policy step: exact ties in x, s and the |ds| sort keys
 # (the reference's stable-sort / "<=" tie rules); every step is its own (pre-state, post-state) pair
-TIE_CASES = ["ties_mass_td3", "ties_hss_td3_mixed"]
+# (ties_y_*: y snapped to a 0.5 m grid as well - vehicles exactly between two lanes, closest-lane argmin ties)
+TIE_CASES = ["ties_mass_td3", "ties_hss_td3_mixed", "ties_y_mass_td3_mixed"]

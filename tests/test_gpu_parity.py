@@ -161,25 +161,26 @@ def test_four_ctas_per_sm_build_of_the_step_kernel(mm, orc, shield, traffic, td,
         mm.set_step_variant(0)
 
 
-@pytest.mark.parametrize("shield,traffic,td", [("cbf-cav", "cav", 3), ("cbf-avs_cint", "mixed", 3), ("cbf-cav", "mixed", 2),
-                                               ("none", "cav", 3)])
-def test_cuda_vs_oracle_scenes_with_exact_ties(mm, orc, shield, traffic, td):
+@pytest.mark.parametrize("shield,traffic,td,snap_y", [("cbf-cav", "cav", 3, False), ("cbf-avs_cint", "mixed", 3, False),
+                                                      ("cbf-cav", "mixed", 2, True), ("none", "cav", 3, True)])
+def test_cuda_vs_oracle_scenes_with_exact_ties(mm, orc, shield, traffic, td, snap_y):
     """Tie handling at scale: before every policy step the x positions and speeds of 4096 scenes are snapped to
     integers (as in the TIE_CASES fixtures, where the oracle's tie rules are pinned on the reference), so vehicles share
     x / s and the closest-vehicle keys tie on both sides of an ego in most envs.  The x-ordered walks of the kernel must
-    fall back to their exhaustive scans exactly there; CUDA and oracle are stepped from the same snapped state."""
-    tie_rollout(mm, orc, shield, traffic, td)
+    fall back to their exhaustive scans exactly there; CUDA and oracle are stepped from the same snapped state.
+    snap_y: y on a 0.5 m grid as well (vehicles exactly between bc0 and bc1: the closest-lane argmin ties)."""
+    tie_rollout(mm, orc, shield, traffic, td, snap_y)
 
 
 def test_exact_ties_with_the_four_cta_build(mm, orc):
     try:
         mm.set_step_variant(4)
-        tie_rollout(mm, orc, "cbf-cav", "mixed", 3)
+        tie_rollout(mm, orc, "cbf-cav", "mixed", 3, True)
     finally:
         mm.set_step_variant(0)
 
 
-def tie_rollout(mm, orc, shield, traffic, td):
+def tie_rollout(mm, orc, shield, traffic, td, snap_y=False):
     import torch
     E, T = 4096, 30
     cfg = dict(mm.DEFAULT_CONFIG, safety_guarantee=shield, traffic_type=traffic, traffic_density=td, HEADWAY_TIME=0.5,
@@ -195,6 +196,8 @@ def tie_rollout(mm, orc, shield, traffic, td):
         um = used_mask(st)
         st["x"] = np.where(um, np.round(st["x"]), st["x"])
         st["speed"] = np.where(um, np.round(st["speed"]), st["speed"])
+        if snap_y:
+            st["y"] = np.where(um, np.round(st["y"] * 2) / 2, st["y"])
         # the newest history record is the current state (log_step after every move): keep that invariant
         h1 = um & (st["hist_len"] >= 1)
         st["rec1_x"] = np.where(h1, st["x"], st["rec1_x"])
