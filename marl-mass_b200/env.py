@@ -518,6 +518,12 @@ class MergeEnvLCMARL(object):
         return bool(st["crashed"][0, :len(self.controlled_vehicles)].any())
 
     def render(self, mode="human"):
+        """abstract.py:512-556.  'rgb_array': the frame MAPPO.evaluation records (mappo.py:292-322), rasterised on the
+        CPU from the device state (render.py); 'human' would open a pygame window in the reference - there is no
+        display surface here, nothing is shown and None is returned."""
+        if mode == "rgb_array":
+            from .render import render_scene
+            return render_scene(self._state(), 0, self.config)
         return None
 
     def close(self):

@@ -249,3 +249,31 @@ def test_training_driver_reads_the_reference_ini_layout():
     if os.path.exists(ref):
         env_ref, kw_ref, tr_ref = train.load_ini(ref)
         assert env_ref == env_cfg and kw_ref == kw and tr_ref["test_seeds"] == tr["test_seeds"]
+
+
+def test_render_scene_from_state():
+    """CPU renderer that replaces the pygame viewer (abstract.py:512-556): frame shape of the reference's surface,
+    vehicles drawn where the state puts them, in the reference's colours."""
+    import marl_mass_b200 as mm
+    from marl_mass_b200 import render
+    st = mm.spawn.spawn_state([3], 3, "mixed")
+    n = int(st["n_veh"][0])
+    st["x"][0, :n] = np.linspace(260, 440, n)          # inside the window [250, 450] x [-16, 24]
+    st["y"][0, :n] = np.where(st["kind"][0, :n] == 1, 0.0, 4.0)
+    st["heading"][0, :n] = 0.0
+    st["crashed"][0, 0] = 1
+    img = render.render_scene(st, 0, dict(mm.DEFAULT_CONFIG))
+    assert img.shape == (120, 600, 3) and img.dtype == np.uint8
+    px = lambda x, y: img[int((y + 16) * 3), int((x - 250) * 3)]
+    assert tuple(px(st["x"][0, 0], st["y"][0, 0])) == render.RED
+    for i in range(1, n):
+        want = render.GREEN if st["kind"][0, i] == 1 else render.BLUE
+        assert tuple(px(st["x"][0, i], st["y"][0, i])) == want, i
+    assert tuple(px(300.0, 14.0)) == render.GREY and tuple(px(420.0, 4.0)) == render.OBSTACLE
+    assert (img == 255).all(axis=2).sum() > 600      # lane borders
+    # a vehicle turned by 90 degrees covers 5 m in y
+    st["heading"][0, 1] = np.pi / 2
+    img2 = render.render_scene(st, 0, dict(mm.DEFAULT_CONFIG))
+    x1, y1 = st["x"][0, 1], st["y"][0, 1]
+    assert tuple(img2[int((y1 + 2.2 + 16) * 3), int((x1 - 250) * 3)]) != render.GREY
+    assert tuple(img2[int((y1 + 16) * 3), int((x1 + 2.2 - 250) * 3)]) in (render.GREY, render.WHITE)
