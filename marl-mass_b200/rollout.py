@@ -51,6 +51,79 @@ class CriticNetwork(nn.Module):
         return self.fc3(out)
 
 
+class ActorCriticNetwork(nn.Module):
+    """marl/single_agent/Model_gi.py:137-220: the shared-trunk network of `MAPPO_GI` (mappo_gi.py:142-148 builds it
+    with `state_split=True` and hidden size = critic_hidden_size).  The split reads the observation as five vehicles
+    of FIVE features - presence | x, y | vx, vy - through fixed column lists that stop at column 24, also when the env
+    delivers 5 x 6 = 30 columns (merge-multi-agent-v1): kept as the reference has it.  out_type "p": log-softmax over
+    the actions, with `action_mask` the masked logits are -1e8 (Model_gi.py:207-213); "v": the state value."""
+    COLS1 = (0, 5, 10, 15, 20)
+    COLS2 = (1, 2, 6, 7, 11, 12, 16, 17, 21, 22)
+    COLS3 = (3, 4, 8, 9, 13, 14, 18, 19, 23, 24)
+
+    def __init__(self, state_dim=NS, action_dim=NA, hidden_size=128, critic_output_size=1, state_split=True):
+        super().__init__()
+        self.state_split = bool(state_split)
+        if self.state_split:
+            self.fc11 = nn.Linear(5, hidden_size // 4)
+            self.fc12 = nn.Linear(10, hidden_size // 2)
+            self.fc13 = nn.Linear(10, hidden_size // 2)
+            self.fc2 = nn.Linear(hidden_size // 4 + hidden_size // 2 + hidden_size // 2, hidden_size)
+        else:
+            self.fc1 = nn.Linear(state_dim, hidden_size)
+            self.fc2 = nn.Linear(hidden_size, hidden_size)
+        self.actor_linear = nn.Linear(hidden_size, action_dim)
+        self.critic_linear = nn.Linear(hidden_size, critic_output_size)
+
+    def trunk(self, state):
+        if self.state_split:
+            out = torch.cat([torch.relu(self.fc11(state[:, self.COLS1])), torch.relu(self.fc12(state[:, self.COLS2])),
+                             torch.relu(self.fc13(state[:, self.COLS3]))], 1)
+        else:
+            out = torch.relu(self.fc1(state))
+        return torch.relu(self.fc2(out))
+
+    def policy_head(self, hidden, action_mask=None):
+        logits = self.actor_linear(hidden)
+        if action_mask is not None:
+            logits = torch.where(action_mask == 0, torch.full_like(logits, -1e8), logits)
+            return torch.log_softmax(logits + 1e-8, dim=1)
+        return torch.log_softmax(logits, dim=1)
+
+    def forward(self, state, action_mask=None, out_type="p"):
+        hidden = self.trunk(state)
+        return self.policy_head(hidden, action_mask) if out_type == "p" else self.critic_linear(hidden)
+
+
+def shared_network_loss(policy, policy_target, states, actions_one_hot, returns, clip_param=0.2, critic_loss="mse",
+                        pairwise=False):
+    """The loss of one `MAPPO_GI.train` update with the shared network (mappo_gi.py:307-343): PPO-clip surrogate with
+    the advantage `return - V(s)` (value detached) plus the value regression, summed.  -> (loss, actor_loss, critic_loss)
+
+    `pairwise`: the reference multiplies `ratio` [N] by `advantages` [N, 1] (mappo_gi.py:313-326, mappo.py:173-183), which
+    broadcasts to an [N, N] table of every ratio against every advantage before min / mean.  With its batches of 100
+    samples that is what it trains on; with the 1e5..1e6-sample minibatches of the batched learner the table cannot
+    exist, so the default is the per-sample PPO surrogate (ratio_i * adv_i) the formula stands for.  pairwise=True
+    reproduces the reference's table (small batches; used to pin this function against the reference's arithmetic)."""
+    hidden = policy.trunk(states)
+    logp = (policy.policy_head(hidden) * actions_one_hot).sum(1)
+    values = policy.critic_linear(hidden)
+    adv = returns - values.detach()
+    with torch.no_grad():
+        old_logp = (policy_target(states) * actions_one_hot).sum(1)
+    ratio = torch.exp(logp - old_logp)
+    if not pairwise:
+        adv = adv.squeeze(1)
+    surr1 = ratio * adv
+    surr2 = torch.clamp(ratio, 1.0 - clip_param, 1.0 + clip_param) * adv
+    actor_loss = -torch.min(surr1, surr2).mean()
+    if critic_loss == "huber":
+        c_loss = nn.functional.smooth_l1_loss(values, returns)
+    else:
+        c_loss = nn.functional.mse_loss(values, returns)
+    return actor_loss + c_loss, actor_loss, c_loss
+
+
 def _ptr(t):
     return C.c_void_p(0 if t is None else t.data_ptr())
 
@@ -144,7 +217,7 @@ class BatchedMAPPORollout(object):
     def act_torch(self, obs, n_agents):
         """Plain torch fp32 actor + torch.multinomial: the numerics reference of `act_fused`."""
         logp = self.actor(obs.view(-1, NS))                               # [E*12, 5]
-        a = torch.multinomial(logp.exp(), 1).view(self.E, MAXV)           # exploration_action, mappo.py:225-230
+        a = torch.multinomial(logp.exp(), 1).view(obs.shape[0], MAXV)           # exploration_action, mappo.py:225-230
         live = self._slot < n_agents[:, None]
         return torch.where(live, a, torch.ones_like(a)).to(torch.int8), live
 
@@ -177,12 +250,23 @@ class BatchedMAPPORollout(object):
         if self.reward_scale > 0:
             R /= self.reward_scale
         # bootstrap where the last step did not end the episode (mappo.py:148-150)
-        a_fin, _ = self._act(self.obs, v["n_agents"])
-        onehot = torch.nn.functional.one_hot(a_fin.long(), NA).float()
-        final_value = self.critic(self.obs.view(-1, NS), onehot.view(-1, NA)).view(E, MAXV)
+        final_value = self._final_value(self.obs, v["n_agents"])
         returns = discounted_returns(R, D, final_value, self.gamma)
         self.buf = dict(states=S, actions=A, returns=returns, live=L, dones=D, rewards=R)
         return self.buf
+
+    def _final_value(self, obs, n_agents):
+        a_fin, _ = self._act(obs, n_agents)
+        onehot = torch.nn.functional.one_hot(a_fin.long(), NA).float()
+        return self.critic(obs.view(-1, NS), onehot.view(-1, NA)).view(self.E, MAXV)
+
+    def networks(self):
+        """every module a replica must hold identically (sync_parameters, the replica check of train.py)"""
+        return [self.actor, self.critic, self.actor_target, self.critic_target]
+
+    def sample_actions(self, obs, n_agents, seed, step):
+        """MAPPO.action (mappo.py:231-236): a draw from the softmax, also at evaluation time."""
+        return actor_sample(self.actor, obs.contiguous(), n_agents, seed=seed, step=step)
 
     # ---- data parallelism over env shards (SURVEY.md 8e): one process per GPU, each with its own envs; the only
     # traffic is the gradient all-reduce of the two small networks (~42 k parameters each) per minibatch
@@ -194,7 +278,7 @@ class BatchedMAPPORollout(object):
         """Broadcast rank `src`'s networks (call once after construction under torchrun)."""
         import torch.distributed as dist
         if self._world() > 1:
-            for m in (self.actor, self.critic, self.actor_target, self.critic_target):
+            for m in self.networks():
                 for t in list(m.parameters()) + list(m.buffers()):
                     dist.broadcast(t.data, src)
 
@@ -254,4 +338,70 @@ class BatchedMAPPORollout(object):
                          "samples": int(idx.numel())}
         self.actor_target.load_state_dict(self.actor.state_dict())     # TARGET_TAU = 1.0 in every shipped ini
         self.critic_target.load_state_dict(self.critic.state_dict())
+        return stats
+
+
+class BatchedMAPPOGIRollout(BatchedMAPPORollout):
+    """`MAPPO_GI` with `shared_network = True` (marl/mappo_gi.py; the 6 `*-shared*.ini` configs, run_mappo.py:232-277):
+    ONE ActorCriticNetwork (Model_gi.py:137-220, state_split) gives the action distribution and the state value, one
+    RMSprop optimiser at `actor_lr` (mappo_gi.py:150-156) steps the summed loss (`shared_network_loss`), the bootstrap
+    value is V(final state) (mappo_gi.py:396-404).  Rollout, reward selection, scaling and returns are the base class's.
+    As in the reference the policy is evaluated WITHOUT an action mask everywhere (`self.policy(state)`,
+    mappo_gi.py:309,359): `action_masking` only changes what env.reset / step report.  The action draw runs as torch
+    layers (the fused actor kernel is the 30-128-128-5 network of `MAPPO`)."""
+
+    def __init__(self, env, policy=None, hidden_size=128, **kw):
+        kw["fused"] = False
+        dev = torch.device("cuda", env.device)
+        super().__init__(env, **kw)
+        self.policy = (policy or ActorCriticNetwork(NS, NA, hidden_size, 1, state_split=True)).to(dev)
+        self.policy_target = ActorCriticNetwork(NS, NA, hidden_size, 1, state_split=self.policy.state_split).to(dev)
+        self.policy_target.load_state_dict(self.policy.state_dict())
+        self.policy_opt = torch.optim.RMSprop(self.policy.parameters(), lr=self.actor_opt.param_groups[0]["lr"])
+        self.actor = self.critic = self.actor_target = self.critic_target = None     # not part of this learner
+        self.actor_opt = self.critic_opt = None
+
+    @torch.no_grad()
+    def act_torch(self, obs, n_agents):
+        logp = self.policy(obs.view(-1, NS))
+        a = torch.multinomial(logp.exp(), 1).view(obs.shape[0], MAXV)           # exploration_action, mappo_gi.py:368-373
+        live = self._slot < n_agents[:, None]
+        return torch.where(live, a, torch.ones_like(a)).to(torch.int8), live
+
+    def _final_value(self, obs, n_agents):
+        return self.policy(obs.view(-1, NS), out_type="v").view(self.E, MAXV)
+
+    def networks(self):
+        return [self.policy, self.policy_target]
+
+    def sample_actions(self, obs, n_agents, seed, step):
+        return self.act_torch(obs, n_agents)[0]
+
+    def update(self, minibatch=1 << 18, epochs=1):
+        """One pass of `MAPPO_GI.train` (shared branch, mappo_gi.py:307-349) over the last rollout, all agents at once;
+        under torch.distributed the gradients are averaged over the ranks."""
+        b = self.buf
+        idx = b["live"].reshape(-1).nonzero(as_tuple=False).squeeze(1)
+        S = b["states"].reshape(-1, NS)
+        A = torch.nn.functional.one_hot(b["actions"].reshape(-1), NA).float()
+        G = b["returns"].reshape(-1, 1)
+        stats = {}
+        n_max = torch.tensor([idx.numel()], device=self.dev)
+        if self._world() > 1:
+            import torch.distributed as dist
+            dist.all_reduce(n_max, op=dist.ReduceOp.MAX)
+        n_mb = max(1, -(-int(n_max) // int(minibatch)))       # same count on every rank
+        params = list(self.policy.parameters())
+        for _ in range(epochs):
+            perm = idx[torch.randperm(idx.numel(), device=self.dev)]
+            for j in torch.tensor_split(perm, n_mb):
+                loss, a_loss, c_loss = shared_network_loss(self.policy, self.policy_target, S[j], A[j], G[j], self.clip_param)
+                self.policy_opt.zero_grad(set_to_none=True)
+                loss.backward()
+                self._allreduce_grads(params)
+                nn.utils.clip_grad_norm_(params, self.max_grad_norm)
+                self.policy_opt.step()
+                stats = {"actor_loss": float(a_loss.detach()), "critic_loss": float(c_loss.detach()),
+                         "samples": int(idx.numel())}
+        self.policy_target.load_state_dict(self.policy.state_dict())   # TARGET_TAU = 1.0 in every shipped ini
         return stats

@@ -43,7 +43,10 @@ def load_ini(path):
         "critic_lr": c.getfloat(T, "critic_lr"),
     }
     train = {"test_seeds": c.get(T, "test_seeds", fallback=",".join(str(i) for i in range(0, 600, 20))),
-             "eval_episodes": c.getint(T, "EVAL_EPISODES", fallback=20), "torch_seed": c.getint(M, "torch_seed", fallback=0)}
+             "eval_episodes": c.getint(T, "EVAL_EPISODES", fallback=20), "torch_seed": c.getint(M, "torch_seed", fallback=0),
+             # run_mappo.py:126,232: shared_network selects MAPPO_GI with its one ActorCriticNetwork
+             "shared_network": c.getboolean(M, "shared_network", fallback=False),
+             "critic_hidden_size": c.getint(M, "critic_hidden_size", fallback=128)}
     return env_cfg, rollout_kw, train
 
 
@@ -51,7 +54,7 @@ def train(config, n_envs=4096, iterations=30, device=0, eval_interval=10, miniba
     import torch
     from . import evaluation as ev
     from .env import DEFAULT_CONFIG, MergeEnvBatched
-    from .rollout import BatchedMAPPORollout, actor_sample
+    from .rollout import BatchedMAPPOGIRollout, BatchedMAPPORollout
     import torch.distributed as dist
     from . import dist as mmd
     env_cfg, rollout_kw, tr = load_ini(config) if isinstance(config, str) else config
@@ -64,7 +67,11 @@ def train(config, n_envs=4096, iterations=30, device=0, eval_interval=10, miniba
     torch.manual_seed(tr["torch_seed"])
     env = MergeEnvBatched(n_envs, dict(DEFAULT_CONFIG, **env_cfg), device=device)
     env.reset(seed=mmd.rank_seed(env_cfg["seed"], rank) if world > 1 else env_cfg["seed"])
-    pol = BatchedMAPPORollout(env, seed=tr["torch_seed"] + 104729 * rank, **rollout_kw)
+    if tr.get("shared_network"):
+        pol = BatchedMAPPOGIRollout(env, hidden_size=tr.get("critic_hidden_size", 128),
+                                    seed=tr["torch_seed"] + 104729 * rank, **rollout_kw)
+    else:
+        pol = BatchedMAPPORollout(env, seed=tr["torch_seed"] + 104729 * rank, **rollout_kw)
     pol.sync_parameters()
     if rank != 0:
         log = lambda *_: None
@@ -72,7 +79,7 @@ def train(config, n_envs=4096, iterations=30, device=0, eval_interval=10, miniba
 
     def act(obs, n_agents):      # MAPPO.action (mappo.py:231-236): a draw from the softmax, also at evaluation time
         draws["n"] += 1
-        return actor_sample(pol.actor, obs.contiguous(), n_agents, seed=tr["torch_seed"] + 7919, step=draws["n"])
+        return pol.sample_actions(obs, n_agents, seed=tr["torch_seed"] + 7919, step=draws["n"])
 
     history = []
     for it in range(iterations):
@@ -95,7 +102,7 @@ def train(config, n_envs=4096, iterations=30, device=0, eval_interval=10, miniba
                         "eval_avg_speed": float(np.mean(info["avg_speeds"])), "eval_crashes": int(np.sum(info["crash_count"])),
                         "eval_min_headway": info["min_headway"], "eval_merge_percent": float(np.mean(info["merge_percents"]))})
         if world > 1 and it == iterations - 1:      # the replicas must still hold identical networks
-            flat = torch.cat([q.detach().reshape(-1) for q in list(pol.actor.parameters()) + list(pol.critic.parameters())])
+            flat = torch.cat([q.detach().reshape(-1) for m in pol.networks() for q in m.parameters()])
             hi, lo = flat.clone(), flat.clone()
             dist.all_reduce(hi, op=dist.ReduceOp.MAX)
             dist.all_reduce(lo, op=dist.ReduceOp.MIN)

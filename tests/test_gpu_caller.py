@@ -287,3 +287,37 @@ def test_batched_evaluation_of_the_idm_baseline(mm):
         assert abs(info["avg_speeds"][i] - sp / t) < 1e-5 and info["merge_percents"][i] == inf["merge_percent"] == 100.0
         assert info["crash_count"][i] == env.is_crashed() and vs[i].shape == (t, n)
     env.close()
+
+
+def test_shared_network_rollout_and_training_driver(mm):
+    """MAPPO_GI with shared_network = True (the `*-shared*.ini` configs): one ActorCriticNetwork draws the actions and
+    bootstraps the returns; one update changes it and re-syncs the target; the ini driver selects it."""
+    import torch
+    from marl_mass_b200.rollout import BatchedMAPPOGIRollout
+    from marl_mass_b200.train import load_ini, train
+    torch.manual_seed(0)
+    E, T = 1024, 20
+    cfg = dict(mm.DEFAULT_CONFIG, safety_guarantee="cbf-cav", traffic_density=3, traffic_type="mixed", HEADWAY_TIME=0.5,
+               cbf_eta=0.03125, agent_reward="srew", HIGH_SPEED_REWARD=4, HEADWAY_COST=1, MERGING_LANE_COST=8)
+    env = mm.MergeEnvBatched(E, cfg)
+    ro = BatchedMAPPOGIRollout(env, roll_out_n_steps=T)
+    env.reset(seed=5)
+    env.stats(reset=True)
+    ro.obs = env.buffers()["obs"]
+    b = ro.collect()
+    assert b["states"].shape == (T, E, 12, 30) and torch.isfinite(b["returns"]).all()
+    assert int(b["live"].sum()) == int(env.stats()["agent_steps"])
+    # a rollout that did not end is bootstrapped with V(final state): gamma^k * V enters the last returns
+    open_env = (b["dones"][-1] == 0).nonzero(as_tuple=True)[0][0]
+    v_fin = ro.policy(ro.obs.view(-1, 30), out_type="v").view(E, 12)[open_env, 0]
+    assert torch.allclose(b["returns"][-1, open_env, 0], b["rewards"][-1, open_env, 0] + 0.99 * v_fin, atol=1e-5)
+    before = [p.detach().clone() for p in ro.policy.parameters()]
+    st = ro.update(minibatch=1 << 15)
+    assert st["samples"] == int(b["live"].sum()) and np.isfinite(st["actor_loss"]) and np.isfinite(st["critic_loss"])
+    assert all(not torch.equal(a, p) for a, p in zip(before, ro.policy.parameters()))
+    assert all(torch.equal(p, q) for p, q in zip(ro.policy.parameters(), ro.policy_target.parameters()))
+    env.close()
+    ini = os.path.join(ROOT, "examples", "mass_td3_mixed_srew_shared.ini")
+    assert load_ini(ini)[2]["shared_network"] is True
+    hist = train(ini, n_envs=512, iterations=2, eval_interval=1, log=lambda *_: None)
+    assert len(hist) == 2 and np.isfinite(hist[-1]["eval_reward"]) and hist[-1]["agent_steps"] > 0

@@ -277,3 +277,61 @@ def test_render_scene_from_state():
     x1, y1 = st["x"][0, 1], st["y"][0, 1]
     assert tuple(img2[int((y1 + 2.2 + 16) * 3), int((x1 - 250) * 3)]) != render.GREY
     assert tuple(img2[int((y1 + 16) * 3), int((x1 + 2.2 - 250) * 3)]) in (render.GREY, render.WHITE)
+
+
+def _gi_net(g, prefix):
+    import torch
+    from marl_mass_b200.rollout import ActorCriticNetwork
+    net = ActorCriticNetwork(30, 5, 128, 1, state_split=True)
+    sd = {k: torch.from_numpy(g[prefix + k.replace(".", "_")]) for k in net.state_dict()}
+    net.load_state_dict(sd)
+    return net
+
+
+def test_shared_actor_critic_network_matches_the_reference_vectors():
+    """rollout.ActorCriticNetwork against outputs frozen from the reference's Model_gi.ActorCriticNetwork
+    (oracle/refharness/gen_golden_mappo_gi.py): log-probabilities without / with action mask, state values."""
+    import torch
+    g = np.load(os.path.join(ROOT, "tests", "golden", "mappo_gi_caller.npz"))
+    net = _gi_net(g, "w_")
+    obs = torch.from_numpy(g["obs"])
+    with torch.no_grad():
+        assert np.abs(net(obs).numpy() - g["logp"]).max() < 1e-5
+        masked = net(obs, action_mask=torch.from_numpy(g["mask"])).numpy()
+        assert np.abs(net(obs, out_type="v").numpy() - g["value"]).max() < 1e-5
+    keep = g["mask"] == 1
+    assert np.abs(masked[keep] - g["logp_masked"][keep]).max() < 1e-5
+    assert (masked[~keep] < -1e7).all() and (g["logp_masked"][~keep] < -1e7).all()
+
+
+def test_shared_network_update_matches_one_reference_train_step():
+    """shared_network_loss(pairwise=True) + RMSprop + grad clip = one MAPPO_GI.train update of the reference's own code
+    (parameters after the step frozen in the fixture); the per-sample surrogate the batched learner uses differs from
+    the reference's [N, N] table only through which (ratio, advantage) pairs enter the min / mean."""
+    import torch
+    from marl_mass_b200.rollout import shared_network_loss
+    g = np.load(os.path.join(ROOT, "tests", "golden", "mappo_gi_caller.npz"))
+    net, target = _gi_net(g, "w_"), _gi_net(g, "t_")
+    opt = torch.optim.RMSprop(net.parameters(), lr=float(g["lr"]))
+    s, a, r = (torch.from_numpy(g[k]) for k in ("train_states", "train_actions", "train_returns"))
+    loss, a_loss, c_loss = shared_network_loss(net, target, s, a, r, float(g["clip_param"]), pairwise=True)
+    opt.zero_grad()
+    loss.backward()
+    torch.nn.utils.clip_grad_norm_(net.parameters(), float(g["max_grad_norm"]))
+    opt.step()
+    moved = 0.0
+    for k, v in net.state_dict().items():
+        want = g["after_" + k.replace(".", "_")]
+        assert np.abs(v.numpy() - want).max() < 2e-6, k
+        moved = max(moved, float(np.abs(want - g["w_" + k.replace(".", "_")]).max()))
+    assert moved > 1e-3
+    # per-sample form: same critic term, a surrogate over the N diagonal pairs instead of all N x N
+    net2 = _gi_net(g, "w_")
+    l2, a2, c2 = shared_network_loss(net2, target, s, a, r, float(g["clip_param"]))
+    assert abs(float(c2.detach()) - float(c_loss.detach())) < 1e-6 and np.isfinite(float(a2.detach()))
+    with torch.no_grad():
+        h = net2.trunk(s)
+        ratio = torch.exp((net2.policy_head(h) * a).sum(1) - (target(s) * a).sum(1))
+        adv = (r - net2.critic_linear(h)).squeeze(1)
+        want = -torch.min(ratio * adv, torch.clamp(ratio, 0.8, 1.2) * adv).mean()
+    assert abs(float(a2.detach()) - float(want)) < 1e-6
