@@ -95,6 +95,28 @@ class ActorCriticNetwork(nn.Module):
         return self.policy_head(hidden, action_mask) if out_type == "p" else self.critic_linear(hidden)
 
 
+def mappo_losses(actor, actor_target, critic, critic_target, states, actions_one_hot, returns, clip_param=0.2,
+                 critic_loss="mse", pairwise=False):
+    """The two losses of one `MAPPO.train` update (mappo.py:170-199): the PPO-clip surrogate with the advantage
+    `return - Q_target(s, a)` for the actor, the regression of Q(s, a) on the return for the critic.  They share no
+    parameters, so stepping the actor first (as the reference does) or both at once is the same update.
+    `pairwise`: see `shared_network_loss`.  -> (actor_loss, critic_loss)"""
+    with torch.no_grad():
+        adv = returns - critic_target(states, actions_one_hot)
+        old_logp = (actor_target(states) * actions_one_hot).sum(1)
+    logp = (actor(states) * actions_one_hot).sum(1)
+    ratio = torch.exp(logp - old_logp)
+    if not pairwise:
+        adv = adv.squeeze(1)
+    actor_loss = -torch.min(ratio * adv, torch.clamp(ratio, 1.0 - clip_param, 1.0 + clip_param) * adv).mean()
+    values = critic(states, actions_one_hot)
+    if critic_loss == "huber":
+        c_loss = nn.functional.smooth_l1_loss(values, returns)
+    else:
+        c_loss = nn.functional.mse_loss(values, returns)
+    return actor_loss, c_loss
+
+
 def shared_network_loss(policy, policy_target, states, actions_one_hot, returns, clip_param=0.2, critic_loss="mse",
                         pairwise=False):
     """The loss of one `MAPPO_GI.train` update with the shared network (mappo_gi.py:307-343): PPO-clip surrogate with
@@ -297,7 +319,8 @@ class BatchedMAPPORollout(object):
             o += q.numel()
 
     def update(self, minibatch=1 << 18, epochs=1):
-        """PPO-clip actor update and critic regression on the last rollout (mappo.py:161-206), all agents at once.
+        """PPO-clip actor update and critic regression on the last rollout (mappo.py:161-206, `mappo_losses`), all
+        agents at once, with the per-sample surrogate (the reference's [N] x [N, 1] product is an N x N table).
         Under torch.distributed every rank runs the same number of minibatches and the gradients are averaged."""
         b = self.buf
         live = b["live"].reshape(-1)
@@ -314,21 +337,13 @@ class BatchedMAPPORollout(object):
         for _ in range(epochs):
             perm = idx[torch.randperm(idx.numel(), device=self.dev)]
             for j in torch.tensor_split(perm, n_mb):
-                s, a, g = S[j], A[j], G[j]
-                with torch.no_grad():
-                    adv = g - self.critic_target(s, a)
-                    old_logp = (self.actor_target(s) * a).sum(1)
-                logp = (self.actor(s) * a).sum(1)
-                ratio = torch.exp(logp - old_logp)
-                surr = torch.min(ratio * adv.squeeze(1),
-                                 torch.clamp(ratio, 1 - self.clip_param, 1 + self.clip_param) * adv.squeeze(1))
-                actor_loss = -surr.mean()
+                actor_loss, critic_loss = mappo_losses(self.actor, self.actor_target, self.critic, self.critic_target,
+                                                       S[j], A[j], G[j], self.clip_param)
                 self.actor_opt.zero_grad(set_to_none=True)
                 actor_loss.backward()
                 self._allreduce_grads(list(self.actor.parameters()))
                 nn.utils.clip_grad_norm_(self.actor.parameters(), self.max_grad_norm)
                 self.actor_opt.step()
-                critic_loss = nn.functional.mse_loss(self.critic(s, a), g)
                 self.critic_opt.zero_grad(set_to_none=True)
                 critic_loss.backward()
                 self._allreduce_grads(list(self.critic.parameters()))

@@ -335,3 +335,33 @@ def test_shared_network_update_matches_one_reference_train_step():
         adv = (r - net2.critic_linear(h)).squeeze(1)
         want = -torch.min(ratio * adv, torch.clamp(ratio, 0.8, 1.2) * adv).mean()
     assert abs(float(a2.detach()) - float(want)) < 1e-6
+
+
+def test_mappo_update_matches_one_reference_train_step():
+    """mappo_losses(pairwise=True) + RMSprop + grad clip on both networks = one MAPPO.train update of the reference's
+    own code (oracle/refharness/gen_golden_mappo_train.py: parameters after the step frozen in the fixture)."""
+    import torch
+    from marl_mass_b200.rollout import ActorNetwork, CriticNetwork, mappo_losses
+    g = np.load(os.path.join(ROOT, "tests", "golden", "mappo_train_step.npz"))
+
+    def net(cls, prefix):
+        n = cls()
+        n.load_state_dict({k: torch.from_numpy(g[prefix + "_" + k.replace(".", "_")]) for k in n.state_dict()})
+        return n
+    actor, critic = net(ActorNetwork, "actor"), net(CriticNetwork, "critic")
+    actor_t, critic_t = net(ActorNetwork, "actor_t"), net(CriticNetwork, "critic_t")
+    s, a, r = (torch.from_numpy(g[k]) for k in ("train_states", "train_actions", "train_returns"))
+    a_loss, c_loss = mappo_losses(actor, actor_t, critic, critic_t, s, a, r, float(g["clip_param"]), pairwise=True)
+    for n, loss in ((actor, a_loss), (critic, c_loss)):
+        opt = torch.optim.RMSprop(n.parameters(), lr=float(g["lr"]))
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(n.parameters(), float(g["max_grad_norm"]))
+        opt.step()
+    for name, n in (("actor", actor), ("critic", critic)):
+        moved = 0.0
+        for k, v in n.state_dict().items():
+            want = g["%s_after_%s" % (name, k.replace(".", "_"))]
+            assert np.abs(v.numpy() - want).max() < 2e-6, (name, k)
+            moved = max(moved, float(np.abs(want - g["%s_%s" % (name, k.replace(".", "_"))]).max()))
+        assert moved > 1e-3, name
