@@ -147,13 +147,35 @@ b, e = mmd.shard_range(65536 * 2, rank, 2)
 assert e - b == 65536 and b == rank * 65536
 s = mmd.summarize(tot)
 assert s["crash_rate"] == 1.0 and s["shield_active_frac"] == 1.0
+# the learner's data parallelism (rollout.py): parameters broadcast from rank 0, gradients averaged over the ranks
+import torch
+from marl_mass_b200.rollout import ActorCriticNetwork, BatchedMAPPOGIRollout
+torch.manual_seed(100 + rank)
+ro = BatchedMAPPOGIRollout.__new__(BatchedMAPPOGIRollout)
+ro.policy, ro.policy_target = ActorCriticNetwork(), ActorCriticNetwork()
+ro.sync_parameters()
+flat = torch.cat([q.detach().reshape(-1) for m in ro.networks() for q in m.parameters()])
+both = [torch.zeros_like(flat) for _ in range(2)]
+dist.all_gather(both, flat)
+assert torch.equal(both[0], both[1])
+x = torch.randn(16, 30)
+ro.policy(x).sum().backward()
+params = [q for q in ro.policy.parameters() if q.grad is not None]
+mine = torch.cat([q.grad.reshape(-1) for q in params]).clone()
+grads = [torch.zeros_like(mine) for _ in range(2)]
+dist.all_gather(grads, mine)
+assert not torch.equal(grads[0], grads[1])
+ro._allreduce_grads(params)
+after = torch.cat([q.grad.reshape(-1) for q in params])
+assert torch.allclose(after, (grads[0] + grads[1]) / 2, atol=1e-7)
 dist.destroy_process_group()
 print("ok", rank)
 """
 
 
 def test_stats_all_reduce_world_size_2_gloo(tmp_path):
-    """The only collective on the path: SUM of the counters, MIN of min_headway."""
+    """The only collective on the path: SUM of the counters, MIN of min_headway; and the learner's
+    parameter broadcast + gradient averaging over the ranks."""
     script = tmp_path / "worker.py"
     script.write_text(_WORKER)
     port = str(29500 + os.getpid() % 2000)
