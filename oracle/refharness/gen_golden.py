@@ -86,6 +86,9 @@ CASES = {
                                 mixed_traffic=True), [42, 43], 117, "snap"),
     # the same plus y snapped to a 0.5 m grid: vehicles exactly half-way between bc0 and bc1 during a lane change (the
     # closest-lane argmin ties and list order decides), lateral offsets exactly on the on_lane / is_lc margins
+    # the v0 env (MDPVehicle / IDMVehicle, no history, no shield) with the same snapping
+    "ties_v0_unsafe_td2_mixed": (dict(env_name="merge-multi-agent-v0", safety_guarantee="none", traffic_density=2,
+                                      HEADWAY_TIME=1.2), [47, 48], 119, "snapy"),
     "ties_y_mass_td3_mixed": (dict(safety_guarantee="cbf-cav", traffic_density=3, traffic_type="mixed",
                                    mixed_traffic=True), [44, 45, 46], 118, "snapy"),
 }

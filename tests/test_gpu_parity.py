@@ -5,7 +5,7 @@ and (b) the CPU oracle on seeded scenes.  Discrete outputs bit-exact; continuous
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_CASES, TIE_CASES, V0_CASES
+from conftest import GOLDEN_CASES, TIE_CASES, V0_CASES, V0_TIE_CASES
 from helpers import (ENV_FIELDS, F64_FIELDS, I32_FIELDS, LC_BOUNDARY_EPS, OUT_F, OUT_I, SH_F, SH_I, compare_states,
                      load_golden, obs25, rel_err, used_mask)
 
@@ -747,7 +747,7 @@ def test_action_masking_surface(mm):
     b.close()
 
 
-@pytest.mark.parametrize("name", V0_CASES)
+@pytest.mark.parametrize("name", V0_CASES + V0_TIE_CASES)
 def test_v0_env_cuda_vs_golden_and_adapter(mm, orc, name):
     """BASELINE configs[0]: env merge-multi-agent-v0 (no shield, MDPVehicle, 5x5 observation) teacher-forced against
     the reference, then whole episodes through make('merge-multi-agent-v0')."""
@@ -765,6 +765,8 @@ def test_v0_env_cuda_vs_golden_and_adapter(mm, orc, name):
     check_outputs(got, {k: g[k] for k in OUT_F + OUT_I}, g["st_n_cav"][rows])
     assert np.array_equal(v["action_mask"].cpu().numpy().astype(np.int32), g["avail_bits"])
     env.close()
+    if name in V0_TIE_CASES:        # snapped before every step: no episode to replay
+        return
     single = mm.make("merge-multi-agent-v0", config=env_config(cfg))
     ep = g["ep_start"]
     for j, seed in enumerate(cfg["seeds"]):

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle as orc
-from conftest import GOLDEN_CASES, TIE_CASES, V0_CASES
+from conftest import GOLDEN_CASES, TIE_CASES, V0_CASES, V0_TIE_CASES
 from helpers import (ENV_FIELDS, F64_FIELDS, LC_BOUNDARY_EPS, OUT_F, OUT_I, SH_F, SH_I, compare_states,
                      load_golden, obs25, rel_err)
 
@@ -137,7 +137,7 @@ def test_fixture_inventory():
         assert same_x >= 5 and same_key >= 100, (name, same_x, same_key)
 
 
-@pytest.mark.parametrize("name", V0_CASES)
+@pytest.mark.parametrize("name", V0_CASES + V0_TIE_CASES)
 def test_v0_env_teacher_forced_and_free_running(name):
     """BASELINE configs[0] (test-configs_marl-cav-unsafe.ini, env merge-multi-agent-v0): MDPVehicle CAVs without the
     [-12.5, 6] acceleration clip, plain IDMVehicle HDVs, 5x5 Kinematics observation."""
@@ -153,6 +153,8 @@ def test_v0_env_teacher_forced_and_free_running(name):
         got = obs25(out[k]) if k == "obs" else out[k]
         assert rel_err(got, g[k]).max() <= TOL, k
     assert not out["sh_ran"].any()
+    if name in V0_TIE_CASES:        # snapped before every step: no chain to run freely
+        return
     ep = g["ep_start"]
     for j in range(len(ep) - 1):
         steps = np.where((rows >= ep[j]) & (rows < ep[j + 1] - 1))[0]
