@@ -84,7 +84,7 @@ CASES = {
     "ties_mass_td3": (dict(safety_guarantee="cbf-cav", traffic_density=3, mixed_traffic=False), [40, 41], 116, "snap"),
     "ties_hss_td3_mixed": (dict(safety_guarantee="cbf-avs_cint", traffic_density=3, traffic_type="mixed",
                                 mixed_traffic=True), [42, 43], 117, "snap"),
-    # the same plus y snapped to a 0.5 m grid: vehicles exactly half-way between bc0 and bc1 during a lane change (the
+    # the same plus speeds on a 2.5 m/s grid (half-way between speed levels) and y snapped to a 0.5 m grid: vehicles exactly half-way between bc0 and bc1 during a lane change (the
     # closest-lane argmin ties and list order decides), lateral offsets exactly on the on_lane / is_lc margins
     # the v0 env (MDPVehicle / IDMVehicle, no history, no shield) with the same snapping
     "ties_v0_unsafe_td2_mixed": (dict(env_name="merge-multi-agent-v0", safety_guarantee="none", traffic_density=2,
@@ -123,6 +123,9 @@ def run_case(name):
                     veh.speed = float(np.round(veh.speed))
                     if snap_y:
                         veh.position[1] = float(np.round(veh.position[1] * 2) / 2)
+                        # speeds on a 2.5 m/s grid: 12.5, 17.5, 22.5, 27.5 sit exactly between two speed levels, where
+                        # FASTER / SLOWER round half to even (controller.py:302-305, 327-337)
+                        veh.speed = float(np.round(veh.speed / 2.5) * 2.5)
                     # the newest history record IS the current state (log_step after every move,
                     # safe_controller.py:187-205, behavior.py:509-519): keep that invariant
                     if getattr(veh, "state_hist", None):

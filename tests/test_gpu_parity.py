@@ -168,7 +168,8 @@ def test_cuda_vs_oracle_scenes_with_exact_ties(mm, orc, shield, traffic, td, sna
     integers (as in the TIE_CASES fixtures, where the oracle's tie rules are pinned on the reference), so vehicles share
     x / s and the closest-vehicle keys tie on both sides of an ego in most envs.  The x-ordered walks of the kernel must
     fall back to their exhaustive scans exactly there; CUDA and oracle are stepped from the same snapped state.
-    snap_y: y on a 0.5 m grid as well (vehicles exactly between bc0 and bc1: the closest-lane argmin ties)."""
+    snap_y: y on a 0.5 m grid as well (vehicles exactly between bc0 and bc1: the closest-lane argmin ties) and speeds
+    on a 2.5 m/s grid (half-way between speed levels: np.round's half-to-even in speed_to_index)."""
     tie_rollout(mm, orc, shield, traffic, td, snap_y)
 
 
@@ -198,6 +199,8 @@ def tie_rollout(mm, orc, shield, traffic, td, snap_y=False):
         st["speed"] = np.where(um, np.round(st["speed"]), st["speed"])
         if snap_y:
             st["y"] = np.where(um, np.round(st["y"] * 2) / 2, st["y"])
+            # 12.5, 17.5, ... m/s: half-way between two speed levels, FASTER / SLOWER round half to even
+            st["speed"] = np.where(um, np.round(st["speed"] / 2.5) * 2.5, st["speed"])
         # the newest history record is the current state (log_step after every move): keep that invariant
         h1 = um & (st["hist_len"] >= 1)
         st["rec1_x"] = np.where(h1, st["x"], st["rec1_x"])
