@@ -86,6 +86,10 @@ CASES = {
                                 mixed_traffic=True), [42, 43], 117, "snap"),
     # the same plus speeds on a 2.5 m/s grid (half-way between speed levels) and y snapped to a 0.5 m grid: vehicles exactly half-way between bc0 and bc1 during a lane change (the
     # closest-lane argmin ties and list order decides), lateral offsets exactly on the on_lane / is_lc margins
+    # x on a 0.5 m grid: vehicles exactly on the after_end thresholds x = 217.5 / 317.5 / 417.5 (s > len - 2.5 is strict,
+    # lane.py:95) as well as on the lane ends
+    "ties_half_mass_td3_mixed": (dict(safety_guarantee="cbf-cav", traffic_density=3, traffic_type="mixed",
+                                      mixed_traffic=True), [50, 51, 52], 120, "snaph"),
     # the v0 env (MDPVehicle / IDMVehicle, no history, no shield) with the same snapping
     "ties_v0_unsafe_td2_mixed": (dict(env_name="merge-multi-agent-v0", safety_guarantee="none", traffic_density=2,
                                       HEADWAY_TIME=1.2), [47, 48], 119, "snapy"),
@@ -99,7 +103,8 @@ SH_F = ("safe_acc", "safe_steer", "nom_acc", "nom_steer")
 
 def run_case(name):
     overrides, seeds, aseed = CASES[name][:3]
-    snap = len(CASES[name]) > 3 and CASES[name][3] in ("snap", "snapy")
+    snap = len(CASES[name]) > 3 and CASES[name][3] in ("snap", "snapy", "snaph")
+    snap_h = len(CASES[name]) > 3 and CASES[name][3] == "snaph"
     snap_y = len(CASES[name]) > 3 and CASES[name][3] == "snapy"
     hdv_env = overrides.get("env_name") == "merge-multi-agent-hdv-v1"
     env = rl.make_env(**overrides)
@@ -119,7 +124,7 @@ def run_case(name):
         while not done:
             if snap:
                 for veh in env.road.vehicles:
-                    veh.position[0] = float(np.round(veh.position[0]))
+                    veh.position[0] = float(np.round(veh.position[0] * 2) / 2 if snap_h else np.round(veh.position[0]))
                     veh.speed = float(np.round(veh.speed))
                     if snap_y:
                         veh.position[1] = float(np.round(veh.position[1] * 2) / 2)

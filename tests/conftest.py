@@ -30,5 +30,6 @@ HDV_CASES = ["hdv_td3"]
 # x positions and speeds snapped to integers before every policy step: exact ties in x, s and the |ds| sort keys
 # (the reference's stable-sort / "<=" tie rules); every step is its own (pre-state, post-state) pair
 # (ties_y_*: y snapped to a 0.5 m grid as well - vehicles exactly between two lanes, closest-lane argmin ties)
-TIE_CASES = ["ties_mass_td3", "ties_hss_td3_mixed", "ties_y_mass_td3_mixed"]
+# (ties_half_*: x on a 0.5 m grid - vehicles exactly on the strict after_end thresholds 217.5 / 317.5 / 417.5)
+TIE_CASES = ["ties_mass_td3", "ties_hss_td3_mixed", "ties_y_mass_td3_mixed", "ties_half_mass_td3_mixed"]
 V0_TIE_CASES = ["ties_v0_unsafe_td2_mixed"]      # the same snapping on env merge-multi-agent-v0 (teacher-forced only)

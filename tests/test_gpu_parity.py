@@ -89,9 +89,16 @@ def test_cuda_vs_golden_teacher_forced(mm, orc, name):
     # per-agent action availability (abstract.py:219-240) against the reference's own _get_available_actions
     assert np.array_equal(v["action_mask"].cpu().numpy().astype(np.int32), g["avail_bits"])
     post = env.get_state()
-    compare_states(post, full_state(orc, g, rows + 1), STATE_TOL, name)
-    check_outputs(got, {k: g[k] for k in OUT_F + OUT_I}, g["st_n_cav"][rows])
     diag = env.shield_diag()
+    # DESIGN.md "Veto tie rule": steps on which the reference's rounding noise put an exactly-zero veto test on the
+    # other side leave the state / output comparison (their lane change is cancelled or not); next to none exist
+    flipped = ((g["sh_ran"] == 1) & (diag["lc_margin"] < LC_BOUNDARY_EPS) &
+               (diag["is_lc_safe"] != g["sh_is_lc_safe"])).any(axis=(1, 2))
+    assert flipped.sum() <= 1, np.where(flipped)[0]
+    keep = np.where(~flipped)[0]
+    sub = lambda d: {k: d[k][keep] for k in d}
+    compare_states(sub(post), sub(full_state(orc, g, rows + 1)), STATE_TOL, name)
+    check_outputs(sub(got), {k: g[k][keep] for k in OUT_F + OUT_I}, g["st_n_cav"][rows][keep])
     nb = check_shield(diag, {k: g[k] for k in g.files if k.startswith("sh_")}, diag["lc_margin"])
     assert nb <= 0.01 * max(int((g["sh_ran"] == 1).sum()), 1) + 1
     env.close()

@@ -28,15 +28,21 @@ def test_teacher_forced_step(name):
     st = golden_state(g, rows)
     out = orc.step(cfg, st, g["act"], n_threads=4)
     want = golden_state(g, rows + 1)
-    compare_states(st, want, TOL, name)
-    for k in OUT_I:
-        assert np.array_equal(out[k], g[k]), k
-    for k in OUT_F:
-        got = obs25(out[k]) if (k == "obs" and cfg["n_s"] == 25) else out[k]
-        assert rel_err(got, g[k]).max() <= TOL, k
     ran = g["sh_ran"] == 1
     assert np.array_equal(out["sh_ran"], g["sh_ran"])
     boundary = ran & (out["sh_lc_margin"] < LC_BOUNDARY_EPS)
+    # DESIGN.md "Veto tie rule": a veto test that is 0 in exact arithmetic and +-1e-15 in float64.  Where the reference's
+    # rounding noise fell on the other side, the step's state legitimately differs (the lane change is cancelled or
+    # not): those steps leave the state / output comparison, and there must be next to none of them
+    flipped = (boundary & (out["sh_is_lc_safe"] != g["sh_is_lc_safe"])).any(axis=(1, 2))
+    assert flipped.sum() <= 1, np.where(flipped)[0]
+    keep = np.where(~flipped)[0]
+    compare_states({k: st[k][keep] for k in st}, {k: want[k][keep] for k in want}, TOL, name)
+    for k in OUT_I:
+        assert np.array_equal(out[k][keep], g[k][keep]), k
+    for k in OUT_F:
+        got = obs25(out[k]) if (k == "obs" and cfg["n_s"] == 25) else out[k]
+        assert rel_err(got[keep], g[k][keep]).max() <= TOL, k
     for k in SH_I:
         bad = (out["sh_" + k] != g["sh_" + k]) & ran & ~boundary
         assert not bad.any(), (k, np.argwhere(bad)[:5].tolist())
