@@ -16,6 +16,10 @@ CASES = [("cbf-cav", "cav", 3, "default", "steer"), ("cbf-cav", "mixed", 3, "sre
          ("cbf-cav", "av", 3, "default", "steer"), ("cbf-avs_cint", "av", 2, "srew", "steer")]
 rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 first_round = int(sys.argv[2]) if len(sys.argv) > 2 else 0      # seeds depend on the round index
+# "snap": before every policy step x -> 0.5 m grid, y -> 0.5 m grid, speed -> 2.5 m/s grid (odd steps) or integers (even
+# steps), newest history record re-synced, state uploaded: exact ties and boundary values in every scene (the tie
+# fixtures of tests/golden at scale); the comparison is then per step (teacher-forced from the oracle's state)
+snap = len(sys.argv) > 3 and sys.argv[3] == "snap"
 E, T = 4096, 100
 total_env_steps, boundary = 0, 0
 t0 = time.time()
@@ -31,6 +35,15 @@ for rnd in range(first_round, first_round + rounds):
         rng = np.random.RandomState(100 * rnd + ci)
         alive, clean = np.ones(E, bool), np.ones(E, bool)
         for t in range(T):
+            if snap:
+                um = used_mask(st)
+                st["x"] = np.where(um, np.round(st["x"] * 2) / 2, st["x"])
+                st["y"] = np.where(um, np.round(st["y"] * 2) / 2, st["y"])
+                st["speed"] = np.where(um, np.round(st["speed"] / 2.5) * 2.5 if t % 2 else np.round(st["speed"]), st["speed"])
+                h1 = um & (st["hist_len"] >= 1)
+                st["rec1_x"] = np.where(h1, st["x"], st["rec1_x"])
+                st["rec1_vx"] = np.where(h1, st["speed"] * np.cos(st["heading"]), st["rec1_vx"])
+                env.set_state(st)
             a = rng.randint(0, 5, size=(E, 12)).astype(np.int8)
             want = orc.step(ocfg, st, a, n_threads=16)
             _, _, _, v = env.step(torch.from_numpy(a).cuda())
@@ -64,4 +77,4 @@ for rnd in range(first_round, first_round + rounds):
         env.close()
         print("round %d %-13s %-6s td%d %-8s %-9s ok  (%.0f s, %d env-steps compared so far, %d veto-boundary solves)" % (
             rnd, shield, traffic, td, reward, lateral, time.time() - t0, total_env_steps, boundary), flush=True)
-print("SOAK OK", total_env_steps, "env-steps")
+print("SOAK OK", total_env_steps, "env-steps", "(snapped: exact ties / boundary values)" if snap else "")
