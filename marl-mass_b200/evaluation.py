@@ -20,12 +20,16 @@ def eval_num_cav(i, traffic_density):
     return {1: (i + 1) % 3, 2: (i + 2) % 4, 3: (i + 4) % 6}[int(traffic_density)]
 
 
-def evaluation(action_fn, config, test_seeds, eval_episodes=None, is_train=True, device=0):
+def evaluation(action_fn, config, test_seeds, eval_episodes=None, is_train=True, device=0, output_dir=None, tag="testing"):
     """action_fn(obs [E, 12, n_s] cuda f32, n_agents [E] cuda i32) -> actions [E, 12] (cuda, integer).
 
     Returns (rewards, (vehicle_speed, vehicle_position), ext_info) as `MAPPO.evaluation` does: rewards[i] is the list
     of global rewards of episode i; vehicle_speed[i] / vehicle_position[i] are arrays [steps_i, n_agents_i];
-    ext_info has steps, avg_speeds, crash_count, step_time, min_headway, traffic_speeds, merge_percents."""
+    ext_info has steps, avg_speeds, crash_count, step_time, min_headway, traffic_speeds, merge_percents.
+
+    output_dir: where the reference records one video per episode (mappo.py:290-302, 321-327), this writes the same
+    frames as PNG files `<tag>_episode_<i>/frame_<t>.png` (the first after reset, then one per policy step), rendered
+    on the CPU from the device state (render.py); there is no video encoder in the image."""
     import torch
     seeds = [int(s) for s in (test_seeds.split(",") if isinstance(test_seeds, str) else test_seeds)]
     n_ep = len(seeds) if eval_episodes is None else int(eval_episodes)
@@ -48,6 +52,16 @@ def evaluation(action_fn, config, test_seeds, eval_episodes=None, is_train=True,
     crashed = np.zeros(n_ep, bool)
     min_headway = float("inf")
     t_total, n_steps = 0.0, 0
+
+    def write_frames(st, which, t):
+        import os
+        from .render import render_scene, save_png
+        for e in which:
+            d = os.path.join(output_dir, "%s_episode_%d" % (tag, e))
+            os.makedirs(d, exist_ok=True)
+            save_png(os.path.join(d, "frame_%03d.png" % t), render_scene(st, int(e), env.config))
+    if output_dir is not None:
+        write_frames(env.get_state(), range(n_ep), 0)
     while active.any():
         t0 = time.process_time()
         a = action_fn(env.obs_view(), n_agents).to(torch.int8)
@@ -58,6 +72,8 @@ def evaluation(action_fn, config, test_seeds, eval_episodes=None, is_train=True,
         st = env.get_state()
         out = {k: v[k].cpu().numpy() for k in ("reward", "done", "average_speed", "traffic_speed", "min_headway",
                                                 "merge_percent")}
+        if output_dir is not None:
+            write_frames(st, np.nonzero(active)[0], n_steps)
         for e in np.nonzero(active)[0]:
             n = int(n_host[e])
             steps[e] += 1

@@ -224,7 +224,7 @@ def test_rollout_collect_and_update_run_on_the_fused_path(mm):
     env.close()
 
 
-def test_batched_evaluation_equals_the_sequential_protocol(mm):
+def test_batched_evaluation_equals_the_sequential_protocol(mm, tmp_path):
     """evaluation.evaluation (every evaluation episode as one env of a batch) == MAPPO.evaluation's loop
     (marl/mappo.py:255-361) driven through the single-env adapter, episode by episode, with the same action table."""
     import torch
@@ -239,9 +239,16 @@ def test_batched_evaluation_equals_the_sequential_protocol(mm):
         step["t"] += 1
         return a
 
-    rewards, (vs, vp), info = ev.evaluation(action_fn, cfg, seeds, is_train=True)
+    rewards, (vs, vp), info = ev.evaluation(action_fn, cfg, seeds, is_train=True, output_dir=str(tmp_path))
+    # the frames the reference would record as a video (mappo.py:290-327): one after reset + one per policy step
+    for i in range(len(seeds)):
+        frames = sorted(os.listdir(os.path.join(str(tmp_path), "testing_episode_%d" % i)))
+        assert len(frames) == info["steps"][i] + 1 and frames[0] == "frame_000.png"
+    with open(os.path.join(str(tmp_path), "testing_episode_0", "frame_000.png"), "rb") as f:
+        assert f.read(8) == b"\x89PNG\r\n\x1a\n"
     env = mm.make("merge-multi-agent-v1")
     env.config.update(cfg)
+    assert env.render(mode="rgb_array") is not None and env.render(mode="rgb_array").shape == (120, 600, 3)
     min_hw = float("inf")
     for i, s in enumerate(seeds):
         obs, _ = env.reset(is_training=False, testing_seeds=s, num_CAV=ev.eval_num_cav(i, 2))
