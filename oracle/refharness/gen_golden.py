@@ -90,6 +90,15 @@ CASES = {
     # lane.py:95) as well as on the lane ends
     "ties_half_mass_td3_mixed": (dict(safety_guarantee="cbf-cav", traffic_density=3, traffic_type="mixed",
                                       mixed_traffic=True), [50, 51, 52], 120, "snaph"),
+    # the baseline supervisors (central_layer.py / decentralised_dmc.py, the 8 priority / dmc ini files): they only
+    # REPLACE the meta-actions before _simulate (abstract.py:459-467).  The fixtures hold the policy's tuple (`act`), the
+    # supervised tuple the env then executed (`new_act` = info["new_action"]) and the np.random.rand() draws the
+    # supervisor consumed (`rand_draws`): groundwork for a supervisor kernel, and today a check that the v0 dynamics
+    # under the supervised actions are the un-shielded dynamics
+    "priority_v0_td3_mixed": (dict(env_name="merge-multi-agent-v0", safety_guarantee="priority", traffic_density=3,
+                                   HEADWAY_TIME=1.2, mixed_traffic=True), [1, 2, 3], 121),
+    "dmc_v0_td3_mixed": (dict(env_name="merge-multi-agent-v0", safety_guarantee="dmc", traffic_density=3,
+                              HEADWAY_TIME=1.2, mixed_traffic=True), [1, 2, 3], 122),
     # the v0 env (MDPVehicle / IDMVehicle, no history, no shield) with the same snapping
     "ties_v0_unsafe_td2_mixed": (dict(env_name="merge-multi-agent-v0", safety_guarantee="none", traffic_density=2,
                                       HEADWAY_TIME=1.2), [47, 48], 119, "snapy"),
@@ -117,6 +126,8 @@ def run_case(name):
     sh = {k: [] for k in SH_I + SH_F}
     qps = []
     arng = np.random.RandomState(aseed)
+    supervised = overrides.get("safety_guarantee") in ("priority", "dmc")
+    new_acts, draws = [], []
     for seed in seeds:
         env.reset(is_training=False, testing_seeds=seed)
         rl.drain_shield_log()
@@ -140,7 +151,26 @@ def run_case(name):
             states.append(st)
             n = int(st["n_cav"])
             a = arng.randint(0, 5, size=n)
-            obs, reward, done, info = env.step(tuple(int(x) for x in a))
+            if supervised:      # log the global-generator draws of the supervisor (priority tie-breaks)
+                log_rand, real_rand = [], np.random.rand
+
+                def logging_rand(*shape):
+                    v = real_rand(*shape)
+                    log_rand.append(float(v))
+                    return v
+                np.random.rand = logging_rand
+            try:
+                obs, reward, done, info = env.step(tuple(int(x) for x in a))
+            finally:
+                if supervised:
+                    np.random.rand = real_rand
+            if supervised:
+                na = np.full(M, -1, np.int8)
+                na[:n] = np.asarray(info["new_action"], np.int64)
+                new_acts.append(na)
+                d = np.full(16, np.nan)
+                d[:len(log_rand)] = log_rand
+                draws.append(d)
             if hdv_env:     # every vehicle is observed and rewarded, nobody is controlled
                 o = rl.step_outputs_hdv(env, obs, reward, done, info)
                 n = int(st["n_veh"])
@@ -206,6 +236,9 @@ def run_case(name):
     data["ep_start"] = np.array(ep_start, np.int32)
     data["act"] = np.stack(acts)
     data["row_of_step"] = np.array(rows, np.int32)
+    if supervised:
+        data["new_act"] = np.stack(new_acts)
+        data["rand_draws"] = np.stack(draws)
     for k, v in outs.items():
         data[k] = np.stack(v) if np.ndim(v[0]) else np.array(v)
     for k in SH_I + SH_F:

@@ -33,3 +33,6 @@ HDV_CASES = ["hdv_td3"]
 # (ties_half_*: x on a 0.5 m grid - vehicles exactly on the strict after_end thresholds 217.5 / 317.5 / 417.5)
 TIE_CASES = ["ties_mass_td3", "ties_hss_td3_mixed", "ties_y_mass_td3_mixed", "ties_half_mass_td3_mixed"]
 V0_TIE_CASES = ["ties_v0_unsafe_td2_mixed"]      # the same snapping on env merge-multi-agent-v0 (teacher-forced only)
+# baseline supervisors priority / dmc on env v0: the policy's actions, the supervised actions the env executed and the
+# supervisor's random draws (the supervisor itself is not built: DESIGN.md section 8)
+SUPERVISED_CASES = ["priority_v0_td3_mixed", "dmc_v0_td3_mixed"]

@@ -5,7 +5,7 @@ and (b) the CPU oracle on seeded scenes.  Discrete outputs bit-exact; continuous
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_CASES, TIE_CASES, V0_CASES, V0_TIE_CASES
+from conftest import GOLDEN_CASES, SUPERVISED_CASES, TIE_CASES, V0_CASES, V0_TIE_CASES
 from helpers import (ENV_FIELDS, F64_FIELDS, I32_FIELDS, LC_BOUNDARY_EPS, OUT_F, OUT_I, SH_F, SH_I, compare_states,
                      load_golden, obs25, rel_err, used_mask)
 
@@ -791,3 +791,24 @@ def test_v0_env_cuda_vs_golden_and_adapter(mm, orc, name):
             assert done == bool(g["done"][t])
         assert done
     single.close()
+
+
+@pytest.mark.parametrize("name", SUPERVISED_CASES)
+def test_supervised_actions_drive_the_unshielded_v0_dynamics(mm, orc, name):
+    """safety_guarantee = priority | dmc only replaces the meta-actions before _simulate (abstract.py:459-467): the CUDA
+    v0 step with the supervised tuple the reference executed reproduces the reference's post-state and outputs.  (The
+    supervisors themselves are not built: make_mm_config rejects those values.)"""
+    import torch
+    g, cfg = load_golden(name)
+    with pytest.raises(ValueError):
+        mm.make_mm_config(dict(mm.DEFAULT_CONFIG, **env_config(cfg)))
+    rows = g["row_of_step"]
+    env = mm.MergeEnvBatched(len(rows), dict(env_config(cfg), safety_guarantee="none"))
+    assert env.n_s == 25
+    env.set_state(full_state(orc, g, rows))
+    _, _, _, v = env.step(torch.from_numpy(np.ascontiguousarray(g["new_act"])).cuda())
+    got = outputs_to_numpy(v, OUT_F + OUT_I)
+    got["obs"] = obs25(got["obs"])
+    compare_states(env.get_state(), full_state(orc, g, rows + 1), STATE_TOL, name, v0=True)
+    check_outputs(got, {k: g[k] for k in OUT_F + OUT_I}, g["st_n_cav"][rows])
+    env.close()

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle as orc
-from conftest import GOLDEN_CASES, TIE_CASES, V0_CASES, V0_TIE_CASES
+from conftest import GOLDEN_CASES, SUPERVISED_CASES, TIE_CASES, V0_CASES, V0_TIE_CASES
 from helpers import (ENV_FIELDS, F64_FIELDS, LC_BOUNDARY_EPS, OUT_F, OUT_I, SH_F, SH_I, compare_states,
                      load_golden, obs25, rel_err)
 
@@ -218,3 +218,29 @@ def test_hdv_env_teacher_forced_and_free_running():
         out = orc.step(cfg, st, g["act"][first + np.minimum(t, 99)], n_threads=2)
     assert out["done"].all() and (st["steps"] == 100).all()
     compare_states(st, golden_state(g, ep[1:] - 1), 1e-6, "hdv free-running")
+
+
+@pytest.mark.parametrize("name", SUPERVISED_CASES)
+def test_supervised_actions_drive_the_unshielded_v0_dynamics(name):
+    """safety_guarantee = priority | dmc (central_layer.py, decentralised_dmc.py) only replaces the meta-action tuple
+    before _simulate (abstract.py:459-467): stepping the un-shielded v0 env with the supervised tuple the reference
+    executed (`new_act`) reproduces its post-state and outputs.  The fixtures also carry the policy's tuple and the
+    supervisor's random draws for the supervisor kernel that is not built yet."""
+    g, cfg = load_golden(name)
+    assert cfg["safety_guarantee"] in ("priority", "dmc") and cfg["n_s"] == 25
+    changed = (g["act"] != g["new_act"]).any(axis=1)
+    assert changed.sum() >= 20 and (~np.isnan(g["rand_draws"])).sum(1).min() >= g["st_n_cav"][g["row_of_step"]].min()
+    rows = g["row_of_step"]
+    st = golden_state(g, rows)
+    out = orc.step(dict(cfg, safety_guarantee="none"), st, g["new_act"], n_threads=4)
+    compare_states(st, golden_state(g, rows + 1), TOL, name, v0=True)
+    for k in OUT_I:
+        assert np.array_equal(out[k], g[k]), k
+    for k in OUT_F:
+        got = obs25(out[k]) if k == "obs" else out[k]
+        assert rel_err(got, g[k]).max() <= TOL, k
+    # and the policy's own tuple would NOT have: the supervisor's replacements matter
+    st2 = golden_state(g, rows[changed])
+    orc.step(dict(cfg, safety_guarantee="none"), st2, g["act"][changed], n_threads=4)
+    want = golden_state(g, rows[changed] + 1)
+    assert np.abs(st2["speed"] - want["speed"]).max() > 1e-3 or np.abs(st2["y"] - want["y"]).max() > 1e-3
