@@ -90,6 +90,9 @@ CASES = {
     # lane.py:95) as well as on the lane ends
     "ties_half_mass_td3_mixed": (dict(safety_guarantee="cbf-cav", traffic_density=3, traffic_type="mixed",
                                       mixed_traffic=True), [50, 51, 52], 120, "snaph"),
+    # the all-HDV env with the snapping (IDM / MOBIL only; every vehicle observed)
+    "ties_hdv_td3": (dict(env_name="merge-multi-agent-hdv-v1", safety_guarantee="cbf-cav", traffic_density=3,
+                          traffic_type="hdv", mixed_traffic=True), [14, 15], 123, "snapy"),
     # the baseline supervisors (central_layer.py / decentralised_dmc.py, the 8 priority / dmc ini files): they only
     # REPLACE the meta-actions before _simulate (abstract.py:459-467).  The fixtures hold the policy's tuple (`act`), the
     # supervised tuple the env then executed (`new_act` = info["new_action"]) and the np.random.rand() draws the

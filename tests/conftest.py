@@ -27,6 +27,7 @@ GOLDEN_CASES = ["unsafe_td1", "unsafe_td3", "unsafe_td2_mixed", "hss_td3", "hss_
 V0_CASES = ["v0_unsafe_td1", "v0_unsafe_td2_mixed"]
 # env merge-multi-agent-hdv-v1 (MergeEnvLCHDV, traffic_type = hdv): every vehicle observed, nobody controlled
 HDV_CASES = ["hdv_td3"]
+HDV_TIE_CASES = ["ties_hdv_td3"]      # the same env with x / y / speed snapped to grid values before every step
 # x positions and speeds snapped to integers before every policy step: exact ties in x, s and the |ds| sort keys
 # (the reference's stable-sort / "<=" tie rules); every step is its own (pre-state, post-state) pair
 # (ties_y_*: y snapped to a 0.5 m grid as well - vehicles exactly between two lanes, closest-lane argmin ties)

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle as orc
-from conftest import GOLDEN_CASES, SUPERVISED_CASES, TIE_CASES, V0_CASES, V0_TIE_CASES
+from conftest import GOLDEN_CASES, HDV_TIE_CASES, SUPERVISED_CASES, TIE_CASES, V0_CASES, V0_TIE_CASES
 from helpers import (ENV_FIELDS, F64_FIELDS, LC_BOUNDARY_EPS, OUT_F, OUT_I, SH_F, SH_I, compare_states,
                      load_golden, obs25, rel_err)
 
@@ -192,10 +192,11 @@ def test_caller_side_restatements_match_the_reference_vectors():
     assert np.allclose(got[:, 0], np.concatenate([a[:, 0], b[:, 0]]))
 
 
-def test_hdv_env_teacher_forced_and_free_running():
+@pytest.mark.parametrize("name", ["hdv_td3"] + HDV_TIE_CASES)
+def test_hdv_env_teacher_forced_and_free_running(name):
     """MergeEnvLCHDV (merge-multi-agent-hdv-v1, test-idm-td3.ini): IDM / MOBIL only; one observation row and one reward
     term per vehicle, reward = their mean, done on any crash or at the horizon, min headway over every vehicle."""
-    g, cfg = load_golden("hdv_td3")
+    g, cfg = load_golden(name)
     rows = g["row_of_step"]
     st = golden_state(g, rows)
     out = orc.step(cfg, st, g["act"], n_threads=4)
@@ -209,6 +210,8 @@ def test_hdv_env_teacher_forced_and_free_running():
         assert rel_err(out[k], g[k]).max() <= TOL, k
     assert rel_err(out["agents_rewards"], g["agents_rewards"]).max() <= TOL
     assert np.array_equal(out["average_speed"], out["traffic_speed"]) and (out["sh_ran"] == 0).all()
+    if name in HDV_TIE_CASES:       # snapped before every step: no chain to run freely
+        return
     assert rel_err(orc.observe(golden_state(g, g["ep_start"][:-1]), env_hdv=True)[:, :, 0].sum(1), nv[g["ep_start"][:-1]].astype(float)).max() == 0
     # free running: whole episodes from the reference's reset states
     ep = g["ep_start"]
