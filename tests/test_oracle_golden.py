@@ -247,3 +247,42 @@ def test_supervised_actions_drive_the_unshielded_v0_dynamics(name):
     orc.step(dict(cfg, safety_guarantee="none"), st2, g["act"][changed], n_threads=4)
     want = golden_state(g, rows[changed] + 1)
     assert np.abs(st2["speed"] - want["speed"]).max() > 1e-3 or np.abs(st2["y"] - want["y"]).max() > 1e-3
+
+
+def test_qp_closed_form_minimises_the_reference_objective():
+    """The closed form against a direct minimisation of the QP the reference hands to cvxopt
+    (cbf.py:110-135): min 1/2 (u0^2 + u1^2 + 1e18 s^2) s.t. a u0 - s <= c_i, lo <= u0 <= hi.  u1 = 0 and
+    s = max(0, max_i(a u0 - c_i)) at the optimum, which leaves a convex 1-D problem solved here by ternary search."""
+    from fractions import Fraction
+    rng = np.random.RandomState(5)
+    n_checked = n_active = 0
+    for _ in range(1000):
+        a = float(rng.choice([1.0, -1.0]) * rng.uniform(0.01, 0.08)) if rng.rand() > 0.05 else 0.0
+        c_lead = float(rng.normal(0.05, 0.15))
+        has_adj = bool(rng.rand() < 0.5)
+        c_adj = float(rng.normal(0.05, 0.15)) if has_adj else 0.0
+        lo = float(-12.5 / 15 + rng.uniform(-0.2, 0.2))
+        hi = float(6.0 / 15 + rng.uniform(-0.2, 0.2))
+        if rng.rand() < 0.1:
+            lo, hi = lo + 1.0, hi + 1.0           # box entirely above zero
+        cs = [c_lead] + ([c_adj] if has_adj else [])
+
+        def f(u):           # exact rational arithmetic: the 1e18 weight swamps 1/2 u^2 in float64
+            u = Fraction(u)
+            s = max(Fraction(0), max(Fraction(a) * u - Fraction(c) for c in cs))
+            return u * u / 2 + Fraction(10 ** 18, 2) * s * s
+        l, h = lo, hi
+        for _ in range(120):
+            m1, m2 = l + (h - l) / 3, h - (h - l) / 3
+            if f(m1) <= f(m2):
+                h = m2
+            else:
+                l = m1
+        u_num = 0.5 * (l + h)
+        u, act = orc.qp(a, c_lead, c_adj, has_adj, lo, hi)
+        assert lo <= u <= hi
+        assert f(u) <= f(u_num) * (1 + Fraction(1, 10 ** 9)) + Fraction(1, 10 ** 18), (a, cs, lo, hi, u, u_num)
+        assert abs(u - u_num) <= 1e-6, (a, cs, lo, hi, u, u_num)
+        n_checked += 1
+        n_active += int(act != 0)
+    assert n_checked == 1000 and 100 < n_active < 900
