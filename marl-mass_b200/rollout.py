@@ -238,7 +238,7 @@ class BatchedMAPPORollout(object):
     @torch.no_grad()
     def act_torch(self, obs, n_agents):
         """Plain torch fp32 actor + torch.multinomial: the numerics reference of `act_fused`."""
-        logp = self.actor(obs.view(-1, NS))                               # [E*12, 5]
+        logp = self.actor(obs.reshape(-1, NS))                               # [E*12, 5]
         a = torch.multinomial(logp.exp(), 1).view(obs.shape[0], MAXV)           # exploration_action, mappo.py:225-230
         live = self._slot < n_agents[:, None]
         return torch.where(live, a, torch.ones_like(a)).to(torch.int8), live
@@ -280,7 +280,7 @@ class BatchedMAPPORollout(object):
     def _final_value(self, obs, n_agents):
         a_fin, _ = self._act(obs, n_agents)
         onehot = torch.nn.functional.one_hot(a_fin.long(), NA).float()
-        return self.critic(obs.view(-1, NS), onehot.view(-1, NA)).view(self.E, MAXV)
+        return self.critic(obs.reshape(-1, NS), onehot.view(-1, NA)).view(self.E, MAXV)
 
     def networks(self):
         """every module a replica must hold identically (sync_parameters, the replica check of train.py)"""
@@ -378,13 +378,13 @@ class BatchedMAPPOGIRollout(BatchedMAPPORollout):
 
     @torch.no_grad()
     def act_torch(self, obs, n_agents):
-        logp = self.policy(obs.view(-1, NS))
+        logp = self.policy(obs.reshape(-1, NS))
         a = torch.multinomial(logp.exp(), 1).view(obs.shape[0], MAXV)           # exploration_action, mappo_gi.py:368-373
         live = self._slot < n_agents[:, None]
         return torch.where(live, a, torch.ones_like(a)).to(torch.int8), live
 
     def _final_value(self, obs, n_agents):
-        return self.policy(obs.view(-1, NS), out_type="v").view(self.E, MAXV)
+        return self.policy(obs.reshape(-1, NS), out_type="v").view(self.E, MAXV)
 
     def networks(self):
         return [self.policy, self.policy_target]
