@@ -286,3 +286,23 @@ def test_qp_closed_form_minimises_the_reference_objective():
         n_checked += 1
         n_active += int(act != 0)
     assert n_checked == 1000 and 100 < n_active < 900
+
+
+def test_oracle_threads_do_not_change_results():
+    """The multi-threaded oracle is the CPU baseline bench.py times: any thread count gives the bits of one thread."""
+    import copy
+    import marl_mass_b200 as mm
+    cfg = dict(mm.DEFAULT_CONFIG, safety_guarantee="cbf-cav", traffic_type="mixed", traffic_density=3, HEADWAY_TIME=0.5,
+               cbf_eta=0.03125)
+    st1 = mm.spawn.spawn_state(list(range(300)), 3, "mixed")
+    st7 = copy.deepcopy(st1)
+    ocfg = orc.make_config(cfg)
+    rng = np.random.RandomState(3)
+    for t in range(12):
+        a = rng.randint(0, 5, size=(300, 12)).astype(np.int8)
+        o1 = orc.step(ocfg, st1, a, n_threads=1)
+        o7 = orc.step(ocfg, st7, a, n_threads=7)
+        for k in o1:
+            assert np.array_equal(o1[k], o7[k], equal_nan=True), (t, k)
+    for k in st1:
+        assert np.array_equal(st1[k], st7[k]), k
