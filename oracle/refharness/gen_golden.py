@@ -101,7 +101,7 @@ CASES = {
     "priority_v0_td3_mixed": (dict(env_name="merge-multi-agent-v0", safety_guarantee="priority", traffic_density=3,
                                    HEADWAY_TIME=1.2, mixed_traffic=True), [1, 2, 3], 121),
     "dmc_v0_td3_mixed": (dict(env_name="merge-multi-agent-v0", safety_guarantee="dmc", traffic_density=3,
-                              HEADWAY_TIME=1.2, mixed_traffic=True), [1, 2, 3], 122),
+                              HEADWAY_TIME=1.2, mixed_traffic=True), [1, 2, 3, 4, 5, 6, 7], 122),
     # the v0 env (MDPVehicle / IDMVehicle, no history, no shield) with the same snapping
     "ties_v0_unsafe_td2_mixed": (dict(env_name="merge-multi-agent-v0", safety_guarantee="none", traffic_density=2,
                                       HEADWAY_TIME=1.2), [47, 48], 119, "snapy"),

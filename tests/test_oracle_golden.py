@@ -306,3 +306,21 @@ def test_oracle_threads_do_not_change_results():
             assert np.array_equal(o1[k], o7[k], equal_nan=True), (t, k)
     for k in st1:
         assert np.array_equal(st1[k], st7[k]), k
+
+
+def test_dmc_supervisor_restatement_matches_the_reference():
+    """oracle/supervisor.py (decentralised_dmc.py + mdp_controller.py + idm_controller.py restated as a pure function of
+    scene, action tuple and random draws) reproduces the tuple the reference's `safety_layer_dmc` handed to _simulate on
+    every step of the fixture, including the ~25 % of steps on which it replaced an action."""
+    import supervisor as sup
+    g, cfg = load_golden("dmc_v0_td3_mixed")
+    rows = g["row_of_step"]
+    st = golden_state(g, rows)
+    replaced = 0
+    for t in range(len(rows)):
+        n = int(st["n_cav"][t])
+        want = [int(x) for x in g["new_act"][t, :n]]
+        got = sup.dmc_supervisor(st, t, g["act"][t], g["rand_draws"][t], cfg["HEADWAY_TIME"])
+        assert got == want, (t, [int(x) for x in g["act"][t, :n]], got, want)
+        replaced += int(want != [int(x) for x in g["act"][t, :n]])
+    assert replaced >= 100
