@@ -99,7 +99,7 @@ CASES = {
     # supervisor consumed (`rand_draws`): groundwork for a supervisor kernel, and today a check that the v0 dynamics
     # under the supervised actions are the un-shielded dynamics
     "priority_v0_td3_mixed": (dict(env_name="merge-multi-agent-v0", safety_guarantee="priority", traffic_density=3,
-                                   HEADWAY_TIME=1.2, mixed_traffic=True), [1, 2, 3], 121),
+                                   HEADWAY_TIME=1.2, mixed_traffic=True), [1, 2, 3, 4, 5, 6, 7], 121),
     "dmc_v0_td3_mixed": (dict(env_name="merge-multi-agent-v0", safety_guarantee="dmc", traffic_density=3,
                               HEADWAY_TIME=1.2, mixed_traffic=True), [1, 2, 3, 4, 5, 6, 7], 122),
     # the v0 env (MDPVehicle / IDMVehicle, no history, no shield) with the same snapping

@@ -1,6 +1,8 @@
-"""CPU restatement of the reference's decentralised baseline supervisor `safety_layer_dmc` — TEST INFRASTRUCTURE ONLY.
+"""CPU restatement of the reference's baseline supervisors `safety_supervisor` (priority) and `safety_layer_dmc` —
+TEST INFRASTRUCTURE ONLY.
 
 Follows (file:line in /root/reference):
+  highway_env/vehicle/safety/central_layer.py:16-178      safety_supervisor (is_priority=True)
   highway_env/vehicle/safety/decentralised_dmc.py:16-67   _evaluate_vehicle_action
   highway_env/vehicle/safety/decentralised_dmc.py:70-198  safety_layer_dmc
   highway_env/envs/common/mdp_controller.py:19-126        mdp_controller (look-ahead step of a CAV)
@@ -12,8 +14,8 @@ Follows (file:line in /root/reference):
 The supervisor runs once per policy step on env merge-multi-agent-v0, before `_simulate` (abstract.py:459-467), and only
 replaces entries of the meta-action tuple.  It is a pure function of (scene, action tuple, the np.random.rand() draws it
 consumes), which is how it is written here: small pure-Python loops over <= 11 vehicles x 18 look-ahead points.  Pinned
-against the fixtures tests/golden/dmc_v0_td3_mixed.npz (oracle/refharness/gen_golden.py), see tests/test_oracle_golden.py.
-No product code imports this module; the CUDA supervisor it is meant to check is not built yet.
+against the fixtures tests/golden/priority_v0_td3_mixed.npz and dmc_v0_td3_mixed.npz (oracle/refharness/gen_golden.py), see tests/test_oracle_golden.py.
+No product code imports this module; the CUDA supervisors it is meant to check are not built yet.
 """
 import math
 
@@ -408,3 +410,90 @@ def dmc_supervisor(state, e, actions, draws, headway_time=1.2):
                 result[i] = acts[rooms.index(max(rooms))]
                 break
     return result
+
+
+def _neighbour_sets(v, road):
+    """central_layer.py:84-110: (v_fl, v_rl, v_fr, v_rr) of an ego on the (partly propagated) copy of the scene."""
+    if v.lane in MAIN:
+        v_fl, v_rl = surrounding_vehicles(v, road)
+        if side_lanes(v.lane):
+            v_fr, v_rr = surrounding_vehicles(v, road, side_lanes(v.lane)[0])
+        elif v.lane == L_AB0 and v.x > 220.0:
+            v_fr, v_rr = surrounding_vehicles(v, road, L_KB0)
+        else:
+            v_fr, v_rr = None, None
+    else:
+        v_fr, v_rr = surrounding_vehicles(v, road)
+        if side_lanes(v.lane):
+            v_fl, v_rl = surrounding_vehicles(v, road, side_lanes(v.lane)[0])
+        elif v.lane == L_KB0:
+            v_fl, v_rl = surrounding_vehicles(v, road, L_AB0)
+        else:
+            v_fl, v_rl = None, None
+    return v_fl, v_rl, v_fr, v_rr
+
+
+def priority_supervisor(state, e, actions, draws, headway_time=1.2):
+    """-> the supervised action list of env `e` (central_layer.py:16-178, `safety_supervisor` with is_priority=True).
+    CAVs are handled one after the other in priority order; each rolls itself and its four surrounding vehicles 18
+    points ahead ON THE SHARED COPY of the scene (vehicles an earlier ego already propagated are not moved again, an
+    ego that was propagated as somebody's neighbour restarts from its real state), and at the first predicted collision
+    takes the available action with the largest safety room - for the rest of its own look-ahead as well.
+    `draws`: np.random.rand() values in consumption order (one per CAV, then two per IDM decision as they occur)."""
+    original = vehicles_of(state, e)
+    road = [v.copy() for v in original]
+    cavs = [i for i, v in enumerate(road) if v.cav]
+    actions = [int(a) for a in actions[:len(cavs)]]
+    k = len(cavs)
+    order = priority_order(road, cavs, draws, headway_time)
+    captured = {i: road[i] for i in cavs}          # the objects the queue holds
+    for turn, i in enumerate(order):
+        first_change = True
+        if len(captured[i].traj) == N_POINTS:      # moved as a neighbour before: start again from the real state
+            road[i] = original[i].copy()
+        v = road[i]
+        acts = available_actions(v)
+        v_fl, v_rl, v_fr, v_rr = _neighbour_sets(v, road)
+        for t in range(N_POINTS):
+            for o in (v_fl, v_fr, v, v_rl, v_rr):
+                if o is None:
+                    continue
+                if len(o.traj) == N_POINTS and turn != 0 and o is not v:
+                    continue
+                if not o.cav:
+                    if t == 0:
+                        generate_actions(o, road, float(draws[k]), float(draws[k + 1]))
+                        k += 2
+                    idm_controller(o)
+                elif o is not v:
+                    # `actions[v.id]` (central_layer.py:135) with v.id == 0 for every vehicle: ControlledVehicle sets
+                    # id = 0 (controller.py:49) and the per-vehicle assignment in reset is commented out
+                    # (abstract.py:196-198), so every neighbouring CAV is rolled forward with the FIRST CAV's action
+                    mdp_controller(o, actions[0])
+                else:
+                    mdp_controller(o, actions[i])
+            for o in (v_fl, v_rl, v_fr, v_rr):
+                if o is None or v.crashed or o is v:
+                    continue
+                ox, oy, oh, osp = o.traj[t]
+                if is_colliding(v, ox, oy, oh, VLEN, VWID):
+                    v.speed = min((v.speed, osp), key=abs)
+                    v.crashed = o.crashed = True
+            if not v.crashed and is_colliding(v, OBSTACLE[0], OBSTACLE[1], 0.0, 2.0, 2.0):
+                v.speed = min((v.speed, 0), key=abs)
+                v.crashed = True
+            if v.crashed:
+                rooms, updated = [], []
+                for a in acts:
+                    c = original[i].copy()
+                    rooms.append(check_safety_room(c, a, [v_fl, v_rl, v_fr, v_rr], t))
+                    updated.append(c)
+                best = rooms.index(max(rooms))
+                v = road[i] = updated[best]
+                if first_change:
+                    first_change = False
+                    actions[i] = acts[best]
+                for o in (v_fl, v_rl, v_fr, v_rr):
+                    if o is not None and o.crashed:
+                        o.crashed = False
+    return actions

@@ -308,19 +308,22 @@ def test_oracle_threads_do_not_change_results():
         assert np.array_equal(st1[k], st7[k]), k
 
 
-def test_dmc_supervisor_restatement_matches_the_reference():
-    """oracle/supervisor.py (decentralised_dmc.py + mdp_controller.py + idm_controller.py restated as a pure function of
-    scene, action tuple and random draws) reproduces the tuple the reference's `safety_layer_dmc` handed to _simulate on
-    every step of the fixture, including the ~25 % of steps on which it replaced an action."""
+@pytest.mark.parametrize("name", SUPERVISED_CASES)
+def test_supervisor_restatements_match_the_reference(name):
+    """oracle/supervisor.py (central_layer.py / decentralised_dmc.py + mdp_controller.py + idm_controller.py restated as
+    pure functions of scene, action tuple and random draws) reproduces the tuple the reference's `safety_supervisor` /
+    `safety_layer_dmc` handed to _simulate on every step of the fixtures, including the ~25 % of steps on which an
+    action was replaced."""
     import supervisor as sup
-    g, cfg = load_golden("dmc_v0_td3_mixed")
+    g, cfg = load_golden(name)
+    fn = sup.priority_supervisor if cfg["safety_guarantee"] == "priority" else sup.dmc_supervisor
     rows = g["row_of_step"]
     st = golden_state(g, rows)
     replaced = 0
     for t in range(len(rows)):
         n = int(st["n_cav"][t])
         want = [int(x) for x in g["new_act"][t, :n]]
-        got = sup.dmc_supervisor(st, t, g["act"][t], g["rand_draws"][t], cfg["HEADWAY_TIME"])
+        got = fn(st, t, g["act"][t], g["rand_draws"][t], cfg["HEADWAY_TIME"])
         assert got == want, (t, [int(x) for x in g["act"][t, :n]], got, want)
         replaced += int(want != [int(x) for x in g["act"][t, :n]])
     assert replaced >= 100
