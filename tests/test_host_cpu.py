@@ -387,3 +387,62 @@ def test_mappo_update_matches_one_reference_train_step():
             assert np.abs(v.numpy() - want).max() < 2e-6, (name, k)
             moved = max(moved, float(np.abs(want - g["%s_%s" % (name, k.replace(".", "_"))]).max()))
         assert moved > 1e-3, name
+
+
+@pytest.mark.parametrize("name", ["priority_v0_td3_mixed", "dmc_v0_td3_mixed"])
+def test_supervisor_core_matches_reference_fixtures(name, tmp_path):
+    """csrc/supervisor_core.h - the priority / dmc supervisors as host+device code, the source the supervisor kernels
+    will compile - built for the host and run on every step of the reference fixtures: the supervised tuple must be the
+    one the reference handed to _simulate.  (The kernels are not wired up yet; this pins their logic on the CPU.)"""
+    import oracle as orc
+    g, cfg = load_golden(name)
+    src = os.path.join(ROOT, "marl-mass_b200", "csrc", "supervisor_host.cpp")
+    lib_path = str(tmp_path / "libsupervisor_host.so")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", src, "-o", lib_path])
+    lib = ctypes.CDLL(lib_path)
+    dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
+    lib.mm_supervisor_host.argtypes = [ctypes.c_int] * 3 + [dp] * 5 + [ip] * 5 + [dp, ctypes.c_double]
+    rows = g["row_of_step"]
+    st = orc.state_from_golden(g, rows)
+    kind = 0 if cfg["safety_guarantee"] == "priority" else 1
+    replaced = 0
+    for t in range(len(rows)):
+        n, n_cav = int(st["n_veh"][t]), int(st["n_cav"][t])
+        f = lambda k: np.ascontiguousarray(st[k][t, :n], np.float64)
+        i = lambda k: np.ascontiguousarray(st[k][t, :n], np.int32)
+        arrs = [f("x"), f("y"), f("heading"), f("speed"), f("target_speed"), i("lane"), i("target_lane"), i("speed_index"),
+                i("crashed")]
+        act = np.ascontiguousarray(g["act"][t, :n_cav], np.int32)
+        draws = np.ascontiguousarray(np.nan_to_num(g["rand_draws"][t]), np.float64)
+        rc = lib.mm_supervisor_host(kind, n, n_cav, *[a.ctypes.data_as(dp if a.dtype == np.float64 else ip) for a in arrs],
+                                    act.ctypes.data_as(ip), draws.ctypes.data_as(dp), float(cfg["HEADWAY_TIME"]))
+        assert rc == 0
+        want = g["new_act"][t, :n_cav].astype(np.int32)
+        assert np.array_equal(act, want), (t, g["act"][t, :n_cav].tolist(), act.tolist(), want.tolist())
+        replaced += int(not np.array_equal(want, g["act"][t, :n_cav]))
+    assert replaced >= 100
+
+
+def test_supervisor_core_compiles_for_sm100a(tmp_path):
+    """The same header is device code: a thread-per-scene stub kernel around both supervisors compiles for sm_100a."""
+    import shutil
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    stub = tmp_path / "supervisor_stub.cu"
+    stub.write_text(r"""
+#include "supervisor_core.h"
+using namespace mmsup;
+__global__ void supervisor_stub(int kind, int n_scenes, const Veh *scenes, const int *n_veh, const int *n_cav, int *actions,
+                                const double *draws, double headway_time) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_scenes) return;
+    Veh road[MAXV];
+    const Veh *orig = scenes + (size_t)e * MAXV;
+    for (int i = 0; i < n_veh[e]; ++i) road[i] = orig[i];
+    if (kind == 0) priority_supervisor(road, orig, n_veh[e], n_cav[e], actions + e * MAXV, draws + e * 16, headway_time);
+    else dmc_supervisor(road, orig, n_veh[e], n_cav[e], actions + e * MAXV, draws + e * 16, headway_time);
+}
+""")
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-fmad=false", "-std=c++17",
+                           "-I", os.path.join(ROOT, "marl-mass_b200", "csrc"), "-c", str(stub), "-o", str(tmp_path / "stub.o")])
