@@ -6,7 +6,7 @@
 // written as plain functions over one scene so that the SAME source compiles for the host (g++, the CPU parity test
 // tests/test_host_cpu.py::test_supervisor_core_*) and for sm_100a (MM_HD = __host__ __device__ under nvcc).
 // State of play: logic verified on the CPU against the reference fixtures (every step of priority_v0_td3_mixed /
-// dmc_v0_td3_mixed, via oracle/supervisor.py's pinned restatement and directly); the kernel wrapper, the Philox draws of
+// dmc_v0_td3_mixed, through the host build of this header); the kernel wrapper, the Philox draws of
 // the batched mode and the GPU parity tests are the next step — until then make_mm_config keeps
 // rejecting safety_guarantee = priority | dmc.
 //
