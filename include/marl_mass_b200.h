@@ -199,6 +199,16 @@ int mm_discounted_returns(const float *rewards, const uint8_t *dones, const floa
  * an almost empty one, -27 % step time); 3 / 4: force one (process-wide; tests). */
 int mm_set_step_variant(int variant);
 
+/* EXPERIMENTAL - the baseline supervisors of env merge-multi-agent-v0 (safety_guarantee = priority | dmc:
+ * highway_env/vehicle/safety/central_layer.py:16-178, decentralised_dmc.py:70-198; called from AbstractEnv.step before
+ * _simulate, abstract.py:459-467).  Rewrites the meta-action tuples in place: actions [n_envs][MM_MAXV] int8 DEVICE;
+ * kind 0 = priority, 1 = dmc; draws [n_envs][MM_SUPERVISOR_DRAWS] f64 DEVICE = the uniform [0,1) numbers the reference
+ * takes from np.random.rand() (one per CAV, then two per IDM decision of the look-ahead).  The logic
+ * (csrc/supervisor_core.h) returns the reference's tuples when built for the host; this device entry point has not been
+ * verified on a GPU yet, nothing calls it from mm_step, and the config layer still rejects the two values. */
+#define MM_SUPERVISOR_DRAWS 32
+int mm_supervise(mm_env *env, int kind, int8_t *actions_dev, const double *draws_dev, void *stream);
+
 /* Launch bookkeeping for bench.py ("gpu_launches") */
 int64_t mm_kernel_launches(const mm_env *env);
 const char *mm_last_error(void);

@@ -64,10 +64,12 @@ class MMError(RuntimeError):
 
 _lib = None
 
+SUPERVISOR_DRAWS = 32     # MM_SUPERVISOR_DRAWS
 EXPORTS = ("mm_create", "mm_destroy", "mm_set_config", "mm_num_envs", "mm_reset", "mm_step", "mm_step_host",
            "mm_step_host_ragged",
            "mm_buffers_get", "mm_get_state", "mm_set_state", "mm_get_shield_diag", "mm_stats", "mm_shield_qp",
-           "mm_actor_sample", "mm_set_actor_impl", "mm_set_step_variant", "mm_discounted_returns", "mm_kernel_launches", "mm_last_error", "mm_version")
+           "mm_actor_sample", "mm_set_actor_impl", "mm_set_step_variant", "mm_discounted_returns", "mm_supervise",
+           "mm_kernel_launches", "mm_last_error", "mm_version")
 
 
 def lib():
@@ -104,6 +106,7 @@ def lib():
     L.mm_kernel_launches.restype = C.c_int64
     L.mm_last_error.restype = C.c_char_p
     L.mm_version.restype = C.c_char_p
+    L.mm_supervise.argtypes = [h, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     for name in EXPORTS:
         if name not in ("mm_kernel_launches", "mm_last_error", "mm_version"):
             getattr(L, name).restype = C.c_int

@@ -502,6 +502,21 @@ int mm_set_actor_impl(int impl) {
     return 0;
 }
 
+int mm_supervise(mm_env *env, int kind, int8_t *actions_dev, const double *draws_dev, void *stream) {
+    if (!env) return fail(MM_ERR_ARG, "env is null");
+    if (kind != 0 && kind != 1) return fail(MM_ERR_ARG, "kind must be 0 (priority) or 1 (dmc)");
+    if (!actions_dev || !draws_dev) return fail(MM_ERR_ARG, "actions and draws are required");
+    if (!env->cfg.env_v0) return fail(MM_ERR_ARG, "the supervisors belong to env merge-multi-agent-v0");
+    CUDA_OK(cudaSetDevice(env->device));
+    size_t stack = 0;
+    CUDA_OK(cudaDeviceGetLimit(&stack, cudaLimitStackSize));
+    if (stack < 32768) CUDA_OK(cudaDeviceSetLimit(cudaLimitStackSize, 32768));   // 17 KB frame: 2 x 12 x 18-point trajectories
+    launch_supervisor(env->st, env->n_envs, kind, actions_dev, draws_dev, MM_SUPERVISOR_DRAWS, env->cfg.headway_time, stream);
+    env->launches += 1;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int mm_set_step_variant(int variant) {
     if (variant != 0 && variant != 3 && variant != 4) return fail(MM_ERR_ARG, "variant must be 0 (automatic), 3 or 4");
     set_step_variant(variant);

@@ -150,9 +150,8 @@ MM_HD inline double idm_acceleration(const Veh *road, int self, int front) {
     const Veh &e = road[self];
     double acc = 3.0 * (1 - pow(fmax(e.speed, 0.0) / not_zero(e.target_speed), 4.0));
     if (front != -1) {
-        double fx = OBST_X, fy = OBST_Y, fh = 0.0, fs = 0.0;
-        if (front != OBSTACLE_ID) { fx = road[front].x; fy = road[front].y; fh = road[front].heading; fs = road[front].speed; }
-        (void)fy;
+        double fx = OBST_X, fh = 0.0, fs = 0.0;
+        if (front != OBSTACLE_ID) { fx = road[front].x; fh = road[front].heading; fs = road[front].speed; }
         double d = lane_s(e.lane, fx) - lane_s(e.lane, e.x);
         double ch = cos(e.heading), sh = sin(e.heading);
         double dv = (e.speed * ch - fs * cos(fh)) * ch + (e.speed * sh - fs * sin(fh)) * sh;

@@ -327,6 +327,25 @@ class MergeEnvBatched(object):
     def kernel_launches(self):
         return int(self._L.mm_kernel_launches(self._h))
 
+    def supervise(self, actions, kind, draws=None):
+        """EXPERIMENTAL (mm_supervise): the reference's baseline supervisors of env v0 - `priority`
+        (central_layer.py:16-178) or `dmc` (decentralised_dmc.py:70-198) - applied to the current scenes: returns the
+        action tuples the reference would hand to _simulate.  actions [E, 12] integer cuda tensor; draws [E, 32] float64
+        cuda = the uniform numbers the reference takes from np.random.rand() (default: torch.rand).  The logic is
+        verified on the CPU against the reference; this device entry point has not been verified on a GPU yet, step()
+        does not call it and make_mm_config still rejects safety_guarantee = priority | dmc."""
+        import torch
+        k = {"priority": 0, "dmc": 1}[kind]
+        dev = torch.device("cuda", self.device)
+        out = actions.to(device=dev, dtype=torch.int8).contiguous().clone()
+        if draws is None:
+            draws = torch.rand((self.n_envs, _lib.SUPERVISOR_DRAWS), dtype=torch.float64, device=dev)
+        draws = draws.to(device=dev, dtype=torch.float64).contiguous()
+        assert out.shape == (self.n_envs, MAXV) and draws.shape == (self.n_envs, _lib.SUPERVISOR_DRAWS)
+        _lib.check(self._L.mm_supervise(self._h, k, C.c_void_p(out.data_ptr()), C.c_void_p(draws.data_ptr()),
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return out
+
 
 def set_step_variant(variant=0):
     """0: automatic choice between the 3- and the 4-CTAs-per-SM build of the step kernel; 3 / 4: force one."""

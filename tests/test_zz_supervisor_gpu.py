@@ -1,0 +1,39 @@
+"""EXPERIMENTAL device entry point of the baseline supervisors (mm_supervise): first contact with a GPU.
+
+The supervisor logic (csrc/supervisor_core.h) is pinned on the CPU (tests/test_host_cpu.py::test_supervisor_core_*); its
+kernel wrapper was written after the round's GPU budget was spent, so these tests are non-strict xfail: a pass shows up
+as XPASS, a failure does not turn the suite red, and nothing in the product path depends on the outcome.  The file sorts
+last on purpose."""
+import numpy as np
+import pytest
+
+from conftest import SUPERVISED_CASES
+from helpers import load_golden
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="mm_supervise has not been verified on a GPU yet")]
+
+
+@pytest.mark.parametrize("name", SUPERVISED_CASES)
+def test_device_supervisor_reproduces_the_reference_tuples(name):
+    import torch
+    import marl_mass_b200 as mm
+    import oracle as orc
+    from test_gpu_parity import env_config
+    g, cfg = load_golden(name)
+    rows = g["row_of_step"]
+    T = len(rows)
+    env = mm.MergeEnvBatched(T, dict(env_config(cfg), safety_guarantee="none"))
+    try:
+        env.set_state(orc.state_from_golden(g, rows))
+        draws = np.zeros((T, 32))
+        draws[:, :16] = np.nan_to_num(g["rand_draws"])
+        got = env.supervise(torch.from_numpy(np.ascontiguousarray(g["act"])).cuda(), cfg["safety_guarantee"],
+                            torch.from_numpy(draws).cuda())
+        torch.cuda.synchronize()
+        got = got.cpu().numpy()
+        live = np.arange(12)[None, :] < g["st_n_cav"][rows][:, None]
+        bad = np.argwhere((got != g["new_act"]) & live)
+        assert len(bad) == 0, (len(bad), bad[:5].tolist())
+        assert np.array_equal(got[~live], g["act"][~live])
+    finally:
+        env.close()
