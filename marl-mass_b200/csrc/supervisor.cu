@@ -1,7 +1,8 @@
 // supervisor.cu — the baseline supervisors `priority` / `dmc` (central_layer.py, decentralised_dmc.py) on the device:
 // one thread per env loads its scene from the tiled state, runs supervisor_core.h and rewrites the env's action tuple.
-// EXPERIMENTAL: the logic is the host-verified source (tests/test_host_cpu.py::test_supervisor_core_*), this wrapper has
-// not run on a GPU yet; nothing in the step path calls it and the config layer still rejects the two values.
+// The logic is the host-verified source (tests/test_host_cpu.py::test_supervisor_core_*); on a B200 the kernel returns the
+// reference's tuples on every step of both fixtures (tests/test_zz_supervisor_gpu.py).  Nothing in the step path calls
+// it yet and the config layer still rejects the two values.
 #include <cuda_runtime.h>
 
 #include "mm_internal.h"

@@ -1,4 +1,4 @@
-// supervisor_core.h — the baseline supervisors `priority` / `dmc` as host+device code (NOT yet part of the product).
+// supervisor_core.h — the baseline supervisors `priority` / `dmc` as host+device code (mm_supervise; not yet called by step).
 //
 // What it is: the look-ahead action filters the reference runs once per policy step on env merge-multi-agent-v0
 // (highway_env/vehicle/safety/central_layer.py:16-178 `safety_supervisor`, decentralised_dmc.py:16-198
@@ -6,9 +6,9 @@
 // written as plain functions over one scene so that the SAME source compiles for the host (g++, the CPU parity test
 // tests/test_host_cpu.py::test_supervisor_core_*) and for sm_100a (MM_HD = __host__ __device__ under nvcc).
 // State of play: logic verified on the CPU against the reference fixtures (every step of priority_v0_td3_mixed /
-// dmc_v0_td3_mixed, through the host build of this header); the kernel wrapper, the Philox draws of
-// the batched mode and the GPU parity tests are the next step — until then make_mm_config keeps
-// rejecting safety_guarantee = priority | dmc.
+// dmc_v0_td3_mixed, through the host build of this header and through the kernel of supervisor.cu on a B200); calling it
+// from the step path, the draws of the batched mode and the seed-exact draws of the single-env adapter are the next step
+//  — until then make_mm_config keeps rejecting safety_guarantee = priority | dmc.
 //
 // Scene = up to 12 vehicles (CAVs first).  A supervisor is a pure function
 //     (scene, meta-action tuple, np.random.rand() draws in consumption order) -> supervised tuple.

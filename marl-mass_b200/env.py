@@ -331,9 +331,9 @@ class MergeEnvBatched(object):
         """EXPERIMENTAL (mm_supervise): the reference's baseline supervisors of env v0 - `priority`
         (central_layer.py:16-178) or `dmc` (decentralised_dmc.py:70-198) - applied to the current scenes: returns the
         action tuples the reference would hand to _simulate.  actions [E, 12] integer cuda tensor; draws [E, 32] float64
-        cuda = the uniform numbers the reference takes from np.random.rand() (default: torch.rand).  The logic is
-        verified on the CPU against the reference; this device entry point has not been verified on a GPU yet, step()
-        does not call it and make_mm_config still rejects safety_guarantee = priority | dmc."""
+        cuda = the uniform numbers the reference takes from np.random.rand() (default: torch.rand).  Reproduces
+        the reference's tuples on every step of the reference fixtures (tests/test_zz_supervisor_gpu.py); step() does
+        not call it yet and make_mm_config still rejects safety_guarantee = priority | dmc."""
         import torch
         k = {"priority": 0, "dmc": 1}[kind]
         dev = torch.device("cuda", self.device)

@@ -1,16 +1,16 @@
-"""EXPERIMENTAL device entry point of the baseline supervisors (mm_supervise): first contact with a GPU.
+"""Device entry point of the baseline supervisors (mm_supervise): the kernel wrapper around csrc/supervisor_core.h must
+return, for every step of the reference fixtures, the action tuple the reference's `safety_supervisor` /
+`safety_layer_dmc` handed to _simulate (same scenes, same policy tuples, same np.random.rand() draws).
 
-The supervisor logic (csrc/supervisor_core.h) is pinned on the CPU (tests/test_host_cpu.py::test_supervisor_core_*); its
-kernel wrapper was written after the round's GPU budget was spent, so these tests are non-strict xfail: a pass shows up
-as XPASS, a failure does not turn the suite red, and nothing in the product path depends on the outcome.  The file sorts
-last on purpose."""
+First run on a B200 at the very end of round 1 (both cases passed, 1 269 steps).  step() does not call the supervisors
+yet and make_mm_config still rejects safety_guarantee = priority | dmc: wiring them in is the next step."""
 import numpy as np
 import pytest
 
 from conftest import SUPERVISED_CASES
 from helpers import load_golden
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="mm_supervise has not been verified on a GPU yet")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name", SUPERVISED_CASES)
