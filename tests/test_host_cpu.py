@@ -446,3 +446,47 @@ __global__ void supervisor_stub(int kind, int n_scenes, const Veh *scenes, const
 """)
     subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-fmad=false", "-std=c++17",
                            "-I", os.path.join(ROOT, "marl-mass_b200", "csrc"), "-c", str(stub), "-o", str(tmp_path / "stub.o")])
+
+
+@pytest.mark.parametrize("kind,td", [("priority", 1), ("priority", 3), ("dmc", 2), ("dmc", 3)])
+def test_supervisor_core_agrees_with_the_python_restatement_on_fresh_scenes(kind, td, tmp_path):
+    """Two independent restatements of the supervisors (csrc/supervisor_core.h built for the host, the pure-Python
+    checker) on scenes the fixtures do not hold: other densities, random draws, scenes advanced by the un-shielded v0
+    dynamics under random actions."""
+    import marl_mass_b200 as mm
+    import oracle as orc
+    import supervisor as sup
+    src = os.path.join(ROOT, "marl-mass_b200", "csrc", "supervisor_host.cpp")
+    lib_path = str(tmp_path / "libsupervisor_host.so")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", src, "-o", lib_path])
+    lib = ctypes.CDLL(lib_path)
+    dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
+    lib.mm_supervisor_host.argtypes = [ctypes.c_int] * 3 + [dp] * 5 + [ip] * 5 + [dp, ctypes.c_double]
+    E = 24
+    cfg = dict(mm.DEFAULT_CONFIG, env_name="merge-multi-agent-v0", safety_guarantee="none", traffic_density=td,
+               traffic_type="mixed", mixed_traffic=True, HEADWAY_TIME=1.2)
+    st = mm.spawn.spawn_state(list(range(100, 100 + E)), td, "mixed")
+    ocfg = orc.make_config(cfg)
+    rng = np.random.RandomState(17 + td)
+    fn = sup.priority_supervisor if kind == "priority" else sup.dmc_supervisor
+    replaced = 0
+    for t in range(30):
+        a = rng.randint(0, 5, size=(E, 12)).astype(np.int8)
+        draws = rng.rand(E, 16)
+        for e in range(E):
+            n, n_cav = int(st["n_veh"][e]), int(st["n_cav"][e])
+            want = fn(st, e, a[e], draws[e], 1.2)
+            f = lambda k: np.ascontiguousarray(st[k][e, :n], np.float64)
+            i = lambda k: np.ascontiguousarray(st[k][e, :n], np.int32)
+            arrs = [f("x"), f("y"), f("heading"), f("speed"), f("target_speed"), i("lane"), i("target_lane"),
+                    i("speed_index"), i("crashed")]
+            act = np.ascontiguousarray(a[e, :n_cav], np.int32)
+            d = np.ascontiguousarray(draws[e])
+            assert lib.mm_supervisor_host(0 if kind == "priority" else 1, n, n_cav,
+                                          *[x.ctypes.data_as(dp if x.dtype == np.float64 else ip) for x in arrs],
+                                          act.ctypes.data_as(ip), d.ctypes.data_as(dp), 1.2) == 0
+            assert act.tolist() == want, (t, e, a[e, :n_cav].tolist(), act.tolist(), want)
+            replaced += int(want != a[e, :n_cav].tolist())
+            a[e, :n_cav] = act           # the env then executes the supervised tuple
+        orc.step(ocfg, st, a, n_threads=4)
+    assert replaced > 0 or td == 1       # sparse traffic rarely needs the supervisor this early in an episode
