@@ -333,7 +333,9 @@ class MergeEnvBatched(object):
         action tuples the reference would hand to _simulate.  actions [E, 12] integer cuda tensor; draws [E, 32] float64
         cuda = the uniform numbers the reference takes from np.random.rand() (default: torch.rand).  Reproduces
         the reference's tuples on every step of the reference fixtures (tests/test_zz_supervisor_gpu.py); step() does
-        not call it yet and make_mm_config still rejects safety_guarantee = priority | dmc."""
+        not call it yet and make_mm_config still rejects safety_guarantee = priority | dmc.  Until then the supervised
+        policy step of a batch on env v0 (safety_guarantee = "none") is the composition
+        `env.step(env.supervise(actions, kind))`, both halves of which are pinned on the reference fixtures."""
         import torch
         k = {"priority": 0, "dmc": 1}[kind]
         dev = torch.device("cuda", self.device)
