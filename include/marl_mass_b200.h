@@ -204,7 +204,8 @@ int mm_set_step_variant(int variant);
  * _simulate, abstract.py:459-467).  Rewrites the meta-action tuples in place: actions [n_envs][MM_MAXV] int8 DEVICE;
  * kind 0 = priority, 1 = dmc; draws [n_envs][MM_SUPERVISOR_DRAWS] f64 DEVICE = the uniform [0,1) numbers the reference
  * takes from np.random.rand() (one per CAV, then two per IDM decision of the look-ahead).  Returns the reference's
- * tuples on every step of the reference fixtures, built for the host and on a B200 (tests/test_zz_supervisor_gpu.py).
+ * tuples on every step of the reference fixtures, built for the host and (fully inlined build) on a B200
+ * (tests/test_zz_supervisor_gpu.py).
  * Not wired in yet: mm_step does not call it and the config layer still rejects the two values. */
 #define MM_SUPERVISOR_DRAWS 32
 int mm_supervise(mm_env *env, int kind, int8_t *actions_dev, const double *draws_dev, void *stream);

@@ -17,8 +17,11 @@
 
 #if defined(__CUDACC__)
 #define MM_HD __host__ __device__
+#define MM_HD_CALL __host__ __device__ __noinline__   // big helpers stay calls on the device: inlined everywhere, ptxas
+                                                      // needs ~9 minutes for the two supervisors
 #else
 #define MM_HD
+#define MM_HD_CALL
 #endif
 
 namespace mmsup {
@@ -114,7 +117,7 @@ MM_HD inline void bicycle(Veh &v, double steer, double acc) {
     push_traj(v);
 }
 // mdp_controller.py:19-66: the meta-action is re-applied on every look-ahead point, `lane` is never updated
-MM_HD inline void mdp_controller(Veh &v, int action) {
+MM_HD_CALL inline void mdp_controller(Veh &v, int action) {
     follow_road(v);
     if (action == A_FASTER) v.target_speed += 5;
     else if (action == A_SLOWER) v.target_speed -= 5;
@@ -161,7 +164,7 @@ MM_HD inline double idm_acceleration(const Veh *road, int self, int front) {
     return acc;
 }
 // idm_controller.py:60-79 (mobil's gain is identically 0 in the look-ahead: no lane change is ever started there)
-MM_HD inline void generate_actions(Veh *road, int n, int self, double draw_steer, double draw_acc) {
+MM_HD_CALL inline void generate_actions(Veh *road, int n, int self, double draw_steer, double draw_acc) {
     Veh &v = road[self];
     int front = front_on_own_lane(road, n, self);
     follow_road(v);
@@ -169,7 +172,7 @@ MM_HD inline void generate_actions(Veh *road, int n, int self, double draw_steer
     v.steer = clipd(steering_control(steer_lane, v) * (draw_steer * 0.1 + 0.95), -MAX_STEER, MAX_STEER);
     v.acc = clipd(idm_acceleration(road, self, front) * (draw_acc * 0.1 + 0.95), -6.0, 6.0);
 }
-MM_HD inline void idm_controller(Veh &v) {
+MM_HD_CALL inline void idm_controller(Veh &v) {
     if (v.crashed) { push_traj(v); return; }
     clip_actions(v.steer, v.acc, v.speed, false);
     bicycle(v, v.steer, v.acc);
@@ -196,7 +199,7 @@ MM_HD inline void surrounding(const Veh *road, int n, int self, int lane, int &f
     }
 }
 // (v_fl, v_rl, v_fr, v_rr), central_layer.py:84-110 / decentralised_dmc.py:139-168
-MM_HD inline void neighbour_sets(const Veh *road, int n, int self, int nb[4]) {
+MM_HD_CALL inline void neighbour_sets(const Veh *road, int n, int self, int nb[4]) {
     const Veh &v = road[self];
     int fl = -1, rl = -1, fr = -1, rr = -1;
     if (lane_main(v.lane)) {
@@ -225,7 +228,7 @@ MM_HD inline bool has_corner_inside(double c1x, double c1y, double l1, double w1
         if (point_in_rotated_rectangle(c1x + c * px[k] - s * py[k], c1y + s * px[k] + c * py[k], c2x, c2y, l2, w2, a2)) return true;
     return false;
 }
-MM_HD inline bool is_colliding(const Veh &v, double ox, double oy, double oh, double olen, double owid) {
+MM_HD_CALL inline bool is_colliding(const Veh &v, double ox, double oy, double oh, double olen, double owid) {
     if (hypot(ox - v.x, oy - v.y) > VLEN) return false;
     return has_corner_inside(v.x, v.y, 0.9 * VLEN, 0.9 * VWID, v.heading, ox, oy, 0.9 * olen, 0.9 * owid, oh) ||
            has_corner_inside(ox, oy, 0.9 * olen, 0.9 * owid, oh, v.x, v.y, 0.9 * VLEN, 0.9 * VWID, v.heading);
@@ -247,7 +250,7 @@ MM_HD inline int available_actions(const Veh &v, int acts[5]) {
 }
 // abstract.py:242-280: `c` keeps being stepped across calls; only its first NPTS trajectory points are ever read.
 // nb = (v_fl, *, v_fr, *) in positions 0 and 2 for both supervisors
-MM_HD inline double check_safety_room(Veh &c, int action, const Veh *road, const int nb[4], int time_steps) {
+MM_HD_CALL inline double check_safety_room(Veh &c, int action, const Veh *road, const int nb[4], int time_steps) {
     double best = 0;
     for (int t = 0; t <= time_steps; ++t) {
         mdp_controller(c, action);
@@ -277,7 +280,7 @@ MM_HD inline double headway_distance(const Veh *road, int n, int self) {
     return headway;
 }
 // central_layer.py:33-63 / decentralised_dmc.py:88-117: CAV indices by ascending priority number (PriorityQueue)
-MM_HD inline void priority_order(const Veh *road, int n, int n_cav, const double *draws, double headway_time, int order[MAXV]) {
+MM_HD_CALL inline void priority_order(const Veh *road, int n, int n_cav, const double *draws, double headway_time, int order[MAXV]) {
     double key[MAXV];
     for (int i = 0; i < n_cav; ++i) {
         const Veh &v = road[i];
@@ -293,7 +296,7 @@ MM_HD inline void priority_order(const Veh *road, int n, int n_cav, const double
 }
 
 // the collision test of one look-ahead point (abstract.py:721-755 for the four neighbours, then the obstacle)
-MM_HD inline void collide_at(Veh *road, int self, const int nb[4], int t) {
+MM_HD_CALL inline void collide_at(Veh *road, int self, const int nb[4], int t) {
     Veh &v = road[self];
     for (int q = 0; q < 4; ++q) {
         int o = nb[q];
