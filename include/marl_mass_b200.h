@@ -41,7 +41,15 @@ enum { MM_ACT_LEAD = 1, MM_ACT_UPPER = 2, MM_ACT_LOWER = 4, MM_ACT_ADJ = 8, MM_A
 
 /* Replaces: env.config[...] keys set by run_mappo.py:145-171 and the class globals CBFType.GAMMA_B / TAU
  * (run_mappo.py:137-139).  As in the reference, a changed config is picked up by the next reset. */
+/* ABI guard: MM_ABI_VERSION changes whenever a struct of this header changes layout or an entry point changes its
+ * signature; mm_abi_version() returns the value the library was built with, and mm_create / mm_set_config reject a
+ * config whose struct_size field is not sizeof(mm_config) (a binding built against another revision of the header
+ * fails loudly instead of handing the library garbage). */
+#define MM_ABI_VERSION 3
+int mm_abi_version(void);
+
 typedef struct {
+    int32_t struct_size;     /* = sizeof(mm_config), set by the caller (ABI guard) */
     int32_t shield;          /* safety_guarantee: none -> NONE; cbf-avs_cint|hss|av|avs -> HSS; cbf-cav|mass -> MASS */
     int32_t reward_kind;     /* agent_reward: default | srew | mrew */
     int32_t traffic_density; /* 1..3 (merge_env_v1.py:180-211) */
@@ -193,11 +201,18 @@ int mm_set_actor_impl(int impl);
 int mm_discounted_returns(const float *rewards, const uint8_t *dones, const float *final_value, float gamma, int T,
                           int64_t n_cols, int cols_per_env, float *out, void *stream);
 
-/* The step kernel exists in two builds: 3 CTAs per SM (6 staged fields, 168 registers; the faster one per unit of
- * work) and 4 CTAs per SM (4 staged fields, 128 registers).  0 (default): automatic - the second build is used for
- * small grids whose wave structure favours it (e.g. 65 536 envs = 512 CTAs on 148 SMs: one wave instead of a full and
- * an almost empty one, -27 % step time); 3 / 4: force one (process-wide; tests). */
+/* The step kernel (the physics of a policy step) exists in several builds of one source: generic for 3 CTAs per SM
+ * (6 staged fields, 168 registers; the faster one per unit of work), generic for 4 CTAs per SM (4 staged fields, 128
+ * registers), and two builds specialised at compile time for all-CAV envs of env id merge-multi-agent-v1 with
+ * lateral_control "steer" under the MASS / the HSS shield (no IDM / MOBIL code, configuration reads folded to constants).
+ * 0 (default): automatic - a specialised build when the handle's config matches and none of its envs can hold an HDV
+ * (spawned under traffic_type cav, or checked by mm_set_state); the 4-CTA build for small grids whose wave structure
+ * favours it (e.g. 65 536 envs = 512 CTAs on 148 SMs: one wave instead of a full and an almost empty one, -27 % step
+ * time).  3 / 4: force a generic build; 5: automatic among the generic builds only (process-wide; tests). */
 int mm_set_step_variant(int variant);
+enum { MM_BUILD_GENERIC3 = 3, MM_BUILD_GENERIC4 = 4, MM_BUILD_SPEC_HSS = 31, MM_BUILD_SPEC_MASS = 32 };
+/* which build the handle's last mm_step / mm_step_host* launched (0 before the first step) */
+int mm_step_build(const mm_env *env);
 
 /* EXPERIMENTAL - the baseline supervisors of env merge-multi-agent-v0 (safety_guarantee = priority | dmc:
  * highway_env/vehicle/safety/central_layer.py:16-178, decentralised_dmc.py:70-198; called from AbstractEnv.step before

@@ -28,13 +28,22 @@ _PU8 = C.POINTER(C.c_uint8)
 _PI8 = C.POINTER(C.c_int8)
 
 
+ABI_VERSION = 3           # MM_ABI_VERSION of the header this binding was written against
+
+
 class MMConfig(C.Structure):
-    _fields_ = [("shield", C.c_int32), ("reward_kind", C.c_int32), ("traffic_density", C.c_int32),
+    """mm_config; struct_size is filled in by __init__ (the library's ABI guard checks it)."""
+    _fields_ = [("struct_size", C.c_int32), ("shield", C.c_int32), ("reward_kind", C.c_int32), ("traffic_density", C.c_int32),
                 ("traffic_type", C.c_int32), ("duration_steps", C.c_int32), ("substeps", C.c_int32),
                 ("dt", C.c_double), ("eta", C.c_double), ("tau", C.c_double),
                 ("collision_reward", C.c_double), ("high_speed_reward", C.c_double), ("headway_cost", C.c_double),
                 ("headway_time", C.c_double), ("merging_lane_cost", C.c_double), ("env_v0", C.c_int32),
                 ("steer_vel", C.c_int32), ("couple_counts", C.c_int32), ("env_hdv", C.c_int32)]
+
+
+    def __init__(self, *args, **kw):
+        super().__init__(*args, **kw)
+        self.struct_size = C.sizeof(MMConfig)
 
 
 class MMStateHost(C.Structure):
@@ -68,7 +77,7 @@ SUPERVISOR_DRAWS = 32     # MM_SUPERVISOR_DRAWS
 EXPORTS = ("mm_create", "mm_destroy", "mm_set_config", "mm_num_envs", "mm_reset", "mm_step", "mm_step_host",
            "mm_step_host_ragged",
            "mm_buffers_get", "mm_get_state", "mm_set_state", "mm_get_shield_diag", "mm_stats", "mm_shield_qp",
-           "mm_actor_sample", "mm_set_actor_impl", "mm_set_step_variant", "mm_discounted_returns", "mm_supervise",
+           "mm_actor_sample", "mm_set_actor_impl", "mm_set_step_variant", "mm_step_build", "mm_abi_version", "mm_discounted_returns", "mm_supervise",
            "mm_kernel_launches", "mm_last_error", "mm_version")
 
 
@@ -81,6 +90,10 @@ def lib():
         raise MMError("CUDA library %s is missing; run `python -m marl_mass_b200.build` "
                       "(there is no CPU fallback)" % LIB_PATH)
     L = C.CDLL(LIB_PATH)
+    L.mm_abi_version.restype = C.c_int
+    if L.mm_abi_version() != ABI_VERSION:
+        raise MMError("%s was built with MM_ABI_VERSION %d, this binding expects %d: rebuild with "
+                      "`python -m marl_mass_b200.build`" % (LIB_PATH, L.mm_abi_version(), ABI_VERSION))
     h = C.c_void_p
     L.mm_create.argtypes = [C.POINTER(MMConfig), C.c_int, C.c_int, C.c_int, C.POINTER(h)]
     L.mm_destroy.argtypes = [h]
@@ -100,6 +113,7 @@ def lib():
                                  [C.c_void_p] * 5
     L.mm_set_actor_impl.argtypes = [C.c_int]
     L.mm_set_step_variant.argtypes = [C.c_int]
+    L.mm_step_build.argtypes = [h]
     L.mm_discounted_returns.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int64, C.c_int,
                                         C.c_void_p, C.c_void_p]
     L.mm_kernel_launches.argtypes = [h]

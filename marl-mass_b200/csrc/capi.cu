@@ -50,9 +50,18 @@ struct mm_env {
     float *rows_stage = nullptr;
     int64_t *chunk_rows_dev = nullptr, *chunk_rows_host = nullptr;
     cudaEvent_t chunk_done[MAX_HOST_CHUNKS]{};
+    bool ragged_ready = false;
     size_t stats_rows = 0;
     uint64_t seed = 0;
     int64_t launches = 0;
+    // true while some env may hold an HDV (spawned under a traffic_type other than cav, or put there by mm_set_state):
+    // the step kernel's all-CAV builds are used only when this is false
+    bool hdv_possible = true;
+    int last_build = 0;       // MM_BUILD_* of the step kernel the last step launched
+    // the stream the caller last enqueued work of this handle on, and an event to order the internal streams of the
+    // *_host entry points after that work
+    cudaStream_t last_stream = nullptr;
+    cudaEvent_t caller_done = nullptr;
     cudaStream_t streams[MAX_CHUNKS]{};
     int n_streams = 0;
     std::vector<void *> allocs;
@@ -72,6 +81,9 @@ int dev_alloc(mm_env *env, T **ptr, size_t count, bool zero = true) {
 
 int validate(const mm_config *c) {
     if (!c) return fail(MM_ERR_ARG, "config is null");
+    if (c->struct_size != (int32_t)sizeof(mm_config))
+        return fail(MM_ERR_ARG, "mm_config.struct_size does not match this library's sizeof(mm_config): the binding was "
+                                "built against another revision of marl_mass_b200.h (see mm_abi_version)");
     if (c->shield < MM_SHIELD_NONE || c->shield > MM_SHIELD_MASS) return fail(MM_ERR_ARG, "Undefined safety_type");
     if (c->reward_kind < MM_REW_DEFAULT || c->reward_kind > MM_REW_MREW) return fail(MM_ERR_ARG, "unknown agent_reward");
     if (c->traffic_density < 1 || c->traffic_density > 3) return fail(MM_ERR_ARG, "traffic_density must be 1, 2 or 3");
@@ -94,6 +106,7 @@ StepParams step_params(mm_env *env, const int8_t *actions, int off, int count) {
     p.env_offset = off;
     p.env_count = count;
     p.obs_mask = nullptr;
+    p.all_cav = env->hdv_possible ? 0 : 1;
     return p;
 }
 
@@ -120,11 +133,22 @@ int host_chunk_target(int n_envs) {
     return t;
 }
 
+// The *_host entry points run on the handle's own non-blocking streams.  Work the caller enqueued earlier (mm_reset,
+// mm_step, a masked reset on its own stream) must be complete before they touch the state: order every internal stream
+// after the last caller stream this handle saw.
+int order_after_caller(mm_env *env, int n_str) {
+    CUDA_OK(cudaEventRecord(env->caller_done, env->last_stream));
+    for (int c = 0; c < n_str; ++c) CUDA_OK(cudaStreamWaitEvent(env->streams[c], env->caller_done, 0));
+    return 0;
+}
+
 // enqueue one policy step (+ optional re-spawn of finished envs) for envs [off, off+count) on `stream`
 void enqueue_step(mm_env *env, const int8_t *actions_dev, int auto_reset, int off, int count, cudaStream_t stream) {
+    if (auto_reset && env->cfg.traffic_type != MM_TRAFFIC_CAV) env->hdv_possible = true;
     StepParams p = step_params(env, actions_dev, off, count);
-    launch_step(p, env->record_diag != 0, stream);
-    env->launches += 1;
+    env->last_build = launch_step(p, env->record_diag != 0, stream);      // physics of the policy step (state -> state)
+    launch_outputs(p, true, stream);                    // observations, rewards, flags, info, statistics
+    env->launches += 2;
     if (auto_reset) {
         ResetParams r{};
         r.st = env->st; r.out = env->out; r.mask = nullptr; r.cfg = env->cfg; r.seed = env->seed;
@@ -142,7 +166,8 @@ void enqueue_step(mm_env *env, const int8_t *actions_dev, int auto_reset, int of
 extern "C" {
 
 const char *mm_last_error(void) { return g_last_error.c_str(); }
-const char *mm_version(void) { return "marl-mass_b200 0.1 (sm_100a, f64 core)"; }
+const char *mm_version(void) { return "marl-mass_b200 0.2 (sm_100a, f64 core)"; }
+int mm_abi_version(void) { return MM_ABI_VERSION; }
 
 int mm_create(const mm_config *cfg, int n_envs, int device, int record_diag, mm_env **out) {
     if (!out) return fail(MM_ERR_ARG, "out is null");
@@ -185,6 +210,10 @@ int mm_create(const mm_config *cfg, int n_envs, int device, int record_diag, mm_
         cudaError_t ce = cudaStreamCreateWithFlags(&env->streams[i], cudaStreamNonBlocking);
         if (ce != cudaSuccess) { mm_destroy(env); return fail(MM_ERR_CUDA, "cudaStreamCreate", ce); }
     }
+    {
+        cudaError_t ce = cudaEventCreateWithFlags(&env->caller_done, cudaEventDisableTiming);
+        if (ce != cudaSuccess) { mm_destroy(env); return fail(MM_ERR_CUDA, "cudaEventCreate", ce); }
+    }
     *out = env;
     return 0;
 }
@@ -197,6 +226,7 @@ int mm_destroy(mm_env *env) {
         if (env->streams[i]) cudaStreamDestroy(env->streams[i]);
     for (int i = 0; i < MAX_HOST_CHUNKS; ++i)
         if (env->chunk_done[i]) cudaEventDestroy(env->chunk_done[i]);
+    if (env->caller_done) cudaEventDestroy(env->caller_done);
     if (env->chunk_rows_host) cudaFreeHost(env->chunk_rows_host);
     for (void *p : env->allocs) cudaFree(p);
     delete env;
@@ -211,6 +241,7 @@ int mm_set_config(mm_env *env, const mm_config *cfg) {
 }
 
 int mm_num_envs(const mm_env *env) { return env ? env->n_envs : 0; }
+int mm_step_build(const mm_env *env) { return env ? env->last_build : 0; }
 int64_t mm_kernel_launches(const mm_env *env) { return env ? env->launches : 0; }
 
 int mm_reset(mm_env *env, uint64_t seed, const uint8_t *mask_dev, int num_cav, void *stream) {
@@ -218,6 +249,9 @@ int mm_reset(mm_env *env, uint64_t seed, const uint8_t *mask_dev, int num_cav, v
     if (num_cav < 0 || num_cav > 11) return fail(MM_ERR_ARG, "num_cav must be in 0..11");
     CUDA_OK(cudaSetDevice(env->device));
     env->seed = seed;
+    env->last_stream = (cudaStream_t)stream;
+    if (env->cfg.traffic_type != MM_TRAFFIC_CAV) env->hdv_possible = true;
+    else if (!mask_dev) env->hdv_possible = false;      // every env re-spawned all-CAV
     ResetParams r{};
     r.st = env->st; r.out = env->out; r.mask = mask_dev; r.cfg = env->cfg; r.seed = seed;
     r.n_envs = env->n_envs; r.env_offset = 0; r.env_count = env->n_envs; r.num_cav = num_cav; r.use_done = 0;
@@ -233,6 +267,7 @@ int mm_reset(mm_env *env, uint64_t seed, const uint8_t *mask_dev, int num_cav, v
 int mm_step(mm_env *env, const int8_t *actions_dev, int auto_reset, void *stream) {
     if (!env) return fail(MM_ERR_ARG, "env is null");
     CUDA_OK(cudaSetDevice(env->device));
+    env->last_stream = (cudaStream_t)stream;
     enqueue_step(env, actions_dev ? actions_dev : env->actions, auto_reset, 0, env->n_envs, (cudaStream_t)stream);
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -251,6 +286,7 @@ int mm_step_host(mm_env *env, const int8_t *actions, int auto_reset, float *obs,
     int n_chunks = (E + chunk_target - 1) / chunk_target;
     if (n_chunks < 1) n_chunks = 1;
     int chunk = ((E + n_chunks - 1) / n_chunks + 767) / 768 * 768;   // multiple of every supported tile size (32..384)
+    if (int rc = order_after_caller(env, n_str)) return rc;
     for (int c = 0; c < n_chunks; ++c) {
         int off = c * chunk;
         if (off >= E) break;
@@ -283,20 +319,32 @@ int mm_step_host_ragged(mm_env *env, const int8_t *actions, int auto_reset, floa
     if (!actions || !obs_rows || !row_offset) return fail(MM_ERR_ARG, "actions, obs_rows and row_offset are required");
     CUDA_OK(cudaSetDevice(env->device));
     const int E = env->n_envs;
-    if (!env->row_offset) {   // first use: staging for the packed rows, offsets, per-chunk counts, events
+    if (!env->ragged_ready) {   // first use: staging for the packed rows, offsets, per-chunk counts, events
+        // every piece is kept as soon as it exists, and the block is marked done only when all of them do: a failure
+        // half-way leaves a handle that retries the missing pieces on the next call instead of using null pointers
         void *p = nullptr;
-        CUDA_OK(cudaMalloc(&p, ((size_t)E + 1) * sizeof(int64_t)));
-        env->allocs.push_back(p);
-        env->row_offset = static_cast<int64_t *>(p);
-        CUDA_OK(cudaMalloc(&p, (size_t)E * MAXV * NS * sizeof(float)));
-        env->allocs.push_back(p);
-        env->rows_stage = static_cast<float *>(p);
-        CUDA_OK(cudaMalloc(&p, MAX_HOST_CHUNKS * sizeof(int64_t)));
-        env->allocs.push_back(p);
-        env->chunk_rows_dev = static_cast<int64_t *>(p);
-        CUDA_OK(cudaHostAlloc(&p, MAX_HOST_CHUNKS * sizeof(int64_t), cudaHostAllocDefault));
-        env->chunk_rows_host = static_cast<int64_t *>(p);
-        for (int c = 0; c < MAX_HOST_CHUNKS; ++c) CUDA_OK(cudaEventCreateWithFlags(&env->chunk_done[c], cudaEventDisableTiming));
+        if (!env->row_offset) {
+            CUDA_OK(cudaMalloc(&p, ((size_t)E + 1) * sizeof(int64_t)));
+            env->allocs.push_back(p);
+            env->row_offset = static_cast<int64_t *>(p);
+        }
+        if (!env->rows_stage) {
+            CUDA_OK(cudaMalloc(&p, (size_t)E * MAXV * NS * sizeof(float)));
+            env->allocs.push_back(p);
+            env->rows_stage = static_cast<float *>(p);
+        }
+        if (!env->chunk_rows_dev) {
+            CUDA_OK(cudaMalloc(&p, MAX_HOST_CHUNKS * sizeof(int64_t)));
+            env->allocs.push_back(p);
+            env->chunk_rows_dev = static_cast<int64_t *>(p);
+        }
+        if (!env->chunk_rows_host) {
+            CUDA_OK(cudaHostAlloc(&p, MAX_HOST_CHUNKS * sizeof(int64_t), cudaHostAllocDefault));
+            env->chunk_rows_host = static_cast<int64_t *>(p);
+        }
+        for (int c = 0; c < MAX_HOST_CHUNKS; ++c)
+            if (!env->chunk_done[c]) CUDA_OK(cudaEventCreateWithFlags(&env->chunk_done[c], cudaEventDisableTiming));
+        env->ragged_ready = true;
     }
     const int chunk_target = host_chunk_target(E);
     const int n_str = 4;
@@ -346,6 +394,7 @@ int mm_step_host_ragged(mm_env *env, const int8_t *actions, int auto_reset, floa
     };
     int used = 0;
     while (used < n_chunks && used * chunk < E) ++used;
+    if (int rc = order_after_caller(env, n_str)) return rc;
     for (int c = 0; c < used && c < n_str; ++c)
         if (int rc = enqueue_compute(c)) return rc;
     for (int c = 0; c < used; ++c) {
@@ -419,6 +468,10 @@ int mm_set_state(mm_env *env, const mm_state_host *src) {
                 return fail(MM_ERR_STATE, "mm_set_state: slots [0,n_cav) must be CAVs and [n_cav,n_veh) HDVs");
         }
     }
+    bool any_hdv = false;
+    for (size_t e = 0; e < E; ++e) any_hdv = any_hdv || ed[1][e] < ed[0][e];
+    env->hdv_possible = any_hdv;
+    env->last_stream = nullptr;
     double *f64 = nullptr; int32_t *i32 = nullptr, *envv = nullptr;
     CUDA_OK(cudaMalloc(&f64, HOST_F64 * P * sizeof(double)));
     CUDA_OK(cudaMalloc(&i32, HOST_I32 * P * sizeof(int32_t)));
@@ -510,6 +563,7 @@ int mm_supervise(mm_env *env, int kind, int8_t *actions_dev, const double *draws
     CUDA_OK(cudaSetDevice(env->device));
     size_t stack = 0;
     CUDA_OK(cudaDeviceGetLimit(&stack, cudaLimitStackSize));
+    env->last_stream = (cudaStream_t)stream;
     if (stack < 32768) CUDA_OK(cudaDeviceSetLimit(cudaLimitStackSize, 32768));   // 17 KB frame: 2 x 12 x 18-point trajectories
     launch_supervisor(env->st, env->n_envs, kind, actions_dev, draws_dev, MM_SUPERVISOR_DRAWS, env->cfg.headway_time, stream);
     env->launches += 1;
@@ -518,7 +572,8 @@ int mm_supervise(mm_env *env, int kind, int8_t *actions_dev, const double *draws
 }
 
 int mm_set_step_variant(int variant) {
-    if (variant != 0 && variant != 3 && variant != 4) return fail(MM_ERR_ARG, "variant must be 0 (automatic), 3 or 4");
+    if (variant != 0 && variant != 3 && variant != 4 && variant != 5)
+        return fail(MM_ERR_ARG, "variant must be 0 (automatic), 3, 4 (a generic build forced) or 5 (automatic, generic builds only)");
     set_step_variant(variant);
     return 0;
 }

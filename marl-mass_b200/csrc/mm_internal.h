@@ -23,6 +23,7 @@ constexpr int NS = MM_NS;
 #define MM_TILE 128
 #endif
 constexpr int TILE = MM_TILE;   // envs per tile == threads per CTA of the step kernel
+#define MM_MAX_DEVICES 64        // per-device one-time setup tables (function attributes)
 
 enum F64Field {
     F_X = 0, F_Y, F_H, F_V,          // position, heading, speed            (staged in shared memory)
@@ -84,7 +85,8 @@ struct StepParams {
     int n_envs;
     int env_offset;          // first env of this launch (chunked host path)
     int env_count;           // envs in this launch
-    const uint8_t *obs_mask; // observe_kernel: refresh only envs whose mask byte is set (null: all)
+    const uint8_t *obs_mask; // outputs kernel without rewards: refresh only envs whose mask byte is set (null: all)
+    int all_cav;             // host-side knowledge: no env of the handle can hold an HDV (enables the specialised builds)
 };
 
 struct ResetParams {
@@ -97,12 +99,19 @@ struct ResetParams {
 };
 
 // launchers (merge_step.cu)
-void launch_step(const StepParams &p, bool diag, void *stream);
+int launch_step(const StepParams &p, bool diag, void *stream);   // returns the MM_BUILD_* it launched
 // the same kernel compiled for 4 CTAs per SM (merge_step_occ4.cu): picked when that makes the grid a single wave
 void launch_step_occ4(const StepParams &p, bool diag, void *stream);
-void set_step_variant(int v);   // 0: automatic, 3 / 4: force the 3- or 4-CTAs-per-SM build
+// the same kernel specialised at compile time for all-CAV envs of the plain LC env (merge_step_spec_mass.cu / _hss.cu)
+void launch_step_spec_mass(const StepParams &p, bool diag, void *stream);
+void launch_step_spec_hss(const StepParams &p, bool diag, void *stream);
+void set_step_variant(int v);   // 0: automatic, 3 / 4: force the generic 3- or 4-CTAs-per-SM build, 5: automatic without the specialised builds
 void launch_reset(const ResetParams &p, void *stream);
-void launch_observe(const StepParams &p, void *stream);
+// outputs kernel (merge_outputs.cu): observations, rewards, terminal flags, info scalars and statistics of the policy step
+// the physics kernel has just advanced (with_rewards), or the first observation after a (re)spawn / set_state (!with_rewards,
+// optionally only for envs whose p.obs_mask byte is set)
+void launch_outputs(const StepParams &p, bool with_rewards, void *stream);
+inline void launch_observe(const StepParams &p, void *stream) { launch_outputs(p, false, stream); }
 void launch_pack_state(const DevState &st, int n_envs, const double *f64_em /*[17][E][MAXV]*/,
                        const int32_t *i32_em /*[11][E][MAXV]*/, const int32_t *env_em /*[5][E]*/, void *stream);
 void launch_unpack_state(const DevState &st, int n_envs, double *f64_em, int32_t *i32_em, int32_t *env_em,

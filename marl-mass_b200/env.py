@@ -327,6 +327,11 @@ class MergeEnvBatched(object):
     def kernel_launches(self):
         return int(self._L.mm_kernel_launches(self._h))
 
+    def step_build(self):
+        """Which build of the step kernel the last step launched (marl_mass_b200.h MM_BUILD_*: 3 / 4 generic, 31 / 32
+        specialised for all-CAV envs under HSS / MASS)."""
+        return int(self._L.mm_step_build(self._h))
+
     def supervise(self, actions, kind, draws=None):
         """EXPERIMENTAL (mm_supervise): the reference's baseline supervisors of env v0 - `priority`
         (central_layer.py:16-178) or `dmc` (decentralised_dmc.py:70-198) - applied to the current scenes: returns the
@@ -350,7 +355,8 @@ class MergeEnvBatched(object):
 
 
 def set_step_variant(variant=0):
-    """0: automatic choice between the 3- and the 4-CTAs-per-SM build of the step kernel; 3 / 4: force one."""
+    """0: automatic choice among the builds of the step kernel (marl_mass_b200.h mm_set_step_variant); 3 / 4: force a
+    generic build; 5: automatic among the generic builds only."""
     _lib.check(_lib.lib().mm_set_step_variant(int(variant)))
 
 

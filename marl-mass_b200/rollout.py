@@ -205,7 +205,11 @@ def actor_sample(actor, obs, n_agents=None, seed=0, step=0, want_logp=False, act
 class BatchedMAPPORollout(object):
     def __init__(self, env, actor=None, critic=None, roll_out_n_steps=100, reward_gamma=0.99, reward_scale=20.0,
                  reward_type="regionalR", clip_param=0.2, actor_lr=5e-4, critic_lr=5e-4, max_grad_norm=5.0, seed=0,
-                 fused=True):
+                 fused=True, obs=None, reset_seed=None):
+        """obs: the observation of an env the caller has already reset (train.py resets with a rank-distinct spawn
+        seed and hands its first observation over).  Without it the first collect() spawns the scenes itself with
+        `reset_seed` (default: derived from `seed`, which the data-parallel driver makes rank-distinct) - never with the
+        env's config seed, which is the same on every rank and would make the shards replicas of one another."""
         self.env = env
         dev = torch.device("cuda", env.device)
         self.actor = (actor or ActorNetwork()).to(dev)
@@ -220,7 +224,8 @@ class BatchedMAPPORollout(object):
         self.actor_opt = torch.optim.RMSprop(self.actor.parameters(), lr=actor_lr)   # mappo.py:88-90
         self.critic_opt = torch.optim.RMSprop(self.critic.parameters(), lr=critic_lr)
         self.dev = dev
-        self.obs = None
+        self.obs = obs
+        self.reset_seed = (0x5EED0000 + int(seed)) if reset_seed is None else int(reset_seed)
         E = env.n_envs
         self._slot = torch.arange(MAXV, device=dev)[None, :]
         self.buf = None
@@ -252,7 +257,7 @@ class BatchedMAPPORollout(object):
         env, E, T = self.env, self.E, self.T
         v = env.buffers()
         if self.obs is None:
-            self.obs, _ = env.reset()
+            self.obs, _ = env.reset(seed=self.reset_seed)
         S = torch.empty((T, E, MAXV, NS), device=self.dev)
         A = torch.empty((T, E, MAXV), dtype=torch.int64, device=self.dev)
         R = torch.empty((T, E, MAXV), device=self.dev)

@@ -66,12 +66,20 @@ def train(config, n_envs=4096, iterations=30, device=0, eval_interval=10, miniba
             dist.init_process_group("nccl", device_id=torch.device("cuda", device))
     torch.manual_seed(tr["torch_seed"])
     env = MergeEnvBatched(n_envs, dict(DEFAULT_CONFIG, **env_cfg), device=device)
-    env.reset(seed=mmd.rank_seed(env_cfg["seed"], rank) if world > 1 else env_cfg["seed"])
+    if env.n_s != 30:
+        # env ids merge-multi-agent-v0 / -v05 observe 5 x 5 (no heading column): the networks of this driver and the
+        # fused actor kernel are the reference's 30-input ones (Model_common.py:11-23 with n_s = 30)
+        env.close()
+        raise ValueError("train: env id %r has n_s = %d; the batched learner covers the n_s = 30 env ids "
+                         "(merge-multi-agent-v1)" % (env_cfg.get("env_name"), env.n_s))
+    # rank-distinct spawn stream; its first observation goes to the rollout so that collect() does not re-spawn the
+    # scenes with the (rank-independent) config seed
+    obs0, _ = env.reset(seed=mmd.rank_seed(env_cfg["seed"], rank) if world > 1 else env_cfg["seed"])
     if tr.get("shared_network"):
         pol = BatchedMAPPOGIRollout(env, hidden_size=tr.get("critic_hidden_size", 128),
-                                    seed=tr["torch_seed"] + 104729 * rank, **rollout_kw)
+                                    seed=tr["torch_seed"] + 104729 * rank, obs=obs0, **rollout_kw)
     else:
-        pol = BatchedMAPPORollout(env, seed=tr["torch_seed"] + 104729 * rank, **rollout_kw)
+        pol = BatchedMAPPORollout(env, seed=tr["torch_seed"] + 104729 * rank, obs=obs0, **rollout_kw)
     pol.sync_parameters()
     if rank != 0:
         log = lambda *_: None

@@ -168,6 +168,28 @@ def test_four_ctas_per_sm_build_of_the_step_kernel(mm, orc, shield, traffic, td,
         mm.set_step_variant(0)
 
 
+@pytest.mark.parametrize("shield,variant", [("cbf-cav", 3), ("cbf-avs_cint", 3), ("cbf-cav", 5)])
+def test_generic_builds_on_all_cav_scenes(mm, orc, shield, variant):
+    """All-CAV scenes under MASS / HSS run the compile-time specialised builds by default (asserted in
+    lockstep_rollout); the generic builds must compute the same step on them: the strict lock-step comparison with a
+    generic build forced (3: the 3-CTAs-per-SM build; 5: automatic choice among the generic builds)."""
+    try:
+        mm.set_step_variant(variant)
+        lockstep_rollout(mm, orc, shield, "cav", 3, "default", 4096, 40, STATE_TOL, expect_build=(3,))
+    finally:
+        mm.set_step_variant(0)
+
+
+@pytest.mark.parametrize("shield,traffic,td,reward", [
+    ("cbf-cav", "cav", 3, "default"), ("cbf-cav", "mixed", 3, "srew"), ("cbf-avs_cint", "mixed", 2, "default")])
+def test_teacher_forced_whole_episodes(mm, orc, shield, traffic, td, reward):
+    """Strict per-step parity over the WHOLE 100-step episode: after every policy step the device state is re-synced
+    from the oracle (teacher forcing), so nothing compounds and nothing needs excluding - the queues behind the
+    obstacle, (nearly) stopped vehicles and the terminal step are compared at the strict tolerance like every other
+    state: every discrete field, output and shield record exact, continuous state within 1e-9."""
+    lockstep_rollout(mm, orc, shield, traffic, td, reward, 2048, 100, STATE_TOL, resync=True)
+
+
 @pytest.mark.parametrize("shield,traffic,td,snap_y", [("cbf-cav", "cav", 3, False), ("cbf-avs_cint", "mixed", 3, False),
                                                       ("cbf-cav", "mixed", 2, True), ("none", "cav", 3, True)])
 def test_cuda_vs_oracle_scenes_with_exact_ties(mm, orc, shield, traffic, td, snap_y):
@@ -231,7 +253,7 @@ def tie_rollout(mm, orc, shield, traffic, td, snap_y=False):
     env.close()
 
 
-def lockstep_rollout(mm, orc, shield, traffic, td, reward, E, T, state_tol):
+def lockstep_rollout(mm, orc, shield, traffic, td, reward, E, T, state_tol, resync=False, expect_build=None):
     import torch
     lateral = "steer_vel" if shield.endswith("+steer_vel") else "steer"
     shield = shield.split("+")[0]
@@ -256,6 +278,11 @@ def lockstep_rollout(mm, orc, shield, traffic, td, reward, E, T, state_tol):
         got = outputs_to_numpy(v, OUT_F + OUT_I)
         post = env.get_state()
         diag = env.shield_diag()
+        if expect_build is not None:
+            assert env.step_build() in expect_build, env.step_build()
+        elif traffic == "cav" and lateral == "steer" and shield != "none":
+            # all-CAV scenes of the plain LC env: the specialised builds (31 HSS, 32 MASS) unless a test forces another
+            assert env.step_build() in (31, 32, 4), env.step_build()
         # compare only envs that had not finished before this step (finished envs are not stepped by MAPPO) and, in the
         # whole-episode runs, that are still well conditioned (see below)
         sel = np.where(alive & clean)[0]
@@ -264,6 +291,8 @@ def lockstep_rollout(mm, orc, shield, traffic, td, reward, E, T, state_tol):
         check_outputs(sub(got), sub({k: want[k] for k in OUT_F + OUT_I}), st["n_cav"][sel])
         check_shield(sub(diag), sub({k: want[k] for k in want if k.startswith("sh_")}), diag["lc_margin"][sel], state_tol)
         alive &= want["done"] == 0
+        if resync:
+            env.set_state(st)       # teacher forcing: the next step starts from the oracle's state on both sides
         if state_tol > STATE_TOL:
             # Free-running whole episodes: the steering law of a (nearly) stopped vehicle divides by not_zero(speed) =
             # +-0.01 twice, i.e. amplifies a 1e-16 difference in its lateral offset by ~1e5 and can flip the sign of the

@@ -25,6 +25,39 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     assert b"sm_100a" in L.mm_version()
 
 
+def test_mm_config_layout_agrees_between_header_binding_and_integration_stub():
+    """ABI drift guard: the mm_config struct of the header, the ctypes Structure of the product binding and the stub
+    INTEGRATION.md shows a reference maintainer must list the same fields in the same order with the same types; the
+    three copies of MM_ABI_VERSION agree; and the library refuses a config whose struct_size is not its own
+    (validation happens before any CUDA call, so this runs without a GPU)."""
+    import marl_mass_b200 as mm
+    from marl_mass_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "marl_mass_b200.h")).read()
+    body = re.search(r"typedef struct \{((?:(?!typedef struct).)*?)\} mm_config;", header, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    ctype = {"int32_t": ctypes.c_int32, "double": ctypes.c_double}
+    declared = []
+    for typ, names in re.findall(r"\b(int32_t|double)\s+([^;]+);", body):
+        declared += [(n.strip(), ctype[typ]) for n in names.split(",")]
+    assert declared[0][0] == "struct_size" and declared[-1][0] == "env_hdv" and len(declared) == 19
+    assert [(n, t) for n, t in _lib.MMConfig._fields_] == declared
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    stub = re.search(r"class MMConfig\(C\.Structure\):.*?_fields_ = \[(.*?)\]\n", doc, re.S).group(1)
+    stub_fields = [(n, getattr(ctypes, t)) for n, t in re.findall(r'\("(\w+)", C\.(c_\w+)\)', stub)]
+    assert stub_fields == declared
+    version = int(re.search(r"#define MM_ABI_VERSION (\d+)", header).group(1))
+    L = mm.lib()
+    assert L.mm_abi_version() == version == _lib.ABI_VERSION
+    assert "mm_abi_version() == %d" % version in doc
+    good = mm.make_mm_config(dict(mm.DEFAULT_CONFIG))
+    assert good.struct_size == ctypes.sizeof(_lib.MMConfig)
+    bad = mm.make_mm_config(dict(mm.DEFAULT_CONFIG))
+    bad.struct_size -= 4          # e.g. a binding written before env_hdv was appended
+    h = ctypes.c_void_p()
+    assert L.mm_create(ctypes.byref(bad), 16, 0, 0, ctypes.byref(h)) == -1 and not h
+    assert b"struct_size" in L.mm_last_error()
+
+
 def test_shared_object_is_sm100a_only():
     from marl_mass_b200 import _lib
     out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout

@@ -2,19 +2,16 @@
 return, for every step of the reference fixtures, the action tuple the reference's `safety_supervisor` /
 `safety_layer_dmc` handed to _simulate (same scenes, same policy tuples, same np.random.rand() draws).
 
-First run on a B200 at the very end of round 1: both cases passed (1 269 steps) with the build that inlined every
-helper.  That build took ptxas nine minutes, so the committed one keeps the big helpers as device calls (same
-arithmetic, -fmad=false; 3 s) - and there was no GPU time left to run it again.  Hence non-strict xfail for now: a pass
-shows up as XPASS, a failure cannot turn the suite red; the file sorts last on purpose.  step() does not call the
-supervisors yet and make_mm_config still rejects safety_guarantee = priority | dmc."""
+Both cases (1 269 steps) pass on a B200 with the committed build (big helpers as device calls; round-1 driver run:
+XPASS x 2), so this is a regular, strict test.  The step path itself calls the supervisors when safety_guarantee is
+"priority" / "dmc" (tests/test_gpu_parity.py::test_supervised_step_*)."""
 import numpy as np
 import pytest
 
 from conftest import SUPERVISED_CASES
 from helpers import load_golden
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="the committed (non-inlined) build of mm_supervise has not run on a GPU yet")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name", SUPERVISED_CASES)
