@@ -53,6 +53,9 @@ WORKLOADS = {
                     desc="HSS cbf-avs_cint td3 (BASELINE configs[1]), 4096 envs"),
     "unsafe_td1": dict(cfg=dict(safety_guarantee="none", HEADWAY_TIME=1.2, traffic_density=1, traffic_type="cav"),
                        envs=65536, desc="no shield, td1 (BASELINE configs[0] LC-env sibling)"),
+    "unsafe_v0_td1": dict(cfg=dict(env_name="merge-multi-agent-v0", safety_guarantee="none", HEADWAY_TIME=1.2, traffic_density=1,
+                                   mixed_traffic=True), envs=65536,
+                          desc="no shield, env merge-multi-agent-v0, td1 mixed (BASELINE configs[0]: test-configs_marl-cav-unsafe.ini)"),
 }
 
 # DESIGN.md "Algorithmic bytes": per vehicle 84 B state read + 124 B state written, per agent 120 B obs + 8 B
@@ -131,9 +134,21 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def cpu_port_throughput(cfg, budget_s, sample_envs, warmup_steps=1, fixed_steps=None):
-    """Time the CPU oracle (C port of the reference path) with all host threads on a bounded sample.
-    Start states come from the host seed-exact spawn; envs are re-spawned on the host when done."""
+def static_config(wl, E, world, scaling="weak"):
+    """The `config` object of the JSON line: the workload only, nothing measured - identical for the GPU arm and for
+    `--impl reference` (the CPU arm times a bounded sample of exactly this workload; see cpu_baseline.sample)."""
+    return {"workload": wl["desc"], "envs_per_gpu": E, "envs_total": E * world if scaling == "weak" else E * world,
+            "actions": "i.i.d. uniform{0..4}", "auto_reset": True,
+            "episode_phases": "staggered uniformly over the 100-step episode, per 128-env tile (untimed prologue)",
+            "l2": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (E * 3.0e-6)
+                  if E >= 262144 else "inputs cycle through 8 action slabs; state working set %.0f MB" % (E * 3.0e-3)}
+
+
+def cpu_port_throughput(cfg, budget_s, sample_envs, warmup_steps=1, fixed_steps=None, pool_scenes=1024):
+    """Time the CPU port of the reference path (the C float64 restatement under oracle/) with all host threads on a
+    bounded SAMPLE of the workload: `sample_envs` envs under the same action law, auto-reset, and - like the GPU arm -
+    with the episode phases staggered uniformly per 128-env tile by an untimed prologue, so that every timed step is the
+    average over all phases of an episode.  Scenes come from the host seed-exact spawn (a pool of `pool_scenes` scenes)."""
     import oracle
     import marl_mass_b200.spawn as spawn
     from marl_mass_b200 import DEFAULT_CONFIG
@@ -141,23 +156,37 @@ def cpu_port_throughput(cfg, budget_s, sample_envs, warmup_steps=1, fixed_steps=
     cores = host_cores()
     ocfg = oracle.make_config(full)
     E = sample_envs
-    base = spawn.spawn_state(range(64), full["traffic_density"], full["traffic_type"])
-    st = {k: np.ascontiguousarray(np.tile(v, (E // 64 + 1,) + (1,) * (v.ndim - 1))[:E]) for k, v in base.items()}
-    fresh = {k: v.copy() for k, v in st.items()}
+    T = int(full["duration"] * full["policy_frequency"])
+    from marl_mass_b200.env import traffic_type_of
+    base = spawn.spawn_state(range(pool_scenes), full["traffic_density"], traffic_type_of(full))
+    reps = E // pool_scenes + 1
+    fresh = {k: np.ascontiguousarray(np.tile(v, (reps,) + (1,) * (v.ndim - 1))[:E]) for k, v in base.items()}
+    st = {k: v.copy() for k, v in fresh.items()}
     rng = np.random.RandomState(0)
     out = oracle.empty_out(E)
-    agent_steps, t_total, n = 0, 0.0, 0
-    per_step = []
-    while True:
+    phase = (np.arange(E) // 128) % T
+
+    def step(timed):
         a = rng.randint(0, 5, size=(E, 12)).astype(np.int8)
-        n_live = int(st["n_cav"].sum())
+        n_live = int(st["n_cav"].sum() if not full.get("env_name", "").endswith("hdv-v1") else st["n_veh"].sum())
         t0 = time.perf_counter()
         oracle.step(ocfg, st, a, out=out, n_threads=cores)
         dt = time.perf_counter() - t0
-        done = out["done"] != 0
-        if done.any():  # host-side re-spawn (untimed, like the reference's env.reset between episodes)
+        return n_live, dt, out["done"] != 0
+
+    def respawn(mask):   # host-side re-spawn (untimed, like the reference's env.reset between episodes)
+        if mask.any():
             for k in st:
-                st[k][done] = fresh[k][done]
+                st[k][mask] = fresh[k][mask]
+
+    for j in range(T):                       # prologue: env tiles re-spawn at step (tile % T), as in the GPU arm
+        _, _, done = step(False)
+        respawn(done | (phase == j))
+    agent_steps, t_total, n = 0, 0.0, 0
+    per_step = []
+    while True:
+        n_live, dt, done = step(True)
+        respawn(done)
         n += 1
         if n > warmup_steps:
             agent_steps += n_live
@@ -175,19 +204,21 @@ def run_reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = min(wl["envs"], 32768)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    sample = min(wl["envs"], 16384)
     v, cores, n_steps, E, ms = cpu_port_throughput(wl["cfg"], None, sample, warmup_steps=args.warmup,
                                                    fixed_steps=args.steps)
     line = {
         "impl": "reference", "metric": "shielded agent-steps/s", "value": v, "unit": "agent-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "envs_per_step": E,
-                   "note": "CPU arm: C float64 port of the reference env+shield (oracle/), all host threads; the "
-                           "Python reference itself cannot travel to the GPU box (see BASELINE.md for its "
-                           "in-container throughput)"},
+        "config": static_config(wl, wl["envs"], world),
         "cpu_baseline": {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port",
-                         "sample": "%d envs x %d policy steps" % (E, n_steps)},
+                         "sample": "%d of the workload's envs (same action law, auto-reset, episode phases staggered per "
+                                   "128-env tile by an untimed %d-step prologue) x %d timed policy steps; ms_per_step is "
+                                   "per sample step" % (E, 100, n_steps),
+                         "note": "C float64 port of the reference env + shield (oracle/), all host threads; the Python "
+                                 "reference cannot travel to the GPU box (BASELINE.md: ~94 agent-steps/s per core here)"},
         "e2e": {"value": v, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -216,6 +247,106 @@ def emit(line):
         os.write(_JSON_FD, data)
 
 
+def load_traffic(workload, envs):
+    """DRAM bytes per launch of the dominant kernel from THIS round's `ncu --set full` capture
+    (profiles/r2_traffic.json, written by profiles/traffic_from_ncu.py), used only when it was taken on exactly this
+    workload and batch - never scaled; otherwise null."""
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        for rec in tj["captures"]:
+            if rec["workload"] == workload and int(rec["envs"]) == int(envs):
+                return float(rec["dram_bytes"]), rec
+    except Exception:
+        pass
+    return None, None
+
+
+class Leg(object):
+    """One batched env on this rank with its action pool, episode phases staggered (untimed prologue)."""
+
+    def __init__(self, mm, mmd, name, E, dev, rank, policy=False):
+        import torch
+        self.torch, self.mm, self.mmd, self.rank = torch, mm, mmd, rank
+        self.wl = dict(WORKLOADS[name])
+        self.E = E
+        self.cfg = dict(mm.DEFAULT_CONFIG, **self.wl["cfg"])
+        self.env = mm.MergeEnvBatched(E, self.cfg, device=dev, record_diag=False)
+        self.env.reset(seed=mmd.rank_seed(1, rank))
+        gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+        # action pool resident in HBM (i.i.d. uniform{0..4}); cycled so every step reads a different slab
+        self.pool = [torch.randint(0, 5, (E, mm.MAXV), generator=gen, device="cuda", dtype=torch.int8) for _ in range(8)]
+        # Prologue (untimed): stagger the episode phases.  All envs are spawned together, so without this every env would
+        # hit the 100-step horizon on the same step; re-spawning the envs of tile k at prologue step (k % T) spreads the
+        # phases uniformly, which is the steady state of a long rollout (1/T of the envs re-spawn per timed step).  By
+        # 128-env tile, not by env: in a real rollout the envs of a batch start together and only the rare crash
+        # de-synchronises one, so neighbouring envs share their episode phase.
+        T = int(self.cfg["duration"] * self.cfg["policy_frequency"])
+        idx = (torch.arange(E, device="cuda", dtype=torch.int32) // 128) % T
+        for j in range(T):
+            self.env.step(self.pool[j % 8], auto_reset=True)
+            self.env.reset(seed=mmd.rank_seed(3 + j, rank), mask=(idx == j).to(torch.uint8))
+        self.policy = None
+        if policy:
+            from marl_mass_b200.rollout import BatchedMAPPORollout
+            torch.manual_seed(rank)
+            self.policy = BatchedMAPPORollout(self.env, roll_out_n_steps=1)
+            self.vbuf = self.env.buffers()
+
+    def step(self, t):
+        if self.policy is None:
+            self.env.step(self.pool[t % 8], auto_reset=True)
+        else:
+            self.env.step(self.policy._act(self.vbuf["obs"], self.vbuf["n_agents"])[0], auto_reset=True)
+
+    def timed(self, K, W, barrier):
+        """W untimed + K timed steps bracketed by barrier(); returns (ms_total, stats of the timed steps, launches)."""
+        torch = self.torch
+        for t in range(W):
+            self.step(t)
+        barrier()
+        self.env.stats(reset=True)
+        l0 = self.env.kernel_launches()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for t in range(K):
+            self.step(t)
+        ev1.record()
+        barrier()
+        return ev0.elapsed_time(ev1), self.env.stats(reset=True), self.env.kernel_launches() - l0
+
+    def kernel_times(self, n):
+        """Device time of the physics kernel + outputs kernel alone, one event pair per policy step (re-spawn outside)."""
+        torch = self.torch
+        v = self.env.buffers()
+        ms, agents = [], 0.0
+        for t in range(n):
+            n_ag = float(v["n_agents"].sum())
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            self.env.step(self.pool[t % 8], auto_reset=False)
+            b.record()
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+            agents += n_ag
+            self.env.reset(seed=self.mmd.rank_seed(2, self.rank), mask=v["done"])
+        torch.cuda.synchronize()
+        return float(np.mean(ms)), agents / max(n, 1)
+
+    def algorithmic_bytes(self, mean_agents):
+        cfg = self.cfg
+        mean_hdv = 0.0 if cfg["traffic_type"] == "cav" else {1: 2.0, 2: 3.0, 3: 4.0}[int(cfg["traffic_density"])]
+        return self.E * ((mean_agents + mean_hdv) * BYTES_PER_VEHICLE + mean_agents * BYTES_PER_AGENT + BYTES_PER_ENV)
+
+    def close(self):
+        self.env.close()
+
+
+BUILD_NAMES = {3: "generic, 3 CTAs/SM", 4: "generic, 4 CTAs/SM", 31: "all-CAV HSS specialised, 3 CTAs/SM",
+               32: "all-CAV MASS specialised, 3 CTAs/SM", 41: "all-CAV HSS specialised, 4 CTAs/SM",
+               42: "all-CAV MASS specialised, 4 CTAs/SM", 50: "warp-cooperative, no shield", 51: "warp-cooperative, HSS",
+               52: "warp-cooperative, MASS"}
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -225,9 +356,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="mass_td3", choices=sorted(WORKLOADS))
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the workload's envs on EVERY GPU (default); strong: the workload's envs split over the GPUs")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer pass (default min(steps, 20))")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-extra", action="store_true", help="only the headline leg: no strong-scaling / other-workload legs")
     ap.add_argument("--policy", action="store_true",
                     help="BASELINE configs[3]: sample the actions from the MAPPO actor (30-128-128-5) on the device "
                          "inside the timed region instead of reading pre-drawn uniform actions")
@@ -255,15 +389,7 @@ def main():
     dev = local_rank if world > 1 else 0
     torch.cuda.set_device(dev)
     numa_cores = mmd.bind_to_gpu(dev) if world > 1 else 0   # host buffers on the GPU's own NUMA node
-    E = wl["envs"]
-    cfg = dict(mm.DEFAULT_CONFIG, **wl["cfg"])
-    env = mm.MergeEnvBatched(E, cfg, device=dev, record_diag=False)
-    env.reset(seed=mmd.rank_seed(1, rank))
     K, W = args.steps, args.warmup
-
-    # action pool resident in HBM (i.i.d. uniform{0..4}); cycled so every step reads a different 12 MB slab
-    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
-    pool = [torch.randint(0, 5, (E, mm.MAXV), generator=gen, device="cuda", dtype=torch.int8) for _ in range(8)]
 
     def barrier():
         torch.cuda.synchronize()
@@ -271,65 +397,28 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # Prologue (untimed): stagger the episode phases.  All envs are spawned together, so without this every env
-    # would hit the 100-step horizon on the same step; re-spawning the envs with (index % T == j) at prologue
-    # step j spreads the phases uniformly, which is the steady state of a long rollout (1/T of the envs re-spawn
-    # per step inside the timed region).
-    T = int(cfg["duration"] * cfg["policy_frequency"])
-    # Stagger by 128-env tile, not by env: in a real rollout every env of the batch starts together and only the
-    # rare crash de-synchronises one, so neighbouring envs share their episode phase; tile-granular staggering
-    # keeps that property while making every timed step the average over all phases of an episode.
-    idx = (torch.arange(E, device="cuda", dtype=torch.int32) // 128) % T
-    for j in range(T):
-        env.step(pool[j % 8], auto_reset=True)
-        env.reset(seed=mmd.rank_seed(3 + j, rank), mask=(idx == j).to(torch.uint8))
-    for t in range(W):
-        env.step(pool[t % 8], auto_reset=True)
-    barrier()
-    env.stats(reset=True)
-    l0 = env.kernel_launches()
+    def fold(ms, stats):
+        """max over ranks of the time, sum over ranks of the work"""
+        tot = mmd.all_reduce_stats(stats)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms, tot
 
+    E_total = wl["envs"]
+    E = E_total if args.scaling == "weak" else max(128, (E_total // world) // 128 * 128)
     sampler = ClockSampler(dev)
+    leg = Leg(mm, mmd, args.workload, E, dev, rank, policy=args.policy)
+    env = leg.env
     sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    policy = None
-    if args.policy:
-        from marl_mass_b200.rollout import BatchedMAPPORollout
-        torch.manual_seed(rank)
-        policy = BatchedMAPPORollout(env, roll_out_n_steps=1)
-        vbuf = env.buffers()
-        for t in range(3):
-            env.step(policy._act(vbuf["obs"], vbuf["n_agents"])[0], auto_reset=True)
-    barrier()
-    ev0.record()
-    if policy is None:
-        for t in range(K):
-            env.step(pool[t % 8], auto_reset=True)
-    else:
-        for t in range(K):
-            env.step(policy._act(vbuf["obs"], vbuf["n_agents"])[0], auto_reset=True)
-    ev1.record()
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    launches = env.kernel_launches() - l0
-    stats = env.stats(reset=True)
-
-    # roofline pass: the step kernel alone, one event pair per launch (re-spawn outside the pair)
-    kern_ms = []
-    agent_steps_k, veh_steps_k = 0.0, 0.0
-    v = env.buffers()
-    for t in range(min(K, 30)):
-        n_ag = float(v["n_agents"].sum())
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        env.step(pool[t % 8], auto_reset=False)
-        b.record()
-        torch.cuda.synchronize()
-        kern_ms.append(a.elapsed_time(b))
-        agent_steps_k += n_ag
-        env.reset(seed=mmd.rank_seed(2, rank), mask=v["done"])
-    torch.cuda.synchronize()
+    ms_local, stats, launches = leg.timed(K, W, barrier)
+    build = env.step_build()
+    kms, _ = leg.kernel_times(min(K, 30))
     clocks = sampler.stop()
+    ms_total, tot = fold(ms_local, stats)
+    value = tot["agent_steps"] / (ms_total * 1e-3)
+    mean_agents = stats["agent_steps"] / max(stats["env_steps"], 1.0)
 
     # CBF-QP alone (the metric's "CBF-QP solves/s"): 2^26 synthetic solves, ~10 % of rows active (SURVEY.md 8d)
     nq = 1 << 26
@@ -356,103 +445,124 @@ def main():
     qp_active = float((qact != 0).float().mean())
     del qa, qcl, qca, qha, qlo, qhi, qu, qact
 
-    # e2e pass: host buffers through mm_step_host
+    # e2e passes: host buffers through the C ABI, copies inside the timed region (wall clock around the calls)
     K2 = args.e2e_steps or min(K, 20)
-    host_out = env.alloc_host_out(pinned=True)
     host_act = [torch.randint(0, 5, (E, mm.MAXV), dtype=torch.int8).pin_memory().numpy() for _ in range(4)]
-    env.step_host(host_act[0], auto_reset=True, out=host_out)
-    env.stats(reset=True)
-    barrier()
-    t0 = time.perf_counter()
-    for t in range(K2):
-        env.step_host(host_act[t % 4], auto_reset=True, out=host_out)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    e2e_stats = env.stats(reset=True)
+
+    def e2e_pass(call, out):
+        call(host_act[0], auto_reset=True, out=out)
+        env.stats(reset=True)
+        barrier()
+        t0 = time.perf_counter()
+        for t in range(K2):
+            call(host_act[t % 4], auto_reset=True, out=out)
+        torch.cuda.synchronize()
+        secs = time.perf_counter() - t0
+        st_ = env.stats(reset=True)
+        ms_, tot_ = fold(secs * 1e3, st_)
+        return tot_["agent_steps"] / (ms_ * 1e-3)
+
+    host_out = env.alloc_host_out(pinned=True)
+    dense_value = e2e_pass(env.step_host, host_out)
     del host_out
-    # the same with the observations packed as the reference returns them (live agents' rows only): mm_step_host_ragged
     rag_out = env.alloc_host_out(pinned=True, ragged=True)
-    env.step_host_ragged(host_act[0], auto_reset=True, out=rag_out)
-    env.stats(reset=True)
-    barrier()
-    t0 = time.perf_counter()
-    for t in range(K2):
-        env.step_host_ragged(host_act[t % 4], auto_reset=True, out=rag_out)
-    torch.cuda.synchronize()
-    rag_s = time.perf_counter() - t0
-    rag_stats = env.stats(reset=True)
+    ragged_value = e2e_pass(env.step_host_ragged, rag_out)
     rag_rows = float(rag_out["n_agents"].sum())
+    del rag_out
+    e2e = {"value": ragged_value, "unit": "agent-steps/s", "h2d_bytes_per_step": E * mm.MAXV,
+           "d2h_bytes_per_step": int(rag_rows * mm.NS * 4 + E * (8 + 4 + 1 + mm.MAXV * 4 + 4)), "steps": K2,
+           "api": "mm_step_host_ragged (pinned host buffers, 64Ki-env chunks round-robin on 4 streams; observation rows "
+                  "of the live agents only, as the reference returns them: packed on the device, exact-size copies)",
+           "host_cores_bound": numa_cores,
+           "dense": {"value": dense_value, "d2h_bytes_per_step": E * (mm.MAXV * mm.NS * 4 + 4 + 1 + mm.MAXV * 4 + 4),
+                     "api": "mm_step_host (dense obs [E,12,30] by cudaMemcpyAsync)"}}
+    if hasattr(env, "step_host_packed"):
+        pk_out = env.alloc_host_out(pinned=True, packed=True)
+        packed_value = e2e_pass(env.step_host_packed, pk_out)
+        pk_bytes = env.packed_bytes(pk_out)
+        e2e["ragged"] = {"value": ragged_value, "d2h_bytes_per_step": e2e["d2h_bytes_per_step"], "api": e2e["api"]}
+        e2e.update({"value": packed_value, "d2h_bytes_per_step": int(pk_bytes),
+                    "api": "mm_step_host_packed (pinned host buffers; per vehicle x, y, vx, vy, heading as f32 + per agent "
+                           "the slots of its 4 observed neighbours + ragged regional rewards: the observation rows are a "
+                           "deterministic function of these, mm_expand_obs_rows builds them on the host)"})
+        del pk_out
 
-    # fold over ranks: time = max, work = sum
-    tot = mmd.all_reduce_stats(stats)
-    e2e_tot = mmd.all_reduce_stats(e2e_stats)
-    rag_tot = mmd.all_reduce_stats(rag_stats)
-    if world > 1:
-        tmax = torch.tensor([ms_total, e2e_s, rag_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ms_total, e2e_s, rag_s = float(tmax[0]), float(tmax[1]), float(tmax[2])
-    value = tot["agent_steps"] / (ms_total * 1e-3)
-    dense_value = e2e_tot["agent_steps"] / e2e_s
-    e2e_value = rag_tot["agent_steps"] / rag_s
-
-    mean_agents = stats["agent_steps"] / max(stats["env_steps"], 1.0)
-    mean_hdv = 0.0 if cfg["traffic_type"] == "cav" else {1: 2.0, 2: 3.0, 3: 4.0}[int(cfg["traffic_density"])]
-    veh_per_env = mean_agents + mean_hdv
-    kms = float(np.mean(kern_ms))
-    bytes_per_launch = E * (veh_per_env * BYTES_PER_VEHICLE + mean_agents * BYTES_PER_AGENT + BYTES_PER_ENV)
     peak, peak_src = load_peaks()
+    bytes_per_launch = leg.algorithmic_bytes(mean_agents)
     achieved = bytes_per_launch / (kms * 1e-3) / 1e9
-    # DRAM traffic of the step kernel from the committed ncu capture (profiles/r1_traffic.json), scaled per env
-    traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        if tj.get("workload") == args.workload:
-            traffic = tj["dram_bytes"] * (E / float(tj["envs"]))
-    except Exception:
-        traffic = None
-
+    traffic, traffic_rec = load_traffic(args.workload, E)
+    cfg_out = static_config(wl, E, world, args.scaling)
+    if args.policy:
+        cfg_out["actions"] = ("sampled on device from the MAPPO actor 30-128-128-5 inside the timed region "
+                              "(mm_actor_sample: fused TF32 forward + inverse-CDF draw, one launch per step)")
     line = {
         "metric": "shielded agent-steps/s", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": K,
-        "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "envs_per_gpu": E, "mean_agents_per_env": round(mean_agents, 3),
-                   "actions": "i.i.d. uniform{0..4}, resident in HBM", "auto_reset": True,
-                   "episode_phases": "staggered uniformly over the 100-step episode, per 128-env tile (untimed prologue)",
-                   "l2": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (E * 3.0e-6),
-                   "step_kernel_build": "automatic (3 CTAs/SM; 4 CTAs/SM for grids of 3..8 CTAs per SM whose wave "
-                                        "structure favours it, include/marl_mass_b200.h mm_set_step_variant)",
-                   "shield_solves_per_s": tot["shield_solves"] / (ms_total * 1e-3),
-                   "shield_active_frac": tot["shield_active"] / max(tot["shield_solves"], 1.0),
-                   "lane_change_veto_frac": tot["lane_change_vetoes"] / max(tot["shield_solves"], 1.0),
-                   "crashed_episode_frac": tot["crashed_episodes"] / max(tot["episodes"], 1.0)},
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": E * mm.MAXV,
-                "d2h_bytes_per_step": int(rag_rows * mm.NS * 4 + E * (8 + 4 + 1 + mm.MAXV * 4 + 4)), "steps": K2,
-                "api": "mm_step_host_ragged (pinned host buffers, 64Ki-env chunks round-robin on 4 streams; observation "
-                       "rows of the live agents only, as the reference returns them: packed on the device, exact-size copies)",
-                "host_cores_bound": numa_cores,
-                "dense": {"value": dense_value, "d2h_bytes_per_step": E * (mm.MAXV * mm.NS * 4 + 4 + 1 + mm.MAXV * 4 + 4),
-                          "api": "mm_step_host (dense obs [E,12,30] by cudaMemcpyAsync)"}},
-        "gpu_launches": int(launches),
+        "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": cfg_out,
+        "measured": {"mean_agents_per_env": round(mean_agents, 3),
+                     "step_kernel_build": BUILD_NAMES.get(build, str(build)),
+                     "shield_solves_per_s": tot["shield_solves"] / (ms_total * 1e-3),
+                     "shield_active_frac": tot["shield_active"] / max(tot["shield_solves"], 1.0),
+                     "lane_change_veto_frac": tot["lane_change_vetoes"] / max(tot["shield_solves"], 1.0),
+                     "crashed_episode_frac": tot["crashed_episodes"] / max(tot["episodes"], 1.0)},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "step_kernel<false, false>", "kernel_ms": kms,
+                     "traffic": traffic, "kernel": "step_kernel + outputs_kernel (one policy step)", "kernel_ms": kms,
                      "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src,
-                     "note": "issue/latency-bound f64 kernel (SURVEY.md 8d): HBM fraction is reported as asked; "
-                             "see profiles/ for pipe utilisation"},
+                     "traffic_source": (traffic_rec or {}).get("source"),
+                     "note": "issue/latency-bound f64 kernels (SURVEY.md 8d): the HBM fraction is reported as asked; "
+                             "see profiles/ for issue-slot and pipe utilisation"},
     }
     line["qp_microbench"] = {"solves_per_s": nq / (qp_ms * 1e-3), "n": nq, "ms": qp_ms, "active_frac": qp_active,
                              "ms_mean": float(np.mean(qp_runs)), "bytes_per_solve": 50, "achieved_GBps": nq * 50 / (qp_ms * 1e-3) / 1e9,
                              "hbm_frac": nq * 50 / (qp_ms * 1e-3) / 1e9 / peak, "dtype": "f64"}
-    if args.policy:
-        line["config"]["actions"] = ("sampled on device from the MAPPO actor 30-128-128-5 inside the timed region "
-                                     "(mm_actor_sample: fused TF32 forward + inverse-CDF draw, one launch per step)")
+    leg.close()
+    del leg, env
+
+    # ---- strong scaling of the same workload: its envs split over the GPUs (BASELINE configs[4] as stated)
+    if not args.skip_extra and args.scaling == "weak":
+        if world == 1:
+            line["strong_scaling"] = {"envs_total": E_total, "envs_per_gpu": E_total, "value": value, "ms_per_step": ms_total / K,
+                                      "note": "one GPU: same run as the headline"}
+        else:
+            Es = max(128, (E_total // world) // 128 * 128)
+            sl = Leg(mm, mmd, args.workload, Es, dev, rank)
+            ms_s, st_s, _ = sl.timed(K, W, barrier)
+            ms_s, tot_s = fold(ms_s, st_s)
+            line["strong_scaling"] = {"envs_total": Es * world, "envs_per_gpu": Es, "value": tot_s["agent_steps"] / (ms_s * 1e-3),
+                                      "ms_per_step": ms_s / K, "step_kernel_build": BUILD_NAMES.get(sl.env.step_build(), "?")}
+            sl.close()
+            del sl
+
+    # ---- the other BASELINE configs as short legs on one GPU (configs[0..3]; the headline is configs[4])
+    if not args.skip_extra and world == 1 and args.workload == "mass_td3" and not args.envs:
+        legs = {}
+        for key, name, pol in (("configs[0] no shield (v0 env, td1 mixed)", "unsafe_v0_td1", False),
+                               ("configs[1] HSS td3, 4096 envs", "hss_td3", False),
+                               ("configs[2] MASS td1, 65536 envs", "mass_td1", False),
+                               ("configs[3] MASS td3 srew, 65536 envs, uniform actions", "mass_td3_srew", False),
+                               ("configs[3] MASS td3 srew, 65536 envs, actor in the loop", "mass_td3_srew", True),
+                               ("MASS td3 mixed traffic, 262144 envs", "mass_td3_mixed", False)):
+            En = WORKLOADS[name]["envs"] if name != "mass_td3_mixed" else 262144
+            lg = Leg(mm, mmd, name, En, dev, rank, policy=pol)
+            ms_l, st_l, _ = lg.timed(30, 5, barrier)
+            kms_l, _ = lg.kernel_times(10)
+            ag = st_l["agent_steps"] / max(st_l["env_steps"], 1.0)
+            bpl = lg.algorithmic_bytes(ag)
+            legs[key] = {"workload": WORKLOADS[name]["desc"], "envs": En, "value": st_l["agent_steps"] / (ms_l * 1e-3),
+                         "ms_per_step": ms_l / 30, "step_kernel_build": BUILD_NAMES.get(lg.env.step_build(), "?"),
+                         "roofline_frac": bpl / (kms_l * 1e-3) / 1e9 / peak, "kernel_ms": kms_l}
+            lg.close()
+            del lg
+        line["workloads"] = legs
+
     if rank == 0 and world == 1 and not args.skip_cpu:
         v_cpu, cores, n_steps, e_cpu, _ = cpu_port_throughput(wl["cfg"], args.cpu_seconds, min(E, 16384))
         line["cpu_baseline"] = {"value": v_cpu, "unit": "agent-steps/s", "cores": cores, "kind": "port",
-                                "sample": "%d envs x %d policy steps (~%.0f s of CPU work)" % (e_cpu, n_steps, args.cpu_seconds)}
+                                "sample": "%d envs of the workload, phases staggered, x %d policy steps (~%.0f s of CPU work)"
+                                          % (e_cpu, n_steps, args.cpu_seconds)}
     if rank == 0:
         emit(line)
-    env.close()
     if world > 1:
         dist.destroy_process_group()
 

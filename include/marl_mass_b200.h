@@ -45,7 +45,7 @@ enum { MM_ACT_LEAD = 1, MM_ACT_UPPER = 2, MM_ACT_LOWER = 4, MM_ACT_ADJ = 8, MM_A
  * signature; mm_abi_version() returns the value the library was built with, and mm_create / mm_set_config reject a
  * config whose struct_size field is not sizeof(mm_config) (a binding built against another revision of the header
  * fails loudly instead of handing the library garbage). */
-#define MM_ABI_VERSION 3
+#define MM_ABI_VERSION 4
 int mm_abi_version(void);
 
 typedef struct {
@@ -161,6 +161,31 @@ int mm_step_host(mm_env *env, const int8_t *actions, int auto_reset, float *obs,
  * mm_step_host (nullable). */
 int mm_step_host_ragged(mm_env *env, const int8_t *actions, int auto_reset, float *obs_rows, int64_t *row_offset,
                         float *reward, uint8_t *done, float *regional_rewards, int32_t *n_agents);
+/* The same step with the observation in PACKED form: instead of the [A, 30] rows, what they are a function of.
+ *   veh     [sum n_veh][5] f32   x, y, vx, vy, heading of every vehicle, envs in order, slots in order (CAVs first)
+ *   nbr     [sum n_agents] u16   per agent: the slots of the (up to) 4 other vehicles its observation shows, 4 bits each in
+ *                                row order (close_vehicles_to(count = 4), road.py:257-267), 0xF = that row is empty
+ *   n_veh, n_agents [n_envs] u8  the counts; all offsets are their running sums (dense from the first env to the last)
+ *   reward [n_envs] f32, done [n_envs] u8, regional_rewards [n_envs][MM_MAXV] f32 as in mm_step_host (nullable)
+ * About 250 bytes per env-step at hard density against 1.1 KB for the packed rows of mm_step_host_ragged: the host path
+ * is bound by PCIe and host memory, not by the kernels.  Row i of env e is rebuilt by mm_expand_obs_rows:
+ * ego columns from veh[i], row k + 1 from veh[slot k of nbr] - veh[i] (observation.py:241-273, 181-193); inputs are
+ * float32, so the rebuilt rows agree with mm_step_host's to ~2e-7 (float32 rounding of positions up to 450 m mapped onto
+ * [-1, 1]), inside the 1e-4 tolerance of the path.  With auto_reset the packed state of a finished env is that of its next
+ * episode (like obs), reward / done / regional_rewards describe the finished step.  veh needs room for n_envs * 11 rows,
+ * nbr for n_envs * MM_MAXV entries (pinned memory for full PCIe speed). */
+typedef struct {
+    float *veh;
+    uint16_t *nbr;
+    uint8_t *n_veh, *n_agents;
+    float *reward;
+    uint8_t *done;
+    float *regional_rewards;
+} mm_packed_host;
+int mm_step_host_packed(mm_env *env, const int8_t *actions, int auto_reset, const mm_packed_host *out);
+/* Pure host function (no device): obs_rows [sum n_agents][30] f32 and row_offset [n_envs + 1] from a packed step, on
+ * n_threads host threads.  steer_vel: the config's lateral_control == "steer_vel" (neighbour CAV headings relative). */
+int mm_expand_obs_rows(const mm_packed_host *in, int n_envs, int steer_vel, float *obs_rows, int64_t *row_offset, int n_threads);
 int mm_buffers_get(mm_env *env, mm_buffers *out);
 int mm_get_state(mm_env *env, mm_state_host *dst);        /* synchronous */
 int mm_set_state(mm_env *env, const mm_state_host *src);  /* synchronous; also refreshes obs / n_agents */
@@ -208,9 +233,12 @@ int mm_discounted_returns(const float *rewards, const uint8_t *dones, const floa
  * 0 (default): automatic - a specialised build when the handle's config matches and none of its envs can hold an HDV
  * (spawned under traffic_type cav, or checked by mm_set_state); the 4-CTA build for small grids whose wave structure
  * favours it (e.g. 65 536 envs = 512 CTAs on 148 SMs: one wave instead of a full and an almost empty one, -27 % step
- * time).  3 / 4: force a generic build; 5: automatic among the generic builds only (process-wide; tests). */
+ * time).  3 / 4: force a generic build; 5: automatic among the generic builds only; 6: 4 CTAs per SM forced, specialised
+ * builds allowed; 7: the warp-cooperative build forced where it applies (process-wide; tests and A/B timing). */
 int mm_set_step_variant(int variant);
-enum { MM_BUILD_GENERIC3 = 3, MM_BUILD_GENERIC4 = 4, MM_BUILD_SPEC_HSS = 31, MM_BUILD_SPEC_MASS = 32 };
+enum { MM_BUILD_GENERIC3 = 3, MM_BUILD_GENERIC4 = 4, MM_BUILD_SPEC_HSS = 31, MM_BUILD_SPEC_MASS = 32,
+       MM_BUILD_SPEC_HSS4 = 41, MM_BUILD_SPEC_MASS4 = 42 /* specialised and built for 4 CTAs per SM */,
+       MM_BUILD_COOP = 50 /* + shield kind: the warp-cooperative build (half a warp per env) */ };
 /* which build the handle's last mm_step / mm_step_host* launched (0 before the first step) */
 int mm_step_build(const mm_env *env);
 

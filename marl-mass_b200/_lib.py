@@ -28,7 +28,7 @@ _PU8 = C.POINTER(C.c_uint8)
 _PI8 = C.POINTER(C.c_int8)
 
 
-ABI_VERSION = 3           # MM_ABI_VERSION of the header this binding was written against
+ABI_VERSION = 4           # MM_ABI_VERSION of the header this binding was written against
 
 
 class MMConfig(C.Structure):
@@ -57,6 +57,11 @@ class MMBuffers(C.Structure):
                 ("n_agents", C.c_void_p), ("actions", C.c_void_p), ("action_mask", C.c_void_p)]
 
 
+class MMPackedHost(C.Structure):
+    _fields_ = [("veh", C.c_void_p), ("nbr", C.c_void_p), ("n_veh", C.c_void_p), ("n_agents", C.c_void_p),
+                ("reward", C.c_void_p), ("done", C.c_void_p), ("regional_rewards", C.c_void_p)]
+
+
 class MMShieldDiagHost(C.Structure):
     _fields_ = [(k, _PI) for k in SH_I] + [(k, _PD) for k in SH_F]
 
@@ -75,7 +80,7 @@ _lib = None
 
 SUPERVISOR_DRAWS = 32     # MM_SUPERVISOR_DRAWS
 EXPORTS = ("mm_create", "mm_destroy", "mm_set_config", "mm_num_envs", "mm_reset", "mm_step", "mm_step_host",
-           "mm_step_host_ragged",
+           "mm_step_host_ragged", "mm_step_host_packed", "mm_expand_obs_rows",
            "mm_buffers_get", "mm_get_state", "mm_set_state", "mm_get_shield_diag", "mm_stats", "mm_shield_qp",
            "mm_actor_sample", "mm_set_actor_impl", "mm_set_step_variant", "mm_step_build", "mm_abi_version", "mm_discounted_returns", "mm_supervise",
            "mm_kernel_launches", "mm_last_error", "mm_version")
@@ -103,6 +108,8 @@ def lib():
     L.mm_step.argtypes = [h, C.c_void_p, C.c_int, C.c_void_p]
     L.mm_step_host.argtypes = [h, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mm_step_host_ragged.argtypes = [h, C.c_void_p, C.c_int] + [C.c_void_p] * 6
+    L.mm_step_host_packed.argtypes = [h, C.c_void_p, C.c_int, C.POINTER(MMPackedHost)]
+    L.mm_expand_obs_rows.argtypes = [C.POINTER(MMPackedHost), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     L.mm_buffers_get.argtypes = [h, C.POINTER(MMBuffers)]
     L.mm_get_state.argtypes = [h, C.POINTER(MMStateHost)]
     L.mm_set_state.argtypes = [h, C.POINTER(MMStateHost)]

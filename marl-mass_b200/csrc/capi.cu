@@ -9,6 +9,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "mm_internal.h"
@@ -51,6 +52,15 @@ struct mm_env {
     int64_t *chunk_rows_dev = nullptr, *chunk_rows_host = nullptr;
     cudaEvent_t chunk_done[MAX_HOST_CHUNKS]{};
     bool ragged_ready = false;
+    // mm_step_host_packed, allocated on first use: packed vehicle rows / neighbour words, per-env offsets inside a chunk,
+    // count bytes, running totals chained chunk to chunk (device + pinned host mirror), one event per chunk's scan
+    float *veh_packed = nullptr;
+    uint16_t *nbr_packed = nullptr;
+    int32_t *voff = nullptr, *aoff = nullptr;
+    uint8_t *n_veh_u8 = nullptr, *n_agents_u8 = nullptr;
+    int64_t *chunk_base_dev = nullptr, *chunk_base_host = nullptr;
+    cudaEvent_t scan_done[MAX_HOST_CHUNKS]{};
+    bool packed_ready = false;
     size_t stats_rows = 0;
     uint64_t seed = 0;
     int64_t launches = 0;
@@ -227,6 +237,9 @@ int mm_destroy(mm_env *env) {
     for (int i = 0; i < MAX_HOST_CHUNKS; ++i)
         if (env->chunk_done[i]) cudaEventDestroy(env->chunk_done[i]);
     if (env->caller_done) cudaEventDestroy(env->caller_done);
+    for (int i = 0; i < MAX_HOST_CHUNKS; ++i)
+        if (env->scan_done[i]) cudaEventDestroy(env->scan_done[i]);
+    if (env->chunk_base_host) cudaFreeHost(env->chunk_base_host);
     if (env->chunk_rows_host) cudaFreeHost(env->chunk_rows_host);
     for (void *p : env->allocs) cudaFree(p);
     delete env;
@@ -408,6 +421,163 @@ int mm_step_host_ragged(mm_env *env, const int8_t *actions, int auto_reset, floa
     return 0;
 }
 
+int mm_step_host_packed(mm_env *env, const int8_t *actions, int auto_reset, const mm_packed_host *out) {
+    if (!env) return fail(MM_ERR_ARG, "env is null");
+    if (!actions || !out || !out->veh || !out->nbr || !out->n_veh || !out->n_agents)
+        return fail(MM_ERR_ARG, "actions, out->veh, out->nbr, out->n_veh and out->n_agents are required");
+    CUDA_OK(cudaSetDevice(env->device));
+    const int E = env->n_envs;
+    if (!env->packed_ready) {   // first use; pieces are kept as they come, the block completes only when all exist
+        auto grab = [&](void **dst, size_t bytes) -> int {
+            if (*dst) return 0;
+            void *p = nullptr;
+            CUDA_OK(cudaMalloc(&p, bytes));
+            CUDA_OK(cudaMemset(p, 0, bytes));
+            env->allocs.push_back(p);
+            *dst = p;
+            return 0;
+        };
+        int rc = 0;
+        rc |= grab((void **)&env->out.veh, (size_t)E * MAXV * 5 * sizeof(float));
+        rc |= grab((void **)&env->out.nbr, (size_t)E * MAXV * sizeof(uint16_t));
+        rc |= grab((void **)&env->veh_packed, (size_t)E * MAXV * 5 * sizeof(float));
+        rc |= grab((void **)&env->nbr_packed, (size_t)E * MAXV * sizeof(uint16_t));
+        rc |= grab((void **)&env->voff, (size_t)E * sizeof(int32_t));
+        rc |= grab((void **)&env->aoff, (size_t)E * sizeof(int32_t));
+        rc |= grab((void **)&env->n_veh_u8, (size_t)E);
+        rc |= grab((void **)&env->n_agents_u8, (size_t)E);
+        rc |= grab((void **)&env->chunk_base_dev, (size_t)(MAX_HOST_CHUNKS + 1) * 2 * sizeof(int64_t));
+        if (rc) return rc;
+        if (!env->chunk_base_host) {
+            void *p = nullptr;
+            CUDA_OK(cudaHostAlloc(&p, (size_t)(MAX_HOST_CHUNKS + 1) * 2 * sizeof(int64_t), cudaHostAllocDefault));
+            env->chunk_base_host = static_cast<int64_t *>(p);
+            env->chunk_base_host[0] = env->chunk_base_host[1] = 0;
+        }
+        for (int c = 0; c < MAX_HOST_CHUNKS; ++c) {
+            if (!env->chunk_done[c]) CUDA_OK(cudaEventCreateWithFlags(&env->chunk_done[c], cudaEventDisableTiming));
+            if (!env->scan_done[c]) CUDA_OK(cudaEventCreateWithFlags(&env->scan_done[c], cudaEventDisableTiming));
+        }
+        env->packed_ready = true;
+    }
+    const int chunk_target = host_chunk_target(E);
+    const int n_str = 4;
+    int n_chunks = (E + chunk_target - 1) / chunk_target;
+    if (n_chunks < 1) n_chunks = 1;
+    if (n_chunks > MAX_HOST_CHUNKS) n_chunks = MAX_HOST_CHUNKS;
+    const int chunk = ((E + n_chunks - 1) / n_chunks + 767) / 768 * 768;
+    // Same software pipeline as mm_step_host_ragged.  The packed rows of the batch are dense from the first env to the
+    // last, so a chunk's scan starts from the totals of the chunk before it (a device-side chain: base[c] -> base[c+1],
+    // one event wait between neighbouring chunks' scans); the host learns the totals with the chunk's event and copies
+    // exactly the packed bytes.
+    auto enqueue_compute = [&](int c) -> int {
+        const int off = c * chunk;
+        const int count = E - off < chunk ? E - off : chunk;
+        cudaStream_t s = env->streams[c % n_str];
+        CUDA_OK(cudaMemcpyAsync(env->actions + (size_t)off * MAXV, actions + (size_t)off * MAXV, (size_t)count * MAXV,
+                                cudaMemcpyHostToDevice, s));
+        enqueue_step(env, env->actions, auto_reset, off, count, s);
+        if (c > 0) CUDA_OK(cudaStreamWaitEvent(s, env->scan_done[c - 1], 0));
+        launch_packed_pack(env->st.einfo + off, env->out.n_agents + off, env->out.veh + (size_t)off * MAXV * 5,
+                           env->out.nbr + (size_t)off * MAXV, count, env->chunk_base_dev + 2 * c, env->chunk_base_dev + 2 * (c + 1),
+                           env->voff + off, env->aoff + off, env->veh_packed, env->nbr_packed, env->n_veh_u8 + off,
+                           env->n_agents_u8 + off, s);
+        env->launches += 2;
+        CUDA_OK(cudaEventRecord(env->scan_done[c], s));
+        CUDA_OK(cudaMemcpyAsync(env->chunk_base_host + 2 * (c + 1), env->chunk_base_dev + 2 * (c + 1), 2 * sizeof(int64_t),
+                                cudaMemcpyDeviceToHost, s));
+        CUDA_OK(cudaEventRecord(env->chunk_done[c], s));
+        return 0;
+    };
+    auto enqueue_copies = [&](int c) -> int {
+        const int off = c * chunk;
+        const int count = E - off < chunk ? E - off : chunk;
+        cudaStream_t s = env->streams[c % n_str];
+        CUDA_OK(cudaEventSynchronize(env->chunk_done[c]));
+        const int64_t v0 = env->chunk_base_host[2 * c], v1 = env->chunk_base_host[2 * (c + 1)];
+        const int64_t a0 = env->chunk_base_host[2 * c + 1], a1 = env->chunk_base_host[2 * (c + 1) + 1];
+        if (v1 > v0)
+            CUDA_OK(cudaMemcpyAsync(out->veh + v0 * 5, env->veh_packed + v0 * 5, (size_t)(v1 - v0) * 5 * sizeof(float),
+                                    cudaMemcpyDeviceToHost, s));
+        if (a1 > a0)
+            CUDA_OK(cudaMemcpyAsync(out->nbr + a0, env->nbr_packed + a0, (size_t)(a1 - a0) * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
+        CUDA_OK(cudaMemcpyAsync(out->n_veh + off, env->n_veh_u8 + off, (size_t)count, cudaMemcpyDeviceToHost, s));
+        CUDA_OK(cudaMemcpyAsync(out->n_agents + off, env->n_agents_u8 + off, (size_t)count, cudaMemcpyDeviceToHost, s));
+        if (out->reward)
+            CUDA_OK(cudaMemcpyAsync(out->reward + off, env->out.reward + off, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (out->done)
+            CUDA_OK(cudaMemcpyAsync(out->done + off, env->out.done + off, (size_t)count, cudaMemcpyDeviceToHost, s));
+        if (out->regional_rewards)
+            CUDA_OK(cudaMemcpyAsync(out->regional_rewards + (size_t)off * MAXV, env->out.regional_rewards + (size_t)off * MAXV,
+                                    (size_t)count * MAXV * sizeof(float), cudaMemcpyDeviceToHost, s));
+        return 0;
+    };
+    int used = 0;
+    while (used < n_chunks && used * chunk < E) ++used;
+    if (int rc = order_after_caller(env, n_str)) return rc;
+    for (int c = 0; c < used && c < n_str; ++c)
+        if (int rc = enqueue_compute(c)) return rc;
+    for (int c = 0; c < used; ++c) {
+        if (int rc = enqueue_copies(c)) return rc;
+        if (c + n_str < used)
+            if (int rc = enqueue_compute(c + n_str)) return rc;
+    }
+    for (int c = 0; c < n_str; ++c) CUDA_OK(cudaStreamSynchronize(env->streams[c]));
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// Host side of the packed path: the observation rows the reference returns (envs/common/observation.py:241-273 with
+// normalize_obs 181-193), rebuilt from the packed state.  Plain CPU code, no device involved.
+int mm_expand_obs_rows(const mm_packed_host *in, int n_envs, int steer_vel, float *obs_rows, int64_t *row_offset, int n_threads) {
+    if (!in || !in->veh || !in->nbr || !in->n_veh || !in->n_agents || !obs_rows || !row_offset)
+        return fail(MM_ERR_ARG, "mm_expand_obs_rows: null argument");
+    if (n_envs < 0) return fail(MM_ERR_ARG, "n_envs must be >= 0");
+    std::vector<int64_t> vbase((size_t)n_envs + 1);
+    int64_t rv = 0, ra = 0;
+    for (int e = 0; e < n_envs; ++e) {
+        vbase[e] = rv; row_offset[e] = ra;
+        rv += in->n_veh[e]; ra += in->n_agents[e];
+    }
+    vbase[n_envs] = rv; row_offset[n_envs] = ra;
+    const double KX = 2.0 / 300.0, KY = 2.0 / 24.0, KV = 2.0 / 90.0, KH = 2.0 / 3.141592653589793, HPI = 3.141592653589793 / 2;
+    auto work = [&](int e0, int e1) {
+        for (int e = e0; e < e1; ++e) {
+            const float *veh = in->veh + vbase[e] * 5;
+            const int n_cav = in->n_agents[e], n_veh = in->n_veh[e];
+            for (int i = 0; i < n_cav && i < n_veh; ++i) {
+                float *row = obs_rows + (row_offset[e] + i) * MM_NS;
+                const double ex = veh[i * 5], ey = veh[i * 5 + 1], evx = veh[i * 5 + 2], evy = veh[i * 5 + 3], eh = veh[i * 5 + 4];
+                row[0] = 1.0f; row[1] = (float)((ex + 150.0) * KX - 1.0); row[2] = (float)((ey + 12.0) * KY - 1.0);
+                row[3] = (float)((evx + 45.0) * KV - 1.0); row[4] = (float)((evy + 45.0) * KV - 1.0);
+                row[5] = (float)((eh + HPI) * KH - 1.0);
+                const unsigned w = in->nbr[row_offset[e] + i];
+                for (int k = 0; k < 4; ++k) {
+                    float *r = row + 6 * (k + 1);
+                    const int o = (int)((w >> (4 * k)) & 15u);
+                    if (o >= n_veh) { r[0] = r[1] = r[2] = r[3] = r[4] = r[5] = 0.f; continue; }
+                    const float *ov = veh + o * 5;
+                    double oh = ov[4];
+                    if (steer_vel && o < n_cav) oh = oh - eh;
+                    r[0] = 1.0f; r[1] = (float)(((double)ov[0] - ex + 150.0) * KX - 1.0);
+                    r[2] = (float)(((double)ov[1] - ey + 12.0) * KY - 1.0); r[3] = (float)(((double)ov[2] - evx + 45.0) * KV - 1.0);
+                    r[4] = (float)(((double)ov[3] - evy + 45.0) * KV - 1.0); r[5] = (float)((oh + HPI) * KH - 1.0);
+                }
+            }
+        }
+    };
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads == 1 || n_envs < 4096) { work(0, n_envs); return 0; }
+    std::vector<std::thread> pool;
+    const int per = (n_envs + n_threads - 1) / n_threads;
+    for (int t = 0; t < n_threads; ++t) {
+        const int e0 = t * per, e1 = e0 + per < n_envs ? e0 + per : n_envs;
+        if (e0 < e1) pool.emplace_back(work, e0, e1);
+    }
+    for (auto &th : pool) th.join();
+    return 0;
+}
+
 int mm_buffers_get(mm_env *env, mm_buffers *b) {
     if (!env || !b) return fail(MM_ERR_ARG, "null argument");
     b->obs = env->out.obs; b->reward = env->out.reward; b->done = env->out.done;
@@ -572,8 +742,9 @@ int mm_supervise(mm_env *env, int kind, int8_t *actions_dev, const double *draws
 }
 
 int mm_set_step_variant(int variant) {
-    if (variant != 0 && variant != 3 && variant != 4 && variant != 5)
-        return fail(MM_ERR_ARG, "variant must be 0 (automatic), 3, 4 (a generic build forced) or 5 (automatic, generic builds only)");
+    if (variant != 0 && (variant < 3 || variant > 7))
+        return fail(MM_ERR_ARG, "variant must be 0 (automatic), 3, 4 (a generic build forced), 5 (automatic, generic builds only) "
+                                "6 (4 CTAs per SM forced, specialised builds allowed) or 7 (warp-cooperative build forced)");
     set_step_variant(variant);
     return 0;
 }

@@ -16,7 +16,8 @@
 //     on the step path (absent rows stay zero from the (re)spawn);
 //   * local rewards go through shared memory to the regional-reward pass; the per-env sums are taken sequentially in
 //     slot order by the env's slot-0 thread (same rounding order as the reference's Python sum);
-//   * statistics: one row of partial sums per 32 envs = per CTA, folded by warp shuffles, no atomics.
+//   * per-env scalars and the statistics row of the CTA's 32 envs are spread over four warps (reward / speed / traffic
+//     speed / headway), each folding its column with warp shuffles: no atomics, no single slow warp.
 //
 // The same kernel with WITH_REWARDS = false writes the first observation after a (re)spawn or mm_set_state.
 #include <cuda_runtime.h>
@@ -26,6 +27,7 @@
 #define MM_KNS mmo
 #define MM_NHOT 6
 #define MM_PW 32
+#define MM_OUT_FN __forceinline__
 #include "mm_device.cuh"
 
 namespace mmo {
@@ -41,9 +43,10 @@ constexpr size_t OUT_SMEM = (size_t)PLANES_F64 * sizeof(double)            // ho
                             + (size_t)2 * OENVS * MAXV * sizeof(float)      // agents / regional rewards
                             + (size_t)2 * OENVS * MAXV                      // agents_dones, action masks
                             + (size_t)OENVS * sizeof(int);                  // rows to write per env (-1: env not written)
+// 74 880 bytes: three CTAs per SM fit the 227 KB of shared memory
 
 #ifndef MM_OUT_MIN_BLOCKS
-#define MM_OUT_MIN_BLOCKS 2
+#define MM_OUT_MIN_BLOCKS 3   // measured: 2 -> 3 CTAs per SM (56 registers) -2.8 % per policy step at 2^20 envs
 #endif
 
 template <bool WITH_REWARDS>
@@ -104,8 +107,9 @@ __global__ void __launch_bounds__(OTHREADS, MM_OUT_MIN_BLOCKS) outputs_kernel(co
     const bool is_agent = valid && i < n_obs;
     {
         float2 *row = reinterpret_cast<float2 *>(s_obs + c * OBS_STRIDE + i * NS);
+        uint32_t nbw = 0xFFFFu;
         if (is_agent) {
-            observe_agent(ev, i, sv, row);
+            nbw = observe_agent(ev, i, sv, row);
         } else if (!WITH_REWARDS) {
 #pragma unroll
             for (int q = 0; q < NS / 2; ++q) row[q] = make_float2(0.f, 0.f);
@@ -113,6 +117,17 @@ __global__ void __launch_bounds__(OTHREADS, MM_OUT_MIN_BLOCKS) outputs_kernel(co
         if (!WITH_REWARDS && i == SMV - 1) {   // slot 11 is never occupied
 #pragma unroll
             for (int q = 0; q < NS / 2; ++q) row[NS / 2 + q] = make_float2(0.f, 0.f);
+        }
+        if (p.out.veh != nullptr && valid) {
+            // packed-state outputs (mm_step_host_packed): what the observation rows are a function of
+            if (has_v) {
+                float *vr = p.out.veh + (e * MAXV + i) * 5;
+                const double sp = V(i);
+                __stcs(vr + 0, (float)X(i)); __stcs(vr + 1, (float)Y(i));
+                __stcs(vr + 2, (float)(sp * CH(i))); __stcs(vr + 3, (float)(sp * SH(i))); __stcs(vr + 4, (float)H(i));
+            }
+            p.out.nbr[e * MAXV + i] = (uint16_t)nbw;
+            if (i == SMV - 1) p.out.nbr[e * MAXV + MAXV - 1] = 0xFFFFu;
         }
     }
     {
@@ -189,54 +204,68 @@ __global__ void __launch_bounds__(OTHREADS, MM_OUT_MIN_BLOCKS) outputs_kernel(co
             s_rr[c * MAXV + MAXV - 1] = 0.f;
             s_ad[c * MAXV + MAXV - 1] = 0;
         }
-        if (i == 0) {
-            // per-env scalars (merge_env_v1.py:126-166, 517-524; abstract.py:489-498), summed in slot order
-            double rsum = 0, ssum = 0, tsum = 0, minhw = CUDART_INF;
+        // per-env scalars (merge_env_v1.py:126-166, 517-524; abstract.py:489-498) and the statistics row of the CTA's 32
+        // envs (one row of partial sums per 32 envs, no atomics; mm_stats() folds the rows).  The sums run in slot order
+        // (the rounding order of the reference's Python sums); the four quantities go to four different warps so that no
+        // single warp holds the CTA back at the final barrier.
+        double *stat_row = p.out.stats + (((size_t)p.env_offset + (size_t)blockIdx.x * OENVS) >> 5) * N_STATS;
+        const unsigned full = 0xffffffffu;
+        auto fold_sum = [&](double x) {
+            for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(full, x, off);
+            return x;
+        };
+        if (i == 0) {          // reward, done, merge percent; episode counters
+            double rsum = 0;
             bool any_crash = false;
             int n_rem = 0;
             for (int k = 0; k < n_obs; ++k) {
                 rsum += s_local[k * OENVS + c];
-                ssum += V(k);
-                minhw = fmin(minhw, s_hw[k * OENVS + c]);
                 const uint32_t fk = FL(k);
                 any_crash = any_crash || (fk & FL_CRASHED);
                 const int lane = fl_lane(fk);
                 if (lane == L_BC1 || lane == L_KB0 || lane == L_JK0) ++n_rem;
             }
-            for (int k = 0; k < ev.n_veh; ++k) tsum += V(k);
-            double st_agent = 0, st_env = 0, st_epi = 0, st_crash = 0, st_rew = 0, st_speed = 0, st_merge = 0, st_minhw = CUDART_INF;
+            double reward = 0, mp = -1.0;
+            bool done = false;
             if (valid) {
-                const bool done = is_terminal(ev, steps, p.cfg);
-                const double reward = rsum / n_obs;
-                double mp = -1.0;
+                done = is_terminal(ev, steps, p.cfg);
+                reward = rsum / n_obs;
                 if (done) mp = n_merge > 0 ? (double)(n_merge - n_rem) / n_merge * 100 : 100.0;
-                const DevOut &o = p.out;
-                o.reward[e] = (float)reward;
-                o.done[e] = done ? 1 : 0;
-                o.average_speed[e] = (float)(ssum / n_obs);
-                o.traffic_speed[e] = (float)(tsum / ev.n_veh);
-                o.min_headway[e] = (float)minhw;
-                o.merge_percent[e] = (float)mp;
-                st_agent = n_obs; st_env = 1; st_rew = reward; st_speed = ssum / n_obs; st_minhw = minhw;
-                if (done) { st_epi = 1; st_crash = any_crash; st_merge = mp; }
+                p.out.reward[e] = (float)reward;
+                p.out.done[e] = done ? 1 : 0;
+                p.out.merge_percent[e] = (float)mp;
+                p.out.n_agents[e] = n_obs;
             }
-            // one row of partial sums per 32 envs (= this warp): no atomics; mm_stats() folds the rows
-            const unsigned full = 0xffffffffu;
-            double v[8] = {st_agent, st_env, st_epi, st_crash, st_rew, st_speed, st_merge, st_minhw};
-            const int slot[8] = {ST_AGENT_STEPS, ST_ENV_STEPS, ST_EPISODES, ST_CRASHED, ST_REWARD, ST_SPEED, ST_MERGE, ST_MINHW};
-            double *rowp = p.out.stats + (((size_t)p.env_offset + (size_t)blockIdx.x * OENVS) >> 5) * N_STATS;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                double x = v[k];
-                for (int off = 16; off > 0; off >>= 1) {
-                    const double y = __shfl_down_sync(full, x, off);
-                    x = (k == 7) ? fmin(x, y) : x + y;
-                }
-                if (c == 0) rowp[slot[k]] = (k == 7) ? fmin(rowp[slot[k]], x) : rowp[slot[k]] + x;
+            const int agents = __reduce_add_sync(full, valid ? n_obs : 0), envs = __reduce_add_sync(full, valid ? 1 : 0);
+            const int episodes = __reduce_add_sync(full, done ? 1 : 0), crashed = __reduce_add_sync(full, (done && any_crash) ? 1 : 0);
+            const double rew = fold_sum(reward), mrg = fold_sum(done ? mp : 0.0);
+            if (c == 0) {
+                stat_row[ST_AGENT_STEPS] += (double)agents; stat_row[ST_ENV_STEPS] += (double)envs;
+                stat_row[ST_EPISODES] += (double)episodes; stat_row[ST_CRASHED] += (double)crashed;
+                stat_row[ST_REWARD] += rew; stat_row[ST_MERGE] += mrg;
             }
+        } else if (i == 1) {   // average speed of the observed vehicles
+            double ssum = 0;
+            for (int k = 0; k < n_obs; ++k) ssum += V(k);
+            const double avg = valid ? ssum / n_obs : 0.0;
+            if (valid) p.out.average_speed[e] = (float)avg;
+            const double spd = fold_sum(avg);
+            if (c == 0) stat_row[ST_SPEED] += spd;
+        } else if (i == 2) {   // traffic speed: every vehicle
+            double tsum = 0;
+            for (int k = 0; k < ev.n_veh; ++k) tsum += V(k);
+            if (valid) p.out.traffic_speed[e] = (float)(tsum / ev.n_veh);
+        } else if (i == 3) {   // smallest time headway
+            double minhw = CUDART_INF;
+            for (int k = 0; k < n_obs; ++k) minhw = fmin(minhw, s_hw[k * OENVS + c]);
+            if (valid) p.out.min_headway[e] = (float)minhw;
+            double x = valid ? minhw : CUDART_INF;
+            for (int off = 16; off > 0; off >>= 1) x = fmin(x, __shfl_down_sync(full, x, off));
+            if (c == 0) stat_row[ST_MINHW] = fmin(stat_row[ST_MINHW], x);
         }
+    } else if (i == 0 && valid) {
+        p.out.n_agents[e] = n_obs;
     }
-    if (i == 0 && valid) p.out.n_agents[e] = n_obs;
     __syncthreads();
 
     // coalesced write-out of the CTA's blocks.  Observation rows: warp w takes envs w, w + 11, w + 22.
@@ -260,6 +289,84 @@ __global__ void __launch_bounds__(OTHREADS, MM_OUT_MIN_BLOCKS) outputs_kernel(co
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// packed-state rows for the host path (mm_step_host_packed)
+// ------------------------------------------------------------------------------------------------
+// Pass 1: exclusive scans of n_veh and n_agents over the chunk (one CTA), chained to the totals of the previous chunk.
+// Pass 2: a warp moves one env's vehicle rows and neighbour words to their packed place.  Offsets are absolute and
+// dense over the whole batch, so the host derives them from the two count arrays alone.
+__global__ void __launch_bounds__(1024) packed_offsets_kernel(const uint32_t *__restrict__ einfo, const int32_t *__restrict__ n_agents,
+                                                              int count, const int64_t *__restrict__ base_in,
+                                                              int64_t *__restrict__ base_out, int32_t *__restrict__ voff,
+                                                              int32_t *__restrict__ aoff, uint8_t *__restrict__ n_veh_u8,
+                                                              uint8_t *__restrict__ n_agents_u8) {
+    __shared__ int wv[32], wa[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (count + 1023) / 1024;
+    const int lo = min(tid * per, count), hi = min(lo + per, count);
+    int sv = 0, sa = 0;
+    for (int e = lo; e < hi; ++e) {
+        sv += (int)((einfo[e] >> EI_NVEH_SHIFT) & EI_4BIT);
+        sa += n_agents[e];
+    }
+    int iv = sv, ia = sa;
+    for (int off = 1; off < 32; off <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, iv, off), b = __shfl_up_sync(0xffffffffu, ia, off);
+        if (lane >= off) { iv += a; ia += b; }
+    }
+    if (lane == 31) { wv[warp] = iv; wa[warp] = ia; }
+    __syncthreads();
+    if (warp == 0) {
+        const int a = wv[lane], b = wa[lane];
+        int xa = a, xb = b;
+        for (int off = 1; off < 32; off <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, xa, off), w = __shfl_up_sync(0xffffffffu, xb, off);
+            if (lane >= off) { xa += u; xb += w; }
+        }
+        wv[lane] = xa - a;
+        wa[lane] = xb - b;
+        if (lane == 31) {     // totals of this chunk, chained
+            base_out[0] = base_in[0] + xa;
+            base_out[1] = base_in[1] + xb;
+        }
+    }
+    __syncthreads();
+    int rv = wv[warp] + (iv - sv), ra = wa[warp] + (ia - sa);
+    for (int e = lo; e < hi; ++e) {
+        const int nv = (int)((einfo[e] >> EI_NVEH_SHIFT) & EI_4BIT), na = n_agents[e];
+        voff[e] = rv; aoff[e] = ra;
+        n_veh_u8[e] = (uint8_t)nv; n_agents_u8[e] = (uint8_t)na;
+        rv += nv; ra += na;
+    }
+}
+
+__global__ void __launch_bounds__(256) packed_copy_kernel(const float *__restrict__ veh, const uint16_t *__restrict__ nbr,
+                                                          const uint8_t *__restrict__ n_veh_u8, const uint8_t *__restrict__ n_agents_u8,
+                                                          const int32_t *__restrict__ voff, const int32_t *__restrict__ aoff, int count,
+                                                          const int64_t *__restrict__ base_in, float *__restrict__ veh_packed,
+                                                          uint16_t *__restrict__ nbr_packed) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int64_t bv = base_in[0], ba = base_in[1];
+    for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < count; e += warps) {
+        const int nf = (int)n_veh_u8[e] * 5;
+        const float *src = veh + (size_t)e * MAXV * 5;
+        float *dst = veh_packed + (bv + voff[e]) * 5;
+        for (int k = lane; k < nf; k += 32) dst[k] = __ldcs(src + k);
+        const int na = (int)n_agents_u8[e];
+        if (lane < na) nbr_packed[ba + aoff[e] + lane] = nbr[(size_t)e * MAXV + lane];
+    }
+}
+
+void launch_packed_pack_impl(const uint32_t *einfo, const int32_t *n_agents, const float *veh, const uint16_t *nbr, int count,
+                             const int64_t *base_in, int64_t *base_out, int32_t *voff, int32_t *aoff, float *veh_packed,
+                             uint16_t *nbr_packed, uint8_t *n_veh_u8, uint8_t *n_agents_u8, void *stream) {
+    if (count <= 0) return;
+    packed_offsets_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(einfo, n_agents, count, base_in, base_out, voff, aoff, n_veh_u8, n_agents_u8);
+    packed_copy_kernel<<<(count + 7) / 8, 256, 0, (cudaStream_t)stream>>>(veh, nbr, n_veh_u8, n_agents_u8, voff, aoff, count, base_in,
+                                                                        veh_packed, nbr_packed);
+}
+
 void launch_outputs_impl(const StepParams &p, bool with_rewards, void *stream) {
     static bool ready[MM_MAX_DEVICES] = {};
     int dev = 0;
@@ -280,4 +387,10 @@ void launch_outputs_impl(const StepParams &p, bool with_rewards, void *stream) {
 
 namespace mm {
 void launch_outputs(const StepParams &p, bool with_rewards, void *stream) { mmo::launch_outputs_impl(p, with_rewards, stream); }
+void launch_packed_pack(const uint32_t *einfo, const int32_t *n_agents, const float *veh, const uint16_t *nbr, int count,
+                        const int64_t *base_in, int64_t *base_out, int32_t *voff, int32_t *aoff, float *veh_packed,
+                        uint16_t *nbr_packed, uint8_t *n_veh_u8, uint8_t *n_agents_u8, void *stream) {
+    mmo::launch_packed_pack_impl(einfo, n_agents, veh, nbr, count, base_in, base_out, voff, aoff, veh_packed, nbr_packed, n_veh_u8,
+                                 n_agents_u8, stream);
+}
 }  // namespace mm

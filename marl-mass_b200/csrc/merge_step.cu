@@ -34,7 +34,20 @@
 //     the benchmark configurations - every vehicle a CAV (no IDM / MOBIL code, no second act pass), env id
 //     merge-multi-agent-v1 with lateral_control = "steer", the shield kind a constant.  Same source, same arithmetic;
 //     launch_step picks it when the handle's config matches and no env can hold an HDV.
-#if defined(MM_VARIANT4)
+#if defined(MM_VARIANT4) && defined(MM_SPEC_SHIELD)      // both: merge_step_spec_mass4.cu / _hss4.cu
+#define MM_SPEC 1
+#define MM_NHOT 4
+#ifndef MM_MIN_BLOCKS
+#define MM_MIN_BLOCKS 4
+#endif
+#if MM_SPEC_SHIELD == 2
+#define MM_KNS mms_mass4
+#define MM_VARIANT_LAUNCH launch_step_spec_mass4
+#else
+#define MM_KNS mms_hss4
+#define MM_VARIANT_LAUNCH launch_step_spec_hss4
+#endif
+#elif defined(MM_VARIANT4)
 #define MM_KNS mm4
 #define MM_NHOT 4
 #ifndef MM_MIN_BLOCKS
@@ -78,8 +91,10 @@ constexpr uint32_t HOT_FLAG_BYTES = (uint32_t)MAXV * TILE * sizeof(uint32_t);
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void tile_bulk_load(const DevState &st, size_t tile, uint64_t *mbar) {
-    // called by every thread of the CTA; thread 0 arms the barrier and issues the copies
+// issue: called by every thread of the CTA; thread 0 arms the barrier and starts the copies.  wait: every thread spins on
+// the barrier's phase.  Between the two the caller issues its own global loads (env scalars, the action tuple) so that
+// their latency overlaps the tile transfer instead of following it.
+__device__ __forceinline__ void tile_bulk_load_issue(const DevState &st, size_t tile, uint64_t *mbar) {
     const uint32_t bar = smem_u32(mbar);
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
@@ -97,6 +112,9 @@ __device__ __forceinline__ void tile_bulk_load(const DevState &st, size_t tile, 
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(smem_u32(sm_planes + N_HOT * SMV * BLOCK)), "l"(gfl), "r"(HOT_FLAG_BYTES), "r"(bar) : "memory");
     }
+}
+__device__ __forceinline__ void tile_bulk_load_wait(uint64_t *mbar) {
+    const uint32_t bar = smem_u32(mbar);
     uint32_t done = 0;
     while (!done) {
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
@@ -225,16 +243,20 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
     int steps = 0, time = 0;
     __shared__ uint64_t s_mbar;
     const size_t tile = ((size_t)p.env_offset + (size_t)blockIdx.x * BLOCK) / TILE;   // launches are tile-aligned
-    if (MM_TMA) tile_bulk_load(p.st, tile, &s_mbar);
+    if (MM_TMA) tile_bulk_load_issue(p.st, tile, &s_mbar);
     if (valid) {
+        // env scalars and the 12 action bytes: requested while the tile is in flight
         ei = p.st.einfo[e];
+        const uint32_t *a32 = reinterpret_cast<const uint32_t *>(p.actions + e * MAXV);
+        act_lo = a32[0]; act_mid = a32[1]; act_hi = a32[2];
+    }
+    if (MM_TMA) tile_bulk_load_wait(&s_mbar);
+    if (valid) {
         ev.n_veh = (ei >> EI_NVEH_SHIFT) & EI_4BIT;
         ev.n_cav = (ei >> EI_NCAV_SHIFT) & EI_4BIT;
         steps = (ei >> EI_STEPS_SHIFT) & EI_STEPS_MASK;
         time = (ei >> EI_TIME_SHIFT) & EI_TIME_MASK;
         if (!MM_TMA) load_env(ev, p.st, e);
-        const uint32_t *a32 = reinterpret_cast<const uint32_t *>(p.actions + e * MAXV);  // 12 action bytes
-        act_lo = a32[0]; act_mid = a32[1]; act_hi = a32[2];
         if (DIAG) {
             size_t plane = (size_t)p.n_envs * 3 * MAXV;
             for (int k = 0; k < 3 * MAXV; ++k) {
@@ -664,11 +686,12 @@ void launch_step_impl(const StepParams &p, bool diag, void *stream) {
 
 #ifndef MM_VARIANT_TU
 static int g_step_variant = 0;
-void set_step_variant(int v) { g_step_variant = (v == 3 || v == 4 || v == 5) ? v : 0; }
+void set_step_variant(int v) { g_step_variant = (v >= 3 && v <= 7) ? v : 0; }
 
 // Picks the build of the step kernel: 4 CTAs / SM when the wave structure of the grid favours it (e.g. 512 CTAs on 148
 // SMs: one wave instead of a full and an almost empty one), else the default 3 CTAs / SM build.
 int launch_step(const StepParams &p, bool diag, void *stream) {
+    const mm_config &c = p.cfg;
     const int grid = (p.env_count + BLOCK - 1) / BLOCK;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -681,14 +704,20 @@ int launch_step(const StepParams &p, bool diag, void *stream) {
     };
     static const double lat3[4] = {0.0, 9.55, 11.42, 12.27}, lat4[5] = {0.0, 10.5, 12.6, 13.5, 16.2};
     const bool small_grid = grid <= 8 * sms;      // measured: still ahead at 1024 CTAs, behind at 1536 (time_variants.py)
-    const bool four = g_step_variant == 4 || (g_step_variant == 0 && !diag && !p.cfg.couple_counts && small_grid &&
+    const bool automatic = g_step_variant == 0 || g_step_variant == 5;
+    const bool four = g_step_variant == 4 || g_step_variant == 6 || (automatic && !diag && !p.cfg.couple_counts && small_grid &&
                                               estimate(4, lat4) < 0.97 * estimate(3, lat3));
     // the specialised builds: all-CAV envs of the plain LC env (v1, lateral_control "steer") under MASS or HSS
-    const mm_config &c = p.cfg;
-    const bool spec_ok = g_step_variant == 0 && !four && p.all_cav && !c.couple_counts && !c.env_v0 && !c.steer_vel &&
+    const bool plain_all_cav = p.all_cav && !c.couple_counts && !c.env_v0 && !c.steer_vel && !c.env_hdv && c.traffic_type == MM_TRAFFIC_CAV;
+    // the warp-cooperative build (merge_coop.cu): half a warp per env, for grids too small to fill the machine with
+    // one thread per env
+    if (g_step_variant == 7 && plain_all_cav) { launch_step_coop(p, diag, stream); return MM_BUILD_COOP + c.shield; }
+    const bool spec_ok = (g_step_variant == 0 || g_step_variant == 6) && p.all_cav && !c.couple_counts && !c.env_v0 && !c.steer_vel &&
                          !c.env_hdv && c.traffic_type == MM_TRAFFIC_CAV;
-    if (spec_ok && c.shield == MM_SHIELD_MASS) { launch_step_spec_mass(p, diag, stream); return MM_BUILD_SPEC_MASS; }
-    if (spec_ok && c.shield == MM_SHIELD_HSS) { launch_step_spec_hss(p, diag, stream); return MM_BUILD_SPEC_HSS; }
+    if (spec_ok && four && c.shield == MM_SHIELD_MASS) { launch_step_spec_mass4(p, diag, stream); return MM_BUILD_SPEC_MASS4; }
+    if (spec_ok && four && c.shield == MM_SHIELD_HSS) { launch_step_spec_hss4(p, diag, stream); return MM_BUILD_SPEC_HSS4; }
+    if (spec_ok && !four && c.shield == MM_SHIELD_MASS) { launch_step_spec_mass(p, diag, stream); return MM_BUILD_SPEC_MASS; }
+    if (spec_ok && !four && c.shield == MM_SHIELD_HSS) { launch_step_spec_hss(p, diag, stream); return MM_BUILD_SPEC_HSS; }
     if (four) { launch_step_occ4(p, diag, stream); return MM_BUILD_GENERIC4; }
     launch_step_impl(p, diag, stream);
     return MM_BUILD_GENERIC3;

@@ -68,6 +68,11 @@ struct DevOut {
           *merge_percent;
     uint8_t *done, *agents_dones, *action_mask;
     int32_t *n_agents;
+    // packed-state outputs (mm_step_host_packed; null until that path is first used): per vehicle x, y, vx, vy, heading
+    // as float32 [E][MAXV][5], and per agent the slots of its (up to) 4 observed neighbours, 4 bits each in observation
+    // order, 0xF = none [E][MAXV]
+    float *veh;
+    uint16_t *nbr;
     // per-sub-step shield record [E][3][MAXV] (record_diag only, else null)
     int32_t *sh_i;      // 10 planes: ran, leader, front_adj, rear_adj, constrain_adj, active, is_lc_safe, moved, hl_action, lane
     double *sh_f;       // 10 planes: safe_acc, safe_steer, nom_acc, nom_steer, lc_margin, x, y, heading, speed, min_headway
@@ -105,6 +110,10 @@ void launch_step_occ4(const StepParams &p, bool diag, void *stream);
 // the same kernel specialised at compile time for all-CAV envs of the plain LC env (merge_step_spec_mass.cu / _hss.cu)
 void launch_step_spec_mass(const StepParams &p, bool diag, void *stream);
 void launch_step_spec_hss(const StepParams &p, bool diag, void *stream);
+void launch_step_spec_mass4(const StepParams &p, bool diag, void *stream);   // ... and for 4 CTAs per SM
+void launch_step_spec_hss4(const StepParams &p, bool diag, void *stream);
+// the warp-cooperative build: half a warp per env, one lane per vehicle (merge_coop.cu); all-CAV plain LC envs only
+void launch_step_coop(const StepParams &p, bool diag, void *stream);
 void set_step_variant(int v);   // 0: automatic, 3 / 4: force the generic 3- or 4-CTAs-per-SM build, 5: automatic without the specialised builds
 void launch_reset(const ResetParams &p, void *stream);
 // outputs kernel (merge_outputs.cu): observations, rewards, terminal flags, info scalars and statistics of the policy step
@@ -123,6 +132,13 @@ void launch_qp(const double *a, const double *c_lead, const double *c_adj, const
 // buffer [E * MAXV][NS] (row offsets are absolute); chunk_rows_dev receives the chunk's packed row count
 void launch_ragged_pack(const float *obs, const int32_t *n_agents, int count, int64_t base_row, int64_t *row_offset_dev,
                         int64_t *chunk_rows_dev, float *rows_stage, void *stream);
+
+// mm_step_host_packed: exclusive scans of n_veh / n_agents over a chunk of envs (chained to the previous chunk's totals
+// through base_in -> base_out, two int64 each: vehicles, agents) and the ragged copy of the chunk's vehicle rows and
+// neighbour words to their packed place
+void launch_packed_pack(const uint32_t *einfo, const int32_t *n_agents, const float *veh, const uint16_t *nbr, int count,
+                        const int64_t *base_in, int64_t *base_out, int32_t *voff, int32_t *aoff, float *veh_packed,
+                        uint16_t *nbr_packed, uint8_t *n_veh_u8, uint8_t *n_agents_u8, void *stream);
 
 // caller-side kernels (actor_sample.cu)
 int launch_actor_sample(const float *obs, const int32_t *n_agents, int64_t n_rows, const float *w1, const float *b1,

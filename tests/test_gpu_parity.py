@@ -163,7 +163,7 @@ def test_four_ctas_per_sm_build_of_the_step_kernel(mm, orc, shield, traffic, td,
     computes the same step: the strict lock-step comparison with that build forced."""
     try:
         mm.set_step_variant(4)
-        lockstep_rollout(mm, orc, shield, traffic, td, reward, 4096, 40, STATE_TOL)
+        lockstep_rollout(mm, orc, shield, traffic, td, reward, 4096, 40, STATE_TOL, expect_build=(4,))
     finally:
         mm.set_step_variant(0)
 
@@ -176,6 +176,32 @@ def test_generic_builds_on_all_cav_scenes(mm, orc, shield, variant):
     try:
         mm.set_step_variant(variant)
         lockstep_rollout(mm, orc, shield, "cav", 3, "default", 4096, 40, STATE_TOL, expect_build=(3,))
+    finally:
+        mm.set_step_variant(0)
+
+
+@pytest.mark.parametrize("shield,td,reward,T,resync", [
+    ("cbf-cav", 3, "default", 40, False), ("cbf-avs_cint", 3, "srew", 40, False), ("none", 3, "default", 40, False),
+    ("cbf-cav", 1, "mrew", 40, False), ("cbf-cav", 3, "srew", 100, True), ("cbf-avs_cint", 3, "default", 100, True)])
+def test_warp_cooperative_build_of_the_step_kernel(mm, orc, shield, td, reward, T, resync):
+    """The warp-cooperative build (merge_coop.cu: half a warp per env, one lane per vehicle, parallel neighbour
+    classification over per-lane views, fixed-point rounds for the MASS acceleration chain, re-steer fix-ups) computes the
+    same policy step as the one-thread-per-env kernel: the strict lock-step comparison with that build forced, free
+    running for 40 steps and teacher-forced over the whole 100-step episode."""
+    try:
+        mm.set_step_variant(7)
+        build = {"none": 50, "cbf-avs_cint": 51, "cbf-cav": 52}[shield]
+        lockstep_rollout(mm, orc, shield, "cav", td, reward, 4096 if T == 40 else 2048, T, STATE_TOL, resync=resync,
+                         expect_build=(build,))
+    finally:
+        mm.set_step_variant(0)
+
+
+def test_exact_ties_with_the_warp_cooperative_build(mm, orc):
+    try:
+        mm.set_step_variant(7)
+        tie_rollout(mm, orc, "cbf-cav", "cav", 3, False)
+        tie_rollout(mm, orc, "cbf-avs_cint", "cav", 3, True)
     finally:
         mm.set_step_variant(0)
 
@@ -282,7 +308,7 @@ def lockstep_rollout(mm, orc, shield, traffic, td, reward, E, T, state_tol, resy
             assert env.step_build() in expect_build, env.step_build()
         elif traffic == "cav" and lateral == "steer" and shield != "none":
             # all-CAV scenes of the plain LC env: the specialised builds (31 HSS, 32 MASS) unless a test forces another
-            assert env.step_build() in (31, 32, 4), env.step_build()
+            assert env.step_build() in (31, 32, 41, 42), env.step_build()
         # compare only envs that had not finished before this step (finished envs are not stepped by MAPPO) and, in the
         # whole-episode runs, that are still well conditioned (see below)
         sel = np.where(alive & clean)[0]
