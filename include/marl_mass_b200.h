@@ -35,6 +35,7 @@ enum { MM_SHIELD_NONE = 0, MM_SHIELD_HSS = 1, MM_SHIELD_MASS = 2 };
 enum { MM_REW_DEFAULT = 0, MM_REW_SREW = 1, MM_REW_MREW = 2 };
 enum { MM_TRAFFIC_CAV = 0, MM_TRAFFIC_MIXED = 1, MM_TRAFFIC_AV = 2 /* one CAV, the rest HDVs (merge_env_v1.py:485-489) */,
        MM_TRAFFIC_HDV = 3 /* HDVs only (490-494); with env_hdv */ };
+enum { MM_SUPERVISOR_NONE = 0, MM_SUPERVISOR_PRIORITY = 1, MM_SUPERVISOR_DMC = 2 };
 enum { MM_NB_NONE = -1, MM_NB_OBSTACLE = -2 };
 /* QP active-set code reported per shield solve */
 enum { MM_ACT_LEAD = 1, MM_ACT_UPPER = 2, MM_ACT_LOWER = 4, MM_ACT_ADJ = 8, MM_ACT_SLACK = 16 };
@@ -45,7 +46,7 @@ enum { MM_ACT_LEAD = 1, MM_ACT_UPPER = 2, MM_ACT_LOWER = 4, MM_ACT_ADJ = 8, MM_A
  * signature; mm_abi_version() returns the value the library was built with, and mm_create / mm_set_config reject a
  * config whose struct_size field is not sizeof(mm_config) (a binding built against another revision of the header
  * fails loudly instead of handing the library garbage). */
-#define MM_ABI_VERSION 4
+#define MM_ABI_VERSION 5
 int mm_abi_version(void);
 
 typedef struct {
@@ -72,6 +73,9 @@ typedef struct {
     int32_t env_hdv;         /* 1: env id merge-multi-agent-hdv-v1 (MergeEnvLCHDV, merge_env_v1.py:552-674; traffic_type
                                 hdv): no controlled vehicles - every vehicle is observed and rewarded (its row in obs /
                                 agents_rewards), any crash ends the episode, no regional rewards / per-agent dones */
+    int32_t supervisor;      /* safety_guarantee: priority -> PRIORITY, dmc -> DMC, else NONE.  The look-ahead baselines
+                                (vehicle/safety/central_layer.py:16-178, decentralised_dmc.py:70-198) that AbstractEnv.step
+                                runs on the action tuple before _simulate (abstract.py:459-464); shield must be NONE */
 } mm_config;
 
 typedef struct mm_env mm_env;
@@ -109,6 +113,8 @@ typedef struct {
     int8_t *actions;          /* [n_envs][MM_MAXV] device-side action buffer read by mm_step(actions=NULL) */
     uint8_t *action_mask;     /* [n_envs][MM_MAXV] bit a = meta-action a available (_get_available_actions,
                                  abstract.py:219-240), per agent; info["action_mask"] when action_masking is on */
+    int8_t *new_actions;      /* [n_envs][MM_MAXV] info["new_action"]: the tuple _simulate executed when a baseline
+                                 supervisor is configured (abstract.py:458-467); not written otherwise */
 } mm_buffers;
 
 /* Host arrays receiving the per-sub-step shield record of the last mm_step, [n_envs][3][MM_MAXV].
@@ -230,11 +236,15 @@ int mm_discounted_returns(const float *rewards, const uint8_t *dones, const floa
  * (6 staged fields, 168 registers; the faster one per unit of work), generic for 4 CTAs per SM (4 staged fields, 128
  * registers), and two builds specialised at compile time for all-CAV envs of env id merge-multi-agent-v1 with
  * lateral_control "steer" under the MASS / the HSS shield (no IDM / MOBIL code, configuration reads folded to constants).
- * 0 (default): automatic - a specialised build when the handle's config matches and none of its envs can hold an HDV
- * (spawned under traffic_type cav, or checked by mm_set_state); the 4-CTA build for small grids whose wave structure
+ * A fifth build maps half a warp to an env and a lane to a vehicle (the warp-cooperative build, merge_coop.cu) for
+ * batches too small to fill the machine with one thread per env.
+ * 0 (default): automatic - for all-CAV envs of the plain LC env the warp-cooperative build up to 12 288 envs and a
+ * specialised build above (when none of the handle's envs can hold an HDV: spawned under traffic_type cav, or checked by
+ * mm_set_state); the 4-CTA build for small grids whose wave structure
  * favours it (e.g. 65 536 envs = 512 CTAs on 148 SMs: one wave instead of a full and an almost empty one, -27 % step
  * time).  3 / 4: force a generic build; 5: automatic among the generic builds only; 6: 4 CTAs per SM forced, specialised
- * builds allowed; 7: the warp-cooperative build forced where it applies (process-wide; tests and A/B timing). */
+ * builds allowed; 7: the warp-cooperative build forced where it applies; 8: automatic among the one-thread-per-env builds
+ * (process-wide; tests and A/B timing). */
 int mm_set_step_variant(int variant);
 enum { MM_BUILD_GENERIC3 = 3, MM_BUILD_GENERIC4 = 4, MM_BUILD_SPEC_HSS = 31, MM_BUILD_SPEC_MASS = 32,
        MM_BUILD_SPEC_HSS4 = 41, MM_BUILD_SPEC_MASS4 = 42 /* specialised and built for 4 CTAs per SM */,
@@ -242,16 +252,23 @@ enum { MM_BUILD_GENERIC3 = 3, MM_BUILD_GENERIC4 = 4, MM_BUILD_SPEC_HSS = 31, MM_
 /* which build the handle's last mm_step / mm_step_host* launched (0 before the first step) */
 int mm_step_build(const mm_env *env);
 
-/* EXPERIMENTAL - the baseline supervisors of env merge-multi-agent-v0 (safety_guarantee = priority | dmc:
- * highway_env/vehicle/safety/central_layer.py:16-178, decentralised_dmc.py:70-198; called from AbstractEnv.step before
- * _simulate, abstract.py:459-467).  Rewrites the meta-action tuples in place: actions [n_envs][MM_MAXV] int8 DEVICE;
- * kind 0 = priority, 1 = dmc; draws [n_envs][MM_SUPERVISOR_DRAWS] f64 DEVICE = the uniform [0,1) numbers the reference
- * takes from np.random.rand() (one per CAV, then two per IDM decision of the look-ahead).  Returns the reference's
- * tuples on every step of the reference fixtures, built for the host and (fully inlined build) on a B200
- * (tests/test_zz_supervisor_gpu.py).
- * Not wired in yet: mm_step does not call it and the config layer still rejects the two values. */
+/* The baseline supervisors of safety_guarantee = priority | dmc (highway_env/vehicle/safety/central_layer.py:16-178,
+ * decentralised_dmc.py:70-198; called from AbstractEnv.step before _simulate, abstract.py:459-467).  With
+ * mm_config.supervisor set, mm_step / mm_step_host* run them on every policy step: the supervised tuples land in
+ * mm_buffers.new_actions and are what the step executes.  The reference draws np.random.rand() numbers for them (one per
+ * CAV for the priority tie-break, then two per IDM decision of the look-ahead); the batched path draws from
+ * Philox4x32-10 keyed (seed, env, episode, policy step).  For teacher forcing and for the seed-exact single-env adapter
+ * the caller can supply the draws: mm_set_supervisor_draws(draws_dev [n_envs][MM_SUPERVISOR_DRAWS] f64 DEVICE, consumed in
+ * order; NULL returns to Philox) applies to every following step until changed, and mm_supervisor_draws_used copies to
+ * the host how many draws each env consumed in the last step (the adapter advances its MT19937 replay by that).
+ *
+ * mm_supervise is the supervisor alone: rewrites actions [n_envs][MM_MAXV] int8 DEVICE in place for the current scenes;
+ * kind 0 = priority, 1 = dmc; draws_dev as above (NULL: Philox); n_used_dev (nullable) [n_envs] int32 DEVICE.  It returns
+ * the reference's tuples on every step of the reference fixtures (tests/test_zz_supervisor_gpu.py). */
 #define MM_SUPERVISOR_DRAWS 32
-int mm_supervise(mm_env *env, int kind, int8_t *actions_dev, const double *draws_dev, void *stream);
+int mm_supervise(mm_env *env, int kind, int8_t *actions_dev, const double *draws_dev, int32_t *n_used_dev, void *stream);
+int mm_set_supervisor_draws(mm_env *env, const double *draws_dev);
+int mm_supervisor_draws_used(mm_env *env, int32_t *n_used_host);
 
 /* Launch bookkeeping for bench.py ("gpu_launches") */
 int64_t mm_kernel_launches(const mm_env *env);

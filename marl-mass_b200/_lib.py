@@ -28,7 +28,7 @@ _PU8 = C.POINTER(C.c_uint8)
 _PI8 = C.POINTER(C.c_int8)
 
 
-ABI_VERSION = 4           # MM_ABI_VERSION of the header this binding was written against
+ABI_VERSION = 5           # MM_ABI_VERSION of the header this binding was written against
 
 
 class MMConfig(C.Structure):
@@ -38,7 +38,7 @@ class MMConfig(C.Structure):
                 ("dt", C.c_double), ("eta", C.c_double), ("tau", C.c_double),
                 ("collision_reward", C.c_double), ("high_speed_reward", C.c_double), ("headway_cost", C.c_double),
                 ("headway_time", C.c_double), ("merging_lane_cost", C.c_double), ("env_v0", C.c_int32),
-                ("steer_vel", C.c_int32), ("couple_counts", C.c_int32), ("env_hdv", C.c_int32)]
+                ("steer_vel", C.c_int32), ("couple_counts", C.c_int32), ("env_hdv", C.c_int32), ("supervisor", C.c_int32)]
 
 
     def __init__(self, *args, **kw):
@@ -54,7 +54,7 @@ class MMBuffers(C.Structure):
     _fields_ = [("obs", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p), ("agents_rewards", C.c_void_p),
                 ("regional_rewards", C.c_void_p), ("agents_dones", C.c_void_p), ("average_speed", C.c_void_p),
                 ("traffic_speed", C.c_void_p), ("min_headway", C.c_void_p), ("merge_percent", C.c_void_p),
-                ("n_agents", C.c_void_p), ("actions", C.c_void_p), ("action_mask", C.c_void_p)]
+                ("n_agents", C.c_void_p), ("actions", C.c_void_p), ("action_mask", C.c_void_p), ("new_actions", C.c_void_p)]
 
 
 class MMPackedHost(C.Structure):
@@ -82,7 +82,7 @@ SUPERVISOR_DRAWS = 32     # MM_SUPERVISOR_DRAWS
 EXPORTS = ("mm_create", "mm_destroy", "mm_set_config", "mm_num_envs", "mm_reset", "mm_step", "mm_step_host",
            "mm_step_host_ragged", "mm_step_host_packed", "mm_expand_obs_rows",
            "mm_buffers_get", "mm_get_state", "mm_set_state", "mm_get_shield_diag", "mm_stats", "mm_shield_qp",
-           "mm_actor_sample", "mm_set_actor_impl", "mm_set_step_variant", "mm_step_build", "mm_abi_version", "mm_discounted_returns", "mm_supervise",
+           "mm_actor_sample", "mm_set_actor_impl", "mm_set_step_variant", "mm_step_build", "mm_abi_version", "mm_discounted_returns", "mm_supervise", "mm_set_supervisor_draws", "mm_supervisor_draws_used",
            "mm_kernel_launches", "mm_last_error", "mm_version")
 
 
@@ -127,7 +127,9 @@ def lib():
     L.mm_kernel_launches.restype = C.c_int64
     L.mm_last_error.restype = C.c_char_p
     L.mm_version.restype = C.c_char_p
-    L.mm_supervise.argtypes = [h, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mm_supervise.argtypes = [h, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mm_set_supervisor_draws.argtypes = [h, C.c_void_p]
+    L.mm_supervisor_draws_used.argtypes = [h, C.c_void_p]
     for name in EXPORTS:
         if name not in ("mm_kernel_launches", "mm_last_error", "mm_version"):
             getattr(L, name).restype = C.c_int

@@ -46,6 +46,11 @@ struct mm_env {
     DevState st{};
     DevOut out{};
     int8_t *actions = nullptr;
+    // baseline supervisors (mm_config.supervisor): the tuples _simulate executes (info["new_action"]), the draws a caller
+    // supplied for the next steps (null: Philox), the draws each env consumed in the last step
+    int8_t *new_actions = nullptr;
+    const double *sup_draws = nullptr;
+    int32_t *sup_used = nullptr;
     // mm_step_host_ragged, allocated on first use: first packed row of every env, packed-row staging, per-chunk counts
     int64_t *row_offset = nullptr;
     float *rows_stage = nullptr;
@@ -103,6 +108,9 @@ int validate(const mm_config *c) {
     if (c->substeps < 1 || c->substeps > 3) return fail(MM_ERR_ARG, "substeps must be in 1..3");
     if (c->duration_steps < 1 || c->duration_steps > 255) return fail(MM_ERR_ARG, "duration_steps must be in 1..255");
     if (!(c->dt > 0)) return fail(MM_ERR_ARG, "dt must be positive");
+    if (c->supervisor < MM_SUPERVISOR_NONE || c->supervisor > MM_SUPERVISOR_DMC) return fail(MM_ERR_ARG, "unknown supervisor");
+    if (c->supervisor != MM_SUPERVISOR_NONE && c->shield != MM_SHIELD_NONE)
+        return fail(MM_ERR_ARG, "safety_guarantee is either a CBF shield or a baseline supervisor, not both");
     return 0;
 }
 
@@ -155,6 +163,15 @@ int order_after_caller(mm_env *env, int n_str) {
 // enqueue one policy step (+ optional re-spawn of finished envs) for envs [off, off+count) on `stream`
 void enqueue_step(mm_env *env, const int8_t *actions_dev, int auto_reset, int off, int count, cudaStream_t stream) {
     if (auto_reset && env->cfg.traffic_type != MM_TRAFFIC_CAV) env->hdv_possible = true;
+    if (env->cfg.supervisor != MM_SUPERVISOR_NONE) {
+        // abstract.py:459-464: new_action = safety_supervisor / safety_layer_dmc (env, action); _simulate(new_action)
+        int8_t *na = env->new_actions + (size_t)off * MAXV;
+        cudaMemcpyAsync(na, actions_dev + (size_t)off * MAXV, (size_t)count * MAXV, cudaMemcpyDeviceToDevice, stream);
+        launch_supervisor(env->st, off, count, env->cfg.supervisor == MM_SUPERVISOR_PRIORITY ? 0 : 1, env->new_actions,
+                          env->sup_draws, MM_SUPERVISOR_DRAWS, env->cfg.headway_time, env->seed, env->sup_used, stream);
+        env->launches += 1;
+        actions_dev = env->new_actions;
+    }
     StepParams p = step_params(env, actions_dev, off, count);
     env->last_build = launch_step(p, env->record_diag != 0, stream);      // physics of the policy step (state -> state)
     launch_outputs(p, true, stream);                    // observations, rewards, flags, info, statistics
@@ -171,6 +188,17 @@ void enqueue_step(mm_env *env, const int8_t *actions_dev, int auto_reset, int of
     }
 }
 
+}  // namespace
+
+namespace {
+int ensure_supervisor_stack(mm_env *env) {
+    // the supervisors keep 2 x 12 vehicles x 18-point trajectories per thread: a 17 KB frame
+    CUDA_OK(cudaSetDevice(env->device));
+    size_t stack = 0;
+    CUDA_OK(cudaDeviceGetLimit(&stack, cudaLimitStackSize));
+    if (stack < 32768) CUDA_OK(cudaDeviceSetLimit(cudaLimitStackSize, 32768));
+    return 0;
+}
 }  // namespace
 
 extern "C" {
@@ -207,6 +235,8 @@ int mm_create(const mm_config *cfg, int n_envs, int device, int record_diag, mm_
     rc |= dev_alloc(env, &env->out.n_agents, E);
     rc |= dev_alloc(env, &env->out.action_mask, E * MAXV);
     rc |= dev_alloc(env, &env->actions, E * MAXV);
+    rc |= dev_alloc(env, &env->new_actions, E * MAXV);
+    rc |= dev_alloc(env, &env->sup_used, E);
     env->stats_rows = (E + 31) / 32;
     rc |= dev_alloc(env, &env->out.stats, env->stats_rows * N_STATS);
     if (record_diag) {
@@ -224,6 +254,8 @@ int mm_create(const mm_config *cfg, int n_envs, int device, int record_diag, mm_
         cudaError_t ce = cudaEventCreateWithFlags(&env->caller_done, cudaEventDisableTiming);
         if (ce != cudaSuccess) { mm_destroy(env); return fail(MM_ERR_CUDA, "cudaEventCreate", ce); }
     }
+    if (cfg->supervisor != MM_SUPERVISOR_NONE)
+        if (int rc2 = ensure_supervisor_stack(env)) { mm_destroy(env); return rc2; }
     *out = env;
     return 0;
 }
@@ -250,6 +282,21 @@ int mm_set_config(mm_env *env, const mm_config *cfg) {
     if (!env) return fail(MM_ERR_ARG, "env is null");
     if (int rc = validate(cfg)) return rc;
     env->cfg = *cfg;
+    if (cfg->supervisor != MM_SUPERVISOR_NONE) return ensure_supervisor_stack(env);
+    return 0;
+}
+
+int mm_set_supervisor_draws(mm_env *env, const double *draws_dev) {
+    if (!env) return fail(MM_ERR_ARG, "env is null");
+    env->sup_draws = draws_dev;
+    return 0;
+}
+
+int mm_supervisor_draws_used(mm_env *env, int32_t *n_used_host) {
+    if (!env || !n_used_host) return fail(MM_ERR_ARG, "null argument");
+    CUDA_OK(cudaSetDevice(env->device));
+    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemcpy(n_used_host, env->sup_used, (size_t)env->n_envs * sizeof(int32_t), cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -585,6 +632,7 @@ int mm_buffers_get(mm_env *env, mm_buffers *b) {
     b->agents_dones = env->out.agents_dones; b->average_speed = env->out.average_speed;
     b->traffic_speed = env->out.traffic_speed; b->min_headway = env->out.min_headway;
     b->merge_percent = env->out.merge_percent; b->n_agents = env->out.n_agents; b->actions = env->actions; b->action_mask = env->out.action_mask;
+    b->new_actions = env->new_actions;
     return 0;
 }
 
@@ -725,26 +773,24 @@ int mm_set_actor_impl(int impl) {
     return 0;
 }
 
-int mm_supervise(mm_env *env, int kind, int8_t *actions_dev, const double *draws_dev, void *stream) {
+int mm_supervise(mm_env *env, int kind, int8_t *actions_dev, const double *draws_dev, int32_t *n_used_dev, void *stream) {
     if (!env) return fail(MM_ERR_ARG, "env is null");
     if (kind != 0 && kind != 1) return fail(MM_ERR_ARG, "kind must be 0 (priority) or 1 (dmc)");
-    if (!actions_dev || !draws_dev) return fail(MM_ERR_ARG, "actions and draws are required");
-    if (!env->cfg.env_v0) return fail(MM_ERR_ARG, "the supervisors belong to env merge-multi-agent-v0");
-    CUDA_OK(cudaSetDevice(env->device));
-    size_t stack = 0;
-    CUDA_OK(cudaDeviceGetLimit(&stack, cudaLimitStackSize));
+    if (!actions_dev) return fail(MM_ERR_ARG, "actions are required");
+    if (int rc = ensure_supervisor_stack(env)) return rc;
     env->last_stream = (cudaStream_t)stream;
-    if (stack < 32768) CUDA_OK(cudaDeviceSetLimit(cudaLimitStackSize, 32768));   // 17 KB frame: 2 x 12 x 18-point trajectories
-    launch_supervisor(env->st, env->n_envs, kind, actions_dev, draws_dev, MM_SUPERVISOR_DRAWS, env->cfg.headway_time, stream);
+    launch_supervisor(env->st, 0, env->n_envs, kind, actions_dev, draws_dev, MM_SUPERVISOR_DRAWS, env->cfg.headway_time, env->seed,
+                      n_used_dev, stream);
     env->launches += 1;
     CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 int mm_set_step_variant(int variant) {
-    if (variant != 0 && (variant < 3 || variant > 7))
+    if (variant != 0 && (variant < 3 || variant > 8))
         return fail(MM_ERR_ARG, "variant must be 0 (automatic), 3, 4 (a generic build forced), 5 (automatic, generic builds only) "
-                                "6 (4 CTAs per SM forced, specialised builds allowed) or 7 (warp-cooperative build forced)");
+                                "6 (4 CTAs per SM forced, specialised builds allowed), 7 (warp-cooperative build forced) or 8 (automatic among the "
+                                "one-thread-per-env builds)");
     set_step_variant(variant);
     return 0;
 }

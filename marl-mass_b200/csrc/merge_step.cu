@@ -75,6 +75,7 @@
 #define MM_PW MM_TILE
 #endif
 #include "mm_device.cuh"
+#include "mm_philox.cuh"
 
 namespace MM_KNS {
 
@@ -372,42 +373,6 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
 // ------------------------------------------------------------------------------------------------
 // device-side spawn (merge_env_v1.py:180-211, 265-364; abstract.py:176-199) with Philox4x32-10
 // ------------------------------------------------------------------------------------------------
-struct Philox {
-    uint32_t key[2], ctr[4], out[4];
-    int have;
-    __device__ Philox(uint64_t seed, uint64_t stream, uint32_t episode) {
-        key[0] = (uint32_t)seed; key[1] = (uint32_t)(seed >> 32);
-        ctr[0] = 0; ctr[1] = episode; ctr[2] = (uint32_t)stream; ctr[3] = (uint32_t)(stream >> 32);
-        have = 0;
-    }
-    __device__ void round_(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-        uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-        uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-        uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
-        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
-    }
-    __device__ uint32_t next() {
-        if (have == 0) {
-            uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
-            uint32_t k0 = key[0], k1 = key[1];
-#pragma unroll
-            for (int r = 0; r < 10; ++r) {
-                round_(c, k0, k1);
-                k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-            }
-            out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
-            ctr[0]++;
-            have = 4;
-        }
-        return out[--have];
-    }
-    __device__ double uniform() {  // [0, 1) with 53 bits
-        uint64_t a = next(), b = next();
-        return (double)(((a << 21) ^ b) & ((1ull << 53) - 1)) * (1.0 / 9007199254740992.0);
-    }
-    __device__ int below(int n) { return (int)(((uint64_t)next() * (uint64_t)n) >> 32); }
-};
-
 __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ ResetParams p) {
     const int local = blockIdx.x * BLOCK + threadIdx.x;
     if (local >= p.env_count) return;
@@ -686,7 +651,7 @@ void launch_step_impl(const StepParams &p, bool diag, void *stream) {
 
 #ifndef MM_VARIANT_TU
 static int g_step_variant = 0;
-void set_step_variant(int v) { g_step_variant = (v >= 3 && v <= 7) ? v : 0; }
+void set_step_variant(int v) { g_step_variant = (v >= 3 && v <= 8) ? v : 0; }
 
 // Picks the build of the step kernel: 4 CTAs / SM when the wave structure of the grid favours it (e.g. 512 CTAs on 148
 // SMs: one wave instead of a full and an almost empty one), else the default 3 CTAs / SM build.
@@ -704,15 +669,22 @@ int launch_step(const StepParams &p, bool diag, void *stream) {
     };
     static const double lat3[4] = {0.0, 9.55, 11.42, 12.27}, lat4[5] = {0.0, 10.5, 12.6, 13.5, 16.2};
     const bool small_grid = grid <= 8 * sms;      // measured: still ahead at 1024 CTAs, behind at 1536 (time_variants.py)
-    const bool automatic = g_step_variant == 0 || g_step_variant == 5;
+    const bool automatic = g_step_variant == 0 || g_step_variant == 5 || g_step_variant == 8;
     const bool four = g_step_variant == 4 || g_step_variant == 6 || (automatic && !diag && !p.cfg.couple_counts && small_grid &&
                                               estimate(4, lat4) < 0.97 * estimate(3, lat3));
     // the specialised builds: all-CAV envs of the plain LC env (v1, lateral_control "steer") under MASS or HSS
     const bool plain_all_cav = p.all_cav && !c.couple_counts && !c.env_v0 && !c.steer_vel && !c.env_hdv && c.traffic_type == MM_TRAFFIC_CAV;
     // the warp-cooperative build (merge_coop.cu): half a warp per env, for grids too small to fill the machine with
     // one thread per env
-    if (g_step_variant == 7 && plain_all_cav) { launch_step_coop(p, diag, stream); return MM_BUILD_COOP + c.shield; }
-    const bool spec_ok = (g_step_variant == 0 || g_step_variant == 6) && p.all_cav && !c.couple_counts && !c.env_v0 && !c.steer_vel &&
+    // Measured crossover (profiles/r2_e_ab_coop_sizes.txt): at 8 192 envs the cooperative build is 1.4-1.6 x faster
+    // (0.22 / 0.27 ms per step against 0.36 / 0.38 for HSS / MASS), at 16 384 envs the thread-per-env builds are ahead
+    // again (0.37 / 0.40 against 0.39 / 0.49); at 2^20 envs it costs 3 x more issue slots per env.
+    const bool coop_pays = p.env_count <= 12288;
+    if (plain_all_cav && (g_step_variant == 7 || (g_step_variant == 0 && coop_pays))) {
+        launch_step_coop(p, diag, stream);
+        return MM_BUILD_COOP + c.shield;
+    }
+    const bool spec_ok = (g_step_variant == 0 || g_step_variant == 6 || g_step_variant == 8) && p.all_cav && !c.couple_counts && !c.env_v0 && !c.steer_vel &&
                          !c.env_hdv && c.traffic_type == MM_TRAFFIC_CAV;
     if (spec_ok && four && c.shield == MM_SHIELD_MASS) { launch_step_spec_mass4(p, diag, stream); return MM_BUILD_SPEC_MASS4; }
     if (spec_ok && four && c.shield == MM_SHIELD_HSS) { launch_step_spec_hss4(p, diag, stream); return MM_BUILD_SPEC_HSS4; }

@@ -1,14 +1,13 @@
-// supervisor_core.h — the baseline supervisors `priority` / `dmc` as host+device code (mm_supervise; not yet called by step).
+// supervisor_core.h — the baseline supervisors `priority` / `dmc` as host+device code (mm_supervise; called by mm_step when
+// mm_config.supervisor is set).
 //
 // What it is: the look-ahead action filters the reference runs once per policy step on env merge-multi-agent-v0
 // (highway_env/vehicle/safety/central_layer.py:16-178 `safety_supervisor`, decentralised_dmc.py:16-198
 // `safety_layer_dmc`, with envs/common/mdp_controller.py, idm_controller.py and abstract.py:219-280, 614-635, 721-755),
 // written as plain functions over one scene so that the SAME source compiles for the host (g++, the CPU parity test
 // tests/test_host_cpu.py::test_supervisor_core_*) and for sm_100a (MM_HD = __host__ __device__ under nvcc).
-// State of play: logic verified on the CPU against the reference fixtures (every step of priority_v0_td3_mixed /
-// dmc_v0_td3_mixed, through the host build of this header and through the kernel of supervisor.cu on a B200); calling it
-// from the step path, the draws of the batched mode and the seed-exact draws of the single-env adapter are the next step
-//  — until then make_mm_config keeps rejecting safety_guarantee = priority | dmc.
+// The logic is pinned on the CPU against the reference fixtures (every step of priority_v0_td3_mixed / dmc_v0_td3_mixed,
+// through the host build of this header) and on a B200 through the kernel of supervisor.cu.
 //
 // Scene = up to 12 vehicles (CAVs first).  A supervisor is a pure function
 //     (scene, meta-action tuple, np.random.rand() draws in consumption order) -> supervised tuple.
@@ -311,7 +310,7 @@ MM_HD_CALL inline void collide_at(Veh *road, int self, const int nb[4], int t) {
 
 // decentralised_dmc.py:70-198.  `road`: working copy (modified); `orig`: the scene; actions[n_cav] in/out.
 MM_HD inline void dmc_supervisor(Veh *road, const Veh *orig, int n, int n_cav, int *actions, const double *draws,
-                                 double headway_time) {
+                                 double headway_time, int *n_used = nullptr) {
     int order[MAXV];
     priority_order(road, n, n_cav, draws, headway_time, order);
     int k = n_cav;
@@ -322,6 +321,7 @@ MM_HD inline void dmc_supervisor(Veh *road, const Veh *orig, int n, int n_cav, i
         k += 2;
         for (int t = 0; t < NPTS; ++t) idm_controller(road[j]);
     }
+    if (n_used) *n_used = k;      // np.random.rand() calls of this supervisor run: one per CAV, two per IDM vehicle
     for (int q = 0; q < n_cav; ++q) {
         const int i = order[q];
         Veh &v = road[i];
@@ -352,7 +352,7 @@ MM_HD inline void dmc_supervisor(Veh *road, const Veh *orig, int n, int n_cav, i
 
 // central_layer.py:16-178 (is_priority = True)
 MM_HD inline void priority_supervisor(Veh *road, const Veh *orig, int n, int n_cav, int *actions, const double *draws,
-                                      double headway_time) {
+                                      double headway_time, int *n_used = nullptr) {
     int order[MAXV];
     priority_order(road, n, n_cav, draws, headway_time, order);
     int k = n_cav;
@@ -395,6 +395,7 @@ MM_HD inline void priority_supervisor(Veh *road, const Veh *orig, int n, int n_c
             }
         }
     }
+    if (n_used) *n_used = k;      // one per CAV, then two per IDM decision the look-aheads made
 }
 
 }  // namespace mmsup

@@ -5,7 +5,7 @@
 extern "C" int mm_supervisor_host(int kind /* 0 priority, 1 dmc */, int n, int n_cav, const double *x, const double *y,
                                   const double *heading, const double *speed, const double *target_speed, const int *lane,
                                   const int *target_lane, const int *speed_index, const int *crashed, int *actions,
-                                  const double *draws, double headway_time) {
+                                  const double *draws, double headway_time, int *n_draws_used) {
     using namespace mmsup;
     if (n < 1 || n > MAXV || n_cav < 0 || n_cav > n) return 1;
     Veh orig[MAXV], road[MAXV];
@@ -17,7 +17,7 @@ extern "C" int mm_supervisor_host(int kind /* 0 priority, 1 dmc */, int n, int n
         v.cav = i < n_cav; v.crashed = crashed[i] != 0; v.n_traj = 0;
         road[i] = v;
     }
-    if (kind == 0) priority_supervisor(road, orig, n, n_cav, actions, draws, headway_time);
-    else dmc_supervisor(road, orig, n, n_cav, actions, draws, headway_time);
+    if (kind == 0) priority_supervisor(road, orig, n, n_cav, actions, draws, headway_time, n_draws_used);
+    else dmc_supervisor(road, orig, n, n_cav, actions, draws, headway_time, n_draws_used);
     return 0;
 }

@@ -24,7 +24,11 @@ from . import _lib
 from . import spawn as _spawn
 from ._lib import ENV_FIELDS, F64_FIELDS, I32_FIELDS, MAXV, NA, NS, SH_F, SH_I
 
-SHIELD = {"none": 0, "cbf-hss": 1, "cbf-av": 1, "cbf-avs": 1, "cbf-avs_cint": 1, "cbf-mass": 2, "cbf-cav": 2}
+SHIELD = {"none": 0, "cbf-hss": 1, "cbf-av": 1, "cbf-avs": 1, "cbf-avs_cint": 1, "cbf-mass": 2, "cbf-cav": 2,
+          # the look-ahead baselines act on the action tuple before _simulate (abstract.py:459-464); the vehicles themselves
+          # run un-shielded (safe_controller.py:232-239)
+          "priority": 0, "dmc": 0}
+SUPERVISOR = {"priority": 1, "dmc": 2}
 REWARD = {"default": 0, "srew": 1, "mrew": 2}
 TRAFFIC = {"cav": 0, "mixed": 1, "av": 2, "hdv": 3}
 
@@ -54,8 +58,7 @@ def make_mm_config(cfg):
         raise KeyError("env id %r is not provided by marl_mass_b200 (available: %s)" % (env_name, list(ENV_IDS)))
     v0 = env_name == "merge-multi-agent-v0"
     sg = cfg.get("safety_guarantee", "none")
-    if sg in ("priority", "dmc"):
-        raise ValueError("safety_guarantee %r (look-ahead baseline shields) is outside the batched hot path" % sg)
+    supervisor = SUPERVISOR.get(sg, 0)
     if sg not in SHIELD:
         raise ValueError("Undefined safety_type:{0}".format(sg.split("-")[-1]))
     lat = cfg.get("lateral_control", "steer")
@@ -85,7 +88,7 @@ def make_mm_config(cfg):
         collision_reward=float(cfg["COLLISION_REWARD"]), high_speed_reward=float(cfg["HIGH_SPEED_REWARD"]),
         headway_cost=float(cfg["HEADWAY_COST"]), headway_time=float(cfg["HEADWAY_TIME"]),
         merging_lane_cost=float(cfg["MERGING_LANE_COST"]),
-        couple_counts=int(bool(cfg.get("couple_vehicle_counts", False))), env_hdv=int(hdv_env))
+        couple_counts=int(bool(cfg.get("couple_vehicle_counts", False))), env_hdv=int(hdv_env), supervisor=supervisor)
 
 
 class _DevArray(object):
@@ -145,7 +148,8 @@ class MergeEnvBatched(object):
                     "agents_rewards": ((E, MAXV), "<f4"), "regional_rewards": ((E, MAXV), "<f4"),
                     "agents_dones": ((E, MAXV), "|u1"), "average_speed": ((E,), "<f4"),
                     "traffic_speed": ((E,), "<f4"), "min_headway": ((E,), "<f4"), "merge_percent": ((E,), "<f4"),
-                    "n_agents": ((E,), "<i4"), "actions": ((E, MAXV), "|i1"), "action_mask": ((E, MAXV), "|u1")}
+                    "n_agents": ((E,), "<i4"), "actions": ((E, MAXV), "|i1"), "action_mask": ((E, MAXV), "|u1"),
+                    "new_actions": ((E, MAXV), "|i1")}
             dev = "cuda:%d" % self.device
             self._views = {k: torch.as_tensor(_DevArray(getattr(b, k), shp, ts, self), device=dev)
                            for k, (shp, ts) in spec.items()}
@@ -185,7 +189,9 @@ class MergeEnvBatched(object):
         self._apply_config()
         seeds = list(seeds)
         assert len(seeds) == self.n_envs
-        st = _spawn.spawn_state(seeds, self.config["traffic_density"], traffic_type_of(self.config), num_CAV)
+        self.spawn_rngs = []       # one MT19937 replay per env, positioned after the spawn draws (supervisor draws follow)
+        st = _spawn.spawn_state(seeds, self.config["traffic_density"], traffic_type_of(self.config), num_CAV,
+                                rngs=self.spawn_rngs)
         self.set_state(st)
         v = self.buffers()
         return v["obs"], self.action_mask()
@@ -253,10 +259,56 @@ class MergeEnvBatched(object):
                                                C.c_void_p(ptr.get("regional_rewards", 0)), C.c_void_p(ptr.get("n_agents", 0))))
         return out
 
-    def alloc_host_out(self, pinned=True, ragged=False):
+    def step_host_packed(self, actions, auto_reset=False, out=None):
+        """`step_host` with the observation in packed form (mm_step_host_packed): per vehicle x, y, vx, vy, heading
+        (float32) and per agent the slots of the vehicles its observation rows show, plus reward / done / regional
+        rewards - about 250 bytes per env-step instead of 1.1 KB of observation rows.  out["veh"][V0:V0 + n_veh[e]] are
+        env e's vehicles (V0 = n_veh[:e].sum()), out["nbr"][A0:A0 + n_agents[e]] its agents' neighbour words.
+        `expand_obs_rows(out)` rebuilds the [A, 30] rows on the host.  `out` comes from `alloc_host_out(packed=True)`."""
+        a = actions if isinstance(actions, np.ndarray) else actions.numpy()
+        assert a.dtype == np.int8 and a.flags.c_contiguous and a.size == self.n_envs * MAXV
+        if out is None:
+            out = self.alloc_host_out(packed=True)
+        _lib.check(self._L.mm_step_host_packed(self._h, C.c_void_p(a.ctypes.data), int(bool(auto_reset)),
+                                               C.byref(self._packed_struct(out))))
+        return out
+
+    @staticmethod
+    def _packed_struct(out):
+        ptr = lambda k: C.c_void_p(out[k].ctypes.data) if out.get(k) is not None else C.c_void_p(0)
+        return _lib.MMPackedHost(veh=ptr("veh"), nbr=ptr("nbr"), n_veh=ptr("n_veh"), n_agents=ptr("n_agents"),
+                                 reward=ptr("reward"), done=ptr("done"), regional_rewards=ptr("regional_rewards"))
+
+    def expand_obs_rows(self, out, n_threads=0, obs_rows=None, row_offset=None):
+        """Observation rows of a packed step, rebuilt on the host (mm_expand_obs_rows; no device involved):
+        -> (obs_rows [sum n_agents, 30] f32, row_offset [E + 1] int64); env e's rows are obs_rows[row_offset[e]:row_offset[e + 1]]."""
+        import os
+        E = self.n_envs
+        rows = int(out["n_agents"].sum(dtype=np.int64))
+        if obs_rows is None:
+            obs_rows = np.empty((rows, NS), np.float32)
+        if row_offset is None:
+            row_offset = np.empty((E + 1,), np.int64)
+        assert obs_rows.dtype == np.float32 and obs_rows.flags.c_contiguous and obs_rows.shape[0] >= rows
+        steer_vel = int(self.config.get("lateral_control", "steer") == "steer_vel" and not self.v0)
+        _lib.check(self._L.mm_expand_obs_rows(C.byref(self._packed_struct(out)), E, steer_vel, C.c_void_p(obs_rows.ctypes.data),
+                                              C.c_void_p(row_offset.ctypes.data), int(n_threads or len(os.sched_getaffinity(0)))))
+        return obs_rows[:rows], row_offset
+
+    def packed_bytes(self, out):
+        """Device-to-host bytes of one mm_step_host_packed call that filled `out`."""
+        E = self.n_envs
+        return (int(out["n_veh"].sum(dtype=np.int64)) * 20 + int(out["n_agents"].sum(dtype=np.int64)) * 2 +
+                E * (1 + 1 + 4 + 1 + MAXV * 4))
+
+    def alloc_host_out(self, pinned=True, ragged=False, packed=False):
         import torch
         E = self.n_envs
         mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=pinned).numpy()
+        if packed:
+            return {"veh": mk((E * 11, 5), torch.float32), "nbr": mk((E * MAXV,), torch.uint16),
+                    "n_veh": mk((E,), torch.uint8), "n_agents": mk((E,), torch.uint8), "reward": mk((E,), torch.float32),
+                    "done": mk((E,), torch.uint8), "regional_rewards": mk((E, MAXV), torch.float32)}
         out = {"reward": mk((E,), torch.float32), "done": mk((E,), torch.uint8),
                "regional_rewards": mk((E, MAXV), torch.float32), "n_agents": mk((E,), torch.int32)}
         if ragged:
@@ -332,31 +384,48 @@ class MergeEnvBatched(object):
         specialised for all-CAV envs under HSS / MASS)."""
         return int(self._L.mm_step_build(self._h))
 
-    def supervise(self, actions, kind, draws=None):
-        """EXPERIMENTAL (mm_supervise): the reference's baseline supervisors of env v0 - `priority`
-        (central_layer.py:16-178) or `dmc` (decentralised_dmc.py:70-198) - applied to the current scenes: returns the
-        action tuples the reference would hand to _simulate.  actions [E, 12] integer cuda tensor; draws [E, 32] float64
-        cuda = the uniform numbers the reference takes from np.random.rand() (default: torch.rand).  Reproduces
-        the reference's tuples on every step of the reference fixtures (tests/test_zz_supervisor_gpu.py); step() does
-        not call it yet and make_mm_config still rejects safety_guarantee = priority | dmc.  Until then the supervised
-        policy step of a batch on env v0 (safety_guarantee = "none") is the composition
-        `env.step(env.supervise(actions, kind))`, both halves of which are pinned on the reference fixtures."""
+    def supervise(self, actions, kind, draws=None, return_used=False):
+        """The reference's baseline supervisors alone (mm_supervise) - `priority` (central_layer.py:16-178) or `dmc`
+        (decentralised_dmc.py:70-198) - applied to the current scenes: returns the action tuples the reference would hand
+        to _simulate.  actions [E, 12] integer cuda tensor; draws [E, 32] float64 cuda = the uniform numbers the reference
+        takes from np.random.rand() in consumption order (None: Philox draws keyed (seed, env, episode, step)).
+        With safety_guarantee = "priority" / "dmc" in the config, step() does this itself on every policy step."""
         import torch
         k = {"priority": 0, "dmc": 1}[kind]
         dev = torch.device("cuda", self.device)
         out = actions.to(device=dev, dtype=torch.int8).contiguous().clone()
-        if draws is None:
-            draws = torch.rand((self.n_envs, _lib.SUPERVISOR_DRAWS), dtype=torch.float64, device=dev)
-        draws = draws.to(device=dev, dtype=torch.float64).contiguous()
-        assert out.shape == (self.n_envs, MAXV) and draws.shape == (self.n_envs, _lib.SUPERVISOR_DRAWS)
-        _lib.check(self._L.mm_supervise(self._h, k, C.c_void_p(out.data_ptr()), C.c_void_p(draws.data_ptr()),
+        dptr = C.c_void_p(0)
+        if draws is not None:
+            draws = draws.to(device=dev, dtype=torch.float64).contiguous()
+            assert draws.shape == (self.n_envs, _lib.SUPERVISOR_DRAWS)
+            dptr = C.c_void_p(draws.data_ptr())
+        used = torch.zeros(self.n_envs, dtype=torch.int32, device=dev)
+        assert out.shape == (self.n_envs, MAXV)
+        _lib.check(self._L.mm_supervise(self._h, k, C.c_void_p(out.data_ptr()), dptr, C.c_void_p(used.data_ptr()),
                                         C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-        return out
+        return (out, used) if return_used else out
+
+    def set_supervisor_draws(self, draws=None):
+        """Draws for the supervisors inside the following step() calls (mm_set_supervisor_draws): [E, 32] float64 cuda,
+        consumed in order; None returns to the Philox stream.  The tensor is kept alive by the env."""
+        import torch
+        if draws is not None:
+            draws = draws.to(device=torch.device("cuda", self.device), dtype=torch.float64).contiguous()
+            assert draws.shape == (self.n_envs, _lib.SUPERVISOR_DRAWS)
+        self._sup_draws = draws
+        _lib.check(self._L.mm_set_supervisor_draws(self._h, C.c_void_p(0 if draws is None else draws.data_ptr())))
+
+    def supervisor_draws_used(self):
+        """[E] int32: how many draws each env's supervisor consumed in the last step."""
+        used = np.zeros(self.n_envs, np.int32)
+        _lib.check(self._L.mm_supervisor_draws_used(self._h, C.c_void_p(used.ctypes.data)))
+        return used
 
 
 def set_step_variant(variant=0):
     """0: automatic choice among the builds of the step kernel (marl_mass_b200.h mm_set_step_variant); 3 / 4: force a
-    generic build; 5: automatic among the generic builds only."""
+    generic build; 5: automatic among the generic builds only; 6: 4 CTAs per SM, specialised builds allowed; 7: the
+    warp-cooperative build where it applies; 8: automatic among the one-thread-per-env builds."""
     _lib.check(_lib.lib().mm_set_step_variant(int(variant)))
 
 
@@ -474,7 +543,19 @@ class MergeEnvLCMARL(object):
         a[0, :n] = np.asarray(tuple(action), np.int64)[:n]
         v = self._b.buffers()
         v["actions"].copy_(torch.from_numpy(a))
-        self._b.step(None)
+        new_action = action
+        if self.config.get("safety_guarantee") in ("priority", "dmc"):
+            # abstract.py:459-464.  The supervisor's np.random.rand() numbers are the next draws of the stream the spawn
+            # left behind: hand the kernel a look-ahead of that stream, then advance the replay by what it consumed
+            rs = self._b.spawn_rngs[0]
+            peek = np.random.RandomState()
+            peek.set_state(rs.get_state())
+            self._b.set_supervisor_draws(torch.from_numpy(peek.rand(1, _lib.SUPERVISOR_DRAWS)))
+            self._b.step(None)
+            rs.rand(int(self._b.supervisor_draws_used()[0]))
+            new_action = tuple(int(x) for x in v["new_actions"][0, :n].cpu().numpy())
+        else:
+            self._b.step(None)
         torch.cuda.synchronize(self._b.device)
         self._cache = None
         self.steps += 1
@@ -488,7 +569,7 @@ class MergeEnvLCMARL(object):
         self.vehicle_speed.append(speeds)
         self.vehicle_pos.append([float(st["x"][0, i]) for i in range(n)])
         info = {
-            "speed": speeds[0], "crashed": bool(st["crashed"][0, 0]), "action": action, "new_action": action,
+            "speed": speeds[0], "crashed": bool(st["crashed"][0, 0]), "action": action, "new_action": new_action,
             "action_mask": self._mask(n), "average_speed": float(v["average_speed"][0]),
             "vehicle_speed": np.array(self.vehicle_speed), "vehicle_position": np.array(self.vehicle_pos),
             "agents_dones": tuple(bool(x) for x in v["agents_dones"][0, :n].cpu().numpy()),

@@ -61,9 +61,14 @@ def num_vehicles(rs, traffic_density, traffic_type, num_CAV=0):
     return int(num_CAV), int(num_HDV)
 
 
-def spawn_scene(seed, traffic_density=1, traffic_type="cav", num_CAV=0):
-    """One scene: list of (kind, x, y, speed) in road.vehicles order plus n_merge."""
+def spawn_scene(seed, traffic_density=1, traffic_type="cav", num_CAV=0, rng_out=None):
+    """One scene: list of (kind, x, y, speed) in road.vehicles order plus n_merge.  rng_out (a list): receives the
+    generator as the spawn left it - the reference keeps drawing from the same process-global stream afterwards (the
+    baseline supervisors' np.random.rand() calls, central_layer.py:55 / idm_controller.py:60-79), and nothing else on
+    the step path consumes it, so the adapter continues this replay step by step."""
     rs = np.random.RandomState(int(seed))
+    if rng_out is not None:
+        rng_out.append(rs)
     num_CAV, num_HDV = num_vehicles(rs, traffic_density, traffic_type, num_CAV)
     spawn_points_s = [10, 60, 110, 160, 210, 260]
     spawn_points_m = [5, 55, 105, 155, 205, 255]
@@ -127,13 +132,14 @@ def fill_scene(st, e, vehicles, n_merge):
     st["time"][e] = 0
 
 
-def spawn_state(seeds, traffic_density=1, traffic_type="cav", num_CAV=0):
-    """Env-major state dict holding the reference's scene for each seed (num_CAV: one value or one per seed)."""
+def spawn_state(seeds, traffic_density=1, traffic_type="cav", num_CAV=0, rngs=None):
+    """Env-major state dict holding the reference's scene for each seed (num_CAV: one value or one per seed).
+    rngs (a list): receives one generator per scene, positioned after the spawn draws (see spawn_scene)."""
     seeds = list(seeds)
     n_cav = list(num_CAV) if hasattr(num_CAV, "__len__") else [num_CAV] * len(seeds)
     assert len(n_cav) == len(seeds)
     st = empty_state(len(seeds))
     for e, s in enumerate(seeds):
-        vehicles, n_merge = spawn_scene(s, traffic_density, traffic_type, int(n_cav[e]))
+        vehicles, n_merge = spawn_scene(s, traffic_density, traffic_type, int(n_cav[e]), rng_out=rngs)
         fill_scene(st, e, vehicles, n_merge)
     return st

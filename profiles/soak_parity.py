@@ -1,5 +1,8 @@
-"""Parity soak beyond the test suite: whole-episode CUDA-vs-oracle lock step on fresh seeds and all shield / traffic /
-reward / lateral-control variants.  python profiles/soak_parity.py [n_rounds]   (needs the GPU box; oracle = checker)"""
+"""Parity soak: whole-episode CUDA-vs-oracle lock step on fresh seeds and all shield / traffic / reward / lateral-control
+variants.  python profiles/soak_parity.py [n_rounds] [first_round] [snap]   (needs the GPU box; oracle = checker)
+MM_SOAK_ENVS (default 4096) sets the batch; one snapped round at 1024 envs is part of the GPU test suite
+(tests/test_gpu_parity.py::test_soak_round_with_snapped_scenes).  The build of the step kernel rotates with the round:
+automatic (specialised builds where they apply), generic 3 / 4 CTAs per SM, warp-cooperative (where it applies)."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
@@ -20,11 +23,11 @@ first_round = int(sys.argv[2]) if len(sys.argv) > 2 else 0      # seeds depend o
 # steps), newest history record re-synced, state uploaded: exact ties and boundary values in every scene (the tie
 # fixtures of tests/golden at scale); the comparison is then per step (teacher-forced from the oracle's state)
 snap = len(sys.argv) > 3 and sys.argv[3] == "snap"
-E, T = 4096, 100
+E, T = int(os.environ.get("MM_SOAK_ENVS", "4096")), 100
 total_env_steps, boundary = 0, 0
 t0 = time.time()
 for rnd in range(first_round, first_round + rounds):
-    mm.set_step_variant(4 if rnd % 2 else 3)                    # odd rounds: the 4-CTAs-per-SM build of the step kernel
+    mm.set_step_variant((0, 4, 7, 3)[rnd % 4])                  # which build of the step kernel this round exercises
     for ci, (shield, traffic, td, reward, lateral) in enumerate(CASES):
         cfg = dict(mm.DEFAULT_CONFIG, safety_guarantee=shield, lateral_control=lateral, traffic_type=traffic, traffic_density=td,
                    agent_reward=reward, HEADWAY_TIME=0.5, cbf_eta=0.03125, HIGH_SPEED_REWARD=4, HEADWAY_COST=1, MERGING_LANE_COST=8)

@@ -2,6 +2,8 @@
 and (b) the CPU oracle on seeded scenes.  Discrete outputs bit-exact; continuous state <= 1e-9 relative
 (float64 core; the north-star tolerance is 1e-4), float32 outputs (obs, rewards) <= 2e-6.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -168,16 +170,36 @@ def test_four_ctas_per_sm_build_of_the_step_kernel(mm, orc, shield, traffic, td,
         mm.set_step_variant(0)
 
 
-@pytest.mark.parametrize("shield,variant", [("cbf-cav", 3), ("cbf-avs_cint", 3), ("cbf-cav", 5)])
-def test_generic_builds_on_all_cav_scenes(mm, orc, shield, variant):
-    """All-CAV scenes under MASS / HSS run the compile-time specialised builds by default (asserted in
-    lockstep_rollout); the generic builds must compute the same step on them: the strict lock-step comparison with a
-    generic build forced (3: the 3-CTAs-per-SM build; 5: automatic choice among the generic builds)."""
+@pytest.mark.parametrize("shield,variant,build", [("cbf-cav", 3, 3), ("cbf-avs_cint", 3, 3), ("cbf-cav", 5, 3),
+                                                  ("cbf-cav", 8, 32), ("cbf-avs_cint", 8, 31), ("cbf-cav", 6, 42),
+                                                  ("cbf-avs_cint", 6, 41)])
+def test_thread_per_env_builds_on_all_cav_scenes(mm, orc, shield, variant, build):
+    """All-CAV scenes under MASS / HSS have five builds of the step kernel to choose from; at this batch size the
+    automatic choice is the warp-cooperative one (asserted in lockstep_rollout).  The one-thread-per-env builds must
+    compute the same step: the strict lock-step comparison with each forced - generic (3; 5: automatic among the generic
+    builds), compile-time specialised for 3 CTAs per SM (8: automatic among the thread-per-env builds -> 31 HSS, 32 MASS)
+    and for 4 CTAs per SM (6 -> 41, 42)."""
     try:
         mm.set_step_variant(variant)
-        lockstep_rollout(mm, orc, shield, "cav", 3, "default", 4096, 40, STATE_TOL, expect_build=(3,))
+        lockstep_rollout(mm, orc, shield, "cav", 3, "default", 4096, 40, STATE_TOL, expect_build=(build,))
     finally:
         mm.set_step_variant(0)
+
+
+def test_automatic_build_choice_follows_the_batch_size(mm):
+    """mm_step_build() after a step: warp-cooperative for a small all-CAV batch, specialised one-thread-per-env builds for
+    larger ones (4 CTAs per SM where the wave structure favours it), generic when HDVs can be present."""
+    import torch
+    want = {(4096, "cav"): (52,), (65536, "cav"): (42,), (200000, "cav"): (32, 42), (4096, "mixed"): (3, 4)}
+    for (E, traffic), builds in want.items():
+        cfg = dict(mm.DEFAULT_CONFIG, safety_guarantee="cbf-cav", traffic_type=traffic, traffic_density=3, HEADWAY_TIME=0.5,
+                   cbf_eta=0.03125)
+        env = mm.MergeEnvBatched(E, cfg)
+        env.reset(seed=1)
+        env.step(torch.ones((E, 12), dtype=torch.int8, device="cuda"))
+        torch.cuda.synchronize()
+        assert env.step_build() in builds, (E, traffic, env.step_build())
+        env.close()
 
 
 @pytest.mark.parametrize("shield,td,reward,T,resync", [
@@ -234,6 +256,22 @@ def test_exact_ties_with_the_four_cta_build(mm, orc):
         tie_rollout(mm, orc, "cbf-cav", "mixed", 3, True)
     finally:
         mm.set_step_variant(0)
+
+
+@pytest.mark.parametrize("round_index", [0, 2])
+def test_soak_round_with_snapped_scenes(round_index):
+    """One round of profiles/soak_parity.py inside the suite: the 11 shield / traffic / density / reward / lateral-control
+    variants x 1024 fresh scenes x the whole 100-step episode, every scene snapped to grid values before every policy
+    step (exact ties in x, s and the closest-vehicle keys, vehicles on lane ends and after_end thresholds, speeds
+    half-way between speed levels), compared per step against the oracle: every discrete state field, discrete output
+    and non-boundary shield record identical.  Round 0 runs the automatic build choice (specialised builds on the
+    all-CAV variants), round 2 forces the warp-cooperative build where it applies."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "soak_parity.py"), "1", str(round_index), "snap"],
+                       env=dict(os.environ, MM_SOAK_ENVS="1024"), capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and "SOAK OK" in p.stdout, (p.stdout[-1500:], p.stderr[-1500:])
 
 
 def tie_rollout(mm, orc, shield, traffic, td, snap_y=False):
@@ -306,9 +344,9 @@ def lockstep_rollout(mm, orc, shield, traffic, td, reward, E, T, state_tol, resy
         diag = env.shield_diag()
         if expect_build is not None:
             assert env.step_build() in expect_build, env.step_build()
-        elif traffic == "cav" and lateral == "steer" and shield != "none":
-            # all-CAV scenes of the plain LC env: the specialised builds (31 HSS, 32 MASS) unless a test forces another
-            assert env.step_build() in (31, 32, 41, 42), env.step_build()
+        elif traffic == "cav" and lateral == "steer":
+            # all-CAV scenes of the plain LC env at this batch size: the warp-cooperative build unless a test forces another
+            assert env.step_build() in (50, 51, 52), env.step_build()
         # compare only envs that had not finished before this step (finished envs are not stepped by MAPPO) and, in the
         # whole-episode runs, that are still well conditioned (see below)
         sel = np.where(alive & clean)[0]
@@ -416,6 +454,48 @@ def test_ragged_host_step_equals_device_step(mm):
         assert np.array_equal(rew.cpu().numpy(), out["reward"])
         assert np.array_equal(done.cpu().numpy(), out["done"])
         assert np.array_equal(v["regional_rewards"].cpu().numpy(), out["regional_rewards"])
+    a_env.close()
+    b_env.close()
+
+
+@pytest.mark.parametrize("traffic,lateral,E", [("cav", "steer", 70000), ("mixed", "steer_vel", 3000)])
+def test_packed_host_step_expands_to_the_observation_rows(mm, traffic, lateral, E):
+    """mm_step_host_packed hands over per-vehicle state + neighbour slots instead of observation rows;
+    mm_expand_obs_rows rebuilds the rows on the host.  Two handles stepped with the same actions from the same spawn: the
+    rebuilt rows equal the rows of mm_step_host_ragged to float32 rounding of the packed inputs (<= 1e-6 on the [-1, 1]
+    scale), counts / reward / done / regional rewards are identical; several chunks (70 000 envs) and auto-reset."""
+    import torch
+    cfg = dict(mm.DEFAULT_CONFIG, safety_guarantee="cbf-cav", traffic_type=traffic, traffic_density=3, HEADWAY_TIME=0.5,
+               cbf_eta=0.03125, lateral_control=lateral, duration=2)
+    a_env, b_env = mm.MergeEnvBatched(E, cfg), mm.MergeEnvBatched(E, cfg)
+    a_env.reset(seed=77)
+    b_env.reset(seed=77)
+    rng = np.random.RandomState(3)
+    pk, rg = a_env.alloc_host_out(pinned=True, packed=True), b_env.alloc_host_out(pinned=True, ragged=True)
+    n_done = 0
+    for t in range(14):
+        act = rng.randint(0, 5, size=(E, 12)).astype(np.int8)
+        a_env.step_host_packed(act, auto_reset=True, out=pk)
+        b_env.step_host_ragged(act, auto_reset=True, out=rg)
+        assert np.array_equal(pk["n_agents"].astype(np.int32), rg["n_agents"])
+        assert np.array_equal(pk["done"], rg["done"]) and np.array_equal(pk["reward"], rg["reward"])
+        assert np.array_equal(pk["regional_rewards"], rg["regional_rewards"])
+        n_done += int(pk["done"].sum())
+        rows, off = a_env.expand_obs_rows(pk, n_threads=4)
+        assert off[-1] == rows.shape[0] == int(rg["n_agents"].sum())
+        # the ragged path packs its rows per 64 Ki-env chunk; gather them env by env
+        want = np.concatenate([rg["obs_rows"][rg["row_offset"][e]:rg["row_offset"][e] + rg["n_agents"][e]] for e in range(0, E, 997)])
+        got = np.concatenate([rows[off[e]:off[e + 1]] for e in range(0, E, 997)])
+        assert np.abs(got - want).max() <= 1e-6, np.abs(got - want).max()
+        st = a_env.get_state()
+        assert np.array_equal(pk["n_veh"].astype(np.int32), st["n_veh"])
+        e = int(rng.randint(E))
+        v0 = int(pk["n_veh"][:e].sum(dtype=np.int64))
+        nv = int(st["n_veh"][e])
+        assert np.allclose(pk["veh"][v0:v0 + nv, 0], st["x"][e, :nv].astype(np.float32), rtol=0, atol=0)
+        assert np.allclose(pk["veh"][v0:v0 + nv, 4], st["heading"][e, :nv].astype(np.float32), rtol=0, atol=0)
+    assert n_done >= E    # every env finished a 10-step episode: re-spawned scenes went through the packed path
+    assert a_env.packed_bytes(pk) < 0.3 * (int(rg["n_agents"].sum()) * 120 + E * 61)
     a_env.close()
     b_env.close()
 
@@ -852,21 +932,88 @@ def test_v0_env_cuda_vs_golden_and_adapter(mm, orc, name):
 
 
 @pytest.mark.parametrize("name", SUPERVISED_CASES)
-def test_supervised_actions_drive_the_unshielded_v0_dynamics(mm, orc, name):
-    """safety_guarantee = priority | dmc only replaces the meta-actions before _simulate (abstract.py:459-467): the CUDA
-    v0 step with the supervised tuple the reference executed reproduces the reference's post-state and outputs.  (The
-    supervisors themselves are not built: make_mm_config rejects those values.)"""
+def test_supervised_step_reproduces_the_reference(mm, orc, name):
+    """safety_guarantee = priority | dmc: the supervisor replaces the meta-actions before _simulate (abstract.py:459-467).
+    Teacher-forced on every step of the reference fixtures: from the reference's pre-state, with the policy's tuple and
+    the np.random.rand() draws the reference consumed, one mm_step (supervisor + physics + outputs) must produce the
+    supervised tuple the reference executed (info["new_action"]), its post-state and its outputs, and report the number
+    of draws the reference made."""
     import torch
     g, cfg = load_golden(name)
-    with pytest.raises(ValueError):
-        mm.make_mm_config(dict(mm.DEFAULT_CONFIG, **env_config(cfg)))
     rows = g["row_of_step"]
-    env = mm.MergeEnvBatched(len(rows), dict(env_config(cfg), safety_guarantee="none"))
-    assert env.n_s == 25
+    T = len(rows)
+    env = mm.MergeEnvBatched(T, env_config(cfg))
+    assert env.n_s == 25 and mm.make_mm_config(env.config).supervisor == {"priority": 1, "dmc": 2}[cfg["safety_guarantee"]]
     env.set_state(full_state(orc, g, rows))
-    _, _, _, v = env.step(torch.from_numpy(np.ascontiguousarray(g["new_act"])).cuda())
-    got = outputs_to_numpy(v, OUT_F + OUT_I)
+    draws = np.zeros((T, 32))
+    draws[:, :16] = np.nan_to_num(g["rand_draws"])
+    env.set_supervisor_draws(torch.from_numpy(draws).cuda())
+    _, _, _, v = env.step(torch.from_numpy(np.ascontiguousarray(g["act"])).cuda())
+    got = outputs_to_numpy(v, OUT_F + OUT_I + ("new_actions",))
+    live = np.arange(12)[None, :] < g["st_n_cav"][rows][:, None]
+    assert np.array_equal(got["new_actions"][live], g["new_act"][live])
+    assert int((g["new_act"][live] != g["act"][live]).sum()) > 100          # the supervisors did replace actions
+    assert np.array_equal(env.supervisor_draws_used(), np.sum(~np.isnan(g["rand_draws"]), axis=1))
     got["obs"] = obs25(got["obs"])
     compare_states(env.get_state(), full_state(orc, g, rows + 1), STATE_TOL, name, v0=True)
     check_outputs(got, {k: g[k] for k in OUT_F + OUT_I}, g["st_n_cav"][rows])
     env.close()
+
+
+@pytest.mark.parametrize("name", SUPERVISED_CASES)
+def test_single_env_adapter_replays_supervised_episodes(mm, name):
+    """make("merge-multi-agent-v0") with safety_guarantee = priority | dmc is seed-exact: reset(testing_seeds = s) builds
+    the reference's scene and leaves its MT19937 stream where the reference's is, every step hands the supervisor the
+    next draws of that stream and advances it by what was consumed - the whole episode reproduces the reference's
+    supervised tuples, rewards and observations."""
+    g, cfg = load_golden(name)
+    ep, rows = g["ep_start"], g["row_of_step"]
+    env = mm.make("merge-multi-agent-v0", config={k: cfg[k] for k in cfg if k not in ("seeds", "env_name")})
+    for k, seed in enumerate(cfg["seeds"][:3]):
+        obs, _ = env.reset(is_training=False, testing_seeds=seed)
+        steps = np.where((rows >= ep[k]) & (rows < ep[k + 1] - 1))[0]
+        n = len(env.controlled_vehicles)
+        for t in steps:
+            obs, reward, done, info = env.step(tuple(int(a) for a in g["act"][t, :n]))
+            assert tuple(info["new_action"]) == tuple(int(a) for a in g["new_act"][t, :n]), (seed, int(t))
+            assert abs(reward - float(g["reward"][t])) <= 1e-4 * max(1.0, abs(float(g["reward"][t])))
+            assert np.abs(obs - g["obs"][t, :n]).max() <= 1e-5, (seed, int(t))
+            assert done == bool(g["done"][t])
+    env.close()
+
+
+def test_batched_supervisors_draw_from_philox_and_only_touch_the_actions(mm):
+    """Batched mode: the supervisors take their uniform numbers from Philox keyed (seed, env, episode, policy step).
+    Two handles with the same seed agree bit for bit, the executed tuples differ from the policy's on some steps, and an
+    env whose tuple was not changed moves exactly as without a supervisor."""
+    import torch
+    E = 2048
+    cfg = dict(mm.DEFAULT_CONFIG, env_name="merge-multi-agent-v0", safety_guarantee="dmc", traffic_density=3, mixed_traffic=True)
+    a_env, b_env = mm.MergeEnvBatched(E, cfg), mm.MergeEnvBatched(E, cfg)
+    c_env = mm.MergeEnvBatched(E, dict(cfg, safety_guarantee="none"))
+    for env in (a_env, b_env, c_env):
+        env.reset(seed=5)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    changed_total = 0
+    for t in range(12):
+        act = torch.randint(0, 5, (E, 12), generator=gen, device="cuda", dtype=torch.int8)
+        pre = c_env.get_state()
+        _, _, _, va = a_env.step(act)
+        _, _, _, vb = b_env.step(act)
+        torch.cuda.synchronize()
+        na = va["new_actions"].cpu().numpy()
+        assert np.array_equal(na, vb["new_actions"].cpu().numpy())
+        sa, sb = a_env.get_state(), b_env.get_state()
+        assert all(np.array_equal(sa[k], sb[k]) for k in sa)
+        live = np.arange(12)[None, :] < pre["n_cav"][:, None]
+        changed = ((na != act.cpu().numpy()) & live).any(axis=1)
+        changed_total += int(changed.sum())
+        # the un-supervised handle executes the supervised tuples: same dynamics
+        c_env.step(torch.from_numpy(np.where(live, na, act.cpu().numpy())).cuda())
+        sc = c_env.get_state()
+        assert all(np.array_equal(sa[k], sc[k]) for k in ("x", "y", "speed", "lane", "crashed"))
+    assert changed_total > 0
+    for env in (a_env, b_env, c_env):
+        env.close()
+
+

@@ -39,7 +39,7 @@ def test_mm_config_layout_agrees_between_header_binding_and_integration_stub():
     declared = []
     for typ, names in re.findall(r"\b(int32_t|double)\s+([^;]+);", body):
         declared += [(n.strip(), ctype[typ]) for n in names.split(",")]
-    assert declared[0][0] == "struct_size" and declared[-1][0] == "env_hdv" and len(declared) == 19
+    assert declared[0][0] == "struct_size" and declared[-1][0] == "supervisor" and len(declared) == 20
     assert [(n, t) for n, t in _lib.MMConfig._fields_] == declared
     doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     stub = re.search(r"class MMConfig\(C\.Structure\):.*?_fields_ = \[(.*?)\]\n", doc, re.S).group(1)
@@ -94,8 +94,11 @@ def test_config_mapping_and_error_behaviour():
     with pytest.raises(AttributeError, match="Lateral control"):     # safe_controller.py:173-176
         mm.make_mm_config(dict(mm.DEFAULT_CONFIG, lateral_control="torque"))
     assert mm.make_mm_config(dict(mm.DEFAULT_CONFIG, lateral_control="steer_vel")).steer_vel == 1
-    with pytest.raises(ValueError):
-        mm.make_mm_config(dict(mm.DEFAULT_CONFIG, safety_guarantee="priority"))
+    for sg, code in (("priority", 1), ("dmc", 2)):      # abstract.py:459-464: supervisors on the action tuple, vehicles un-shielded
+        c = mm.make_mm_config(dict(mm.DEFAULT_CONFIG, safety_guarantee=sg, env_name="merge-multi-agent-v0"))
+        assert (c.shield, c.supervisor, c.env_v0) == (0, code, 1)
+    assert mm.make_mm_config(dict(mm.DEFAULT_CONFIG, safety_guarantee="priority")).supervisor == 1    # env v1 as well
+    assert mm.make_mm_config(dict(mm.DEFAULT_CONFIG, safety_guarantee="cbf-cav")).supervisor == 0
     with pytest.raises(KeyError):
         mm.make("merge-v1")
 
@@ -253,8 +256,8 @@ def test_discounted_returns_match_reference_formula():
 
 
 def test_shipped_ini_files_map_onto_the_batched_path():
-    """Every shipped marl/configs/*.ini except the look-ahead baseline shields (priority / dmc) resolves to an
-    mm_config.  Needs the reference tree (present in the build container only)."""
+    """Every shipped marl/configs/*.ini resolves to an mm_config - the 8 look-ahead baseline configs (priority / dmc)
+    included, as a supervisor on the action tuple.  Needs the reference tree (present in the build container only)."""
     import configparser
     import glob
     import marl_mass_b200 as mm
@@ -278,8 +281,7 @@ def test_shipped_ini_files_map_onto_the_batched_path():
             ok.append(os.path.basename(f))
         except (ValueError, KeyError, AttributeError) as ex:
             rejected[os.path.basename(f)] = str(ex)
-    assert len(ok) == 29 and len(rejected) == 8
-    assert all(("priority" in m) or ("dmc" in m) for m in rejected.values())
+    assert len(ok) == 37 and not rejected, rejected
     assert "test-idm-td3.ini" in ok
     for must in ("marl_cav-heading-t_headway-cbf-cav.ini", "marl_cav-heading-t_headway-cbf-avs_cint.ini",
                  "marl_cav-heading-t_headway-cbf-cav-td3-srew.ini", "marl_cav-heading-t_headway-cbf-cav-mixed.ini",
@@ -425,8 +427,9 @@ def test_mappo_update_matches_one_reference_train_step():
 @pytest.mark.parametrize("name", ["priority_v0_td3_mixed", "dmc_v0_td3_mixed"])
 def test_supervisor_core_matches_reference_fixtures(name, tmp_path):
     """csrc/supervisor_core.h - the priority / dmc supervisors as host+device code, the source the supervisor kernels
-    will compile - built for the host and run on every step of the reference fixtures: the supervised tuple must be the
-    one the reference handed to _simulate.  (The kernels are not wired up yet; this pins their logic on the CPU.)"""
+    compile - built for the host and run on every step of the reference fixtures: the supervised tuple must be the one
+    the reference handed to _simulate, and the number of draws it reports as consumed the number of np.random.rand()
+    calls the reference made (the single-env adapter advances its MT19937 replay by that count)."""
     import oracle as orc
     g, cfg = load_golden(name)
     src = os.path.join(ROOT, "marl-mass_b200", "csrc", "supervisor_host.cpp")
@@ -434,7 +437,7 @@ def test_supervisor_core_matches_reference_fixtures(name, tmp_path):
     subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", src, "-o", lib_path])
     lib = ctypes.CDLL(lib_path)
     dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
-    lib.mm_supervisor_host.argtypes = [ctypes.c_int] * 3 + [dp] * 5 + [ip] * 5 + [dp, ctypes.c_double]
+    lib.mm_supervisor_host.argtypes = [ctypes.c_int] * 3 + [dp] * 5 + [ip] * 5 + [dp, ctypes.c_double, ip]
     rows = g["row_of_step"]
     st = orc.state_from_golden(g, rows)
     kind = 0 if cfg["safety_guarantee"] == "priority" else 1
@@ -447,13 +450,40 @@ def test_supervisor_core_matches_reference_fixtures(name, tmp_path):
                 i("crashed")]
         act = np.ascontiguousarray(g["act"][t, :n_cav], np.int32)
         draws = np.ascontiguousarray(np.nan_to_num(g["rand_draws"][t]), np.float64)
+        used = ctypes.c_int(-1)
         rc = lib.mm_supervisor_host(kind, n, n_cav, *[a.ctypes.data_as(dp if a.dtype == np.float64 else ip) for a in arrs],
-                                    act.ctypes.data_as(ip), draws.ctypes.data_as(dp), float(cfg["HEADWAY_TIME"]))
+                                    act.ctypes.data_as(ip), draws.ctypes.data_as(dp), float(cfg["HEADWAY_TIME"]), ctypes.byref(used))
         assert rc == 0
+        assert used.value == int(np.sum(~np.isnan(g["rand_draws"][t]))), (t, used.value)
         want = g["new_act"][t, :n_cav].astype(np.int32)
         assert np.array_equal(act, want), (t, g["act"][t, :n_cav].tolist(), act.tolist(), want.tolist())
         replaced += int(not np.array_equal(want, g["act"][t, :n_cav]))
     assert replaced >= 100
+
+
+@pytest.mark.parametrize("name", ["priority_v0_td3_mixed", "dmc_v0_td3_mixed"])
+def test_supervisor_draws_continue_the_spawn_stream(name):
+    """Seed-exact supervisors in the single-env adapter: the reference takes the supervisors' np.random.rand() numbers from
+    the process-global MT19937 stream that reset() seeded and the spawn consumed first; nothing else on the step path
+    draws from it.  So the generator `spawn_scene` hands back, advanced step by step by the number of draws the
+    supervisor consumed, reproduces every draw the reference logged for the episode."""
+    from marl_mass_b200 import spawn
+    from marl_mass_b200.env import traffic_type_of
+    g, cfg = load_golden(name)
+    ep, rows, rd = g["ep_start"], g["row_of_step"], g["rand_draws"]
+    total = 0
+    for k, seed in enumerate(cfg["seeds"]):
+        rngs = []
+        spawn.spawn_scene(seed, cfg["traffic_density"], traffic_type_of(cfg), 0, rng_out=rngs)
+        rs = rngs[0]
+        for t in np.where((rows >= ep[k]) & (rows < ep[k + 1] - 1))[0]:
+            n = int(np.sum(~np.isnan(rd[t])))
+            peek = np.random.RandomState()
+            peek.set_state(rs.get_state())
+            assert np.array_equal(peek.rand(32)[:n], rd[t, :n]), (seed, int(t))
+            rs.rand(n)
+            total += n
+    assert total > 3000
 
 
 def test_supervisor_core_compiles_for_sm100a(tmp_path):
@@ -494,7 +524,7 @@ def test_supervisor_core_agrees_with_the_python_restatement_on_fresh_scenes(kind
     subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", src, "-o", lib_path])
     lib = ctypes.CDLL(lib_path)
     dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
-    lib.mm_supervisor_host.argtypes = [ctypes.c_int] * 3 + [dp] * 5 + [ip] * 5 + [dp, ctypes.c_double]
+    lib.mm_supervisor_host.argtypes = [ctypes.c_int] * 3 + [dp] * 5 + [ip] * 5 + [dp, ctypes.c_double, ip]
     E = 24
     cfg = dict(mm.DEFAULT_CONFIG, env_name="merge-multi-agent-v0", safety_guarantee="none", traffic_density=td,
                traffic_type="mixed", mixed_traffic=True, HEADWAY_TIME=1.2)
@@ -517,7 +547,7 @@ def test_supervisor_core_agrees_with_the_python_restatement_on_fresh_scenes(kind
             d = np.ascontiguousarray(draws[e])
             assert lib.mm_supervisor_host(0 if kind == "priority" else 1, n, n_cav,
                                           *[x.ctypes.data_as(dp if x.dtype == np.float64 else ip) for x in arrs],
-                                          act.ctypes.data_as(ip), d.ctypes.data_as(dp), 1.2) == 0
+                                          act.ctypes.data_as(ip), d.ctypes.data_as(dp), 1.2, None) == 0
             assert act.tolist() == want, (t, e, a[e, :n_cav].tolist(), act.tolist(), want)
             replaced += int(want != a[e, :n_cav].tolist())
             a[e, :n_cav] = act           # the env then executes the supervised tuple

@@ -23,15 +23,16 @@ def test_device_supervisor_reproduces_the_reference_tuples(name):
     g, cfg = load_golden(name)
     rows = g["row_of_step"]
     T = len(rows)
-    env = mm.MergeEnvBatched(T, dict(env_config(cfg), safety_guarantee="none"))
+    env = mm.MergeEnvBatched(T, dict(env_config(cfg), safety_guarantee="none"))   # the supervisor alone: mm_supervise
     try:
         env.set_state(orc.state_from_golden(g, rows))
         draws = np.zeros((T, 32))
         draws[:, :16] = np.nan_to_num(g["rand_draws"])
-        got = env.supervise(torch.from_numpy(np.ascontiguousarray(g["act"])).cuda(), cfg["safety_guarantee"],
-                            torch.from_numpy(draws).cuda())
+        got, used = env.supervise(torch.from_numpy(np.ascontiguousarray(g["act"])).cuda(), cfg["safety_guarantee"],
+                                  torch.from_numpy(draws).cuda(), return_used=True)
         torch.cuda.synchronize()
         got = got.cpu().numpy()
+        assert np.array_equal(used.cpu().numpy(), np.sum(~np.isnan(g["rand_draws"]), axis=1))
         live = np.arange(12)[None, :] < g["st_n_cav"][rows][:, None]
         bad = np.argwhere((got != g["new_act"]) & live)
         assert len(bad) == 0, (len(bad), bad[:5].tolist())
