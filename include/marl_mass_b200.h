@@ -221,8 +221,21 @@ int mm_actor_sample(const float *obs, const int32_t *n_agents, int64_t n_rows, c
                     const float *w2, const float *b2, const float *w3, const float *b3, uint64_t seed, uint64_t step,
                     const uint8_t *action_mask, int8_t *actions, float *logp_all, float *logp_sel, void *stream);
 
-/* Implementation switch of mm_actor_sample (process-wide): 0 = tcgen05 (default), 1 = the warp-level mma.sync kernel
- * kept as an independent cross-check. */
+/* The same fused forward + draw for a 30 - h1 - 128 - 5 network, fp16 tensor-core operands with fp32 accumulation:
+ * h1 = 128 is the MAPPO actor above; h1 = 160 is the shared-trunk network of MAPPO_GI with state_split
+ * (marl/single_agent/Model_gi.py:137-220): its three first-layer blocks fc11 / fc12 / fc13 over fixed column lists are
+ * one 30 -> 160 layer whose weight w1 [160][30] is zero outside the blocks (the caller scatters them; b1 = the three
+ * biases concatenated), w2 = fc2.weight [128][160], w3 / b3 = actor_linear.  value_w [128] / value_b [1] (nullable) =
+ * critic_linear: values [n_rows] receives V(s) from the same hidden activations (the bootstrap value of
+ * mappo_gi.py:396-404).  Everything else as in mm_actor_sample. */
+int mm_actor_sample_mlp(const float *obs, const int32_t *n_agents, int64_t n_rows, int h1, const float *w1, const float *b1,
+                        const float *w2, const float *b2, const float *w3, const float *b3, const float *value_w,
+                        const float *value_b, uint64_t seed, uint64_t step, const uint8_t *action_mask, int8_t *actions,
+                        float *logp_all, float *logp_sel, float *values, void *stream);
+
+/* Implementation switch of mm_actor_sample (process-wide): 0 = tcgen05 with fp16 operands, two CTAs per SM (default,
+ * the kernel of mm_actor_sample_mlp); 1 = the warp-level mma.sync TF32 kernel kept as an independent cross-check;
+ * 2 = the first tcgen05 kernel (TF32 operands, one CTA per SM). */
 int mm_set_actor_impl(int impl);
 
 /* mm_discounted_returns: MAPPO._discount_reward (marl/mappo.py:364-370) for every (env, agent) column of a rollout at

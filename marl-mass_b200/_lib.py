@@ -82,7 +82,7 @@ SUPERVISOR_DRAWS = 32     # MM_SUPERVISOR_DRAWS
 EXPORTS = ("mm_create", "mm_destroy", "mm_set_config", "mm_num_envs", "mm_reset", "mm_step", "mm_step_host",
            "mm_step_host_ragged", "mm_step_host_packed", "mm_expand_obs_rows",
            "mm_buffers_get", "mm_get_state", "mm_set_state", "mm_get_shield_diag", "mm_stats", "mm_shield_qp",
-           "mm_actor_sample", "mm_set_actor_impl", "mm_set_step_variant", "mm_step_build", "mm_abi_version", "mm_discounted_returns", "mm_supervise", "mm_set_supervisor_draws", "mm_supervisor_draws_used",
+           "mm_actor_sample", "mm_actor_sample_mlp", "mm_set_actor_impl", "mm_set_step_variant", "mm_step_build", "mm_abi_version", "mm_discounted_returns", "mm_supervise", "mm_set_supervisor_draws", "mm_supervisor_draws_used",
            "mm_kernel_launches", "mm_last_error", "mm_version")
 
 
@@ -118,6 +118,8 @@ def lib():
     L.mm_shield_qp.argtypes = [C.c_void_p] * 6 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mm_actor_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 6 + [C.c_uint64, C.c_uint64] + \
                                  [C.c_void_p] * 5
+    L.mm_actor_sample_mlp.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int] + [C.c_void_p] * 8 + [C.c_uint64, C.c_uint64] + \
+                                     [C.c_void_p] * 6
     L.mm_set_actor_impl.argtypes = [C.c_int]
     L.mm_set_step_variant.argtypes = [C.c_int]
     L.mm_step_build.argtypes = [h]

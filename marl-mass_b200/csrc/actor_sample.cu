@@ -479,6 +479,282 @@ actor_sample_tcgen05_kernel(const float *__restrict__ obs, const int32_t *__rest
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------
+// tcgen05, second generation: fp16 operands, two CTAs per SM, any first-layer width, optional value head
+// ------------------------------------------------------------------------------------------------
+// The TF32 kernel above runs one tile at a time per SM: stage -> MMA -> epilogue -> MMA -> epilogue, each phase waiting
+// for the one before (ncu: long-scoreboard stalls on tcgen05.ld / mbarrier polls, tensor pipe 19 % busy).  This one
+// halves every shared-memory operand (kind::f16: fp16 has TF32's 10-bit mantissa; observations live in [-1, 1], the
+// hidden activations of these networks stay far below 65 504) so that TWO CTAs fit an SM (<= 108 KB each, 256 TMEM
+// columns each): while one CTA's threads run an epilogue the other CTA's MMAs and loads proceed - the overlap of a
+// software pipeline without warp specialisation.  MMAs are K = 16 (half as many instructions).
+//   H1 = 128: MAPPO ActorNetwork 30-128-128-5 (Model_common.py:5-23).
+//   H1 = 160: MAPPO_GI ActorCriticNetwork with state_split (Model_gi.py:137-220): its three first-layer blocks
+//             (5 -> 32, 10 -> 64, 10 -> 64 over fixed column lists) are ONE 30 -> 160 layer whose weight matrix is zero
+//             outside the blocks; the host scatters fc11 / fc12 / fc13 into it (rollout.py).  The optional sixth output
+//             column is critic_linear (the state value V(s), mappo_gi.py:396-404).
+// CTA = 256 threads: warp w reads TMEM lane quarter w % 4 (hardware rule) and column half w / 4.  D2 reuses D1's
+// columns (D1 is dead once epilogue 1 has been read and the CTA has synchronised).
+template <int H1>
+struct M5 {
+    static constexpr int THREADS = 256;
+    static constexpr int ROWS = 128;
+    static constexpr int CH1 = H1 / 8;                        // k-chunks (8 halves = 16 bytes) of layer 2
+    static constexpr uint32_t A_CHUNK = ROWS * 16;            // one k-chunk of the 128 rows of a tile / of W2's 128 rows
+    static constexpr uint32_t W1_CHUNK = H1 * 16;             // one k-chunk of W1's H1 rows
+    static constexpr uint32_t A1 = 0;                         // [4 chunks][128] 16 B
+    static constexpr uint32_t W1 = A1 + 4 * A_CHUNK;          // [4 chunks][H1]
+    static constexpr uint32_t A2 = W1 + 4 * W1_CHUNK;         // [CH1][128]
+    static constexpr uint32_t W2 = A2 + CH1 * A_CHUNK;        // [CH1][128]
+    static constexpr uint32_t W3 = W2 + CH1 * A_CHUNK;        // [128 hidden][8] f32: 5 logit columns, the value column, 2 unused
+    static constexpr uint32_t B1 = W3 + AC_HID * 8 * 4;
+    static constexpr uint32_t B2 = B1 + H1 * 4;
+    static constexpr uint32_t B3 = B2 + AC_HID * 4;
+    static constexpr uint32_t PART = B3 + 8 * 4;              // [128 rows][8] f32: partial outputs of the upper column half
+    static constexpr uint32_t BAR = PART + ROWS * 8 * 4;      // 2 mbarriers + the TMEM base address
+    static constexpr uint32_t SMEM = BAR + 32;
+    // instruction descriptors, kind::f16: F32 accumulate, fp16 A / B, K-major, M = 128, N = H1 (layer 1) / 128 (layer 2)
+    static constexpr uint32_t IDESC1 = (1u << 4) | ((uint32_t)(H1 >> 3) << 17) | ((128u >> 4) << 24);
+    static constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)(AC_HID >> 3) << 17) | ((128u >> 4) << 24);
+};
+
+__device__ __forceinline__ uint64_t m5_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+    // K-major, SWIZZLE_NONE: start address, LBO (between the two 16-byte k-chunks of an MMA), SBO (between 8-row groups)
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void m5_mma(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                 ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void m5_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));    // low half = a, high half = b
+    return r;
+}
+
+template <int H1>
+__global__ void __launch_bounds__(256, 2)
+actor_mlp_tcgen05_kernel(const float *__restrict__ obs, const int32_t *__restrict__ n_agents, int64_t n_rows,
+                         const float *__restrict__ w1, const float *__restrict__ b1, const float *__restrict__ w2,
+                         const float *__restrict__ b2, const float *__restrict__ w3, const float *__restrict__ b3,
+                         const float *__restrict__ wv, const float *__restrict__ bv, uint64_t seed, uint64_t step,
+                         const uint8_t *__restrict__ mask_bits, int8_t *__restrict__ actions, float *__restrict__ logp_all,
+                         float *__restrict__ logp_sel, float *__restrict__ values) {
+    using L = M5<H1>;
+    extern __shared__ __align__(128) uint8_t m5_sm[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint4 *a1 = reinterpret_cast<uint4 *>(m5_sm + L::A1), *w1f = reinterpret_cast<uint4 *>(m5_sm + L::W1);
+    uint4 *a2 = reinterpret_cast<uint4 *>(m5_sm + L::A2), *w2f = reinterpret_cast<uint4 *>(m5_sm + L::W2);
+    float *w3s = reinterpret_cast<float *>(m5_sm + L::W3), *b1s = reinterpret_cast<float *>(m5_sm + L::B1);
+    float *b2s = reinterpret_cast<float *>(m5_sm + L::B2), *b3s = reinterpret_cast<float *>(m5_sm + L::B3);
+    float *part = reinterpret_cast<float *>(m5_sm + L::PART);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(m5_sm + L::BAR);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(m5_sm + L::BAR + 16);
+    const uint32_t bar1 = t5_smem(bars), bar2 = t5_smem(bars + 1);
+
+    // ---- one-time setup: weights in operand layout (fp16), barriers, TMEM ----
+    for (int idx = tid; idx < 4 * H1; idx += L::THREADS) {           // W1: [out n][in k], k padded 30 -> 32
+        const int c = idx / H1, n = idx % H1, k = 8 * c;
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = k + q < AC_IN ? w1[n * AC_IN + k + q] : 0.f;
+        w1f[idx] = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+    }
+    for (int idx = tid; idx < L::CH1 * L::ROWS; idx += L::THREADS) {  // W2: [out n = 128][in k = H1]
+        const int c = idx / L::ROWS, n = idx % L::ROWS;
+        const float4 lo = *reinterpret_cast<const float4 *>(w2 + n * H1 + 8 * c), hi = *reinterpret_cast<const float4 *>(w2 + n * H1 + 8 * c + 4);
+        w2f[idx] = make_uint4(pack_h2(lo.x, lo.y), pack_h2(lo.z, lo.w), pack_h2(hi.x, hi.y), pack_h2(hi.z, hi.w));
+    }
+    for (int idx = tid; idx < AC_HID * 8; idx += L::THREADS) {
+        const int h = idx >> 3, k = idx & 7;
+        w3s[idx] = k < AC_OUT ? w3[k * AC_HID + h] : (k == AC_OUT && wv ? wv[h] : 0.f);
+    }
+    for (int idx = tid; idx < H1; idx += L::THREADS) b1s[idx] = b1[idx];
+    for (int idx = tid; idx < AC_HID; idx += L::THREADS) b2s[idx] = b2[idx];
+    if (tid < 8) b3s[tid] = tid < AC_OUT ? b3[tid] : (tid == AC_OUT && bv ? bv[0] : 0.f);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar2));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(t5_smem(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t a1_addr = t5_smem(a1), w1_addr = t5_smem(w1f), a2_addr = t5_smem(a2), w2_addr = t5_smem(w2f);
+
+    const int row_in_tile = 32 * (warp & 3) + lane;        // TMEM lane = row of the tile this thread reads
+    const int hh = warp >> 2;                              // column half
+    const uint32_t t_lane = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+    const int64_t n_tiles = (n_rows + L::ROWS - 1) / L::ROWS;
+    // observation staging: thread t handles row t % 128, k-chunks 2 * (t / 128) and + 1 (8 floats each)
+    const int st_r = tid & (L::ROWS - 1), st_c0 = 2 * (tid >> 7);
+    float2 pre[8];
+    auto fetch = [&](int64_t tile) {
+        const int64_t row = tile * L::ROWS + st_r;
+        const float2 *src = reinterpret_cast<const float2 *>(obs + row * AC_IN);   // rows are 120 B: 8-byte aligned
+        const bool ok = tile < n_tiles && row < n_rows;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int f2 = 4 * st_c0 + q;                  // float2 index inside the row: 15 hold data
+            pre[q] = (ok && f2 < AC_IN / 2) ? __ldg(src + f2) : make_float2(0.f, 0.f);
+        }
+    };
+    fetch(blockIdx.x);
+    uint32_t parity = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, parity ^= 1) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+            a1[(st_c0 + q) * L::ROWS + st_r] = make_uint4(pack_h2(pre[4 * q].x, pre[4 * q].y), pack_h2(pre[4 * q + 1].x, pre[4 * q + 1].y),
+                                                         pack_h2(pre[4 * q + 2].x, pre[4 * q + 2].y), pack_h2(pre[4 * q + 3].x, pre[4 * q + 3].y));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                m5_mma(tmem, m5_desc(a1_addr + j * 2 * L::A_CHUNK, L::A_CHUNK), m5_desc(w1_addr + j * 2 * L::W1_CHUNK, L::W1_CHUNK),
+                       L::IDESC1, j > 0);
+            t5_commit(bar1);
+        }
+        fetch(tile + gridDim.x);                           // next tile's rows: in flight during this tile's epilogues
+        t5_wait(bar1, parity);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- epilogue 1: h1 = relu(D1 + b1) -> A2 (this thread: its row, H1 / 2 columns in pieces of 16) ----
+#pragma unroll 1
+        for (int it = 0; it < H1 / 32; ++it) {
+            const int col = hh * (H1 / 2) + 16 * it;
+            uint32_t v[16];
+            m5_ld16(t_lane + (uint32_t)col, v);
+            float h[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) h[q] = fmaxf(__uint_as_float(v[q]) + b1s[col + q], 0.f);
+            a2[(col / 8) * L::ROWS + row_in_tile] = make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
+            a2[(col / 8 + 1) * L::ROWS + row_in_tile] = make_uint4(pack_h2(h[8], h[9]), pack_h2(h[10], h[11]), pack_h2(h[12], h[13]), pack_h2(h[14], h[15]));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < H1 / 16; ++j)
+                m5_mma(tmem, m5_desc(a2_addr + j * 2 * L::A_CHUNK, L::A_CHUNK), m5_desc(w2_addr + j * 2 * L::A_CHUNK, L::A_CHUNK),
+                       L::IDESC2, j > 0);
+            t5_commit(bar2);
+        }
+        t5_wait(bar2, parity);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- epilogue 2: h2 = relu(D2 + b2); the 128 -> 5 (+ value) output layer as FMAs over this thread's 64 hidden units ----
+        float lg[AC_OUT + 1] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+        for (int it = 0; it < 4; ++it) {
+            const int col = hh * 64 + 16 * it;
+            uint32_t v[16];
+            m5_ld16(t_lane + (uint32_t)col, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float h = fmaxf(__uint_as_float(v[j]) + b2s[col + j], 0.f);
+                const float4 wa = *reinterpret_cast<const float4 *>(w3s + (col + j) * 8);
+                const float2 wb = *reinterpret_cast<const float2 *>(w3s + (col + j) * 8 + 4);
+                lg[0] = fmaf(h, wa.x, lg[0]); lg[1] = fmaf(h, wa.y, lg[1]); lg[2] = fmaf(h, wa.z, lg[2]);
+                lg[3] = fmaf(h, wa.w, lg[3]); lg[4] = fmaf(h, wb.x, lg[4]); lg[5] = fmaf(h, wb.y, lg[5]);
+            }
+        }
+        if (hh == 1) {
+#pragma unroll
+            for (int k = 0; k <= AC_OUT; ++k) part[row_in_tile * 8 + k] = lg[k];
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        const int64_t row = tile * L::ROWS + row_in_tile;
+        if (hh == 0 && row < n_rows) {
+            float l[AC_OUT];
+#pragma unroll
+            for (int k = 0; k < AC_OUT; ++k) l[k] = lg[k] + part[row_in_tile * 8 + k] + b3s[k];
+            if (values) values[row] = lg[AC_OUT] + part[row_in_tile * 8 + AC_OUT] + b3s[AC_OUT];
+            apply_action_mask(l, mask_bits, row);
+            float m = l[0];
+#pragma unroll
+            for (int k = 1; k < AC_OUT; ++k) m = fmaxf(m, l[k]);
+            float e[AC_OUT], S = 0.f;
+#pragma unroll
+            for (int k = 0; k < AC_OUT; ++k) { e[k] = __expf(l[k] - m); S += e[k]; }
+            const float logS = __logf(S);
+            const float u = (float)(philox_row(seed, step, (uint64_t)row) >> 8) * (1.0f / 16777216.0f);
+            const float target = u * S;
+            int a = AC_OUT - 1;
+            float c = 0.f;
+            bool found = false;
+#pragma unroll
+            for (int k = 0; k < AC_OUT; ++k) {
+                c += e[k];
+                if (!found && target < c) { a = k; found = true; }
+            }
+            bool live = true;
+            if (n_agents) live = (int)(row % MAXV) < n_agents[row / MAXV];
+            actions[row] = (int8_t)(live ? a : 1);
+            if (logp_sel) logp_sel[row] = l[a] - m - logS;
+            if (logp_all) {
+#pragma unroll
+                for (int k = 0; k < AC_OUT; ++k) logp_all[row * AC_OUT + k] = l[k] - m - logS;
+            }
+        }
+        __syncthreads();   // `part` and D (TMEM columns) are reused by the next tile
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+}
+
+template <int H1>
+static int launch_actor_mlp_t(const float *obs, const int32_t *n_agents, int64_t n_rows, const float *w1, const float *b1,
+                              const float *w2, const float *b2, const float *w3, const float *b3, const float *wv, const float *bv,
+                              uint64_t seed, uint64_t step, const uint8_t *mask_bits, int8_t *actions, float *logp_all,
+                              float *logp_sel, float *values, void *stream) {
+    static bool ready[MM_MAX_DEVICES] = {};
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MM_MAX_DEVICES) return 1;
+    if (!ready[dev]) {
+        if (cudaFuncSetAttribute(actor_mlp_tcgen05_kernel<H1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M5<H1>::SMEM) != cudaSuccess)
+            return 1;
+        ready[dev] = true;
+    }
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t tiles = (n_rows + 127) / 128, ctas = tiles < 2 * sms ? tiles : 2 * sms;   // persistent: two CTAs per SM
+    actor_mlp_tcgen05_kernel<H1><<<(unsigned)ctas, 256, M5<H1>::SMEM, (cudaStream_t)stream>>>(
+        obs, n_agents, n_rows, w1, b1, w2, b2, w3, b3, wv, bv, seed, step, mask_bits, actions, logp_all, logp_sel, values);
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+int launch_actor_mlp(const float *obs, const int32_t *n_agents, int64_t n_rows, int h1, const float *w1, const float *b1,
+                     const float *w2, const float *b2, const float *w3, const float *b3, const float *wv, const float *bv,
+                     uint64_t seed, uint64_t step, const uint8_t *mask_bits, int8_t *actions, float *logp_all, float *logp_sel,
+                     float *values, void *stream) {
+    if (n_rows <= 0) return 0;
+    if (h1 == 128)
+        return launch_actor_mlp_t<128>(obs, n_agents, n_rows, w1, b1, w2, b2, w3, b3, wv, bv, seed, step, mask_bits, actions, logp_all,
+                                       logp_sel, values, stream);
+    if (h1 == 160)
+        return launch_actor_mlp_t<160>(obs, n_agents, n_rows, w1, b1, w2, b2, w3, b3, wv, bv, seed, step, mask_bits, actions, logp_all,
+                                       logp_sel, values, stream);
+    return 2;
+}
+
 // R_t = r_t + gamma * R_{t+1}, restarted after a terminal step: MAPPO._discount_reward (marl/mappo.py:364-370) for every
 // (env, agent) column of a rollout at once.  rewards / out [T][n_cols], dones [T][n_cols / cols_per_env] (1 where step t
 // ended the episode of that env), final_value [n_cols] (critic bootstrap; ignored where the last step was terminal).
@@ -508,8 +784,8 @@ int launch_discounted_returns(const float *rewards, const uint8_t *dones, const 
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
-int g_actor_impl = -1;   // -1: not chosen yet; 0: tcgen05; 1: mma.sync
-void set_actor_impl(int impl) { g_actor_impl = impl ? 1 : 0; }
+int g_actor_impl = -1;   // -1: not chosen yet; 0: tcgen05 fp16, two CTAs per SM; 1: mma.sync TF32; 2: tcgen05 TF32, one CTA per SM
+void set_actor_impl(int impl) { g_actor_impl = (impl == 1 || impl == 2) ? impl : 0; }
 
 int launch_actor_sample(const float *obs, const int32_t *n_agents, int64_t n_rows, const float *w1, const float *b1,
                         const float *w2, const float *b2, const float *w3, const float *b3, uint64_t seed, uint64_t step,
@@ -526,8 +802,11 @@ int launch_actor_sample(const float *obs, const int32_t *n_agents, int64_t n_row
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // g_actor_impl (mm_set_actor_impl; initial value from MM_ACTOR_IMPL=mma): 1 selects the warp-level mma.sync kernel
     // above, kept as the independent cross-check of the tcgen05 one
-    if (g_actor_impl < 0) { const char *e = getenv("MM_ACTOR_IMPL"); g_actor_impl = (e && e[0] == 'm') ? 1 : 0; }
-    if (g_actor_impl == 0) {
+    if (g_actor_impl < 0) { const char *e = getenv("MM_ACTOR_IMPL"); g_actor_impl = (e && e[0] == 'm') ? 1 : ((e && e[0] == 't') ? 2 : 0); }
+    if (g_actor_impl == 0)
+        return launch_actor_mlp(obs, n_agents, n_rows, 128, w1, b1, w2, b2, w3, b3, nullptr, nullptr, seed, step, mask_bits, actions,
+                                logp_all, logp_sel, nullptr, stream);
+    if (g_actor_impl == 2) {
         static bool t5_attr = false;
         if (!t5_attr) {
             if (cudaFuncSetAttribute(actor_sample_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T5_SMEM) != cudaSuccess)

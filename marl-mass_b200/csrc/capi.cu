@@ -767,8 +767,23 @@ int mm_actor_sample(const float *obs, const int32_t *n_agents, int64_t n_rows, c
     return 0;
 }
 
+int mm_actor_sample_mlp(const float *obs, const int32_t *n_agents, int64_t n_rows, int h1, const float *w1, const float *b1,
+                        const float *w2, const float *b2, const float *w3, const float *b3, const float *value_w,
+                        const float *value_b, uint64_t seed, uint64_t step, const uint8_t *action_mask, int8_t *actions,
+                        float *logp_all, float *logp_sel, float *values, void *stream) {
+    if (!obs || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !actions) return fail(MM_ERR_ARG, "null argument");
+    if (h1 != 128 && h1 != 160) return fail(MM_ERR_ARG, "h1 must be 128 (ActorNetwork) or 160 (ActorCriticNetwork, state_split)");
+    if (n_rows < 0) return fail(MM_ERR_ARG, "n_rows must be >= 0");
+    if (n_agents && n_rows % MAXV != 0) return fail(MM_ERR_ARG, "n_rows must be a multiple of MM_MAXV when n_agents is given");
+    if (values && (!value_w || !value_b)) return fail(MM_ERR_ARG, "values needs value_w and value_b");
+    if (launch_actor_mlp(obs, n_agents, n_rows, h1, w1, b1, w2, b2, w3, b3, value_w, value_b, seed, step, action_mask, actions,
+                         logp_all, logp_sel, values, stream))
+        return fail(MM_ERR_CUDA, cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
+
 int mm_set_actor_impl(int impl) {
-    if (impl != 0 && impl != 1) return fail(MM_ERR_ARG, "impl must be 0 (tcgen05) or 1 (mma.sync)");
+    if (impl < 0 || impl > 2) return fail(MM_ERR_ARG, "impl must be 0 (tcgen05 fp16), 1 (mma.sync TF32) or 2 (tcgen05 TF32)");
     set_actor_impl(impl);
     return 0;
 }

@@ -172,8 +172,60 @@ def discounted_returns(rewards, dones, final_value, gamma):
 
 
 def set_actor_impl(name):
-    """'tcgen05' (default) or 'mma' (the warp-level mma.sync kernel, kept as a cross-check)."""
-    _lib.check(_lib.lib().mm_set_actor_impl({"tcgen05": 0, "mma": 1}[name]))
+    """'tcgen05' (default: fp16 operands, two CTAs per SM), 'mma' (the warp-level mma.sync TF32 kernel, kept as an
+    independent cross-check) or 'tcgen05_tf32' (the first tcgen05 kernel: TF32 operands, one CTA per SM)."""
+    _lib.check(_lib.lib().mm_set_actor_impl({"tcgen05": 0, "mma": 1, "tcgen05_tf32": 2}[name]))
+
+
+_DENSE_CACHE = {}
+
+
+def _split_first_layer(policy):
+    """The three first-layer blocks of the state_split network (Model_gi.py:137-176: fc11 over the presence columns,
+    fc12 over x / y, fc13 over vx / vy) as ONE 30 -> 160 layer: weight [160][30], zero outside the blocks, bias [160].
+    Cached per module until a parameter changes (torch bumps `_version` on every in-place update)."""
+    ps = (policy.fc11.weight, policy.fc11.bias, policy.fc12.weight, policy.fc12.bias, policy.fc13.weight, policy.fc13.bias)
+    key = tuple((p.data_ptr(), p._version) for p in ps)
+    hit = _DENSE_CACHE.get(id(policy))
+    if hit is not None and hit[0] == key:
+        return hit[1], hit[2]
+    h4, h2 = policy.fc11.out_features, policy.fc12.out_features
+    w = torch.zeros((h4 + 2 * h2, NS), dtype=torch.float32, device=ps[0].device)
+    w[:h4, list(policy.COLS1)] = ps[0].detach().float()
+    w[h4:h4 + h2, list(policy.COLS2)] = ps[2].detach().float()
+    w[h4 + h2:, list(policy.COLS3)] = ps[4].detach().float()
+    b = torch.cat([ps[1].detach().float(), ps[3].detach().float(), ps[5].detach().float()]).contiguous()
+    _DENSE_CACHE[id(policy)] = (key, w, b)
+    return w, b
+
+
+def policy_sample(policy, obs, n_agents=None, seed=0, step=0, want_logp=False, action_mask=None, want_value=False):
+    """Fused forward + exploration draw of the MAPPO_GI shared network (mm_actor_sample_mlp with h1 = 160): `policy` is
+    an ActorCriticNetwork with state_split and hidden size 128; -> actions int8 [...] (+ log-probabilities [..., 5] with
+    want_logp, + V(s) [...] from critic_linear with want_value).  Other arguments as for `actor_sample`."""
+    assert policy.state_split and policy.fc2.out_features == 128 and policy.fc2.in_features == 160, \
+        "the fused kernel covers the reference's shared network (hidden size 128, state_split)"
+    rows = obs.numel() // NS
+    obs = obs.contiguous()
+    assert obs.is_cuda and obs.dtype == torch.float32
+    w1, b1 = _split_first_layer(policy)
+    w = [policy.fc2.weight, policy.fc2.bias, policy.actor_linear.weight, policy.actor_linear.bias,
+         policy.critic_linear.weight, policy.critic_linear.bias]
+    w = [t.detach().contiguous().float() for t in w]
+    actions = torch.empty(obs.shape[:-1], dtype=torch.int8, device=obs.device)
+    logp = torch.empty(obs.shape[:-1] + (NA,), dtype=torch.float32, device=obs.device) if want_logp else None
+    values = torch.empty(obs.shape[:-1], dtype=torch.float32, device=obs.device) if want_value else None
+    if n_agents is not None:
+        assert n_agents.dtype == torch.int32 and n_agents.is_cuda and n_agents.numel() * MAXV == rows
+    if action_mask is not None:
+        assert action_mask.dtype == torch.uint8 and action_mask.is_cuda and action_mask.numel() == rows
+        action_mask = action_mask.contiguous()
+    _lib.check(_lib.lib().mm_actor_sample_mlp(_ptr(obs), _ptr(n_agents), C.c_int64(rows), 160, _ptr(w1), _ptr(b1), _ptr(w[0]),
+                                              _ptr(w[1]), _ptr(w[2]), _ptr(w[3]), _ptr(w[4]), _ptr(w[5]), C.c_uint64(seed),
+                                              C.c_uint64(step), _ptr(action_mask), _ptr(actions), _ptr(logp), _ptr(None),
+                                              _ptr(values), _stream()))
+    out = (actions,) + ((logp,) if want_logp else ()) + ((values,) if want_value else ())
+    return out if len(out) > 1 else actions
 
 
 def actor_sample(actor, obs, n_agents=None, seed=0, step=0, want_logp=False, action_mask=None):
@@ -367,14 +419,17 @@ class BatchedMAPPOGIRollout(BatchedMAPPORollout):
     RMSprop optimiser at `actor_lr` (mappo_gi.py:150-156) steps the summed loss (`shared_network_loss`), the bootstrap
     value is V(final state) (mappo_gi.py:396-404).  Rollout, reward selection, scaling and returns are the base class's.
     As in the reference the policy is evaluated WITHOUT an action mask everywhere (`self.policy(state)`,
-    mappo_gi.py:309,359): `action_masking` only changes what env.reset / step report.  The action draw runs as torch
-    layers (the fused actor kernel is the 30-128-128-5 network of `MAPPO`)."""
+    mappo_gi.py:309,359): `action_masking` only changes what env.reset / step report.  With the reference's hidden size
+    (128) the action draw and the bootstrap value come from the fused kernel (`policy_sample`: mm_actor_sample_mlp with
+    the three first-layer blocks as one 30 -> 160 layer); other sizes run as torch layers."""
 
     def __init__(self, env, policy=None, hidden_size=128, **kw):
-        kw["fused"] = False
+        net = policy or ActorCriticNetwork(NS, NA, hidden_size, 1, state_split=True)
+        kw["fused"] = bool(kw.get("fused", True)) and net.state_split and net.fc2.in_features == 160 and \
+            net.fc2.out_features == 128
         dev = torch.device("cuda", env.device)
         super().__init__(env, **kw)
-        self.policy = (policy or ActorCriticNetwork(NS, NA, hidden_size, 1, state_split=True)).to(dev)
+        self.policy = net.to(dev)
         self.policy_target = ActorCriticNetwork(NS, NA, hidden_size, 1, state_split=self.policy.state_split).to(dev)
         self.policy_target.load_state_dict(self.policy.state_dict())
         self.policy_opt = torch.optim.RMSprop(self.policy.parameters(), lr=self.actor_opt.param_groups[0]["lr"])
@@ -388,13 +443,23 @@ class BatchedMAPPOGIRollout(BatchedMAPPORollout):
         live = self._slot < n_agents[:, None]
         return torch.where(live, a, torch.ones_like(a)).to(torch.int8), live
 
+    @torch.no_grad()
+    def act_fused(self, obs, n_agents):
+        self._draws += 1
+        a = policy_sample(self.policy, obs, n_agents, seed=self.seed, step=self._draws)
+        return a, self._slot < n_agents[:, None]
+
     def _final_value(self, obs, n_agents):
+        if self.fused:     # V(s) from the same kernel family: critic_linear as a sixth output column
+            return policy_sample(self.policy, obs, n_agents, seed=self.seed, step=0, want_value=True)[1].view(self.E, MAXV)
         return self.policy(obs.reshape(-1, NS), out_type="v").view(self.E, MAXV)
 
     def networks(self):
         return [self.policy, self.policy_target]
 
     def sample_actions(self, obs, n_agents, seed, step):
+        if self.fused:
+            return policy_sample(self.policy, obs.contiguous(), n_agents, seed=seed, step=step)
         return self.act_torch(obs, n_agents)[0]
 
     def update(self, minibatch=1 << 18, epochs=1):

@@ -39,3 +39,14 @@ print("act_fused          %.3f ms" % timed(lambda: pol.act_fused(v["obs"], v["n_
 print("act_fused + step   %.3f ms" % timed(lambda: env.step(pol.act_fused(v["obs"], v["n_agents"])[0], auto_reset=True)))
 lp = mm.rollout.actor_sample(pol.actor, obs, v["n_agents"], seed=1, step=1, want_logp=True)[1]
 print("max |logp_fused - logp_torch| = %.3e" % float((lp.view(-1, 5) - logp).abs().max()))
+# round 2: the three actor kernels and the MAPPO_GI shared network on the same rows
+from marl_mass_b200 import rollout
+for name in ("tcgen05", "tcgen05_tf32", "mma"):
+    rollout.set_actor_impl(name)
+    print("actor_sample %-13s %.4f ms" % (name, timed(lambda: rollout.actor_sample(pol.actor, obs, v["n_agents"], seed=1, step=1), n=50)))
+rollout.set_actor_impl("tcgen05")
+gi = rollout.ActorCriticNetwork().cuda()
+with torch.no_grad():
+    print("GI torch forward+draw      %.4f ms" % timed(lambda: torch.multinomial(gi(obs.view(-1, mm.NS)).exp(), 1)))
+print("GI policy_sample (h1=160)  %.4f ms" % timed(lambda: rollout.policy_sample(gi, obs, v["n_agents"], seed=1, step=1), n=50))
+print("GI policy_sample + value   %.4f ms" % timed(lambda: rollout.policy_sample(gi, obs, v["n_agents"], seed=1, step=1, want_value=True), n=50))

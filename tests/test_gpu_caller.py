@@ -109,6 +109,73 @@ def test_tcgen05_and_mma_sync_actor_kernels_agree(mm):
     assert float((a_m != a_t).float().mean()) < 5e-3
 
 
+def test_all_three_actor_kernels_agree(mm):
+    """fp16 tcgen05 (default) vs TF32 tcgen05 vs TF32 mma.sync on the same network and rows: fp16 and TF32 operands share
+    the 10-bit mantissa, accumulation is fp32 everywhere -> log-probabilities within 1e-2, the same draw except next to
+    a CDF step."""
+    import torch
+    from marl_mass_b200 import rollout
+    torch.manual_seed(4)
+    actor = rollout.ActorNetwork().cuda()
+    obs = (torch.rand(70001, mm.NS, device="cuda") * 2.2 - 1.1).contiguous()
+    out = {}
+    try:
+        for name in ("tcgen05", "tcgen05_tf32", "mma"):
+            rollout.set_actor_impl(name)
+            out[name] = rollout.actor_sample(actor, obs, None, seed=9, step=1, want_logp=True)
+            torch.cuda.synchronize()
+    finally:
+        rollout.set_actor_impl("tcgen05")
+    ref = torch.log_softmax(actor.fc3(torch.relu(actor.fc2(torch.relu(actor.fc1(obs))))), dim=1)
+    for name, (a, lp) in out.items():
+        assert float((lp - ref).abs().max()) < 1e-2, name
+        assert float((a != out["tcgen05"][0]).float().mean()) < 5e-3, name
+
+
+def test_fused_shared_network_of_mappo_gi(mm):
+    """mm_actor_sample_mlp with h1 = 160: the MAPPO_GI ActorCriticNetwork (state_split: three first-layer blocks over
+    fixed column lists, scattered into one 30 -> 160 weight matrix) against the torch fp32 module - log-probabilities with
+    and without invalid-action masking, the value head, draw frequencies following the softmax, absent agents -> IDLE."""
+    import torch
+    from marl_mass_b200 import rollout
+    torch.manual_seed(11)
+    pol = rollout.ActorCriticNetwork().cuda()
+    for p in pol.parameters():
+        p.data.mul_(2.0)
+    n = 50000
+    obs = (torch.rand(n, mm.NS, device="cuda") * 2.2 - 1.1).contiguous()
+    mask = torch.randint(0, 32, (n,), device="cuda", dtype=torch.uint8) | 2           # IDLE always available
+    a, lp, v = rollout.policy_sample(pol, obs, None, seed=3, step=1, want_logp=True, want_value=True)
+    a_m, lp_m = rollout.policy_sample(pol, obs, None, seed=3, step=1, want_logp=True, action_mask=mask)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        want = pol(obs)
+        want_v = pol(obs, out_type="v").squeeze(1)
+        bits = ((mask[:, None].int() >> torch.arange(5, device="cuda")[None, :]) & 1)
+        want_m = pol(obs, action_mask=bits)
+    assert float((lp - want).abs().max()) < 2e-2 and float((v - want_v).abs().max()) < 2e-2 * max(1.0, float(want_v.abs().max()))
+    ok = bits.bool()
+    assert float((lp_m - want_m)[ok].abs().max()) < 2e-2
+    assert bool(ok.gather(1, a_m.long()[:, None]).all())                              # a masked action is never drawn
+    # the weights change in place (an optimiser step): the cached dense first layer must follow
+    with torch.no_grad():
+        pol.fc12.weight.add_(0.05)
+        lp2 = rollout.policy_sample(pol, obs, None, seed=3, step=1, want_logp=True)[1]
+        assert float((lp2 - pol(obs)).abs().max()) < 2e-2
+    # draw frequencies of one row replicated
+    row = obs[:1].expand(200000, mm.NS).contiguous()
+    acts = rollout.policy_sample(pol, row, None, seed=5, step=7)
+    freq = torch.bincount(acts.long(), minlength=5).float() / acts.numel()
+    p_row = pol(obs[:1]).exp()[0]
+    assert float((freq - p_row).abs().max()) < 6 * float((p_row * (1 - p_row) / acts.numel()).sqrt().max()) + 2e-3
+    # absent agents get IDLE
+    env_obs = (torch.rand(64, 12, mm.NS, device="cuda") * 2 - 1).contiguous()
+    n_ag = torch.randint(1, 12, (64,), device="cuda", dtype=torch.int32)
+    acts = rollout.policy_sample(pol, env_obs, n_ag, seed=1, step=1)
+    dead = torch.arange(12, device="cuda")[None, :] >= n_ag[:, None]
+    assert bool((acts[dead] == 1).all())
+
+
 def test_invalid_action_masking_of_the_gi_actor(mm):
     """Model_gi.ActorNetwork (marl/single_agent/Model_gi.py:63-66): logits[action_mask == 0] = -1e8, then log-softmax.
     The env's own action masks (action_masking = True) go straight into the kernel; masked actions are never drawn."""
