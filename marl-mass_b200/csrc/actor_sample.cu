@@ -502,20 +502,22 @@ struct M5 {
     static constexpr int CH1 = H1 / 8;                        // k-chunks (8 halves = 16 bytes) of layer 2
     static constexpr uint32_t A_CHUNK = ROWS * 16;            // one k-chunk of the 128 rows of a tile / of W2's 128 rows
     static constexpr uint32_t W1_CHUNK = H1 * 16;             // one k-chunk of W1's H1 rows
+    static constexpr uint32_t W3_CHUNK = 16 * 16;             // one k-chunk of the output layer's 16 rows (5 logits, the value, 10 zero)
     static constexpr uint32_t A1 = 0;                         // [4 chunks][128] 16 B
     static constexpr uint32_t W1 = A1 + 4 * A_CHUNK;          // [4 chunks][H1]
-    static constexpr uint32_t A2 = W1 + 4 * W1_CHUNK;         // [CH1][128]
+    static constexpr uint32_t A2 = W1 + 4 * W1_CHUNK;         // [CH1][128]: h1, then (first 16 chunks) h2
     static constexpr uint32_t W2 = A2 + CH1 * A_CHUNK;        // [CH1][128]
-    static constexpr uint32_t W3 = W2 + CH1 * A_CHUNK;        // [128 hidden][8] f32: 5 logit columns, the value column, 2 unused
-    static constexpr uint32_t B1 = W3 + AC_HID * 8 * 4;
+    static constexpr uint32_t W3 = W2 + CH1 * A_CHUNK;        // [16 chunks][16]
+    static constexpr uint32_t B1 = W3 + 16 * W3_CHUNK;
     static constexpr uint32_t B2 = B1 + H1 * 4;
     static constexpr uint32_t B3 = B2 + AC_HID * 4;
-    static constexpr uint32_t PART = B3 + 8 * 4;              // [128 rows][8] f32: partial outputs of the upper column half
-    static constexpr uint32_t BAR = PART + ROWS * 8 * 4;      // 2 mbarriers + the TMEM base address
+    static constexpr uint32_t BAR = B3 + 8 * 4;               // 3 mbarriers + the TMEM base address
     static constexpr uint32_t SMEM = BAR + 32;
-    // instruction descriptors, kind::f16: F32 accumulate, fp16 A / B, K-major, M = 128, N = H1 (layer 1) / 128 (layer 2)
+    static constexpr uint32_t D3_COL = 192;                   // TMEM columns: D1 0..H1-1, D2 0..127 (reuses D1's), D3 192..207
+    // instruction descriptors, kind::f16: F32 accumulate, fp16 A / B, K-major, M = 128, N = H1 / 128 / 16
     static constexpr uint32_t IDESC1 = (1u << 4) | ((uint32_t)(H1 >> 3) << 17) | ((128u >> 4) << 24);
     static constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)(AC_HID >> 3) << 17) | ((128u >> 4) << 24);
+    static constexpr uint32_t IDESC3 = (1u << 4) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
 };
 
 __device__ __forceinline__ uint64_t m5_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
@@ -553,12 +555,12 @@ actor_mlp_tcgen05_kernel(const float *__restrict__ obs, const int32_t *__restric
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint4 *a1 = reinterpret_cast<uint4 *>(m5_sm + L::A1), *w1f = reinterpret_cast<uint4 *>(m5_sm + L::W1);
     uint4 *a2 = reinterpret_cast<uint4 *>(m5_sm + L::A2), *w2f = reinterpret_cast<uint4 *>(m5_sm + L::W2);
-    float *w3s = reinterpret_cast<float *>(m5_sm + L::W3), *b1s = reinterpret_cast<float *>(m5_sm + L::B1);
-    float *b2s = reinterpret_cast<float *>(m5_sm + L::B2), *b3s = reinterpret_cast<float *>(m5_sm + L::B3);
-    float *part = reinterpret_cast<float *>(m5_sm + L::PART);
+    uint4 *w3f = reinterpret_cast<uint4 *>(m5_sm + L::W3);
+    float *b1s = reinterpret_cast<float *>(m5_sm + L::B1), *b2s = reinterpret_cast<float *>(m5_sm + L::B2);
+    float *b3s = reinterpret_cast<float *>(m5_sm + L::B3);
     uint64_t *bars = reinterpret_cast<uint64_t *>(m5_sm + L::BAR);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(m5_sm + L::BAR + 16);
-    const uint32_t bar1 = t5_smem(bars), bar2 = t5_smem(bars + 1);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(m5_sm + L::BAR + 24);
+    const uint32_t bar1 = t5_smem(bars), bar2 = t5_smem(bars + 1), bar3 = t5_smem(bars + 2);
 
     // ---- one-time setup: weights in operand layout (fp16), barriers, TMEM ----
     for (int idx = tid; idx < 4 * H1; idx += L::THREADS) {           // W1: [out n][in k], k padded 30 -> 32
@@ -573,9 +575,12 @@ actor_mlp_tcgen05_kernel(const float *__restrict__ obs, const int32_t *__restric
         const float4 lo = *reinterpret_cast<const float4 *>(w2 + n * H1 + 8 * c), hi = *reinterpret_cast<const float4 *>(w2 + n * H1 + 8 * c + 4);
         w2f[idx] = make_uint4(pack_h2(lo.x, lo.y), pack_h2(lo.z, lo.w), pack_h2(hi.x, hi.y), pack_h2(hi.z, hi.w));
     }
-    for (int idx = tid; idx < AC_HID * 8; idx += L::THREADS) {
-        const int h = idx >> 3, k = idx & 7;
-        w3s[idx] = k < AC_OUT ? w3[k * AC_HID + h] : (k == AC_OUT && wv ? wv[h] : 0.f);
+    for (int idx = tid; idx < 16 * 16; idx += L::THREADS) {          // output layer: rows 0..4 logits, 5 the value head, rest zero
+        const int c = idx / 16, n = idx % 16;
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = n < AC_OUT ? w3[n * AC_HID + 8 * c + q] : (n == AC_OUT && wv ? wv[8 * c + q] : 0.f);
+        w3f[idx] = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
     }
     for (int idx = tid; idx < H1; idx += L::THREADS) b1s[idx] = b1[idx];
     for (int idx = tid; idx < AC_HID; idx += L::THREADS) b2s[idx] = b2[idx];
@@ -583,6 +588,7 @@ actor_mlp_tcgen05_kernel(const float *__restrict__ obs, const int32_t *__restric
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar1));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar2));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar3));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -594,7 +600,7 @@ actor_mlp_tcgen05_kernel(const float *__restrict__ obs, const int32_t *__restric
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
-    const uint32_t a1_addr = t5_smem(a1), w1_addr = t5_smem(w1f), a2_addr = t5_smem(a2), w2_addr = t5_smem(w2f);
+    const uint32_t a1_addr = t5_smem(a1), w1_addr = t5_smem(w1f), a2_addr = t5_smem(a2), w2_addr = t5_smem(w2f), w3_addr = t5_smem(w3f);
 
     const int row_in_tile = 32 * (warp & 3) + lane;        // TMEM lane = row of the tile this thread reads
     const int hh = warp >> 2;                              // column half
@@ -659,62 +665,71 @@ actor_mlp_tcgen05_kernel(const float *__restrict__ obs, const int32_t *__restric
         }
         t5_wait(bar2, parity);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- epilogue 2: h2 = relu(D2 + b2); the 128 -> 5 (+ value) output layer as FMAs over this thread's 64 hidden units ----
-        float lg[AC_OUT + 1] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        // ---- epilogue 2: h2 = relu(D2 + b2) -> the first 16 chunks of A2 (MMA2 has finished reading h1) ----
 #pragma unroll 1
         for (int it = 0; it < 4; ++it) {
             const int col = hh * 64 + 16 * it;
             uint32_t v[16];
             m5_ld16(t_lane + (uint32_t)col, v);
+            float h[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float h = fmaxf(__uint_as_float(v[j]) + b2s[col + j], 0.f);
-                const float4 wa = *reinterpret_cast<const float4 *>(w3s + (col + j) * 8);
-                const float2 wb = *reinterpret_cast<const float2 *>(w3s + (col + j) * 8 + 4);
-                lg[0] = fmaf(h, wa.x, lg[0]); lg[1] = fmaf(h, wa.y, lg[1]); lg[2] = fmaf(h, wa.z, lg[2]);
-                lg[3] = fmaf(h, wa.w, lg[3]); lg[4] = fmaf(h, wb.x, lg[4]); lg[5] = fmaf(h, wb.y, lg[5]);
-            }
+            for (int q = 0; q < 16; ++q) h[q] = fmaxf(__uint_as_float(v[q]) + b2s[col + q], 0.f);
+            a2[(col / 8) * L::ROWS + row_in_tile] = make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
+            a2[(col / 8 + 1) * L::ROWS + row_in_tile] = make_uint4(pack_h2(h[8], h[9]), pack_h2(h[10], h[11]), pack_h2(h[12], h[13]), pack_h2(h[14], h[15]));
         }
-        if (hh == 1) {
-#pragma unroll
-            for (int k = 0; k <= AC_OUT; ++k) part[row_in_tile * 8 + k] = lg[k];
-        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
+        // ---- output layer 128 -> 5 (+ value) as a third MMA (N = 16): D3 = h2 * W3^T ----
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < AC_HID / 16; ++j)
+                m5_mma(tmem + L::D3_COL, m5_desc(a2_addr + j * 2 * L::A_CHUNK, L::A_CHUNK), m5_desc(w3_addr + j * 2 * L::W3_CHUNK, L::W3_CHUNK),
+                       L::IDESC3, j > 0);
+            t5_commit(bar3);
+        }
+        t5_wait(bar3, parity);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int64_t row = tile * L::ROWS + row_in_tile;
-        if (hh == 0 && row < n_rows) {
-            float l[AC_OUT];
+        if (hh == 0) {
+            uint32_t v[16];
+            m5_ld16(t_lane + L::D3_COL, v);
+            if (row < n_rows) {
+                float l[AC_OUT];
 #pragma unroll
-            for (int k = 0; k < AC_OUT; ++k) l[k] = lg[k] + part[row_in_tile * 8 + k] + b3s[k];
-            if (values) values[row] = lg[AC_OUT] + part[row_in_tile * 8 + AC_OUT] + b3s[AC_OUT];
-            apply_action_mask(l, mask_bits, row);
-            float m = l[0];
+                for (int k = 0; k < AC_OUT; ++k) l[k] = __uint_as_float(v[k]) + b3s[k];
+                if (values) values[row] = __uint_as_float(v[AC_OUT]) + b3s[AC_OUT];
+                apply_action_mask(l, mask_bits, row);
+                float m = l[0];
 #pragma unroll
-            for (int k = 1; k < AC_OUT; ++k) m = fmaxf(m, l[k]);
-            float e[AC_OUT], S = 0.f;
+                for (int k = 1; k < AC_OUT; ++k) m = fmaxf(m, l[k]);
+                float e[AC_OUT], S = 0.f;
 #pragma unroll
-            for (int k = 0; k < AC_OUT; ++k) { e[k] = __expf(l[k] - m); S += e[k]; }
-            const float logS = __logf(S);
-            const float u = (float)(philox_row(seed, step, (uint64_t)row) >> 8) * (1.0f / 16777216.0f);
-            const float target = u * S;
-            int a = AC_OUT - 1;
-            float c = 0.f;
-            bool found = false;
+                for (int k = 0; k < AC_OUT; ++k) { e[k] = __expf(l[k] - m); S += e[k]; }
+                const float logS = __logf(S);
+                const float u = (float)(philox_row(seed, step, (uint64_t)row) >> 8) * (1.0f / 16777216.0f);
+                const float target = u * S;
+                int a = AC_OUT - 1;
+                float c = 0.f;
+                bool found = false;
 #pragma unroll
-            for (int k = 0; k < AC_OUT; ++k) {
-                c += e[k];
-                if (!found && target < c) { a = k; found = true; }
-            }
-            bool live = true;
-            if (n_agents) live = (int)(row % MAXV) < n_agents[row / MAXV];
-            actions[row] = (int8_t)(live ? a : 1);
-            if (logp_sel) logp_sel[row] = l[a] - m - logS;
-            if (logp_all) {
+                for (int k = 0; k < AC_OUT; ++k) {
+                    c += e[k];
+                    if (!found && target < c) { a = k; found = true; }
+                }
+                bool live = true;
+                if (n_agents) live = (int)(row % MAXV) < n_agents[row / MAXV];
+                actions[row] = (int8_t)(live ? a : 1);
+                if (logp_sel) logp_sel[row] = l[a] - m - logS;
+                if (logp_all) {
 #pragma unroll
-                for (int k = 0; k < AC_OUT; ++k) logp_all[row * AC_OUT + k] = l[k] - m - logS;
+                    for (int k = 0; k < AC_OUT; ++k) logp_all[row * AC_OUT + k] = l[k] - m - logS;
+                }
             }
         }
-        __syncthreads();   // `part` and D (TMEM columns) are reused by the next tile
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();   // TMEM columns and A2 are reused by the next tile
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

@@ -513,10 +513,12 @@ int mm_step_host_packed(mm_env *env, const int8_t *actions, int auto_reset, cons
     if (n_chunks < 1) n_chunks = 1;
     if (n_chunks > MAX_HOST_CHUNKS) n_chunks = MAX_HOST_CHUNKS;
     const int chunk = ((E + n_chunks - 1) / n_chunks + 767) / 768 * 768;
-    // Same software pipeline as mm_step_host_ragged.  The packed rows of the batch are dense from the first env to the
-    // last, so a chunk's scan starts from the totals of the chunk before it (a device-side chain: base[c] -> base[c+1],
-    // one event wait between neighbouring chunks' scans); the host learns the totals with the chunk's event and copies
-    // exactly the packed bytes.
+    // Chunks of ~64 Ki envs round-robin on four compute streams; ALL of a step's compute is enqueued up front (a chunk
+    // touches only its own envs and its own range of the packed buffers), so the GPU never waits for the host.  The
+    // packed rows of the batch are dense from the first env to the last: a chunk's scan starts from the totals of the
+    // chunk before it (a device-side chain base[c] -> base[c+1], one event wait between neighbouring chunks' scans).
+    // The host learns a chunk's totals with the chunk's event and then issues exactly-sized copies on a copy stream, in
+    // chunk order, while later chunks compute.
     auto enqueue_compute = [&](int c) -> int {
         const int off = c * chunk;
         const int count = E - off < chunk ? E - off : chunk;
@@ -539,8 +541,10 @@ int mm_step_host_packed(mm_env *env, const int8_t *actions, int auto_reset, cons
     auto enqueue_copies = [&](int c) -> int {
         const int off = c * chunk;
         const int count = E - off < chunk ? E - off : chunk;
-        cudaStream_t s = env->streams[c % n_str];
+        cudaStream_t s = env->streams[n_str + c % n_str];      // copy streams: the compute streams stay busy
         CUDA_OK(cudaEventSynchronize(env->chunk_done[c]));
+        static const bool nocopy = getenv("MM_PACKED_NOCOPY") != nullptr;     // timing experiment: compute + packing only
+        if (nocopy) return 0;
         const int64_t v0 = env->chunk_base_host[2 * c], v1 = env->chunk_base_host[2 * (c + 1)];
         const int64_t a0 = env->chunk_base_host[2 * c + 1], a1 = env->chunk_base_host[2 * (c + 1) + 1];
         if (v1 > v0)
@@ -561,15 +565,12 @@ int mm_step_host_packed(mm_env *env, const int8_t *actions, int auto_reset, cons
     };
     int used = 0;
     while (used < n_chunks && used * chunk < E) ++used;
-    if (int rc = order_after_caller(env, n_str)) return rc;
-    for (int c = 0; c < used && c < n_str; ++c)
+    if (int rc = order_after_caller(env, 2 * n_str)) return rc;
+    for (int c = 0; c < used; ++c)
         if (int rc = enqueue_compute(c)) return rc;
-    for (int c = 0; c < used; ++c) {
+    for (int c = 0; c < used; ++c)
         if (int rc = enqueue_copies(c)) return rc;
-        if (c + n_str < used)
-            if (int rc = enqueue_compute(c + n_str)) return rc;
-    }
-    for (int c = 0; c < n_str; ++c) CUDA_OK(cudaStreamSynchronize(env->streams[c]));
+    for (int c = 0; c < 2 * n_str; ++c) CUDA_OK(cudaStreamSynchronize(env->streams[c]));
     CUDA_OK(cudaGetLastError());
     return 0;
 }
