@@ -46,7 +46,7 @@ enum { MM_ACT_LEAD = 1, MM_ACT_UPPER = 2, MM_ACT_LOWER = 4, MM_ACT_ADJ = 8, MM_A
  * signature; mm_abi_version() returns the value the library was built with, and mm_create / mm_set_config reject a
  * config whose struct_size field is not sizeof(mm_config) (a binding built against another revision of the header
  * fails loudly instead of handing the library garbage). */
-#define MM_ABI_VERSION 5
+#define MM_ABI_VERSION 6
 int mm_abi_version(void);
 
 typedef struct {
@@ -227,11 +227,14 @@ int mm_actor_sample(const float *obs, const int32_t *n_agents, int64_t n_rows, c
  * one 30 -> 160 layer whose weight w1 [160][30] is zero outside the blocks (the caller scatters them; b1 = the three
  * biases concatenated), w2 = fc2.weight [128][160], w3 / b3 = actor_linear.  value_w [128] / value_b [1] (nullable) =
  * critic_linear: values [n_rows] receives V(s) from the same hidden activations (the bootstrap value of
- * mappo_gi.py:396-404).  Everything else as in mm_actor_sample. */
+ * mappo_gi.py:396-404).  Rollout-buffer appends of MAPPO.interact (mappo.py:117-131), fused: obs_copy (nullable)
+ * [n_rows][30] receives the rows the actions were drawn from (point it at slot t of the state buffer), live_out (nullable)
+ * [n_rows] u8 = 1 where the row belongs to an agent that exists (needs n_agents), and `actions` can be slot t of the
+ * action buffer.  Everything else as in mm_actor_sample. */
 int mm_actor_sample_mlp(const float *obs, const int32_t *n_agents, int64_t n_rows, int h1, const float *w1, const float *b1,
                         const float *w2, const float *b2, const float *w3, const float *b3, const float *value_w,
                         const float *value_b, uint64_t seed, uint64_t step, const uint8_t *action_mask, int8_t *actions,
-                        float *logp_all, float *logp_sel, float *values, void *stream);
+                        float *logp_all, float *logp_sel, float *values, float *obs_copy, uint8_t *live_out, void *stream);
 
 /* Implementation switch of mm_actor_sample (process-wide): 0 = tcgen05 with fp16 operands, two CTAs per SM (default,
  * the kernel of mm_actor_sample_mlp); 1 = the warp-level mma.sync TF32 kernel kept as an independent cross-check;

@@ -28,7 +28,7 @@ _PU8 = C.POINTER(C.c_uint8)
 _PI8 = C.POINTER(C.c_int8)
 
 
-ABI_VERSION = 5           # MM_ABI_VERSION of the header this binding was written against
+ABI_VERSION = 6           # MM_ABI_VERSION of the header this binding was written against
 
 
 class MMConfig(C.Structure):
@@ -119,7 +119,7 @@ def lib():
     L.mm_actor_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 6 + [C.c_uint64, C.c_uint64] + \
                                  [C.c_void_p] * 5
     L.mm_actor_sample_mlp.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int] + [C.c_void_p] * 8 + [C.c_uint64, C.c_uint64] + \
-                                     [C.c_void_p] * 6
+                                     [C.c_void_p] * 8
     L.mm_set_actor_impl.argtypes = [C.c_int]
     L.mm_set_step_variant.argtypes = [C.c_int]
     L.mm_step_build.argtypes = [h]

@@ -487,14 +487,18 @@ actor_sample_tcgen05_kernel(const float *__restrict__ obs, const int32_t *__rest
 // halves every shared-memory operand (kind::f16: fp16 has TF32's 10-bit mantissa; observations live in [-1, 1], the
 // hidden activations of these networks stay far below 65 504) so that TWO CTAs fit an SM (<= 108 KB each, 256 TMEM
 // columns each): while one CTA's threads run an epilogue the other CTA's MMAs and loads proceed - the overlap of a
-// software pipeline without warp specialisation.  MMAs are K = 16 (half as many instructions).
+// software pipeline without warp specialisation.  MMAs are K = 16 (half as many instructions).  The 128 -> 5 output
+// layer (+ the value column) is a third MMA (N = 16) on h2 staged as fp16: as per-thread FMAs over shared-memory weights
+// it was ~55 % of the kernel's instructions (ncu: 55 M warp-instructions per launch, issue slots 46 % busy).
+// 786 432 rows: TF32 kernel 0.167 ms -> 0.115 (fp16, two CTAs / SM) -> 0.093 (third MMA).
 //   H1 = 128: MAPPO ActorNetwork 30-128-128-5 (Model_common.py:5-23).
 //   H1 = 160: MAPPO_GI ActorCriticNetwork with state_split (Model_gi.py:137-220): its three first-layer blocks
 //             (5 -> 32, 10 -> 64, 10 -> 64 over fixed column lists) are ONE 30 -> 160 layer whose weight matrix is zero
 //             outside the blocks; the host scatters fc11 / fc12 / fc13 into it (rollout.py).  The optional sixth output
 //             column is critic_linear (the state value V(s), mappo_gi.py:396-404).
 // CTA = 256 threads: warp w reads TMEM lane quarter w % 4 (hardware rule) and column half w / 4.  D2 reuses D1's
-// columns (D1 is dead once epilogue 1 has been read and the CTA has synchronised).
+// columns (D1 is dead once epilogue 1 has been read and the CTA has synchronised), h2 reuses h1's shared memory, D3 sits
+// in columns 192..207; the final epilogue (log-softmax, draw) runs in the 128 threads of column half 0, one row each.
 template <int H1>
 struct M5 {
     static constexpr int THREADS = 256;
@@ -549,7 +553,8 @@ actor_mlp_tcgen05_kernel(const float *__restrict__ obs, const int32_t *__restric
                          const float *__restrict__ b2, const float *__restrict__ w3, const float *__restrict__ b3,
                          const float *__restrict__ wv, const float *__restrict__ bv, uint64_t seed, uint64_t step,
                          const uint8_t *__restrict__ mask_bits, int8_t *__restrict__ actions, float *__restrict__ logp_all,
-                         float *__restrict__ logp_sel, float *__restrict__ values) {
+                         float *__restrict__ logp_sel, float *__restrict__ values, float *__restrict__ obs_copy,
+                         uint8_t *__restrict__ live_out) {
     using L = M5<H1>;
     extern __shared__ __align__(128) uint8_t m5_sm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -617,6 +622,9 @@ actor_mlp_tcgen05_kernel(const float *__restrict__ obs, const int32_t *__restric
         for (int q = 0; q < 8; ++q) {
             const int f2 = 4 * st_c0 + q;                  // float2 index inside the row: 15 hold data
             pre[q] = (ok && f2 < AC_IN / 2) ? __ldg(src + f2) : make_float2(0.f, 0.f);
+            // rollout buffer (MAPPO.interact appends the state it acted on, mappo.py:117-131): the rows pass through
+            // this thread anyway
+            if (obs_copy && ok && f2 < AC_IN / 2) __stcs(reinterpret_cast<float2 *>(obs_copy + row * AC_IN) + f2, pre[q]);
         }
     };
     fetch(blockIdx.x);
@@ -721,6 +729,7 @@ actor_mlp_tcgen05_kernel(const float *__restrict__ obs, const int32_t *__restric
                 bool live = true;
                 if (n_agents) live = (int)(row % MAXV) < n_agents[row / MAXV];
                 actions[row] = (int8_t)(live ? a : 1);
+                if (live_out) live_out[row] = live ? 1 : 0;
                 if (logp_sel) logp_sel[row] = l[a] - m - logS;
                 if (logp_all) {
 #pragma unroll
@@ -740,7 +749,7 @@ template <int H1>
 static int launch_actor_mlp_t(const float *obs, const int32_t *n_agents, int64_t n_rows, const float *w1, const float *b1,
                               const float *w2, const float *b2, const float *w3, const float *b3, const float *wv, const float *bv,
                               uint64_t seed, uint64_t step, const uint8_t *mask_bits, int8_t *actions, float *logp_all,
-                              float *logp_sel, float *values, void *stream) {
+                              float *logp_sel, float *values, float *obs_copy, uint8_t *live_out, void *stream) {
     static bool ready[MM_MAX_DEVICES] = {};
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MM_MAX_DEVICES) return 1;
@@ -752,21 +761,22 @@ static int launch_actor_mlp_t(const float *obs, const int32_t *n_agents, int64_t
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t tiles = (n_rows + 127) / 128, ctas = tiles < 2 * sms ? tiles : 2 * sms;   // persistent: two CTAs per SM
     actor_mlp_tcgen05_kernel<H1><<<(unsigned)ctas, 256, M5<H1>::SMEM, (cudaStream_t)stream>>>(
-        obs, n_agents, n_rows, w1, b1, w2, b2, w3, b3, wv, bv, seed, step, mask_bits, actions, logp_all, logp_sel, values);
+        obs, n_agents, n_rows, w1, b1, w2, b2, w3, b3, wv, bv, seed, step, mask_bits, actions, logp_all, logp_sel, values, obs_copy,
+        live_out);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
 int launch_actor_mlp(const float *obs, const int32_t *n_agents, int64_t n_rows, int h1, const float *w1, const float *b1,
                      const float *w2, const float *b2, const float *w3, const float *b3, const float *wv, const float *bv,
                      uint64_t seed, uint64_t step, const uint8_t *mask_bits, int8_t *actions, float *logp_all, float *logp_sel,
-                     float *values, void *stream) {
+                     float *values, float *obs_copy, uint8_t *live_out, void *stream) {
     if (n_rows <= 0) return 0;
     if (h1 == 128)
         return launch_actor_mlp_t<128>(obs, n_agents, n_rows, w1, b1, w2, b2, w3, b3, wv, bv, seed, step, mask_bits, actions, logp_all,
-                                       logp_sel, values, stream);
+                                       logp_sel, values, obs_copy, live_out, stream);
     if (h1 == 160)
         return launch_actor_mlp_t<160>(obs, n_agents, n_rows, w1, b1, w2, b2, w3, b3, wv, bv, seed, step, mask_bits, actions, logp_all,
-                                       logp_sel, values, stream);
+                                       logp_sel, values, obs_copy, live_out, stream);
     return 2;
 }
 
@@ -820,7 +830,7 @@ int launch_actor_sample(const float *obs, const int32_t *n_agents, int64_t n_row
     if (g_actor_impl < 0) { const char *e = getenv("MM_ACTOR_IMPL"); g_actor_impl = (e && e[0] == 'm') ? 1 : ((e && e[0] == 't') ? 2 : 0); }
     if (g_actor_impl == 0)
         return launch_actor_mlp(obs, n_agents, n_rows, 128, w1, b1, w2, b2, w3, b3, nullptr, nullptr, seed, step, mask_bits, actions,
-                                logp_all, logp_sel, nullptr, stream);
+                                logp_all, logp_sel, nullptr, nullptr, nullptr, stream);
     if (g_actor_impl == 2) {
         static bool t5_attr = false;
         if (!t5_attr) {

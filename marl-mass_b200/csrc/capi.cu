@@ -35,7 +35,7 @@ int fail(mm_status code, const char *what, cudaError_t ce = cudaSuccess) {
     } while (0)
 
 constexpr int MAX_CHUNKS = 8;
-constexpr int MAX_HOST_CHUNKS = 64;   // chunks of one mm_step_host_ragged call
+constexpr int MAX_HOST_CHUNKS = 64;   // chunks of one mm_step_host_ragged / _packed call
 constexpr int HOST_F64 = 17, HOST_I32 = 11, HOST_ENV = 5;
 
 }  // namespace
@@ -63,7 +63,7 @@ struct mm_env {
     uint16_t *nbr_packed = nullptr;
     int32_t *voff = nullptr, *aoff = nullptr;
     uint8_t *n_veh_u8 = nullptr, *n_agents_u8 = nullptr;
-    int64_t *chunk_base_dev = nullptr, *chunk_base_host = nullptr;
+    int64_t *chunk_base_dev = nullptr, *chunk_base_host = nullptr, *chunk_base_host_dev = nullptr;
     cudaEvent_t scan_done[MAX_HOST_CHUNKS]{};
     bool packed_ready = false;
     size_t stats_rows = 0;
@@ -135,9 +135,12 @@ int reset_stats(mm_env *env) {
     return 0;
 }
 
-// Envs per chunk of the host paths: 64 Ki for large batches; a mid-size batch is still cut in 4 chunks (>= 16 Ki envs),
-// one per stream, so that its device-to-host copies overlap the compute of the following chunks instead of trailing a
-// single launch (8 smaller chunks were measured too: the extra launches and copies cost more than the overlap gains).
+// Envs per chunk of the host paths.  Large batches: ONE WAVE of the step kernel's default build - 3 CTAs of 128 envs per
+// SM, 56 832 envs on a 148-SM B200 - rounded to the 768-env granule every tile size divides.  Measured on the packed
+// path at 2^20 envs (profiles/r2_k_e2e_chunks.txt): 56 832 -> 11.0 ms per step, 65 536 (1.15 waves) 11.4, 75 264 (one wave
+// of the 4-CTA build) 11.8, 113 664 -> 12.8, 150 528 -> 14.0 against 8.7 ms for the un-chunked device-resident step.  A
+// mid-size batch is still cut in 4 chunks (>= 16 Ki envs), one per stream, so that its device-to-host copies overlap the
+// compute of the following chunks instead of trailing a single launch.
 int host_chunk_target(int n_envs) {
     static const int forced = [] {
         const char *s = getenv("MM_HOST_CHUNK");
@@ -145,9 +148,13 @@ int host_chunk_target(int n_envs) {
         return v > 0 ? v : 0;
     }();
     if (forced) return forced;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int wave = sms * 3 * TILE / 768 * 768;
     int t = (n_envs + 3) / 4;     // one chunk per stream
     if (t < 16384) t = 16384;
-    if (t > 65536) t = 65536;
+    if (t > wave) t = wave;
     return t;
 }
 
@@ -497,8 +504,12 @@ int mm_step_host_packed(mm_env *env, const int8_t *actions, int auto_reset, cons
         if (rc) return rc;
         if (!env->chunk_base_host) {
             void *p = nullptr;
-            CUDA_OK(cudaHostAlloc(&p, (size_t)(MAX_HOST_CHUNKS + 1) * 2 * sizeof(int64_t), cudaHostAllocDefault));
+            // mapped: the scan kernel writes a chunk's totals here itself.  (A small device-to-host memcpy per chunk on
+            // the compute streams sits in the copy engine's queue until its chunk has run - and every data copy issued
+            // later queues behind it: measured, the packed rows then left only after ALL compute had finished.)
+            CUDA_OK(cudaHostAlloc(&p, (size_t)(MAX_HOST_CHUNKS + 1) * 2 * sizeof(int64_t), cudaHostAllocMapped));
             env->chunk_base_host = static_cast<int64_t *>(p);
+            CUDA_OK(cudaHostGetDevicePointer((void **)&env->chunk_base_host_dev, p, 0));
             env->chunk_base_host[0] = env->chunk_base_host[1] = 0;
         }
         for (int c = 0; c < MAX_HOST_CHUNKS; ++c) {
@@ -529,12 +540,10 @@ int mm_step_host_packed(mm_env *env, const int8_t *actions, int auto_reset, cons
         if (c > 0) CUDA_OK(cudaStreamWaitEvent(s, env->scan_done[c - 1], 0));
         launch_packed_pack(env->st.einfo + off, env->out.n_agents + off, env->out.veh + (size_t)off * MAXV * 5,
                            env->out.nbr + (size_t)off * MAXV, count, env->chunk_base_dev + 2 * c, env->chunk_base_dev + 2 * (c + 1),
-                           env->voff + off, env->aoff + off, env->veh_packed, env->nbr_packed, env->n_veh_u8 + off,
+                           env->chunk_base_host_dev + 2 * (c + 1), env->voff + off, env->aoff + off, env->veh_packed, env->nbr_packed, env->n_veh_u8 + off,
                            env->n_agents_u8 + off, s);
         env->launches += 2;
         CUDA_OK(cudaEventRecord(env->scan_done[c], s));
-        CUDA_OK(cudaMemcpyAsync(env->chunk_base_host + 2 * (c + 1), env->chunk_base_dev + 2 * (c + 1), 2 * sizeof(int64_t),
-                                cudaMemcpyDeviceToHost, s));
         CUDA_OK(cudaEventRecord(env->chunk_done[c], s));
         return 0;
     };
@@ -771,14 +780,14 @@ int mm_actor_sample(const float *obs, const int32_t *n_agents, int64_t n_rows, c
 int mm_actor_sample_mlp(const float *obs, const int32_t *n_agents, int64_t n_rows, int h1, const float *w1, const float *b1,
                         const float *w2, const float *b2, const float *w3, const float *b3, const float *value_w,
                         const float *value_b, uint64_t seed, uint64_t step, const uint8_t *action_mask, int8_t *actions,
-                        float *logp_all, float *logp_sel, float *values, void *stream) {
+                        float *logp_all, float *logp_sel, float *values, float *obs_copy, uint8_t *live_out, void *stream) {
     if (!obs || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !actions) return fail(MM_ERR_ARG, "null argument");
     if (h1 != 128 && h1 != 160) return fail(MM_ERR_ARG, "h1 must be 128 (ActorNetwork) or 160 (ActorCriticNetwork, state_split)");
     if (n_rows < 0) return fail(MM_ERR_ARG, "n_rows must be >= 0");
     if (n_agents && n_rows % MAXV != 0) return fail(MM_ERR_ARG, "n_rows must be a multiple of MM_MAXV when n_agents is given");
     if (values && (!value_w || !value_b)) return fail(MM_ERR_ARG, "values needs value_w and value_b");
     if (launch_actor_mlp(obs, n_agents, n_rows, h1, w1, b1, w2, b2, w3, b3, value_w, value_b, seed, step, action_mask, actions,
-                         logp_all, logp_sel, values, stream))
+                         logp_all, logp_sel, values, obs_copy, live_out, stream))
         return fail(MM_ERR_CUDA, cudaGetErrorString(cudaGetLastError()));
     return 0;
 }

@@ -297,7 +297,8 @@ __global__ void __launch_bounds__(OTHREADS, MM_OUT_MIN_BLOCKS) outputs_kernel(co
 // dense over the whole batch, so the host derives them from the two count arrays alone.
 __global__ void __launch_bounds__(1024) packed_offsets_kernel(const uint32_t *__restrict__ einfo, const int32_t *__restrict__ n_agents,
                                                               int count, const int64_t *__restrict__ base_in,
-                                                              int64_t *__restrict__ base_out, int32_t *__restrict__ voff,
+                                                              int64_t *__restrict__ base_out, int64_t *__restrict__ base_out_host,
+                                                              int32_t *__restrict__ voff,
                                                               int32_t *__restrict__ aoff, uint8_t *__restrict__ n_veh_u8,
                                                               uint8_t *__restrict__ n_agents_u8) {
     __shared__ int wv[32], wa[32];
@@ -325,9 +326,13 @@ __global__ void __launch_bounds__(1024) packed_offsets_kernel(const uint32_t *__
         }
         wv[lane] = xa - a;
         wa[lane] = xb - b;
-        if (lane == 31) {     // totals of this chunk, chained
-            base_out[0] = base_in[0] + xa;
-            base_out[1] = base_in[1] + xb;
+        if (lane == 31) {     // totals of this chunk, chained; the host's copy goes straight to mapped pinned memory
+            const int64_t tv = base_in[0] + xa, ta = base_in[1] + xb;
+            base_out[0] = tv;
+            base_out[1] = ta;
+            base_out_host[0] = tv;
+            base_out_host[1] = ta;
+            __threadfence_system();
         }
     }
     __syncthreads();
@@ -359,10 +364,11 @@ __global__ void __launch_bounds__(256) packed_copy_kernel(const float *__restric
 }
 
 void launch_packed_pack_impl(const uint32_t *einfo, const int32_t *n_agents, const float *veh, const uint16_t *nbr, int count,
-                             const int64_t *base_in, int64_t *base_out, int32_t *voff, int32_t *aoff, float *veh_packed,
-                             uint16_t *nbr_packed, uint8_t *n_veh_u8, uint8_t *n_agents_u8, void *stream) {
+                             const int64_t *base_in, int64_t *base_out, int64_t *base_out_host, int32_t *voff, int32_t *aoff,
+                             float *veh_packed, uint16_t *nbr_packed, uint8_t *n_veh_u8, uint8_t *n_agents_u8, void *stream) {
     if (count <= 0) return;
-    packed_offsets_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(einfo, n_agents, count, base_in, base_out, voff, aoff, n_veh_u8, n_agents_u8);
+    packed_offsets_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(einfo, n_agents, count, base_in, base_out, base_out_host, voff, aoff,
+                                                                n_veh_u8, n_agents_u8);
     packed_copy_kernel<<<(count + 7) / 8, 256, 0, (cudaStream_t)stream>>>(veh, nbr, n_veh_u8, n_agents_u8, voff, aoff, count, base_in,
                                                                         veh_packed, nbr_packed);
 }
@@ -388,9 +394,9 @@ void launch_outputs_impl(const StepParams &p, bool with_rewards, void *stream) {
 namespace mm {
 void launch_outputs(const StepParams &p, bool with_rewards, void *stream) { mmo::launch_outputs_impl(p, with_rewards, stream); }
 void launch_packed_pack(const uint32_t *einfo, const int32_t *n_agents, const float *veh, const uint16_t *nbr, int count,
-                        const int64_t *base_in, int64_t *base_out, int32_t *voff, int32_t *aoff, float *veh_packed,
-                        uint16_t *nbr_packed, uint8_t *n_veh_u8, uint8_t *n_agents_u8, void *stream) {
-    mmo::launch_packed_pack_impl(einfo, n_agents, veh, nbr, count, base_in, base_out, voff, aoff, veh_packed, nbr_packed, n_veh_u8,
-                                 n_agents_u8, stream);
+                        const int64_t *base_in, int64_t *base_out, int64_t *base_out_host, int32_t *voff, int32_t *aoff,
+                        float *veh_packed, uint16_t *nbr_packed, uint8_t *n_veh_u8, uint8_t *n_agents_u8, void *stream) {
+    mmo::launch_packed_pack_impl(einfo, n_agents, veh, nbr, count, base_in, base_out, base_out_host, voff, aoff, veh_packed, nbr_packed,
+                                 n_veh_u8, n_agents_u8, stream);
 }
 }  // namespace mm

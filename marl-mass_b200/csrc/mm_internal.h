@@ -134,11 +134,12 @@ void launch_ragged_pack(const float *obs, const int32_t *n_agents, int count, in
                         int64_t *chunk_rows_dev, float *rows_stage, void *stream);
 
 // mm_step_host_packed: exclusive scans of n_veh / n_agents over a chunk of envs (chained to the previous chunk's totals
-// through base_in -> base_out, two int64 each: vehicles, agents) and the ragged copy of the chunk's vehicle rows and
+// through base_in -> base_out, two int64 each: vehicles, agents; base_out_host = the same totals written to mapped pinned
+// host memory, so that no device-to-host copy of them queues in front of the data copies) and the ragged copy of the chunk's vehicle rows and
 // neighbour words to their packed place
 void launch_packed_pack(const uint32_t *einfo, const int32_t *n_agents, const float *veh, const uint16_t *nbr, int count,
-                        const int64_t *base_in, int64_t *base_out, int32_t *voff, int32_t *aoff, float *veh_packed,
-                        uint16_t *nbr_packed, uint8_t *n_veh_u8, uint8_t *n_agents_u8, void *stream);
+                        const int64_t *base_in, int64_t *base_out, int64_t *base_out_host, int32_t *voff, int32_t *aoff,
+                        float *veh_packed, uint16_t *nbr_packed, uint8_t *n_veh_u8, uint8_t *n_agents_u8, void *stream);
 
 // caller-side kernels (actor_sample.cu)
 int launch_actor_sample(const float *obs, const int32_t *n_agents, int64_t n_rows, const float *w1, const float *b1,
@@ -149,7 +150,7 @@ void set_actor_impl(int impl);
 int launch_actor_mlp(const float *obs, const int32_t *n_agents, int64_t n_rows, int h1, const float *w1, const float *b1,
                      const float *w2, const float *b2, const float *w3, const float *b3, const float *wv, const float *bv,
                      uint64_t seed, uint64_t step, const uint8_t *mask_bits, int8_t *actions, float *logp_all, float *logp_sel,
-                     float *values, void *stream);
+                     float *values, float *obs_copy, uint8_t *live_out, void *stream);
 int launch_discounted_returns(const float *rewards, const uint8_t *dones, const float *final_value, float gamma, int T,
                               int64_t n_cols, int cols_per_env, float *out, void *stream);
 

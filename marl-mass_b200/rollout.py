@@ -199,7 +199,8 @@ def _split_first_layer(policy):
     return w, b
 
 
-def policy_sample(policy, obs, n_agents=None, seed=0, step=0, want_logp=False, action_mask=None, want_value=False):
+def policy_sample(policy, obs, n_agents=None, seed=0, step=0, want_logp=False, action_mask=None, want_value=False,
+                  out_actions=None, obs_copy=None, live_out=None):
     """Fused forward + exploration draw of the MAPPO_GI shared network (mm_actor_sample_mlp with h1 = 160): `policy` is
     an ActorCriticNetwork with state_split and hidden size 128; -> actions int8 [...] (+ log-probabilities [..., 5] with
     want_logp, + V(s) [...] from critic_linear with want_value).  Other arguments as for `actor_sample`."""
@@ -212,7 +213,9 @@ def policy_sample(policy, obs, n_agents=None, seed=0, step=0, want_logp=False, a
     w = [policy.fc2.weight, policy.fc2.bias, policy.actor_linear.weight, policy.actor_linear.bias,
          policy.critic_linear.weight, policy.critic_linear.bias]
     w = [t.detach().contiguous().float() for t in w]
-    actions = torch.empty(obs.shape[:-1], dtype=torch.int8, device=obs.device)
+    actions = torch.empty(obs.shape[:-1], dtype=torch.int8, device=obs.device) if out_actions is None else out_actions
+    assert actions.dtype == torch.int8 and actions.is_contiguous() and actions.numel() == rows
+    _check_record_slots(rows, obs_copy, live_out)
     logp = torch.empty(obs.shape[:-1] + (NA,), dtype=torch.float32, device=obs.device) if want_logp else None
     values = torch.empty(obs.shape[:-1], dtype=torch.float32, device=obs.device) if want_value else None
     if n_agents is not None:
@@ -223,35 +226,54 @@ def policy_sample(policy, obs, n_agents=None, seed=0, step=0, want_logp=False, a
     _lib.check(_lib.lib().mm_actor_sample_mlp(_ptr(obs), _ptr(n_agents), C.c_int64(rows), 160, _ptr(w1), _ptr(b1), _ptr(w[0]),
                                               _ptr(w[1]), _ptr(w[2]), _ptr(w[3]), _ptr(w[4]), _ptr(w[5]), C.c_uint64(seed),
                                               C.c_uint64(step), _ptr(action_mask), _ptr(actions), _ptr(logp), _ptr(None),
-                                              _ptr(values), _stream()))
+                                              _ptr(values), _ptr(obs_copy), _ptr(live_out), _stream()))
     out = (actions,) + ((logp,) if want_logp else ()) + ((values,) if want_value else ())
     return out if len(out) > 1 else actions
 
 
-def actor_sample(actor, obs, n_agents=None, seed=0, step=0, want_logp=False, action_mask=None):
+def actor_sample(actor, obs, n_agents=None, seed=0, step=0, want_logp=False, action_mask=None, out_actions=None,
+                 obs_copy=None, live_out=None):
     """Fused actor forward + exploration draw (mm_actor_sample): obs [..., 30] f32 cuda -> actions int8 [...].
 
     `actor` is an ActorNetwork (or any module with fc1/fc2/fc3 Linear layers 30-128-128-5); its parameters are read
     in place.  n_agents [E] int32 marks the live rows when obs is the env's [E, 12, 30] buffer.  With want_logp the
     log-probabilities of all five actions are returned too ([..., 5] f32).  action_mask: uint8 bit masks, one per row
-    (`env.buffers()["action_mask"]`, bit k = action k available) for the MAPPO_GI actor's invalid-action masking."""
+    (`env.buffers()["action_mask"]`, bit k = action k available) for the MAPPO_GI actor's invalid-action masking.
+    Rollout-buffer appends fused into the same launch (MAPPO.interact, mappo.py:117-131): out_actions (int8, slot t of
+    the action buffer) receives the actions, obs_copy (f32, slot t of the state buffer) the rows they were drawn from,
+    live_out (uint8) 1 where the row's agent exists."""
     rows = obs.numel() // NS
     obs = obs.contiguous()
     assert obs.is_cuda and obs.dtype == torch.float32
     w = [actor.fc1.weight, actor.fc1.bias, actor.fc2.weight, actor.fc2.bias, actor.fc3.weight, actor.fc3.bias]
     assert tuple(w[0].shape) == (128, NS) and tuple(w[2].shape) == (128, 128) and tuple(w[4].shape) == (NA, 128)
     w = [t.detach().contiguous().float() for t in w]
-    actions = torch.empty(obs.shape[:-1], dtype=torch.int8, device=obs.device)
+    actions = torch.empty(obs.shape[:-1], dtype=torch.int8, device=obs.device) if out_actions is None else out_actions
+    assert actions.dtype == torch.int8 and actions.is_contiguous() and actions.numel() == rows
     logp = torch.empty(obs.shape[:-1] + (NA,), dtype=torch.float32, device=obs.device) if want_logp else None
     if n_agents is not None:
         assert n_agents.dtype == torch.int32 and n_agents.is_cuda and n_agents.numel() * MAXV == rows
     if action_mask is not None:
         assert action_mask.dtype == torch.uint8 and action_mask.is_cuda and action_mask.numel() == rows
         action_mask = action_mask.contiguous()
-    _lib.check(_lib.lib().mm_actor_sample(_ptr(obs), _ptr(n_agents), C.c_int64(rows), *[_ptr(t) for t in w],
-                                          C.c_uint64(seed), C.c_uint64(step), _ptr(action_mask), _ptr(actions), _ptr(logp),
-                                          _ptr(None), _stream()))
+    if obs_copy is None and live_out is None:
+        _lib.check(_lib.lib().mm_actor_sample(_ptr(obs), _ptr(n_agents), C.c_int64(rows), *[_ptr(t) for t in w],
+                                              C.c_uint64(seed), C.c_uint64(step), _ptr(action_mask), _ptr(actions), _ptr(logp),
+                                              _ptr(None), _stream()))
+    else:
+        _check_record_slots(rows, obs_copy, live_out)
+        _lib.check(_lib.lib().mm_actor_sample_mlp(_ptr(obs), _ptr(n_agents), C.c_int64(rows), 128, *[_ptr(t) for t in w],
+                                                  _ptr(None), _ptr(None), C.c_uint64(seed), C.c_uint64(step), _ptr(action_mask),
+                                                  _ptr(actions), _ptr(logp), _ptr(None), _ptr(None), _ptr(obs_copy), _ptr(live_out),
+                                                  _stream()))
     return (actions, logp) if want_logp else actions
+
+
+def _check_record_slots(rows, obs_copy, live_out):
+    if obs_copy is not None:
+        assert obs_copy.is_cuda and obs_copy.dtype == torch.float32 and obs_copy.is_contiguous() and obs_copy.numel() == rows * NS
+    if live_out is not None:
+        assert live_out.is_cuda and live_out.dtype == torch.uint8 and live_out.is_contiguous() and live_out.numel() == rows
 
 
 class BatchedMAPPORollout(object):
@@ -293,6 +315,12 @@ class BatchedMAPPORollout(object):
         return a, self._slot < n_agents[:, None]
 
     @torch.no_grad()
+    def _record_act(self, obs, n_agents, a_slot, s_slot, l_slot):
+        self._draws += 1
+        return actor_sample(self.actor, obs, n_agents, seed=self.seed, step=self._draws, out_actions=a_slot, obs_copy=s_slot,
+                            live_out=l_slot)
+
+    @torch.no_grad()
     def act_torch(self, obs, n_agents):
         """Plain torch fp32 actor + torch.multinomial: the numerics reference of `act_fused`."""
         logp = self.actor(obs.reshape(-1, NS))                               # [E*12, 5]
@@ -311,21 +339,27 @@ class BatchedMAPPORollout(object):
         if self.obs is None:
             self.obs, _ = env.reset(seed=self.reset_seed)
         S = torch.empty((T, E, MAXV, NS), device=self.dev)
-        A = torch.empty((T, E, MAXV), dtype=torch.int64, device=self.dev)
+        A8 = torch.empty((T, E, MAXV), dtype=torch.int8, device=self.dev)
+        L8 = torch.empty((T, E, MAXV), dtype=torch.uint8, device=self.dev)
         R = torch.empty((T, E, MAXV), device=self.dev)
         D = torch.empty((T, E), device=self.dev)
-        L = torch.empty((T, E, MAXV), dtype=torch.bool, device=self.dev)
         for t in range(T):
-            n_agents = v["n_agents"].clone()
-            S[t].copy_(self.obs)
-            a, live = self._act(self.obs, n_agents)
+            if self.fused:
+                # the draw kernel appends to the rollout buffer itself: state S[t], action A8[t], live mask L8[t]
+                a = self._record_act(self.obs, v["n_agents"], A8[t], S[t], L8[t])
+            else:
+                n_agents = v["n_agents"].clone()
+                S[t].copy_(self.obs)
+                a, live = self._act(self.obs, n_agents)
+                A8[t].copy_(a)
+                L8[t].copy_(live)
             self.obs, reward, done, info = env.step(a, auto_reset=True)
-            A[t], L[t] = a.long(), live
             if self.reward_type == "regionalR":
                 R[t].copy_(info["regional_rewards"])
             else:
                 R[t].copy_(reward[:, None].expand(E, MAXV))
             D[t].copy_(done)
+        A, L = A8.long(), L8.bool()
         if self.reward_scale > 0:
             R /= self.reward_scale
         # bootstrap where the last step did not end the episode (mappo.py:148-150)
@@ -448,6 +482,12 @@ class BatchedMAPPOGIRollout(BatchedMAPPORollout):
         self._draws += 1
         a = policy_sample(self.policy, obs, n_agents, seed=self.seed, step=self._draws)
         return a, self._slot < n_agents[:, None]
+
+    @torch.no_grad()
+    def _record_act(self, obs, n_agents, a_slot, s_slot, l_slot):
+        self._draws += 1
+        return policy_sample(self.policy, obs, n_agents, seed=self.seed, step=self._draws, out_actions=a_slot, obs_copy=s_slot,
+                             live_out=l_slot)
 
     def _final_value(self, obs, n_agents):
         if self.fused:     # V(s) from the same kernel family: critic_linear as a sixth output column

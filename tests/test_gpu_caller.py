@@ -176,6 +176,27 @@ def test_fused_shared_network_of_mappo_gi(mm):
     assert bool((acts[dead] == 1).all())
 
 
+def test_actor_kernel_appends_to_the_rollout_buffer(mm):
+    """The draw kernels write slot t of the rollout buffer themselves (state the action was drawn from, action, live
+    mask: MAPPO.interact's appends, mappo.py:117-131): same actions as the plain call, the rows copied bit for bit."""
+    import torch
+    from marl_mass_b200 import rollout
+    torch.manual_seed(2)
+    E = 3001
+    obs = (torch.rand(E, 12, mm.NS, device="cuda") * 2 - 1).contiguous()
+    n_ag = torch.randint(1, 12, (E,), device="cuda", dtype=torch.int32)
+    for net, fn in ((rollout.ActorNetwork().cuda(), rollout.actor_sample), (rollout.ActorCriticNetwork().cuda(), rollout.policy_sample)):
+        plain = fn(net, obs, n_ag, seed=4, step=9)
+        S = torch.zeros(2, E, 12, mm.NS, device="cuda")
+        A8 = torch.full((2, E, 12), -1, dtype=torch.int8, device="cuda")
+        L8 = torch.full((2, E, 12), 7, dtype=torch.uint8, device="cuda")
+        got = fn(net, obs, n_ag, seed=4, step=9, out_actions=A8[1], obs_copy=S[1], live_out=L8[1])
+        torch.cuda.synchronize()
+        assert got.data_ptr() == A8[1].data_ptr() and torch.equal(A8[1], plain)
+        assert torch.equal(S[1], obs) and float(S[0].abs().max()) == 0.0 and int((A8[0] != -1).sum()) == 0
+        assert torch.equal(L8[1].bool(), torch.arange(12, device="cuda")[None, :] < n_ag[:, None])
+
+
 def test_invalid_action_masking_of_the_gi_actor(mm):
     """Model_gi.ActorNetwork (marl/single_agent/Model_gi.py:63-66): logits[action_mask == 0] = -1e8, then log-softmax.
     The env's own action masks (action_masking = True) go straight into the kernel; masked actions are never drawn."""
