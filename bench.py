@@ -53,6 +53,12 @@ WORKLOADS = {
                     desc="HSS cbf-avs_cint td3 (BASELINE configs[1]), 4096 envs"),
     "unsafe_td1": dict(cfg=dict(safety_guarantee="none", HEADWAY_TIME=1.2, traffic_density=1, traffic_type="cav"),
                        envs=65536, desc="no shield, td1 (BASELINE configs[0] LC-env sibling)"),
+    "dmc_v0_td3": dict(cfg=dict(env_name="merge-multi-agent-v0", safety_guarantee="dmc", HEADWAY_TIME=1.2, traffic_density=3,
+                                mixed_traffic=True), envs=65536,
+                       desc="baseline supervisor dmc, env merge-multi-agent-v0, td3 mixed (marl_cav-heading-t_headway-dmc-mixed.ini)"),
+    "priority_v0_td3": dict(cfg=dict(env_name="merge-multi-agent-v0", safety_guarantee="priority", HEADWAY_TIME=1.2, traffic_density=3,
+                                     mixed_traffic=True), envs=65536,
+                            desc="baseline supervisor priority, env merge-multi-agent-v0, td3 mixed (marl_cav-heading-t_headway-priority-mixed.ini)"),
     "unsafe_v0_td1": dict(cfg=dict(env_name="merge-multi-agent-v0", safety_guarantee="none", HEADWAY_TIME=1.2, traffic_density=1,
                                    mixed_traffic=True), envs=65536,
                           desc="no shield, env merge-multi-agent-v0, td1 mixed (BASELINE configs[0]: test-configs_marl-cav-unsafe.ini)"),
@@ -545,7 +551,7 @@ def main():
                                ("MASS td3 mixed traffic, 262144 envs", "mass_td3_mixed", False)):
             En = WORKLOADS[name]["envs"] if name != "mass_td3_mixed" else 262144
             lg = Leg(mm, mmd, name, En, dev, rank, policy=pol)
-            ms_l, st_l, _ = lg.timed(30, 5, barrier)
+            ms_l, st_l, _ = lg.timed(30, 20, barrier)    # 20 warm-up steps: every action slab has been seen twice (graph replay)
             kms_l, _ = lg.kernel_times(10)
             ag = st_l["agent_steps"] / max(st_l["env_steps"], 1.0)
             bpl = lg.algorithmic_bytes(ag)

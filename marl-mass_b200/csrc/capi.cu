@@ -35,6 +35,7 @@ int fail(mm_status code, const char *what, cudaError_t ce = cudaSuccess) {
     } while (0)
 
 constexpr int MAX_CHUNKS = 8;
+constexpr int GRAPH_MAX_ENVS = 131072;   // mm_step replays a CUDA graph up to this batch size (above, launch overhead is noise)
 constexpr int MAX_HOST_CHUNKS = 64;   // chunks of one mm_step_host_ragged / _packed call
 constexpr int HOST_F64 = 17, HOST_I32 = 11, HOST_ENV = 5;
 
@@ -77,6 +78,15 @@ struct mm_env {
     // *_host entry points after that work
     cudaStream_t last_stream = nullptr;
     cudaEvent_t caller_done = nullptr;
+    // Small batches are launch-bound (a policy step of 4 096 envs is four kernels of 3-100 us): mm_step replays the
+    // sequence as a CUDA graph.  One instantiated graph per (action buffer, auto_reset); `epoch` advances with everything
+    // a captured launch bakes in (config, seed, HDV knowledge, supervisor draws, the process-wide step variant).
+    struct StepGraph {
+        const int8_t *actions; int auto_reset; uint64_t epoch; unsigned long long variant_epoch;
+        cudaGraphExec_t exec; int build; int launches;
+    };
+    std::vector<StepGraph> graphs;
+    uint64_t epoch = 0;
     cudaStream_t streams[MAX_CHUNKS]{};
     int n_streams = 0;
     std::vector<void *> allocs;
@@ -169,7 +179,7 @@ int order_after_caller(mm_env *env, int n_str) {
 
 // enqueue one policy step (+ optional re-spawn of finished envs) for envs [off, off+count) on `stream`
 void enqueue_step(mm_env *env, const int8_t *actions_dev, int auto_reset, int off, int count, cudaStream_t stream) {
-    if (auto_reset && env->cfg.traffic_type != MM_TRAFFIC_CAV) env->hdv_possible = true;
+    if (auto_reset && env->cfg.traffic_type != MM_TRAFFIC_CAV && !env->hdv_possible) { env->hdv_possible = true; ++env->epoch; }
     if (env->cfg.supervisor != MM_SUPERVISOR_NONE) {
         // abstract.py:459-464: new_action = safety_supervisor / safety_layer_dmc (env, action); _simulate(new_action)
         int8_t *na = env->new_actions + (size_t)off * MAXV;
@@ -275,6 +285,8 @@ int mm_destroy(mm_env *env) {
         if (env->streams[i]) cudaStreamDestroy(env->streams[i]);
     for (int i = 0; i < MAX_HOST_CHUNKS; ++i)
         if (env->chunk_done[i]) cudaEventDestroy(env->chunk_done[i]);
+    for (auto &g : env->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
     if (env->caller_done) cudaEventDestroy(env->caller_done);
     for (int i = 0; i < MAX_HOST_CHUNKS; ++i)
         if (env->scan_done[i]) cudaEventDestroy(env->scan_done[i]);
@@ -289,6 +301,7 @@ int mm_set_config(mm_env *env, const mm_config *cfg) {
     if (!env) return fail(MM_ERR_ARG, "env is null");
     if (int rc = validate(cfg)) return rc;
     env->cfg = *cfg;
+    ++env->epoch;
     if (cfg->supervisor != MM_SUPERVISOR_NONE) return ensure_supervisor_stack(env);
     return 0;
 }
@@ -296,6 +309,7 @@ int mm_set_config(mm_env *env, const mm_config *cfg) {
 int mm_set_supervisor_draws(mm_env *env, const double *draws_dev) {
     if (!env) return fail(MM_ERR_ARG, "env is null");
     env->sup_draws = draws_dev;
+    ++env->epoch;
     return 0;
 }
 
@@ -315,10 +329,13 @@ int mm_reset(mm_env *env, uint64_t seed, const uint8_t *mask_dev, int num_cav, v
     if (!env) return fail(MM_ERR_ARG, "env is null");
     if (num_cav < 0 || num_cav > 11) return fail(MM_ERR_ARG, "num_cav must be in 0..11");
     CUDA_OK(cudaSetDevice(env->device));
+    if (seed != env->seed) ++env->epoch;      // the auto-reset of a captured step carries the seed
     env->seed = seed;
     env->last_stream = (cudaStream_t)stream;
+    const bool hdv_before = env->hdv_possible;
     if (env->cfg.traffic_type != MM_TRAFFIC_CAV) env->hdv_possible = true;
     else if (!mask_dev) env->hdv_possible = false;      // every env re-spawned all-CAV
+    if (hdv_before != env->hdv_possible) ++env->epoch;
     ResetParams r{};
     r.st = env->st; r.out = env->out; r.mask = mask_dev; r.cfg = env->cfg; r.seed = seed;
     r.n_envs = env->n_envs; r.env_offset = 0; r.env_count = env->n_envs; r.num_cav = num_cav; r.use_done = 0;
@@ -335,7 +352,50 @@ int mm_step(mm_env *env, const int8_t *actions_dev, int auto_reset, void *stream
     if (!env) return fail(MM_ERR_ARG, "env is null");
     CUDA_OK(cudaSetDevice(env->device));
     env->last_stream = (cudaStream_t)stream;
-    enqueue_step(env, actions_dev ? actions_dev : env->actions, auto_reset, 0, env->n_envs, (cudaStream_t)stream);
+    const int8_t *actions = actions_dev ? actions_dev : env->actions;
+    static const bool no_graph = getenv("MM_NO_GRAPH") != nullptr;
+    if (no_graph || env->n_envs > GRAPH_MAX_ENVS) {
+        enqueue_step(env, actions, auto_reset, 0, env->n_envs, (cudaStream_t)stream);
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    }
+    // graph replay: first sight of a key runs eagerly (one-time function-attribute setup stays out of a capture), the
+    // second captures the sequence on an internal stream, later ones replay it on the caller's stream
+    const unsigned long long vep = step_variant_epoch();
+    for (auto &g : env->graphs) {
+        if (g.actions != actions || g.auto_reset != auto_reset) continue;
+        if (g.epoch != env->epoch || g.variant_epoch != vep) {      // stale: drop and start over
+            if (g.exec) cudaGraphExecDestroy(g.exec);
+            g = env->graphs.back();
+            env->graphs.pop_back();
+            break;
+        }
+        if (!g.exec) {
+            cudaStream_t cs = env->streams[0];
+            cudaGraph_t graph = nullptr;
+            CUDA_OK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+            const int64_t l0 = env->launches;
+            enqueue_step(env, actions, auto_reset, 0, env->n_envs, cs);
+            g.launches = (int)(env->launches - l0);
+            env->launches = l0;
+            g.build = env->last_build;
+            cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+            if (ce != cudaSuccess || !graph) return fail(MM_ERR_CUDA, "cudaStreamEndCapture", ce);
+            ce = cudaGraphInstantiate(&g.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) { g.exec = nullptr; return fail(MM_ERR_CUDA, "cudaGraphInstantiate", ce); }
+        }
+        CUDA_OK(cudaGraphLaunch(g.exec, (cudaStream_t)stream));
+        env->launches += g.launches;
+        env->last_build = g.build;
+        return 0;
+    }
+    if (env->graphs.size() >= 16) {      // bounded cache: forget the oldest key
+        if (env->graphs.front().exec) cudaGraphExecDestroy(env->graphs.front().exec);
+        env->graphs.erase(env->graphs.begin());
+    }
+    env->graphs.push_back({actions, auto_reset, env->epoch, vep, nullptr, 0, 0});
+    enqueue_step(env, actions, auto_reset, 0, env->n_envs, (cudaStream_t)stream);
     CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -698,6 +758,7 @@ int mm_set_state(mm_env *env, const mm_state_host *src) {
     }
     bool any_hdv = false;
     for (size_t e = 0; e < E; ++e) any_hdv = any_hdv || ed[1][e] < ed[0][e];
+    if (env->hdv_possible != any_hdv) ++env->epoch;
     env->hdv_possible = any_hdv;
     env->last_stream = nullptr;
     double *f64 = nullptr; int32_t *i32 = nullptr, *envv = nullptr;

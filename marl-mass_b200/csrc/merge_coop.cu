@@ -219,20 +219,18 @@ __global__ void __launch_bounds__(CTHREADS, MM_COOP_MIN_BLOCKS) coop_step_kernel
                     const bool e_eff_bc = (e_eff == L_BC0) | (e_eff == L_BC1);
                     bool oa_left = false;
                     id_ol = MM_NB_NONE; id_oa = MM_NB_NONE; id_oar = MM_NB_NONE;
-                    double last_key = -1.0;
-                    int last_id = -1;
+                    uint32_t taken = 0;
 #pragma unroll 1
                     for (int k = 0; k < 5; ++k) {
-                        // k-th smallest (key, slot): sorted() is stable, equal keys keep slot order
+                        // k-th smallest (key, slot): sorted() is stable, equal keys keep slot order - the first minimum
+                        // among the slots not taken yet
                         double best = CUDART_INF;
                         int o = -1;
 #pragma unroll
-                        for (int j = 0; j < SMV; ++j) {
-                            const bool after = key[j] > last_key || (key[j] == last_key && j > last_id);
-                            if (after && key[j] < best) { best = key[j]; o = j; }
-                        }
+                        for (int j = 0; j < SMV; ++j)
+                            if (!((taken >> j) & 1u) && key[j] < best) { best = key[j]; o = j; }
                         if (o < 0) break;
-                        last_key = best; last_id = o;
+                        taken |= 1u << o;
                         // multi_agent_state (decentral_layer.py:85-257), one candidate
                         const bool mv = RANK[col + o] < rank;
                         const double ox = mv ? NX[col + o] : X(o);
@@ -502,10 +500,12 @@ __global__ void __launch_bounds__(CTHREADS, MM_COOP_MIN_BLOCKS) coop_step_kernel
         const unsigned close_mask = (__ballot_sync(hmask, close) & hmask) >> (threadIdx.x & 16);
         if (close_mask && running && i == 0) collision_pass(ev, close_mask);
         __syncwarp();
+        // _is_terminal (merge_env_v1.py:168-172): a lane looks at its own vehicle, a ballot gathers the env's answer
+        const bool out_i = running && has_v && i < ev.n_cav && ((FL(i) & FL_CRASHED) || X(i) < 0);
+        const bool any_out = (__ballot_sync(hmask, out_i) & hmask) != 0;
         if (running) {
             time = min(time + 1, (int)EI_TIME_MASK);
-            // _is_terminal (merge_env_v1.py:168-172), evaluated by every lane on the shared planes
-            if (is_terminal(ev, steps, p.cfg)) running = false;   // abstract.py:530
+            if (steps >= p.cfg.duration_steps || any_out) running = false;   // abstract.py:530
         }
         __syncwarp();
     }

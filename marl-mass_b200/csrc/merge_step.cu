@@ -651,7 +651,9 @@ void launch_step_impl(const StepParams &p, bool diag, void *stream) {
 
 #ifndef MM_VARIANT_TU
 static int g_step_variant = 0;
-void set_step_variant(int v) { g_step_variant = (v >= 3 && v <= 8) ? v : 0; }
+static unsigned long long g_variant_epoch = 0;     // bumped by every change of the variant: cached step graphs are keyed on it
+void set_step_variant(int v) { g_step_variant = (v >= 3 && v <= 8) ? v : 0; ++g_variant_epoch; }
+unsigned long long step_variant_epoch() { return g_variant_epoch; }
 
 // Picks the build of the step kernel: 4 CTAs / SM when the wave structure of the grid favours it (e.g. 512 CTAs on 148
 // SMs: one wave instead of a full and an almost empty one), else the default 3 CTAs / SM build.

@@ -114,6 +114,7 @@ void launch_step_spec_mass4(const StepParams &p, bool diag, void *stream);   // 
 void launch_step_spec_hss4(const StepParams &p, bool diag, void *stream);
 // the warp-cooperative build: half a warp per env, one lane per vehicle (merge_coop.cu); all-CAV plain LC envs only
 void launch_step_coop(const StepParams &p, bool diag, void *stream);
+unsigned long long step_variant_epoch();   // changes whenever set_step_variant was called
 void set_step_variant(int v);   // 0: automatic, 3 / 4: force the generic 3- or 4-CTAs-per-SM build, 5: automatic without the specialised builds
 void launch_reset(const ResetParams &p, void *stream);
 // outputs kernel (merge_outputs.cu): observations, rewards, terminal flags, info scalars and statistics of the policy step
