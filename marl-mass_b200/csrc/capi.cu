@@ -34,7 +34,7 @@ int fail(mm_status code, const char *what, cudaError_t ce = cudaSuccess) {
         if (_ce != cudaSuccess) return fail(MM_ERR_CUDA, #expr, _ce);        \
     } while (0)
 
-constexpr int MAX_CHUNKS = 8;
+constexpr int MAX_CHUNKS = 16;
 constexpr int GRAPH_MAX_ENVS = 131072;   // mm_step replays a CUDA graph up to this batch size (above, launch overhead is noise)
 constexpr int MAX_HOST_CHUNKS = 64;   // chunks of one mm_step_host_ragged / _packed call
 constexpr int HOST_F64 = 17, HOST_I32 = 11, HOST_ENV = 5;
@@ -579,7 +579,7 @@ int mm_step_host_packed(mm_env *env, const int8_t *actions, int auto_reset, cons
         env->packed_ready = true;
     }
     const int chunk_target = host_chunk_target(E);
-    const int n_str = 4;
+    static const int n_str = [] { const char *e = getenv("MM_HOST_STREAMS"); int v = e ? atoi(e) : 0; return (v >= 1 && v <= 8) ? v : 4; }();
     int n_chunks = (E + chunk_target - 1) / chunk_target;
     if (n_chunks < 1) n_chunks = 1;
     if (n_chunks > MAX_HOST_CHUNKS) n_chunks = MAX_HOST_CHUNKS;

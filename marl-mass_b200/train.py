@@ -65,13 +65,13 @@ def train(config, n_envs=4096, iterations=30, device=0, eval_interval=10, miniba
         if not dist.is_initialized():
             dist.init_process_group("nccl", device_id=torch.device("cuda", device))
     torch.manual_seed(tr["torch_seed"])
+    if env_cfg.get("env_name", "merge-multi-agent-v1") != "merge-multi-agent-v1":
+        # env ids merge-multi-agent-v0 / -v05 observe 5 x 5 (no heading column, n_s = 25) and -hdv-v1 has no agents: the
+        # networks of this driver and the fused actor kernels are the reference's 30-input ones (Model_common.py:11-23
+        # with n_s = 30).  Rejected before anything is built (a 25-column state would otherwise be fed to 30 inputs).
+        raise ValueError("train: env id %r is not covered by the batched learner (n_s = 30 env id merge-multi-agent-v1 only)"
+                         % (env_cfg.get("env_name"),))
     env = MergeEnvBatched(n_envs, dict(DEFAULT_CONFIG, **env_cfg), device=device)
-    if env.n_s != 30:
-        # env ids merge-multi-agent-v0 / -v05 observe 5 x 5 (no heading column): the networks of this driver and the
-        # fused actor kernel are the reference's 30-input ones (Model_common.py:11-23 with n_s = 30)
-        env.close()
-        raise ValueError("train: env id %r has n_s = %d; the batched learner covers the n_s = 30 env ids "
-                         "(merge-multi-agent-v1)" % (env_cfg.get("env_name"), env.n_s))
     # rank-distinct spawn stream; its first observation goes to the rollout so that collect() does not re-spawn the
     # scenes with the (rank-independent) config seed
     obs0, _ = env.reset(seed=mmd.rank_seed(env_cfg["seed"], rank) if world > 1 else env_cfg["seed"])

@@ -197,6 +197,25 @@ def test_actor_kernel_appends_to_the_rollout_buffer(mm):
         assert torch.equal(L8[1].bool(), torch.arange(12, device="cuda")[None, :] < n_ag[:, None])
 
 
+def test_rollouts_of_different_ranks_spawn_different_scenes(mm):
+    """Data-parallel shards must not be replicas: a rollout that spawns its own scenes uses a spawn seed derived from its
+    (rank-distinct) seed, never the env's config seed, so two ranks' first collect() see different scenes - and the same
+    rank seed reproduces its scenes."""
+    import torch
+    from marl_mass_b200 import rollout
+    cfg = dict(mm.DEFAULT_CONFIG, safety_guarantee="cbf-cav", traffic_density=3, HEADWAY_TIME=0.5, cbf_eta=0.03125, seed=11)
+    states = []
+    for rank_seed in (0, 104729, 0):
+        env = mm.MergeEnvBatched(256, cfg)
+        pol = rollout.BatchedMAPPORollout(env, roll_out_n_steps=2, seed=rank_seed)
+        pol.collect()
+        torch.cuda.synchronize()
+        states.append(env.get_state())
+        env.close()
+    assert not np.array_equal(states[0]["n_veh"], states[1]["n_veh"]) or not np.array_equal(states[0]["x"], states[1]["x"])
+    assert np.array_equal(states[0]["n_veh"], states[2]["n_veh"])
+
+
 def test_invalid_action_masking_of_the_gi_actor(mm):
     """Model_gi.ActorNetwork (marl/single_agent/Model_gi.py:63-66): logits[action_mask == 0] = -1e8, then log-softmax.
     The env's own action masks (action_masking = True) go straight into the kernel; masked actions are never drawn."""

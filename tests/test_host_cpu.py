@@ -289,6 +289,16 @@ def test_shipped_ini_files_map_onto_the_batched_path():
         assert must in ok
 
 
+def test_training_driver_rejects_env_ids_it_does_not_cover():
+    """The batched learner's networks take the 30-column KinematicLC state; the n_s = 25 env ids (v0, v05) and the all-HDV
+    env are refused before anything is built (no GPU needed to find out)."""
+    from marl_mass_b200 import train as tr
+    for env_name in ("merge-multi-agent-v0", "merge-multi-agent-v05", "merge-multi-agent-hdv-v1"):
+        cfg = ({"env_name": env_name, "seed": 0}, {}, {"torch_seed": 0})
+        with pytest.raises(ValueError, match="not covered by the batched learner"):
+            tr.train(cfg, n_envs=8, iterations=1)
+
+
 def test_training_driver_reads_the_reference_ini_layout():
     """train.load_ini: the sections / keys / fallbacks of run_mappo.py:113-171, on the shipped example and (when the
     reference tree is present) on the reference's own MASS td3 srew ini - both must give the same configuration."""
