@@ -46,7 +46,7 @@ enum { MM_ACT_LEAD = 1, MM_ACT_UPPER = 2, MM_ACT_LOWER = 4, MM_ACT_ADJ = 8, MM_A
  * signature; mm_abi_version() returns the value the library was built with, and mm_create / mm_set_config reject a
  * config whose struct_size field is not sizeof(mm_config) (a binding built against another revision of the header
  * fails loudly instead of handing the library garbage). */
-#define MM_ABI_VERSION 6
+#define MM_ABI_VERSION 7
 int mm_abi_version(void);
 
 typedef struct {
@@ -197,6 +197,21 @@ int mm_get_state(mm_env *env, mm_state_host *dst);        /* synchronous */
 int mm_set_state(mm_env *env, const mm_state_host *src);  /* synchronous; also refreshes obs / n_agents */
 int mm_get_shield_diag(mm_env *env, mm_shield_diag_host *dst);   /* requires record_diag */
 int mm_stats(mm_env *env, mm_stats_t *out, int reset);    /* synchronous */
+
+/* The shield alone: safety_layer(safety_type, action, vehicle, dt, ...) (highway_env/vehicle/safety/decentral_layer.py:
+ * 767-817, as MDPLCVehicle.step calls it through get_safe_action, safe_controller.py:229-250) for every CAV of the current
+ * scenes, against the scenes as they are - the view the front-most vehicle of a sub-step has; nothing is stepped and no
+ * state is written (the reference's side effects on the vehicle - is_collaborating, is_lc_safe, target_lane_index,
+ * min_headway, the on-ramp HDV record shift - are returned / kept local instead).  Inputs: the clipped low-level action
+ * per CAV, nom_steer / nom_acc [n_envs][MM_MAXV] f64 DEVICE.  Outputs [n_envs][MM_MAXV], DEVICE: the shielded action,
+ * the time headway the shield computed, and the status the reference logs: whether the shield ran (its gate: fg_params
+ * set and two history records), the neighbour classification of multi_agent_state (slot ids, MM_NB_NONE, MM_NB_OBSTACLE),
+ * constrain_adj, the QP active set (MM_ACT_*), is_lc_safe. */
+typedef struct {
+    double *safe_steer, *safe_acc, *min_headway;
+    int32_t *ran, *leader, *front_adj, *rear_adj, *constrain_adj, *active, *is_lc_safe;
+} mm_shield_query_out;
+int mm_shield_query(mm_env *env, const double *nom_steer, const double *nom_acc, const mm_shield_query_out *out, void *stream);
 
 /* The CBF-QP alone (cbf.py:110-161 through cvxopt.solvers.qp): n independent solves on DEVICE arrays;
  * u and active may alias nothing else.  Used for the solves/s microbenchmark and the QP known-answer tests. */

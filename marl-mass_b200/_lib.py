@@ -28,7 +28,7 @@ _PU8 = C.POINTER(C.c_uint8)
 _PI8 = C.POINTER(C.c_int8)
 
 
-ABI_VERSION = 6           # MM_ABI_VERSION of the header this binding was written against
+ABI_VERSION = 7           # MM_ABI_VERSION of the header this binding was written against
 
 
 class MMConfig(C.Structure):
@@ -62,6 +62,11 @@ class MMPackedHost(C.Structure):
                 ("reward", C.c_void_p), ("done", C.c_void_p), ("regional_rewards", C.c_void_p)]
 
 
+class MMShieldQueryOut(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("safe_steer", "safe_acc", "min_headway", "ran", "leader", "front_adj", "rear_adj",
+                                          "constrain_adj", "active", "is_lc_safe")]
+
+
 class MMShieldDiagHost(C.Structure):
     _fields_ = [(k, _PI) for k in SH_I] + [(k, _PD) for k in SH_F]
 
@@ -81,7 +86,7 @@ _lib = None
 SUPERVISOR_DRAWS = 32     # MM_SUPERVISOR_DRAWS
 EXPORTS = ("mm_create", "mm_destroy", "mm_set_config", "mm_num_envs", "mm_reset", "mm_step", "mm_step_host",
            "mm_step_host_ragged", "mm_step_host_packed", "mm_expand_obs_rows",
-           "mm_buffers_get", "mm_get_state", "mm_set_state", "mm_get_shield_diag", "mm_stats", "mm_shield_qp",
+           "mm_buffers_get", "mm_get_state", "mm_set_state", "mm_get_shield_diag", "mm_stats", "mm_shield_qp", "mm_shield_query",
            "mm_actor_sample", "mm_actor_sample_mlp", "mm_set_actor_impl", "mm_set_step_variant", "mm_step_build", "mm_abi_version", "mm_discounted_returns", "mm_supervise", "mm_set_supervisor_draws", "mm_supervisor_draws_used",
            "mm_kernel_launches", "mm_last_error", "mm_version")
 
@@ -115,6 +120,7 @@ def lib():
     L.mm_set_state.argtypes = [h, C.POINTER(MMStateHost)]
     L.mm_get_shield_diag.argtypes = [h, C.POINTER(MMShieldDiagHost)]
     L.mm_stats.argtypes = [h, C.POINTER(MMStats), C.c_int]
+    L.mm_shield_query.argtypes = [h, C.c_void_p, C.c_void_p, C.POINTER(MMShieldQueryOut), C.c_void_p]
     L.mm_shield_qp.argtypes = [C.c_void_p] * 6 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mm_actor_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 6 + [C.c_uint64, C.c_uint64] + \
                                  [C.c_void_p] * 5

@@ -817,6 +817,20 @@ int mm_stats(mm_env *env, mm_stats_t *out, int reset) {
     return 0;
 }
 
+int mm_shield_query(mm_env *env, const double *nom_steer, const double *nom_acc, const mm_shield_query_out *out, void *stream) {
+    if (!env || !nom_steer || !nom_acc || !out) return fail(MM_ERR_ARG, "null argument");
+    int32_t *oi[7] = {out->ran, out->leader, out->front_adj, out->rear_adj, out->constrain_adj, out->active, out->is_lc_safe};
+    for (int k = 0; k < 7; ++k)
+        if (!oi[k]) return fail(MM_ERR_ARG, "mm_shield_query: every output array is required");
+    if (!out->safe_steer || !out->safe_acc || !out->min_headway) return fail(MM_ERR_ARG, "mm_shield_query: every output array is required");
+    CUDA_OK(cudaSetDevice(env->device));
+    env->last_stream = (cudaStream_t)stream;
+    launch_shield_query(env->st, env->cfg, env->n_envs, nom_steer, nom_acc, out->safe_steer, out->safe_acc, out->min_headway, oi, stream);
+    env->launches += 1;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int mm_shield_qp(const double *a, const double *c_lead, const double *c_adj, const uint8_t *has_adj, const double *lo,
                  const double *hi, int64_t n, double *u, uint8_t *active, void *stream) {
     if (!a || !c_lead || !c_adj || !has_adj || !lo || !hi || !u || !active) return fail(MM_ERR_ARG, "null argument");

@@ -604,6 +604,58 @@ void launch_ragged_pack(const float *obs, const int32_t *n_agents, int count, in
 }
 
 // ------------------------------------------------------------------------------------------------
+// stand-alone shield query (mm_shield_query): safety_layer(...) for every CAV of the current scenes, nothing stepped
+// ------------------------------------------------------------------------------------------------
+// decentral_layer.py:767-817 as the reference calls it from MDPLCVehicle.step: (nominal action, vehicle, road) -> (safe
+// action, status).  One thread per env; the scene is copied to shared memory, every CAV is evaluated against the scene AS
+// IT IS (no vehicle has moved: the view the front-most vehicle of a sub-step has), and nothing is written back.
+struct ShieldQueryParams {
+    DevState st;
+    mm_config cfg;
+    int n_envs;
+    const double *nom_steer, *nom_acc;                 // [E][MAXV] clipped low-level action per CAV
+    double *safe_steer, *safe_acc, *min_headway;       // [E][MAXV]
+    int32_t *ran, *leader, *front_adj, *rear_adj, *constrain_adj, *active, *is_lc_safe;   // [E][MAXV]
+};
+
+__global__ void __launch_bounds__(BLOCK) shield_query_kernel(const __grid_constant__ ShieldQueryParams p) {
+    const int tid = threadIdx.x;
+    const int local = blockIdx.x * BLOCK + tid;
+    if (local >= p.n_envs) return;
+    const size_t e = (size_t)local;
+    Env ev;
+    ev.tid = tid;
+    ev.g = p.st.f64 + f64_index(e, 0, 0);
+    const uint32_t ei = p.st.einfo[e];
+    ev.n_veh = (ei >> EI_NVEH_SHIFT) & EI_4BIT;
+    ev.n_cav = (ei >> EI_NCAV_SHIFT) & EI_4BIT;
+    load_env(ev, p.st, e);
+    ev.live = order_by_x_desc(ev);
+    ev.pos = invert_order(ev.live, ev.n_veh);
+    for (int i = 0; i < MAXV; ++i) {
+        const size_t k = e * MAXV + i;
+        int ran = 0;
+        ShieldRec rec{MM_NB_NONE, MM_NB_NONE, MM_NB_NONE, 0, 0, 1, 0.0, 0.0};
+        double steer = 0.0, acc = 0.0;
+        if (i < ev.n_cav) {
+            const uint32_t f = FL(i);
+            steer = p.nom_steer[k];
+            acc = p.nom_acc[k];
+            // get_safe_action gate (safe_controller.py:229-239)
+            if (CFG_SHIELD(p.cfg) != MM_SHIELD_NONE && !CFG_V0(p.cfg) && (f & FL_FG) && fl_hist(f) >= 2) {
+                const double nom_steer = steer, nom_acc = acc;
+                shield<false, true>(ev, p.cfg, i, nom_steer, nom_acc, GF(F_REC1VX, i), GF(F_GVX, i), steer, acc, rec);
+                FL(i) = f;          // the evaluation of one vehicle leaves no trace for the next one
+                ran = 1;
+            }
+        }
+        p.ran[k] = ran; p.leader[k] = rec.leader; p.front_adj[k] = rec.front_adj; p.rear_adj[k] = rec.rear_adj;
+        p.constrain_adj[k] = rec.constrain_adj; p.active[k] = rec.active; p.is_lc_safe[k] = rec.is_lc_safe;
+        p.safe_steer[k] = steer; p.safe_acc[k] = acc; p.min_headway[k] = ran ? rec.min_headway : 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // stand-alone QP kernel (solves/s microbenchmark, known-answer tests)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) qp_kernel(const double *__restrict__ a, const double *__restrict__ c_lead,
@@ -713,6 +765,22 @@ void launch_unpack_state(const DevState &st, int n_envs, double *f64_em, int32_t
                          void *stream) {
     size_t n = (size_t)n_envs * MAXV;
     unpack_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(st, n_envs, f64_em, i32_em, env_em);
+}
+
+void launch_shield_query(const DevState &st, const mm_config &cfg, int n_envs, const double *nom_steer, const double *nom_acc,
+                         double *safe_steer, double *safe_acc, double *min_headway, int32_t *const *out_i, void *stream) {
+    static bool ready[MM_MAX_DEVICES] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MM_MAX_DEVICES) return;
+    if (!ready[dev]) {
+        if (cudaFuncSetAttribute(shield_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEP_SMEM) != cudaSuccess) return;
+        ready[dev] = true;
+    }
+    ShieldQueryParams p{st, cfg, n_envs, nom_steer, nom_acc, safe_steer, safe_acc, min_headway,
+                        out_i[0], out_i[1], out_i[2], out_i[3], out_i[4], out_i[5], out_i[6]};
+    const int grid = (n_envs + BLOCK - 1) / BLOCK;
+    if (grid <= 0) return;
+    shield_query_kernel<<<grid, BLOCK, STEP_SMEM, (cudaStream_t)stream>>>(p);
 }
 
 void launch_qp(const double *a, const double *c_lead, const double *c_adj, const uint8_t *has_adj, const double *lo,

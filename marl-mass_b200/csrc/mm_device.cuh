@@ -478,7 +478,7 @@ __device__ __forceinline__ void get_corner(double px, double py, double ch, doub
 
 struct ShieldRec {
     int leader, front_adj, rear_adj, constrain_adj, active, is_lc_safe;
-    double lc_margin;
+    double lc_margin, min_headway;
 };
 
 // road.py:257-267: the `count` nearest (by |longitudinal offset in the ego lane|, stable) among vehicles
@@ -574,7 +574,9 @@ __device__ __forceinline__ int close_vehicles(const Env &ev, int self, uint32_t 
 // multi_agent_state (85-257) and CBF_AV / CBF_CAV (cbf.py:197-430).  Returns the shielded (steer, acc).
 // `act_steer`, `act_acc`: the clipped nominal action; `rec1vx`, `ge`: the ego's last logged vx and fg g.vx (the caller
 // has them in registers already).  WITH_MARGIN: also report the veto margin (diagnostic builds only).
-template <bool WITH_MARGIN>
+// QUERY: evaluate only (mm_shield_query) - nothing outside the caller's shared-memory copy of the scene is written: the
+// min_headway field and the in-place shift of an on-ramp HDV's record stay local.
+template <bool WITH_MARGIN, bool QUERY = false>
 __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, double act_steer, double act_acc, double rec1vx,
                                     double ge, double &out_steer, double &out_acc, ShieldRec &rec) {
     const double dt = cfg.dt, eta = cfg.eta, tau = cfg.tau;
@@ -647,7 +649,7 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
             // on-ramp HDV: its record is shifted IN PLACE by half a second of ego speed (decentral_layer.py:175-184);
             // it takes the front-adjacent role whoever held it
             x_onramp = GF(F_REC2X, o) + 0.5 * evx_raw;
-            GF(F_REC2X, o) = x_onramp;
+            if (!QUERY) GF(F_REC2X, o) = x_onramp;
             vx_onramp = GF(F_REC2VX, o);
             id_oa = o;
             oa_onramp = true;
@@ -723,7 +725,8 @@ __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, dou
     double buffer = (ACC_HI + 0.1) * dt * tau;
     double sd_l = evx * tau + VLEN + buffer;
     double sd_r = sv_oar * tau + VLEN + buffer;
-    GF(F_MINHW, self) = (x_ol - ex - VLEN) / evx;
+    rec.min_headway = (x_ol - ex - VLEN) / evx;
+    if (!QUERY) GF(F_MINHW, self) = rec.min_headway;
 
     // one-step predictions (decentral_layer.py:60-77)
     double v_ll = fmax(0.0, evx + act_acc * dt);

@@ -126,6 +126,9 @@ void launch_pack_state(const DevState &st, int n_envs, const double *f64_em /*[1
                        const int32_t *i32_em /*[11][E][MAXV]*/, const int32_t *env_em /*[5][E]*/, void *stream);
 void launch_unpack_state(const DevState &st, int n_envs, double *f64_em, int32_t *i32_em, int32_t *env_em,
                          void *stream);
+// out_i: ran, leader, front_adj, rear_adj, constrain_adj, active, is_lc_safe (device arrays [n_envs][MAXV])
+void launch_shield_query(const DevState &st, const mm_config &cfg, int n_envs, const double *nom_steer, const double *nom_acc,
+                         double *safe_steer, double *safe_acc, double *min_headway, int32_t *const *out_i, void *stream);
 void launch_qp(const double *a, const double *c_lead, const double *c_adj, const uint8_t *has_adj,
                const double *lo, const double *hi, int64_t n, double *u, uint8_t *active, void *stream);
 

@@ -371,6 +371,24 @@ class MergeEnvBatched(object):
         _lib.check(self._L.mm_get_shield_diag(self._h, C.byref(s)))
         return d
 
+    def shield_query(self, nom_steer, nom_acc, stream=None):
+        """The shield alone (mm_shield_query): `safety_layer(...)` (decentral_layer.py:767-817) for every CAV of the
+        current scenes, nothing stepped, no state written.  nom_steer / nom_acc: [E, 12] float64 cuda (the clipped
+        low-level action per CAV).  -> dict of [E, 12] cuda tensors: safe_steer, safe_acc, min_headway (f64), ran,
+        leader, front_adj, rear_adj, constrain_adj, active, is_lc_safe (int32)."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        ns = nom_steer.to(device=dev, dtype=torch.float64).contiguous()
+        na = nom_acc.to(device=dev, dtype=torch.float64).contiguous()
+        assert ns.shape == (self.n_envs, MAXV) and na.shape == (self.n_envs, MAXV)
+        out = {k: torch.empty((self.n_envs, MAXV), dtype=torch.float64, device=dev) for k in ("safe_steer", "safe_acc", "min_headway")}
+        out.update({k: torch.empty((self.n_envs, MAXV), dtype=torch.int32, device=dev)
+                    for k in ("ran", "leader", "front_adj", "rear_adj", "constrain_adj", "active", "is_lc_safe")})
+        s = _lib.MMShieldQueryOut(**{k: C.c_void_p(v.data_ptr()) for k, v in out.items()})
+        _lib.check(self._L.mm_shield_query(self._h, C.c_void_p(ns.data_ptr()), C.c_void_p(na.data_ptr()), C.byref(s),
+                                           self._stream_ptr(stream)))
+        return out
+
     def stats(self, reset=False):
         s = _lib.MMStats()
         _lib.check(self._L.mm_stats(self._h, C.byref(s), int(reset)))

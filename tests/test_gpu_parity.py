@@ -501,6 +501,45 @@ def test_packed_host_step_expands_to_the_observation_rows(mm, traffic, lateral, 
     b_env.close()
 
 
+@pytest.mark.parametrize("name", ["hss_td3", "mass_td3_srew", "mass_td3_mixed", "mass_td1", "steervel_mass_td2", "ties_mass_td3"])
+def test_stand_alone_shield_query_matches_the_reference_records(mm, orc, name):
+    """mm_shield_query = safety_layer(...) for every CAV against the scene as it is.  The reference evaluates its shields
+    front to back inside a sub-step, so its logged record of the FRONT-MOST vehicle in sub-step 0 (nobody has moved yet)
+    is exactly such an evaluation: on every golden step whose front-most vehicle is a shielded CAV, the query - fed the
+    nominal action the reference logged - must return the logged safe action, neighbour ids, active set and veto flag.
+    The query writes nothing: the state is unchanged afterwards."""
+    import torch
+    g, cfg = load_golden(name)
+    rows = g["row_of_step"]
+    st = full_state(orc, g, rows)
+    env = mm.MergeEnvBatched(len(rows), env_config(cfg))
+    env.set_state(st)
+    before = env.get_state()
+    xs = np.where(used_mask(st), st["x"], -1e9)
+    front = xs.argmax(axis=1)                                   # first maximum = lowest slot on ties, as the stable sort
+    idx = np.arange(len(rows))
+    ran0 = g["sh_ran"][:, 0, :]
+    sel = ran0[idx, front] == 1
+    assert sel.sum() > 50, sel.sum()
+    nom_steer = np.where(ran0 == 1, g["sh_nom_steer"][:, 0, :], 0.0)
+    nom_acc = np.where(ran0 == 1, g["sh_nom_acc"][:, 0, :], 0.0)
+    out = env.shield_query(torch.from_numpy(nom_steer).cuda(), torch.from_numpy(nom_acc).cuda())
+    torch.cuda.synchronize()
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    r, f = idx[sel], front[sel]
+    assert np.array_equal(out["ran"][r, f], np.ones(len(r), np.int32))
+    for k in ("leader", "front_adj", "rear_adj", "constrain_adj", "active", "is_lc_safe"):
+        assert np.array_equal(out[k][r, f], g["sh_" + k][r, 0, f]), k
+    assert rel_err(out["safe_acc"][r, f], g["sh_safe_acc"][r, 0, f]).max() <= STATE_TOL
+    # steering: a vetoed lane change re-steers towards the own lane only if a lane change is under way, i.e. it reads the
+    # target lane - which the reference's act() has already updated for this sub-step when its shield runs, and the
+    # fixture's pre-step state has not.  Compared wherever the shield did not veto.
+    free = g["sh_is_lc_safe"][r, 0, f] == 1
+    assert free.sum() > 30 and rel_err(out["safe_steer"][r, f][free], g["sh_safe_steer"][r, 0, f][free]).max() <= STATE_TOL
+    compare_states(env.get_state(), before, 0.0, name + " (query left the state alone)")
+    env.close()
+
+
 def test_checkpoint_resume_continues_bit_identically(mm, tmp_path):
     """save() / load(): a rollout resumed from a checkpoint in a fresh handle continues exactly like the original."""
     import torch
