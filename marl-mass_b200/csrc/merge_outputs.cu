@@ -298,30 +298,31 @@ __global__ void __launch_bounds__(OTHREADS, MM_OUT_MIN_BLOCKS) outputs_kernel(co
 __global__ void __launch_bounds__(1024) packed_offsets_kernel(const uint32_t *__restrict__ einfo, const int32_t *__restrict__ n_agents,
                                                               int count, const int64_t *__restrict__ base_in,
                                                               int64_t *__restrict__ base_out, int64_t *__restrict__ base_out_host,
-                                                              int32_t *__restrict__ voff,
-                                                              int32_t *__restrict__ aoff, uint8_t *__restrict__ n_veh_u8,
-                                                              uint8_t *__restrict__ n_agents_u8) {
+                                                              int32_t *__restrict__ voff, int32_t *__restrict__ aoff,
+                                                              uint8_t *__restrict__ n_veh_u8, uint8_t *__restrict__ n_agents_u8) {
+    // One CTA, 32 warps; warp w owns the contiguous segment [w * seg, (w + 1) * seg) and walks it 32 envs at a time with
+    // coalesced loads and a warp scan.  Pass 1 sums the segments, the 32 sums are scanned, pass 2 writes the offsets.
+    // (The first version gave every thread a private run of 54 envs: strided loads and stores, 192 us per chunk, and the
+    // chunks' scans are chained - 3.6 ms of a 2^20-env step.)
     __shared__ int wv[32], wa[32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = (count + 1023) / 1024;
-    const int lo = min(tid * per, count), hi = min(lo + per, count);
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int seg = ((count + 31) / 32 + 31) / 32 * 32;
+    const int lo = min(warp * seg, count), hi = min(lo + seg, count);
     int sv = 0, sa = 0;
-    for (int e = lo; e < hi; ++e) {
+    for (int e = lo + lane; e < hi; e += 32) {
         sv += (int)((einfo[e] >> EI_NVEH_SHIFT) & EI_4BIT);
         sa += n_agents[e];
     }
-    int iv = sv, ia = sa;
-    for (int off = 1; off < 32; off <<= 1) {
-        const int a = __shfl_up_sync(0xffffffffu, iv, off), b = __shfl_up_sync(0xffffffffu, ia, off);
-        if (lane >= off) { iv += a; ia += b; }
-    }
-    if (lane == 31) { wv[warp] = iv; wa[warp] = ia; }
+    sv = __reduce_add_sync(full, sv);
+    sa = __reduce_add_sync(full, sa);
+    if (lane == 0) { wv[warp] = sv; wa[warp] = sa; }
     __syncthreads();
     if (warp == 0) {
         const int a = wv[lane], b = wa[lane];
         int xa = a, xb = b;
         for (int off = 1; off < 32; off <<= 1) {
-            const int u = __shfl_up_sync(0xffffffffu, xa, off), w = __shfl_up_sync(0xffffffffu, xb, off);
+            const int u = __shfl_up_sync(full, xa, off), w = __shfl_up_sync(full, xb, off);
             if (lane >= off) { xa += u; xb += w; }
         }
         wv[lane] = xa - a;
@@ -336,12 +337,27 @@ __global__ void __launch_bounds__(1024) packed_offsets_kernel(const uint32_t *__
         }
     }
     __syncthreads();
-    int rv = wv[warp] + (iv - sv), ra = wa[warp] + (ia - sa);
-    for (int e = lo; e < hi; ++e) {
-        const int nv = (int)((einfo[e] >> EI_NVEH_SHIFT) & EI_4BIT), na = n_agents[e];
-        voff[e] = rv; aoff[e] = ra;
-        n_veh_u8[e] = (uint8_t)nv; n_agents_u8[e] = (uint8_t)na;
-        rv += nv; ra += na;
+    int rv = wv[warp], ra = wa[warp];
+    for (int e0 = lo; e0 < hi; e0 += 32) {
+        const int e = e0 + lane;
+        int nv = 0, na = 0;
+        if (e < hi) {
+            nv = (int)((einfo[e] >> EI_NVEH_SHIFT) & EI_4BIT);
+            na = n_agents[e];
+        }
+        int iv = nv, ia = na;
+        for (int off = 1; off < 32; off <<= 1) {
+            const int u = __shfl_up_sync(full, iv, off), w = __shfl_up_sync(full, ia, off);
+            if (lane >= off) { iv += u; ia += w; }
+        }
+        if (e < hi) {
+            voff[e] = rv + iv - nv;
+            aoff[e] = ra + ia - na;
+            n_veh_u8[e] = (uint8_t)nv;
+            n_agents_u8[e] = (uint8_t)na;
+        }
+        rv += __shfl_sync(full, iv, 31);
+        ra += __shfl_sync(full, ia, 31);
     }
 }
 
