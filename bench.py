@@ -488,7 +488,7 @@ def main():
         pk_bytes = env.packed_bytes(pk_out)
         e2e["ragged"] = {"value": ragged_value, "d2h_bytes_per_step": e2e["d2h_bytes_per_step"], "api": e2e["api"]}
         e2e.update({"value": packed_value, "d2h_bytes_per_step": int(pk_bytes),
-                    "api": "mm_step_host_packed (pinned host buffers; per vehicle x, y, vx, vy, heading as f32 + per agent "
+                    "api": "mm_step_host_packed (pinned host buffers; per vehicle x, y, heading, speed as f32 + per agent "
                            "the slots of its 4 observed neighbours + ragged regional rewards: the observation rows are a "
                            "deterministic function of these, mm_expand_obs_rows builds them on the host)"})
         del pk_out

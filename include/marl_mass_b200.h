@@ -27,6 +27,7 @@ extern "C" {
 #define MM_OBS_FEATS 6      /* presence,x,y,vx,vy,heading (observation.py:232) */
 #define MM_NS 30            /* MergeEnvLCMARL.n_s (merge_env_v1.py:413) */
 #define MM_NA 5             /* n_a: LANE_LEFT, IDLE, LANE_RIGHT, FASTER, SLOWER (action.py:141-147) */
+#define MM_VEH_F32 4        /* floats per vehicle of the packed host path: x, y, heading, speed */
 
 typedef enum { MM_OK = 0, MM_ERR_ARG = -1, MM_ERR_CUDA = -2, MM_ERR_STATE = -3 } mm_status;
 
@@ -46,7 +47,7 @@ enum { MM_ACT_LEAD = 1, MM_ACT_UPPER = 2, MM_ACT_LOWER = 4, MM_ACT_ADJ = 8, MM_A
  * signature; mm_abi_version() returns the value the library was built with, and mm_create / mm_set_config reject a
  * config whose struct_size field is not sizeof(mm_config) (a binding built against another revision of the header
  * fails loudly instead of handing the library garbage). */
-#define MM_ABI_VERSION 7
+#define MM_ABI_VERSION 8
 int mm_abi_version(void);
 
 typedef struct {
@@ -168,15 +169,15 @@ int mm_step_host(mm_env *env, const int8_t *actions, int auto_reset, float *obs,
 int mm_step_host_ragged(mm_env *env, const int8_t *actions, int auto_reset, float *obs_rows, int64_t *row_offset,
                         float *reward, uint8_t *done, float *regional_rewards, int32_t *n_agents);
 /* The same step with the observation in PACKED form: instead of the [A, 30] rows, what they are a function of.
- *   veh     [sum n_veh][5] f32   x, y, vx, vy, heading of every vehicle, envs in order, slots in order (CAVs first)
+ *   veh     [sum n_veh][MM_VEH_F32] f32   x, y, heading, speed of every vehicle, envs in order, slots in order (CAVs first)
  *   nbr     [sum n_agents] u16   per agent: the slots of the (up to) 4 other vehicles its observation shows, 4 bits each in
  *                                row order (close_vehicles_to(count = 4), road.py:257-267), 0xF = that row is empty
  *   n_veh, n_agents [n_envs] u8  the counts; all offsets are their running sums (dense from the first env to the last)
  *   reward [n_envs] f32, done [n_envs] u8, regional_rewards [n_envs][MM_MAXV] f32 as in mm_step_host (nullable)
- * About 250 bytes per env-step at hard density against 1.1 KB for the packed rows of mm_step_host_ragged: the host path
+ * About 215 bytes per env-step at hard density against 1.1 KB for the packed rows of mm_step_host_ragged: the host path
  * is bound by PCIe and host memory, not by the kernels.  Row i of env e is rebuilt by mm_expand_obs_rows:
- * ego columns from veh[i], row k + 1 from veh[slot k of nbr] - veh[i] (observation.py:241-273, 181-193); inputs are
- * float32, so the rebuilt rows agree with mm_step_host's to ~2e-7 (float32 rounding of positions up to 450 m mapped onto
+ * ego columns from veh[i] (vx, vy = speed * cos / sin(heading), kinematics.py:215-217), row k + 1 from veh[slot k of nbr]
+ * - veh[i] (observation.py:241-273, 181-193); inputs are float32, so the rebuilt rows agree with mm_step_host's to ~2e-7 (float32 rounding of positions up to 450 m mapped onto
  * [-1, 1]), inside the 1e-4 tolerance of the path.  With auto_reset the packed state of a finished env is that of its next
  * episode (like obs), reward / done / regional_rewards describe the finished step.  veh needs room for n_envs * 11 rows,
  * nbr for n_envs * MM_MAXV entries (pinned memory for full PCIe speed). */

@@ -28,7 +28,7 @@ _PU8 = C.POINTER(C.c_uint8)
 _PI8 = C.POINTER(C.c_int8)
 
 
-ABI_VERSION = 7           # MM_ABI_VERSION of the header this binding was written against
+ABI_VERSION = 8           # MM_ABI_VERSION of the header this binding was written against
 
 
 class MMConfig(C.Structure):

@@ -552,9 +552,9 @@ int mm_step_host_packed(mm_env *env, const int8_t *actions, int auto_reset, cons
             return 0;
         };
         int rc = 0;
-        rc |= grab((void **)&env->out.veh, (size_t)E * MAXV * 5 * sizeof(float));
+        rc |= grab((void **)&env->out.veh, (size_t)E * MAXV * MM_VEH_F32 * sizeof(float));
         rc |= grab((void **)&env->out.nbr, (size_t)E * MAXV * sizeof(uint16_t));
-        rc |= grab((void **)&env->veh_packed, (size_t)E * MAXV * 5 * sizeof(float));
+        rc |= grab((void **)&env->veh_packed, (size_t)E * MAXV * MM_VEH_F32 * sizeof(float));
         rc |= grab((void **)&env->nbr_packed, (size_t)E * MAXV * sizeof(uint16_t));
         rc |= grab((void **)&env->voff, (size_t)E * sizeof(int32_t));
         rc |= grab((void **)&env->aoff, (size_t)E * sizeof(int32_t));
@@ -598,7 +598,7 @@ int mm_step_host_packed(mm_env *env, const int8_t *actions, int auto_reset, cons
                                 cudaMemcpyHostToDevice, s));
         enqueue_step(env, env->actions, auto_reset, off, count, s);
         if (c > 0) CUDA_OK(cudaStreamWaitEvent(s, env->scan_done[c - 1], 0));
-        launch_packed_pack(env->st.einfo + off, env->out.n_agents + off, env->out.veh + (size_t)off * MAXV * 5,
+        launch_packed_pack(env->st.einfo + off, env->out.n_agents + off, env->out.veh + (size_t)off * MAXV * MM_VEH_F32,
                            env->out.nbr + (size_t)off * MAXV, count, env->chunk_base_dev + 2 * c, env->chunk_base_dev + 2 * (c + 1),
                            env->chunk_base_host_dev + 2 * (c + 1), env->voff + off, env->aoff + off, env->veh_packed, env->nbr_packed, env->n_veh_u8 + off,
                            env->n_agents_u8 + off, s);
@@ -617,7 +617,7 @@ int mm_step_host_packed(mm_env *env, const int8_t *actions, int auto_reset, cons
         const int64_t v0 = env->chunk_base_host[2 * c], v1 = env->chunk_base_host[2 * (c + 1)];
         const int64_t a0 = env->chunk_base_host[2 * c + 1], a1 = env->chunk_base_host[2 * (c + 1) + 1];
         if (v1 > v0)
-            CUDA_OK(cudaMemcpyAsync(out->veh + v0 * 5, env->veh_packed + v0 * 5, (size_t)(v1 - v0) * 5 * sizeof(float),
+            CUDA_OK(cudaMemcpyAsync(out->veh + v0 * MM_VEH_F32, env->veh_packed + v0 * MM_VEH_F32, (size_t)(v1 - v0) * MM_VEH_F32 * sizeof(float),
                                     cudaMemcpyDeviceToHost, s));
         if (a1 > a0)
             CUDA_OK(cudaMemcpyAsync(out->nbr + a0, env->nbr_packed + a0, (size_t)(a1 - a0) * sizeof(uint16_t), cudaMemcpyDeviceToHost, s));
@@ -660,11 +660,18 @@ int mm_expand_obs_rows(const mm_packed_host *in, int n_envs, int steer_vel, floa
     const double KX = 2.0 / 300.0, KY = 2.0 / 24.0, KV = 2.0 / 90.0, KH = 2.0 / 3.141592653589793, HPI = 3.141592653589793 / 2;
     auto work = [&](int e0, int e1) {
         for (int e = e0; e < e1; ++e) {
-            const float *veh = in->veh + vbase[e] * 5;
+            const float *veh = in->veh + vbase[e] * MM_VEH_F32;
             const int n_cav = in->n_agents[e], n_veh = in->n_veh[e];
+            double vx[MM_MAXV], vy[MM_MAXV];                      // Vehicle.velocity = speed * [cos, sin](heading)
+            for (int j = 0; j < n_veh && j < MM_MAXV; ++j) {
+                const double h = veh[j * MM_VEH_F32 + 2], sp = veh[j * MM_VEH_F32 + 3];
+                vx[j] = sp * std::cos(h);
+                vy[j] = sp * std::sin(h);
+            }
             for (int i = 0; i < n_cav && i < n_veh; ++i) {
                 float *row = obs_rows + (row_offset[e] + i) * MM_NS;
-                const double ex = veh[i * 5], ey = veh[i * 5 + 1], evx = veh[i * 5 + 2], evy = veh[i * 5 + 3], eh = veh[i * 5 + 4];
+                const double ex = veh[i * MM_VEH_F32], ey = veh[i * MM_VEH_F32 + 1], eh = veh[i * MM_VEH_F32 + 2];
+                const double evx = vx[i], evy = vy[i];
                 row[0] = 1.0f; row[1] = (float)((ex + 150.0) * KX - 1.0); row[2] = (float)((ey + 12.0) * KY - 1.0);
                 row[3] = (float)((evx + 45.0) * KV - 1.0); row[4] = (float)((evy + 45.0) * KV - 1.0);
                 row[5] = (float)((eh + HPI) * KH - 1.0);
@@ -673,12 +680,12 @@ int mm_expand_obs_rows(const mm_packed_host *in, int n_envs, int steer_vel, floa
                     float *r = row + 6 * (k + 1);
                     const int o = (int)((w >> (4 * k)) & 15u);
                     if (o >= n_veh) { r[0] = r[1] = r[2] = r[3] = r[4] = r[5] = 0.f; continue; }
-                    const float *ov = veh + o * 5;
-                    double oh = ov[4];
+                    const float *ov = veh + o * MM_VEH_F32;
+                    double oh = ov[2];
                     if (steer_vel && o < n_cav) oh = oh - eh;
                     r[0] = 1.0f; r[1] = (float)(((double)ov[0] - ex + 150.0) * KX - 1.0);
-                    r[2] = (float)(((double)ov[1] - ey + 12.0) * KY - 1.0); r[3] = (float)(((double)ov[2] - evx + 45.0) * KV - 1.0);
-                    r[4] = (float)(((double)ov[3] - evy + 45.0) * KV - 1.0); r[5] = (float)((oh + HPI) * KH - 1.0);
+                    r[2] = (float)(((double)ov[1] - ey + 12.0) * KY - 1.0); r[3] = (float)((vx[o] - evx + 45.0) * KV - 1.0);
+                    r[4] = (float)((vy[o] - evy + 45.0) * KV - 1.0); r[5] = (float)((oh + HPI) * KH - 1.0);
                 }
             }
         }

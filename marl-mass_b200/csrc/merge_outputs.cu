@@ -120,12 +120,9 @@ __global__ void __launch_bounds__(OTHREADS, MM_OUT_MIN_BLOCKS) outputs_kernel(co
         }
         if (p.out.veh != nullptr && valid) {
             // packed-state outputs (mm_step_host_packed): what the observation rows are a function of
-            if (has_v) {
-                float *vr = p.out.veh + (e * MAXV + i) * 5;
-                const double sp = V(i);
-                __stcs(vr + 0, (float)X(i)); __stcs(vr + 1, (float)Y(i));
-                __stcs(vr + 2, (float)(sp * CH(i))); __stcs(vr + 3, (float)(sp * SH(i))); __stcs(vr + 4, (float)H(i));
-            }
+            if (has_v)      // one aligned 16-byte store per vehicle
+                __stcs(reinterpret_cast<float4 *>(p.out.veh) + (e * MAXV + i),
+                       make_float4((float)X(i), (float)Y(i), (float)H(i), (float)V(i)));
             p.out.nbr[e * MAXV + i] = (uint16_t)nbw;
             if (i == SMV - 1) p.out.nbr[e * MAXV + MAXV - 1] = 0xFFFFu;
         }
@@ -370,9 +367,9 @@ __global__ void __launch_bounds__(256) packed_copy_kernel(const float *__restric
     const int warps = (gridDim.x * blockDim.x) >> 5;
     const int64_t bv = base_in[0], ba = base_in[1];
     for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < count; e += warps) {
-        const int nf = (int)n_veh_u8[e] * 5;
-        const float *src = veh + (size_t)e * MAXV * 5;
-        float *dst = veh_packed + (bv + voff[e]) * 5;
+        const int nf = (int)n_veh_u8[e] * MM_VEH_F32;
+        const float *src = veh + (size_t)e * MAXV * MM_VEH_F32;
+        float *dst = veh_packed + (bv + voff[e]) * MM_VEH_F32;
         for (int k = lane; k < nf; k += 32) dst[k] = __ldcs(src + k);
         const int na = (int)n_agents_u8[e];
         if (lane < na) nbr_packed[ba + aoff[e] + lane] = nbr[(size_t)e * MAXV + lane];

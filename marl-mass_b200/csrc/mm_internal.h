@@ -68,8 +68,8 @@ struct DevOut {
           *merge_percent;
     uint8_t *done, *agents_dones, *action_mask;
     int32_t *n_agents;
-    // packed-state outputs (mm_step_host_packed; null until that path is first used): per vehicle x, y, vx, vy, heading
-    // as float32 [E][MAXV][5], and per agent the slots of its (up to) 4 observed neighbours, 4 bits each in observation
+    // packed-state outputs (mm_step_host_packed; null until that path is first used): per vehicle x, y, heading, speed
+    // as float32 [E][MAXV][MM_VEH_F32], and per agent the slots of its (up to) 4 observed neighbours, 4 bits each in observation
     // order, 0xF = none [E][MAXV]
     float *veh;
     uint16_t *nbr;

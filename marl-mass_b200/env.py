@@ -260,9 +260,9 @@ class MergeEnvBatched(object):
         return out
 
     def step_host_packed(self, actions, auto_reset=False, out=None):
-        """`step_host` with the observation in packed form (mm_step_host_packed): per vehicle x, y, vx, vy, heading
+        """`step_host` with the observation in packed form (mm_step_host_packed): per vehicle x, y, heading, speed
         (float32) and per agent the slots of the vehicles its observation rows show, plus reward / done / regional
-        rewards - about 250 bytes per env-step instead of 1.1 KB of observation rows.  out["veh"][V0:V0 + n_veh[e]] are
+        rewards - about 215 bytes per env-step instead of 1.1 KB of observation rows.  out["veh"][V0:V0 + n_veh[e]] are
         env e's vehicles (V0 = n_veh[:e].sum()), out["nbr"][A0:A0 + n_agents[e]] its agents' neighbour words.
         `expand_obs_rows(out)` rebuilds the [A, 30] rows on the host.  `out` comes from `alloc_host_out(packed=True)`."""
         a = actions if isinstance(actions, np.ndarray) else actions.numpy()
@@ -298,7 +298,7 @@ class MergeEnvBatched(object):
     def packed_bytes(self, out):
         """Device-to-host bytes of one mm_step_host_packed call that filled `out`."""
         E = self.n_envs
-        return (int(out["n_veh"].sum(dtype=np.int64)) * 20 + int(out["n_agents"].sum(dtype=np.int64)) * 2 +
+        return (int(out["n_veh"].sum(dtype=np.int64)) * 16 + int(out["n_agents"].sum(dtype=np.int64)) * 2 +
                 E * (1 + 1 + 4 + 1 + MAXV * 4))
 
     def alloc_host_out(self, pinned=True, ragged=False, packed=False):
@@ -306,7 +306,7 @@ class MergeEnvBatched(object):
         E = self.n_envs
         mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=pinned).numpy()
         if packed:
-            return {"veh": mk((E * 11, 5), torch.float32), "nbr": mk((E * MAXV,), torch.uint16),
+            return {"veh": mk((E * 11, 4), torch.float32), "nbr": mk((E * MAXV,), torch.uint16),
                     "n_veh": mk((E,), torch.uint8), "n_agents": mk((E,), torch.uint8), "reward": mk((E,), torch.float32),
                     "done": mk((E,), torch.uint8), "regional_rewards": mk((E, MAXV), torch.float32)}
         out = {"reward": mk((E,), torch.float32), "done": mk((E,), torch.uint8),

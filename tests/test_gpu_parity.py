@@ -493,7 +493,8 @@ def test_packed_host_step_expands_to_the_observation_rows(mm, traffic, lateral, 
         v0 = int(pk["n_veh"][:e].sum(dtype=np.int64))
         nv = int(st["n_veh"][e])
         assert np.allclose(pk["veh"][v0:v0 + nv, 0], st["x"][e, :nv].astype(np.float32), rtol=0, atol=0)
-        assert np.allclose(pk["veh"][v0:v0 + nv, 4], st["heading"][e, :nv].astype(np.float32), rtol=0, atol=0)
+        assert np.allclose(pk["veh"][v0:v0 + nv, 2], st["heading"][e, :nv].astype(np.float32), rtol=0, atol=0)
+        assert np.allclose(pk["veh"][v0:v0 + nv, 3], st["speed"][e, :nv].astype(np.float32), rtol=0, atol=0)
     assert n_done >= E    # every env finished a 10-step episode: re-spawned scenes went through the packed path
     # all-CAV: a fifth of the ragged path's bytes; with HDVs (state rows but no observation rows of their own) under half
     assert a_env.packed_bytes(pk) < (0.3 if traffic == "cav" else 0.5) * (int(rg["n_agents"].sum()) * 120 + E * 61)
