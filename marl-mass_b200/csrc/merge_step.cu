@@ -553,33 +553,40 @@ __global__ void unpack_state_kernel(DevState st, int n_envs, double *f64_em, int
 __global__ void __launch_bounds__(1024) ragged_offsets_kernel(const int32_t *__restrict__ n_agents, int count,
                                                               int64_t base_row, int64_t *__restrict__ row_offset,
                                                               int64_t *__restrict__ chunk_rows) {
+    // one CTA, 32 warps, each walking a contiguous segment 32 envs at a time: coalesced loads, warp scans (see
+    // packed_offsets_kernel in merge_outputs.cu; a private run of envs per thread cost 52 us per chunk)
     __shared__ int warp_sum[32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = (count + 1023) / 1024;
-    const int lo = min(tid * per, count), hi = min(lo + per, count);
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int seg = ((count + 31) / 32 + 31) / 32 * 32;
+    const int lo = min(warp * seg, count), hi = min(lo + seg, count);
     int sum = 0;
-    for (int e = lo; e < hi; ++e) sum += n_agents[e];
-    int incl = sum;
-    for (int off = 1; off < 32; off <<= 1) {
-        int v = __shfl_up_sync(0xffffffffu, incl, off);
-        if (lane >= off) incl += v;
-    }
-    if (lane == 31) warp_sum[warp] = incl;
+    for (int e = lo + lane; e < hi; e += 32) sum += n_agents[e];
+    sum = __reduce_add_sync(full, sum);
+    if (lane == 0) warp_sum[warp] = sum;
     __syncthreads();
     if (warp == 0) {
-        int w = warp_sum[lane], wi = w;
+        const int w = warp_sum[lane];
+        int wi = w;
         for (int off = 1; off < 32; off <<= 1) {
-            int v = __shfl_up_sync(0xffffffffu, wi, off);
+            const int v = __shfl_up_sync(full, wi, off);
             if (lane >= off) wi += v;
         }
         warp_sum[lane] = wi - w;   // exclusive
         if (lane == 31) *chunk_rows = wi;
     }
     __syncthreads();
-    int64_t run = base_row + warp_sum[warp] + (incl - sum);
-    for (int e = lo; e < hi; ++e) {
-        row_offset[e] = run;
-        run += n_agents[e];
+    int64_t run = base_row + warp_sum[warp];
+    for (int e0 = lo; e0 < hi; e0 += 32) {
+        const int e = e0 + lane;
+        const int n = e < hi ? n_agents[e] : 0;
+        int incl = n;
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(full, incl, off);
+            if (lane >= off) incl += v;
+        }
+        if (e < hi) row_offset[e] = run + incl - n;
+        run += __shfl_sync(full, incl, 31);
     }
 }
 
