@@ -18,6 +18,7 @@
 //     fragment order with the same permutation, so no shuffle or shared-memory round trip separates the layers.
 // Measured at 786 432 rows: torch layers 1.89 ms, mma.sync 0.20 ms, tcgen05 0.17 ms (profiles/README.md); this op is
 // ~33 GFLOP per step, so both are bound by their epilogues and staging, not by the tensor pipe.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <cstdlib>
@@ -745,6 +746,289 @@ actor_mlp_tcgen05_kernel(const float *__restrict__ obs, const int32_t *__restric
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------
+// tcgen05, third generation: one warpgroup per tile, four (H1 = 128) or three (H1 = 160) tiles in flight per SM
+// ------------------------------------------------------------------------------------------------
+// ncu on the two-CTA kernel above (profiles/r2_w_ncu_summary.txt): issue slots 33 % busy, 47 % of the stall samples on
+// the long scoreboard (mbarrier polls after each of the three MMAs, and the rollout-buffer store of a row right behind
+// its load, which made the prefetch synchronous), 1 400 thread-instructions per row of which the bias add + relu +
+// convert of the 256 hidden activations were two thirds.  Changes:
+//   * the weights sit in shared memory ONCE per SM and every warpgroup (128 threads = the 128 TMEM lanes = the 128 rows of
+//     a tile) runs its own tile pipeline on its own operand buffers, TMEM columns, named barrier and mbarrier: more
+//     tiles in flight per SM, no CTA-wide barrier;
+//   * biases ride in the MMAs: an extra K-step multiplies a constant block (1, 1, 0, ...) by (hi, lo) fp16 halves of the
+//     bias (layer 1 uses its two padding columns k = 30, 31), so the accumulator already holds D + b to ~2^-22;
+//   * the epilogue of a hidden layer is cvt.rn.relu.f16x2.f32 - one instruction per two activations - and a 16-byte
+//     shared store per eight;
+//   * D3 reuses the first 16 columns of the tile's TMEM region (D2 is dead once epilogue 2 has synchronised).
+template <int H1>
+struct M6 {
+    static constexpr int NWG = H1 == 128 ? 4 : 3;            // tiles in flight: shared memory (H1 = 160) or TMEM (128) bound
+    static constexpr int THREADS = 128 * NWG;
+    static constexpr int ROWS = 128;
+    static constexpr int CH1 = H1 / 8;
+    static constexpr uint32_t A_CHUNK = ROWS * 16;
+    static constexpr uint32_t W1_CHUNK = H1 * 16;
+    static constexpr uint32_t W3_CHUNK = 16 * 16;
+    static constexpr uint32_t W1 = 0;                             // [4 chunks][H1]: k = 30, 31 carry b1 (hi, lo)
+    static constexpr uint32_t W2 = W1 + 4 * W1_CHUNK;             // [CH1 + 2][128]: the last two chunks carry b2
+    static constexpr uint32_t W3 = W2 + (CH1 + 2) * A_CHUNK;      // [16 + 2][16]: the last two carry b3 and the value bias
+    static constexpr uint32_t ONES = W3 + 18 * W3_CHUNK;          // [2 chunks][128]: (1, 1, 0, ..., 0) per row
+    static constexpr uint32_t TILE0 = ONES + 2 * A_CHUNK;         // per warpgroup: A1 [4][128], A2 [CH1][128]
+    static constexpr uint32_t TILE_BYTES = (4 + CH1) * A_CHUNK;
+    static constexpr uint32_t BAR = TILE0 + NWG * TILE_BYTES;     // NWG mbarriers + the TMEM base address
+    static constexpr uint32_t SMEM = BAR + 8 * NWG + 16;
+    static constexpr uint32_t TMEM_COLS = 512;
+    static constexpr uint32_t REGION = H1;                        // TMEM columns per warpgroup
+    static constexpr uint32_t IDESC1 = (1u << 4) | ((uint32_t)(H1 >> 3) << 17) | ((128u >> 4) << 24);
+    static constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)(AC_HID >> 3) << 17) | ((128u >> 4) << 24);
+    static constexpr uint32_t IDESC3 = (1u << 4) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+};
+static_assert(M6<128>::SMEM <= 227 * 1024 && M6<160>::SMEM <= 227 * 1024, "actor kernel shared memory");
+static_assert(M6<128>::NWG * M6<128>::REGION <= 512 && M6<160>::NWG * M6<160>::REGION <= 512, "actor kernel TMEM columns");
+
+__device__ __forceinline__ uint32_t pack_relu_h2(uint32_t a_bits, uint32_t b_bits) {
+    uint32_t r;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(b_bits)), "f"(__uint_as_float(a_bits)));
+    return r;
+}
+__device__ __forceinline__ uint32_t hi_lo_h2(float b) {          // fp16 halves whose sum is b to ~2^-22
+    const __half hi = __float2half_rn(b), lo = __float2half_rn(b - __half2float(hi));
+    return (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
+}
+__device__ __forceinline__ void wg_sync(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
+
+template <int H1>
+__global__ void __launch_bounds__(M6<H1>::THREADS, 1)
+actor_mlp_wg_kernel(const float *__restrict__ obs, const int32_t *__restrict__ n_agents, int64_t n_rows,
+                    const float *__restrict__ w1, const float *__restrict__ b1, const float *__restrict__ w2,
+                    const float *__restrict__ b2, const float *__restrict__ w3, const float *__restrict__ b3,
+                    const float *__restrict__ wv, const float *__restrict__ bv, uint64_t seed, uint64_t step,
+                    const uint8_t *__restrict__ mask_bits, int8_t *__restrict__ actions, float *__restrict__ logp_all,
+                    float *__restrict__ logp_sel, float *__restrict__ values, float *__restrict__ obs_copy,
+                    uint8_t *__restrict__ live_out) {
+    using L = M6<H1>;
+    extern __shared__ __align__(128) uint8_t m6_sm[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, wg = warp >> 2;
+    uint4 *w1f = reinterpret_cast<uint4 *>(m6_sm + L::W1), *w2f = reinterpret_cast<uint4 *>(m6_sm + L::W2);
+    uint4 *w3f = reinterpret_cast<uint4 *>(m6_sm + L::W3), *ones = reinterpret_cast<uint4 *>(m6_sm + L::ONES);
+    uint4 *a1 = reinterpret_cast<uint4 *>(m6_sm + L::TILE0 + wg * L::TILE_BYTES), *a2 = a1 + 4 * L::ROWS;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(m6_sm + L::BAR);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(m6_sm + L::BAR + 8 * L::NWG);
+    const uint32_t bar = t5_smem(bars + wg);
+
+    // ---- one-time setup: weights and biases in operand layout (fp16), the constant block, barriers, TMEM ----
+    for (int idx = tid; idx < 4 * H1; idx += L::THREADS) {
+        const int c = idx / H1, n = idx % H1, k = 8 * c;
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = k + q < AC_IN ? w1[n * AC_IN + k + q] : 0.f;
+        uint4 o = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+        if (c == 3) o.w = hi_lo_h2(b1[n]);                            // k = 30, 31
+        w1f[idx] = o;
+    }
+    for (int idx = tid; idx < (L::CH1 + 2) * L::ROWS; idx += L::THREADS) {
+        const int c = idx / L::ROWS, n = idx % L::ROWS;
+        if (c < L::CH1) {
+            const float4 lo = *reinterpret_cast<const float4 *>(w2 + n * H1 + 8 * c), hi = *reinterpret_cast<const float4 *>(w2 + n * H1 + 8 * c + 4);
+            w2f[idx] = make_uint4(pack_h2(lo.x, lo.y), pack_h2(lo.z, lo.w), pack_h2(hi.x, hi.y), pack_h2(hi.z, hi.w));
+        } else {
+            w2f[idx] = make_uint4(c == L::CH1 ? hi_lo_h2(b2[n]) : 0u, 0u, 0u, 0u);
+        }
+    }
+    for (int idx = tid; idx < 18 * 16; idx += L::THREADS) {          // rows 0..4 logits, 5 the value head, rest zero
+        const int c = idx / 16, n = idx % 16;
+        if (c < 16) {
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = n < AC_OUT ? w3[n * AC_HID + 8 * c + q] : (n == AC_OUT && wv ? wv[8 * c + q] : 0.f);
+            w3f[idx] = make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+        } else {
+            const float b = n < AC_OUT ? b3[n] : (n == AC_OUT && bv ? bv[0] : 0.f);
+            w3f[idx] = make_uint4(c == 16 ? hi_lo_h2(b) : 0u, 0u, 0u, 0u);
+        }
+    }
+    for (int idx = tid; idx < 2 * L::ROWS; idx += L::THREADS) ones[idx] = make_uint4(idx < L::ROWS ? 0x3C003C00u : 0u, 0u, 0u, 0u);
+    if (tid < L::NWG) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(t5_smem(bars + tid)));
+    if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(t5_smem(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot + (uint32_t)wg * L::REGION;          // this warpgroup's columns
+    const uint32_t a1_addr = t5_smem(a1), a2_addr = t5_smem(a2), w1_addr = t5_smem(w1f), w2_addr = t5_smem(w2f);
+    const uint32_t w3_addr = t5_smem(w3f), ones_addr = t5_smem(ones);
+
+    const int r = tid & 127;                                              // row of the tile = TMEM lane
+    const uint32_t t_lane = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+    const int64_t n_tiles = (n_rows + L::ROWS - 1) / L::ROWS;
+    const int64_t stride = (int64_t)gridDim.x * L::NWG;
+    // observation rows: a tile is 128 x 30 floats = 960 contiguous float4 (row-per-thread loads touched 30 cache lines per
+    // request: 5.3 x the minimal sector count, L1 request stage 55 % busy - profiles/r2_x_*); thread r takes float4
+    // r, r + 128, ...: coalesced, and each float4 is two in-row pairs (30 and the flat index are even) -> two half2 stores
+    constexpr int TILE_F4 = L::ROWS * AC_IN / 4, PRE = (TILE_F4 + 127) / 128;
+    const int64_t total_f = n_rows * AC_IN;
+    float4 pre[PRE];
+    auto fetch = [&](int64_t tile) {
+#pragma unroll
+        for (int q = 0; q < PRE; ++q) {
+            const int i = r + 128 * q;
+            const int64_t g = tile * (L::ROWS * AC_IN) + 4 * i;                    // flat float index
+            pre[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < TILE_F4 && tile < n_tiles) {
+                if (g + 4 <= total_f) pre[q] = __ldg(reinterpret_cast<const float4 *>(obs + g));
+                else if (g + 2 <= total_f) { const float2 h = __ldg(reinterpret_cast<const float2 *>(obs + g)); pre[q].x = h.x; pre[q].y = h.y; }
+            }
+        }
+    };
+    uint32_t *a1w = reinterpret_cast<uint32_t *>(a1);
+    a1[3 * L::ROWS + r].w = 0x3C003C00u;                       // k = 30, 31: the constant 1 that multiplies b1 (never overwritten)
+    auto a1_word = [&](int f) {                                // 32-bit word of A1 that holds elements (f, f + 1) of the flat tile
+        const int row = f / AC_IN, col = f - AC_IN * row;
+        return ((col >> 3) * L::ROWS + row) * 4 + ((col & 7) >> 1);
+    };
+    // tile t belongs to warpgroup (t / gridDim.x) % NWG of CTA t % gridDim.x: a short batch spreads over the SMs first
+    int64_t tile = (int64_t)wg * gridDim.x + blockIdx.x;
+    fetch(tile);
+    uint32_t parity = 0;
+    for (; tile < n_tiles; tile += stride) {
+        // ---- stage the observation rows as fp16; rollout buffer (MAPPO.interact appends the state it acted on,
+        // mappo.py:117-131): the rows pass through here anyway - stored now, not behind the loads, so that the prefetch
+        // stays asynchronous ----
+#pragma unroll
+        for (int q = 0; q < PRE; ++q) {
+            const int i = r + 128 * q;
+            if (i < TILE_F4) {
+                a1w[a1_word(4 * i)] = pack_h2(pre[q].x, pre[q].y);
+                a1w[a1_word(4 * i + 2)] = pack_h2(pre[q].z, pre[q].w);
+                if (obs_copy) {
+                    const int64_t g = tile * (L::ROWS * AC_IN) + 4 * i;
+                    if (g + 4 <= total_f) __stcs(reinterpret_cast<float4 *>(obs_copy + g), pre[q]);
+                    else if (g + 2 <= total_f) __stcs(reinterpret_cast<float2 *>(obs_copy + g), make_float2(pre[q].x, pre[q].y));
+                }
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        wg_sync(wg);
+        if (r == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                m5_mma(tmem, m5_desc(a1_addr + j * 2 * L::A_CHUNK, L::A_CHUNK), m5_desc(w1_addr + j * 2 * L::W1_CHUNK, L::W1_CHUNK),
+                       L::IDESC1, j > 0);
+            t5_commit(bar);
+        }
+        fetch(tile + stride);                                  // next tile's rows: in flight during this tile's MMAs and epilogues
+        t5_wait(bar, parity); parity ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- epilogue 1: h1 = relu(D1) -> A2 ----
+#pragma unroll 1
+        for (int col = 0; col < H1; col += 32) {
+            uint32_t v[32];
+            t5_ld32(t_lane + (uint32_t)col, v);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                a2[(col / 8 + g) * L::ROWS + r] = make_uint4(pack_relu_h2(v[8 * g], v[8 * g + 1]), pack_relu_h2(v[8 * g + 2], v[8 * g + 3]),
+                                                            pack_relu_h2(v[8 * g + 4], v[8 * g + 5]), pack_relu_h2(v[8 * g + 6], v[8 * g + 7]));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        wg_sync(wg);
+        if (r == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < H1 / 16; ++j)
+                m5_mma(tmem, m5_desc(a2_addr + j * 2 * L::A_CHUNK, L::A_CHUNK), m5_desc(w2_addr + j * 2 * L::A_CHUNK, L::A_CHUNK),
+                       L::IDESC2, j > 0);
+            m5_mma(tmem, m5_desc(ones_addr, L::A_CHUNK), m5_desc(w2_addr + (H1 / 16) * 2 * L::A_CHUNK, L::A_CHUNK), L::IDESC2, 1);
+            t5_commit(bar);
+        }
+        t5_wait(bar, parity); parity ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- epilogue 2: h2 = relu(D2) -> the first 16 chunks of A2 (MMA2 has finished reading h1) ----
+#pragma unroll 1
+        for (int col = 0; col < AC_HID; col += 32) {
+            uint32_t v[32];
+            t5_ld32(t_lane + (uint32_t)col, v);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                a2[(col / 8 + g) * L::ROWS + r] = make_uint4(pack_relu_h2(v[8 * g], v[8 * g + 1]), pack_relu_h2(v[8 * g + 2], v[8 * g + 3]),
+                                                            pack_relu_h2(v[8 * g + 4], v[8 * g + 5]), pack_relu_h2(v[8 * g + 6], v[8 * g + 7]));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        wg_sync(wg);
+        // ---- output layer 128 -> 5 (+ value), N = 16, into the first columns of the region ----
+        if (r == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < AC_HID / 16; ++j)
+                m5_mma(tmem, m5_desc(a2_addr + j * 2 * L::A_CHUNK, L::A_CHUNK), m5_desc(w3_addr + j * 2 * L::W3_CHUNK, L::W3_CHUNK),
+                       L::IDESC3, j > 0);
+            m5_mma(tmem, m5_desc(ones_addr, L::A_CHUNK), m5_desc(w3_addr + 16 * L::W3_CHUNK, L::W3_CHUNK), L::IDESC3, 1);
+            t5_commit(bar);
+        }
+        t5_wait(bar, parity); parity ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {
+            const int64_t row = tile * L::ROWS + r;
+            uint32_t v[16];
+            m5_ld16(t_lane, v);
+            if (row < n_rows) {
+                float l[AC_OUT];
+#pragma unroll
+                for (int k = 0; k < AC_OUT; ++k) l[k] = __uint_as_float(v[k]);
+                if (values) values[row] = __uint_as_float(v[AC_OUT]);
+                apply_action_mask(l, mask_bits, row);
+                float m = l[0];
+#pragma unroll
+                for (int k = 1; k < AC_OUT; ++k) m = fmaxf(m, l[k]);
+                float e[AC_OUT], S = 0.f;
+#pragma unroll
+                for (int k = 0; k < AC_OUT; ++k) { e[k] = __expf(l[k] - m); S += e[k]; }
+                const float logS = __logf(S);
+                const float u = (float)(philox_row(seed, step, (uint64_t)row) >> 8) * (1.0f / 16777216.0f);
+                const float target = u * S;
+                int a = AC_OUT - 1;
+                float c = 0.f;
+                bool found = false;
+#pragma unroll
+                for (int k = 0; k < AC_OUT; ++k) {
+                    c += e[k];
+                    if (!found && target < c) { a = k; found = true; }
+                }
+                bool live = true;
+                if (n_agents) live = (int)(row % MAXV) < n_agents[row / MAXV];
+                actions[row] = (int8_t)(live ? a : 1);
+                if (live_out) live_out[row] = live ? 1 : 0;
+                if (logp_sel) logp_sel[row] = l[a] - m - logS;
+                if (logp_all) {
+#pragma unroll
+                    for (int k = 0; k < AC_OUT; ++k) logp_all[row * AC_OUT + k] = l[k] - m - logS;
+                }
+            }
+        }
+        // no barrier here: the next tile's first wg_sync orders these TMEM reads before its first MMA
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(*tmem_slot) : "memory");
+}
+
+// -1: not chosen yet; 0: tcgen05 fp16, a warpgroup per tile; 1: mma.sync TF32; 2: tcgen05 TF32, one CTA per SM; 3: tcgen05 fp16, two CTAs per SM
+int g_actor_impl = -1;
+void set_actor_impl(int impl) { g_actor_impl = (impl >= 1 && impl <= 3) ? impl : 0; }
+static void resolve_actor_impl() {
+    if (g_actor_impl >= 0) return;
+    const char *e = getenv("MM_ACTOR_IMPL");
+    g_actor_impl = !e ? 0 : (e[0] == 'm' ? 1 : (e[0] == 't' ? 2 : (e[0] == 'c' ? 3 : 0)));
+}
+
 template <int H1>
 static int launch_actor_mlp_t(const float *obs, const int32_t *n_agents, int64_t n_rows, const float *w1, const float *b1,
                               const float *w2, const float *b2, const float *w3, const float *b3, const float *wv, const float *bv,
@@ -759,6 +1043,19 @@ static int launch_actor_mlp_t(const float *obs, const int32_t *n_agents, int64_t
         ready[dev] = true;
     }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_actor_impl != 3) {                                       // default: one warpgroup per tile, one CTA per SM
+        static bool wg_ready[MM_MAX_DEVICES] = {};
+        if (!wg_ready[dev]) {
+            if (cudaFuncSetAttribute(actor_mlp_wg_kernel<H1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M6<H1>::SMEM) != cudaSuccess)
+                return 1;
+            wg_ready[dev] = true;
+        }
+        const int64_t n_tiles = (n_rows + 127) / 128, grid = n_tiles < sms ? n_tiles : sms;
+        actor_mlp_wg_kernel<H1><<<(unsigned)grid, M6<H1>::THREADS, M6<H1>::SMEM, (cudaStream_t)stream>>>(
+            obs, n_agents, n_rows, w1, b1, w2, b2, w3, b3, wv, bv, seed, step, mask_bits, actions, logp_all, logp_sel, values, obs_copy,
+            live_out);
+        return cudaGetLastError() == cudaSuccess ? 0 : 1;
+    }
     const int64_t tiles = (n_rows + 127) / 128, ctas = tiles < 2 * sms ? tiles : 2 * sms;   // persistent: two CTAs per SM
     actor_mlp_tcgen05_kernel<H1><<<(unsigned)ctas, 256, M5<H1>::SMEM, (cudaStream_t)stream>>>(
         obs, n_agents, n_rows, w1, b1, w2, b2, w3, b3, wv, bv, seed, step, mask_bits, actions, logp_all, logp_sel, values, obs_copy,
@@ -771,6 +1068,7 @@ int launch_actor_mlp(const float *obs, const int32_t *n_agents, int64_t n_rows, 
                      uint64_t seed, uint64_t step, const uint8_t *mask_bits, int8_t *actions, float *logp_all, float *logp_sel,
                      float *values, float *obs_copy, uint8_t *live_out, void *stream) {
     if (n_rows <= 0) return 0;
+    resolve_actor_impl();
     if (h1 == 128)
         return launch_actor_mlp_t<128>(obs, n_agents, n_rows, w1, b1, w2, b2, w3, b3, wv, bv, seed, step, mask_bits, actions, logp_all,
                                        logp_sel, values, obs_copy, live_out, stream);
@@ -809,8 +1107,6 @@ int launch_discounted_returns(const float *rewards, const uint8_t *dones, const 
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
-int g_actor_impl = -1;   // -1: not chosen yet; 0: tcgen05 fp16, two CTAs per SM; 1: mma.sync TF32; 2: tcgen05 TF32, one CTA per SM
-void set_actor_impl(int impl) { g_actor_impl = (impl == 1 || impl == 2) ? impl : 0; }
 
 int launch_actor_sample(const float *obs, const int32_t *n_agents, int64_t n_rows, const float *w1, const float *b1,
                         const float *w2, const float *b2, const float *w3, const float *b3, uint64_t seed, uint64_t step,
@@ -827,8 +1123,8 @@ int launch_actor_sample(const float *obs, const int32_t *n_agents, int64_t n_row
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // g_actor_impl (mm_set_actor_impl; initial value from MM_ACTOR_IMPL=mma): 1 selects the warp-level mma.sync kernel
     // above, kept as the independent cross-check of the tcgen05 one
-    if (g_actor_impl < 0) { const char *e = getenv("MM_ACTOR_IMPL"); g_actor_impl = (e && e[0] == 'm') ? 1 : ((e && e[0] == 't') ? 2 : 0); }
-    if (g_actor_impl == 0)
+    resolve_actor_impl();
+    if (g_actor_impl == 0 || g_actor_impl == 3)
         return launch_actor_mlp(obs, n_agents, n_rows, 128, w1, b1, w2, b2, w3, b3, nullptr, nullptr, seed, step, mask_bits, actions,
                                 logp_all, logp_sel, nullptr, nullptr, nullptr, stream);
     if (g_actor_impl == 2) {

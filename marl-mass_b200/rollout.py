@@ -172,9 +172,10 @@ def discounted_returns(rewards, dones, final_value, gamma):
 
 
 def set_actor_impl(name):
-    """'tcgen05' (default: fp16 operands, two CTAs per SM), 'mma' (the warp-level mma.sync TF32 kernel, kept as an
-    independent cross-check) or 'tcgen05_tf32' (the first tcgen05 kernel: TF32 operands, one CTA per SM)."""
-    _lib.check(_lib.lib().mm_set_actor_impl({"tcgen05": 0, "mma": 1, "tcgen05_tf32": 2}[name]))
+    """'tcgen05' (default: fp16 operands, a warpgroup per 128-row tile, weights once per SM), 'mma' (the warp-level
+    mma.sync TF32 kernel, kept as an independent cross-check), 'tcgen05_tf32' (the first tcgen05 kernel: TF32 operands,
+    one CTA per SM) or 'tcgen05_cta' (fp16 operands, two CTAs per SM: the default of the first half of round 2)."""
+    _lib.check(_lib.lib().mm_set_actor_impl({"tcgen05": 0, "mma": 1, "tcgen05_tf32": 2, "tcgen05_cta": 3}[name]))
 
 
 _DENSE_CACHE = {}

@@ -109,10 +109,10 @@ def test_tcgen05_and_mma_sync_actor_kernels_agree(mm):
     assert float((a_m != a_t).float().mean()) < 5e-3
 
 
-def test_all_three_actor_kernels_agree(mm):
-    """fp16 tcgen05 (default) vs TF32 tcgen05 vs TF32 mma.sync on the same network and rows: fp16 and TF32 operands share
-    the 10-bit mantissa, accumulation is fp32 everywhere -> log-probabilities within 1e-2, the same draw except next to
-    a CDF step."""
+def test_all_four_actor_kernels_agree(mm):
+    """fp16 tcgen05 (default: a warpgroup per tile, biases inside the MMAs; and the two-CTA build with fp32 bias adds) vs
+    TF32 tcgen05 vs TF32 mma.sync on the same network and rows: fp16 and TF32 operands share the 10-bit mantissa,
+    accumulation is fp32 everywhere -> log-probabilities within 1e-2, the same draw except next to a CDF step."""
     import torch
     from marl_mass_b200 import rollout
     torch.manual_seed(4)
@@ -120,7 +120,7 @@ def test_all_three_actor_kernels_agree(mm):
     obs = (torch.rand(70001, mm.NS, device="cuda") * 2.2 - 1.1).contiguous()
     out = {}
     try:
-        for name in ("tcgen05", "tcgen05_tf32", "mma"):
+        for name in ("tcgen05", "tcgen05_cta", "tcgen05_tf32", "mma"):
             rollout.set_actor_impl(name)
             out[name] = rollout.actor_sample(actor, obs, None, seed=9, step=1, want_logp=True)
             torch.cuda.synchronize()
@@ -130,6 +130,8 @@ def test_all_three_actor_kernels_agree(mm):
     for name, (a, lp) in out.items():
         assert float((lp - ref).abs().max()) < 1e-2, name
         assert float((a != out["tcgen05"][0]).float().mean()) < 5e-3, name
+    # the two fp16 builds round the same operands: only the bias path differs (hi + lo fp16 halves inside the MMA vs fp32 add)
+    assert float((out["tcgen05"][1] - out["tcgen05_cta"][1]).abs().max()) < 2e-3
 
 
 def test_fused_shared_network_of_mappo_gi(mm):
