@@ -188,11 +188,21 @@ __device__ __forceinline__ void flush_shield_counts(uint32_t shield_counts, doub
 #endif
 #define PHASE_BARRIER(level) do { if (MM_PHASE_SYNC >= (level)) __syncthreads(); } while (0)
 
-__device__ __forceinline__ int meta_action(uint32_t lo, uint32_t mid, uint32_t hi, int i) {
-    uint32_t w = i < 4 ? lo : (i < 8 ? mid : hi);
-    int a = (int)(int8_t)((w >> (8 * (i & 3))) & 0xffu);
-    return (a >= 0 && a <= 4) ? a : A_IDLE;
+// The 12 action bytes of an env as 12 nibbles (out-of-range bytes read as IDLE).  Packed right behind the loads, before
+// the sub-step loop: the loop then reads a register that is known to have arrived.  (Selecting from the three loaded
+// words inside the loop made ptxas wait there, every rank, on a scoreboard it shares with the two cold-field prefetches
+// issued just above - their L2 round trip, meant to overlap the steering law, was exposed: 3.4 % of the stall samples.)
+__device__ __forceinline__ uint64_t pack_actions(uint32_t lo, uint32_t mid, uint32_t hi) {
+    uint64_t acts = 0;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+        const uint32_t w = k < 4 ? lo : (k < 8 ? mid : hi);
+        const uint32_t b = (w >> (8 * (k & 3))) & 0xffu;
+        acts |= (uint64_t)(b <= 4u ? b : (uint32_t)A_IDLE) << (4 * k);
+    }
+    return acts;
 }
+__device__ __forceinline__ int meta_action(uint64_t acts, int i) { return (int)((acts >> (4 * i)) & 7u); }
 
 // DYN_RANKS: the rank loops run to the largest vehicle count of the CTA's envs instead of MAXV - 1.  Only worth a
 // second instantiation when the envs of a tile share their counts (mm_config.couple_counts); with independent counts
@@ -252,6 +262,7 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
         act_lo = a32[0]; act_mid = a32[1]; act_hi = a32[2];
     }
     if (MM_TMA) tile_bulk_load_wait(&s_mbar);
+    const uint64_t acts = pack_actions(act_lo, act_mid, act_hi);
     if (valid) {
         ev.n_veh = (ei >> EI_NVEH_SHIFT) & EI_4BIT;
         ev.n_cav = (ei >> EI_NCAV_SHIFT) & EI_4BIT;
@@ -293,7 +304,7 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
             if (apply_meta && !merged) {
                 for (int i = 0; i < ev.n_cav; ++i) {
                     double st_, ac_;
-                    cav_act(ev, i, meta_action(act_lo, act_mid, act_hi, i), sv, st_, ac_);
+                    cav_act(ev, i, meta_action(acts, i), sv, st_, ac_);
                 }
             }
             // road.py:277,286: stable sort by x, descending.  After the first sub-step the live order of the previous
@@ -344,7 +355,7 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
                 ge = GF(F_GVX, i);
                 if (merged) {
                     // sub-step 0 calls act(meta) and then act(None); the second call recomputes the same controls
-                    cav_act(ev, i, apply_meta ? meta_action(act_lo, act_mid, act_hi, i) : A_NONE, sv, st_, ac_);
+                    cav_act(ev, i, apply_meta ? meta_action(acts, i) : A_NONE, sv, st_, ac_);
                 } else {
                     st_ = GF(F_ACT_STEER, i);
                     ac_ = GF(F_ACT_ACC, i);
