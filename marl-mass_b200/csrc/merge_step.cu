@@ -74,6 +74,7 @@
 #ifndef MM_PW
 #define MM_PW MM_TILE
 #endif
+#define MM_TPE 1
 #include "mm_device.cuh"
 #include "mm_philox.cuh"
 
@@ -254,7 +255,12 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
     int steps = 0, time = 0;
     __shared__ uint64_t s_mbar;
     const size_t tile = ((size_t)p.env_offset + (size_t)blockIdx.x * BLOCK) / TILE;   // launches are tile-aligned
-    if (MM_TMA) tile_bulk_load_issue(p.st, tile, &s_mbar);
+    if (tid == 0) {
+        s_tile_g = p.st.f64 + tile * (size_t)F_COUNT * MAXV * TILE;
+        s_cfgd[0] = p.cfg.dt; s_cfgd[1] = p.cfg.eta; s_cfgd[2] = p.cfg.tau;
+    }
+    if (MM_TMA) tile_bulk_load_issue(p.st, tile, &s_mbar);   // (contains the CTA barrier that publishes the two above)
+    else __syncthreads();
     if (valid) {
         // env scalars and the 12 action bytes: requested while the tile is in flight
         ei = p.st.einfo[e];
@@ -639,6 +645,11 @@ struct ShieldQueryParams {
 __global__ void __launch_bounds__(BLOCK) shield_query_kernel(const __grid_constant__ ShieldQueryParams p) {
     const int tid = threadIdx.x;
     const int local = blockIdx.x * BLOCK + tid;
+    if (tid == 0) {                                   // MM_TPE: one CTA = one tile (BLOCK == TILE, env 0 starts a tile)
+        s_tile_g = p.st.f64 + (size_t)blockIdx.x * F_COUNT * MAXV * TILE;
+        s_cfgd[0] = p.cfg.dt; s_cfgd[1] = p.cfg.eta; s_cfgd[2] = p.cfg.tau;
+    }
+    __syncthreads();
     if (local >= p.n_envs) return;
     const size_t e = (size_t)local;
     Env ev;

@@ -84,6 +84,26 @@ constexpr double VLEN_SQ_GT = 0x1.9000000000001p+4;
 constexpr int SMV = 11;
 constexpr int PLANES_F64 = N_HOT * SMV * BLOCK + (SMV + 1) * BLOCK / 2;   // doubles: hot f64 planes + the u32 flags plane
 extern __shared__ __align__(16) double sm_planes[];   // [N_HOT][SMV][BLOCK] f64 + [SMV+1][BLOCK] u32
+// MM_TPE (thread-per-env kernels: one CTA = one tile, thread t = env column t): the column index, the tile base and the
+// shield's three configuration doubles are read from threadIdx / static shared memory instead of through `Env &` and
+// `const mm_config &`.  Both live in the kernel's stack frame / parameter space; out-of-line functions reached them with
+// local-memory and generic loads that miss the L1 (28 KB next to 221 KB of shared memory) - ncu: ~4 % of the step
+// kernel's stall samples behind five such loads per vehicle step.
+#ifdef MM_TPE
+__shared__ double *s_tile_g;
+__shared__ double s_cfgd[3];                  // dt, eta, tau
+#define EV_TID ((int)threadIdx.x)
+#define EV_G (s_tile_g + threadIdx.x)
+#define CFG_DT(cfg) (s_cfgd[0])
+#define CFG_ETA(cfg) (s_cfgd[1])
+#define CFG_TAU(cfg) (s_cfgd[2])
+#else
+#define EV_TID (ev.tid)
+#define EV_G (ev.g)
+#define CFG_DT(cfg) ((cfg).dt)
+#define CFG_ETA(cfg) ((cfg).eta)
+#define CFG_TAU(cfg) ((cfg).tau)
+#endif
 struct Env {
     int tid;                    // threadIdx.x: column of this env inside the CTA's planes
     double *g;                  // this env's column of its tile; element (f, i) at [(f*MAXV+i)*TILE]
@@ -93,7 +113,7 @@ struct Env {
 };
 __device__ __forceinline__ int nib(uint64_t w, int k) { return (int)((w >> (4 * k)) & 15ull); }
 
-#define SMF(f, i) (sm_planes[((f) * SMV + (i)) * BLOCK + ev.tid])
+#define SMF(f, i) (sm_planes[((f) * SMV + (i)) * BLOCK + EV_TID])
 #define X(i) SMF(F_X, i)
 #define Y(i) SMF(F_Y, i)
 #define H(i) SMF(F_H, i)
@@ -105,8 +125,8 @@ __device__ __forceinline__ int nib(uint64_t w, int k) { return (int)((w >> (4 * 
 #define CH(i) GF(F_COSH, i)
 #define SH(i) GF(F_SINH, i)
 #endif
-#define FL(i) (reinterpret_cast<uint32_t *>(sm_planes + N_HOT * SMV * BLOCK)[(i) * BLOCK + ev.tid])
-#define GF(f, i) (*tile_ptr(ev.g, (f), (i)))
+#define FL(i) (reinterpret_cast<uint32_t *>(sm_planes + N_HOT * SMV * BLOCK)[(i) * BLOCK + EV_TID])
+#define GF(f, i) (*tile_ptr(EV_G, (f), (i)))
 
 __device__ __forceinline__ double *tile_ptr(double *col, int f, int i) {
     double *q = col + ((f) * MAXV + (i)) * TILE;
@@ -579,11 +599,11 @@ __device__ __forceinline__ int close_vehicles(const Env &ev, int self, uint32_t 
 template <bool WITH_MARGIN, bool QUERY = false>
 __device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, double act_steer, double act_acc, double rec1vx,
                                     double ge, double &out_steer, double &out_acc, ShieldRec &rec) {
-    const double dt = cfg.dt, eta = cfg.eta, tau = cfg.tau;
+    const double dt = CFG_DT(cfg), eta = CFG_ETA(cfg), tau = CFG_TAU(cfg);
     const bool mass = CFG_SHIELD(cfg) == MM_SHIELD_MASS;
-    // `ev` lives in the caller's stack frame: read the tile base now, so that the record fetch below does not start with a
-    // local-memory load in front of its address arithmetic (ncu: 1.4 % of the kernel's stall samples at that one wait)
-    double *const gbase = ev.g;
+    // read the tile base now, so that the record fetch below does not start with a load in front of its address
+    // arithmetic (ncu: 1.4 % of the kernel's stall samples at that one wait)
+    double *const gbase = EV_G;
 #define GQ(f, i) (*tile_ptr(gbase, (f), (i)))
     uint32_t f = FL(self);
     const int elane = fl_lane(f);
