@@ -75,6 +75,11 @@
 #define MM_PW MM_TILE
 #endif
 #define MM_TPE 1
+// one call site per kernel: inline, the shield reads the env's order words and counts from the caller's registers (as an
+// out-of-line function it took them through the stack: 152 -> 140 registers, 144 -> 48 bytes of stack in the MASS build)
+#ifndef MM_SHIELD_FN
+#define MM_SHIELD_FN __forceinline__
+#endif
 #include "mm_device.cuh"
 #include "mm_philox.cuh"
 

@@ -596,8 +596,11 @@ __device__ __forceinline__ int close_vehicles(const Env &ev, int self, uint32_t 
 // has them in registers already).  WITH_MARGIN: also report the veto margin (diagnostic builds only).
 // QUERY: evaluate only (mm_shield_query) - nothing outside the caller's shared-memory copy of the scene is written: the
 // min_headway field and the in-place shift of an on-ramp HDV's record stay local.
+#ifndef MM_SHIELD_FN
+#define MM_SHIELD_FN __noinline__
+#endif
 template <bool WITH_MARGIN, bool QUERY = false>
-__device__ __noinline__ void shield(Env &ev, const mm_config &cfg, int self, double act_steer, double act_acc, double rec1vx,
+__device__ MM_SHIELD_FN void shield(Env &ev, const mm_config &cfg, int self, double act_steer, double act_acc, double rec1vx,
                                     double ge, double &out_steer, double &out_acc, ShieldRec &rec) {
     const double dt = CFG_DT(cfg), eta = CFG_ETA(cfg), tau = CFG_TAU(cfg);
     const bool mass = CFG_SHIELD(cfg) == MM_SHIELD_MASS;
