@@ -80,6 +80,18 @@
 #ifndef MM_SHIELD_FN
 #define MM_SHIELD_FN __forceinline__
 #endif
+// likewise the steering law and the libdevice trigonometry (same code, same bits: only the call, its argument moves
+// and the convergence barriers around it go): 8.02 -> 7.75 ms per 2^20-env step; tan / atan / asin stay calls in the
+// generic builds, which measured 2 % faster that way with HDVs present (profiles/r2_z_ab_inline*.txt)
+#ifndef MM_STEER_FN
+#define MM_STEER_FN __forceinline__
+#endif
+#ifndef MM_TRIG_FN
+#define MM_TRIG_FN __forceinline__
+#endif
+#if !defined(MM_TRIG1_FN) && defined(MM_SPEC_SHIELD)
+#define MM_TRIG1_FN __forceinline__
+#endif
 #include "mm_device.cuh"
 #include "mm_philox.cuh"
 

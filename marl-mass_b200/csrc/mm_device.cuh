@@ -149,12 +149,18 @@ __device__ __forceinline__ uint32_t fl_set(uint32_t f, uint32_t shift, uint32_t 
 // 233 KB of SASS and instruction-cache misses its top stall (profiles/r1_v1_*); as out-of-line functions
 // the whole kernel is a fraction of that.  Same libdevice code, same bits.
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ double m_sin(double x) { return sin(x); }
-__device__ __noinline__ double m_cos(double x) { return cos(x); }
-__device__ __noinline__ double2 m_sincos(double x) { double2 r; sincos(x, &r.x, &r.y); return r; }
-__device__ __noinline__ double m_tan(double x) { return tan(x); }
-__device__ __noinline__ double m_atan(double x) { return atan(x); }
-__device__ __noinline__ double m_asin(double x) { return asin(x); }
+#ifndef MM_TRIG_FN
+#define MM_TRIG_FN __noinline__
+#endif
+#ifndef MM_TRIG1_FN
+#define MM_TRIG1_FN __noinline__
+#endif
+__device__ MM_TRIG_FN double m_sin(double x) { return sin(x); }
+__device__ MM_TRIG_FN double m_cos(double x) { return cos(x); }
+__device__ MM_TRIG_FN double2 m_sincos(double x) { double2 r; sincos(x, &r.x, &r.y); return r; }
+__device__ MM_TRIG1_FN double m_tan(double x) { return tan(x); }
+__device__ MM_TRIG1_FN double m_atan(double x) { return atan(x); }
+__device__ MM_TRIG1_FN double m_asin(double x) { return asin(x); }
 __device__ __noinline__ double m_exp(double x) { return exp(x); }
 __device__ __noinline__ double m_log(double x) { return log(x); }
 __device__ __noinline__ double m_pow(double x, double y) { return pow(x, y); }
@@ -244,7 +250,10 @@ __device__ MM_INL_A int closest_lane(double px, double py, double heading) {
 }
 
 // controller.py:146-187
-__device__ __noinline__ double steering_control(double px, double py, double heading, double speed, int tlane) {
+#ifndef MM_STEER_FN
+#define MM_STEER_FN __noinline__
+#endif
+__device__ MM_STEER_FN double steering_control(double px, double py, double heading, double speed, int tlane) {
     double s = lane_s(tlane, px);
     double r = lane_r(tlane, s, py);
     double future_heading = lane_heading_at(tlane, s + speed * PURSUIT_TAU);

@@ -63,7 +63,7 @@ for r, loc in zip(data, lines_of):
     fn = func_at.get(loc, "?") if loc else "?"
     for key, tab in ((fn, byf), (loc, byl)):
         c = tab[key]
-        c["smp"] += s; c["inst"] += i; c["thr"] += t
+        c["smp"] += s; c["inst"] += i; c["thr"] += t; c["code"] += 1
         for st in stalls:
             c[st] += int(r[idx[st]])
 print("kernel %s\nsamples %d warp-inst %d lanes %.1f" % (kname, S, I, T / max(I, 1)))
@@ -74,7 +74,7 @@ for c in byf.values():
 print(" ".join("%s %.1f%%" % (k[6:], 100.0 * v / S) for k, v in tot.most_common(8)))
 for name, c in sorted(byf.items(), key=lambda kv: -kv[1]["smp"])[:top]:
     ts = sorted(((c[st], st[6:]) for st in stalls), reverse=True)[:3]
-    print("%-26s smp %5.1f%% inst %5.1f%% lanes %4.1f  %s" % (name, 100.0 * c["smp"] / S, 100.0 * c["inst"] / I, c["thr"] / max(c["inst"], 1),
+    print("%-26s smp %5.1f%% inst %5.1f%% lanes %4.1f code %5d  %s" % (name, 100.0 * c["smp"] / S, 100.0 * c["inst"] / I, c["thr"] / max(c["inst"], 1), c["code"],
                                                          " ".join("%s=%d%%" % (n, 100 * v / max(c["smp"], 1)) for v, n in ts)))
 print("--- hottest source lines")
 for loc, c in sorted(byl.items(), key=lambda kv: -kv[1]["smp"])[:top]:
