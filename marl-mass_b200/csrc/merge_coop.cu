@@ -75,7 +75,7 @@ __device__ __forceinline__ Geom move_geom(double x, double y, double h, double v
     double c_hb = ch * g.cb - sh * g.sb, s_hb = sh * g.cb + ch * g.sb;
     g.nx = x + v * c_hb * dt;
     g.ny = y + v * s_hb * dt;
-    g.nh = h + v * g.sb / (VLEN / 2) * dt;
+    g.nh = h + div_nz(v * g.sb, VLEN / 2) * dt;
     double2 scn = m_sincos(g.nh);
     g.ncos = scn.y;
     g.nsin = scn.x;

@@ -174,6 +174,18 @@ __device__ __forceinline__ double not_zero(double x) {
     return x > 0 ? 1e-2 : -1e-2;
 }
 __device__ __forceinline__ double clipd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+// x / y for a finite y != 0 where x is often exactly zero (a vehicle on its lane's centre line, a zero steering angle).
+// CUDA's f64 division checks its fast result against the normal range and otherwise calls a ~90-instruction slow path;
+// a zero quotient fails that check, and with it every warp that held one such lane took the call (ncu: 4.1 % of the step
+// kernel's instructions).  +-0 / y is +-0 with the product's sign, which x * y delivers; the division itself always sees
+// a non-zero numerator.  Same bits as the plain division.
+__device__ __forceinline__ double div_nz(double x, double y) {
+    const bool z = x == 0.0;
+    double num = z ? 1.0 : x;
+    asm("" : "+d"(num));            // opaque: otherwise the compiler folds the two selects back into a plain x / y
+    const double q = num / y;
+    return z ? x * y : q;
+}
 // Python's floored float modulo by a positive modulus
 __device__ __forceinline__ double pymod_pos(double a, double b) {
     if (a >= 0 && a < b) return a;  // fmod(a, b) == a exactly when 0 <= a < b: skip the (iterative) fmod
@@ -259,7 +271,7 @@ __device__ MM_STEER_FN double steering_control(double px, double py, double head
     double future_heading = lane_heading_at(tlane, s + speed * PURSUIT_TAU);
     double lat_cmd = -KP_LATERAL * r;
     double nz = not_zero(speed);
-    double heading_cmd = m_asin(clipd(lat_cmd / nz, -1.0, 1.0));
+    double heading_cmd = m_asin(clipd(div_nz(lat_cmd, nz), -1.0, 1.0));
     double heading_ref = future_heading + clipd(heading_cmd, -PI / 4, PI / 4);
     double rate_cmd = KP_HEADING * wrap_to_pi(heading_ref - heading);
     double steering = m_asin(clipd(VLEN / 2 / nz * rate_cmd, -1.0, 1.0));
@@ -937,7 +949,7 @@ __device__ void vehicle_step(Env &ev, const StepParams &p, int i, int sub, size_
     double c_hb = ch * cb - sh * sb, s_hb = sh * cb + ch * sb;  // cos / sin (heading + beta)
     double nx = X(i) + speed * c_hb * dt;
     double ny = Y(i) + speed * s_hb * dt;
-    double nh = sv ? heading + speed * sb / (VLEN / 2) : heading + speed * sb / (VLEN / 2) * dt;
+    double nh = sv ? heading + div_nz(speed * sb, VLEN / 2) : heading + div_nz(speed * sb, VLEN / 2) * dt;
     double nv = fmax(0.0, speed + acc * dt);
     double2 scn = m_sincos(nh);
     if (cav) {
