@@ -86,6 +86,9 @@
 #ifndef MM_STEER_FN
 #define MM_STEER_FN __forceinline__
 #endif
+#ifndef MM_HDV_FN            // IDM / MOBIL helpers (they took `Env &`): mixed traffic 0.905 -> 0.783 ms at 65 536 envs
+#define MM_HDV_FN __forceinline__
+#endif
 #ifndef MM_TRIG_FN
 #define MM_TRIG_FN __forceinline__
 #endif
@@ -203,6 +206,9 @@ __device__ __forceinline__ void flush_shield_counts(uint32_t shield_counts, doub
 #endif
 #ifndef MM_SORT_LANES
 #define MM_SORT_LANES 0   // measured: < 1 % (profiles/README.md); kept as an experiment knob
+#endif
+#ifndef MM_RANK_BARRIER_STRIDE
+#define MM_RANK_BARRIER_STRIDE 1   // experiment knob: a barrier every n-th rank of the step loop
 #endif
 #define PHASE_BARRIER(level) do { if (MM_PHASE_SYNC >= (level)) __syncthreads(); } while (0)
 
@@ -367,7 +373,7 @@ __global__ void __launch_bounds__(BLOCK, MM_MIN_BLOCKS) step_kernel(const __grid
         }
 #pragma unroll 1
         for (int q = 0; q < (MM_PHASE_SYNC >= 2 ? n_rank : n_live); ++q) {  // road.step(dt): same order
-            PHASE_BARRIER(2);
+            if (MM_RANK_BARRIER_STRIDE == 1 || q % MM_RANK_BARRIER_STRIDE == 0) PHASE_BARRIER(2);
             int i = 0;
             double rec1vx = 0, ge = 0, st_ = 0, ac_ = 0;
             if (q < n_live) {

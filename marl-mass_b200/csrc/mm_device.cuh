@@ -149,6 +149,9 @@ __device__ __forceinline__ uint32_t fl_set(uint32_t f, uint32_t shift, uint32_t 
 // 233 KB of SASS and instruction-cache misses its top stall (profiles/r1_v1_*); as out-of-line functions
 // the whole kernel is a fraction of that.  Same libdevice code, same bits.
 // ------------------------------------------------------------------------------------------------
+#ifndef MM_HDV_FN
+#define MM_HDV_FN __noinline__   // the IDM / MOBIL helpers (generic builds only)
+#endif
 #ifndef MM_TRIG_FN
 #define MM_TRIG_FN __noinline__
 #endif
@@ -326,7 +329,7 @@ __device__ __forceinline__ void ent_pos(const Env &ev, int id, double &px, doubl
 }
 
 // road.py:352-381 (candidates: vehicles in list order, then the obstacle): the exhaustive scan, kept for the tie cases
-__device__ __noinline__ void neighbour_vehicles_scan(const Env &ev, int self, int lane, int &front, int &rear) {
+__device__ MM_HDV_FN void neighbour_vehicles_scan(const Env &ev, int self, int lane, int &front, int &rear) {
     double s = lane_s(lane, X(self)), s_front = 0, s_rear = 0;
     front = -1;
     rear = -1;
@@ -349,7 +352,7 @@ __device__ __noinline__ void neighbour_vehicles_scan(const Env &ev, int self, in
 // (s = 100, r = 0; every other lane fails on_lane), where it competes by its s like a vehicle and, being last in the
 // candidate list, wins ties for the front place.  Equal longitudinal positions between vehicles are where list order
 // decides: any such equality on the way defers to the scan.
-__device__ __noinline__ void neighbour_vehicles(const Env &ev, int self, int lane, int &front, int &rear) {
+__device__ MM_HDV_FN void neighbour_vehicles(const Env &ev, int self, int lane, int &front, int &rear) {
     const uint64_t live = ev.live;
     const int ps = nib(ev.pos, self);
     const double s = lane_s(lane, X(self)), hi = c_lane_len[lane] + VLEN;
@@ -389,7 +392,7 @@ __device__ __noinline__ void neighbour_vehicles(const Env &ev, int self, int lan
 }
 
 // behavior.py:141-156
-__device__ __noinline__ double desired_gap(const Env &ev, int ego, int front) {
+__device__ MM_HDV_FN double desired_gap(const Env &ev, int ego, int front) {
     double fvx = 0, fvy = 0;
     if (front != OBST) {
         fvx = V(front) * CH(front);
@@ -401,7 +404,7 @@ __device__ __noinline__ double desired_gap(const Env &ev, int ego, int front) {
 }
 
 // behavior.py:111-139 (ego/front: -1 None, OBST obstacle)
-__device__ __noinline__ double idm_acc(const Env &ev, int ego, int front) {
+__device__ MM_HDV_FN double idm_acc(const Env &ev, int ego, int front) {
     if (ego < 0 || ego == OBST) return 0.0;
     double acc = 3.0 * (1 - m_pow(fmax(V(ego), 0.0) / not_zero(GF(F_TSPEED, ego)), 4.0));
     if (front >= 0) {
@@ -416,7 +419,7 @@ __device__ __noinline__ double idm_acc(const Env &ev, int ego, int front) {
 }
 
 // behavior.py:186-266 (route None, POLITENESS 0: the follower terms enter the jerk with weight 0.0)
-__device__ __noinline__ int hdv_change_lane(Env &ev, int self, uint32_t f, int tl) {
+__device__ MM_HDV_FN int hdv_change_lane(Env &ev, int self, uint32_t f, int tl) {
     int lane = fl_lane(f);
     if (lane != tl) {
         if (lane_road(lane) == lane_road(tl)) {
@@ -454,7 +457,7 @@ __device__ __noinline__ int hdv_change_lane(Env &ev, int self, uint32_t f, int t
 }
 
 // behavior.py:74-100
-__device__ __noinline__ void hdv_act(Env &ev, int i) {
+__device__ MM_HDV_FN void hdv_act(Env &ev, int i) {
     uint32_t f = FL(i);
     if (f & FL_CRASHED) return;
     int front, rear;
