@@ -5,7 +5,7 @@ MM_SOAK_ENVS (default 4096) sets the batch; one snapped round at 1024 envs is pa
 automatic (specialised builds where they apply), generic 3 / 4 CTAs per SM, warp-cooperative (where it applies)."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests"), os.path.join(ROOT, "profiles")):
     sys.path.insert(0, p)
 import numpy as np
 import torch
@@ -13,10 +13,8 @@ import marl_mass_b200 as mm
 import oracle as orc
 from helpers import F64_FIELDS, I32_FIELDS, ENV_FIELDS, OUT_I, rel_err, used_mask, LC_BOUNDARY_EPS, SH_I
 
-CASES = [("cbf-cav", "cav", 3, "default", "steer"), ("cbf-cav", "mixed", 3, "srew", "steer"), ("cbf-avs_cint", "cav", 3, "default", "steer"),
-         ("cbf-avs_cint", "mixed", 2, "mrew", "steer"), ("none", "mixed", 1, "default", "steer"), ("cbf-cav", "cav", 1, "mrew", "steer"),
-         ("cbf-cav", "mixed", 3, "default", "steer_vel"), ("cbf-cav", "cav", 2, "srew", "steer"), ("cbf-avs_cint", "mixed", 3, "default", "steer_vel"),
-         ("cbf-cav", "av", 3, "default", "steer"), ("cbf-avs_cint", "av", 2, "srew", "steer")]
+from soak_cases import CASES
+
 rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 first_round = int(sys.argv[2]) if len(sys.argv) > 2 else 0      # seeds depend on the round index
 # "snap": before every policy step x -> 0.5 m grid, y -> 0.5 m grid, speed -> 2.5 m/s grid (odd steps) or integers (even
