@@ -11,7 +11,7 @@ import numpy as np
 import torch
 import marl_mass_b200 as mm
 import oracle as orc
-from helpers import F64_FIELDS, I32_FIELDS, ENV_FIELDS, OUT_I, rel_err, used_mask, LC_BOUNDARY_EPS, SH_I
+from helpers import F64_FIELDS, I32_FIELDS, ENV_FIELDS, OUT_I, rel_err, used_mask, LC_BOUNDARY_EPS, SH_I, near_tie_inside_step
 
 from soak_cases import CASES
 
@@ -22,7 +22,7 @@ first_round = int(sys.argv[2]) if len(sys.argv) > 2 else 0      # seeds depend o
 # fixtures of tests/golden at scale); the comparison is then per step (teacher-forced from the oracle's state)
 snap = len(sys.argv) > 3 and sys.argv[3] == "snap"
 E, T = int(os.environ.get("MM_SOAK_ENVS", "4096")), 100
-total_env_steps, boundary = 0, 0
+total_env_steps, boundary, ulp_ties = 0, 0, 0
 t0 = time.time()
 for rnd in range(first_round, first_round + rounds):
     mm.set_step_variant((0, 4, 7, 3)[rnd % 4])                  # which build of the step kernel this round exercises
@@ -46,6 +46,7 @@ for rnd in range(first_round, first_round + rounds):
                 st["rec1_vx"] = np.where(h1, st["speed"] * np.cos(st["heading"]), st["rec1_vx"])
                 env.set_state(st)
             a = rng.randint(0, 5, size=(E, 12)).astype(np.int8)
+            pre = {k: np.array(v, copy=True) for k, v in st.items()}
             want = orc.step(ocfg, st, a, n_threads=16)
             _, _, _, v = env.step(torch.from_numpy(a).cuda())
             post = env.get_state()
@@ -69,13 +70,22 @@ for rnd in range(first_round, first_round + rounds):
             ran = (want["sh_ran"] == 1) & sel[:, None, None]
             bnd = ran & (diag["lc_margin"] < LC_BOUNDARY_EPS)
             boundary += int(bnd.sum())
+            tied = np.zeros(E, bool)
             for k in SH_I:
                 bad = (diag[k] != want["sh_" + k]) & ran & ~bnd
-                assert not bad.any(), (shield, traffic, td, t, "shield", k, np.argwhere(bad)[:4].tolist())
+                for e in np.unique(np.argwhere(bad)[:, 0]):
+                    assert near_tie_inside_step(orc, ocfg, pre, int(e), a), (shield, traffic, td, t, "shield", k, np.argwhere(bad)[:4].tolist())
+                    tied[e] = True
+            if tied.any():
+                ulp_ties += int(tied.sum())
+                print("  round %d case %d step %d: env(s) %s end a sub-step within 4 ulp of a tie in x (libdevice vs glibc "
+                      "trigonometry): dropped from the rest of the episode" % (rnd, ci, t, np.flatnonzero(tied).tolist()), flush=True)
+                clean &= ~tied
             total_env_steps += int(sel.sum())
             alive &= want["done"] == 0
             clean &= ~((st["speed"] < 3.0) & used_mask(st)).any(axis=1)
         env.close()
         print("round %d %-13s %-6s td%d %-8s %-9s ok  (%.0f s, %d env-steps compared so far, %d veto-boundary solves)" % (
             rnd, shield, traffic, td, reward, lateral, time.time() - t0, total_env_steps, boundary), flush=True)
-print("SOAK OK", total_env_steps, "env-steps", "(snapped: exact ties / boundary values)" if snap else "")
+print("SOAK OK", total_env_steps, "env-steps", "(snapped: exact ties / boundary values)" if snap else "",
+      "| sub-step ulp ties dropped:", ulp_ties)

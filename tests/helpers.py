@@ -80,3 +80,26 @@ def compare_states(got, want, tol, what="", v0=False):
         worst = max(worst, float(err.max()))
         assert err.max() <= tol, "%s field %s rel err %.3e > %.1e" % (what, k, err.max(), tol)
     return worst
+
+
+def near_tie_inside_step(orc, ocfg, pre, e, a):
+    """True if, inside this policy step of env e, two vehicles end a sub-step within 4 ulp of each other in x.  The
+    oracle (glibc) and the kernels (libdevice) agree on every +, *, / and sqrt bit for bit, but their sin / tan / atan /
+    asin may differ in the last place; a vehicle that steers by 1e-7 rad can therefore end a sub-step one ulp apart on
+    the two sides, and when another vehicle sits exactly there (the snapped grids make x + v dt coincide: 373.5 +
+    17.5 / 15 == 374 + 10 / 15) the NEXT sub-step's front / rear classification sees a tie on one side and an order on
+    the other.  Such a step is reported and its env dropped from the rest of the episode; anything else still fails."""
+    one = {k: np.array(v[e:e + 1], copy=True) for k, v in pre.items()}
+    full = ocfg.substeps
+    try:
+        for k in range(1, full):
+            ocfg.substeps = k
+            s1 = {kk: vv.copy() for kk, vv in one.items()}
+            orc.step(ocfg, s1, a[e:e + 1], n_threads=1)
+            n = int(s1["n_veh"][0])
+            x = np.sort(s1["x"][0][:n])
+            if n > 1 and (np.diff(x) <= 4 * np.spacing(np.abs(x[1:]))).any():
+                return True
+    finally:
+        ocfg.substeps = full
+    return False

@@ -563,3 +563,34 @@ def test_supervisor_core_agrees_with_the_python_restatement_on_fresh_scenes(kind
             a[e, :n_cav] = act           # the env then executes the supervised tuple
         orc.step(ocfg, st, a, n_threads=4)
     assert replaced > 0 or td == 1       # sparse traffic rarely needs the supervisor this early in an episode
+
+
+def test_sub_step_ulp_tie_scene_is_recognised():
+    """tests/golden/ulp_tie_scene.npz: the one scene of 37 M snapped soak env-steps whose shield record differed between the
+    kernels and the oracle (profiles/soak_repro.py 302 1 snap).  Vehicle 4 steers by 4e-7 rad; its x after the first
+    sub-step is one ulp apart on the two sides (cos(h + beta) by glibc vs the angle-sum form with libdevice tan) and
+    vehicle 2 lands exactly there (373.5 + 17.5 / 15 == 374 + 10 / 15), so the second sub-step sees a tie on one side and
+    an order on the other.  The soak reports such steps instead of failing; this pins the detector and the scene."""
+    import oracle as orc
+    from helpers import near_tie_inside_step
+    sys.path.insert(0, os.path.join(ROOT, "profiles"))
+    from soak_cases import CASES
+    import importlib
+    mm = importlib.import_module("marl_mass_b200")
+    d = np.load(os.path.join(ROOT, "tests", "golden", "ulp_tie_scene.npz"))
+    shield, traffic, td, reward, lateral = CASES[1]
+    cfg = dict(mm.DEFAULT_CONFIG, safety_guarantee=shield, lateral_control=lateral, traffic_type=traffic, traffic_density=td,
+               agent_reward=reward, HEADWAY_TIME=0.5, cbf_eta=0.03125, HIGH_SPEED_REWARD=4, HEADWAY_COST=1, MERGING_LANE_COST=8)
+    ocfg = orc.make_config(cfg)
+    pre = {k[4:]: np.array(d[k])[None].copy() for k in d.files if k.startswith("pre_")}
+    a = d["actions"][None].astype(np.int8)
+    assert near_tie_inside_step(orc, ocfg, pre, 0, a) and ocfg.substeps == 3
+    # the oracle's own records are the ones the soak expected
+    st = {k: v.copy() for k, v in pre.items()}
+    want = orc.step(ocfg, st, a, n_threads=1)
+    for k in ("leader", "front_adj", "rear_adj"):
+        assert np.array_equal(np.asarray(want["sh_" + k])[0], d["want_" + k])
+    # and the scene without the coincidence (vehicle 2 a millimetre back) is not flagged
+    pre["x"][0, 2] -= 1e-3
+    pre["rec1_x"][0, 2] -= 1e-3
+    assert not near_tie_inside_step(orc, ocfg, pre, 0, a)
