@@ -145,12 +145,14 @@ int reset_stats(mm_env *env) {
     return 0;
 }
 
-// Envs per chunk of the host paths.  Large batches: ONE WAVE of the step kernel's default build - 3 CTAs of 128 envs per
-// SM, 56 832 envs on a 148-SM B200 - rounded to the 768-env granule every tile size divides.  Measured on the packed
-// path at 2^20 envs (profiles/r2_k_e2e_chunks.txt): 56 832 -> 11.0 ms per step, 65 536 (1.15 waves) 11.4, 75 264 (one wave
-// of the 4-CTA build) 11.8, 113 664 -> 12.8, 150 528 -> 14.0 against 8.7 ms for the un-chunked device-resident step.  A
-// mid-size batch is still cut in 4 chunks (>= 16 Ki envs), one per stream, so that its device-to-host copies overlap the
-// compute of the following chunks instead of trailing a single launch.
+// Envs per chunk of the host paths.  Large batches: HALF A WAVE of the step kernel's default build - 3 CTAs of 128 envs
+// per SM make 56 832 envs a wave on a 148-SM B200 - rounded to the 768-env granule every tile size divides; two chunks
+// on different streams fill the machine, and the copy of the last chunk that trails the compute is half as long.
+// Measured on the packed path at 2^20 envs: mid-round kernels (profiles/r2_k_e2e_chunks.txt) 56 832 -> 11.0 ms per step,
+// 65 536 (1.15 waves) 11.4, 75 264 (one wave of the 4-CTA build) 11.8, 113 664 -> 12.8, 150 528 -> 14.0; final kernels
+// (profiles/r2_final_e2e_chunks.txt) 56 832 -> 8.87, 37 888 -> 8.73, 28 416 -> 8.68, 18 944 -> 9.44 against 7.5 ms for the
+// un-chunked device-resident step.  A mid-size batch is still cut in 4 chunks (>= 16 Ki envs), one per stream, so that
+// its device-to-host copies overlap the compute of the following chunks instead of trailing a single launch.
 int host_chunk_target(int n_envs) {
     static const int forced = [] {
         const char *s = getenv("MM_HOST_CHUNK");
@@ -161,10 +163,10 @@ int host_chunk_target(int n_envs) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int wave = sms * 3 * TILE / 768 * 768;
+    const int half_wave = sms * 3 * TILE / 2 / 768 * 768;
     int t = (n_envs + 3) / 4;     // one chunk per stream
     if (t < 16384) t = 16384;
-    if (t > wave) t = wave;
+    if (t > half_wave) t = half_wave;
     return t;
 }
 
