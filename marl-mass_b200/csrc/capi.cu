@@ -36,6 +36,7 @@ int fail(mm_status code, const char *what, cudaError_t ce = cudaSuccess) {
 
 constexpr int MAX_CHUNKS = 16;
 constexpr int GRAPH_MAX_ENVS = 131072;   // mm_step replays a CUDA graph up to this batch size (above, launch overhead is noise)
+constexpr int MM_SUP_TASKS_PER_ENV = 2;   // predicted collisions per env and step the dmc task list holds (more: evaluated in place)
 constexpr int MAX_HOST_CHUNKS = 64;   // chunks of one mm_step_host_ragged / _packed call
 constexpr int HOST_F64 = 17, HOST_I32 = 11, HOST_ENV = 5;
 
@@ -52,6 +53,8 @@ struct mm_env {
     int8_t *new_actions = nullptr;
     const double *sup_draws = nullptr;
     int32_t *sup_used = nullptr;
+    void *sup_tasks = nullptr;          // dmc pass 2: MM_SUP_TASKS_PER_ENV task records per env (allocated with the first dmc use)
+    int *sup_task_count = nullptr;      // one counter per call (calls start on distinct tiles)
     // mm_step_host_ragged, allocated on first use: first packed row of every env, packed-row staging, per-chunk counts
     int64_t *row_offset = nullptr;
     float *rows_stage = nullptr;
@@ -186,9 +189,12 @@ void enqueue_step(mm_env *env, const int8_t *actions_dev, int auto_reset, int of
         // abstract.py:459-464: new_action = safety_supervisor / safety_layer_dmc (env, action); _simulate(new_action)
         int8_t *na = env->new_actions + (size_t)off * MAXV;
         cudaMemcpyAsync(na, actions_dev + (size_t)off * MAXV, (size_t)count * MAXV, cudaMemcpyDeviceToDevice, stream);
-        launch_supervisor(env->st, off, count, env->cfg.supervisor == MM_SUPERVISOR_PRIORITY ? 0 : 1, env->new_actions,
-                          env->sup_draws, MM_SUPERVISOR_DRAWS, env->cfg.headway_time, env->seed, env->sup_used, stream);
-        env->launches += 1;
+        const bool dmc = env->cfg.supervisor != MM_SUPERVISOR_PRIORITY;
+        launch_supervisor(env->st, off, count, dmc ? 1 : 0, env->new_actions, env->sup_draws, MM_SUPERVISOR_DRAWS,
+                          env->cfg.headway_time, env->seed, env->sup_used,
+                          static_cast<char *>(env->sup_tasks) + (size_t)off * MM_SUP_TASKS_PER_ENV * supervisor_task_bytes(),
+                          env->sup_task_count + off / TILE, count * MM_SUP_TASKS_PER_ENV, stream);
+        env->launches += dmc ? 2 : 1;
         actions_dev = env->new_actions;
     }
     StepParams p = step_params(env, actions_dev, off, count);
@@ -216,6 +222,16 @@ int ensure_supervisor_stack(mm_env *env) {
     size_t stack = 0;
     CUDA_OK(cudaDeviceGetLimit(&stack, cudaLimitStackSize));
     if (stack < 32768) CUDA_OK(cudaDeviceSetLimit(cudaLimitStackSize, 32768));
+    if (!env->sup_tasks) {
+        const size_t E_pad = ((size_t)env->n_envs + TILE - 1) / TILE * TILE;
+        void *p = nullptr;
+        CUDA_OK(cudaMalloc(&p, E_pad * MM_SUP_TASKS_PER_ENV * supervisor_task_bytes()));
+        env->allocs.push_back(p);
+        env->sup_tasks = p;
+        CUDA_OK(cudaMalloc(&p, (E_pad / TILE + 1) * sizeof(int)));
+        env->allocs.push_back(p);
+        env->sup_task_count = static_cast<int *>(p);
+    }
     return 0;
 }
 }  // namespace
@@ -890,8 +906,8 @@ int mm_supervise(mm_env *env, int kind, int8_t *actions_dev, const double *draws
     if (int rc = ensure_supervisor_stack(env)) return rc;
     env->last_stream = (cudaStream_t)stream;
     launch_supervisor(env->st, 0, env->n_envs, kind, actions_dev, draws_dev, MM_SUPERVISOR_DRAWS, env->cfg.headway_time, env->seed,
-                      n_used_dev, stream);
-    env->launches += 1;
+                      n_used_dev, env->sup_tasks, env->sup_task_count, env->n_envs * MM_SUP_TASKS_PER_ENV, stream);
+    env->launches += kind == 1 ? 2 : 1;
     CUDA_OK(cudaGetLastError());
     return 0;
 }

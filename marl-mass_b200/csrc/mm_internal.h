@@ -161,7 +161,9 @@ int launch_discounted_returns(const float *rewards, const uint8_t *dones, const 
 // envs [env_offset, env_offset + env_count); draws null: Philox draws keyed (seed, env, episode, step); n_used_out
 // (nullable) [n_envs]: how many draws each env's supervisor consumed
 void launch_supervisor(const DevState &st, int env_offset, int env_count, int kind, int8_t *actions, const double *draws,
-                       int draws_per_env, double headway_time, uint64_t seed, int32_t *n_used_out, void *stream);
+                       int draws_per_env, double headway_time, uint64_t seed, int32_t *n_used_out, void *tasks,
+                       int *task_count, int task_capacity, void *stream);
+size_t supervisor_task_bytes();
 
 // element (field f, slot i) of env e
 __host__ __device__ inline size_t f64_index(size_t e, int f, int i) {

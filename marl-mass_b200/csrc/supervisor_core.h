@@ -266,6 +266,37 @@ MM_HD_CALL inline double check_safety_room(Veh &c, int action, const Veh *road, 
     return best;
 }
 
+// The device's two-pass mode of the dmc supervisor (supervisor.cu): a predicted collision is RECORDED - the ego, its
+// available actions, and the x-trajectories of its four neighbours, which is all check_safety_room reads of `road` - and
+// evaluated later, one (task, action) pair per lane.  Nothing after the evaluation depends on its result except the
+// ego's entry of the action tuple, so the scan of the scene goes on without it.
+struct DmcTask {
+    int env, cav, n_acts, acts[5], nb[4];
+    double tx[4][NPTS];
+};
+struct DmcTaskSink {
+    DmcTask *tasks;
+    int *count;          // atomically incremented; may run past `capacity` (those collisions are evaluated in place)
+    int capacity, env;
+};
+// check_safety_room on a recorded task: tx[q][t] == road[nb[q]].tx[t]
+MM_HD_CALL inline double check_safety_room_tx(Veh &c, int action, const double (*tx)[NPTS], const int nb[4], int time_steps) {
+    double best = 0;
+    for (int t = 0; t <= time_steps; ++t) {
+        mdp_controller(c, action);
+        double room = c.lane == L_BC1 ? 420.0 - c.x : 100.0;
+        if (action == A_LANE_LEFT || action == A_LANE_RIGHT) {
+            for (int q = 0; q < 4; ++q)
+                if (nb[q] >= 0 && fabs(tx[q][t] - c.tx[t]) <= room) room = fabs(tx[q][t] - c.tx[t]);
+        } else {
+            const int q = lane_main(c.lane) ? 0 : 2;
+            if (nb[q] >= 0 && tx[q][t] - c.tx[t] <= room) room = tx[q][t] - c.tx[t];
+        }
+        if (t == 0 || room < best) best = room;
+    }
+    return best;
+}
+
 // abstract.py:620-635
 MM_HD inline double headway_distance(const Veh *road, int n, int self) {
     const Veh &v = road[self];
@@ -310,7 +341,8 @@ MM_HD_CALL inline void collide_at(Veh *road, int self, const int nb[4], int t) {
 
 // decentralised_dmc.py:70-198.  `road`: working copy (modified); `orig`: the scene; actions[n_cav] in/out.
 MM_HD inline void dmc_supervisor(Veh *road, const Veh *orig, int n, int n_cav, int *actions, const double *draws,
-                                 double headway_time, int *n_used = nullptr) {
+                                 double headway_time, int *n_used = nullptr, DmcTaskSink *sink = nullptr) {
+    (void)sink;
     int order[MAXV];
     priority_order(road, n, n_cav, draws, headway_time, order);
     int k = n_cav;
@@ -334,6 +366,22 @@ MM_HD inline void dmc_supervisor(Veh *road, const Veh *orig, int n, int n_cav, i
             v.x = v.tx[t]; v.y = v.ty[t]; v.heading = v.th[t];
             collide_at(road, i, nb, t);
             if (v.crashed) {
+#if defined(__CUDA_ARCH__)
+                if (sink) {
+                    const int slot = atomicAdd(sink->count, 1);
+                    if (slot < sink->capacity) {
+                        DmcTask &task = sink->tasks[slot];
+                        task.env = sink->env; task.cav = i; task.n_acts = n_acts;
+                        for (int a = 0; a < 5; ++a) task.acts[a] = a < n_acts ? acts[a] : A_IDLE;
+                        for (int q = 0; q < 4; ++q) {
+                            task.nb[q] = nb[q];
+                            if (nb[q] >= 0)
+                                for (int tt = 0; tt < NPTS; ++tt) task.tx[q][tt] = road[nb[q]].tx[tt];
+                        }
+                        break;
+                    }
+                }
+#endif
                 double best_room = 0;
                 int best = 0;
                 for (int a = 0; a < n_acts; ++a) {
