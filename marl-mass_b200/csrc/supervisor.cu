@@ -9,6 +9,7 @@
 // consumption order (teacher forcing; the single-env adapter replays the MT19937 stream and advances it by the count this
 // kernel reports).  `draws` == null: Philox4x32-10 keyed (seed, env, episode, policy step) - the batched mode.
 #include <cuda_runtime.h>
+#include <cstdlib>
 
 #include "mm_internal.h"
 #include "mm_philox.cuh"
@@ -115,6 +116,10 @@ void launch_supervisor(const DevState &st, int env_offset, int env_count, int ki
     if (grid <= 0) return;
     cudaStream_t s = (cudaStream_t)stream;
     mmsup::DmcTask *tk = kind == 1 ? static_cast<mmsup::DmcTask *>(tasks) : nullptr;
+    // test knob: MM_SUP_TASK_CAP=<n> shrinks the task list, so that collisions past the n-th are evaluated in place
+    static const int cap_override = [] { const char *v = getenv("MM_SUP_TASK_CAP"); return v ? atoi(v) : -1; }();
+    if (cap_override >= 0 && cap_override < task_capacity) task_capacity = cap_override;
+    if (task_capacity <= 0) tk = nullptr;
     if (tk) cudaMemsetAsync(task_count, 0, sizeof(int), s);
     supervisor_kernel<<<grid, block, 0, s>>>(st, env_offset, env_count, kind, actions, draws, draws_per_env, headway_time, seed,
                                              n_used_out, tk, task_count, task_capacity);

@@ -39,3 +39,20 @@ def test_device_supervisor_reproduces_the_reference_tuples(name):
         assert np.array_equal(got[~live], g["act"][~live])
     finally:
         env.close()
+
+
+@pytest.mark.parametrize("cap", [0, 7])
+def test_dmc_with_a_short_task_list(cap):
+    """The dmc supervisor defers predicted collisions to a task list (supervisor.cu, two kernels); collisions that do not
+    fit are evaluated in place by the scan.  MM_SUP_TASK_CAP shrinks the list (0: one kernel, everything in place; 7:
+    seven deferred, the rest in place) - the tuples must not change.  The knob is read once per process: subprocess."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    if "MM_SUP_TASK_CAP" in os.environ:
+        pytest.skip("inner run")
+    p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_zz_supervisor_gpu.py"), "-q", "-x", "-m", "gpu",
+                        "-k", "reproduces_the_reference_tuples and dmc"],
+                       env=dict(os.environ, MM_SUP_TASK_CAP=str(cap)), capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0 and "1 passed" in p.stdout, (p.stdout[-1500:], p.stderr[-1500:])
