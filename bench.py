@@ -477,7 +477,7 @@ def main():
     del rag_out
     e2e = {"value": ragged_value, "unit": "agent-steps/s", "h2d_bytes_per_step": E * mm.MAXV,
            "d2h_bytes_per_step": int(rag_rows * mm.NS * 4 + E * (8 + 4 + 1 + mm.MAXV * 4 + 4)), "steps": K2,
-           "api": "mm_step_host_ragged (pinned host buffers, 64Ki-env chunks round-robin on 4 streams; observation rows "
+           "api": "mm_step_host_ragged (pinned host buffers, half-wave chunks (28 416 envs) round-robin on 4 streams; observation rows "
                   "of the live agents only, as the reference returns them: packed on the device, exact-size copies)",
            "host_cores_bound": numa_cores,
            "dense": {"value": dense_value, "d2h_bytes_per_step": E * (mm.MAXV * mm.NS * 4 + 4 + 1 + mm.MAXV * 4 + 4),

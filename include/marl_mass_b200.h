@@ -162,7 +162,7 @@ int mm_step_host(mm_env *env, const int8_t *actions, int auto_reset, float *obs,
 /* mm_step_host with the observations as the reference returns them (obs ndarray [A, n_s] per env,
  * merge_env_v1.py:126-166): only the rows of the agents that exist.  Env e's rows are
  * obs_rows[row_offset[e] * 30 .. (row_offset[e] + n_agents[e]) * 30); offsets are absolute, increasing, and dense inside
- * every 64 Ki-env chunk (chunk c starts at row chunk_first_env * MM_MAXV; row_offset[n_envs] = n_envs * MM_MAXV).
+ * every chunk of the call (half a wave of the step kernel, 28 416 envs on a 148-SM part; chunk c starts at row chunk_first_env * MM_MAXV; row_offset[n_envs] = n_envs * MM_MAXV).
  * obs_rows has room for n_envs * MM_MAXV rows of 30 f32 (pinned memory for full PCIe speed); only the packed rows are
  * transferred: a quarter fewer bytes at hard density.  row_offset [n_envs + 1] int64 host; the other outputs as in
  * mm_step_host (nullable). */
