@@ -594,3 +594,19 @@ def test_sub_step_ulp_tie_scene_is_recognised():
     pre["x"][0, 2] -= 1e-3
     pre["rec1_x"][0, 2] -= 1e-3
     assert not near_tie_inside_step(orc, ocfg, pre, 0, a)
+
+
+def test_zero_numerator_division_identity():
+    """csrc/mm_device.cuh div_nz: for a finite y != 0, x / y with x == +-0 is +-0 with the sign of the product - the value
+    x * y has - so routing zero numerators around CUDA's division (whose slow path every zero quotient enters) cannot
+    change a bit.  Checked here in IEEE double arithmetic on the host, signs of zero included."""
+    rng = np.random.RandomState(5)
+    y = np.concatenate([rng.uniform(-50, 50, 1000), [1e-2, -1e-2, 2.5, -2.5, 1e-300, -1e300]])
+    y = y[y != 0]
+    for zero in (0.0, -0.0):
+        x = np.full_like(y, zero)
+        q, p = x / y, x * y
+        assert np.array_equal(q, p) and np.array_equal(np.signbit(q), np.signbit(p))
+    x = rng.uniform(-5, 5, y.shape)
+    stand_in = np.where(x == 0, 1.0, x)
+    assert np.array_equal(np.where(x == 0, x * y, stand_in / y), x / y)
