@@ -683,6 +683,7 @@ int mm_expand_obs_rows(const mm_packed_host *in, int n_envs, int steer_vel, floa
             double vx[MM_MAXV], vy[MM_MAXV];                      // Vehicle.velocity = speed * [cos, sin](heading)
             for (int j = 0; j < n_veh && j < MM_MAXV; ++j) {
                 const double h = veh[j * MM_VEH_F32 + 2], sp = veh[j * MM_VEH_F32 + 3];
+                if (h == 0.0) { vx[j] = sp; vy[j] = sp * h; continue; }   // most vehicles drive straight: cos = 1, sin = +-0
                 vx[j] = sp * std::cos(h);
                 vy[j] = sp * std::sin(h);
             }
